@@ -1,0 +1,85 @@
+"""Galerkin assembly of the ODE model and its closures (test oracle only).
+
+Follows /root/reference/src/ODEModels.jl:22-61:
+  B_ij  = <Psi_i, Psi_j>                                   (:32)
+  A1_ij = -<Psi_i, y d/dx Psi_j> - <Psi_i, [v_j,0,0]>      (:33-36)
+  A2_ij = <Psi_i, laplacian Psi_j>                         (:35)
+  N_ijk = -<Psi_i, (Psi_j . grad) Psi_k>, kept iff |val| > 1e-15   (:39-49)
+  f(x,R)  = B \\ (A1 x + (1/R) A2 x + N(x))                 (:57)
+  Df(x,R) = B \\ (A1 + (1/R) A2 + derivative(N,x))          (:58)
+"""
+from __future__ import annotations
+
+from fractions import Fraction
+
+import numpy as np
+
+from .algebra import (Poly, bf_dotgrad, bf_innerproduct, bf_innerproduct_terms, bf_laplacian,
+                      bf_polymul, bf_vex, bf_xderivative)
+from .basis import basisIndices, basisSet
+from .bilinear import SparseBilinear
+
+N_THRESHOLD = 1e-15  # ODEModels.jl:46 (absolute)
+
+
+def assemble_linear(Psi):
+    """B, A1, A2 as m x m nested lists in the number type of Psi."""
+    m = len(Psi)
+    T = type(Psi[0][0].coeff)
+    y = Poly([T(0), T(1)])
+    B = [[bf_innerproduct(Psi[i], Psi[j]) for j in range(m)] for i in range(m)]
+    yPx = [bf_polymul(y, bf_xderivative(Psi[j])) for j in range(m)]
+    vex = [bf_vex(Psi[j]) for j in range(m)]
+    lap = [bf_laplacian(Psi[j]) for j in range(m)]
+    A1a = [[-bf_innerproduct(Psi[i], yPx[j]) for j in range(m)] for i in range(m)]
+    A1b = [[-bf_innerproduct(Psi[i], vex[j]) for j in range(m)] for i in range(m)]
+    A2 = [[bf_innerproduct(Psi[i], lap[j]) for j in range(m)] for i in range(m)]
+    A1 = [[A1a[i][j] + A1b[i][j] for j in range(m)] for i in range(m)]
+    return B, A1, A2
+
+
+def assemble_N_dense(Psi, threshold=N_THRESHOLD):
+    """Dense m x m x m object/float array with the reference's absolute threshold."""
+    m = len(Psi)
+    T = type(Psi[0][0].coeff)
+    dt = np.float64 if T is float else object
+    Nd = np.zeros((m, m, m), dtype=dt)
+    if dt is object:
+        Nd[...] = Fraction(0)
+    for j in range(m):
+        for k in range(m):
+            g = bf_dotgrad(Psi[j], Psi[k])
+            for i in range(m):
+                val = -bf_innerproduct_terms(Psi[i], g)
+                if abs(val) > threshold:
+                    Nd[i, j, k] = val
+    return Nd
+
+
+class ODEModel:
+    """Restatement of the reference struct (fields alpha, gamma, H, ijkl, Psi, B, A1, A2, N)."""
+
+    def __init__(self, alpha, gamma, J, K, L, H, normalize=False, ijkl=None):
+        self.alpha, self.gamma, self.H = alpha, gamma, list(H) if H is not None else None
+        self.ijkl = basisIndices(J, K, L, self.H) if ijkl is None else np.asarray(ijkl, np.int64)
+        self.Psi = basisSet(alpha, gamma, self.ijkl, normalize=normalize)
+        B, A1, A2 = assemble_linear(self.Psi)
+        self.exact = isinstance(self.Psi[0][0].coeff, Fraction)
+        if self.exact:
+            self.B, self.A1, self.A2 = B, A1, A2
+        else:
+            self.B, self.A1, self.A2 = (np.array(M, dtype=np.float64) for M in (B, A1, A2))
+        self.N = SparseBilinear.from_dense(assemble_N_dense(self.Psi))
+
+    def __len__(self):
+        return len(self.Psi)
+
+    # closures (float models only)
+    def f(self, x, R):
+        x = np.asarray(x, dtype=np.float64)
+        rhs = self.A1 @ x + (1.0 / R) * (self.A2 @ x) + self.N(x)
+        return np.linalg.solve(self.B, rhs)
+
+    def Df(self, x, R):
+        x = np.asarray(x, dtype=np.float64)
+        return np.linalg.solve(self.B, self.A1 + (1.0 / R) * self.A2 + self.N.derivative(x))
