@@ -1,0 +1,266 @@
+// C ABI: SparseBilinear entry points (reference: src/SparseBilinear.jl).
+#include <algorithm>
+#include <memory>
+#include <vector>
+
+#include "bilinear.h"
+#include "bilinear_kernels.cuh"
+
+using namespace ca;
+
+struct ca_bilinear {
+  int device = 0;
+  int64_t m = 0, nnz = 0;
+  std::vector<Term> coo;  // 0-based copy of the caller's COO, reference order
+  DevicePack sym;         // (j,k) ~ (k,j): N(x), JVP
+  std::unique_ptr<DevicePack> ord;      // ordered pairs: N(x,y), built on first use
+  std::unique_ptr<JacobianPack> jac;    // built on first use
+  // staging for the host-pointer entry points
+  cudaStream_t streams[2] = {nullptr, nullptr};
+  DeviceBuffer<double> stage_in[2], stage_out[2], small_x, small_y, small_out, jac_out;
+  ~ca_bilinear() {
+    for (auto& s : streams)
+      if (s) cudaStreamDestroy(s);
+  }
+  void bind() const { CA_CUDA(cudaSetDevice(device)); }
+  void need_streams() {
+    for (auto& s : streams)
+      if (!s) CA_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  }
+  DevicePack& ordered() {
+    if (!ord) {
+      ord.reset(new DevicePack);
+      ord->upload(pack_terms(coo, (int32_t)m, /*symmetric=*/false, kNtMax));
+    }
+    return *ord;
+  }
+  JacobianPack& jacobian() {
+    if (!jac) {
+      jac.reset(new JacobianPack);
+      jac->build(coo, (int32_t)m);
+    }
+    return *jac;
+  }
+};
+
+namespace ca {
+
+// Shared with the model code: evaluates a packed operator for a host ensemble, chunked and
+// double-buffered (H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c when the
+// host buffers are page-locked, see ca_pin).
+void eval_batched_host(const DevicePack& op, cudaStream_t streams[2], DeviceBuffer<double> in[2],
+                       DeviceBuffer<double> out[2], const double* X, int64_t nstates, double* OUT,
+                       int64_t m_in, int64_t m_out) {
+  if (nstates <= 0) return;
+  const int64_t bytes_per_state = (m_in + m_out) * (int64_t)sizeof(double);
+  int64_t chunk = std::max<int64_t>(4096, (256ll << 20) / bytes_per_state);
+  chunk = std::min(chunk, nstates);
+  chunk = (chunk + 31) / 32 * 32;
+  for (int b = 0; b < 2; ++b) {
+    if (in[b].count < (size_t)(chunk * m_in)) in[b].alloc((size_t)(chunk * m_in));
+    if (out[b].count < (size_t)(chunk * m_out)) out[b].alloc((size_t)(chunk * m_out));
+  }
+  int c = 0;
+  for (int64_t s0 = 0; s0 < nstates; s0 += chunk, ++c) {
+    const int b = c & 1;
+    const int64_t n = std::min(chunk, nstates - s0);
+    cudaStream_t st = streams[b];
+    CA_CUDA(cudaMemcpy2DAsync(in[b].ptr, (size_t)n * sizeof(double), X + s0,
+                              (size_t)nstates * sizeof(double), (size_t)n * sizeof(double),
+                              (size_t)m_in, cudaMemcpyHostToDevice, st));
+    launch_batched(op, MODE_QUAD, in[b].ptr, nullptr, n, n, out[b].ptr, n, st);
+    CA_CUDA(cudaMemcpy2DAsync(OUT + s0, (size_t)nstates * sizeof(double), out[b].ptr,
+                              (size_t)n * sizeof(double), (size_t)n * sizeof(double), (size_t)m_out,
+                              cudaMemcpyDeviceToHost, st));
+  }
+  CA_CUDA(cudaStreamSynchronize(streams[0]));
+  CA_CUDA(cudaStreamSynchronize(streams[1]));
+}
+
+}  // namespace ca
+
+extern "C" {
+
+int32_t ca_bilinear_create(const int64_t* ijk, const double* val, int64_t nnz, int64_t m,
+                           ca_bilinear** out) {
+  return guarded([&] {
+    if (!out) fail(CA_ERR_INVALID, "ca_bilinear_create: out is null");
+    *out = nullptr;
+    if (m <= 0) fail(CA_ERR_INVALID, "ca_bilinear_create: m must be positive");
+    if (nnz < 0 || (nnz > 0 && (!ijk || !val)))
+      fail(CA_ERR_INVALID, "ijk and val must have same number of rows");
+    std::unique_ptr<ca_bilinear> h(new ca_bilinear);
+    h->m = m;
+    h->nnz = nnz;
+    h->coo.resize((size_t)nnz);
+    for (int64_t r = 0; r < nnz; ++r) {
+      const int64_t i = ijk[r], j = ijk[r + nnz], k = ijk[r + 2 * nnz];
+      if (i < 1 || i > m || j < 1 || j > m || k < 1 || k > m)
+        fail(CA_ERR_INVALID, "ca_bilinear_create: entry %lld has index (%lld,%lld,%lld) outside 1:%lld",
+             (long long)r + 1, (long long)i, (long long)j, (long long)k, (long long)m);
+      h->coo[(size_t)r] = Term{(int32_t)(i - 1), (int32_t)(j - 1), (int32_t)(k - 1), val[r]};
+    }
+    require_device();
+    CA_CUDA(cudaGetDevice(&h->device));
+    h->sym.upload(pack_terms(h->coo, (int32_t)m, /*symmetric=*/true, kNtMax));
+    *out = h.release();
+  });
+}
+
+int32_t ca_bilinear_destroy(ca_bilinear* h) {
+  return guarded([&] {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    delete h;
+  });
+}
+
+int32_t ca_bilinear_info(const ca_bilinear* h, int64_t* m, int64_t* nnz, int64_t* nnz_sym,
+                         int64_t* npairs, int64_t* padded_fma_per_state) {
+  return guarded([&] {
+    if (!h) fail(CA_ERR_INVALID, "null handle");
+    if (m) *m = h->m;
+    if (nnz) *nnz = h->nnz;
+    if (nnz_sym) *nnz_sym = h->sym.nterms;
+    if (npairs) *npairs = h->sym.npairs_distinct;
+    if (padded_fma_per_state) *padded_fma_per_state = h->sym.padded_fma;
+  });
+}
+
+int32_t ca_bilinear_eval(ca_bilinear* h, const double* x, const double* y, double* out) {
+  return guarded([&] {
+    if (!h || !x || !out) fail(CA_ERR_INVALID, "ca_bilinear_eval: null argument");
+    h->bind();
+    const size_t m = (size_t)h->m;
+    h->small_x.upload(x, m);
+    if (y && y != x) h->small_y.upload(y, m);
+    if (h->small_out.count < m) h->small_out.alloc(m);
+    if (y && y != x)
+      launch_batched(h->ordered(), MODE_ORDERED, h->small_x.ptr, h->small_y.ptr, 1, 1, h->small_out.ptr, 1, nullptr);
+    else
+      launch_batched(h->sym, MODE_QUAD, h->small_x.ptr, nullptr, 1, 1, h->small_out.ptr, 1, nullptr);
+    CA_CUDA(cudaMemcpy(out, h->small_out.ptr, m * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+int32_t ca_bilinear_eval_batched(ca_bilinear* h, const double* X, int64_t nstates, double* OUT) {
+  return guarded([&] {
+    if (!h || (nstates > 0 && (!X || !OUT))) fail(CA_ERR_INVALID, "ca_bilinear_eval_batched: null argument");
+    if (nstates < 0) fail(CA_ERR_INVALID, "nstates must be non-negative");
+    h->bind();
+    h->need_streams();
+    eval_batched_host(h->sym, h->streams, h->stage_in, h->stage_out, X, nstates, OUT, h->m, h->m);
+  });
+}
+
+int32_t ca_bilinear_eval_batched_dev(ca_bilinear* h, const double* dX, int64_t nstates, int64_t ldx,
+                                     double* dOUT, int64_t ldo, void* stream) {
+  return guarded([&] {
+    if (!h || (nstates > 0 && (!dX || !dOUT))) fail(CA_ERR_INVALID, "null argument");
+    h->bind();
+    launch_batched(h->sym, MODE_QUAD, dX, nullptr, nstates, ldx, dOUT, ldo, (cudaStream_t)stream);
+  });
+}
+
+int32_t ca_bilinear_eval2_batched_dev(ca_bilinear* h, const double* dX, const double* dY,
+                                      int64_t nstates, int64_t ld, double* dOUT, int64_t ldo,
+                                      void* stream) {
+  return guarded([&] {
+    if (!h || (nstates > 0 && (!dX || !dY || !dOUT))) fail(CA_ERR_INVALID, "null argument");
+    h->bind();
+    launch_batched(h->ordered(), MODE_ORDERED, dX, dY, nstates, ld, dOUT, ldo, (cudaStream_t)stream);
+  });
+}
+
+int32_t ca_bilinear_jvp_batched_dev(ca_bilinear* h, const double* dX, const double* dV,
+                                    int64_t nstates, int64_t ld, double* dOUT, int64_t ldo,
+                                    void* stream) {
+  return guarded([&] {
+    if (!h || (nstates > 0 && (!dX || !dV || !dOUT))) fail(CA_ERR_INVALID, "null argument");
+    h->bind();
+    launch_batched(h->sym, MODE_JVP, dX, dV, nstates, ld, dOUT, ldo, (cudaStream_t)stream);
+  });
+}
+
+int32_t ca_bilinear_jacobian_dev(ca_bilinear* h, const double* dx, double* dDN, void* stream) {
+  return guarded([&] {
+    if (!h || !dx || !dDN) fail(CA_ERR_INVALID, "null argument");
+    h->bind();
+    launch_jacobian(h->jacobian(), dx, dDN, (cudaStream_t)stream);
+  });
+}
+
+int32_t ca_bilinear_jacobian(ca_bilinear* h, const double* x, double* DN) {
+  return guarded([&] {
+    if (!h || !x || !DN) fail(CA_ERR_INVALID, "null argument");
+    h->bind();
+    const size_t m = (size_t)h->m;
+    h->small_x.upload(x, m);
+    if (h->jac_out.count < m * m) h->jac_out.alloc(m * m);
+    launch_jacobian(h->jacobian(), h->small_x.ptr, h->jac_out.ptr, nullptr);
+    CA_CUDA(cudaMemcpy(DN, h->jac_out.ptr, m * m * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+}  // extern "C"
+
+extern "C" int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64_t nnz, int64_t m,
+                                    int32_t symmetric, int64_t* ntiles, int64_t* nterms,
+                                    int64_t* padded_fma, int64_t* pair_products, int64_t* mismatches) {
+  return guarded([&] {
+    std::vector<Term> coo((size_t)nnz);
+    for (int64_t r = 0; r < nnz; ++r)
+      coo[(size_t)r] = Term{(int32_t)(ijk[r] - 1), (int32_t)(ijk[r + nnz] - 1), (int32_t)(ijk[r + 2 * nnz] - 1), val[r]};
+    PackedHost P = pack_terms(coo, (int32_t)m, symmetric != 0, kNtMax);
+    // expected: merged terms
+    struct K { int32_t i, a, b; double v; };
+    auto less = [](const K& x, const K& y) {
+      if (x.i != y.i) return x.i < y.i;
+      if (x.a != y.a) return x.a < y.a;
+      return x.b < y.b;
+    };
+    std::vector<K> want;
+    for (auto t : coo) {
+      if (symmetric && t.a > t.b) std::swap(t.a, t.b);
+      want.push_back({t.i, t.a, t.b, t.v});
+    }
+    std::sort(want.begin(), want.end(), less);
+    std::vector<K> wm;
+    for (size_t r = 0; r < want.size();) {
+      size_t e = r;
+      double s = 0;
+      while (e < want.size() && !less(want[r], want[e]) && !less(want[e], want[r])) s += want[e++].v;
+      if (s != 0.0) wm.push_back({want[r].i, want[r].a, want[r].b, s});
+      r = e;
+    }
+    std::vector<K> got;
+    std::vector<char> row_seen((size_t)m, 0);
+    int64_t bad = 0;
+    for (const TileDesc& T : P.tiles) {
+      for (int n = 0; n < 8 * T.nt; ++n) {
+        const int32_t row = P.rows[(size_t)T.rows_off + n];
+        if (row < 0) continue;
+        if (row_seen[(size_t)row]) ++bad;  // every output row is owned by exactly one tile
+        row_seen[(size_t)row] = 1;
+        for (int k = 0; k < 4 * T.nks; ++k) {
+          const uint32_t pr = P.pairs[(size_t)T.ks_begin * 4 + k];
+          const double v = P.vals[(size_t)T.vals_off + ((size_t)(k / 4) * T.nt + n / 8) * 32 + (n % 8) * 4 + k % 4];
+          if (v != 0.0) got.push_back({row, (int32_t)(pr & 0xffff), (int32_t)(pr >> 16), v});
+        }
+      }
+    }
+    for (int64_t r = 0; r < m; ++r) bad += !row_seen[(size_t)r];
+    std::sort(got.begin(), got.end(), less);
+    if (got.size() != wm.size()) bad += (int64_t)std::max(got.size(), wm.size()) - (int64_t)std::min(got.size(), wm.size());
+    for (size_t r = 0, shown = 0; r < std::min(got.size(), wm.size()); ++r)
+      if (getenv("CA_DEBUG_PACK") && shown < 10 && (got[r].i != wm[r].i || got[r].a != wm[r].a || got[r].b != wm[r].b || got[r].v != wm[r].v)) { ++shown;
+        fprintf(stderr, "r=%zu got (%d,%d,%d,%g) want (%d,%d,%d,%g) sizes %zu %zu\n", r, got[r].i, got[r].a, got[r].b, got[r].v, wm[r].i, wm[r].a, wm[r].b, wm[r].v, got.size(), wm.size()); }
+    for (size_t r = 0; r < std::min(got.size(), wm.size()); ++r)
+      bad += got[r].i != wm[r].i || got[r].a != wm[r].a || got[r].b != wm[r].b || got[r].v != wm[r].v;
+    if (ntiles) *ntiles = (int64_t)P.tiles.size();
+    if (nterms) *nterms = P.nterms;
+    if (padded_fma) *padded_fma = P.padded_fma;
+    if (pair_products) *pair_products = P.pair_products;
+    if (mismatches) *mismatches = bad;
+  });
+}

@@ -1,0 +1,214 @@
+#include "bilinear.h"
+
+#include <algorithm>
+#include <numeric>
+
+#include "bilinear_kernels.cuh"
+
+namespace ca {
+
+void DevicePack::upload(const PackedHost& P) {
+  m = P.m;
+  nin = P.nin;
+  ntiles = (int32_t)P.tiles.size();
+  symmetric = P.symmetric;
+  nterms = P.nterms;
+  npairs_distinct = P.npairs_distinct;
+  padded_fma = P.padded_fma;
+  pair_products = P.pair_products;
+  tiles.upload(P.tiles.data(), P.tiles.size());
+  pairs.upload(P.pairs.data(), P.pairs.size());
+  vals.upload(P.vals.data(), P.vals.size());
+  rows.upload(P.rows.data(), P.rows.size());
+  CA_CUDA(cudaStreamSynchronize(nullptr));  // the host vectors may die after we return
+}
+
+namespace {
+
+struct LaunchCfg {
+  int sms = 0;
+  size_t smem_optin = 0;
+};
+
+const LaunchCfg& device_cfg() {
+  static thread_local int cached_dev = -1;
+  static thread_local LaunchCfg cfg;
+  int dev = 0;
+  CA_CUDA(cudaGetDevice(&dev));
+  if (dev != cached_dev) {
+    int v = 0;
+    CA_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    cfg.sms = v;
+    CA_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cfg.smem_optin = (size_t)v;
+    cached_dev = dev;
+  }
+  return cfg;
+}
+
+template <int MT, int MODE>
+void launch_one(const DevicePack& op, const double* dX, const double* dY, int64_t nstates, int64_t ldx,
+                double* dOUT, int64_t ldo, cudaStream_t stream) {
+  auto kern = bilinear_batched_kernel<MT, MODE>;
+  const size_t smem = batched_smem_bytes<MT, MODE>(op.nin);
+  CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  if (per_sm < 1) fail(CA_ERR_UNSUPPORTED, "batched kernel does not fit (smem %zu B)", smem);
+  const int64_t nblocks = (nstates + 8 * MT - 1) / (8 * MT);
+  const int grid = (int)std::min<int64_t>(nblocks, (int64_t)device_cfg().sms * per_sm);
+  kern<<<grid, kThreads, smem, stream>>>(op.tiles.ptr, op.ntiles, op.pairs.ptr, op.vals.ptr,
+                                         op.rows.ptr, op.nin, dX, dY, nstates, ldx, dOUT, ldo);
+  CA_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+template <int MODE>
+void launch_mode(const DevicePack& op, const double* dX, const double* dY, int64_t nstates,
+                 int64_t ldx, double* dOUT, int64_t ldo, cudaStream_t stream) {
+  const size_t cap = device_cfg().smem_optin;
+  // widest state tile that fits; narrow tiles for tiny ensembles
+  int mt = 4;
+  if (nstates <= 8) mt = 1;
+  else if (nstates <= 16) mt = 2;
+  while (mt > 1 && (mt == 4 ? batched_smem_bytes<4, MODE>(op.nin) : batched_smem_bytes<2, MODE>(op.nin)) > cap)
+    mt /= 2;
+  if (mt == 1 && batched_smem_bytes<1, MODE>(op.nin) > cap)
+    fail(CA_ERR_UNSUPPORTED, "state tile for m = %d does not fit in shared memory", op.m);
+  if (mt == 4) launch_one<4, MODE>(op, dX, dY, nstates, ldx, dOUT, ldo, stream);
+  else if (mt == 2) launch_one<2, MODE>(op, dX, dY, nstates, ldx, dOUT, ldo, stream);
+  else launch_one<1, MODE>(op, dX, dY, nstates, ldx, dOUT, ldo, stream);
+}
+
+}  // namespace
+
+void launch_batched(const DevicePack& op, int mode, const double* dX, const double* dY,
+                    int64_t nstates, int64_t ldx, double* dOUT, int64_t ldo, cudaStream_t stream) {
+  if (nstates <= 0) return;
+  if (ldx < nstates || ldo < nstates) fail(CA_ERR_INVALID, "leading dimension smaller than nstates");
+  if (mode != MODE_QUAD && !dY) fail(CA_ERR_INVALID, "second ensemble missing");
+  if (mode != MODE_ORDERED && !op.symmetric) fail(CA_ERR_INVALID, "quadratic/JVP evaluation needs the symmetric pack");
+  switch (mode) {
+    case MODE_QUAD: launch_mode<MODE_QUAD>(op, dX, dY, nstates, ldx, dOUT, ldo, stream); break;
+    case MODE_ORDERED: launch_mode<MODE_ORDERED>(op, dX, dY, nstates, ldx, dOUT, ldo, stream); break;
+    case MODE_JVP: launch_mode<MODE_JVP>(op, dX, dY, nstates, ldx, dOUT, ldo, stream); break;
+    default: fail(CA_ERR_INVALID, "unknown evaluation mode %d", mode);
+  }
+}
+
+// ----------------------------------------------------------------------------------- Jacobian
+// One thread per structurally non-zero Jacobian entry; entries of a 32-wide slice are stored
+// column-major so a warp reads 32 consecutive (src,val) per step.  Slices are formed after sorting
+// outputs by contribution count inside windows of 4096 outputs, which keeps padding small while
+// neighbouring threads still write neighbouring addresses.
+__global__ void __launch_bounds__(256)
+jacobian_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restrict__ out_pos,
+                const uint16_t* __restrict__ src, const double* __restrict__ val, int64_t nslices,
+                int m, const double* __restrict__ x, double* __restrict__ DN) {
+  extern __shared__ double xs[];
+  for (int j = threadIdx.x; j < m; j += blockDim.x) xs[j] = x[j];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t sl = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); sl < nslices;
+       sl += warps_total) {
+    const int64_t b = slice_off[sl], e = slice_off[sl + 1];
+    double acc0 = 0.0, acc1 = 0.0;
+    int64_t p = b + lane;
+    for (; p + 32 < e; p += 64) {
+      acc0 = fma(val[p], xs[src[p]], acc0);
+      acc1 = fma(val[p + 32], xs[src[p + 32]], acc1);
+    }
+    if (p < e) acc0 = fma(val[p], xs[src[p]], acc0);
+    const int32_t o = out_pos[sl * 32 + lane];
+    if (o >= 0) DN[o] = acc0 + acc1;
+  }
+}
+
+void JacobianPack::build(const std::vector<Term>& coo, int32_t m_) {
+  m = m_;
+  struct E { int64_t out; int32_t src; double v; };
+  std::vector<E> es;
+  es.reserve(coo.size() * 2);
+  for (const Term& t : coo) {
+    es.push_back({(int64_t)t.i + (int64_t)m * t.a, t.b, t.v});  // DN[i,j] += v * x[k]
+    es.push_back({(int64_t)t.i + (int64_t)m * t.b, t.a, t.v});  // DN[i,k] += v * x[j]
+  }
+  std::sort(es.begin(), es.end(), [](const E& a, const E& b) {
+    return a.out != b.out ? a.out < b.out : a.src < b.src;
+  });
+  // merge duplicates
+  std::vector<E> mg;
+  mg.reserve(es.size());
+  for (size_t r = 0; r < es.size();) {
+    size_t e = r;
+    double s = 0;
+    while (e < es.size() && es[e].out == es[r].out && es[e].src == es[r].src) s += es[e++].v;
+    mg.push_back({es[r].out, es[r].src, s});
+    r = e;
+  }
+  nentries = (int64_t)mg.size();
+  // outputs and their ranges
+  std::vector<int64_t> ostart;
+  std::vector<int64_t> opos;
+  for (size_t r = 0; r < mg.size();) {
+    size_t e = r;
+    while (e < mg.size() && mg[e].out == mg[r].out) ++e;
+    ostart.push_back((int64_t)r);
+    opos.push_back(mg[r].out);
+    r = e;
+  }
+  ostart.push_back((int64_t)mg.size());
+  nout = (int64_t)opos.size();
+  std::vector<int64_t> ord(nout);
+  std::iota(ord.begin(), ord.end(), 0);
+  constexpr int64_t kWindow = 4096;
+  for (int64_t w = 0; w < nout; w += kWindow) {
+    auto b = ord.begin() + w, e = ord.begin() + std::min(nout, w + kWindow);
+    std::stable_sort(b, e, [&](int64_t x, int64_t y) {
+      return ostart[x + 1] - ostart[x] > ostart[y + 1] - ostart[y];
+    });
+  }
+  nslices = (nout + 31) / 32;
+  std::vector<int64_t> soff(nslices + 1, 0);
+  std::vector<int32_t> pos((size_t)nslices * 32, -1);
+  for (int64_t s = 0; s < nslices; ++s) {
+    int64_t len = 0;
+    for (int l = 0; l < 32 && s * 32 + l < nout; ++l) {
+      const int64_t o = ord[s * 32 + l];
+      len = std::max(len, ostart[o + 1] - ostart[o]);
+      pos[s * 32 + l] = (int32_t)opos[o];
+    }
+    soff[s + 1] = soff[s] + len * 32;
+  }
+  std::vector<uint16_t> hsrc((size_t)soff[nslices], 0);
+  std::vector<double> hval((size_t)soff[nslices], 0.0);
+  for (int64_t s = 0; s < nslices; ++s)
+    for (int l = 0; l < 32 && s * 32 + l < nout; ++l) {
+      const int64_t o = ord[s * 32 + l];
+      for (int64_t r = ostart[o]; r < ostart[o + 1]; ++r) {
+        const size_t at = (size_t)soff[s] + (size_t)(r - ostart[o]) * 32 + l;
+        hsrc[at] = (uint16_t)mg[r].src;
+        hval[at] = mg[r].v;
+      }
+    }
+  slice_off.upload(soff.data(), soff.size());
+  out_pos.upload(pos.data(), pos.size());
+  src.upload(hsrc.data(), hsrc.size());
+  val.upload(hval.data(), hval.size());
+  CA_CUDA(cudaStreamSynchronize(nullptr));
+}
+
+void launch_jacobian(const JacobianPack& J, const double* dx, double* dDN, cudaStream_t stream) {
+  CA_CUDA(cudaMemsetAsync(dDN, 0, (size_t)J.m * J.m * sizeof(double), stream));
+  if (J.nslices == 0) return;
+  const int warps_per_block = 8;
+  const int64_t want = (J.nslices + warps_per_block - 1) / warps_per_block;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)device_cfg().sms * 8);
+  jacobian_kernel<<<grid, 256, (size_t)J.m * sizeof(double), stream>>>(
+      J.slice_off.ptr, J.out_pos.ptr, J.src.ptr, J.val.ptr, J.nslices, J.m, dx, dDN);
+  CA_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+}  // namespace ca

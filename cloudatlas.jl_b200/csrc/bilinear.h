@@ -1,0 +1,43 @@
+// Device-resident packed operators and their launchers.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "common.h"
+#include "pack.h"
+
+namespace ca {
+
+// A PackedHost uploaded to the current device.
+struct DevicePack {
+  int32_t m = 0, nin = 0, ntiles = 0;
+  bool symmetric = false;
+  int64_t nterms = 0, npairs_distinct = 0, padded_fma = 0, pair_products = 0;
+  DeviceBuffer<TileDesc> tiles;
+  DeviceBuffer<uint32_t> pairs;
+  DeviceBuffer<double> vals;
+  DeviceBuffer<int32_t> rows;
+  void upload(const PackedHost& P);
+};
+
+// mode: MODE_QUAD (Y ignored), MODE_ORDERED (u = X, w = Y), MODE_JVP (X = state, Y = direction).
+void launch_batched(const DevicePack& op, int mode, const double* dX, const double* dY,
+                    int64_t nstates, int64_t ldx, double* dOUT, int64_t ldo, cudaStream_t stream);
+
+// Sliced-ELL structure of the Jacobian  DN[i,j] = sum_k M[(i,j),k] x_k  (SparseBilinear.jl:75-91).
+struct JacobianPack {
+  int32_t m = 0;
+  int64_t nout = 0;      // structurally non-zero Jacobian entries
+  int64_t nentries = 0;  // merged (out, src) contributions
+  int64_t nslices = 0;
+  DeviceBuffer<int64_t> slice_off;  // [nslices+1] offsets (in entries) of each 32-wide slice
+  DeviceBuffer<int32_t> out_pos;    // [nslices*32] linear index i + m*j of each lane's output (-1 pad)
+  DeviceBuffer<uint16_t> src;       // [entries] column-major inside a slice
+  DeviceBuffer<double> val;
+  void build(const std::vector<Term>& coo, int32_t m);
+};
+
+// DN = A_lin + derivative: dDN must hold m*m doubles; it is overwritten.
+void launch_jacobian(const JacobianPack& J, const double* dx, double* dDN, cudaStream_t stream);
+
+}  // namespace ca

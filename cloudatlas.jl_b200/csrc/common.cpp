@@ -1,0 +1,82 @@
+#include "common.h"
+
+#include <cstring>
+
+namespace ca {
+
+static thread_local std::string t_last_error;
+std::atomic<int64_t> g_launches{0};
+
+void set_last_error(const std::string& msg) { t_last_error = msg; }
+
+void fail(int32_t code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw Error(code, buf);
+}
+
+void require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    fail(CA_ERR_NODEVICE, "no CUDA device available (%s); libcloudatlas_b200 has no CPU fallback",
+         e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  int dev = 0;
+  CA_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  CA_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10)
+    fail(CA_ERR_NODEVICE, "device %d has compute capability %d.x; this library is built for sm_100a only",
+         dev, major);
+}
+
+}  // namespace ca
+
+extern "C" {
+
+const char* ca_last_error(void) { return ca::t_last_error.c_str(); }
+
+int32_t ca_version(void) { return 100; }
+
+int64_t ca_launch_count(void) { return ca::g_launches.load(); }
+
+int32_t ca_device_info(int32_t* ndevices, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,
+                       char* name, int32_t name_len) {
+  return ca::guarded([&] {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) n = 0;
+    if (ndevices) *ndevices = n;
+    if (n == 0) ca::fail(CA_ERR_NODEVICE, "no CUDA device available");
+    int dev = 0;
+    CA_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    CA_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (name && name_len > 0) {
+      strncpy(name, p.name, name_len - 1);
+      name[name_len - 1] = 0;
+    }
+  });
+}
+
+int32_t ca_pin(void* host_ptr, int64_t bytes) {
+  return ca::guarded([&] {
+    if (!host_ptr || bytes <= 0) ca::fail(CA_ERR_INVALID, "ca_pin: null pointer or non-positive size");
+    CA_CUDA(cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterDefault));
+  });
+}
+
+int32_t ca_unpin(void* host_ptr) {
+  return ca::guarded([&] {
+    if (!host_ptr) ca::fail(CA_ERR_INVALID, "ca_unpin: null pointer");
+    CA_CUDA(cudaHostUnregister(host_ptr));
+  });
+}
+
+}  // extern "C"

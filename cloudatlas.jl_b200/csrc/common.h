@@ -1,0 +1,81 @@
+// Shared helpers for libcloudatlas_b200: status codes, thread-local error text, CUDA checks.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/cloudatlas_b200.h"
+
+namespace ca {
+
+struct Error : std::runtime_error {
+  int32_t code;
+  Error(int32_t c, const std::string& msg) : std::runtime_error(msg), code(c) {}
+};
+
+void set_last_error(const std::string& msg);
+[[noreturn]] void fail(int32_t code, const char* fmt, ...);
+
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define CA_CUDA(expr)                                                                     \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      ::ca::fail(CA_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,        \
+                 cudaGetErrorString(e__));                                                \
+  } while (0)
+
+// Wraps the body of an extern "C" entry point: exceptions become status codes.
+template <typename F>
+int32_t guarded(F&& body) {
+  try {
+    body();
+    return CA_OK;
+  } catch (const Error& e) {
+    set_last_error(e.what());
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    set_last_error("host allocation failed");
+    return CA_ERR_NOMEM;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return CA_ERR_INVALID;
+  }
+}
+
+// Requires a CUDA device of compute capability 10.x; the library has no other code path.
+void require_device();
+
+template <typename T>
+struct DeviceBuffer {
+  T* ptr = nullptr;
+  size_t count = 0;
+  DeviceBuffer() = default;
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+  ~DeviceBuffer() { release(); }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+  }
+  void alloc(size_t n) {
+    release();
+    if (n == 0) return;
+    CA_CUDA(cudaMalloc(&ptr, n * sizeof(T)));
+    count = n;
+  }
+  void upload(const T* host, size_t n, cudaStream_t s = nullptr) {
+    if (n > count) alloc(n);
+    if (n) CA_CUDA(cudaMemcpyAsync(ptr, host, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+};
+
+}  // namespace ca

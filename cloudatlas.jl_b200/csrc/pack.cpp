@@ -1,0 +1,210 @@
+#include "pack.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <unordered_set>
+
+#include "common.h"
+
+namespace ca {
+
+namespace {
+
+constexpr int kSketch = 8;
+
+inline uint64_t mix64(uint64_t x) {
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+
+struct Row {
+  std::vector<uint64_t> keys;  // sorted pair ids a*nin+b
+  std::vector<double> vals;
+  uint64_t sketch[kSketch];
+};
+
+size_t union_size(const std::vector<uint64_t>& a, const std::vector<uint64_t>& b) {
+  size_t i = 0, j = 0, n = 0;
+  while (i < a.size() && j < b.size()) {
+    if (a[i] == b[j]) { ++i; ++j; }
+    else if (a[i] < b[j]) ++i;
+    else ++j;
+    ++n;
+  }
+  return n + (a.size() - i) + (b.size() - j);
+}
+
+std::vector<uint64_t> union_of(const std::vector<uint64_t>& a, const std::vector<uint64_t>& b) {
+  std::vector<uint64_t> out;
+  out.reserve(a.size() + b.size());
+  std::set_union(a.begin(), a.end(), b.begin(), b.end(), std::back_inserter(out));
+  return out;
+}
+
+}  // namespace
+
+PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt_max) {
+  if (m <= 0) fail(CA_ERR_INVALID, "pack_terms: m must be positive");
+  const int32_t nin = m + 1;
+  if (nin > 65536) fail(CA_ERR_UNSUPPORTED, "pack_terms: m = %d exceeds the 16-bit mode index", m);
+  if (nt_max < 1) nt_max = 1;
+  PackedHost P;
+  P.m = m;
+  P.nin = nin;
+  P.symmetric = symmetric;
+
+  for (auto& t : terms) {
+    if (t.i < 0 || t.i >= m || t.a < 0 || t.a >= nin || t.b < 0 || t.b >= nin)
+      fail(CA_ERR_INVALID, "pack_terms: index out of range (i=%d a=%d b=%d, m=%d)", t.i, t.a, t.b, m);
+    if (symmetric && t.a > t.b) std::swap(t.a, t.b);
+  }
+  std::sort(terms.begin(), terms.end(), [](const Term& x, const Term& y) {
+    if (x.i != y.i) return x.i < y.i;
+    if (x.a != y.a) return x.a < y.a;
+    return x.b < y.b;
+  });
+
+  std::vector<Row> rows(m);
+  {
+    size_t r = 0;
+    while (r < terms.size()) {
+      size_t e = r;
+      double s = 0;
+      while (e < terms.size() && terms[e].i == terms[r].i && terms[e].a == terms[r].a &&
+             terms[e].b == terms[r].b)
+        s += terms[e++].v;
+      if (s != 0.0) {
+        rows[terms[r].i].keys.push_back((uint64_t)terms[r].a * nin + terms[r].b);
+        rows[terms[r].i].vals.push_back(s);
+        ++P.nterms;
+      }
+      r = e;
+    }
+  }
+  {
+    std::unordered_set<uint64_t> all;
+    for (auto& rw : rows) all.insert(rw.keys.begin(), rw.keys.end());
+    P.npairs_distinct = (int64_t)all.size();
+  }
+  for (auto& rw : rows) {
+    for (int h = 0; h < kSketch; ++h) {
+      uint64_t best = ~0ull;
+      for (uint64_t k : rw.keys) best = std::min(best, mix64(k * 0x100000001b3ull + h * 0x51ed27ull));
+      rw.sketch[h] = best;
+    }
+  }
+
+  // ---- cluster rows with near-identical pair sets
+  std::vector<int32_t> order(m);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+    return rows[x].keys.size() > rows[y].keys.size();
+  });
+  std::vector<char> assigned(m, 0);
+  std::vector<std::vector<int32_t>> clusters;
+  std::vector<int32_t> empties;
+  for (int32_t seed : order) {
+    if (assigned[seed]) continue;
+    assigned[seed] = 1;
+    if (rows[seed].keys.empty()) {
+      empties.push_back(seed);
+      continue;
+    }
+    std::vector<int32_t> cl{seed};
+    std::vector<uint64_t> U = rows[seed].keys;
+    std::vector<std::pair<int, int32_t>> cand;
+    for (int32_t r = 0; r < m; ++r) {
+      if (assigned[r] || rows[r].keys.empty()) continue;
+      int agree = 0;
+      for (int h = 0; h < kSketch; ++h) agree += rows[r].sketch[h] == rows[seed].sketch[h];
+      if (agree >= kSketch / 2) cand.push_back({-agree, r});
+    }
+    std::sort(cand.begin(), cand.end());
+    for (auto& c : cand) {
+      const auto& k = rows[c.second].keys;
+      size_t u = union_size(U, k);
+      if ((double)u <= 1.2 * (double)std::max(U.size(), k.size())) {
+        U = union_of(U, k);
+        cl.push_back(c.second);
+        assigned[c.second] = 1;
+      }
+    }
+    std::sort(cl.begin(), cl.end());
+    clusters.push_back(std::move(cl));
+  }
+
+  // ---- split clusters into tiles of <= 8*nt_max rows, lay out fragments
+  auto emit_tile = [&](const std::vector<int32_t>& trows) {
+    TileDesc T{};
+    T.nrows = (int32_t)trows.size();
+    T.nt = (T.nrows + 7) / 8;
+    std::vector<uint64_t> U;
+    for (int32_t r : trows) U = U.empty() ? rows[r].keys : union_of(U, rows[r].keys);
+    T.npairs = (int32_t)U.size();
+    T.nks = (T.npairs + 3) / 4;
+    T.ks_begin = (int32_t)(P.pairs.size() / 4);
+    T.vals_off = (int64_t)P.vals.size();
+    T.rows_off = (int32_t)P.rows.size();
+    for (int n = 0; n < 8 * T.nt; ++n) P.rows.push_back(n < T.nrows ? trows[n] : -1);
+    const uint32_t padpair = (uint32_t)(nin - 1) | ((uint32_t)(nin - 1) << 16);
+    for (int k = 0; k < 4 * T.nks; ++k) {
+      if (k < T.npairs) {
+        uint32_t a = (uint32_t)(U[k] / nin), b = (uint32_t)(U[k] % nin);
+        P.pairs.push_back(a | (b << 16));
+      } else {
+        P.pairs.push_back(padpair);
+      }
+    }
+    P.vals.resize(P.vals.size() + (size_t)T.nks * T.nt * 32, 0.0);
+    double* V = P.vals.data() + T.vals_off;
+    for (int n = 0; n < T.nrows; ++n) {
+      const Row& rw = rows[trows[n]];
+      size_t pos = 0;
+      for (size_t e = 0; e < rw.keys.size(); ++e) {
+        while (U[pos] != rw.keys[e]) ++pos;  // both sorted; rw.keys is a subset of U
+        const int ks = (int)(pos / 4), kk = (int)(pos % 4), nt = n / 8, nn = n % 8;
+        V[((size_t)ks * T.nt + nt) * 32 + nn * 4 + kk] = rw.vals[e];  // lane = (n%8)*4 + (k%4)
+      }
+    }
+    P.padded_fma += (int64_t)T.nks * 4 * T.nt * 8;
+    P.pair_products += (int64_t)T.nks * 4;
+    P.tiles.push_back(T);
+  };
+
+  for (auto& cl : clusters) {
+    const int n = (int)cl.size();
+    const int slots = (n + 7) / 8;                     // n-tiles needed
+    const int ntiles = (slots + nt_max - 1) / nt_max;  // tiles needed
+    int done = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      const int remaining_tiles = ntiles - t;
+      const int take = (n - done + remaining_tiles - 1) / remaining_tiles;  // even split, <= 8*nt_max
+      emit_tile(std::vector<int32_t>(cl.begin() + done, cl.begin() + done + take));
+      done += take;
+    }
+  }
+  // rows without any term still have to be written (as zeros)
+  for (size_t e = 0; e < empties.size(); e += 8 * (size_t)nt_max) {
+    size_t n = std::min(empties.size() - e, (size_t)8 * nt_max);
+    TileDesc T{};
+    T.nrows = (int32_t)n;
+    T.nt = (T.nrows + 7) / 8;
+    T.nks = 0;
+    T.npairs = 0;
+    T.ks_begin = (int32_t)(P.pairs.size() / 4);
+    T.vals_off = (int64_t)P.vals.size();
+    T.rows_off = (int32_t)P.rows.size();
+    for (int k = 0; k < 8 * T.nt; ++k) P.rows.push_back(k < T.nrows ? empties[e + k] : -1);
+    P.tiles.push_back(T);
+  }
+  // long tiles first: the tail of each state block is then made of short tiles
+  std::stable_sort(P.tiles.begin(), P.tiles.end(), [](const TileDesc& x, const TileDesc& y) {
+    return (int64_t)x.nks * x.nt > (int64_t)y.nks * y.nt;
+  });
+  return P;
+}
+
+}  // namespace ca

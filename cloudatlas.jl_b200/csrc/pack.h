@@ -1,0 +1,50 @@
+// Host-side packing of a sparse bilinear (+ linear) operator into DMMA row tiles.
+//
+// The operator  out_i = sum_{(a,b)} V[i,(a,b)] * u_a * w_b  is re-expressed as a block-sparse matrix
+// product over PAIR PRODUCTS: out[s, i] = sum_p P[s, p] * V[p, i] with P[s,(a,b)] = u_a[s] * w_b[s].
+// Output rows with (nearly) identical pair sets -- in a Galerkin model: modes of one wavenumber group
+// and wall-normal parity -- are clustered into tiles of 8*nt rows that share one pair list, so that
+// inside a tile V is dense and feeds mma.sync.m8n8k4.f64 directly:
+//   A fragment = pair products (8 states x 4 pairs), generated on the fly from the state tile in
+//   shared memory;  B fragment = V (4 pairs x 8 rows), streamed from L2 in fragment order.
+// A linear term L[i,j] x_j is the pair (j, ONE) with the pseudo mode ONE == m holding 1.0.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace ca {
+
+struct Term {
+  int32_t i, a, b;  // output row, first and second factor (0-based; a or b == m means the constant 1)
+  double v;
+};
+
+struct TileDesc {
+  int32_t ks_begin;  // first k-step of this tile (one k-step = 4 pairs) in `pairs`
+  int32_t nks;       // number of k-steps
+  int64_t vals_off;  // offset (doubles) of this tile's values: [nks][nt][32 lanes]
+  int32_t rows_off;  // offset into `rows` (8*nt entries, -1 = padding)
+  int32_t nt;        // n-tiles of 8 output rows
+  int32_t nrows;     // real rows in the tile
+  int32_t npairs;    // real pairs in the tile (<= 4*nks)
+};
+
+struct PackedHost {
+  int32_t m = 0;    // outputs
+  int32_t nin = 0;  // inputs including the constant-one pseudo mode (index nin-1)
+  bool symmetric = false;
+  std::vector<TileDesc> tiles;
+  std::vector<uint32_t> pairs;  // a | (b << 16), 4 per k-step
+  std::vector<double> vals;
+  std::vector<int32_t> rows;
+  int64_t nterms = 0;           // merged non-zero terms
+  int64_t npairs_distinct = 0;  // distinct (a,b) over the whole operator
+  int64_t padded_fma = 0;       // FMAs the tiles execute per state (incl. padding)
+  int64_t pair_products = 0;    // pair products formed per state (sum over tiles)
+};
+
+// Merges duplicate (i,a,b), drops exact zeros, clusters rows, lays out fragments.
+// symmetric: (a,b) and (b,a) are the same pair (u == w); ordered otherwise.
+PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt_max);
+
+}  // namespace ca

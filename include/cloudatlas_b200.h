@@ -1,0 +1,98 @@
+/* cloudatlas_b200.h -- C ABI of libcloudatlas_b200.so
+ *
+ * Drop-in boundary for the data-parallel hot path of johnfgibson/CloudAtlas.jl: building and
+ * evaluating  dx/dt = B^-1 (A1 x + A2 x / R + N(x,x))  on NVIDIA B200 (sm_100a).
+ * Every entry point names the reference interface it replaces (file:line under the reference
+ * repository's src/).  Plain pointers and sizes only; no CUDA, torch or C++ types cross the boundary.
+ *
+ * Conventions
+ *   - every function returns an int32 status, 0 = CA_OK; on failure ca_last_error() (thread-local)
+ *     describes it.  The Julia wrapper turns a non-zero status into error(msg), matching the
+ *     reference's error() calls (SparseBilinear.jl:8-9).
+ *   - matrices are column-major (Julia layout).  Index arrays are 1-based int64, exactly as the
+ *     reference's N.ijk (nnz x 3, column-major: all i, then all j, then all k).
+ *   - ensembles of states are nstates x m column-major: X[s + nstates*j] (state index fastest).
+ *   - the caller owns every array it passes; handles own their device memory; *_destroy frees it.
+ *   - a handle lives on the CUDA device that was current when it was created.
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute entry point fails.
+ *   - entry points ending in _dev take DEVICE pointers and a cudaStream_t (as void*, NULL = default
+ *     stream) and are asynchronous; all others take HOST pointers and return when the result is there.
+ */
+#ifndef CLOUDATLAS_B200_H
+#define CLOUDATLAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  CA_OK = 0,
+  CA_ERR_INVALID = 1,   /* bad argument (shape, index out of range, null pointer) */
+  CA_ERR_CUDA = 2,      /* CUDA runtime error (sticky; see ca_last_error) */
+  CA_ERR_NODEVICE = 3,  /* no CUDA device / not an sm_100 device */
+  CA_ERR_NOMEM = 4,
+  CA_ERR_UNSUPPORTED = 5
+};
+
+typedef struct ca_bilinear ca_bilinear; /* SparseBilinear{Float64}, packed on the device */
+typedef struct ca_model ca_model;       /* ODEModel{Float64}: B, A1, A2, N and the folded operators */
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* ca_last_error(void);
+int32_t ca_version(void);
+/* number of CUDA devices visible, name + SM count + compute capability of the current one */
+int32_t ca_device_info(int32_t* ndevices, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,
+                       char* name, int32_t name_len);
+/* page-lock / unlock a caller-owned host buffer so the host-pointer entry points can overlap
+ * copies with kernels (Julia: call on the Array's pointer; optional, results identical) */
+int32_t ca_pin(void* host_ptr, int64_t bytes);
+int32_t ca_unpin(void* host_ptr);
+/* number of kernels launched by this library in the calling process so far (bench bookkeeping) */
+int64_t ca_launch_count(void);
+
+/* ---- SparseBilinear (reference: src/SparseBilinear.jl) -------------------------------------- */
+/* SparseBilinear(ijk, val, m)  -- SparseBilinear.jl:7-11.  ijk: nnz x 3 column-major, 1-based.
+ * Copies the COO, builds the device packing.  Fails with CA_ERR_INVALID where the reference
+ * constructor calls error() (shape) and additionally on out-of-range indices. */
+int32_t ca_bilinear_create(const int64_t* ijk, const double* val, int64_t nnz, int64_t m,
+                           ca_bilinear** out);
+int32_t ca_bilinear_destroy(ca_bilinear* h);
+int32_t ca_bilinear_info(const ca_bilinear* h, int64_t* m, int64_t* nnz, int64_t* nnz_sym,
+                         int64_t* npairs, int64_t* padded_fma_per_state);
+/* N(x,y): out_i = sum_r val_r x[j_r] y[k_r]  -- SparseBilinear.jl:56-65.  y == NULL means N(x)
+ * = N(x,x) (SparseBilinear.jl:70).  x, y, out: m doubles on the host. */
+int32_t ca_bilinear_eval(ca_bilinear* h, const double* x, const double* y, double* out);
+/* N(x_s) for every row s of X (additive entry point: the reference evaluates one state per call).
+ * X, OUT: nstates x m column-major, host.  Chunked, copies overlapped with kernels. */
+int32_t ca_bilinear_eval_batched(ca_bilinear* h, const double* X, int64_t nstates, double* OUT);
+/* same on device memory; ldx/ldo = leading dimensions (>= nstates) */
+int32_t ca_bilinear_eval_batched_dev(ca_bilinear* h, const double* dX, int64_t nstates, int64_t ldx,
+                                     double* dOUT, int64_t ldo, void* stream);
+/* N(x_s, y_s) with two ensembles (ordered product x_j y_k), device memory */
+int32_t ca_bilinear_eval2_batched_dev(ca_bilinear* h, const double* dX, const double* dY,
+                                      int64_t nstates, int64_t ld, double* dOUT, int64_t ldo,
+                                      void* stream);
+/* derivative(N, x): DN[i,j] = sum_k (N_ijk + N_ikj) x_k, dense m x m column-major
+ * -- SparseBilinear.jl:75-91.  Host pointers. */
+int32_t ca_bilinear_jacobian(ca_bilinear* h, const double* x, double* DN);
+int32_t ca_bilinear_jacobian_dev(ca_bilinear* h, const double* dx, double* dDN, void* stream);
+/* matrix-free Jacobian action  DN(x) v = N(x,v) + N(v,x)  for ensembles (Newton-Krylov at m ~ 3000) */
+int32_t ca_bilinear_jvp_batched_dev(ca_bilinear* h, const double* dX, const double* dV,
+                                    int64_t nstates, int64_t ld, double* dOUT, int64_t ldo,
+                                    void* stream);
+
+/* ---- diagnostics (host only, no device needed) ---------------------------------------------- */
+/* Packs a COO operator exactly as ca_bilinear_create does, expands the packed tiles back into
+ * (i,j,k,val) terms and compares them with the (merged) input: *mismatches must come back 0.
+ * Also reports the packing statistics the roofline accounting uses.  Structure check only -- it
+ * evaluates nothing. */
+int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64_t nnz, int64_t m,
+                         int32_t symmetric, int64_t* ntiles, int64_t* nterms, int64_t* padded_fma,
+                         int64_t* pair_products, int64_t* mismatches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLOUDATLAS_B200_H */

@@ -1,0 +1,90 @@
+"""CPU-only checks of the C-ABI boundary: the library loads, exports every declared symbol, rejects bad
+arguments like the reference constructor does, refuses to compute without a device, and the host-side
+packer reproduces its input exactly (structure round trip).  No compute calls."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as g
+
+ca = g.load_package()
+from cloudatlas_b200._lib import _sig, c_f64p, c_i64p, check, exported_symbols, lib  # noqa: E402
+
+_selftest = _sig("ca_selftest_pack", c_i64p, c_f64p, C.c_int64, C.c_int64, C.c_int32,
+                 c_i64p, c_i64p, c_i64p, c_i64p, c_i64p)
+
+
+def pack_stats(ijk, val, m, symmetric):
+    ijk = np.asfortranarray(ijk, dtype=np.int64)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    out = [C.c_int64() for _ in range(5)]
+    check(_selftest(ijk.ctypes.data_as(c_i64p), val.ctypes.data_as(c_f64p), len(val), m, symmetric,
+                    *[C.byref(o) for o in out]))
+    return dict(zip(("ntiles", "nterms", "padded_fma", "pair_products", "mismatches"), (o.value for o in out)))
+
+
+def test_every_declared_symbol_is_exported():
+    names = exported_symbols()
+    assert len(names) >= 15
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_constructor_errors_match_reference():
+    # SparseBilinear.jl:8-9
+    with pytest.raises(ca.CloudAtlasError, match="three columns"):
+        ca.SparseBilinear(np.ones((4, 2), dtype=np.int64), np.ones(4), 3)
+    with pytest.raises(ca.CloudAtlasError, match="same number of rows"):
+        ca.SparseBilinear(np.ones((4, 3), dtype=np.int64), np.ones(5), 3)
+    with pytest.raises(ca.CloudAtlasError, match="outside 1:3"):
+        ca.SparseBilinear(np.array([[1, 4, 1]]), np.ones(1), 3)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    with pytest.raises(ca.CloudAtlasError) as e:
+        ca.SparseBilinear(np.array([[1, 1, 1]]), np.ones(1), 3)
+    assert e.value.code == 3 and "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.parametrize("JKL,nnz", [((1, 1, 3), 396), ((2, 2, 3), 5654)])
+def test_pack_roundtrip_models(JKL, nnz, nagata_H):
+    from oracle.basis import basisIndices
+    from oracle.fastfloat import assemble_N_float
+    ijkl = basisIndices(*JKL, nagata_H)
+    ijk, val = assemble_N_float(1, 2, ijkl)
+    assert len(val) == nnz
+    for sym in (1, 0):
+        st = pack_stats(ijk, val, ijkl.shape[0], sym)
+        assert st["mismatches"] == 0
+        assert st["padded_fma"] >= st["nterms"]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_pack_roundtrip_random(seed):
+    rng = np.random.default_rng(seed)
+    m = int(rng.integers(1, 70))
+    nnz = int(rng.integers(0, 4 * m * m))
+    ijk = rng.integers(1, m + 1, size=(nnz, 3))
+    if seed % 2:
+        ijk[:, 0] = np.minimum(ijk[:, 0], max(1, m // 2))  # leaves rows without terms
+    val = rng.standard_normal(nnz)
+    val[rng.random(nnz) < 0.1] = 0.0                        # explicit zeros are dropped
+    for sym in (1, 0):
+        assert pack_stats(ijk, val, m, sym)["mismatches"] == 0
+
+
+def test_pack_fill_at_307(nagata_H):
+    """The clustering finds the wavenumber/parity classes: >= 75 % of the executed FMAs are real."""
+    from oracle.basis import basisIndices
+    from oracle.fastfloat import assemble_N_float
+    ijkl = basisIndices(3, 3, 12, nagata_H)
+    assert ijkl.shape[0] == 307
+    ijk, val = assemble_N_float(1, 2, ijkl)
+    assert len(val) == 1355658
+    st = pack_stats(ijk, val, 307, 1)
+    assert st["mismatches"] == 0
+    assert st["nterms"] / st["padded_fma"] > 0.75

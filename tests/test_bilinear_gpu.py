@@ -1,0 +1,143 @@
+"""Parity of the CUDA SparseBilinear path (through the C ABI) against the CPU oracle.
+Tolerances: 1e-13 relative (norm-wise) for RHS / Jacobian outputs, as north_star states."""
+import numpy as np
+import pytest
+
+import __graft_entry__ as g
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-13
+
+
+@pytest.fixture(scope="module")
+def ca():
+    return g.load_package()
+
+
+def relerr(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+def model_coo(JKL, nagata_H):
+    from oracle.basis import basisIndices
+    from oracle.fastfloat import assemble_N_float
+    ijkl = basisIndices(*JKL, nagata_H)
+    ijk, val = assemble_N_float(1, 2, ijkl)
+    return ijk, val, ijkl.shape[0]
+
+
+@pytest.fixture(scope="module", params=[(1, 1, 3), (1, 2, 3), (2, 2, 3)], ids=["17d", "27d", "44d"])
+def pair(request, ca, nagata_H):
+    from oracle.bilinear import SparseBilinear as Ref
+    ijk, val, m = model_coo(request.param, nagata_H)
+    return ca.SparseBilinear(ijk, val, m), Ref(ijk, val, m)
+
+
+def test_single_state_eval(pair):
+    N, ref = pair
+    rng = np.random.default_rng(1)
+    x, y = 0.1 * rng.standard_normal(N.m), 0.1 * rng.standard_normal(N.m)
+    assert relerr(N(x), ref(x)) < TOL
+    assert relerr(N(x, y), ref(x, y)) < TOL
+    assert relerr(N(y, x), ref(y, x)) < TOL
+
+
+@pytest.mark.parametrize("nstates", [1, 7, 8, 31, 32, 33, 100, 10000])
+def test_batched_eval_host(pair, nstates):
+    from oracle.bilinear import eval_batched
+    N, ref = pair
+    X = 0.1 * np.random.default_rng(nstates).standard_normal((nstates, N.m))
+    got = N(X)
+    assert got.shape == X.shape
+    assert relerr(got, eval_batched(ref, X)) < TOL
+
+
+def test_batched_empty(pair):
+    N, _ = pair
+    assert N(np.zeros((0, N.m))).shape == (0, N.m)
+
+
+def test_batched_eval_device_and_two_vector(pair, ca):
+    import torch
+    from oracle.bilinear import eval_batched
+    N, ref = pair
+    rng = np.random.default_rng(5)
+    X = 0.1 * rng.standard_normal((999, N.m))
+    Y = 0.1 * rng.standard_normal((999, N.m))
+    dX = torch.from_numpy(np.asfortranarray(X).T.copy()).cuda().t()   # column-major on the device
+    dY = torch.from_numpy(np.asfortranarray(Y).T.copy()).cuda().t()
+    assert relerr(N(dX).cpu().numpy(), eval_batched(ref, X)) < TOL
+    want = np.stack([ref(X[s], Y[s]) for s in range(0, 999, 37)])
+    got = N(dX, dY).cpu().numpy()[::37]
+    assert relerr(got, want) < TOL
+    # leading dimension larger than nstates: a view of the first 500 states
+    assert relerr(N(dX[:500]).cpu().numpy(), eval_batched(ref, X[:500])) < TOL
+
+
+def test_jacobian(pair):
+    N, ref = pair
+    x = 0.1 * np.random.default_rng(2).standard_normal(N.m)
+    DN = N.derivative(x)
+    assert DN.shape == (N.m, N.m)
+    assert relerr(DN, ref.derivative(x)) < TOL
+    # DN(x) x = 2 N(x)   (Euler, degree-2 homogeneity)
+    assert relerr(DN @ x, 2 * ref(x)) < 1e-12
+
+
+def test_jvp_matches_jacobian(pair, ca):
+    import torch
+    N, ref = pair
+    rng = np.random.default_rng(3)
+    X = 0.1 * rng.standard_normal((64, N.m))
+    V = rng.standard_normal((64, N.m))
+    dX = torch.from_numpy(X.T.copy()).cuda().t()
+    dV = torch.from_numpy(V.T.copy()).cuda().t()
+    got = N.jvp(dX, dV).cpu().numpy()
+    want = np.stack([ref.derivative(X[s]) @ V[s] for s in range(64)])
+    assert relerr(got, want) < TOL
+
+
+def test_random_operator_with_duplicates_and_empty_rows(ca):
+    from oracle.bilinear import SparseBilinear as Ref, eval_batched
+    rng = np.random.default_rng(11)
+    m, nnz = 53, 4000
+    ijk = rng.integers(1, m + 1, size=(nnz, 3))
+    ijk[:, 0] = np.minimum(ijk[:, 0], 40)          # rows 41..53 have no terms -> zeros
+    val = rng.standard_normal(nnz)
+    N, ref = ca.SparseBilinear(ijk, val, m), Ref(ijk, val, m)
+    X = rng.standard_normal((257, m))
+    got = N(X)
+    assert relerr(got, eval_batched(ref, X)) < TOL
+    assert np.all(got[:, 40:] == 0.0)
+    x = X[0]
+    assert relerr(N.derivative(x), ref.derivative(x)) < TOL
+    assert relerr(N(x, X[1]), ref(x, X[1])) < TOL
+
+
+def test_energy_conservation_17d(ca, nagata_H):
+    """x . N(x,x) = 0 for the Galerkin-projected advection term (invariant iv)."""
+    ijk, val, m = model_coo((1, 1, 3), nagata_H)
+    from oracle.fastfloat import assemble_linear_float
+    from oracle.basis import basisIndices
+    B, _, _ = assemble_linear_float(1, 2, basisIndices(1, 1, 3, nagata_H))
+    N = ca.SparseBilinear(ijk, val, m)
+    X = np.random.default_rng(4).standard_normal((100, m))
+    E = np.einsum("sm,sm->s", X, N(X))
+    assert np.max(np.abs(E)) < 1e-12 * np.max(np.abs(N(X))) * np.max(np.abs(X)) * m
+
+
+def test_m307_ensemble(ca, nagata_H):
+    """Config 3 of BASELINE.json at parity-test size: 307-mode basis, oracle on a sample of states."""
+    from oracle.bilinear import SparseBilinear as Ref, eval_batched
+    ijk, val, m = model_coo((3, 3, 12), nagata_H)
+    assert m == 307 and len(val) == 1355658
+    N, ref = ca.SparseBilinear(ijk, val, m), Ref(ijk, val, m)
+    X = 0.1 * np.random.default_rng(6).standard_normal((4099, m))
+    got = N(X)
+    idx = np.arange(0, 4099, 41)
+    assert relerr(got[idx], eval_batched(ref, X[idx])) < TOL
+    # size-independent properties on the full ensemble: homogeneity N(2x) = 4 N(x), and row independence
+    assert relerr(N(2 * X), 4 * got) < 1e-15
+    assert np.array_equal(N(X[1000:1100]), got[1000:1100])
+    x = X[0]
+    assert relerr(N.derivative(x), ref.derivative(x)) < TOL
