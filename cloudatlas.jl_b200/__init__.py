@@ -9,7 +9,9 @@ Julia is not available in the build image, and is what tests/ and bench.py drive
 The directory name contains a dot, so load it with ``__graft_entry__.load_package()``.
 """
 from ._lib import CloudAtlasError, LIB_PATH, lib  # noqa: F401
-from .bilinear import SparseBilinear, derivative, sparse  # noqa: F401
+from .bilinear import SparseBilinear, derivative, ensemble_empty, sparse  # noqa: F401
+from .model import ModelOperators  # noqa: F401
+from .basis import Symmetry, basisComponents, basisIndices, halfbox_symmetries, symmetric  # noqa: F401
 
 
 def launch_count() -> int:

@@ -1,0 +1,334 @@
+// C ABI: ODEModel evaluation side (reference: src/ODEModels.jl:54-58).
+#include <algorithm>
+#include <cmath>
+#include <functional>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <vector>
+
+#include "bilinear.h"
+#include "bilinear_kernels.cuh"
+
+using namespace ca;
+
+namespace ca {
+void eval_batched_host(const DevicePack& op, cudaStream_t streams[2], DeviceBuffer<double> in[2],
+                       DeviceBuffer<double> out[2], const double* X, int64_t nstates, double* OUT,
+                       int64_t m_in, int64_t m_out);
+}
+
+namespace {
+
+// vals[pos[t]] = l1[t] + l2[t] * invR : re-targets the linear slots of the packed operator to a new R
+__global__ void patch_linear_kernel(double* __restrict__ vals, const int64_t* __restrict__ pos,
+                                    const double* __restrict__ l1, const double* __restrict__ l2,
+                                    int64_t n, double invR) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) vals[pos[t]] = fma(l2[t], invR, l1[t]);
+}
+
+// Df[i,j] += L1[i,j] + L2[i,j] * invR
+__global__ void add_linear_kernel(double* __restrict__ Df, const double* __restrict__ L1,
+                                  const double* __restrict__ L2, int64_t n, double invR) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) Df[t] += fma(L2[t], invR, L1[t]);
+}
+
+// In-place LU with partial pivoting of a dense g x g block (row-major), then inverse by solving for
+// the identity -- the per-block equivalent of  Bfact = lu(B); Bfact \ I  (ODEModels.jl:54).
+void invert_block(std::vector<double>& A, int g, std::vector<double>& inv) {
+  std::vector<int> piv(g);
+  for (int c = 0; c < g; ++c) {
+    int p = c;
+    for (int r = c + 1; r < g; ++r)
+      if (std::fabs(A[r * g + c]) > std::fabs(A[p * g + c])) p = r;
+    if (A[p * g + c] == 0.0) fail(CA_ERR_INVALID, "ca_model_create: B is singular");
+    piv[c] = p;
+    if (p != c)
+      for (int k = 0; k < g; ++k) std::swap(A[c * g + k], A[p * g + k]);
+    for (int r = c + 1; r < g; ++r) {
+      const double f = A[r * g + c] / A[c * g + c];
+      A[r * g + c] = f;
+      for (int k = c + 1; k < g; ++k) A[r * g + k] -= f * A[c * g + k];
+    }
+  }
+  inv.assign((size_t)g * g, 0.0);
+  std::vector<double> b(g);
+  for (int col = 0; col < g; ++col) {
+    std::fill(b.begin(), b.end(), 0.0);
+    b[col] = 1.0;
+    for (int c = 0; c < g; ++c)
+      if (piv[c] != c) std::swap(b[c], b[piv[c]]);
+    for (int r = 1; r < g; ++r) {
+      double s = b[r];
+      for (int k = 0; k < r; ++k) s -= A[r * g + k] * b[k];
+      b[r] = s;
+    }
+    for (int r = g - 1; r >= 0; --r) {
+      double s = b[r];
+      for (int k = r + 1; k < g; ++k) s -= A[r * g + k] * b[k];
+      b[r] = s / A[r * g + r];
+    }
+    for (int r = 0; r < g; ++r) inv[(size_t)r * g + col] = b[r];
+  }
+}
+
+}  // namespace
+
+struct ca_model {
+  int device = 0;
+  int64_t m = 0;
+  int64_t nblocks = 0, nnz_lin = 0;
+  DevicePack op;           // symmetric pack of Q plus the linear slots
+  JacobianPack jac;        // of Q
+  DeviceBuffer<double> L1, L2;            // dense m x m column-major (for Df)
+  DeviceBuffer<int64_t> lin_pos;          // linear slots inside op.vals
+  DeviceBuffer<double> lin_l1, lin_l2;
+  double cur_invR = std::nan("");
+  cudaStream_t streams[2] = {nullptr, nullptr};
+  DeviceBuffer<double> stage_in[2], stage_out[2], small_x, small_out, jac_out;
+  ~ca_model() {
+    for (auto& s : streams)
+      if (s) cudaStreamDestroy(s);
+  }
+  void bind() const { CA_CUDA(cudaSetDevice(device)); }
+  void need_streams() {
+    for (auto& s : streams)
+      if (!s) CA_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  }
+  // The packed values are shared by all streams: re-targeting R is ordered after everything queued.
+  void set_R(double R, cudaStream_t stream) {
+    if (!(R != 0.0)) fail(CA_ERR_INVALID, "R must be non-zero");
+    const double invR = 1.0 / R;
+    if (invR == cur_invR) return;
+    if (nnz_lin > 0) {
+      CA_CUDA(cudaDeviceSynchronize());
+      patch_linear_kernel<<<(unsigned)((nnz_lin + 255) / 256), 256, 0, stream>>>(
+          op.vals.ptr, lin_pos.ptr, lin_l1.ptr, lin_l2.ptr, nnz_lin, invR);
+      CA_CUDA(cudaGetLastError());
+      count_launch();
+      CA_CUDA(cudaStreamSynchronize(stream));
+    }
+    cur_invR = invR;
+  }
+};
+
+extern "C" {
+
+int32_t ca_model_create(const double* B, const double* A1, const double* A2, int64_t m64,
+                        const int64_t* ijk, const double* val, int64_t nnz, ca_model** out) {
+  return guarded([&] {
+    if (!out) fail(CA_ERR_INVALID, "ca_model_create: out is null");
+    *out = nullptr;
+    if (m64 <= 0 || !B || !A1 || !A2) fail(CA_ERR_INVALID, "ca_model_create: bad operator arguments");
+    if (nnz < 0 || (nnz > 0 && (!ijk || !val))) fail(CA_ERR_INVALID, "ijk and val must have same number of rows");
+    const int m = (int)m64;
+    for (int64_t r = 0; r < nnz; ++r)
+      for (int c = 0; c < 3; ++c)
+        if (ijk[r + c * nnz] < 1 || ijk[r + c * nnz] > m64)
+          fail(CA_ERR_INVALID, "ca_model_create: N entry %lld has an index outside 1:%lld", (long long)r + 1, (long long)m64);
+
+    // ---- blocks of B = connected components of its non-zero pattern
+    std::vector<int> comp(m);
+    std::iota(comp.begin(), comp.end(), 0);
+    std::function<int(int)> find = [&](int a) { while (comp[a] != a) a = comp[a] = comp[comp[a]]; return a; };
+    for (int j = 0; j < m; ++j)
+      for (int i = 0; i < m; ++i)
+        if (i != j && (B[i + (size_t)m * j] != 0.0 || B[j + (size_t)m * i] != 0.0)) {
+          int a = find(i), b = find(j);
+          if (a != b) comp[std::max(a, b)] = std::min(a, b);
+        }
+    std::map<int, std::vector<int>> blocks;
+    for (int i = 0; i < m; ++i) blocks[find(i)].push_back(i);
+
+    // ---- N grouped by output row
+    std::vector<std::vector<std::pair<uint64_t, double>>> byrow(m);
+    for (int64_t r = 0; r < nnz; ++r) {
+      const int i = (int)ijk[r] - 1;
+      const uint64_t j = (uint64_t)ijk[r + nnz] - 1, k = (uint64_t)ijk[r + 2 * nnz] - 1;
+      byrow[i].push_back({j * (uint64_t)m + k, val[r]});
+    }
+    std::vector<Term> qterms;  // folded Q = B^-1 N, ordered (j,k)
+    qterms.reserve((size_t)nnz * 2);
+    std::vector<double> hL1((size_t)m * m, 0.0), hL2((size_t)m * m, 0.0);
+    for (auto& kv : blocks) {
+      const std::vector<int>& G = kv.second;
+      const int g = (int)G.size();
+      std::vector<double> Bg((size_t)g * g), Binv;
+      for (int a = 0; a < g; ++a)
+        for (int b = 0; b < g; ++b) Bg[(size_t)a * g + b] = B[G[a] + (size_t)m * G[b]];
+      invert_block(Bg, g, Binv);
+      // linear operators: rows G of B^-1 A
+      for (int a = 0; a < g; ++a)
+        for (int j = 0; j < m; ++j) {
+          double s1 = 0, s2 = 0;
+          for (int b = 0; b < g; ++b) {
+            s1 += Binv[(size_t)a * g + b] * A1[G[b] + (size_t)m * j];
+            s2 += Binv[(size_t)a * g + b] * A2[G[b] + (size_t)m * j];
+          }
+          hL1[G[a] + (size_t)m * j] = s1;
+          hL2[G[a] + (size_t)m * j] = s2;
+        }
+      // quadratic operator: dense [g x |union of pairs|] times Binv
+      std::vector<uint64_t> U;
+      for (int b = 0; b < g; ++b)
+        for (auto& e : byrow[G[b]]) U.push_back(e.first);
+      std::sort(U.begin(), U.end());
+      U.erase(std::unique(U.begin(), U.end()), U.end());
+      if (U.empty()) continue;
+      std::vector<double> D((size_t)g * U.size(), 0.0);
+      for (int b = 0; b < g; ++b)
+        for (auto& e : byrow[G[b]]) {
+          const size_t p = std::lower_bound(U.begin(), U.end(), e.first) - U.begin();
+          D[(size_t)b * U.size() + p] += e.second;
+        }
+      for (int a = 0; a < g; ++a)
+        for (size_t p = 0; p < U.size(); ++p) {
+          double s = 0;
+          bool any = false;
+          for (int b = 0; b < g; ++b) {
+            const double d = D[(size_t)b * U.size() + p];
+            if (d != 0.0 && Binv[(size_t)a * g + b] != 0.0) {
+              s += Binv[(size_t)a * g + b] * d;
+              any = true;
+            }
+          }
+          if (any && s != 0.0)
+            qterms.push_back(Term{G[a], (int32_t)(U[p] / m), (int32_t)(U[p] % m), s});
+        }
+    }
+
+    require_device();
+    std::unique_ptr<ca_model> h(new ca_model);
+    CA_CUDA(cudaGetDevice(&h->device));
+    h->m = m;
+    h->nblocks = (int64_t)blocks.size();
+    h->jac.build(qterms, m);
+    // linear placeholders (value 1) mark the slots that set_R patches
+    std::vector<Term> all = qterms;
+    for (int j = 0; j < m; ++j)
+      for (int i = 0; i < m; ++i)
+        if (hL1[i + (size_t)m * j] != 0.0 || hL2[i + (size_t)m * j] != 0.0) all.push_back(Term{i, j, m, 1.0});
+    PackedHost P = pack_terms(std::move(all), m, /*symmetric=*/true, kNtMax);
+    std::vector<int64_t> pos;
+    std::vector<double> l1, l2;
+    for (const TileDesc& T : P.tiles)
+      for (int k = 0; k < 4 * T.nks; ++k) {
+        const uint32_t pr = P.pairs[(size_t)T.ks_begin * 4 + k];
+        const int a = pr & 0xffff, b = pr >> 16;
+        if (b != m || a == m) continue;
+        for (int n = 0; n < T.nrows; ++n) {
+          const size_t at = (size_t)T.vals_off + ((size_t)(k / 4) * T.nt + n / 8) * 32 + (n % 8) * 4 + k % 4;
+          if (P.vals[at] == 0.0) continue;
+          const int row = P.rows[(size_t)T.rows_off + n];
+          pos.push_back((int64_t)at);
+          l1.push_back(hL1[row + (size_t)m * a]);
+          l2.push_back(hL2[row + (size_t)m * a]);
+        }
+      }
+    h->nnz_lin = (int64_t)pos.size();
+    h->op.upload(P);
+    h->lin_pos.upload(pos.data(), pos.size());
+    h->lin_l1.upload(l1.data(), l1.size());
+    h->lin_l2.upload(l2.data(), l2.size());
+    h->L1.upload(hL1.data(), hL1.size());
+    h->L2.upload(hL2.data(), hL2.size());
+    CA_CUDA(cudaStreamSynchronize(nullptr));
+    *out = h.release();
+  });
+}
+
+int32_t ca_model_destroy(ca_model* h) {
+  return guarded([&] {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    delete h;
+  });
+}
+
+int32_t ca_model_info(const ca_model* h, int64_t* m, int64_t* nnz_q_sym, int64_t* nnz_lin,
+                      int64_t* npairs, int64_t* padded_fma_per_state, int64_t* nblocks_B) {
+  return guarded([&] {
+    if (!h) fail(CA_ERR_INVALID, "null handle");
+    if (m) *m = h->m;
+    if (nnz_q_sym) *nnz_q_sym = h->op.nterms - h->nnz_lin;
+    if (nnz_lin) *nnz_lin = h->nnz_lin;
+    if (npairs) *npairs = h->op.npairs_distinct;
+    if (padded_fma_per_state) *padded_fma_per_state = h->op.padded_fma;
+    if (nblocks_B) *nblocks_B = h->nblocks;
+  });
+}
+
+int32_t ca_model_rhs_batched_dev(ca_model* h, const double* dX, int64_t nstates, int64_t ldx, double R,
+                                 double* dOUT, int64_t ldo, void* stream) {
+  return guarded([&] {
+    if (!h || (nstates > 0 && (!dX || !dOUT))) fail(CA_ERR_INVALID, "null argument");
+    h->bind();
+    h->set_R(R, (cudaStream_t)stream);
+    launch_batched(h->op, MODE_QUAD, dX, nullptr, nstates, ldx, dOUT, ldo, (cudaStream_t)stream);
+  });
+}
+
+int32_t ca_model_jvp_batched_dev(ca_model* h, const double* dX, const double* dV, int64_t nstates,
+                                 int64_t ld, double R, double* dOUT, int64_t ldo, void* stream) {
+  return guarded([&] {
+    if (!h || (nstates > 0 && (!dX || !dV || !dOUT))) fail(CA_ERR_INVALID, "null argument");
+    h->bind();
+    h->set_R(R, (cudaStream_t)stream);
+    launch_batched(h->op, MODE_JVP, dX, dV, nstates, ld, dOUT, ldo, (cudaStream_t)stream);
+  });
+}
+
+int32_t ca_model_rhs_batched(ca_model* h, const double* X, int64_t nstates, double R, double* OUT) {
+  return guarded([&] {
+    if (!h || (nstates > 0 && (!X || !OUT))) fail(CA_ERR_INVALID, "null argument");
+    if (nstates < 0) fail(CA_ERR_INVALID, "nstates must be non-negative");
+    h->bind();
+    h->need_streams();
+    h->set_R(R, h->streams[0]);
+    eval_batched_host(h->op, h->streams, h->stage_in, h->stage_out, X, nstates, OUT, h->m, h->m);
+  });
+}
+
+int32_t ca_model_rhs(ca_model* h, const double* x, double R, double* out) {
+  return guarded([&] {
+    if (!h || !x || !out) fail(CA_ERR_INVALID, "null argument");
+    h->bind();
+    const size_t m = (size_t)h->m;
+    h->set_R(R, nullptr);
+    h->small_x.upload(x, m);
+    if (h->small_out.count < m) h->small_out.alloc(m);
+    launch_batched(h->op, MODE_QUAD, h->small_x.ptr, nullptr, 1, 1, h->small_out.ptr, 1, nullptr);
+    CA_CUDA(cudaMemcpy(out, h->small_out.ptr, m * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+int32_t ca_model_jac_dev(ca_model* h, const double* dx, double R, double* dDf, void* stream) {
+  return guarded([&] {
+    if (!h || !dx || !dDf) fail(CA_ERR_INVALID, "null argument");
+    if (!(R != 0.0)) fail(CA_ERR_INVALID, "R must be non-zero");
+    h->bind();
+    cudaStream_t st = (cudaStream_t)stream;
+    launch_jacobian(h->jac, dx, dDf, st);
+    const int64_t n = h->m * h->m;
+    add_linear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dDf, h->L1.ptr, h->L2.ptr, n, 1.0 / R);
+    CA_CUDA(cudaGetLastError());
+    count_launch();
+  });
+}
+
+int32_t ca_model_jac(ca_model* h, const double* x, double R, double* Df) {
+  return guarded([&] {
+    if (!h || !x || !Df) fail(CA_ERR_INVALID, "null argument");
+    h->bind();
+    const size_t m = (size_t)h->m;
+    h->small_x.upload(x, m);
+    if (h->jac_out.count < m * m) h->jac_out.alloc(m * m);
+    int32_t st = ca_model_jac_dev(h, h->small_x.ptr, R, h->jac_out.ptr, nullptr);
+    if (st != CA_OK) fail(st, "%s", ca_last_error());
+    CA_CUDA(cudaMemcpy(Df, h->jac_out.ptr, m * m * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+}  // extern "C"

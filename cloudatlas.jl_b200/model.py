@@ -1,0 +1,110 @@
+"""ODEModel evaluation side -- mirror of src/ODEModels.jl:6-63 over the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import CloudAtlasError, _sig, c_f64p, c_i64p, check, vp
+from .bilinear import SparseBilinear, _colmajor_ensemble, _f64, _is_torch, _stream, ensemble_empty
+
+_create = _sig("ca_model_create", c_f64p, c_f64p, c_f64p, C.c_int64, c_i64p, c_f64p, C.c_int64, C.POINTER(vp))
+_destroy = _sig("ca_model_destroy", vp)
+_info = _sig("ca_model_info", vp, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p)
+_rhs = _sig("ca_model_rhs", vp, c_f64p, C.c_double, c_f64p)
+_rhs_b = _sig("ca_model_rhs_batched", vp, c_f64p, C.c_int64, C.c_double, c_f64p)
+_rhs_b_dev = _sig("ca_model_rhs_batched_dev", vp, vp, C.c_int64, C.c_int64, C.c_double, vp, C.c_int64, vp)
+_jac = _sig("ca_model_jac", vp, c_f64p, C.c_double, c_f64p)
+_jac_dev = _sig("ca_model_jac_dev", vp, vp, C.c_double, vp, vp)
+_jvp_b_dev = _sig("ca_model_jvp_batched_dev", vp, vp, vp, C.c_int64, C.c_int64, C.c_double, vp, C.c_int64, vp)
+
+
+class ModelOperators:
+    """Device side of an ODEModel built from given operators (B, A1, A2 dense; N COO).
+
+    ``f(x, R)`` and ``Df(x, R)`` have the reference closures' meaning (ODEModels.jl:57-58); ``f`` also
+    accepts an ensemble (nstates x m), host (numpy) or device (CUDA tensor, column-major).
+    """
+
+    def __init__(self, B, A1, A2, ijk, val):
+        self.B = np.asfortranarray(B, dtype=np.float64)
+        self.A1 = np.asfortranarray(A1, dtype=np.float64)
+        self.A2 = np.asfortranarray(A2, dtype=np.float64)
+        m = self.B.shape[0]
+        if self.B.shape != (m, m) or self.A1.shape != (m, m) or self.A2.shape != (m, m):
+            raise CloudAtlasError(1, "B, A1, A2 must be square and of equal size")
+        ijk = np.asarray(ijk)
+        if ijk.ndim != 2 or ijk.shape[1] != 3:
+            raise CloudAtlasError(1, "ijk must have three columns")
+        self.ijk = np.asfortranarray(ijk, dtype=np.int64)
+        self.val = np.ascontiguousarray(val, dtype=np.float64)
+        if self.ijk.shape[0] != self.val.shape[0]:
+            raise CloudAtlasError(1, "ijk and val must have same number of rows")
+        self.m = m
+        h = vp()
+        check(_create(_f64(self.B), _f64(self.A1), _f64(self.A2), m, self.ijk.ctypes.data_as(c_i64p),
+                      _f64(self.val), self.ijk.shape[0], C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _destroy(h)
+            self._h = None
+
+    def __len__(self):
+        return self.m
+
+    def info(self):
+        v = [C.c_int64() for _ in range(6)]
+        check(_info(self._h, *[C.byref(a) for a in v]))
+        return dict(zip(("m", "nnz_q_sym", "nnz_lin", "npairs", "padded_fma_per_state", "nblocks_B"),
+                        (a.value for a in v)))
+
+    def f(self, x, R):
+        if _is_torch(x):
+            single = x.dim() == 1
+            X = x.reshape(1, -1) if single else x
+            X, n, ld = _colmajor_ensemble(X)
+            OUT = ensemble_empty(n, self.m, X.device)
+            check(_rhs_b_dev(self._h, vp(X.data_ptr()), n, ld, float(R), vp(OUT.data_ptr()), n, _stream()))
+            return OUT.reshape(-1) if single else OUT
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 1:
+            if x.shape[0] != self.m:
+                raise CloudAtlasError(1, f"x has length {x.shape[0]}, expected {self.m}")
+            out = np.empty(self.m)
+            check(_rhs(self._h, _f64(np.ascontiguousarray(x)), float(R), _f64(out)))
+            return out
+        if x.shape[1] != self.m:
+            raise CloudAtlasError(1, f"ensemble has {x.shape[1]} columns, expected {self.m}")
+        X = np.asfortranarray(x)
+        OUT = np.empty(X.shape, order="F")
+        check(_rhs_b(self._h, _f64(X), X.shape[0], float(R), _f64(OUT)))
+        return OUT
+
+    def f_into(self, X, R, OUT):
+        """Host ensemble into a caller-owned (e.g. page-locked) column-major buffer."""
+        check(_rhs_b(self._h, _f64(X), X.shape[0], float(R), _f64(OUT)))
+        return OUT
+
+    def Df(self, x, R):
+        if _is_torch(x):
+            import torch
+            D = torch.empty((self.m, self.m), dtype=torch.float64, device=x.device).t()
+            check(_jac_dev(self._h, vp(x.contiguous().data_ptr()), float(R), vp(D.data_ptr()), _stream()))
+            return D
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        D = np.empty((self.m, self.m), order="F")
+        check(_jac(self._h, _f64(x), float(R), _f64(D)))
+        return D
+
+    def Df_action(self, X, V, R):
+        """Df(x_s, R) v_s for CUDA ensembles (matrix-free)."""
+        X, n, ld = _colmajor_ensemble(X)
+        V, n2, ld2 = _colmajor_ensemble(V)
+        if (n2, ld2) != (n, ld):
+            raise CloudAtlasError(1, "X and V must have the same shape and leading dimension")
+        OUT = ensemble_empty(n, self.m, X.device)
+        check(_jvp_b_dev(self._h, vp(X.data_ptr()), vp(V.data_ptr()), n, ld, float(R), vp(OUT.data_ptr()), n, _stream()))
+        return OUT

@@ -36,6 +36,14 @@ enum {
   CA_ERR_UNSUPPORTED = 5
 };
 
+/* Symmetry(sx,sy,sz,ax,az,s) -- src/Symmetries.jl:3-14.  ax2 = 2*ax, az2 = 2*az (0 or 1: only half-box
+ * shifts are implemented by the reference, Symmetries.jl:33-43). */
+typedef struct ca_symmetry {
+  int32_t sx, sy, sz;
+  int32_t ax2, az2;
+  int32_t s;
+} ca_symmetry;
+
 typedef struct ca_bilinear ca_bilinear; /* SparseBilinear{Float64}, packed on the device */
 typedef struct ca_model ca_model;       /* ODEModel{Float64}: B, A1, A2, N and the folded operators */
 
@@ -51,6 +59,19 @@ int32_t ca_pin(void* host_ptr, int64_t bytes);
 int32_t ca_unpin(void* host_ptr);
 /* number of kernels launched by this library in the calling process so far (bench bookkeeping) */
 int64_t ca_launch_count(void);
+
+/* ---- index sets and basis (reference: src/BasisFunctions.jl, src/Symmetries.jl) --------------- */
+/* basisIndices(J,K,L[,H]) -- BasisFunctions.jl:489-574 with the symmetric() filter of
+ * Symmetries.jl:25-60.  Host only, integer only, bit-exact incl. row order.  nH = 0: unfiltered.
+ * ijkl_out == NULL: size query (*m_inout receives the row count).  Otherwise *m_inout is the capacity
+ * in rows on entry and the row count on exit; ijkl_out is m x 4 column-major. */
+int32_t ca_basis_indices(int32_t J, int32_t K, int32_t L, const ca_symmetry* H, int32_t nH,
+                         int64_t* ijkl_out, int64_t* m_inout);
+/* basisSet(alpha, gamma, ijkl; normalize) in tabular form -- BasisFunctions.jl:630-702: per mode and
+ * velocity component (u,v,w) the factor  coef * E_jx(x) E_kz(z) S_l^(d)(y).  Arrays are m x 3
+ * column-major; d = 0 for S_l, 1 for S_l'; coef == 0 marks an absent component. */
+int32_t ca_basis_components(double alpha, double gamma, const int64_t* ijkl, int64_t m, int32_t normalize,
+                            double* coef, int32_t* jx, int32_t* kz, int32_t* l, int32_t* d);
 
 /* ---- SparseBilinear (reference: src/SparseBilinear.jl) -------------------------------------- */
 /* SparseBilinear(ijk, val, m)  -- SparseBilinear.jl:7-11.  ijk: nnz x 3 column-major, 1-based.
@@ -82,6 +103,31 @@ int32_t ca_bilinear_jacobian_dev(ca_bilinear* h, const double* dx, double* dDN, 
 int32_t ca_bilinear_jvp_batched_dev(ca_bilinear* h, const double* dX, const double* dV,
                                     int64_t nstates, int64_t ld, double* dOUT, int64_t ldo,
                                     void* stream);
+
+/* ---- ODEModel (reference: src/ODEModels.jl) ------------------------------------------------- */
+/* Builds the evaluation side of an ODEModel from its operators: B, A1, A2 (m x m column-major)
+ * and N as COO (as ca_bilinear_create).  Plays the role of  Bfact = lu(B)  and the closures f, Df
+ * (ODEModels.jl:54-58): B is factored once (block-diagonal LU with partial pivoting) and folded into
+ * the operators,  L1 = B^-1 A1,  L2 = B^-1 A2,  Q = B^-1 N,  so that
+ *     f(x,R) = (L1 + L2/R) x + Q(x,x)
+ * is ONE pass of the batched kernel: each state is read once and written once. */
+int32_t ca_model_create(const double* B, const double* A1, const double* A2, int64_t m,
+                        const int64_t* ijk, const double* val, int64_t nnz, ca_model** out);
+int32_t ca_model_destroy(ca_model* h);
+int32_t ca_model_info(const ca_model* h, int64_t* m, int64_t* nnz_q_sym, int64_t* nnz_lin,
+                      int64_t* npairs, int64_t* padded_fma_per_state, int64_t* nblocks_B);
+/* f(x,R) = Bfact \ (A1*x + (1/R)*(A2*x) + N(x))  -- ODEModels.jl:57.  Host pointers, one state. */
+int32_t ca_model_rhs(ca_model* h, const double* x, double R, double* out);
+/* f(x_s,R) for every row of X (nstates x m column-major, host) */
+int32_t ca_model_rhs_batched(ca_model* h, const double* X, int64_t nstates, double R, double* OUT);
+int32_t ca_model_rhs_batched_dev(ca_model* h, const double* dX, int64_t nstates, int64_t ldx, double R,
+                                 double* dOUT, int64_t ldo, void* stream);
+/* Df(x,R) = Bfact \ (A1 + (1/R)*A2 + derivative(N,x))  -- ODEModels.jl:58.  m x m column-major. */
+int32_t ca_model_jac(ca_model* h, const double* x, double R, double* Df);
+int32_t ca_model_jac_dev(ca_model* h, const double* dx, double R, double* dDf, void* stream);
+/* Df(x_s,R) v_s for ensembles, matrix-free */
+int32_t ca_model_jvp_batched_dev(ca_model* h, const double* dX, const double* dV, int64_t nstates,
+                                 int64_t ld, double R, double* dOUT, int64_t ldo, void* stream);
 
 /* ---- diagnostics (host only, no device needed) ---------------------------------------------- */
 /* Packs a COO operator exactly as ca_bilinear_create does, expands the packed tiles back into

@@ -1,0 +1,85 @@
+"""Parity of the folded model RHS / Jacobian (ODEModels.jl:57-58) against the oracle's closures."""
+import numpy as np
+import pytest
+
+import __graft_entry__ as g
+from conftest import read_asc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ca():
+    return g.load_package()
+
+
+def relerr(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope="module", params=[((1, 1, 3), False), ((1, 1, 3), True), ((1, 2, 3), False), ((2, 2, 3), False)],
+                ids=["17d", "17d-normalized", "27d", "44d"])
+def pair(request, ca, nagata_H):
+    from oracle.model import ODEModel
+    JKL, normalize = request.param
+    ref = ODEModel(1.0, 2.0, *JKL, nagata_H, normalize=normalize)
+    dev = ca.ModelOperators(ref.B, ref.A1, ref.A2, ref.N.ijk, ref.N.val)
+    return dev, ref
+
+
+def test_rhs_single_and_batched(pair):
+    dev, ref = pair
+    rng = np.random.default_rng(0)
+    X = 0.1 * rng.standard_normal((1000, dev.m))
+    for R in (200.0, 400.0, 200.0):
+        want = np.stack([ref.f(x, R) for x in X[:50]])
+        # f = B^-1(...): forward error scales with cond(B); the bound is 1e-13 * max(1, cond/10)
+        tol = 1e-13 * max(1.0, np.linalg.cond(ref.B) / 10)
+        assert relerr(dev.f(X[0], R), want[0]) < tol
+        got = dev.f(X, R)
+        assert relerr(got[:50], want) < tol
+        # backward parity, independent of conditioning: B f = A1 x + A2 x / R + N(x)
+        rhs = np.stack([ref.A1 @ x + (ref.A2 @ x) / R + ref.N(x) for x in X[:50]])
+        assert relerr(got[:50] @ ref.B.T, rhs) < 1e-13
+
+
+def test_jacobian(pair):
+    dev, ref = pair
+    x = 0.1 * np.random.default_rng(1).standard_normal(dev.m)
+    tol = 1e-13 * max(1.0, np.linalg.cond(ref.B) / 10)
+    assert relerr(dev.Df(x, 200.0), ref.Df(x, 200.0)) < tol
+    # finite-difference check (Hookstep.jl:77-93)
+    from oracle.hookstep import Df_finitediff
+    fd = Df_finitediff(lambda z: dev.f(z, 200.0), x)
+    assert relerr(fd, dev.Df(x, 200.0)) < 1e-5
+
+
+def test_jvp(pair, ca):
+    import torch
+    dev, ref = pair
+    rng = np.random.default_rng(2)
+    X = 0.1 * rng.standard_normal((40, dev.m))
+    V = rng.standard_normal((40, dev.m))
+    dX = torch.from_numpy(X.T.copy()).cuda().t()
+    dV = torch.from_numpy(V.T.copy()).cuda().t()
+    got = dev.Df_action(dX, dV, 250.0).cpu().numpy()
+    want = np.stack([ref.Df(X[s], 250.0) @ V[s] for s in range(40)])
+    assert relerr(got, want) < 1e-13 * max(1.0, np.linalg.cond(ref.B) / 10)
+
+
+def test_known_equilibrium_17d(ca, known, nagata_H):
+    """test/runtests.jl:40-59 through the CUDA path."""
+    from oracle.model import ODEModel
+    ref = ODEModel(1.0, 2.0, 1, 1, 3, nagata_H)
+    dev = ca.ModelOperators(ref.B, ref.A1, ref.A2, ref.N.ijk, ref.N.val)
+    x = np.array(known["m17_unnormalized"]["xeqb"])
+    assert np.linalg.norm(dev.f(x, 200.0)) / np.linalg.norm(x) < 1e-10
+
+
+def test_27d_residual_of_shipped_guess(ca, known, nagata_H):
+    """continue-eqb.ipynb:115-120 through the CUDA path."""
+    from oracle.model import ODEModel
+    ref = ODEModel(1.0, 2.0, 1, 2, 3, nagata_H)
+    dev = ca.ModelOperators(ref.B, ref.A1, ref.A2, ref.N.ijk, ref.N.val)
+    xg = read_asc(known["m27"]["guess_file"])
+    assert abs(np.linalg.norm(dev.f(xg, 200)) / known["m27"]["norm_f_guess_R200"] - 1) < 1e-12
