@@ -69,7 +69,7 @@ def test_components_match_oracle_basis_set(normalize, nagata_H):
             if f[c].coeff == 0:
                 assert T["coef"][n, c] == 0
                 continue
-            assert abs(T["coef"][n, c] / f[c].coeff - 1) < 2e-15
+            assert abs(T["coef"][n, c] / f[c].coeff - 1) < 1e-14  # the reference norm cancels in monomial form
             assert T["jx"][n, c] == f[c].ejx.waveindex and T["kz"][n, c] == f[c].ekz.waveindex
             assert T["l"][n, c] == ijkl[n, 3]
 
