@@ -10,7 +10,8 @@ The directory name contains a dot, so load it with ``__graft_entry__.load_packag
 """
 from ._lib import CloudAtlasError, LIB_PATH, lib  # noqa: F401
 from .bilinear import SparseBilinear, derivative, ensemble_empty, sparse  # noqa: F401
-from .model import ModelOperators  # noqa: F401
+from .model import ModelOperators, ODEModel  # noqa: F401
+from .assembly import AssemblySlab, all_gather_slabs, assemble, row_partition  # noqa: F401
 from .basis import Symmetry, basisComponents, basisIndices, halfbox_symmetries, symmetric  # noqa: F401
 
 
@@ -26,3 +27,13 @@ def device_info():
     lib.ca_device_info.restype = C.c_int32
     check(lib.ca_device_info(C.byref(nd), C.byref(sm), C.byref(ma), C.byref(mi), name, 128))
     return {"ndevices": nd.value, "sms": sm.value, "cc": (ma.value, mi.value), "name": name.value.decode()}
+
+
+def measure_fp64_peak():
+    """(DMMA TFLOP/s, DFMA TFLOP/s) of the current device."""
+    import ctypes as C
+    from ._lib import _sig, c_f64p, check
+    fn = _sig("ca_measure_fp64_peak", c_f64p, c_f64p)
+    a, b = C.c_double(), C.c_double()
+    check(fn(C.byref(a), C.byref(b)))
+    return a.value, b.value

@@ -1,0 +1,143 @@
+"""Galerkin assembly -- the constructor half of src/ODEModels.jl:22-51 over the C ABI, sharded by output
+mode i across ranks with one all-gather (torch.distributed: NCCL on GPUs, gloo in the CPU tests)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import CloudAtlasError, _sig, c_f64p, c_i64p, check, vp
+
+_assemble = _sig("ca_assemble", C.c_double, C.c_double, c_i64p, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
+                 C.POINTER(vp))
+_destroy = _sig("ca_assembly_destroy", vp)
+_info = _sig("ca_assembly_info", vp, c_i64p, c_i64p, c_i64p, c_i64p, c_f64p)
+_get_linear = _sig("ca_assembly_get_linear", vp, c_f64p, c_f64p, c_f64p)
+_get_coo = _sig("ca_assembly_get_coo", vp, c_i64p, c_f64p)
+_get_linear_dev = _sig("ca_assembly_get_linear_dev", vp, vp, vp, vp, vp)
+_get_coo_dev = _sig("ca_assembly_get_coo_dev", vp, vp, vp, vp, vp, vp)
+
+
+def row_partition(m: int, world: int):
+    """Contiguous ranges of output modes per rank: rank r owns [bounds[r], bounds[r+1])."""
+    base, extra = divmod(m, world)
+    bounds = [0]
+    for r in range(world):
+        bounds.append(bounds[-1] + base + (1 if r < extra else 0))
+    return bounds
+
+
+class AssemblySlab:
+    """Rows [row_begin, row_end) of B, A1, A2 and the N entries with i in that range, on the device."""
+
+    def __init__(self, alpha, gamma, ijkl, normalize=False, row_begin=0, row_end=None):
+        ijkl = np.asfortranarray(ijkl, dtype=np.int64)
+        if ijkl.ndim != 2 or ijkl.shape[1] != 4:
+            raise CloudAtlasError(1, "ijkl must have four columns")
+        self.m = ijkl.shape[0]
+        row_end = self.m if row_end is None else row_end
+        h = vp()
+        check(_assemble(float(alpha), float(gamma), ijkl.ctypes.data_as(c_i64p), self.m, int(bool(normalize)),
+                        int(row_begin), int(row_end), C.byref(h)))
+        self._h = h
+        v = [C.c_int64() for _ in range(4)]
+        sec = C.c_double()
+        check(_info(h, *[C.byref(a) for a in v], C.byref(sec)))
+        _, self.row_begin, self.row_end, self.nnz = (a.value for a in v)
+        self.device_seconds = sec.value
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _destroy(h)
+            self._h = None
+
+    def linear_host(self):
+        B, A1, A2 = (np.zeros((self.m, self.m), order="F") for _ in range(3))
+        check(_get_linear(self._h, *(a.ctypes.data_as(c_f64p) for a in (B, A1, A2))))
+        return B, A1, A2
+
+    def coo_host(self):
+        ijk = np.zeros((self.nnz, 3), dtype=np.int64, order="F")
+        val = np.zeros(self.nnz)
+        check(_get_coo(self._h, ijk.ctypes.data_as(c_i64p), val.ctypes.data_as(c_f64p)))
+        return ijk, val
+
+    def to_torch(self):
+        """Slab as CUDA tensors: linear [3, rows, m] float64 (row-major), idx [3, nnz] int64, val [nnz]."""
+        import torch
+        rows = self.row_end - self.row_begin
+        lin = torch.empty((3, rows, self.m), dtype=torch.float64, device="cuda")
+        idx = torch.empty((3, self.nnz), dtype=torch.int64, device="cuda")
+        val = torch.empty((self.nnz,), dtype=torch.float64, device="cuda")
+        st = vp(torch.cuda.current_stream().cuda_stream)
+        check(_get_linear_dev(self._h, vp(lin[0].data_ptr()), vp(lin[1].data_ptr()), vp(lin[2].data_ptr()), st))
+        check(_get_coo_dev(self._h, vp(idx[0].data_ptr()), vp(idx[1].data_ptr()), vp(idx[2].data_ptr()),
+                           vp(val.data_ptr()), st))
+        return lin, idx, val
+
+
+def all_gather_slabs(lin, idx, val, m, group=None):
+    """The one collective of the assembly path: every rank ends up with the full operators.
+
+    lin: [3, rows_r, m], idx: [3, nnz_r], val: [nnz_r] torch tensors of this rank (any device the
+    process group supports).  Slab sizes differ per rank, so sizes are exchanged first and the payload
+    is padded to the largest slab.  Concatenation in rank order reproduces the reference's
+    lexicographic (i,j,k) order because ranks own contiguous, increasing ranges of i."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = val.device
+    sizes = torch.tensor([lin.shape[1], val.shape[0]], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = torch.stack(all_sizes).cpu()
+    max_rows, max_nnz = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
+    # one payload per dtype: [3*max_rows*m] doubles + [max_nnz] doubles ; [3*max_nnz] int64
+    fbuf = torch.zeros(3 * max_rows * m + max_nnz, dtype=torch.float64, device=dev)
+    fbuf[:3 * max_rows * m].view(3, max_rows, m)[:, :lin.shape[1]] = lin
+    fbuf[3 * max_rows * m:3 * max_rows * m + val.shape[0]] = val
+    ibuf = torch.zeros(3 * max_nnz, dtype=torch.int64, device=dev)
+    ibuf.view(3, max_nnz)[:, :idx.shape[1]] = idx
+    fall = torch.empty(world * fbuf.numel(), dtype=torch.float64, device=dev)
+    iall = torch.empty(world * ibuf.numel(), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(fall, fbuf, group=group)
+    dist.all_gather_into_tensor(iall, ibuf, group=group)
+    fall = fall.view(world, -1)
+    iall = iall.view(world, 3, max_nnz)
+    lins, idxs, vals = [], [], []
+    for r in range(world):
+        rows_r, nnz_r = int(all_sizes[r, 0]), int(all_sizes[r, 1])
+        lins.append(fall[r, :3 * max_rows * m].view(3, max_rows, m)[:, :rows_r])
+        vals.append(fall[r, 3 * max_rows * m:3 * max_rows * m + nnz_r])
+        idxs.append(iall[r, :, :nnz_r])
+    return torch.cat(lins, dim=1), torch.cat(idxs, dim=1), torch.cat(vals)
+
+
+def assemble(alpha, gamma, ijkl, normalize=False, group=None, distributed=None):
+    """Full B, A1, A2 (m x m, column-major numpy) and N's COO (ijk nnz x 3 1-based, val) on every rank.
+
+    With torch.distributed initialised (or ``distributed=True``) each rank assembles its range of output
+    modes on its own GPU and the slabs are exchanged with one all-gather; otherwise a single device does
+    everything.  Returns (B, A1, A2, ijk, val, stats)."""
+    import torch
+    m = np.asarray(ijkl).shape[0]
+    if distributed is None:
+        import torch.distributed as dist
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if not distributed:
+        slab = AssemblySlab(alpha, gamma, ijkl, normalize)
+        B, A1, A2 = slab.linear_host()
+        ijk, val = slab.coo_host()
+        return B, A1, A2, ijk, val, {"device_seconds": slab.device_seconds, "world": 1, "nnz_local": slab.nnz}
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    bounds = row_partition(m, world)
+    slab = AssemblySlab(alpha, gamma, ijkl, normalize, bounds[rank], bounds[rank + 1])
+    lin, idx, val = slab.to_torch()
+    lin, idx, val = all_gather_slabs(lin, idx, val, m, group)
+    lin = lin.cpu().numpy()
+    B, A1, A2 = (np.asfortranarray(lin[q]) for q in range(3))
+    ijk = np.asfortranarray(idx.t().cpu().numpy())
+    return B, A1, A2, ijk, val.cpu().numpy(), {"device_seconds": slab.device_seconds, "world": world,
+                                               "nnz_local": slab.nnz}

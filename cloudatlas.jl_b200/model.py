@@ -61,13 +61,16 @@ class ModelOperators:
         return dict(zip(("m", "nnz_q_sym", "nnz_lin", "npairs", "padded_fma_per_state", "nblocks_B"),
                         (a.value for a in v)))
 
-    def f(self, x, R):
+    def f(self, x, R, out=None):
         if _is_torch(x):
             single = x.dim() == 1
             X = x.reshape(1, -1) if single else x
             X, n, ld = _colmajor_ensemble(X)
-            OUT = ensemble_empty(n, self.m, X.device)
-            check(_rhs_b_dev(self._h, vp(X.data_ptr()), n, ld, float(R), vp(OUT.data_ptr()), n, _stream()))
+            OUT = ensemble_empty(n, self.m, X.device) if out is None else out
+            _, n_o, ldo = _colmajor_ensemble(OUT)
+            if n_o != n or OUT.shape[1] != self.m:
+                raise CloudAtlasError(1, "out must be nstates x m, column-major")
+            check(_rhs_b_dev(self._h, vp(X.data_ptr()), n, ld, float(R), vp(OUT.data_ptr()), ldo, _stream()))
             return OUT.reshape(-1) if single else OUT
         x = np.asarray(x, dtype=np.float64)
         if x.ndim == 1:
@@ -108,3 +111,33 @@ class ModelOperators:
         OUT = ensemble_empty(n, self.m, X.device)
         check(_jvp_b_dev(self._h, vp(X.data_ptr()), vp(V.data_ptr()), n, ld, float(R), vp(OUT.data_ptr()), n, _stream()))
         return OUT
+
+
+class ODEModel(ModelOperators):
+    """ODEModel(alpha, gamma, J, K, L, H; normalize=false) -- ODEModels.jl:6-61.
+
+    Fields as in the reference struct: ``alpha, gamma, H, ijkl, Psi, B, A1, A2, N, f, Df`` (``Psi`` is the
+    tabular basis, ``Bfact`` is folded into the device operators).  The constructor is the assembly
+    driver: index set -> basis tables -> Galerkin assembly on the GPU(s) -> device packing."""
+
+    def __init__(self, alpha, gamma, J, K, L, H, normalize=False, ijkl=None, group=None, verbose=False):
+        from .assembly import assemble
+        from .basis import basisComponents, basisIndices
+        self.alpha, self.gamma = float(alpha), float(gamma)
+        self.H = None if H is None else list(H)
+        self.ijkl = basisIndices(J, K, L, self.H) if ijkl is None else np.asfortranarray(ijkl, dtype=np.int64)
+        m = self.ijkl.shape[0]
+        if verbose:  # the reference prints these (ODEModels.jl:25-26)
+            print(f"J,K,L,m == {J},{K},{L},{m}")
+            print(f"(2J+1)(2K+1)(2L+1) + 1 == {(2 * J + 1) * (2 * K + 1) * (2 * L + 1) + 1}")
+        self.Psi = basisComponents(self.alpha, self.gamma, self.ijkl, normalize)
+        B, A1, A2, ijk, val, self.assembly_stats = assemble(self.alpha, self.gamma, self.ijkl, normalize, group)
+        super().__init__(B, A1, A2, ijk, val)
+        self._N = None
+
+    @property
+    def N(self) -> SparseBilinear:
+        """The unfolded quadratic operator as a SparseBilinear (packed on first use)."""
+        if self._N is None:
+            self._N = SparseBilinear(self.ijk, self.val, self.m)
+        return self._N

@@ -46,6 +46,7 @@ typedef struct ca_symmetry {
 
 typedef struct ca_bilinear ca_bilinear; /* SparseBilinear{Float64}, packed on the device */
 typedef struct ca_model ca_model;       /* ODEModel{Float64}: B, A1, A2, N and the folded operators */
+typedef struct ca_assembly ca_assembly; /* result of a Galerkin assembly (a slab of output modes) */
 
 /* ---- library ------------------------------------------------------------------------------ */
 const char* ca_last_error(void);
@@ -57,6 +58,10 @@ int32_t ca_device_info(int32_t* ndevices, int32_t* sm_count, int32_t* cc_major, 
  * copies with kernels (Julia: call on the Array's pointer; optional, results identical) */
 int32_t ca_pin(void* host_ptr, int64_t bytes);
 int32_t ca_unpin(void* host_ptr);
+/* FP64 roofline denominators of the current device, measured with register-resident loops of
+ * mma.sync.m8n8k4.f64 (DMMA) and of DFMA, best of a few repetitions (MEASURED_PEAKS.json has no FP64
+ * entry; SURVEY.md section 8d asks for an on-box measurement in the same run). */
+int32_t ca_measure_fp64_peak(double* dmma_tflops, double* dfma_tflops);
 /* number of kernels launched by this library in the calling process so far (bench bookkeeping) */
 int64_t ca_launch_count(void);
 
@@ -128,6 +133,31 @@ int32_t ca_model_jac_dev(ca_model* h, const double* dx, double R, double* dDf, v
 /* Df(x_s,R) v_s for ensembles, matrix-free */
 int32_t ca_model_jvp_batched_dev(ca_model* h, const double* dX, const double* dV, int64_t nstates,
                                  int64_t ld, double R, double* dOUT, int64_t ldo, void* stream);
+
+/* ---- Galerkin assembly (reference: src/ODEModels.jl:31-51 over src/BasisFunctions.jl) -------- */
+/* Computes, on the device, for the output modes i in [row_begin, row_end) (0-based, half-open):
+ *   B_ij  = <Psi_i, Psi_j>                                  ODEModels.jl:32
+ *   A1_ij = -<Psi_i, y d/dx Psi_j> - <Psi_i, [v_j,0,0]>     ODEModels.jl:33-36
+ *   A2_ij = <Psi_i, laplacian Psi_j>                        ODEModels.jl:35
+ *   N_ijk = -<Psi_i, (Psi_j . grad) Psi_k>                  ODEModels.jl:39-49
+ * and N's COO in lexicographic (i,j,k) order (SparseBilinear.jl:24-49).  Inner products are exact
+ * Gauss-Legendre contractions in y times closed-form Fourier averages (no monomial coefficients, so
+ * no loss of digits with L).  An N entry is kept iff |N| > 1e-15 (the reference's cut,
+ * ODEModels.jl:46) and |N| > 1e-11 * sum|terms| (discards entries that vanish by cancellation).
+ * Slabs of different ranks concatenate, in rank order, to the full operator (sharding by i). */
+int32_t ca_assemble(double alpha, double gamma, const int64_t* ijkl /* m x 4 column-major */, int64_t m,
+                    int32_t normalize, int64_t row_begin, int64_t row_end, ca_assembly** out);
+int32_t ca_assembly_destroy(ca_assembly* h);
+int32_t ca_assembly_info(const ca_assembly* h, int64_t* m, int64_t* row_begin, int64_t* row_end,
+                         int64_t* nnz, double* device_seconds);
+/* host copies: B, A1, A2 are m x m column-major, only rows [row_begin,row_end) are written */
+int32_t ca_assembly_get_linear(ca_assembly* h, double* B, double* A1, double* A2);
+/* ijk: nnz x 3 column-major, 1-based; val: nnz */
+int32_t ca_assembly_get_coo(ca_assembly* h, int64_t* ijk, double* val);
+/* device copies for the all-gather: linear slabs are (row_end-row_begin) x m ROW-major */
+int32_t ca_assembly_get_linear_dev(ca_assembly* h, double* dB, double* dA1, double* dA2, void* stream);
+int32_t ca_assembly_get_coo_dev(ca_assembly* h, int64_t* d_i, int64_t* d_j, int64_t* d_k, double* d_val,
+                                void* stream);
 
 /* ---- diagnostics (host only, no device needed) ---------------------------------------------- */
 /* Packs a COO operator exactly as ca_bilinear_create does, expands the packed tiles back into

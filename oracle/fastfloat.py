@@ -101,9 +101,35 @@ def assemble_N_float(alpha, gamma, ijkl: np.ndarray, rows=None, tables: FloatTab
     return np.concatenate(out_ijk).astype(np.int64), np.concatenate(out_val)
 
 
-def assemble_linear_float(alpha, gamma, ijkl: np.ndarray):
-    """B, A1, A2 as float64 from the exact-rational assembly (cheap: m^2 entries)."""
-    from .exact import assemble_linear_exact
-    B, A1, A2 = assemble_linear_exact(alpha, gamma, ijkl)
-    conv = np.vectorize(float, otypes=[np.float64])
-    return conv(B), conv(A1), conv(A2)
+def assemble_linear_float(alpha, gamma, ijkl: np.ndarray, tables: FloatTables | None = None):
+    """B, A1, A2 as float64, vectorised over (i,j), from exact-rational wall-normal tables
+    (ODEModels.jl:31-36; same formulas as oracle/exact.py assemble_linear_exact)."""
+    from .exact import _Y2_third
+    t = tables or FloatTables(alpha, gamma, ijkl)
+    a, g = float(Fraction(alpha)), float(Fraction(gamma))
+    m, J, K, T = t.m, t.J, t.K, t.T
+    npid = 3 * (t.L + 1)
+    Y2 = np.array([[float(T.Y2(p, q)) for q in range(npid)] for p in range(npid)])
+    Y2y = np.array([[float(T.Y2(p, q, ypow=1)) for q in range(npid)] for p in range(npid)])
+    # <S_p, (S_q)''> for q = (l, d): d+2 <= 2 is a table entry, d = 1 needs the third derivative
+    Y2pp = np.zeros((npid, npid))
+    for p in range(npid):
+        for l in range(t.L + 1):
+            Y2pp[p, 3 * l + 0] = float(T.Y2(p, 3 * l + 2))
+            Y2pp[p, 3 * l + 1] = float(_Y2_third(T, p, l))
+    B = np.zeros((m, m)); A1 = np.zeros((m, m)); A2 = np.zeros((m, m))
+    for c in range(3):
+        ci, cj = t.coef[:, c][:, None], t.coef[:, c][None, :]
+        xi, xj = t.jx[:, c][:, None] + J, t.jx[:, c][None, :] + J
+        zi, zj = t.kz[:, c][:, None] + K, t.kz[:, c][None, :] + K
+        pi, pj = t.pid[:, c][:, None], t.pid[:, c][None, :]
+        F = ci * cj * t.X2[xi, xj, 0] * t.Z2[zi, zj, 0]
+        y2 = Y2[pi, pj]
+        k2 = (a * t.jx[:, c][None, :]) ** 2 + (g * t.kz[:, c][None, :]) ** 2
+        B += F * y2
+        A2 += F * (Y2pp[pi, pj] - k2 * y2)
+        A1 -= ci * cj * t.X2[xi, xj, 1] * t.Z2[zi, zj, 0] * Y2y[pi, pj]
+    ci, cj = t.coef[:, 0][:, None], t.coef[:, 1][None, :]
+    A1 -= (ci * cj * t.X2[t.jx[:, 0][:, None] + J, t.jx[:, 1][None, :] + J, 0]
+           * t.Z2[t.kz[:, 0][:, None] + K, t.kz[:, 1][None, :] + K, 0] * Y2[t.pid[:, 0][:, None], t.pid[:, 1][None, :]])
+    return B, A1, A2

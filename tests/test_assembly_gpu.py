@@ -1,0 +1,130 @@
+"""Parity of the CUDA Galerkin assembly (ODEModels.jl:31-51) against the oracle.
+L and Q within 1e-12 relative (max-abs difference over max-abs reference); sparsity pattern, order and
+index sets bit-exact (north_star)."""
+import numpy as np
+import pytest
+
+import __graft_entry__ as g
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ca():
+    return g.load_package()
+
+
+def maxrel(a, b):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b))
+
+
+def lib_H(ca):
+    sx, sy, sz, tx, tz = ca.halfbox_symmetries()
+    return [sx * sy * sz, sz * tx * tz]
+
+
+@pytest.mark.parametrize("JKL", [(1, 1, 3), (1, 2, 3), (2, 2, 3)], ids=["17d", "27d", "44d"])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_small_models_against_float_restatement_and_exact(ca, nagata_H, JKL, normalize):
+    from oracle.exact import assemble_N_exact
+    from oracle.model import ODEModel as Ref
+    ref = Ref(1.0, 2.0, *JKL, nagata_H, normalize=normalize)       # the reference's Float64 algorithm
+    dev = ca.ODEModel(1.0, 2.0, *JKL, lib_H(ca), normalize=normalize)
+    assert np.array_equal(dev.ijkl, ref.ijkl)
+    for name in ("B", "A1", "A2"):
+        assert maxrel(getattr(dev, name), getattr(ref, name)) < TOL, name
+    # exact zeros of B (orthogonality) are reproduced exactly
+    assert np.array_equal(dev.B == 0, ref.B == 0)
+    if not normalize:
+        ijk, val = assemble_N_exact(1, 2, ref.ijkl)                  # exact pattern (396 / 1500 / 5654)
+        assert np.array_equal(dev.ijk, ijk)
+        assert maxrel(dev.val, np.array([float(v) for v in val])) < TOL
+    # against the Float64 restatement: same values on the common pattern, extras of the restatement are noise
+    got = {tuple(r): v for r, v in zip(dev.ijk.tolist(), dev.val)}
+    scale = np.max(np.abs(ref.N.val))
+    for r, v in zip(ref.N.ijk.tolist(), ref.N.val):
+        assert abs(got.get(tuple(r), 0.0) - v) < TOL * scale
+    assert len(got) <= ref.N.nnz
+
+
+def test_nnz_of_the_baseline_configs(ca):
+    H = lib_H(ca)
+    for JKL, m, nnz in [((1, 1, 3), 17, 396), ((1, 2, 3), 27, 1500), ((2, 2, 3), 44, 5654)]:
+        slab = ca.AssemblySlab(1.0, 2.0, ca.basisIndices(*JKL, H))
+        assert (slab.m, slab.nnz) == (m, nnz)
+
+
+def test_m307_against_exact_rational_rows(ca, nagata_H):
+    """L = 12: the reference's Float64 is off by 4e-2 here (SURVEY exec. summary); truth is the
+    exact-rational tier, checked on a sample of output rows, the vectorised tier on all of them."""
+    from oracle.exact import assemble_N_exact, assemble_linear_exact
+    from oracle.fastfloat import assemble_N_float
+    ijkl = ca.basisIndices(3, 3, 12, lib_H(ca))
+    slab = ca.AssemblySlab(1.0, 2.0, ijkl)
+    ijk, val = slab.coo_host()
+    assert slab.nnz == 1355658
+    fijk, fval = assemble_N_float(1, 2, ijkl)
+    assert np.array_equal(ijk, fijk)
+    assert maxrel(val, fval) < TOL
+    rows = [0, 5, 77, 150, 233, 306]
+    eijk, eval_ = assemble_N_exact(1, 2, ijkl, rows=rows)
+    sel = np.isin(ijk[:, 0] - 1, rows)
+    assert np.array_equal(ijk[sel], eijk)
+    ev = np.array([float(v) for v in eval_])
+    assert np.max(np.abs(val[sel] - ev)) / np.max(np.abs(ev)) < TOL
+    B, A1, A2 = slab.linear_host()
+    Be, A1e, A2e = assemble_linear_exact(1, 2, ijkl[:60])  # nested basis: leading block of the operators
+    conv = np.vectorize(float, otypes=[np.float64])
+    assert maxrel(B[:60, :60], conv(Be)) < TOL
+    assert maxrel(A1[:60, :60], conv(A1e)) < TOL
+    assert maxrel(A2[:60, :60], conv(A2e)) < TOL
+
+
+def test_row_slabs_concatenate_to_the_full_operator(ca):
+    """Sharding by output mode: emulated ranks on one GPU."""
+    ijkl = ca.basisIndices(2, 2, 3, lib_H(ca))
+    full = ca.AssemblySlab(1.0, 2.0, ijkl)
+    fB, fA1, fA2 = full.linear_host()
+    fijk, fval = full.coo_host()
+    for world in (2, 3, 8):
+        bounds = ca.row_partition(44, world)
+        slabs = [ca.AssemblySlab(1.0, 2.0, ijkl, False, bounds[r], bounds[r + 1]) for r in range(world)]
+        ijk = np.concatenate([s.coo_host()[0] for s in slabs])
+        val = np.concatenate([s.coo_host()[1] for s in slabs])
+        assert np.array_equal(ijk, fijk) and np.array_equal(val, fval)
+        B = sum(s.linear_host()[0] for s in slabs)
+        assert np.array_equal(B, fB)
+    empty = ca.AssemblySlab(1.0, 2.0, ijkl, False, 10, 10)
+    assert empty.nnz == 0
+
+
+def test_scaling_law_of_a_rescaled_basis(ca):
+    """Psi_n -> s_n Psi_n gives N'_ijk = s_i s_j s_k N_ijk; normalisation is such a rescaling."""
+    H = lib_H(ca)
+    ijkl = ca.basisIndices(2, 2, 3, H)
+    a = ca.AssemblySlab(1.0, 2.0, ijkl, False)
+    b = ca.AssemblySlab(1.0, 2.0, ijkl, True)
+    s = 1 / np.sqrt(np.diag(a.linear_host()[0]))
+    (ijk, va), (ijk2, vb) = a.coo_host(), b.coo_host()
+    assert np.array_equal(ijk, ijk2)
+    want = va * s[ijk[:, 0] - 1] * s[ijk[:, 1] - 1] * s[ijk[:, 2] - 1]
+    assert maxrel(vb, want) < 1e-13
+    assert np.allclose(np.diag(b.linear_host()[0]), 1.0, atol=1e-14)
+
+
+def test_full_model_17d_known_answers(ca, known):
+    """test/runtests.jl:40-59 and find-eqb.ipynb:135,203 end to end on the device."""
+    H = lib_H(ca)
+    model = ca.ODEModel(1.0, 2.0, 1, 1, 3, H)
+    assert len(model) == 17
+    x = np.array(known["m17_unnormalized"]["xeqb"])
+    assert np.linalg.norm(model.f(x, 200.0)) / np.linalg.norm(x) < 1e-10
+    modeln = ca.ODEModel(1.0, 2.0, 1, 1, 3, H, normalize=True)
+    assert abs(np.linalg.cond(modeln.B) / known["m17_normalized"]["cond_B"] - 1) < 1e-12
+    assert np.linalg.norm(modeln.f(np.zeros(17), 400.0)) == 0.0
+    xs = np.array(known["m17_normalized"]["xsoln_default_params"])
+    assert np.linalg.norm(modeln.f(xs, 200.0)) / np.linalg.norm(xs) < 1e-11
+    lam = np.linalg.eigvals(modeln.Df(xs, 200.0))
+    for re, im in known["m17_normalized"]["eigs_top"]:
+        assert np.min(np.abs(lam - complex(re, im))) < 1e-9
