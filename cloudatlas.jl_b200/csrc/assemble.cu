@@ -33,17 +33,42 @@ struct DevBasis {
   const double *X2, *Z2, *X3, *Z3, *Y2, *Y2y, *Y3;
 };
 
-__global__ void y3_kernel(const double* __restrict__ F, const double* __restrict__ w,
+// double-double helpers (error-free transformations): the wall-normal integrals must be accurate
+// relative to THEMSELVES, not to the size of the quadrature's terms, because N entries that vanish
+// by cancellation between components are recognised by |sum| <= 1e-11 * sum|terms|.
+struct dd { double hi, lo; };
+__device__ __forceinline__ dd dd_mul(dd a, dd b) {
+  const double p = a.hi * b.hi;
+  double e = fma(a.hi, b.hi, -p);
+  e = fma(a.hi, b.lo, e);
+  e = fma(a.lo, b.hi, e);
+  const double s = p + e;
+  return dd{s, e - (s - p)};
+}
+__device__ __forceinline__ dd dd_add(dd a, dd b) {
+  const double s = a.hi + b.hi, bb = s - a.hi;
+  double e = (a.hi - (s - bb)) + (b.hi - bb);
+  e += a.lo + b.lo;
+  const double t = s + e;
+  return dd{t, e - (t - s)};
+}
+
+__global__ void y3_kernel(const double* __restrict__ F, const double* __restrict__ Flo,
+                          const double* __restrict__ w, const double* __restrict__ wlo,
                           const int8_t* __restrict__ parity, int npid, int ny, double* __restrict__ Y3) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)npid * npid * npid;
   if (t >= total) return;
   const int r = (int)(t % npid), q = (int)((t / npid) % npid), p = (int)(t / ((int64_t)npid * npid));
-  double s = 0.0;
+  dd s{0.0, 0.0};
   if (parity[p] * parity[q] * parity[r] == 1) {  // odd integrands vanish exactly
-    for (int n = 0; n < ny; ++n) s = fma(w[n] * F[p * ny + n], F[q * ny + n] * F[r * ny + n], s);
+    for (int n = 0; n < ny; ++n) {
+      const dd fp{F[p * ny + n], Flo[p * ny + n]}, fq{F[q * ny + n], Flo[q * ny + n]},
+          fr{F[r * ny + n], Flo[r * ny + n]}, wn{w[n], wlo[n]};
+      s = dd_add(s, dd_mul(dd_mul(wn, fp), dd_mul(fq, fr)));
+    }
   }
-  Y3[t] = s;
+  Y3[t] = s.hi + s.lo;
 }
 
 // one thread per (i,j): rows slab [r0,r1) x m, row-major
@@ -209,7 +234,7 @@ int32_t ca_assemble(double alpha, double gamma, const int64_t* ijkl, int64_t m64
       const double ax = T.alpha * c.jx, gz = T.gamma * c.kz;
       k2[n] = ax * ax + gz * gz;
     }
-    DeviceBuffer<double> dcoef, dk2, dX2, dZ2, dX3, dZ3, dY2, dY2y, dY3, dF, dw;
+    DeviceBuffer<double> dcoef, dk2, dX2, dZ2, dX3, dZ3, dY2, dY2y, dY3, dF, dFlo, dw, dwlo;
     DeviceBuffer<int32_t> djx, dkz, dpid;
     DeviceBuffer<int8_t> dpar;
     dcoef.upload(coef.data(), coef.size());
@@ -225,6 +250,8 @@ int32_t ca_assemble(double alpha, double gamma, const int64_t* ijkl, int64_t m64
     dY2y.upload(T.Y2y.data(), T.Y2y.size());
     dF.upload(T.F.data(), T.F.size());
     dw.upload(T.weights.data(), T.weights.size());
+    dFlo.upload(T.Flo.data(), T.Flo.size());
+    dwlo.upload(T.wlo.data(), T.wlo.size());
     dpar.upload(T.parity.data(), T.parity.size());
     const int64_t ny3 = (int64_t)T.npid * T.npid * T.npid;
     dY3.alloc((size_t)ny3);
@@ -233,7 +260,7 @@ int32_t ca_assemble(double alpha, double gamma, const int64_t* ijkl, int64_t m64
     CA_CUDA(cudaEventCreate(&e0));
     CA_CUDA(cudaEventCreate(&e1));
     CA_CUDA(cudaEventRecord(e0));
-    y3_kernel<<<(unsigned)((ny3 + 255) / 256), 256>>>(dF.ptr, dw.ptr, dpar.ptr, T.npid, T.ny, dY3.ptr);
+    y3_kernel<<<(unsigned)((ny3 + 255) / 256), 256>>>(dF.ptr, dFlo.ptr, dw.ptr, dwlo.ptr, dpar.ptr, T.npid, T.ny, dY3.ptr);
     CA_CUDA(cudaGetLastError());
     count_launch();
 

@@ -97,7 +97,7 @@ void fourier_tables(double wn, int J, std::vector<double>& pair2, std::vector<do
     }
 }
 
-void gauss_legendre(int n, std::vector<double>& x, std::vector<double>& w) {
+void gauss_legendre(int n, std::vector<long double>& x, std::vector<long double>& w) {
   x.resize(n);
   w.resize(n);
   const long double pi = 3.141592653589793238462643383279503L;
@@ -115,11 +115,11 @@ void gauss_legendre(int n, std::vector<double>& x, std::vector<double>& w) {
       z -= dz;
       if (fabsl(dz) < 1e-19L) break;
     }
-    x[i] = (double)-z;
-    x[n - 1 - i] = (double)z;
-    w[i] = w[n - 1 - i] = (double)(2 / ((1 - z * z) * pp * pp));
+    x[i] = -z;
+    x[n - 1 - i] = z;
+    w[i] = w[n - 1 - i] = 2 / ((1 - z * z) * pp * pp);
   }
-  if (n & 1) x[n / 2] = 0.0;
+  if (n & 1) x[n / 2] = 0.0L;
 }
 
 }  // namespace
@@ -180,14 +180,15 @@ BasisTables build_tables(double alpha, double gamma, const int64_t* ijkl, int64_
   const int L = T.L;
   T.npid = 4 * (L + 1);
   T.ny = (3 * (L + 3)) / 2 + 2;  // exact for degree 3(L+3)+1 <= 2 ny - 1
-  gauss_legendre(T.ny, T.nodes, T.weights);
-  for (auto& w : T.weights) w *= 0.5;  // inner products are (1/2) int_{-1}^{1}   (BasisFunctions.jl:284)
-  T.F.assign((size_t)T.npid * T.ny, 0.0);
+  std::vector<long double> yl, wl;
+  gauss_legendre(T.ny, yl, wl);
+  for (auto& w : wl) w *= 0.5L;  // inner products are (1/2) int_{-1}^{1}   (BasisFunctions.jl:284)
+  std::vector<long double> Fl((size_t)T.npid * T.ny, 0.0L);
   T.parity.assign(T.npid, 0);
   for (int l = 0; l <= L; ++l)
     for (int d = 0; d < 4; ++d) T.parity[4 * l + d] = (int8_t)(((l + 1 + d) % 2 == 0) ? 1 : -1);
   for (int q = 0; q < T.ny; ++q) {
-    const long double y = T.nodes[q];
+    const long double y = yl[q];
     // Legendre values and first three derivatives: P'_n = P'_{n-2} + (2n-1) P_{n-1}, same one order up
     std::vector<long double> P(L + 1, 0), P1(L + 1, 0), P2(L + 1, 0), P3(L + 1, 0);
     P[0] = 1;
@@ -199,17 +200,31 @@ BasisTables build_tables(double alpha, double gamma, const int64_t* ijkl, int64_
       P3[n] = P3[n - 2] + (2 * n - 1) * P2[n - 1];
     }
     const long double u0 = (1 - y * y) * (1 - y * y), u1 = -4 * y + 4 * y * y * y, u2 = -4 + 12 * y * y, u3 = 24 * y;
-    T.F[(size_t)0 * T.ny + q] = (double)(y - y * y * y / 3);
-    T.F[(size_t)1 * T.ny + q] = (double)(1 - y * y);
-    T.F[(size_t)2 * T.ny + q] = (double)(-2 * y);
-    T.F[(size_t)3 * T.ny + q] = -2.0;
+    Fl[(size_t)0 * T.ny + q] = y - y * y * y / 3;
+    Fl[(size_t)1 * T.ny + q] = 1 - y * y;
+    Fl[(size_t)2 * T.ny + q] = -2 * y;
+    Fl[(size_t)3 * T.ny + q] = -2.0L;
     for (int l = 1; l <= L; ++l) {
       const long double p = P[l - 1], p1 = P1[l - 1], p2 = P2[l - 1], p3 = P3[l - 1];
-      T.F[(size_t)(4 * l + 0) * T.ny + q] = (double)(u0 * p);
-      T.F[(size_t)(4 * l + 1) * T.ny + q] = (double)(u1 * p + u0 * p1);
-      T.F[(size_t)(4 * l + 2) * T.ny + q] = (double)(u2 * p + 2 * u1 * p1 + u0 * p2);
-      T.F[(size_t)(4 * l + 3) * T.ny + q] = (double)(u3 * p + 3 * u2 * p1 + 3 * u1 * p2 + u0 * p3);
+      Fl[(size_t)(4 * l + 0) * T.ny + q] = u0 * p;
+      Fl[(size_t)(4 * l + 1) * T.ny + q] = u1 * p + u0 * p1;
+      Fl[(size_t)(4 * l + 2) * T.ny + q] = u2 * p + 2 * u1 * p1 + u0 * p2;
+      Fl[(size_t)(4 * l + 3) * T.ny + q] = u3 * p + 3 * u2 * p1 + 3 * u1 * p2 + u0 * p3;
     }
+  }
+  T.nodes.resize(T.ny);
+  T.weights.resize(T.ny);
+  T.wlo.resize(T.ny);
+  for (int q = 0; q < T.ny; ++q) {
+    T.nodes[q] = (double)yl[q];
+    T.weights[q] = (double)wl[q];
+    T.wlo[q] = (double)(wl[q] - (long double)T.weights[q]);
+  }
+  T.F.resize(Fl.size());
+  T.Flo.resize(Fl.size());
+  for (size_t e = 0; e < Fl.size(); ++e) {
+    T.F[e] = (double)Fl[e];
+    T.Flo[e] = (double)(Fl[e] - (long double)T.F[e]);
   }
   T.Y2.assign((size_t)T.npid * T.npid, 0.0);
   T.Y2y.assign((size_t)T.npid * T.npid, 0.0);
@@ -217,9 +232,9 @@ BasisTables build_tables(double alpha, double gamma, const int64_t* ijkl, int64_
     for (int q = 0; q < T.npid; ++q) {
       long double s = 0, sy = 0;
       for (int n = 0; n < T.ny; ++n) {
-        const long double t = (long double)T.weights[n] * T.F[(size_t)p * T.ny + n] * T.F[(size_t)q * T.ny + n];
+        const long double t = wl[n] * Fl[(size_t)p * T.ny + n] * Fl[(size_t)q * T.ny + n];
         s += t;
-        sy += t * T.nodes[n];
+        sy += t * yl[n];
       }
       const int par = T.parity[p] * T.parity[q];
       T.Y2[(size_t)p * T.npid + q] = par == 1 ? (double)s : 0.0;    // odd integrand: exactly zero

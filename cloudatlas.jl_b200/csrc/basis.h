@@ -31,7 +31,9 @@ struct BasisTables {
   // wall-normal tables over pid = 4*l + d, d = 0..3
   int npid = 0, ny = 0;
   std::vector<double> nodes, weights;  // Gauss-Legendre on [-1,1]; weights include the 1/2 of the average
-  std::vector<double> F;               // [npid][ny] values of S_l^(d) at the nodes
+  std::vector<double> F;               // [npid][ny] values of S_l^(d) at the nodes (hi part)
+  std::vector<double> Flo, wlo;        // low parts: F + Flo and weights + wlo carry the 64-bit mantissa
+                                       // of the host's long-double evaluation (double-double on the GPU)
   std::vector<int8_t> parity;          // [npid] +1 even / -1 odd
   std::vector<double> Y2, Y2y;         // [npid][npid]: <F_p F_q>, <y F_p F_q>  (exact zeros by parity)
   // Fourier tables, index j+J (k+K): pair  <E_a, d^d E_b>  [n][n][2],  triple  <E_a, E_b d^d E_c>  [n][n][n][2]
