@@ -245,7 +245,7 @@ extern "C" int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64
         for (int k = 0; k < 4 * T.nks; ++k) {
           const uint32_t pr = P.pairs[(size_t)T.ks_begin * 4 + k];
           const double v = P.vals[(size_t)T.vals_off + ((size_t)(k / 4) * T.nt + n / 8) * 32 + (n % 8) * 4 + k % 4];
-          if (v != 0.0) got.push_back({row, (int32_t)(pr & 0xffff), (int32_t)(pr >> 16), v});
+          if (v != 0.0) got.push_back({row, (int32_t)(pr & 0x7fff), (int32_t)(pr >> 16), v});
         }
       }
     }

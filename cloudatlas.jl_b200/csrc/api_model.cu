@@ -216,7 +216,7 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
     for (const TileDesc& T : P.tiles)
       for (int k = 0; k < 4 * T.nks; ++k) {
         const uint32_t pr = P.pairs[(size_t)T.ks_begin * 4 + k];
-        const int a = pr & 0xffff, b = pr >> 16;
+        const int a = pr & 0x7fff, b = pr >> 16;
         if (b != m || a == m) continue;
         for (int n = 0; n < T.nrows; ++n) {
           const size_t at = (size_t)T.vals_off + ((size_t)(k / 4) * T.nt + n / 8) * 32 + (n % 8) * 4 + k % 4;

@@ -11,16 +11,37 @@ void DevicePack::upload(const PackedHost& P) {
   m = P.m;
   nin = P.nin;
   ntiles = (int32_t)P.tiles.size();
+  nt2_tiles = 0;
+  for (const TileDesc& T : P.tiles) nt2_tiles += T.nt == 2;
   symmetric = P.symmetric;
   nterms = P.nterms;
   npairs_distinct = P.npairs_distinct;
   padded_fma = P.padded_fma;
   pair_products = P.pair_products;
   tiles.upload(P.tiles.data(), P.tiles.size());
-  pairs.upload(P.pairs.data(), P.pairs.size());
+  host_pairs = P.pairs;
+  for (auto& b : pairs_mt) b.release();
   vals.upload(P.vals.data(), P.vals.size());
   rows.upload(P.rows.data(), P.rows.size());
   CA_CUDA(cudaStreamSynchronize(nullptr));  // the host vectors may die after we return
+}
+
+const uint2* DevicePack::pairs_for(int mt) const {
+  const int slot = mt == 4 ? 2 : (mt == 2 ? 1 : 0);
+  DeviceBuffer<uint2>& buf = pairs_mt[slot];
+  if (!buf.ptr && !host_pairs.empty()) {
+    std::vector<uint2> w(host_pairs.size());
+    for (size_t e = 0; e < host_pairs.size(); ++e) {
+      const int a = host_pairs[e] & 0x7fff, b = host_pairs[e] >> 16;
+      const uint32_t flag = (host_pairs[e] & 0x8000u) ? kSameA : 0u;
+      if (mt == 4) w[e] = make_uint2(factor_word<4>(a) | flag, factor_word<4>(b));
+      else if (mt == 2) w[e] = make_uint2(factor_word<2>(a) | flag, factor_word<2>(b));
+      else w[e] = make_uint2(factor_word<1>(a) | flag, factor_word<1>(b));
+    }
+    buf.upload(w.data(), w.size());
+    CA_CUDA(cudaStreamSynchronize(nullptr));
+  }
+  return buf.ptr;
 }
 
 namespace {
@@ -57,7 +78,7 @@ void launch_one(const DevicePack& op, const double* dX, const double* dY, int64_
   if (per_sm < 1) fail(CA_ERR_UNSUPPORTED, "batched kernel does not fit (smem %zu B)", smem);
   const int64_t nblocks = (nstates + 8 * MT - 1) / (8 * MT);
   const int grid = (int)std::min<int64_t>(nblocks, (int64_t)device_cfg().sms * per_sm);
-  kern<<<grid, kThreads, smem, stream>>>(op.tiles.ptr, op.ntiles, op.pairs.ptr, op.vals.ptr,
+  kern<<<grid, kThreads, smem, stream>>>(op.tiles.ptr, op.ntiles, op.nt2_tiles, op.pairs_for(MT), op.vals.ptr,
                                          op.rows.ptr, op.nin, dX, dY, nstates, ldx, dOUT, ldo);
   CA_CUDA(cudaGetLastError());
   count_launch();

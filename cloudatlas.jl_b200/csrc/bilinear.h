@@ -10,11 +10,13 @@ namespace ca {
 
 // A PackedHost uploaded to the current device.
 struct DevicePack {
-  int32_t m = 0, nin = 0, ntiles = 0;
+  int32_t m = 0, nin = 0, ntiles = 0, nt2_tiles = 0;  // tiles are ordered nt == 2 first
   bool symmetric = false;
   int64_t nterms = 0, npairs_distinct = 0, padded_fma = 0, pair_products = 0;
   DeviceBuffer<TileDesc> tiles;
-  DeviceBuffer<uint32_t> pairs;
+  std::vector<uint32_t> host_pairs;      // a | flag << 15 | b << 16 (pack.h), kept to derive the per-MT form
+  mutable DeviceBuffer<uint2> pairs_mt[3];  // address-word form for MT = 1, 2, 4 (built on first use)
+  const uint2* pairs_for(int mt) const;
   DeviceBuffer<double> vals;
   DeviceBuffer<int32_t> rows;
   void upload(const PackedHost& P);

@@ -30,75 +30,124 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// State slot swizzle inside a mode's row of the shared tile.  An LDS.64 of a warp is served in two
+// half-warp phases; in a phase the four pair columns read four modes x 32 B.  XOR-ing bits 2-3 of the
+// state slot with the low bits of the mode index sends modes with distinct (mode & 3) -- e.g. the
+// consecutive second factors of an a-major pair list -- to four distinct 8-bank groups: conflict-free.
 template <int MT>
-__device__ __forceinline__ int swz(int mode) {
-  return MT >= 2 ? ((mode & 1) << 3) : 0;
+__host__ __device__ __forceinline__ int swz(int mode) {
+  return MT >= 2 ? ((mode & 3) << 2) : ((mode & 2) << 1);  // MT == 1: rows are 64 B, bit 3 comes from the row
+}
+
+// Address word of a factor (built on the host per MT, see DevicePack::pairs_for): byte offset of the
+// mode's row in the shared tile with the swizzle folded into bits 5-6, so that the lane's four loads are
+//   [w ^ r8], [(w ^ r8) ^ 64], [.. + 128], [.. ^ 64 + 128]        (r8 = 8 * (lane >> 2))
+// Bit 0 of the first factor's word is the "same first factors as the previous k-step" flag.
+template <int MT>
+__host__ __device__ __forceinline__ uint32_t factor_word(int mode) {
+  return (uint32_t)mode * (64u * MT) | ((uint32_t)swz<MT>(mode) << 3);
+}
+constexpr uint32_t kSameA = 1u;
+
+// This warp's contiguous share [k0, k1) of a tile's k-steps.
+__device__ __forceinline__ void warp_range(const TileDesc& T, int warp, int& k0, int& k1) {
+  k0 = (int)(((int64_t)T.nks * warp) / kWarps);
+  k1 = (int)(((int64_t)T.nks * (warp + 1)) / kWarps);
+}
+
+template <int NT>
+struct Prefetch {
+  uint2 pw[kPrefetch];
+  double bv[kPrefetch][NT];
+};
+
+template <int NT>
+__device__ __forceinline__ void prefetch_slot(Prefetch<NT>& pf, int u, const uint2* pp, const double* vp, int step) {
+  pf.pw[u] = __ldg(pp + (size_t)step * 4);
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) pf.bv[u][nt] = __ldg(vp + ((size_t)step * NT + nt) * 32);
+}
+
+// Loads the first kPrefetch k-steps of this warp's share of tile T (issued before the previous tile's
+// reduction so that the L2 latency hides behind its barriers).
+template <int NT>
+__device__ __forceinline__ void tile_prologue(const TileDesc& T, const uint2* __restrict__ pairs,
+                                              const double* __restrict__ vals, int warp, int lane,
+                                              Prefetch<NT>& pf) {
+  int k0, k1;
+  warp_range(T, warp, k0, k1);
+  const int n = k1 - k0;
+  if (n <= 0) return;
+  const uint2* pp = pairs + ((size_t)T.ks_begin + k0) * 4 + (lane & 3);
+  const double* vp = vals + T.vals_off + (size_t)k0 * NT * 32 + lane;
+#pragma unroll
+  for (int u = 0; u < kPrefetch; ++u) prefetch_slot<NT>(pf, u, pp, vp, min(u, n - 1));
+  pf.pw[0].x &= ~kSameA;  // the first k-step of a share always loads its first factors
+}
+
+template <int MT>
+__device__ __forceinline__ double lds_state(const char* base, uint32_t w, int mt) {
+  // mt is a compile-time constant after unrolling: (w ^ 64*(mt&1)) + 128*(mt>>1)
+  return *reinterpret_cast<const double*>(base + ((mt & 1) ? (w ^ 64u) : w) + 128u * (mt >> 1));
 }
 
 template <int MT, int NT, int MODE>
-__device__ __forceinline__ void tile_accumulate(const TileDesc& T, const uint32_t* __restrict__ pairs,
+__device__ __forceinline__ void kstep(const uint2 pw, const double (&bv)[NT], const char* xs, const char* ys,
+                                      uint32_t r8, double (&xa)[MT], double (&va)[MT],
+                                      double (&acc)[MT][NT][2]) {
+  if (!(pw.x & kSameA)) {  // warp-uniform
+    const uint32_t wa = (pw.x & ~7u) ^ r8;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      xa[mt] = lds_state<MT>(xs, wa, mt);
+      if (MODE == MODE_JVP) va[mt] = lds_state<MT>(ys, wa, mt);
+    }
+  }
+  const uint32_t wb = pw.y ^ r8;
+  double a[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    if (MODE == MODE_JVP) a[mt] = xa[mt] * lds_state<MT>(ys, wb, mt) + va[mt] * lds_state<MT>(xs, wb, mt);
+    else a[mt] = xa[mt] * lds_state<MT>(MODE == MODE_ORDERED ? ys : xs, wb, mt);
+  }
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], bv[nt]);
+}
+
+template <int MT, int NT, int MODE>
+__device__ __forceinline__ void tile_accumulate(const TileDesc& T, const uint2* __restrict__ pairs,
                                                 const double* __restrict__ vals, const double* xs,
-                                                const double* ys, int warp, int lane,
+                                                const double* ys, int warp, int lane, Prefetch<NT>& pf,
                                                 double (&acc)[MT][NT][2]) {
-  constexpr int ROW = 8 * MT;
-  const int r = lane >> 2, c = lane & 3;
+  const uint32_t r8 = 8u * (lane >> 2);
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-  const int nmine = T.nks > warp ? (T.nks - warp + kWarps - 1) / kWarps : 0;
-  if (nmine == 0) return;
-  const uint32_t* pp = pairs + (size_t)T.ks_begin * 4 + c;
-  const double* vp = vals + T.vals_off + lane;
-
-  uint32_t pr[kPrefetch];
-  double bv[kPrefetch][NT];
+  int k0, k1;
+  warp_range(T, warp, k0, k1);
+  const int n = k1 - k0;
+  if (n <= 0) return;
+  const uint2* pp = pairs + ((size_t)T.ks_begin + k0) * 4 + (lane & 3);
+  const double* vp = vals + T.vals_off + (size_t)k0 * NT * 32 + lane;
+  const char* xsb = reinterpret_cast<const char*>(xs);
+  const char* ysb = reinterpret_cast<const char*>(ys);
+  double xa[MT], va[MT];  // first factors, kept across k-steps while the pair list stays on the same a
 #pragma unroll
-  for (int u = 0; u < kPrefetch; ++u) {
-    if (u < nmine) {
-      const int ks = warp + u * kWarps;
-      pr[u] = __ldg(pp + (size_t)ks * 4);
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) bv[u][nt] = __ldg(vp + ((size_t)ks * NT + nt) * 32);
-    }
-  }
-  for (int i = 0; i < nmine; i += kPrefetch) {
+  for (int mt = 0; mt < MT; ++mt) xa[mt] = va[mt] = 0.0;
+  int i = 0;
+  for (; i + kPrefetch <= n; i += kPrefetch) {  // branch-free body: refills clamp to the last k-step
 #pragma unroll
     for (int u = 0; u < kPrefetch; ++u) {
-      if (i + u < nmine) {
-        const uint32_t p = pr[u];
-        double b[NT];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) b[nt] = bv[u][nt];
-        if (i + u + kPrefetch < nmine) {
-          const int ks = warp + (i + u + kPrefetch) * kWarps;
-          pr[u] = __ldg(pp + (size_t)ks * 4);
-#pragma unroll
-          for (int nt = 0; nt < NT; ++nt) bv[u][nt] = __ldg(vp + ((size_t)ks * NT + nt) * 32);
-        }
-        const int ja = p & 0xffff, kb = p >> 16;
-        const double* xa = xs + ja * ROW;
-        const double* xb = (MODE == MODE_ORDERED ? ys : xs) + kb * ROW;
-        const int sa = swz<MT>(ja), sb = swz<MT>(kb);
-        double a[MT];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const int s = mt * 8 + r;
-          if (MODE == MODE_JVP) {
-            const double* va = ys + ja * ROW;
-            const double* vb = ys + kb * ROW;
-            a[mt] = xa[s ^ sa] * vb[s ^ sb] + va[s ^ sa] * xb[s ^ sb];
-          } else {
-            a[mt] = xa[s ^ sa] * xb[s ^ sb];
-          }
-        }
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
-      }
+      kstep<MT, NT, MODE>(pf.pw[u], pf.bv[u], xsb, ysb, r8, xa, va, acc);
+      prefetch_slot<NT>(pf, u, pp, vp, min(i + u + kPrefetch, n - 1));
     }
   }
+#pragma unroll
+  for (int u = 0; u < kPrefetch - 1; ++u)
+    if (i + u < n) kstep<MT, NT, MODE>(pf.pw[u], pf.bv[u], xsb, ysb, r8, xa, va, acc);
 }
 
 template <int MT, int NT>
@@ -128,11 +177,34 @@ __device__ __forceinline__ void tile_reduce_store(const TileDesc& T, const int32
   }
 }
 
+// All tiles [tb, te) have NT n-tiles (the packer orders tiles by nt).
+template <int MT, int NT, int MODE>
+__device__ __forceinline__ void run_tiles(const TileDesc* __restrict__ tiles, int tb, int te,
+                                          const uint2* __restrict__ pairs, const double* __restrict__ vals,
+                                          const int32_t* __restrict__ rows, const double* xs, const double* ys,
+                                          double* red, int warp, int lane, int64_t s0, int64_t nstates,
+                                          double* __restrict__ OUT, int64_t ldo) {
+  if (tb >= te) return;
+  Prefetch<NT> pf;
+  TileDesc T = tiles[tb];
+  tile_prologue<NT>(T, pairs, vals, warp, lane, pf);
+  for (int t = tb; t < te; ++t) {
+    double acc[MT][NT][2];
+    tile_accumulate<MT, NT, MODE>(T, pairs, vals, xs, ys, warp, lane, pf, acc);
+    const TileDesc done = T;
+    if (t + 1 < te) {
+      T = tiles[t + 1];
+      tile_prologue<NT>(T, pairs, vals, warp, lane, pf);
+    }
+    tile_reduce_store<MT, NT>(done, rows, red, acc, warp, lane, s0, nstates, OUT, ldo);
+  }
+}
+
 // X, Y: nstates x (nin-1) column-major with leading dimension ldx; OUT: nstates x m, ldo.
 template <int MT, int MODE>
-__global__ void __launch_bounds__(kThreads, MT == 4 ? 2 : (MT == 2 ? 3 : 4))
-bilinear_batched_kernel(const TileDesc* __restrict__ tiles, int ntiles,
-                        const uint32_t* __restrict__ pairs, const double* __restrict__ vals,
+__global__ void __launch_bounds__(kThreads, 2)
+bilinear_batched_kernel(const TileDesc* __restrict__ tiles, int ntiles, int nt2_tiles,
+                        const uint2* __restrict__ pairs, const double* __restrict__ vals,
                         const int32_t* __restrict__ rows, int nin, const double* __restrict__ X,
                         const double* __restrict__ Y, int64_t nstates, int64_t ldx,
                         double* __restrict__ OUT, int64_t ldo) {
@@ -161,18 +233,8 @@ bilinear_batched_kernel(const TileDesc* __restrict__ tiles, int ntiles,
       if (MODE != MODE_QUAD) ys[j * ROW + (s ^ swz<MT>(j))] = vy;
     }
     __syncthreads();
-    for (int t = 0; t < ntiles; ++t) {
-      const TileDesc T = tiles[t];
-      if (T.nt == 1) {
-        double acc[MT][1][2];
-        tile_accumulate<MT, 1, MODE>(T, pairs, vals, xs, ys, warp, lane, acc);
-        tile_reduce_store<MT, 1>(T, rows, red, acc, warp, lane, s0, nstates, OUT, ldo);
-      } else {
-        double acc[MT][2][2];
-        tile_accumulate<MT, 2, MODE>(T, pairs, vals, xs, ys, warp, lane, acc);
-        tile_reduce_store<MT, 2>(T, rows, red, acc, warp, lane, s0, nstates, OUT, ldo);
-      }
-    }
+    run_tiles<MT, 2, MODE>(tiles, 0, nt2_tiles, pairs, vals, rows, xs, ys, red, warp, lane, s0, nstates, OUT, ldo);
+    run_tiles<MT, 1, MODE>(tiles, nt2_tiles, ntiles, pairs, vals, rows, xs, ys, red, warp, lane, s0, nstates, OUT, ldo);
   }
 }
 

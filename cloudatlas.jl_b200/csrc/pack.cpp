@@ -49,7 +49,7 @@ std::vector<uint64_t> union_of(const std::vector<uint64_t>& a, const std::vector
 PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt_max) {
   if (m <= 0) fail(CA_ERR_INVALID, "pack_terms: m must be positive");
   const int32_t nin = m + 1;
-  if (nin > 65536) fail(CA_ERR_UNSUPPORTED, "pack_terms: m = %d exceeds the 16-bit mode index", m);
+  if (nin > 32768) fail(CA_ERR_UNSUPPORTED, "pack_terms: m = %d exceeds the 15-bit mode index", m);
   if (nt_max < 1) nt_max = 1;
   PackedHost P;
   P.m = m;
@@ -158,6 +158,15 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
         P.pairs.push_back(padpair);
       }
     }
+    // flag k-steps whose four first factors repeat the previous k-step's (the kernel keeps them in registers)
+    for (int ks = 1; ks < T.nks; ++ks) {
+      uint32_t* cur = &P.pairs[((size_t)T.ks_begin + ks) * 4];
+      const uint32_t* prev = cur - 4;
+      bool same = true;
+      for (int c = 0; c < 4; ++c) same = same && ((cur[c] & 0x7fffu) == (prev[c] & 0x7fffu));
+      if (same)
+        for (int c = 0; c < 4; ++c) cur[c] |= 0x8000u;
+    }
     P.vals.resize(P.vals.size() + (size_t)T.nks * T.nt * 32, 0.0);
     double* V = P.vals.data() + T.vals_off;
     for (int n = 0; n < T.nrows; ++n) {
@@ -200,9 +209,10 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
     for (int k = 0; k < 8 * T.nt; ++k) P.rows.push_back(k < T.nrows ? empties[e + k] : -1);
     P.tiles.push_back(T);
   }
-  // long tiles first: the tail of each state block is then made of short tiles
+  // wide tiles first (the kernel runs one code path per nt), long before short inside each width
   std::stable_sort(P.tiles.begin(), P.tiles.end(), [](const TileDesc& x, const TileDesc& y) {
-    return (int64_t)x.nks * x.nt > (int64_t)y.nks * y.nt;
+    if (x.nt != y.nt) return x.nt > y.nt;
+    return x.nks > y.nks;
   });
   return P;
 }
