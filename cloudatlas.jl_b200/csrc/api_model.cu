@@ -9,6 +9,7 @@
 
 #include "bilinear.h"
 #include "bilinear_kernels.cuh"
+#include "model.h"
 
 using namespace ca;
 
@@ -76,29 +77,7 @@ void invert_block(std::vector<double>& A, int g, std::vector<double>& inv) {
 
 }  // namespace
 
-struct ca_model {
-  int device = 0;
-  int64_t m = 0;
-  int64_t nblocks = 0, nnz_lin = 0;
-  DevicePack op;           // symmetric pack of Q plus the linear slots
-  JacobianPack jac;        // of Q
-  DeviceBuffer<double> L1, L2;            // dense m x m column-major (for Df)
-  DeviceBuffer<int64_t> lin_pos;          // linear slots inside op.vals
-  DeviceBuffer<double> lin_l1, lin_l2;
-  double cur_invR = std::nan("");
-  cudaStream_t streams[2] = {nullptr, nullptr};
-  DeviceBuffer<double> stage_in[2], stage_out[2], small_x, small_out, jac_out;
-  ~ca_model() {
-    for (auto& s : streams)
-      if (s) cudaStreamDestroy(s);
-  }
-  void bind() const { CA_CUDA(cudaSetDevice(device)); }
-  void need_streams() {
-    for (auto& s : streams)
-      if (!s) CA_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-  }
-  // The packed values are shared by all streams: re-targeting R is ordered after everything queued.
-  void set_R(double R, cudaStream_t stream) {
+void ca_model::set_R(double R, cudaStream_t stream) {
     if (!(R != 0.0)) fail(CA_ERR_INVALID, "R must be non-zero");
     const double invR = 1.0 / R;
     if (invR == cur_invR) return;
@@ -112,7 +91,6 @@ struct ca_model {
     }
     cur_invR = invR;
   }
-};
 
 extern "C" {
 
@@ -227,6 +205,35 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
           l2.push_back(hL2[row + (size_t)m * a]);
         }
       }
+    // CSR of the symmetrised Q by output row, for the in-kernel evaluation of the device-resident solver
+    {
+      std::vector<Term> sym = qterms;
+      for (auto& t : sym)
+        if (t.a > t.b) std::swap(t.a, t.b);
+      std::sort(sym.begin(), sym.end(), [](const Term& x, const Term& y) {
+        if (x.i != y.i) return x.i < y.i;
+        if (x.a != y.a) return x.a < y.a;
+        return x.b < y.b;
+      });
+      std::vector<int32_t> rowptr(m + 1, 0);
+      std::vector<uint32_t> ab;
+      std::vector<double> qv;
+      for (size_t r = 0; r < sym.size();) {
+        size_t e = r;
+        double sum = 0;
+        while (e < sym.size() && sym[e].i == sym[r].i && sym[e].a == sym[r].a && sym[e].b == sym[r].b) sum += sym[e++].v;
+        if (sum != 0.0) {
+          ab.push_back((uint32_t)sym[r].a | ((uint32_t)sym[r].b << 16));
+          qv.push_back(sum);
+          rowptr[sym[r].i + 1]++;
+        }
+        r = e;
+      }
+      for (int i = 0; i < m; ++i) rowptr[i + 1] += rowptr[i];
+      h->q_rowptr.upload(rowptr.data(), rowptr.size());
+      h->q_ab.upload(ab.data(), ab.size());
+      h->q_val.upload(qv.data(), qv.size());
+    }
     h->nnz_lin = (int64_t)pos.size();
     h->op.upload(P);
     h->lin_pos.upload(pos.data(), pos.size());

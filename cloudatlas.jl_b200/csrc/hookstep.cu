@@ -1,0 +1,421 @@
+// Device-resident Newton-hookstep for an ODEModel: one persistent CTA per search.
+//
+// Replaces, for f = model.f(.,R) and Df = model.Df(.,R), the host loop of src/Hookstep.jl:109-352
+// (hookstepsolve) and :21-74 (hookstep).  On a GPU the 17/27/44-dimensional searches of the reference's
+// tests and notebooks are launch-latency-bound if every f, Df, LU and solve is its own kernel, so the
+// whole search runs inside ONE kernel: x, f(x), Df(x), H = Df'Df and the LU workspace live in shared
+// memory, f and Df are evaluated in-kernel from the folded operators (L1 + L2/R, Q = B^-1 N; CSR rows
+// for f, the sliced-ELL Jacobian structure for Df), and every reduction has a fixed order, so a search
+// is bit-reproducible.  Decision tree, constants (mu0 = 1e-6, dtol = 1e-4, factors 3/2, 1/2, 2/3, 4/3,
+// 0.01 / 0.10 / 0.8 / 1.2) and exit flags are the reference's.
+#include <algorithm>
+#include <vector>
+
+#include "model.h"
+
+using namespace ca;
+
+namespace {
+
+constexpr int kHookThreads = 256;
+
+struct SolverArgs {
+  int m;
+  // folded operators
+  const double* L1;
+  const double* L2;
+  const int32_t* q_rowptr;
+  const uint32_t* q_ab;
+  const double* q_val;
+  // Jacobian structure of Q
+  const int64_t* jac_slice_off;
+  const int32_t* jac_out_pos;
+  const uint16_t* jac_src;
+  const double* jac_val;
+  int64_t jac_nslices;
+  // problem
+  const double* R;
+  const double* Xguess;  // nsolve x m column-major
+  int64_t nsolve;
+  ca_search_params p;
+  double* Xout;
+  int32_t* success;
+  ca_solve_log* logs;
+};
+
+// ---- block-wide primitives (all threads call; results identical in every thread) -----------------
+__device__ double block_dot(const double* a, const double* b, int m, double* scratch) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double s = 0.0;
+  for (int i = tid; i < m; i += kHookThreads) s = fma(a[i], b[i], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __syncthreads();  // scratch may still be read from a previous call
+  if (lane == 0) scratch[warp] = s;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < kHookThreads / 32; ++w) t += scratch[w];
+  return t;
+}
+
+// y = A x, A m x m column-major in shared memory; one warp per row, fixed summation order
+__device__ void block_gemv(const double* A, const double* x, double* y, int m, bool transpose) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = warp; i < m; i += kHookThreads / 32) {
+    double s = 0.0;
+    for (int j = lane; j < m; j += 32) s = fma(transpose ? A[j + m * i] : A[i + m * j], x[j], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) y[i] = s;
+  }
+  __syncthreads();
+}
+
+// In-place LU with partial pivoting (first maximal |entry| wins, like LAPACK's idamax).  Returns false
+// on an exactly zero pivot.
+__device__ bool block_lu(double* W, int* piv, int m, int* flag) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int k = 0; k < m; ++k) {
+    if (tid < 32) {
+      double best = -1.0;
+      int at = k;
+      for (int r = k + lane; r < m; r += 32) {
+        const double v = fabs(W[r + m * k]);
+        if (v > best) { best = v; at = r; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, at, o);
+        if (ob > best || (ob == best && oa < at)) { best = ob; at = oa; }
+      }
+      if (lane == 0) {
+        piv[k] = at;
+        if (best == 0.0) *flag = 1;
+      }
+    }
+    __syncthreads();
+    if (*flag) return false;
+    const int p = piv[k];
+    if (p != k)
+      for (int j = tid; j < m; j += kHookThreads) {
+        const double t = W[k + m * j];
+        W[k + m * j] = W[p + m * j];
+        W[p + m * j] = t;
+      }
+    __syncthreads();
+    const double pivot = W[k + m * k];
+    for (int r = k + 1 + tid; r < m; r += kHookThreads) W[r + m * k] /= pivot;
+    __syncthreads();
+    const int n = m - k - 1;
+    for (int idx = tid; idx < n * n; idx += kHookThreads) {
+      const int r = k + 1 + idx % n, c = k + 1 + idx / n;
+      W[r + m * c] = fma(-W[r + m * k], W[k + m * c], W[r + m * c]);
+    }
+    __syncthreads();
+  }
+  return true;
+}
+
+// b <- (LU)^-1 b
+__device__ void block_lu_solve(const double* W, const int* piv, double* b, int m) {
+  const int tid = threadIdx.x;
+  if (tid == 0)
+    for (int k = 0; k < m; ++k) {
+      const int p = piv[k];
+      if (p != k) { const double t = b[k]; b[k] = b[p]; b[p] = t; }
+    }
+  __syncthreads();
+  for (int c = 0; c < m; ++c) {
+    const double f = b[c];
+    for (int r = c + 1 + tid; r < m; r += kHookThreads) b[r] = fma(-W[r + m * c], f, b[r]);
+    __syncthreads();
+  }
+  for (int c = m - 1; c >= 0; --c) {
+    if (tid == 0) b[c] /= W[c + m * c];
+    __syncthreads();
+    const double f = b[c];
+    for (int r = tid; r < c; r += kHookThreads) b[r] = fma(-W[r + m * c], f, b[r]);
+    __syncthreads();
+  }
+}
+
+// out = (L1 + L2/R) x + Q(x,x)   -- ODEModels.jl:57 with B folded in
+__device__ void eval_f(const SolverArgs& a, double invR, const double* x, double* out) {
+  const int m = a.m, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = warp; i < m; i += kHookThreads / 32) {
+    double s = 0.0;
+    for (int j = lane; j < m; j += 32) s = fma(fma(a.L2[i + m * j], invR, a.L1[i + m * j]), x[j], s);
+    for (int e = a.q_rowptr[i] + lane; e < a.q_rowptr[i + 1]; e += 32) {
+      const uint32_t ab = a.q_ab[e];
+      s = fma(a.q_val[e], x[ab & 0xffff] * x[ab >> 16], s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[i] = s;
+  }
+  __syncthreads();
+}
+
+// Df = L1 + L2/R + DQ(x)   -- ODEModels.jl:58 with B folded in; Df m x m column-major in shared memory
+__device__ void eval_Df(const SolverArgs& a, double invR, const double* x, double* Df) {
+  const int m = a.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < m * m; e += kHookThreads) Df[e] = fma(a.L2[e], invR, a.L1[e]);
+  __syncthreads();
+  for (int64_t sl = warp; sl < a.jac_nslices; sl += kHookThreads / 32) {
+    const int64_t b = a.jac_slice_off[sl], e = a.jac_slice_off[sl + 1];
+    double acc = 0.0;
+    for (int64_t p = b + lane; p < e; p += 32) acc = fma(a.jac_val[p], x[a.jac_src[p]], acc);
+    const int32_t o = a.jac_out_pos[sl * 32 + lane];
+    if (o >= 0) Df[o] += acc;  // every output entry belongs to exactly one lane of one slice
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int m = a.m, tid = threadIdx.x;
+  const int64_t s = blockIdx.x;
+  double* Df = sm;
+  double* H = Df + m * m;
+  double* W = H + m * m;
+  double* x = W + m * m;
+  double* fx = x + m;
+  double* dx = fx + m;
+  double* dxn = dx + m;   // Newton step
+  double* xh = dxn + m;   // x + dx
+  double* fh = xh + m;    // f(x + dx)
+  double* g = fh + m;     // Df' fx
+  double* t1 = g + m;
+  double* t2 = t1 + m;
+  double* scratch = t2 + m;          // 8 doubles
+  int* piv = (int*)(scratch + 8);    // m ints
+  int* flag = piv + m;
+
+  const double invR = 1.0 / a.R[s];
+  const double ftol = a.p.ftol, xtol = a.p.xtol;
+  double delta = a.p.delta;
+  ca_solve_log* L = (a.logs && tid == 0) ? &a.logs[s] : nullptr;  // thread 0 writes the per-step log
+  if (L)
+    for (int n = 0; n < CA_LOG_STEPS; ++n) { L->residual[n] = 0.0; L->delta[n] = 0.0; L->hooksteps[n] = 0; }
+  int exit_reason = CA_EXIT_MAX_NEWTON, nsteps = 0, nf = 0, ndf = 0;
+  double last_res = 0.0;
+
+  for (int i = tid; i < m; i += kHookThreads) x[i] = a.Xguess[s + a.nsolve * i];
+  if (tid == 0) *flag = 0;
+  __syncthreads();
+
+  for (int n = 0; n < a.p.Nnewton; ++n) {
+    eval_f(a, invR, x, fx);
+    ++nf;
+    const double rx = 0.5 * block_dot(fx, fx, m, scratch);
+    last_res = sqrt(2 * rx);
+    if (L && n < CA_LOG_STEPS) { L->residual[n] = last_res; L->delta[n] = delta; }
+    nsteps = n;
+    if (last_res <= ftol) { exit_reason = CA_EXIT_CONVERGED; break; }
+    nsteps = n + 1;
+
+    eval_Df(a, invR, x, Df);
+    ++ndf;
+    // Newton step: dx = -Df \ fx
+    for (int e = tid; e < m * m; e += kHookThreads) W[e] = Df[e];
+    for (int i = tid; i < m; i += kHookThreads) dx[i] = -fx[i];
+    __syncthreads();
+    if (!block_lu(W, piv, m, flag)) { exit_reason = CA_EXIT_SINGULAR; break; }
+    block_lu_solve(W, piv, dx, m);
+    const double norm_dx_newt = sqrt(block_dot(dx, dx, m, scratch));
+    block_gemv(Df, dx, t1, m, false);  // Df dx
+    if (block_dot(fx, t1, m, scratch) >= 0.0) { exit_reason = CA_EXIT_RESIDUAL_UP; break; }
+    if (norm_dx_newt < xtol) {
+      for (int i = tid; i < m; i += kHookThreads) x[i] += dx[i];
+      __syncthreads();
+      exit_reason = CA_EXIT_XTOL_NEWTON;
+      break;
+    }
+    for (int i = tid; i < m; i += kHookThreads) { dxn[i] = dx[i]; xh[i] = x[i] + dx[i]; }
+    __syncthreads();
+
+    bool have_H = false;
+    bool xtol_exit = false;
+    int nh = 0;
+    for (int h = 0; h < a.p.Nhook; ++h) {
+      ++nh;
+      if (norm_dx_newt > delta) {
+        // ---- hookstep(fx, Dfx, delta, dx_newt): Newton iteration on mu for norm(dx(mu)) = delta
+        if (!have_H) {
+          for (int e = tid; e < m * m; e += kHookThreads) {
+            const int r = e % m, c = e / m;
+            double sum = 0.0;
+            for (int k = 0; k < m; ++k) sum = fma(Df[k + m * r], Df[k + m * c], sum);
+            H[e] = sum;
+          }
+          __syncthreads();
+          block_gemv(Df, fx, g, m, true);  // Df' fx
+          have_H = true;
+        }
+        double mu = 1e-6;
+        double norm_dx = norm_dx_newt;
+        for (int i = tid; i < m; i += kHookThreads) dx[i] = dxn[i];
+        __syncthreads();
+        bool singular = false;
+        for (int it = 0; it < a.p.Nmusearch; ++it) {
+          const double phi = norm_dx - delta;
+          // phi' = -(1/norm_dx) * dot(dx, (H + mu I) \ dx)
+          for (int e = tid; e < m * m; e += kHookThreads) W[e] = H[e] + ((e % m) == (e / m) ? mu : 0.0);
+          for (int i = tid; i < m; i += kHookThreads) t1[i] = dx[i];
+          __syncthreads();
+          if (!block_lu(W, piv, m, flag)) { singular = true; break; }
+          block_lu_solve(W, piv, t1, m);
+          const double phiprime = -(1.0 / norm_dx) * block_dot(dx, t1, m, scratch);
+          mu = mu - (norm_dx / delta) * (phi / phiprime);
+          // dx = -(H + mu I) \ (Df' fx)
+          for (int e = tid; e < m * m; e += kHookThreads) W[e] = H[e] + ((e % m) == (e / m) ? mu : 0.0);
+          for (int i = tid; i < m; i += kHookThreads) dx[i] = -g[i];
+          __syncthreads();
+          if (!block_lu(W, piv, m, flag)) { singular = true; break; }
+          block_lu_solve(W, piv, dx, m);
+          norm_dx = sqrt(block_dot(dx, dx, m, scratch));
+          if (fabs(norm_dx - delta) / delta <= 1e-4) break;
+        }
+        if (singular) { exit_reason = CA_EXIT_SINGULAR; xtol_exit = true; break; }
+      }
+      block_gemv(Df, dx, t1, m, false);  // Df dx
+      const double norm_dx_cur = sqrt(block_dot(dx, dx, m, scratch));
+      if (norm_dx_cur < xtol) {
+        for (int i = tid; i < m; i += kHookThreads) x[i] += dx[i];
+        __syncthreads();
+        exit_reason = CA_EXIT_XTOL_HOOK;
+        xtol_exit = true;
+        break;
+      }
+      const bool within = norm_dx_newt <= delta;
+      for (int i = tid; i < m; i += kHookThreads) xh[i] = x[i] + dx[i];
+      __syncthreads();
+      eval_f(a, invR, xh, fh);
+      ++nf;
+      const double r_hook = 0.5 * block_dot(fh, fh, m, scratch);
+      const double r_linear = rx + block_dot(fx, t1, m, scratch);
+      for (int i = tid; i < m; i += kHookThreads) t2[i] = fx[i] + t1[i];
+      __syncthreads();
+      const double r_quadratic = 0.5 * block_dot(t2, t2, m, scratch);
+      const double dr_hook = rx - r_hook, dr_linear = rx - r_linear, dr_quadratic = rx - r_quadratic;
+      if (dr_hook > dr_linear) {
+        if (within) break;
+        delta = 3 * delta / 2;
+        continue;
+      } else if (dr_hook < 0.01 * dr_quadratic) {
+        delta = delta / 2;
+        continue;
+      } else if (dr_hook < 0.10 * dr_quadratic) {
+        delta = delta / 2;
+        break;
+      } else if (0.8 * dr_quadratic < dr_hook && dr_hook < 1.2 * dr_quadratic) {
+        const double mm = -dr_linear / delta;
+        const double c = (r_hook - rx - mm * delta) / (delta * delta);
+        const double dnew = -mm / (2 * c);
+        if (within) {
+        } else if (dnew < 2 * delta / 3) {
+          delta = 2 * delta / 3;
+        } else if (dnew > 4 * delta / 3) {
+          delta = 4 * delta / 3;
+        } else {
+          delta = dnew;
+        }
+        break;
+      } else {
+        break;
+      }
+    }
+    if (L && n < CA_LOG_STEPS) { L->delta[n] = delta; L->hooksteps[n] = nh; }
+    if (xtol_exit) break;
+    for (int i = tid; i < m; i += kHookThreads) x[i] = xh[i];
+    __syncthreads();
+  }
+
+  for (int i = tid; i < m; i += kHookThreads) a.Xout[s + a.nsolve * i] = x[i];
+  if (tid == 0) {
+    a.success[s] = exit_reason == CA_EXIT_CONVERGED ? 1 : 0;
+    if (L) {
+      L->exit_reason = exit_reason;
+      L->newton_steps = nsteps;
+      L->f_evals = nf;
+      L->df_evals = ndf;
+      L->final_residual = last_res;
+      L->final_delta = delta;
+      L->device_seconds = 0.0;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int32_t ca_hookstep_solve_model(ca_model* h, const double* R, const double* Xguess, int64_t nsolve,
+                                           const ca_search_params* params, double* X_out, int32_t* success,
+                                           ca_solve_log* logs) {
+  return guarded([&] {
+    if (!h || !R || !Xguess || !X_out || !success) fail(CA_ERR_INVALID, "ca_hookstep_solve_model: null argument");
+    if (nsolve <= 0) fail(CA_ERR_INVALID, "nsolve must be positive");
+    ca_search_params p{1e-8, 1e-8, 0.02, 20, 4, 6, 0};  // Hookstep.jl:6-14 defaults
+    if (params) p = *params;
+    if (p.Nnewton < 0 || p.Nhook < 0 || p.Nmusearch < 0 || !(p.delta > 0)) fail(CA_ERR_INVALID, "bad SearchParams");
+    for (int64_t s = 0; s < nsolve; ++s)
+      if (!(R[s] != 0.0)) fail(CA_ERR_INVALID, "R must be non-zero");
+    h->bind();
+    const int m = (int)h->m;
+    const size_t smem = ((size_t)3 * m * m + 9 * (size_t)m + 8) * sizeof(double) + ((size_t)m + 4) * sizeof(int);
+    int optin = 0;
+    CA_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    if (smem > (size_t)optin)
+      fail(CA_ERR_UNSUPPORTED, "device-resident hookstep needs %zu B of shared memory for m = %d (limit %d); "
+           "use the closure form of hookstepsolve with model.f / model.Df", smem, m, optin);
+    CA_CUDA(cudaFuncSetAttribute(hookstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    DeviceBuffer<double> dR, dX, dOut;
+    DeviceBuffer<int32_t> dSucc;
+    DeviceBuffer<ca_solve_log> dLogs;
+    dR.upload(R, (size_t)nsolve);
+    dX.upload(Xguess, (size_t)nsolve * m);
+    dOut.alloc((size_t)nsolve * m);
+    dSucc.alloc((size_t)nsolve);
+    if (logs) dLogs.alloc((size_t)nsolve);
+    SolverArgs a{};
+    a.m = m;
+    a.L1 = h->L1.ptr;
+    a.L2 = h->L2.ptr;
+    a.q_rowptr = h->q_rowptr.ptr;
+    a.q_ab = h->q_ab.ptr;
+    a.q_val = h->q_val.ptr;
+    a.jac_slice_off = h->jac.slice_off.ptr;
+    a.jac_out_pos = h->jac.out_pos.ptr;
+    a.jac_src = h->jac.src.ptr;
+    a.jac_val = h->jac.val.ptr;
+    a.jac_nslices = h->jac.nslices;
+    a.R = dR.ptr;
+    a.Xguess = dX.ptr;
+    a.nsolve = nsolve;
+    a.p = p;
+    a.Xout = dOut.ptr;
+    a.success = dSucc.ptr;
+    a.logs = logs ? dLogs.ptr : nullptr;
+    cudaEvent_t e0, e1;
+    CA_CUDA(cudaEventCreate(&e0));
+    CA_CUDA(cudaEventCreate(&e1));
+    CA_CUDA(cudaEventRecord(e0));
+    hookstep_kernel<<<(unsigned)nsolve, kHookThreads, smem>>>(a);
+    CA_CUDA(cudaGetLastError());
+    count_launch();
+    CA_CUDA(cudaEventRecord(e1));
+    CA_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    CA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CA_CUDA(cudaMemcpy(X_out, dOut.ptr, (size_t)nsolve * m * sizeof(double), cudaMemcpyDeviceToHost));
+    CA_CUDA(cudaMemcpy(success, dSucc.ptr, (size_t)nsolve * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (logs) {
+      CA_CUDA(cudaMemcpy(logs, dLogs.ptr, (size_t)nsolve * sizeof(ca_solve_log), cudaMemcpyDeviceToHost));
+      for (int64_t s = 0; s < nsolve; ++s) logs[s].device_seconds = ms * 1e-3;
+    }
+  });
+}

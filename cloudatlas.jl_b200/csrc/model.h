@@ -1,0 +1,34 @@
+// The device side of an ODEModel (shared by api_model.cu and hookstep.cu).
+#pragma once
+#include <cmath>
+
+#include "bilinear.h"
+
+struct ca_model {
+  int device = 0;
+  int64_t m = 0;
+  int64_t nblocks = 0, nnz_lin = 0;
+  ca::DevicePack op;           // symmetric pack of Q plus the linear slots
+  ca::JacobianPack jac;        // of Q
+  ca::DeviceBuffer<double> L1, L2;            // dense m x m column-major (for Df)
+  ca::DeviceBuffer<int32_t> q_rowptr;         // CSR of the symmetrised folded Q (a <= b), by output row
+  ca::DeviceBuffer<uint32_t> q_ab;            // a | b << 16
+  ca::DeviceBuffer<double> q_val;
+  ca::DeviceBuffer<int64_t> lin_pos;          // linear slots inside op.vals
+  ca::DeviceBuffer<double> lin_l1, lin_l2;
+  double cur_invR = std::nan("");
+  cudaStream_t streams[2] = {nullptr, nullptr};
+  ca::DeviceBuffer<double> stage_in[2], stage_out[2], small_x, small_out, jac_out;
+  ~ca_model() {
+    for (auto& s : streams)
+      if (s) cudaStreamDestroy(s);
+  }
+  void bind() const { CA_CUDA(cudaSetDevice(device)); }
+  void need_streams() {
+    for (auto& s : streams)
+      if (!s) CA_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  }
+  // The packed values are shared by all streams: re-targeting R is ordered after everything queued.
+  void set_R(double R, cudaStream_t stream);
+};
+

@@ -159,6 +159,44 @@ int32_t ca_assembly_get_linear_dev(ca_assembly* h, double* dB, double* dA1, doub
 int32_t ca_assembly_get_coo_dev(ca_assembly* h, int64_t* d_i, int64_t* d_j, int64_t* d_k, double* d_val,
                                 void* stream);
 
+/* ---- Newton-hookstep (reference: src/Hookstep.jl) --------------------------------------------- */
+/* SearchParams -- Hookstep.jl:6-14, same fields, order and defaults
+ * (ftol = xtol = 1e-8, delta = 0.02, Nnewton = 20, Nhook = 4, Nmusearch = 6, verbosity = 0). */
+typedef struct ca_search_params {
+  double ftol, xtol, delta;
+  int32_t Nnewton, Nhook, Nmusearch, verbosity;
+} ca_search_params;
+
+enum { /* why the search returned (Hookstep.jl line of the return statement) */
+  CA_EXIT_CONVERGED = 1,       /* norm(f(x)) <= ftol, the only exit with success = true   :146-149 */
+  CA_EXIT_RESIDUAL_UP = 2,     /* dot(fx, Dfx*dx) >= 0, returns x                          :176-183 */
+  CA_EXIT_XTOL_NEWTON = 3,     /* norm(dx_newton) < xtol, returns x + dx                   :185-190 */
+  CA_EXIT_XTOL_HOOK = 4,       /* norm(dx_hook) < xtol, returns x + dx                     :216-221 */
+  CA_EXIT_MAX_NEWTON = 5,      /* Nnewton steps done                                       :349-351 */
+  CA_EXIT_SINGULAR = 6         /* a pivot was exactly zero (Julia would throw SingularException) */
+};
+#define CA_LOG_STEPS 64
+typedef struct ca_solve_log {
+  int32_t exit_reason, newton_steps, f_evals, df_evals;
+  double final_residual;              /* norm(f) at the last evaluated Newton iterate */
+  double final_delta;                 /* trust-region radius on exit */
+  double device_seconds;              /* CUDA-event time of the solve kernel */
+  double residual[CA_LOG_STEPS];      /* norm(f(x_n)) at the start of Newton step n */
+  double delta[CA_LOG_STEPS];         /* trust-region radius after step n */
+  int32_t hooksteps[CA_LOG_STEPS];    /* hookstep iterations taken in step n */
+} ca_solve_log;
+
+/* hookstepsolve(x -> model.f(x,R), x -> model.Df(x,R), xguess, params) -- Hookstep.jl:109-352 with
+ * hookstep() :21-74 -- as ONE persistent kernel: a single CTA keeps x, f(x), Df(x), Df'Df and the LU
+ * workspaces in shared memory for the whole search (no launches, no host round trips inside the
+ * loop).  Same decision tree, constants and exit flags as the reference.  m is limited by shared
+ * memory (3 m^2 + 12 m doubles <= 227 KB, m <= 95); larger models return CA_ERR_UNSUPPORTED.
+ * nsolve independent searches (own R, own guess; one CTA each) run in one launch:
+ * R: nsolve, Xguess / X_out: nsolve x m column-major, success / logs: nsolve (logs may be NULL). */
+int32_t ca_hookstep_solve_model(ca_model* h, const double* R, const double* Xguess, int64_t nsolve,
+                                const ca_search_params* params, double* X_out, int32_t* success,
+                                ca_solve_log* logs);
+
 /* ---- diagnostics (host only, no device needed) ---------------------------------------------- */
 /* Packs a COO operator exactly as ca_bilinear_create does, expands the packed tiles back into
  * (i,j,k,val) terms and compares them with the (merged) input: *mismatches must come back 0.
