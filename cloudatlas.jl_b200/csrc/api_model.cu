@@ -182,13 +182,13 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
     CA_CUDA(cudaGetDevice(&h->device));
     h->m = m;
     h->nblocks = (int64_t)blocks.size();
-    h->jac.build(qterms, m);
     // linear placeholders (value 1) mark the slots that set_R patches
     std::vector<Term> all = qterms;
     for (int j = 0; j < m; ++j)
       for (int i = 0; i < m; ++i)
         if (hL1[i + (size_t)m * j] != 0.0 || hL2[i + (size_t)m * j] != 0.0) all.push_back(Term{i, j, m, 1.0});
     PackedHost P = pack_terms(std::move(all), m, /*symmetric=*/true, kNtMax);
+    h->qterms = std::move(qterms);
     std::vector<int64_t> pos;
     std::vector<double> l1, l2;
     for (const TileDesc& T : P.tiles)
@@ -207,7 +207,7 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
       }
     // CSR of the symmetrised Q by output row, for the in-kernel evaluation of the device-resident solver
     {
-      std::vector<Term> sym = qterms;
+      std::vector<Term> sym = h->qterms;
       for (auto& t : sym)
         if (t.a > t.b) std::swap(t.a, t.b);
       std::sort(sym.begin(), sym.end(), [](const Term& x, const Term& y) {
@@ -317,7 +317,7 @@ int32_t ca_model_jac_dev(ca_model* h, const double* dx, double R, double* dDf, v
     if (!(R != 0.0)) fail(CA_ERR_INVALID, "R must be non-zero");
     h->bind();
     cudaStream_t st = (cudaStream_t)stream;
-    launch_jacobian(h->jac, dx, dDf, st);
+    launch_jacobian(h->jacobian(), dx, dDf, st);
     const int64_t n = h->m * h->m;
     add_linear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dDf, h->L1.ptr, h->L2.ptr, n, 1.0 / R);
     CA_CUDA(cudaGetLastError());

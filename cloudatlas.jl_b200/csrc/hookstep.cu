@@ -386,11 +386,12 @@ extern "C" int32_t ca_hookstep_solve_model(ca_model* h, const double* R, const d
     a.q_rowptr = h->q_rowptr.ptr;
     a.q_ab = h->q_ab.ptr;
     a.q_val = h->q_val.ptr;
-    a.jac_slice_off = h->jac.slice_off.ptr;
-    a.jac_out_pos = h->jac.out_pos.ptr;
-    a.jac_src = h->jac.src.ptr;
-    a.jac_val = h->jac.val.ptr;
-    a.jac_nslices = h->jac.nslices;
+    const JacobianPack& J = h->jacobian();
+    a.jac_slice_off = J.slice_off.ptr;
+    a.jac_out_pos = J.out_pos.ptr;
+    a.jac_src = J.src.ptr;
+    a.jac_val = J.val.ptr;
+    a.jac_nslices = J.nslices;
     a.R = dR.ptr;
     a.Xguess = dX.ptr;
     a.nsolve = nsolve;

@@ -9,7 +9,16 @@ struct ca_model {
   int64_t m = 0;
   int64_t nblocks = 0, nnz_lin = 0;
   ca::DevicePack op;           // symmetric pack of Q plus the linear slots
-  ca::JacobianPack jac;        // of Q
+  ca::JacobianPack jac;        // of Q, built on first use (Df, device-resident solver)
+  bool jac_built = false;
+  std::vector<ca::Term> qterms;  // folded Q = B^-1 N (ordered j,k), kept on the host for the lazy builds
+  ca::JacobianPack& jacobian() {
+    if (!jac_built) {
+      jac.build(qterms, (int32_t)m);
+      jac_built = true;
+    }
+    return jac;
+  }
   ca::DeviceBuffer<double> L1, L2;            // dense m x m column-major (for Df)
   ca::DeviceBuffer<int32_t> q_rowptr;         // CSR of the symmetrised folded Q (a <= b), by output row
   ca::DeviceBuffer<uint32_t> q_ab;            // a | b << 16
