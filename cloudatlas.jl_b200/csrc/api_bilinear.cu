@@ -15,6 +15,7 @@ struct ca_bilinear {
   DevicePack sym;         // (j,k) ~ (k,j): N(x), JVP
   std::unique_ptr<DevicePack> ord;      // ordered pairs: N(x,y), built on first use
   std::unique_ptr<JacobianPack> jac;    // built on first use
+  std::unique_ptr<StreamPack> ssym, sord;  // few-state streaming form, built on first use
   // staging for the host-pointer entry points
   cudaStream_t streams[2] = {nullptr, nullptr};
   DeviceBuffer<double> stage_in[2], stage_out[2], small_x, small_y, small_out, jac_out;
@@ -34,6 +35,35 @@ struct ca_bilinear {
     }
     return *ord;
   }
+  StreamPack& stream_sym() {
+    if (!ssym) {
+      ssym.reset(new StreamPack);
+      ssym->build(coo, (int32_t)m, true);
+    }
+    return *ssym;
+  }
+  StreamPack& stream_ord() {
+    if (!sord) {
+      sord.reset(new StreamPack);
+      sord->build(coo, (int32_t)m, false);
+    }
+    return *sord;
+  }
+  // mode-aware dispatch between the DMMA ensemble kernel and the streaming kernel
+  void eval_dev(int mode, const double* dX, const double* dY, int64_t nstates, int64_t ldx, double* dOUT,
+                int64_t ldo, cudaStream_t st) {
+    DevicePack* dp = mode == MODE_ORDERED ? nullptr : &sym;
+    const bool small = nstates <= kStreamMaxStates;
+    if (!small) {
+      if (mode == MODE_ORDERED) dp = &ordered();
+      if (batched_fits(*dp, mode)) {
+        launch_batched(*dp, mode, dX, dY, nstates, ldx, dOUT, ldo, st);
+        return;
+      }
+    }
+    launch_stream(mode == MODE_ORDERED ? stream_ord() : stream_sym(), mode, dX, dY, nstates, ldx, dOUT, ldo,
+                  nullptr, nullptr, 0.0, st);
+  }
   JacobianPack& jacobian() {
     if (!jac) {
       jac.reset(new JacobianPack);
@@ -48,7 +78,7 @@ namespace ca {
 // Shared with the model code: evaluates a packed operator for a host ensemble, chunked and
 // double-buffered (H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c when the
 // host buffers are page-locked, see ca_pin).
-void eval_batched_host(const DevicePack& op, cudaStream_t streams[2], DeviceBuffer<double> in[2],
+void eval_batched_host(const LaunchFn& launch, cudaStream_t streams[2], DeviceBuffer<double> in[2],
                        DeviceBuffer<double> out[2], const double* X, int64_t nstates, double* OUT,
                        int64_t m_in, int64_t m_out) {
   if (nstates <= 0) return;
@@ -68,7 +98,7 @@ void eval_batched_host(const DevicePack& op, cudaStream_t streams[2], DeviceBuff
     CA_CUDA(cudaMemcpy2DAsync(in[b].ptr, (size_t)n * sizeof(double), X + s0,
                               (size_t)nstates * sizeof(double), (size_t)n * sizeof(double),
                               (size_t)m_in, cudaMemcpyHostToDevice, st));
-    launch_batched(op, MODE_QUAD, in[b].ptr, nullptr, n, n, out[b].ptr, n, st);
+    launch(in[b].ptr, n, out[b].ptr, st);
     CA_CUDA(cudaMemcpy2DAsync(OUT + s0, (size_t)nstates * sizeof(double), out[b].ptr,
                               (size_t)n * sizeof(double), (size_t)n * sizeof(double), (size_t)m_out,
                               cudaMemcpyDeviceToHost, st));
@@ -135,10 +165,8 @@ int32_t ca_bilinear_eval(ca_bilinear* h, const double* x, const double* y, doubl
     h->small_x.upload(x, m);
     if (y && y != x) h->small_y.upload(y, m);
     if (h->small_out.count < m) h->small_out.alloc(m);
-    if (y && y != x)
-      launch_batched(h->ordered(), MODE_ORDERED, h->small_x.ptr, h->small_y.ptr, 1, 1, h->small_out.ptr, 1, nullptr);
-    else
-      launch_batched(h->sym, MODE_QUAD, h->small_x.ptr, nullptr, 1, 1, h->small_out.ptr, 1, nullptr);
+    if (y && y != x) h->eval_dev(MODE_ORDERED, h->small_x.ptr, h->small_y.ptr, 1, 1, h->small_out.ptr, 1, nullptr);
+    else h->eval_dev(MODE_QUAD, h->small_x.ptr, nullptr, 1, 1, h->small_out.ptr, 1, nullptr);
     CA_CUDA(cudaMemcpy(out, h->small_out.ptr, m * sizeof(double), cudaMemcpyDeviceToHost));
   });
 }
@@ -149,7 +177,9 @@ int32_t ca_bilinear_eval_batched(ca_bilinear* h, const double* X, int64_t nstate
     if (nstates < 0) fail(CA_ERR_INVALID, "nstates must be non-negative");
     h->bind();
     h->need_streams();
-    eval_batched_host(h->sym, h->streams, h->stage_in, h->stage_out, X, nstates, OUT, h->m, h->m);
+    eval_batched_host([&](const double* dX, int64_t n, double* dOUT, cudaStream_t st) {
+      h->eval_dev(MODE_QUAD, dX, nullptr, n, n, dOUT, n, st);
+    }, h->streams, h->stage_in, h->stage_out, X, nstates, OUT, h->m, h->m);
   });
 }
 
@@ -158,7 +188,7 @@ int32_t ca_bilinear_eval_batched_dev(ca_bilinear* h, const double* dX, int64_t n
   return guarded([&] {
     if (!h || (nstates > 0 && (!dX || !dOUT))) fail(CA_ERR_INVALID, "null argument");
     h->bind();
-    launch_batched(h->sym, MODE_QUAD, dX, nullptr, nstates, ldx, dOUT, ldo, (cudaStream_t)stream);
+    h->eval_dev(MODE_QUAD, dX, nullptr, nstates, ldx, dOUT, ldo, (cudaStream_t)stream);
   });
 }
 
@@ -168,7 +198,7 @@ int32_t ca_bilinear_eval2_batched_dev(ca_bilinear* h, const double* dX, const do
   return guarded([&] {
     if (!h || (nstates > 0 && (!dX || !dY || !dOUT))) fail(CA_ERR_INVALID, "null argument");
     h->bind();
-    launch_batched(h->ordered(), MODE_ORDERED, dX, dY, nstates, ld, dOUT, ldo, (cudaStream_t)stream);
+    h->eval_dev(MODE_ORDERED, dX, dY, nstates, ld, dOUT, ldo, (cudaStream_t)stream);
   });
 }
 
@@ -178,7 +208,7 @@ int32_t ca_bilinear_jvp_batched_dev(ca_bilinear* h, const double* dX, const doub
   return guarded([&] {
     if (!h || (nstates > 0 && (!dX || !dV || !dOUT))) fail(CA_ERR_INVALID, "null argument");
     h->bind();
-    launch_batched(h->sym, MODE_JVP, dX, dV, nstates, ld, dOUT, ldo, (cudaStream_t)stream);
+    h->eval_dev(MODE_JVP, dX, dV, nstates, ld, dOUT, ldo, (cudaStream_t)stream);
   });
 }
 

@@ -13,11 +13,6 @@
 
 using namespace ca;
 
-namespace ca {
-void eval_batched_host(const DevicePack& op, cudaStream_t streams[2], DeviceBuffer<double> in[2],
-                       DeviceBuffer<double> out[2], const double* X, int64_t nstates, double* OUT,
-                       int64_t m_in, int64_t m_out);
-}
 
 namespace {
 
@@ -91,6 +86,17 @@ void ca_model::set_R(double R, cudaStream_t stream) {
     }
     cur_invR = invR;
   }
+
+void ca_model::eval_dev(int mode, const double* dX, const double* dV, int64_t nstates, int64_t ldx, double R,
+                        double* dOUT, int64_t ldo, cudaStream_t st) {
+  if (!(R != 0.0)) fail(CA_ERR_INVALID, "R must be non-zero");
+  if (nstates > kStreamMaxStates && batched_fits(op, mode)) {
+    set_R(R, st);
+    launch_batched(op, mode, dX, dV, nstates, ldx, dOUT, ldo, st);
+    return;
+  }
+  launch_stream(streaming(), mode, dX, dV, nstates, ldx, dOUT, ldo, L1r.ptr, L2r.ptr, 1.0 / R, st);
+}
 
 extern "C" {
 
@@ -241,6 +247,17 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
     h->lin_l2.upload(l2.data(), l2.size());
     h->L1.upload(hL1.data(), hL1.size());
     h->L2.upload(hL2.data(), hL2.size());
+    {
+      std::vector<double> r1((size_t)m * m), r2((size_t)m * m);
+      for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) {
+          r1[(size_t)i * m + j] = hL1[i + (size_t)m * j];
+          r2[(size_t)i * m + j] = hL2[i + (size_t)m * j];
+        }
+      h->L1r.upload(r1.data(), r1.size());
+      h->L2r.upload(r2.data(), r2.size());
+      CA_CUDA(cudaStreamSynchronize(nullptr));
+    }
     CA_CUDA(cudaStreamSynchronize(nullptr));
     *out = h.release();
   });
@@ -272,8 +289,7 @@ int32_t ca_model_rhs_batched_dev(ca_model* h, const double* dX, int64_t nstates,
   return guarded([&] {
     if (!h || (nstates > 0 && (!dX || !dOUT))) fail(CA_ERR_INVALID, "null argument");
     h->bind();
-    h->set_R(R, (cudaStream_t)stream);
-    launch_batched(h->op, MODE_QUAD, dX, nullptr, nstates, ldx, dOUT, ldo, (cudaStream_t)stream);
+    h->eval_dev(MODE_QUAD, dX, nullptr, nstates, ldx, R, dOUT, ldo, (cudaStream_t)stream);
   });
 }
 
@@ -282,8 +298,7 @@ int32_t ca_model_jvp_batched_dev(ca_model* h, const double* dX, const double* dV
   return guarded([&] {
     if (!h || (nstates > 0 && (!dX || !dV || !dOUT))) fail(CA_ERR_INVALID, "null argument");
     h->bind();
-    h->set_R(R, (cudaStream_t)stream);
-    launch_batched(h->op, MODE_JVP, dX, dV, nstates, ld, dOUT, ldo, (cudaStream_t)stream);
+    h->eval_dev(MODE_JVP, dX, dV, nstates, ld, R, dOUT, ldo, (cudaStream_t)stream);
   });
 }
 
@@ -293,8 +308,10 @@ int32_t ca_model_rhs_batched(ca_model* h, const double* X, int64_t nstates, doub
     if (nstates < 0) fail(CA_ERR_INVALID, "nstates must be non-negative");
     h->bind();
     h->need_streams();
-    h->set_R(R, h->streams[0]);
-    eval_batched_host(h->op, h->streams, h->stage_in, h->stage_out, X, nstates, OUT, h->m, h->m);
+    h->set_R(R, h->streams[0]);  // before the two streams start, so no re-targeting happens mid-flight
+    eval_batched_host([&](const double* dX, int64_t n, double* dOUT, cudaStream_t st) {
+      h->eval_dev(MODE_QUAD, dX, nullptr, n, n, R, dOUT, n, st);
+    }, h->streams, h->stage_in, h->stage_out, X, nstates, OUT, h->m, h->m);
   });
 }
 
@@ -303,10 +320,9 @@ int32_t ca_model_rhs(ca_model* h, const double* x, double R, double* out) {
     if (!h || !x || !out) fail(CA_ERR_INVALID, "null argument");
     h->bind();
     const size_t m = (size_t)h->m;
-    h->set_R(R, nullptr);
     h->small_x.upload(x, m);
     if (h->small_out.count < m) h->small_out.alloc(m);
-    launch_batched(h->op, MODE_QUAD, h->small_x.ptr, nullptr, 1, 1, h->small_out.ptr, 1, nullptr);
+    h->eval_dev(MODE_QUAD, h->small_x.ptr, nullptr, 1, 1, R, h->small_out.ptr, 1, nullptr);
     CA_CUDA(cudaMemcpy(out, h->small_out.ptr, m * sizeof(double), cudaMemcpyDeviceToHost));
   });
 }

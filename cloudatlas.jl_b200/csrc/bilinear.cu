@@ -103,6 +103,11 @@ void launch_mode(const DevicePack& op, const double* dX, const double* dY, int64
 
 }  // namespace
 
+bool batched_fits(const DevicePack& op, int mode) {
+  const size_t cap = device_cfg().smem_optin;
+  return (mode == MODE_QUAD ? batched_smem_bytes<1, MODE_QUAD>(op.nin) : batched_smem_bytes<1, MODE_JVP>(op.nin)) <= cap;
+}
+
 void launch_batched(const DevicePack& op, int mode, const double* dX, const double* dY,
                     int64_t nstates, int64_t ldx, double* dOUT, int64_t ldo, cudaStream_t stream) {
   if (nstates <= 0) return;

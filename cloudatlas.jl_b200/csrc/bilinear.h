@@ -1,5 +1,7 @@
 // Device-resident packed operators and their launchers.
 #pragma once
+#include <functional>
+#include <map>
 #include <memory>
 #include <vector>
 
@@ -25,6 +27,43 @@ struct DevicePack {
 // mode: MODE_QUAD (Y ignored), MODE_ORDERED (u = X, w = Y), MODE_JVP (X = state, Y = direction).
 void launch_batched(const DevicePack& op, int mode, const double* dX, const double* dY,
                     int64_t nstates, int64_t ldx, double* dOUT, int64_t ldo, cudaStream_t stream);
+
+// launches one chunk of a host ensemble: (dX, nstates (= leading dimension), dOUT, stream)
+using LaunchFn = std::function<void(const double*, int64_t, double*, cudaStream_t)>;
+void eval_batched_host(const LaunchFn& launch, cudaStream_t streams[2], DeviceBuffer<double> in[2],
+                       DeviceBuffer<double> out[2], const double* X, int64_t nstates, double* OUT,
+                       int64_t m_in, int64_t m_out);
+
+// true if the DMMA ensemble kernel can hold a state tile of this operator in shared memory
+bool batched_fits(const DevicePack& op, int mode);
+constexpr int64_t kStreamMaxStates = 16;  // at or below this many states the streaming kernel is used
+
+// Row-chunked CSR for the few-state ("streaming") evaluation: the operator is read once from HBM per pass
+// of up to 8 states; one warp per row chunk, warp-shuffle reduction, per-row combination of the chunk
+// partials in a fixed order (no atomics).  This is the HBM-bound regime of SURVEY 8(d): single-state
+// f / N / JVP at m ~ 3000 streams nnz_sym * 12 B.
+struct StreamChunk {
+  int32_t row;
+  int32_t count;
+  int64_t begin;
+};
+struct StreamPack {
+  int32_t m = 0, nin = 0;
+  bool symmetric = false;
+  int64_t nentries = 0, nchunks = 0;
+  DeviceBuffer<uint32_t> ab;        // a | b << 16 per entry (16-bit mode indices)
+  DeviceBuffer<double> val;
+  DeviceBuffer<StreamChunk> chunks;
+  DeviceBuffer<int32_t> row_chunk_ptr;  // [m+1]
+  // [nchunks][8] chunk partials, one buffer per CUDA stream that evaluates this operator
+  mutable std::map<cudaStream_t, std::unique_ptr<DeviceBuffer<double>>> partials;
+  double* partial_for(cudaStream_t st) const;
+  void build(std::vector<Term> terms, int32_t m, bool symmetric);
+};
+// Optional dense linear part (row-major L1r, L2r, value L1 + L2*invR), may be null.
+void launch_stream(const StreamPack& sp, int mode, const double* dX, const double* dY, int64_t nstates,
+                   int64_t ldx, double* dOUT, int64_t ldo, const double* L1r, const double* L2r, double invR,
+                   cudaStream_t stream);
 
 // Sliced-ELL structure of the Jacobian  DN[i,j] = sum_k M[(i,j),k] x_k  (SparseBilinear.jl:75-91).
 struct JacobianPack {

@@ -12,6 +12,20 @@ struct ca_model {
   ca::JacobianPack jac;        // of Q, built on first use (Df, device-resident solver)
   bool jac_built = false;
   std::vector<ca::Term> qterms;  // folded Q = B^-1 N (ordered j,k), kept on the host for the lazy builds
+  ca::StreamPack stream;         // few-state streaming form of Q, built on first use
+  bool stream_built = false;
+  ca::DeviceBuffer<double> L1r, L2r;  // row-major copies of L1, L2 for the streaming kernel's dense part
+  ca::StreamPack& streaming() {
+    if (!stream_built) {
+      stream.build(qterms, (int32_t)m, true);
+      stream_built = true;
+    }
+    return stream;
+  }
+  // f (mode QUAD) or Df action (mode JVP) for an ensemble on the device: DMMA kernel for ensembles,
+  // streaming kernel for a few states or when the state tile does not fit
+  void eval_dev(int mode, const double* dX, const double* dV, int64_t nstates, int64_t ldx, double R,
+                double* dOUT, int64_t ldo, cudaStream_t st);
   ca::JacobianPack& jacobian() {
     if (!jac_built) {
       jac.build(qterms, (int32_t)m);

@@ -1,0 +1,229 @@
+// Few-state sparse-bilinear evaluation: coalesced CSR stream with warp-level reductions (HBM-bound).
+//
+// Replaces the reference's COO loop (src/SparseBilinear.jl:56-65) when there are too few states to
+// amortise the operator over a DMMA tile: single-state N(x), N(x,y), f(x,R) and the matrix-free Jacobian
+// action for Newton-Krylov.  Each warp owns one chunk of one output row; lanes read consecutive
+// (a|b, value) entries (12 B, coalesced), gather the factors of up to NB states from shared memory,
+// and the 32 partial sums are combined by shuffles; a second tiny kernel adds the chunk partials of every
+// row in chunk order, so results do not depend on scheduling.
+#include <algorithm>
+
+#include "bilinear.h"
+#include "bilinear_kernels.cuh"
+
+namespace ca {
+
+namespace {
+
+constexpr int kStreamThreads = 256;
+
+template <int NB, int MODE>
+__global__ void __launch_bounds__(kStreamThreads)
+stream_kernel(const uint32_t* __restrict__ ab, const double* __restrict__ val,
+              const StreamChunk* __restrict__ chunks, int64_t nchunks, int nin, const double* __restrict__ X,
+              const double* __restrict__ Y, int64_t ldx, int nb, double* __restrict__ partial) {
+  extern __shared__ double sm[];
+  double* xs = sm;                                    // [nin][NB]
+  double* ys = MODE == MODE_QUAD ? sm : sm + (size_t)nin * NB;
+  for (int o = threadIdx.x; o < nin * NB; o += kStreamThreads) {
+    const int j = o / NB, s = o % NB;
+    double vx = 0.0, vy = 0.0;
+    if (j == nin - 1) {
+      vx = 1.0;
+      vy = MODE == MODE_JVP ? 0.0 : 1.0;
+    } else if (s < nb) {
+      vx = X[s + ldx * (int64_t)j];
+      if (MODE != MODE_QUAD) vy = Y[s + ldx * (int64_t)j];
+    }
+    xs[o] = vx;
+    if (MODE != MODE_QUAD) ys[o] = vy;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * kStreamThreads) >> 5;
+  for (int64_t c = ((int64_t)blockIdx.x * kStreamThreads + threadIdx.x) >> 5; c < nchunks; c += warps) {
+    const StreamChunk ch = chunks[c];
+    double acc[NB];
+#pragma unroll
+    for (int s = 0; s < NB; ++s) acc[s] = 0.0;
+    for (int e = lane; e < ch.count; e += 32) {
+      const uint32_t w = __ldg(ab + ch.begin + e);
+      const double v = __ldg(val + ch.begin + e);
+      const int a = w & 0xffff, b = w >> 16;
+#pragma unroll
+      for (int s = 0; s < NB; ++s) {
+        double p;
+        if (MODE == MODE_QUAD) p = xs[a * NB + s] * xs[b * NB + s];
+        else if (MODE == MODE_ORDERED) p = xs[a * NB + s] * ys[b * NB + s];
+        else p = xs[a * NB + s] * ys[b * NB + s] + ys[a * NB + s] * xs[b * NB + s];
+        acc[s] = fma(v, p, acc[s]);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < NB; ++s) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < NB; ++s) partial[c * 8 + s] = acc[s];
+    }
+  }
+}
+
+// out[s, row] = sum of the row's chunk partials (+ dense linear part: one warp per row)
+template <int MODE>
+__global__ void __launch_bounds__(kStreamThreads)
+stream_combine_kernel(const double* __restrict__ partial, const int32_t* __restrict__ row_chunk_ptr, int m,
+                      int nb, const double* __restrict__ L1r, const double* __restrict__ L2r, double invR,
+                      const double* __restrict__ X, const double* __restrict__ Y, int64_t ldx,
+                      double* __restrict__ OUT, int64_t ldo) {
+  const int lane = threadIdx.x & 31;
+  const int row = (int)(((int64_t)blockIdx.x * kStreamThreads + threadIdx.x) >> 5);
+  if (row >= m) return;
+  for (int s = 0; s < nb; ++s) {
+    double acc = 0.0;
+    if (L1r) {  // (L1 + L2/R) x ; for the Jacobian action the linear part acts on the direction
+      const double* V = MODE == MODE_JVP ? Y : X;
+      for (int j = lane; j < m; j += 32)
+        acc = fma(fma(L2r[(size_t)row * m + j], invR, L1r[(size_t)row * m + j]), V[s + ldx * (int64_t)j], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    }
+    if (lane == 0) {
+      for (int c = row_chunk_ptr[row]; c < row_chunk_ptr[row + 1]; ++c) acc += partial[(int64_t)c * 8 + s];
+      OUT[s + ldo * (int64_t)row] = acc;
+    }
+  }
+}
+
+template <int NB, int MODE>
+void launch_nb(const StreamPack& sp, const double* dX, const double* dY, int nb, int64_t ldx, double* dOUT,
+               int64_t ldo, const double* L1r, const double* L2r, double invR, cudaStream_t st) {
+  const size_t smem = (MODE == MODE_QUAD ? 1 : 2) * (size_t)sp.nin * NB * sizeof(double);
+  auto kern = stream_kernel<NB, MODE>;
+  CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sms = 0, dev = 0;
+  CA_CUDA(cudaGetDevice(&dev));
+  CA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int per_sm = 0;
+  CA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStreamThreads, smem));
+  if (per_sm < 1) fail(CA_ERR_UNSUPPORTED, "streaming kernel does not fit (smem %zu B)", smem);
+  double* partial = sp.partial_for(st);
+  if (sp.nchunks > 0) {
+    const int64_t want = (sp.nchunks + kStreamThreads / 32 - 1) / (kStreamThreads / 32);
+    const int grid = (int)std::min<int64_t>(want, (int64_t)sms * per_sm);
+    kern<<<grid, kStreamThreads, smem, st>>>(sp.ab.ptr, sp.val.ptr, sp.chunks.ptr, sp.nchunks, sp.nin, dX, dY,
+                                             ldx, nb, partial);
+    CA_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  const int grid2 = (sp.m * 32 + kStreamThreads - 1) / kStreamThreads;
+  stream_combine_kernel<MODE><<<grid2, kStreamThreads, 0, st>>>(partial, sp.row_chunk_ptr.ptr, sp.m, nb,
+                                                               L1r, L2r, invR, dX, dY, ldx, dOUT, ldo);
+  CA_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+template <int MODE>
+void launch_mode(const StreamPack& sp, const double* dX, const double* dY, int64_t nstates, int64_t ldx,
+                 double* dOUT, int64_t ldo, const double* L1r, const double* L2r, double invR, cudaStream_t st) {
+  // widest batch whose state tile fits in shared memory
+  int optin = 0, dev = 0;
+  CA_CUDA(cudaGetDevice(&dev));
+  CA_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t per_state = (MODE == MODE_QUAD ? 1 : 2) * (size_t)sp.nin * sizeof(double);
+  int nbmax = 8;
+  while (nbmax > 1 && per_state * nbmax > (size_t)optin / 2) nbmax /= 2;  // keep two CTAs per SM
+  if (per_state > (size_t)optin) fail(CA_ERR_UNSUPPORTED, "m = %d is too large for the streaming kernel", sp.m);
+  for (int64_t s0 = 0; s0 < nstates;) {
+    const int64_t left = nstates - s0;
+    int nb = (int)std::min<int64_t>(left, nbmax);
+    const double* x = dX + s0;
+    const double* y = dY ? dY + s0 : nullptr;
+    double* o = dOUT + s0;
+    if (nb >= 8) { nb = 8; launch_nb<8, MODE>(sp, x, y, nb, ldx, o, ldo, L1r, L2r, invR, st); }
+    else if (nb >= 4) { nb = 4; launch_nb<4, MODE>(sp, x, y, nb, ldx, o, ldo, L1r, L2r, invR, st); }
+    else if (nb >= 2) { nb = 2; launch_nb<2, MODE>(sp, x, y, nb, ldx, o, ldo, L1r, L2r, invR, st); }
+    else { nb = 1; launch_nb<1, MODE>(sp, x, y, nb, ldx, o, ldo, L1r, L2r, invR, st); }
+    s0 += nb;
+  }
+}
+
+}  // namespace
+
+void StreamPack::build(std::vector<Term> terms, int32_t m_, bool symmetric_) {
+  m = m_;
+  nin = m + 1;
+  symmetric = symmetric_;
+  if (nin > 65536) fail(CA_ERR_UNSUPPORTED, "m = %d exceeds the 16-bit mode index", m);
+  for (auto& t : terms)
+    if (symmetric && t.a > t.b) std::swap(t.a, t.b);
+  std::sort(terms.begin(), terms.end(), [](const Term& x, const Term& y) {
+    if (x.i != y.i) return x.i < y.i;
+    if (x.a != y.a) return x.a < y.a;
+    return x.b < y.b;
+  });
+  std::vector<uint32_t> hab;
+  std::vector<double> hval;
+  std::vector<int64_t> rowptr(m + 1, 0);
+  hab.reserve(terms.size());
+  hval.reserve(terms.size());
+  for (size_t r = 0; r < terms.size();) {
+    size_t e = r;
+    double s = 0;
+    while (e < terms.size() && terms[e].i == terms[r].i && terms[e].a == terms[r].a && terms[e].b == terms[r].b)
+      s += terms[e++].v;
+    if (s != 0.0) {
+      hab.push_back((uint32_t)terms[r].a | ((uint32_t)terms[r].b << 16));
+      hval.push_back(s);
+      rowptr[terms[r].i + 1]++;
+    }
+    r = e;
+  }
+  for (int i = 0; i < m; ++i) rowptr[i + 1] += rowptr[i];
+  nentries = (int64_t)hab.size();
+  // chunk length: enough chunks to fill the machine, long enough to amortise the reduction
+  int64_t clen = nentries / (148 * 64);
+  clen = std::max<int64_t>(128, std::min<int64_t>(4096, clen));
+  clen = (clen + 31) / 32 * 32;
+  std::vector<StreamChunk> hchunks;
+  std::vector<int32_t> rcp(m + 1, 0);
+  for (int i = 0; i < m; ++i) {
+    for (int64_t b = rowptr[i]; b < rowptr[i + 1]; b += clen)
+      hchunks.push_back(StreamChunk{i, (int32_t)std::min<int64_t>(clen, rowptr[i + 1] - b), b});
+    rcp[i + 1] = (int32_t)hchunks.size();
+  }
+  nchunks = (int64_t)hchunks.size();
+  ab.upload(hab.data(), hab.size());
+  val.upload(hval.data(), hval.size());
+  chunks.upload(hchunks.data(), hchunks.size());
+  row_chunk_ptr.upload(rcp.data(), rcp.size());
+  partials.clear();
+  CA_CUDA(cudaStreamSynchronize(nullptr));
+}
+
+double* StreamPack::partial_for(cudaStream_t st) const {
+  auto& slot = partials[st];
+  if (!slot) {
+    slot.reset(new DeviceBuffer<double>);
+    slot->alloc((size_t)std::max<int64_t>(nchunks, 1) * 8);
+  }
+  return slot->ptr;
+}
+
+void launch_stream(const StreamPack& sp, int mode, const double* dX, const double* dY, int64_t nstates,
+                   int64_t ldx, double* dOUT, int64_t ldo, const double* L1r, const double* L2r, double invR,
+                   cudaStream_t stream) {
+  if (nstates <= 0) return;
+  if (mode != MODE_QUAD && !dY) fail(CA_ERR_INVALID, "second ensemble missing");
+  if (mode != MODE_ORDERED && !sp.symmetric) fail(CA_ERR_INVALID, "quadratic/JVP evaluation needs the symmetric stream");
+  switch (mode) {
+    case MODE_QUAD: launch_mode<MODE_QUAD>(sp, dX, dY, nstates, ldx, dOUT, ldo, L1r, L2r, invR, stream); break;
+    case MODE_ORDERED: launch_mode<MODE_ORDERED>(sp, dX, dY, nstates, ldx, dOUT, ldo, L1r, L2r, invR, stream); break;
+    case MODE_JVP: launch_mode<MODE_JVP>(sp, dX, dY, nstates, ldx, dOUT, ldo, L1r, L2r, invR, stream); break;
+    default: fail(CA_ERR_INVALID, "unknown evaluation mode %d", mode);
+  }
+}
+
+}  // namespace ca
