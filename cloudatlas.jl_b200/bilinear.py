@@ -35,6 +35,8 @@ def _stream():
 def _colmajor_ensemble(X):
     """torch CUDA ensemble -> (tensor, nstates, ld).  Accepts an (nstates, m) tensor whose
     memory is column-major (stride (1, ld)), which is what Julia hands over."""
+    if X.dim() == 2 and X.shape[0] == 1:  # a single state: any stride along the (length-1) state axis
+        return X, 1, max(X.stride(1), 1)
     if X.dim() != 2 or X.stride(0) != 1:
         raise CloudAtlasError(1, "ensemble must be nstates x m with unit stride along states "
                                  "(column-major, as a Julia Matrix); use ensemble_empty() or X.t().contiguous().t()")
@@ -70,7 +72,7 @@ class SparseBilinear:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _destroy is not None:  # module globals may already be gone at interpreter exit
             _destroy(h)
             self._h = None
 

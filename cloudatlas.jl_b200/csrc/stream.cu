@@ -15,7 +15,8 @@ namespace ca {
 
 namespace {
 
-constexpr int kStreamThreads = 256;
+constexpr int kStreamThreads = 512;
+constexpr int kStreamUnroll = 4;  // independent entry loads in flight per lane
 
 template <int NB, int MODE>
 __global__ void __launch_bounds__(kStreamThreads)
@@ -23,8 +24,8 @@ stream_kernel(const uint32_t* __restrict__ ab, const double* __restrict__ val,
               const StreamChunk* __restrict__ chunks, int64_t nchunks, int nin, const double* __restrict__ X,
               const double* __restrict__ Y, int64_t ldx, int nb, double* __restrict__ partial) {
   extern __shared__ double sm[];
-  double* xs = sm;                                    // [nin][NB]
-  double* ys = MODE == MODE_QUAD ? sm : sm + (size_t)nin * NB;
+  double* xs = sm;                                    // [NB][nin]: one contiguous vector per state, so that the
+  double* ys = MODE == MODE_QUAD ? sm : sm + (size_t)nin * NB;  // consecutive second factors of a row hit consecutive banks
   for (int o = threadIdx.x; o < nin * NB; o += kStreamThreads) {
     const int j = o / NB, s = o % NB;
     double vx = 0.0, vy = 0.0;
@@ -35,8 +36,8 @@ stream_kernel(const uint32_t* __restrict__ ab, const double* __restrict__ val,
       vx = X[s + ldx * (int64_t)j];
       if (MODE != MODE_QUAD) vy = Y[s + ldx * (int64_t)j];
     }
-    xs[o] = vx;
-    if (MODE != MODE_QUAD) ys[o] = vy;
+    xs[s * nin + j] = vx;
+    if (MODE != MODE_QUAD) ys[s * nin + j] = vy;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -46,19 +47,32 @@ stream_kernel(const uint32_t* __restrict__ ab, const double* __restrict__ val,
     double acc[NB];
 #pragma unroll
     for (int s = 0; s < NB; ++s) acc[s] = 0.0;
-    for (int e = lane; e < ch.count; e += 32) {
-      const uint32_t w = __ldg(ab + ch.begin + e);
-      const double v = __ldg(val + ch.begin + e);
+    const uint32_t* pab = ab + ch.begin;
+    const double* pval = val + ch.begin;
+    auto contribute = [&](uint32_t w, double v) {
       const int a = w & 0xffff, b = w >> 16;
 #pragma unroll
       for (int s = 0; s < NB; ++s) {
         double p;
-        if (MODE == MODE_QUAD) p = xs[a * NB + s] * xs[b * NB + s];
-        else if (MODE == MODE_ORDERED) p = xs[a * NB + s] * ys[b * NB + s];
-        else p = xs[a * NB + s] * ys[b * NB + s] + ys[a * NB + s] * xs[b * NB + s];
+        if (MODE == MODE_QUAD) p = xs[s * nin + a] * xs[s * nin + b];
+        else if (MODE == MODE_ORDERED) p = xs[s * nin + a] * ys[s * nin + b];
+        else p = xs[s * nin + a] * ys[s * nin + b] + ys[s * nin + a] * xs[s * nin + b];
         acc[s] = fma(v, p, acc[s]);
       }
+    };
+    int e = lane;
+    for (; e + 32 * (kStreamUnroll - 1) < ch.count; e += 32 * kStreamUnroll) {
+      uint32_t w[kStreamUnroll];
+      double v[kStreamUnroll];
+#pragma unroll
+      for (int u = 0; u < kStreamUnroll; ++u) {
+        w[u] = __ldg(pab + e + 32 * u);
+        v[u] = __ldg(pval + e + 32 * u);
+      }
+#pragma unroll
+      for (int u = 0; u < kStreamUnroll; ++u) contribute(w[u], v[u]);
     }
+    for (; e < ch.count; e += 32) contribute(__ldg(pab + e), __ldg(pval + e));
 #pragma unroll
     for (int s = 0; s < NB; ++s) {
 #pragma unroll

@@ -48,7 +48,7 @@ class ModelOperators:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _destroy is not None:  # module globals may already be gone at interpreter exit
             _destroy(h)
             self._h = None
 
