@@ -90,6 +90,31 @@ void ca_model::set_R(double R, cudaStream_t stream) {
 void ca_model::eval_dev(int mode, const double* dX, const double* dV, int64_t nstates, int64_t ldx, double R,
                         double* dOUT, int64_t ldo, cudaStream_t st) {
   if (!(R != 0.0)) fail(CA_ERR_INVALID, "R must be non-zero");
+  if (mode == MODE_QUAD && m <= kJitMaxM && nstates >= kJitMinStates && !small.failed) {
+    if (!small_tried) {
+      small_tried = true;
+      std::vector<int32_t> li, lj;
+      for (int j = 0; j < (int)m; ++j)
+        for (int i = 0; i < (int)m; ++i)
+          if (hL1[i + (size_t)m * j] != 0.0 || hL2[i + (size_t)m * j] != 0.0) { li.push_back(i); lj.push_back(j); }
+      small.build(merge_terms(qterms, true), li, lj, (int)m);
+    }
+    if (small.ready) {
+      const double invR = 1.0 / R;
+      if (!small.lc_set || invR != small.cur_invR) {
+        std::vector<double> lc(small.lin_i.size());
+        for (size_t e = 0; e < lc.size(); ++e) {
+          const size_t at = small.lin_i[e] + (size_t)m * small.lin_j[e];
+          lc[e] = std::fma(hL2[at], invR, hL1[at]);
+        }
+        CA_CUDA(cudaDeviceSynchronize());  // LC is shared by every stream using this model
+        small.set_linear(lc.data(), st);
+        small.cur_invR = invR;
+      }
+      small.launch(dX, nstates, ldx, dOUT, ldo, st);
+      return;
+    }
+  }
   if (nstates > kStreamMaxStates && batched_fits(op, mode)) {
     set_R(R, st);
     launch_batched(op, mode, dX, dV, nstates, ldx, dOUT, ldo, st);
@@ -247,6 +272,8 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
     h->lin_l2.upload(l2.data(), l2.size());
     h->L1.upload(hL1.data(), hL1.size());
     h->L2.upload(hL2.data(), hL2.size());
+    h->hL1 = hL1;
+    h->hL2 = hL2;
     {
       std::vector<double> r1((size_t)m * m), r2((size_t)m * m);
       for (int i = 0; i < m; ++i)
@@ -355,3 +382,15 @@ int32_t ca_model_jac(ca_model* h, const double* x, double R, double* Df) {
 }
 
 }  // extern "C"
+
+extern "C" int32_t ca_model_kernel_path(ca_model* h, int64_t nstates, int32_t* path, const char** source,
+                                        const char** log) {
+  return guarded([&] {
+    if (!h || !path) fail(CA_ERR_INVALID, "null argument");
+    if (h->m <= kJitMaxM && nstates >= kJitMinStates && h->small.ready) *path = 2;
+    else if (nstates > kStreamMaxStates && batched_fits(h->op, MODE_QUAD)) *path = 0;
+    else *path = 1;
+    if (source) *source = h->small.source.c_str();
+    if (log) *log = h->small.log.c_str();
+  });
+}

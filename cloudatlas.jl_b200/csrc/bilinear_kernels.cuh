@@ -20,7 +20,8 @@ namespace ca {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kNtMax = 2;
-constexpr int kPrefetch = 4;
+constexpr int kPrefetch = 4;       // operator values: k-steps in flight per warp
+constexpr int kPrefetchPairs = 4;  // pair words are needed first in a k-step (address math): fetched further ahead
 
 enum : int { MODE_QUAD = 0, MODE_ORDERED = 1, MODE_JVP = 2 };
 
@@ -57,19 +58,20 @@ __device__ __forceinline__ void warp_range(const TileDesc& T, int warp, int& k0,
 
 template <int NT>
 struct Prefetch {
-  uint2 pw[kPrefetch];
+  uint2 pw[kPrefetchPairs];
   double bv[kPrefetch][NT];
 };
 
+__device__ __forceinline__ void prefetch_pair(uint2& pw, const uint2* pp, int step) { pw = __ldg(pp + (size_t)step * 4); }
+
 template <int NT>
-__device__ __forceinline__ void prefetch_slot(Prefetch<NT>& pf, int u, const uint2* pp, const double* vp, int step) {
-  pf.pw[u] = __ldg(pp + (size_t)step * 4);
+__device__ __forceinline__ void prefetch_vals(double (&bv)[NT], const double* vp, int step) {
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) pf.bv[u][nt] = __ldg(vp + ((size_t)step * NT + nt) * 32);
+  for (int nt = 0; nt < NT; ++nt) bv[nt] = __ldg(vp + ((size_t)step * NT + nt) * 32);
 }
 
-// Loads the first kPrefetch k-steps of this warp's share of tile T (issued before the previous tile's
-// reduction so that the L2 latency hides behind its barriers).
+// Loads the first k-steps of this warp's share of tile T (issued before the previous tile's reduction so
+// that the L2 latency hides behind its barriers).
 template <int NT>
 __device__ __forceinline__ void tile_prologue(const TileDesc& T, const uint2* __restrict__ pairs,
                                               const double* __restrict__ vals, int warp, int lane,
@@ -81,7 +83,9 @@ __device__ __forceinline__ void tile_prologue(const TileDesc& T, const uint2* __
   const uint2* pp = pairs + ((size_t)T.ks_begin + k0) * 4 + (lane & 3);
   const double* vp = vals + T.vals_off + (size_t)k0 * NT * 32 + lane;
 #pragma unroll
-  for (int u = 0; u < kPrefetch; ++u) prefetch_slot<NT>(pf, u, pp, vp, min(u, n - 1));
+  for (int u = 0; u < kPrefetchPairs; ++u) prefetch_pair(pf.pw[u], pp, min(u, n - 1));
+#pragma unroll
+  for (int u = 0; u < kPrefetch; ++u) prefetch_vals<NT>(pf.bv[u], vp, min(u, n - 1));
   pf.pw[0].x &= ~kSameA;  // the first k-step of a share always loads its first factors
 }
 
@@ -138,16 +142,21 @@ __device__ __forceinline__ void tile_accumulate(const TileDesc& T, const uint2* 
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) xa[mt] = va[mt] = 0.0;
   int i = 0;
-  for (; i + kPrefetch <= n; i += kPrefetch) {  // branch-free body: refills clamp to the last k-step
+  for (; i + kPrefetchPairs <= n; i += kPrefetchPairs) {  // branch-free body: refills clamp to the last k-step
 #pragma unroll
-    for (int u = 0; u < kPrefetch; ++u) {
-      kstep<MT, NT, MODE>(pf.pw[u], pf.bv[u], xsb, ysb, r8, xa, va, acc);
-      prefetch_slot<NT>(pf, u, pp, vp, min(i + u + kPrefetch, n - 1));
+    for (int u = 0; u < kPrefetchPairs; ++u) {
+      kstep<MT, NT, MODE>(pf.pw[u], pf.bv[u % kPrefetch], xsb, ysb, r8, xa, va, acc);
+      prefetch_pair(pf.pw[u], pp, min(i + u + kPrefetchPairs, n - 1));
+      prefetch_vals<NT>(pf.bv[u % kPrefetch], vp, min(i + u + kPrefetch, n - 1));
     }
   }
 #pragma unroll
-  for (int u = 0; u < kPrefetch - 1; ++u)
-    if (i + u < n) kstep<MT, NT, MODE>(pf.pw[u], pf.bv[u], xsb, ysb, r8, xa, va, acc);
+  for (int u = 0; u < kPrefetchPairs - 1; ++u) {
+    if (i + u < n) {
+      kstep<MT, NT, MODE>(pf.pw[u], pf.bv[u % kPrefetch], xsb, ysb, r8, xa, va, acc);
+      if (u + kPrefetch < kPrefetchPairs - 1) prefetch_vals<NT>(pf.bv[u % kPrefetch], vp, min(i + u + kPrefetch, n - 1));
+    }
+  }
 }
 
 template <int MT, int NT>

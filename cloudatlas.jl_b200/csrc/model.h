@@ -3,6 +3,7 @@
 #include <cmath>
 
 #include "bilinear.h"
+#include "jit_small.h"
 
 struct ca_model {
   int device = 0;
@@ -12,6 +13,9 @@ struct ca_model {
   ca::JacobianPack jac;        // of Q, built on first use (Df, device-resident solver)
   bool jac_built = false;
   std::vector<ca::Term> qterms;  // folded Q = B^-1 N (ordered j,k), kept on the host for the lazy builds
+  ca::SmallKernel small;         // model-specialised ensemble kernel for small m, compiled on first use
+  bool small_tried = false;
+  std::vector<double> hL1, hL2;  // host copies (column-major) for re-targeting R
   ca::StreamPack stream;         // few-state streaming form of Q, built on first use
   bool stream_built = false;
   ca::DeviceBuffer<double> L1r, L2r;  // row-major copies of L1, L2 for the streaming kernel's dense part

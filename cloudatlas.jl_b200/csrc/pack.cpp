@@ -46,6 +46,27 @@ std::vector<uint64_t> union_of(const std::vector<uint64_t>& a, const std::vector
 
 }  // namespace
 
+std::vector<Term> merge_terms(std::vector<Term> terms, bool symmetric) {
+  for (auto& t : terms)
+    if (symmetric && t.a > t.b) std::swap(t.a, t.b);
+  std::sort(terms.begin(), terms.end(), [](const Term& x, const Term& y) {
+    if (x.i != y.i) return x.i < y.i;
+    if (x.a != y.a) return x.a < y.a;
+    return x.b < y.b;
+  });
+  std::vector<Term> out;
+  out.reserve(terms.size());
+  for (size_t r = 0; r < terms.size();) {
+    size_t e = r;
+    double s = 0;
+    while (e < terms.size() && terms[e].i == terms[r].i && terms[e].a == terms[r].a && terms[e].b == terms[r].b)
+      s += terms[e++].v;
+    if (s != 0.0) out.push_back(Term{terms[r].i, terms[r].a, terms[r].b, s});
+    r = e;
+  }
+  return out;
+}
+
 PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt_max) {
   if (m <= 0) fail(CA_ERR_INVALID, "pack_terms: m must be positive");
   const int32_t nin = m + 1;

@@ -43,6 +43,9 @@ struct PackedHost {
   int64_t pair_products = 0;    // pair products formed per state (sum over tiles)
 };
 
+// Sorted by (i,a,b), duplicates summed, exact zeros dropped; symmetric: (a,b) canonicalised to a <= b first.
+std::vector<Term> merge_terms(std::vector<Term> terms, bool symmetric);
+
 // Merges duplicate (i,a,b), drops exact zeros, clusters rows, lays out fragments.
 // symmetric: (a,b) and (b,a) are the same pair (u == w); ordered otherwise.
 PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt_max);

@@ -61,6 +61,14 @@ class ModelOperators:
         return dict(zip(("m", "nnz_q_sym", "nnz_lin", "npairs", "padded_fma_per_state", "nblocks_B"),
                         (a.value for a in v)))
 
+    def kernel_path(self, nstates):
+        """(path, generated_source, nvrtc_log): which kernel serves an ensemble of this size."""
+        fn = _sig("ca_model_kernel_path", vp, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p))
+        path, src, log = C.c_int32(), C.c_char_p(), C.c_char_p()
+        check(fn(self._h, int(nstates), C.byref(path), C.byref(src), C.byref(log)))
+        names = {0: "dmma_row_tiles", 1: "csr_stream", 2: "nvrtc_straight_line"}
+        return names[path.value], (src.value or b"").decode(), (log.value or b"").decode()
+
     def f(self, x, R, out=None):
         if _is_torch(x):
             single = x.dim() == 1

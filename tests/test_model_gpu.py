@@ -83,3 +83,22 @@ def test_27d_residual_of_shipped_guess(ca, known, nagata_H):
     dev = ca.ModelOperators(ref.B, ref.A1, ref.A2, ref.N.ijk, ref.N.val)
     xg = read_asc(known["m27"]["guess_file"])
     assert abs(np.linalg.norm(dev.f(xg, 200)) / known["m27"]["norm_f_guess_R200"] - 1) < 1e-12
+
+
+def test_small_model_large_ensemble_uses_specialised_kernel(ca, nagata_H):
+    """m <= 48 and >= 4096 states: the NVRTC straight-line kernel; same parity bar, and R re-targeting works."""
+    from oracle.model import ODEModel
+    for JKL in ((1, 1, 3), (2, 2, 3)):
+        ref = ODEModel(1.0, 2.0, *JKL, nagata_H)
+        dev = ca.ModelOperators(ref.B, ref.A1, ref.A2, ref.N.ijk, ref.N.val)
+        rng = np.random.default_rng(7)
+        X = 0.1 * rng.standard_normal((5000, dev.m))
+        small = dev.f(X[:100], 200.0)                      # DMMA path
+        for R in (200.0, 350.0):
+            got = dev.f(X, R)
+            path, src, log = dev.kernel_path(5000)
+            assert path == "nvrtc_straight_line", log
+            assert "ca_small" in src
+            want = np.stack([ref.f(x, R) for x in X[:40]])
+            assert relerr(got[:40], want) < 1e-13 * max(1.0, np.linalg.cond(ref.B) / 10)
+        assert relerr(dev.f(X, 200.0)[:100], small) < 1e-14
