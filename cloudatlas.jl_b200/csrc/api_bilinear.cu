@@ -31,7 +31,7 @@ struct ca_bilinear {
   DevicePack& ordered() {
     if (!ord) {
       ord.reset(new DevicePack);
-      ord->upload(pack_terms(coo, (int32_t)m, /*symmetric=*/false, kNtMax));
+      ord->upload(pack_terms(coo, (int32_t)m, /*symmetric=*/false, kNtMax, window_modes_for((int32_t)m)));
     }
     return *ord;
   }
@@ -132,7 +132,7 @@ int32_t ca_bilinear_create(const int64_t* ijk, const double* val, int64_t nnz, i
     }
     require_device();
     CA_CUDA(cudaGetDevice(&h->device));
-    h->sym.upload(pack_terms(h->coo, (int32_t)m, /*symmetric=*/true, kNtMax));
+    h->sym.upload(pack_terms(h->coo, (int32_t)m, /*symmetric=*/true, kNtMax, window_modes_for((int32_t)m)));
     *out = h.release();
   });
 }
@@ -235,13 +235,14 @@ int32_t ca_bilinear_jacobian(ca_bilinear* h, const double* x, double* DN) {
 }  // extern "C"
 
 extern "C" int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64_t nnz, int64_t m,
-                                    int32_t symmetric, int64_t* ntiles, int64_t* nterms,
-                                    int64_t* padded_fma, int64_t* pair_products, int64_t* mismatches) {
+                                    int32_t symmetric, int32_t window_modes, int64_t* ntiles, int64_t* nterms,
+                                    int64_t* padded_fma, int64_t* pair_products, int64_t* mismatches,
+                                    int64_t* nwindows, int64_t* max_window_modes) {
   return guarded([&] {
     std::vector<Term> coo((size_t)nnz);
     for (int64_t r = 0; r < nnz; ++r)
       coo[(size_t)r] = Term{(int32_t)(ijk[r] - 1), (int32_t)(ijk[r + nnz] - 1), (int32_t)(ijk[r + 2 * nnz] - 1), val[r]};
-    PackedHost P = pack_terms(coo, (int32_t)m, symmetric != 0, kNtMax);
+    PackedHost P = pack_terms(coo, (int32_t)m, symmetric != 0, kNtMax, window_modes);
     // expected: merged terms
     struct K { int32_t i, a, b; double v; };
     auto less = [](const K& x, const K& y) {
@@ -266,18 +267,49 @@ extern "C" int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64
     std::vector<K> got;
     std::vector<char> row_seen((size_t)m, 0);
     int64_t bad = 0;
-    for (const TileDesc& T : P.tiles) {
+    // global mode index of both factors of the pair at (tile, position k)
+    auto factors = [&](size_t tile_index, const TileDesc& T, int k, int32_t& a, int32_t& b) {
+      const uint32_t pr = P.pairs[(size_t)T.ks_begin * 4 + k];
+      a = (int32_t)(pr & 0x7fff);
+      b = (int32_t)(pr >> 16);
+      if (window_modes > 0) {
+        const int ks = T.ks_begin + k / 4;
+        const WindowDesc* W = nullptr;
+        for (const WindowDesc& w : P.windows)
+          if (w.tile == (int32_t)tile_index && ks >= w.ks_begin && ks < w.ks_begin + w.nks) W = &w;
+        if (!W || a >= W->nmodes || b >= W->nmodes) { ++bad; a = b = 0; return; }
+        a = P.modes[(size_t)W->modes_off + a];
+        b = P.modes[(size_t)W->modes_off + b];
+      }
+    };
+    for (size_t ti = 0; ti < P.tiles.size(); ++ti) {
+      const TileDesc& T = P.tiles[ti];
+      std::vector<int32_t> fa(4 * (size_t)T.nks), fb(4 * (size_t)T.nks);
+      for (int k = 0; k < 4 * T.nks; ++k) factors(ti, T, k, fa[k], fb[k]);
       for (int n = 0; n < 8 * T.nt; ++n) {
         const int32_t row = P.rows[(size_t)T.rows_off + n];
         if (row < 0) continue;
         if (row_seen[(size_t)row]) ++bad;  // every output row is owned by exactly one tile
         row_seen[(size_t)row] = 1;
         for (int k = 0; k < 4 * T.nks; ++k) {
-          const uint32_t pr = P.pairs[(size_t)T.ks_begin * 4 + k];
           const double v = P.vals[(size_t)T.vals_off + ((size_t)(k / 4) * T.nt + n / 8) * 32 + (n % 8) * 4 + k % 4];
-          if (v != 0.0) got.push_back({row, (int32_t)(pr & 0x7fff), (int32_t)(pr >> 16), v});
+          if (v != 0.0) got.push_back({row, fa[k], fb[k], v});
         }
       }
+    }
+    if (window_modes > 0) {  // windows tile the k-steps of their tile, in order, and respect the mode cap
+      size_t w = 0;
+      for (size_t ti = 0; ti < P.tiles.size(); ++ti) {
+        int ks = P.tiles[ti].ks_begin;
+        bool last_seen = false;
+        for (; w < P.windows.size() && P.windows[w].tile == (int32_t)ti; ++w) {
+          bad += P.windows[w].ks_begin != ks || P.windows[w].nmodes > window_modes || last_seen;
+          ks += P.windows[w].nks;
+          last_seen = P.windows[w].last != 0;
+        }
+        bad += ks != P.tiles[ti].ks_begin + P.tiles[ti].nks || !last_seen;
+      }
+      bad += w != P.windows.size();
     }
     for (int64_t r = 0; r < m; ++r) bad += !row_seen[(size_t)r];
     std::sort(got.begin(), got.end(), less);
@@ -292,5 +324,7 @@ extern "C" int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64
     if (padded_fma) *padded_fma = P.padded_fma;
     if (pair_products) *pair_products = P.pair_products;
     if (mismatches) *mismatches = bad;
+    if (nwindows) *nwindows = (int64_t)P.windows.size();
+    if (max_window_modes) *max_window_modes = P.max_window_modes;
   });
 }

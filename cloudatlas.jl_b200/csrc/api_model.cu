@@ -218,7 +218,7 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
     for (int j = 0; j < m; ++j)
       for (int i = 0; i < m; ++i)
         if (hL1[i + (size_t)m * j] != 0.0 || hL2[i + (size_t)m * j] != 0.0) all.push_back(Term{i, j, m, 1.0});
-    PackedHost P = pack_terms(std::move(all), m, /*symmetric=*/true, kNtMax);
+    PackedHost P = pack_terms(std::move(all), m, /*symmetric=*/true, kNtMax, window_modes_for(m));
     h->qterms = std::move(qterms);
     std::vector<int64_t> pos;
     std::vector<double> l1, l2;

@@ -19,6 +19,13 @@ void DevicePack::upload(const PackedHost& P) {
   padded_fma = P.padded_fma;
   pair_products = P.pair_products;
   tiles.upload(P.tiles.data(), P.tiles.size());
+  window_modes = P.window_modes;
+  max_window_modes = P.max_window_modes;
+  nwin = (int32_t)P.windows.size();
+  nwin_nt2 = 0;
+  for (const WindowDesc& W : P.windows) nwin_nt2 += P.tiles[W.tile].nt == 2;
+  windows.upload(P.windows.data(), P.windows.size());
+  modes.upload(P.modes.data(), P.modes.size());
   host_pairs = P.pairs;
   for (auto& b : pairs_mt) b.release();
   vals.upload(P.vals.data(), P.vals.size());
@@ -103,10 +110,41 @@ void launch_mode(const DevicePack& op, const double* dX, const double* dY, int64
 
 }  // namespace
 
+int window_modes_for(int32_t m) {
+  if (const char* f = getenv("CA_FORCE_WINDOW_MODES")) {  // test hook: exercise the windowed kernel at small m
+    const int v = atoi(f);
+    if (v >= 4) return v;
+  }
+  // whole-tile packing while x and y/v tiles of 32 states fit next to the reduction buffer (m <= ~380)
+  return batched_smem_bytes<4, MODE_JVP>(m + 1) <= (size_t)227 * 1024 ? 0 : kWindowModes;
+}
+
 bool batched_fits(const DevicePack& op, int mode) {
+  if (op.window_modes > 0) return true;  // windowed packs have an m-independent footprint
   const size_t cap = device_cfg().smem_optin;
   return (mode == MODE_QUAD ? batched_smem_bytes<1, MODE_QUAD>(op.nin) : batched_smem_bytes<1, MODE_JVP>(op.nin)) <= cap;
 }
+
+namespace {
+template <int MODE>
+void launch_windowed(const DevicePack& op, const double* dX, const double* dY, int64_t nstates, int64_t ldx,
+                     double* dOUT, int64_t ldo, cudaStream_t stream) {
+  auto kern = bilinear_windowed_kernel<MODE>;
+  const int wmax = std::max(op.max_window_modes, 1);
+  const size_t smem = windowed_smem_bytes<MODE>(wmax);
+  CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  if (per_sm < 1) fail(CA_ERR_UNSUPPORTED, "windowed kernel does not fit (smem %zu B)", smem);
+  const int64_t nblocks = (nstates + 8 * kWinMT - 1) / (8 * kWinMT);
+  const int grid = (int)std::min<int64_t>(nblocks, (int64_t)device_cfg().sms * per_sm);
+  kern<<<grid, kThreads, smem, stream>>>(op.tiles.ptr, op.windows.ptr, op.nwin, op.nwin_nt2, op.modes.ptr,
+                                         op.pairs_for(kWinMT), op.vals.ptr, op.rows.ptr, wmax, op.nin - 1, dX, dY,
+                                         nstates, ldx, dOUT, ldo);
+  CA_CUDA(cudaGetLastError());
+  count_launch();
+}
+}  // namespace
 
 void launch_batched(const DevicePack& op, int mode, const double* dX, const double* dY,
                     int64_t nstates, int64_t ldx, double* dOUT, int64_t ldo, cudaStream_t stream) {
@@ -114,6 +152,15 @@ void launch_batched(const DevicePack& op, int mode, const double* dX, const doub
   if (ldx < nstates || ldo < nstates) fail(CA_ERR_INVALID, "leading dimension smaller than nstates");
   if (mode != MODE_QUAD && !dY) fail(CA_ERR_INVALID, "second ensemble missing");
   if (mode != MODE_ORDERED && !op.symmetric) fail(CA_ERR_INVALID, "quadratic/JVP evaluation needs the symmetric pack");
+  if (op.window_modes > 0) {
+    switch (mode) {
+      case MODE_QUAD: launch_windowed<MODE_QUAD>(op, dX, dY, nstates, ldx, dOUT, ldo, stream); break;
+      case MODE_ORDERED: launch_windowed<MODE_ORDERED>(op, dX, dY, nstates, ldx, dOUT, ldo, stream); break;
+      case MODE_JVP: launch_windowed<MODE_JVP>(op, dX, dY, nstates, ldx, dOUT, ldo, stream); break;
+      default: fail(CA_ERR_INVALID, "unknown evaluation mode %d", mode);
+    }
+    return;
+  }
   switch (mode) {
     case MODE_QUAD: launch_mode<MODE_QUAD>(op, dX, dY, nstates, ldx, dOUT, ldo, stream); break;
     case MODE_ORDERED: launch_mode<MODE_ORDERED>(op, dX, dY, nstates, ldx, dOUT, ldo, stream); break;

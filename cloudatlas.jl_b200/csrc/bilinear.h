@@ -21,6 +21,10 @@ struct DevicePack {
   const uint2* pairs_for(int mt) const;
   DeviceBuffer<double> vals;
   DeviceBuffer<int32_t> rows;
+  // windowed packs (large m): pair words hold window-local rows
+  int32_t window_modes = 0, nwin = 0, nwin_nt2 = 0, max_window_modes = 0;
+  DeviceBuffer<WindowDesc> windows;
+  DeviceBuffer<int32_t> modes;
   void upload(const PackedHost& P);
 };
 
@@ -33,6 +37,11 @@ using LaunchFn = std::function<void(const double*, int64_t, double*, cudaStream_
 void eval_batched_host(const LaunchFn& launch, cudaStream_t streams[2], DeviceBuffer<double> in[2],
                        DeviceBuffer<double> out[2], const double* X, int64_t nstates, double* OUT,
                        int64_t m_in, int64_t m_out);
+
+// Packing policy: operators whose two-vector state tile (x and y/v, 32 states) fits in shared memory use
+// whole-tile packing; larger ones are packed in windows of kWindowModes modes.
+constexpr int kWindowModes = 96;
+int window_modes_for(int32_t m);
 
 // true if the DMMA ensemble kernel can hold a state tile of this operator in shared memory
 bool batched_fits(const DevicePack& op, int mode);

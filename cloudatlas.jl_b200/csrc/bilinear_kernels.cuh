@@ -50,12 +50,6 @@ __host__ __device__ __forceinline__ uint32_t factor_word(int mode) {
 }
 constexpr uint32_t kSameA = 1u;
 
-// This warp's contiguous share [k0, k1) of a tile's k-steps.
-__device__ __forceinline__ void warp_range(const TileDesc& T, int warp, int& k0, int& k1) {
-  k0 = (int)(((int64_t)T.nks * warp) / kWarps);
-  k1 = (int)(((int64_t)T.nks * (warp + 1)) / kWarps);
-}
-
 template <int NT>
 struct Prefetch {
   uint2 pw[kPrefetchPairs];
@@ -70,18 +64,24 @@ __device__ __forceinline__ void prefetch_vals(double (&bv)[NT], const double* vp
   for (int nt = 0; nt < NT; ++nt) bv[nt] = __ldg(vp + ((size_t)step * NT + nt) * 32);
 }
 
-// Loads the first k-steps of this warp's share of tile T (issued before the previous tile's reduction so
-// that the L2 latency hides behind its barriers).
+// This warp's contiguous share [k0, k1) of a range of nks k-steps.
+__device__ __forceinline__ void warp_share(int nks, int warp, int& k0, int& k1) {
+  k0 = (int)(((int64_t)nks * warp) / kWarps);
+  k1 = (int)(((int64_t)nks * (warp + 1)) / kWarps);
+}
+
+// Loads the first k-steps of this warp's share of a k-step range (a whole tile, or one window of it);
+// issued before the previous range's barriers so that the L2 latency hides behind them.
+// pairs0 / vals0 point at the range's first k-step.
 template <int NT>
-__device__ __forceinline__ void tile_prologue(const TileDesc& T, const uint2* __restrict__ pairs,
-                                              const double* __restrict__ vals, int warp, int lane,
-                                              Prefetch<NT>& pf) {
+__device__ __forceinline__ void range_prologue(const uint2* __restrict__ pairs0, const double* __restrict__ vals0,
+                                               int nks, int warp, int lane, Prefetch<NT>& pf) {
   int k0, k1;
-  warp_range(T, warp, k0, k1);
+  warp_share(nks, warp, k0, k1);
   const int n = k1 - k0;
   if (n <= 0) return;
-  const uint2* pp = pairs + ((size_t)T.ks_begin + k0) * 4 + (lane & 3);
-  const double* vp = vals + T.vals_off + (size_t)k0 * NT * 32 + lane;
+  const uint2* pp = pairs0 + (size_t)k0 * 4 + (lane & 3);
+  const double* vp = vals0 + (size_t)k0 * NT * 32 + lane;
 #pragma unroll
   for (int u = 0; u < kPrefetchPairs; ++u) prefetch_pair(pf.pw[u], pp, min(u, n - 1));
 #pragma unroll
@@ -121,21 +121,16 @@ __device__ __forceinline__ void kstep(const uint2 pw, const double (&bv)[NT], co
 }
 
 template <int MT, int NT, int MODE>
-__device__ __forceinline__ void tile_accumulate(const TileDesc& T, const uint2* __restrict__ pairs,
-                                                const double* __restrict__ vals, const double* xs,
-                                                const double* ys, int warp, int lane, Prefetch<NT>& pf,
-                                                double (&acc)[MT][NT][2]) {
+__device__ __forceinline__ void range_accumulate(const uint2* __restrict__ pairs0, const double* __restrict__ vals0,
+                                                 int nks, const double* xs, const double* ys, int warp, int lane,
+                                                 Prefetch<NT>& pf, double (&acc)[MT][NT][2]) {
   const uint32_t r8 = 8u * (lane >> 2);
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
   int k0, k1;
-  warp_range(T, warp, k0, k1);
+  warp_share(nks, warp, k0, k1);
   const int n = k1 - k0;
   if (n <= 0) return;
-  const uint2* pp = pairs + ((size_t)T.ks_begin + k0) * 4 + (lane & 3);
-  const double* vp = vals + T.vals_off + (size_t)k0 * NT * 32 + lane;
+  const uint2* pp = pairs0 + (size_t)k0 * 4 + (lane & 3);
+  const double* vp = vals0 + (size_t)k0 * NT * 32 + lane;
   const char* xsb = reinterpret_cast<const char*>(xs);
   const char* ysb = reinterpret_cast<const char*>(ys);
   double xa[MT], va[MT];  // first factors, kept across k-steps while the pair list stays on the same a
@@ -196,14 +191,18 @@ __device__ __forceinline__ void run_tiles(const TileDesc* __restrict__ tiles, in
   if (tb >= te) return;
   Prefetch<NT> pf;
   TileDesc T = tiles[tb];
-  tile_prologue<NT>(T, pairs, vals, warp, lane, pf);
+  range_prologue<NT>(pairs + (size_t)T.ks_begin * 4, vals + T.vals_off, T.nks, warp, lane, pf);
   for (int t = tb; t < te; ++t) {
     double acc[MT][NT][2];
-    tile_accumulate<MT, NT, MODE>(T, pairs, vals, xs, ys, warp, lane, pf, acc);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    range_accumulate<MT, NT, MODE>(pairs + (size_t)T.ks_begin * 4, vals + T.vals_off, T.nks, xs, ys, warp, lane, pf, acc);
     const TileDesc done = T;
     if (t + 1 < te) {
       T = tiles[t + 1];
-      tile_prologue<NT>(T, pairs, vals, warp, lane, pf);
+      range_prologue<NT>(pairs + (size_t)T.ks_begin * 4, vals + T.vals_off, T.nks, warp, lane, pf);
     }
     tile_reduce_store<MT, NT>(done, rows, red, acc, warp, lane, s0, nstates, OUT, ldo);
   }
@@ -245,6 +244,124 @@ bilinear_batched_kernel(const TileDesc* __restrict__ tiles, int ntiles, int nt2_
     run_tiles<MT, 2, MODE>(tiles, 0, nt2_tiles, pairs, vals, rows, xs, ys, red, warp, lane, s0, nstates, OUT, ldo);
     run_tiles<MT, 1, MODE>(tiles, nt2_tiles, ntiles, pairs, vals, rows, xs, ys, red, warp, lane, s0, nstates, OUT, ldo);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Windowed variant for large m: instead of the whole state tile, shared memory holds the rows of the
+// modes one WINDOW of k-steps touches (<= wmax, see pack.h), gathered with cp.async into a double
+// buffer while the previous window is being multiplied.  One barrier per window; accumulators live
+// across the windows of a tile.  Footprint: 2 x wmax x 256 B per vector, independent of m.
+constexpr int kWinMT = 4;
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+template <int MODE>
+__device__ __forceinline__ void gather_window(const WindowDesc& W, const int32_t* __restrict__ modes,
+                                              double* xbuf, double* ybuf, const double* __restrict__ X,
+                                              const double* __restrict__ Y, int64_t s0, int64_t nstates,
+                                              int64_t ldx, int one_mode) {
+  constexpr int ROW = 8 * kWinMT;
+  for (int idx = threadIdx.x; idx < W.nmodes * ROW; idx += kThreads) {
+    const int l = idx / ROW, s = idx % ROW;
+    const int g = __ldg(modes + W.modes_off + l);
+    const int slot = l * ROW + (s ^ swz<kWinMT>(l));
+    if (g == one_mode) {
+      xbuf[slot] = 1.0;
+      if (MODE != MODE_QUAD) ybuf[slot] = MODE == MODE_JVP ? 0.0 : 1.0;
+    } else {
+      const bool ok = s0 + s < nstates;
+      const int64_t off = ok ? (s0 + s) + ldx * (int64_t)g : 0;
+      cp_async8(xbuf + slot, X + off, ok ? 8 : 0);
+      if (MODE != MODE_QUAD) cp_async8(ybuf + slot, Y + off, ok ? 8 : 0);
+    }
+  }
+  cp_async_commit();
+}
+
+// windows [gb, ge) all belong to tiles with NT n-tiles; gtotal = number of windows of the operator
+template <int NT, int MODE>
+__device__ __forceinline__ void run_windows(const TileDesc* __restrict__ tiles, const WindowDesc* __restrict__ windows,
+                                            int gb, int ge, int gtotal, const int32_t* __restrict__ modes,
+                                            const uint2* __restrict__ pairs, const double* __restrict__ vals,
+                                            const int32_t* __restrict__ rows, double* bufs, int wmax, int one_mode,
+                                            double* red, int warp, int lane, const double* __restrict__ X,
+                                            const double* __restrict__ Y, int64_t s0, int64_t nstates, int64_t ldx,
+                                            double* __restrict__ OUT, int64_t ldo) {
+  constexpr int MT = kWinMT, ROW = 8 * MT;
+  constexpr int NVEC = MODE == MODE_QUAD ? 1 : 2;
+  if (gb >= ge) return;
+  Prefetch<NT> pf;
+  double acc[MT][NT][2];
+  WindowDesc W = windows[gb];
+  TileDesc T = tiles[W.tile];
+  range_prologue<NT>(pairs + (size_t)W.ks_begin * 4, vals + T.vals_off + (size_t)(W.ks_begin - T.ks_begin) * NT * 32,
+                     W.nks, warp, lane, pf);
+  bool fresh = true;
+  for (int g = gb; g < ge; ++g) {
+    cp_async_wait_all();
+    __syncthreads();  // window g has landed; everyone is done with window g-1, whose buffer is now free
+    if (g + 1 < gtotal) {
+      double* nb = bufs + (size_t)((g + 1) & 1) * NVEC * wmax * ROW;
+      gather_window<MODE>(windows[g + 1], modes, nb, nb + (size_t)wmax * ROW, X, Y, s0, nstates, ldx, one_mode);
+    }
+    if (fresh) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    }
+    const double* xs = bufs + (size_t)(g & 1) * NVEC * wmax * ROW;
+    const double* ys = MODE == MODE_QUAD ? xs : xs + (size_t)wmax * ROW;
+    range_accumulate<MT, NT, MODE>(pairs + (size_t)W.ks_begin * 4,
+                                   vals + T.vals_off + (size_t)(W.ks_begin - T.ks_begin) * NT * 32, W.nks, xs, ys,
+                                   warp, lane, pf, acc);
+    const bool last = W.last != 0;
+    const TileDesc done = T;
+    if (g + 1 < ge) {
+      W = windows[g + 1];
+      T = tiles[W.tile];
+      range_prologue<NT>(pairs + (size_t)W.ks_begin * 4,
+                         vals + T.vals_off + (size_t)(W.ks_begin - T.ks_begin) * NT * 32, W.nks, warp, lane, pf);
+    }
+    if (last) tile_reduce_store<MT, NT>(done, rows, red, acc, warp, lane, s0, nstates, OUT, ldo);
+    fresh = last;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, MODE == MODE_QUAD ? 2 : 1)
+bilinear_windowed_kernel(const TileDesc* __restrict__ tiles, const WindowDesc* __restrict__ windows, int nwin,
+                         int nwin_nt2, const int32_t* __restrict__ modes, const uint2* __restrict__ pairs,
+                         const double* __restrict__ vals, const int32_t* __restrict__ rows, int wmax, int one_mode,
+                         const double* __restrict__ X, const double* __restrict__ Y, int64_t nstates, int64_t ldx,
+                         double* __restrict__ OUT, int64_t ldo) {
+  constexpr int ROW = 8 * kWinMT;
+  constexpr int NVEC = MODE == MODE_QUAD ? 1 : 2;
+  extern __shared__ __align__(16) double smem[];
+  double* bufs = smem;
+  double* red = smem + (size_t)2 * NVEC * wmax * ROW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t nblocks = (nstates + ROW - 1) / ROW;
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int64_t s0 = blk * ROW;
+    __syncthreads();  // the previous block's last window and reduction are finished
+    if (nwin > 0) gather_window<MODE>(windows[0], modes, bufs, bufs + (size_t)wmax * ROW, X, Y, s0, nstates, ldx, one_mode);
+    run_windows<2, MODE>(tiles, windows, 0, nwin_nt2, nwin, modes, pairs, vals, rows, bufs, wmax, one_mode, red, warp,
+                         lane, X, Y, s0, nstates, ldx, OUT, ldo);
+    run_windows<1, MODE>(tiles, windows, nwin_nt2, nwin, nwin, modes, pairs, vals, rows, bufs, wmax, one_mode, red,
+                         warp, lane, X, Y, s0, nstates, ldx, OUT, ldo);
+  }
+}
+
+template <int MODE>
+inline size_t windowed_smem_bytes(int wmax) {
+  const size_t row = 8 * kWinMT;
+  return ((size_t)2 * (MODE == MODE_QUAD ? 1 : 2) * wmax * row + (size_t)kWarps * kNtMax * 8 * row) * sizeof(double);
 }
 
 template <int MT, int MODE>

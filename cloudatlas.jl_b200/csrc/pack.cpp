@@ -67,7 +67,7 @@ std::vector<Term> merge_terms(std::vector<Term> terms, bool symmetric) {
   return out;
 }
 
-PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt_max) {
+PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt_max, int window_modes) {
   if (m <= 0) fail(CA_ERR_INVALID, "pack_terms: m must be positive");
   const int32_t nin = m + 1;
   if (nin > 32768) fail(CA_ERR_UNSUPPORTED, "pack_terms: m = %d exceeds the 15-bit mode index", m);
@@ -76,6 +76,7 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
   P.m = m;
   P.nin = nin;
   P.symmetric = symmetric;
+  P.window_modes = window_modes;
 
   for (auto& t : terms) {
     if (t.i < 0 || t.i >= m || t.a < 0 || t.a >= nin || t.b < 0 || t.b >= nin)
@@ -165,28 +166,108 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
     std::vector<uint64_t> U;
     for (int32_t r : trows) U = U.empty() ? rows[r].keys : union_of(U, rows[r].keys);
     T.npairs = (int32_t)U.size();
-    T.nks = (T.npairs + 3) / 4;
     T.ks_begin = (int32_t)(P.pairs.size() / 4);
     T.vals_off = (int64_t)P.vals.size();
     T.rows_off = (int32_t)P.rows.size();
     for (int n = 0; n < 8 * T.nt; ++n) P.rows.push_back(n < T.nrows ? trows[n] : -1);
-    const uint32_t padpair = (uint32_t)(nin - 1) | ((uint32_t)(nin - 1) << 16);
-    for (int k = 0; k < 4 * T.nks; ++k) {
-      if (k < T.npairs) {
-        uint32_t a = (uint32_t)(U[k] / nin), b = (uint32_t)(U[k] % nin);
-        P.pairs.push_back(a | (b << 16));
-      } else {
-        P.pairs.push_back(padpair);
+    const uint32_t ONE = (uint32_t)(nin - 1);
+    // position of every pair of U in the emitted (padded) pair sequence
+    std::vector<int32_t> where(U.size());
+    if (window_modes <= 0) {
+      T.nks = (T.npairs + 3) / 4;
+      for (int k = 0; k < 4 * T.nks; ++k) {
+        if (k < T.npairs) {
+          where[k] = k;
+          P.pairs.push_back((uint32_t)(U[k] / nin) | ((uint32_t)(U[k] % nin) << 16));
+        } else {
+          P.pairs.push_back(ONE | (ONE << 16));
+        }
       }
-    }
-    // flag k-steps whose four first factors repeat the previous k-step's (the kernel keeps them in registers)
-    for (int ks = 1; ks < T.nks; ++ks) {
-      uint32_t* cur = &P.pairs[((size_t)T.ks_begin + ks) * 4];
-      const uint32_t* prev = cur - 4;
-      bool same = true;
-      for (int c = 0; c < 4; ++c) same = same && ((cur[c] & 0x7fffu) == (prev[c] & 0x7fffu));
-      if (same)
-        for (int c = 0; c < 4; ++c) cur[c] |= 0x8000u;
+      for (int ks = 1; ks < T.nks; ++ks) {
+        uint32_t* cur = &P.pairs[((size_t)T.ks_begin + ks) * 4];
+        const uint32_t* prev = cur - 4;
+        bool same = true;
+        for (int c = 0; c < 4; ++c) same = same && ((cur[c] & 0x7fffu) == (prev[c] & 0x7fffu));
+        if (same)
+          for (int c = 0; c < 4; ++c) cur[c] |= 0x8000u;
+      }
+    } else {
+      // ---- windows: runs of equal first factor are appended while the window's mode set stays small
+      const int tile_index = (int)P.tiles.size();
+      std::vector<uint32_t> wmodes;            // sorted global modes of the open window
+      std::vector<size_t> wpairs;              // indices into U
+      int emitted = 0;                         // pairs emitted so far in this tile (incl. padding)
+      auto close_window = [&]() {
+        if (wpairs.empty()) return;
+        const bool pad = wpairs.size() % 4 != 0;
+        if (pad && !std::binary_search(wmodes.begin(), wmodes.end(), ONE)) {
+          wmodes.push_back(ONE);
+          std::sort(wmodes.begin(), wmodes.end());
+        }
+        WindowDesc W{};
+        W.ks_begin = T.ks_begin + emitted / 4;
+        W.nks = (int32_t)((wpairs.size() + 3) / 4);
+        W.modes_off = (int32_t)P.modes.size();
+        W.nmodes = (int32_t)wmodes.size();
+        W.tile = tile_index;
+        W.last = 0;
+        for (uint32_t g : wmodes) P.modes.push_back((int32_t)g);
+        auto local = [&](uint32_t g) { return (uint32_t)(std::lower_bound(wmodes.begin(), wmodes.end(), g) - wmodes.begin()); };
+        const size_t first_word = P.pairs.size();
+        for (size_t q = 0; q < (size_t)W.nks * 4; ++q) {
+          if (q < wpairs.size()) {
+            const uint64_t key = U[wpairs[q]];
+            where[wpairs[q]] = emitted + (int32_t)q;
+            P.pairs.push_back(local((uint32_t)(key / nin)) | (local((uint32_t)(key % nin)) << 16));
+          } else {
+            P.pairs.push_back(local(ONE) | (local(ONE) << 16));
+          }
+        }
+        for (int ks = 1; ks < W.nks; ++ks) {
+          uint32_t* cur = &P.pairs[first_word + (size_t)ks * 4];
+          const uint32_t* prev = cur - 4;
+          bool same = true;
+          for (int c = 0; c < 4; ++c) same = same && ((cur[c] & 0x7fffu) == (prev[c] & 0x7fffu));
+          if (same)
+            for (int c = 0; c < 4; ++c) cur[c] |= 0x8000u;
+        }
+        emitted += W.nks * 4;
+        P.max_window_modes = std::max(P.max_window_modes, W.nmodes);
+        P.windows.push_back(W);
+        wmodes.clear();
+        wpairs.clear();
+      };
+      auto merged_size = [&](const std::vector<uint32_t>& add) {
+        std::vector<uint32_t> u;
+        std::set_union(wmodes.begin(), wmodes.end(), add.begin(), add.end(), std::back_inserter(u));
+        return u;
+      };
+      const int cap = window_modes - 1;  // leave room for the padding pseudo mode
+      for (size_t r = 0; r < U.size();) {
+        size_t e = r;
+        const uint32_t a = (uint32_t)(U[r] / nin);
+        while (e < U.size() && (uint32_t)(U[e] / nin) == a) ++e;
+        // the run [r, e) shares its first factor; split it if it alone exceeds the cap
+        for (size_t q = r; q < e;) {
+          size_t q1 = std::min(e, q + (size_t)std::max(cap - 1, 1));
+          std::vector<uint32_t> add{a};
+          for (size_t z = q; z < q1; ++z) add.push_back((uint32_t)(U[z] % nin));
+          std::sort(add.begin(), add.end());
+          add.erase(std::unique(add.begin(), add.end()), add.end());
+          std::vector<uint32_t> u = merged_size(add);
+          if ((int)u.size() > cap && !wpairs.empty()) {
+            close_window();
+            u = add;
+          }
+          wmodes = std::move(u);
+          for (size_t z = q; z < q1; ++z) wpairs.push_back(z);
+          q = q1;
+        }
+        r = e;
+      }
+      close_window();
+      if (emitted > 0) P.windows.back().last = 1;
+      T.nks = emitted / 4;
     }
     P.vals.resize(P.vals.size() + (size_t)T.nks * T.nt * 32, 0.0);
     double* V = P.vals.data() + T.vals_off;
@@ -195,7 +276,8 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
       size_t pos = 0;
       for (size_t e = 0; e < rw.keys.size(); ++e) {
         while (U[pos] != rw.keys[e]) ++pos;  // both sorted; rw.keys is a subset of U
-        const int ks = (int)(pos / 4), kk = (int)(pos % 4), nt = n / 8, nn = n % 8;
+        const int at = where[pos];
+        const int ks = at / 4, kk = at % 4, nt = n / 8, nn = n % 8;
         V[((size_t)ks * T.nt + nt) * 32 + nn * 4 + kk] = rw.vals[e];  // lane = (n%8)*4 + (k%4)
       }
     }
@@ -231,10 +313,34 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
     P.tiles.push_back(T);
   }
   // wide tiles first (the kernel runs one code path per nt), long before short inside each width
-  std::stable_sort(P.tiles.begin(), P.tiles.end(), [](const TileDesc& x, const TileDesc& y) {
-    if (x.nt != y.nt) return x.nt > y.nt;
-    return x.nks > y.nks;
+  std::vector<int32_t> perm(P.tiles.size());
+  std::iota(perm.begin(), perm.end(), 0);
+  std::stable_sort(perm.begin(), perm.end(), [&](int32_t x, int32_t y) {
+    if (P.tiles[x].nt != P.tiles[y].nt) return P.tiles[x].nt > P.tiles[y].nt;
+    return P.tiles[x].nks > P.tiles[y].nks;
   });
+  std::vector<TileDesc> sorted;
+  sorted.reserve(P.tiles.size());
+  for (int32_t o : perm) sorted.push_back(P.tiles[o]);
+  if (window_modes > 0) {
+    std::vector<std::vector<WindowDesc>> by_tile(P.tiles.size());
+    for (const WindowDesc& W : P.windows) by_tile[W.tile].push_back(W);
+    P.windows.clear();
+    for (size_t t = 0; t < perm.size(); ++t) {
+      std::vector<WindowDesc>& ws = by_tile[perm[t]];
+      if (ws.empty()) {  // a tile without terms still has to write its zeros
+        WindowDesc W{};
+        W.ks_begin = sorted[t].ks_begin;
+        W.last = 1;
+        ws.push_back(W);
+      }
+      for (WindowDesc W : ws) {
+        W.tile = (int32_t)t;
+        P.windows.push_back(W);
+      }
+    }
+  }
+  P.tiles = std::move(sorted);
   return P;
 }
 

@@ -29,6 +29,19 @@ struct TileDesc {
   int32_t npairs;    // real pairs in the tile (<= 4*nks)
 };
 
+// A window is a contiguous range of a tile's k-steps whose pairs touch at most `window_modes` distinct
+// modes; the windowed kernel gathers exactly those rows of the state tile into shared memory (double
+// buffered), so its footprint no longer grows with m.  Pair words of a windowed pack hold LOCAL row
+// indices into the window's mode list.
+struct WindowDesc {
+  int32_t ks_begin;   // first k-step (global index, as TileDesc::ks_begin)
+  int32_t nks;
+  int32_t modes_off;  // offset into PackedHost::modes
+  int32_t nmodes;
+  int32_t tile;       // owning tile
+  int32_t last;       // 1 if this is the last window of its tile
+};
+
 struct PackedHost {
   int32_t m = 0;    // outputs
   int32_t nin = 0;  // inputs including the constant-one pseudo mode (index nin-1)
@@ -37,6 +50,10 @@ struct PackedHost {
   std::vector<uint32_t> pairs;  // a | (b << 16), 4 per k-step
   std::vector<double> vals;
   std::vector<int32_t> rows;
+  int32_t window_modes = 0;     // 0: not windowed (pair words hold global mode indices)
+  std::vector<WindowDesc> windows;  // in tile order
+  std::vector<int32_t> modes;       // global mode index of every local row of every window
+  int32_t max_window_modes = 0;
   int64_t nterms = 0;           // merged non-zero terms
   int64_t npairs_distinct = 0;  // distinct (a,b) over the whole operator
   int64_t padded_fma = 0;       // FMAs the tiles execute per state (incl. padding)
@@ -48,6 +65,6 @@ std::vector<Term> merge_terms(std::vector<Term> terms, bool symmetric);
 
 // Merges duplicate (i,a,b), drops exact zeros, clusters rows, lays out fragments.
 // symmetric: (a,b) and (b,a) are the same pair (u == w); ordered otherwise.
-PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt_max);
+PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt_max, int window_modes = 0);
 
 }  // namespace ca

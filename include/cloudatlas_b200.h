@@ -207,8 +207,10 @@ int32_t ca_hookstep_solve_model(ca_model* h, const double* R, const double* Xgue
  * Also reports the packing statistics the roofline accounting uses.  Structure check only -- it
  * evaluates nothing. */
 int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64_t nnz, int64_t m,
-                         int32_t symmetric, int64_t* ntiles, int64_t* nterms, int64_t* padded_fma,
-                         int64_t* pair_products, int64_t* mismatches);
+                         int32_t symmetric, int32_t window_modes /* 0 = whole-tile packing */,
+                         int64_t* ntiles, int64_t* nterms, int64_t* padded_fma,
+                         int64_t* pair_products, int64_t* mismatches, int64_t* nwindows,
+                         int64_t* max_window_modes);
 
 #ifdef __cplusplus
 }

@@ -11,17 +11,18 @@ import __graft_entry__ as g
 ca = g.load_package()
 from cloudatlas_b200._lib import _sig, c_f64p, c_i64p, check, exported_symbols, lib  # noqa: E402
 
-_selftest = _sig("ca_selftest_pack", c_i64p, c_f64p, C.c_int64, C.c_int64, C.c_int32,
-                 c_i64p, c_i64p, c_i64p, c_i64p, c_i64p)
+_selftest = _sig("ca_selftest_pack", c_i64p, c_f64p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                 c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p)
 
 
-def pack_stats(ijk, val, m, symmetric):
+def pack_stats(ijk, val, m, symmetric, window_modes=0):
     ijk = np.asfortranarray(ijk, dtype=np.int64)
     val = np.ascontiguousarray(val, dtype=np.float64)
-    out = [C.c_int64() for _ in range(5)]
-    check(_selftest(ijk.ctypes.data_as(c_i64p), val.ctypes.data_as(c_f64p), len(val), m, symmetric,
+    out = [C.c_int64() for _ in range(7)]
+    check(_selftest(ijk.ctypes.data_as(c_i64p), val.ctypes.data_as(c_f64p), len(val), m, symmetric, window_modes,
                     *[C.byref(o) for o in out]))
-    return dict(zip(("ntiles", "nterms", "padded_fma", "pair_products", "mismatches"), (o.value for o in out)))
+    return dict(zip(("ntiles", "nterms", "padded_fma", "pair_products", "mismatches", "nwindows",
+                     "max_window_modes"), (o.value for o in out)))
 
 
 def test_every_declared_symbol_is_exported():
@@ -75,6 +76,9 @@ def test_pack_roundtrip_random(seed):
     val[rng.random(nnz) < 0.1] = 0.0                        # explicit zeros are dropped
     for sym in (1, 0):
         assert pack_stats(ijk, val, m, sym)["mismatches"] == 0
+        for wm in (8, 24, 96):
+            st = pack_stats(ijk, val, m, sym, wm)
+            assert st["mismatches"] == 0 and st["max_window_modes"] <= wm
 
 
 def test_pack_fill_at_307(nagata_H):
@@ -88,3 +92,7 @@ def test_pack_fill_at_307(nagata_H):
     st = pack_stats(ijk, val, 307, 1)
     assert st["mismatches"] == 0
     assert st["nterms"] / st["padded_fma"] > 0.75
+    # windowed packing (state rows gathered per window): same structure, a few per cent of padding more
+    sw = pack_stats(ijk, val, 307, 1, 96)
+    assert sw["mismatches"] == 0 and sw["max_window_modes"] <= 96
+    assert sw["padded_fma"] < 1.05 * st["padded_fma"]

@@ -141,3 +141,44 @@ def test_m307_ensemble(ca, nagata_H):
     assert np.array_equal(N(X[1000:1100]), got[1000:1100])
     x = X[0]
     assert relerr(N.derivative(x), ref.derivative(x)) < TOL
+
+
+@pytest.mark.parametrize("wm", [8, 24, 96])
+def test_windowed_kernel_forced_at_small_m(ca, nagata_H, wm, monkeypatch):
+    """The large-m (windowed, cp.async double-buffered) kernel, forced onto small operators."""
+    import torch
+    from oracle.bilinear import SparseBilinear as Ref, eval_batched
+    monkeypatch.setenv("CA_FORCE_WINDOW_MODES", str(wm))
+    ijk, val, m = model_coo((2, 2, 3), nagata_H)
+    N, ref = ca.SparseBilinear(ijk, val, m), Ref(ijk, val, m)
+    rng = np.random.default_rng(21)
+    X = 0.1 * rng.standard_normal((1003, m))
+    Y = rng.standard_normal((1003, m))
+    assert relerr(N(X), eval_batched(ref, X)) < TOL
+    dX = torch.from_numpy(X.T.copy()).cuda().t()
+    dY = torch.from_numpy(Y.T.copy()).cuda().t()
+    idx = list(range(0, 1003, 59))
+    assert relerr(N(dX, dY).cpu().numpy()[idx], np.stack([ref(X[s], Y[s]) for s in idx])) < TOL
+    assert relerr(N.jvp(dX, dY).cpu().numpy()[idx], np.stack([ref.derivative(X[s]) @ Y[s] for s in idx])) < TOL
+    # random operator with empty rows and duplicates
+    m2, nnz = 53, 4000
+    ijk2 = rng.integers(1, m2 + 1, size=(nnz, 3))
+    ijk2[:, 0] = np.minimum(ijk2[:, 0], 40)
+    v2 = rng.standard_normal(nnz)
+    N2, ref2 = ca.SparseBilinear(ijk2, v2, m2), Ref(ijk2, v2, m2)
+    X2 = rng.standard_normal((300, m2))
+    got = N2(X2)
+    assert relerr(got, eval_batched(ref2, X2)) < TOL
+    assert np.all(got[:, 40:] == 0.0)
+
+
+def test_windowed_model_rhs(ca, nagata_H, monkeypatch):
+    from oracle.model import ODEModel
+    monkeypatch.setenv("CA_FORCE_WINDOW_MODES", "32")
+    ref = ODEModel(1.0, 2.0, 2, 2, 3, nagata_H)
+    dev = ca.ModelOperators(ref.B, ref.A1, ref.A2, ref.N.ijk, ref.N.val)
+    X = 0.1 * np.random.default_rng(3).standard_normal((700, 44))     # < 4096 states: DMMA path, not NVRTC
+    for R in (200.0, 300.0):
+        got = dev.f(X, R)
+        want = np.stack([ref.f(x, R) for x in X[:30]])
+        assert relerr(got[:30], want) < 1e-13 * max(1.0, np.linalg.cond(ref.B) / 10)
