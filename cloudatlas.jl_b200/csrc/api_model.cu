@@ -222,10 +222,22 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
     h->qterms = std::move(qterms);
     std::vector<int64_t> pos;
     std::vector<double> l1, l2;
+    // global (a, b) of the pair at position k of a tile; windowed packs store window-local indices
+    std::vector<const WindowDesc*> win_of_kstep;
+    if (P.window_modes > 0) {
+      win_of_kstep.assign(P.pairs.size() / 4, nullptr);
+      for (const WindowDesc& W : P.windows)
+        for (int ks = 0; ks < W.nks; ++ks) win_of_kstep[(size_t)W.ks_begin + ks] = &W;
+    }
     for (const TileDesc& T : P.tiles)
       for (int k = 0; k < 4 * T.nks; ++k) {
         const uint32_t pr = P.pairs[(size_t)T.ks_begin * 4 + k];
-        const int a = pr & 0x7fff, b = pr >> 16;
+        int a = pr & 0x7fff, b = pr >> 16;
+        if (P.window_modes > 0) {
+          const WindowDesc* W = win_of_kstep[(size_t)T.ks_begin + k / 4];
+          a = P.modes[(size_t)W->modes_off + a];
+          b = P.modes[(size_t)W->modes_off + b];
+        }
         if (b != m || a == m) continue;
         for (int n = 0; n < T.nrows; ++n) {
           const size_t at = (size_t)T.vals_off + ((size_t)(k / 4) * T.nt + n / 8) * 32 + (n % 8) * 4 + k % 4;
@@ -238,32 +250,20 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
       }
     // CSR of the symmetrised Q by output row, for the in-kernel evaluation of the device-resident solver
     {
-      std::vector<Term> sym = h->qterms;
-      for (auto& t : sym)
-        if (t.a > t.b) std::swap(t.a, t.b);
-      std::sort(sym.begin(), sym.end(), [](const Term& x, const Term& y) {
-        if (x.i != y.i) return x.i < y.i;
-        if (x.a != y.a) return x.a < y.a;
-        return x.b < y.b;
-      });
+      const std::vector<Term> sym = merge_terms(h->qterms, true);
       std::vector<int32_t> rowptr(m + 1, 0);
-      std::vector<uint32_t> ab;
-      std::vector<double> qv;
-      for (size_t r = 0; r < sym.size();) {
-        size_t e = r;
-        double sum = 0;
-        while (e < sym.size() && sym[e].i == sym[r].i && sym[e].a == sym[r].a && sym[e].b == sym[r].b) sum += sym[e++].v;
-        if (sum != 0.0) {
-          ab.push_back((uint32_t)sym[r].a | ((uint32_t)sym[r].b << 16));
-          qv.push_back(sum);
-          rowptr[sym[r].i + 1]++;
-        }
-        r = e;
+      std::vector<uint32_t> ab(sym.size());
+      std::vector<double> qv(sym.size());
+      for (size_t e = 0; e < sym.size(); ++e) {
+        ab[e] = (uint32_t)sym[e].a | ((uint32_t)sym[e].b << 16);
+        qv[e] = sym[e].v;
+        rowptr[sym[e].i + 1]++;
       }
       for (int i = 0; i < m; ++i) rowptr[i + 1] += rowptr[i];
       h->q_rowptr.upload(rowptr.data(), rowptr.size());
       h->q_ab.upload(ab.data(), ab.size());
       h->q_val.upload(qv.data(), qv.size());
+      CA_CUDA(cudaStreamSynchronize(nullptr));
     }
     h->nnz_lin = (int64_t)pos.size();
     h->op.upload(P);
