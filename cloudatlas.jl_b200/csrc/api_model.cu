@@ -1,7 +1,9 @@
 // C ABI: ODEModel evaluation side (reference: src/ODEModels.jl:54-58).
 #include <algorithm>
 #include <cmath>
+#include <atomic>
 #include <functional>
+#include <thread>
 #include <map>
 #include <memory>
 #include <numeric>
@@ -138,6 +140,7 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
         if (ijk[r + c * nnz] < 1 || ijk[r + c * nnz] > m64)
           fail(CA_ERR_INVALID, "ca_model_create: N entry %lld has an index outside 1:%lld", (long long)r + 1, (long long)m64);
 
+    PhaseTimer tm("ca_model_create");
     // ---- blocks of B = connected components of its non-zero pattern
     std::vector<int> comp(m);
     std::iota(comp.begin(), comp.end(), 0);
@@ -158,16 +161,26 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
       const uint64_t j = (uint64_t)ijk[r + nnz] - 1, k = (uint64_t)ijk[r + 2 * nnz] - 1;
       byrow[i].push_back({j * (uint64_t)m + k, val[r]});
     }
+    tm.lap("blocks+byrow");
     std::vector<Term> qterms;  // folded Q = B^-1 N, ordered (j,k)
-    qterms.reserve((size_t)nnz * 2);
     std::vector<double> hL1((size_t)m * m, 0.0), hL2((size_t)m * m, 0.0);
-    for (auto& kv : blocks) {
-      const std::vector<int>& G = kv.second;
+    std::vector<const std::vector<int>*> block_list;
+    for (auto& kv : blocks) block_list.push_back(&kv.second);
+    std::vector<std::vector<Term>> block_terms(block_list.size());
+    std::atomic<int> singular{0};
+    // one block of B at a time (independent: rows of different blocks do not mix), on worker threads
+    auto fold_block = [&](size_t bi) {
+      const std::vector<int>& G = *block_list[bi];
       const int g = (int)G.size();
       std::vector<double> Bg((size_t)g * g), Binv;
       for (int a = 0; a < g; ++a)
         for (int b = 0; b < g; ++b) Bg[(size_t)a * g + b] = B[G[a] + (size_t)m * G[b]];
-      invert_block(Bg, g, Binv);
+      try {
+        invert_block(Bg, g, Binv);
+      } catch (const Error&) {
+        singular = 1;
+        return;
+      }
       // linear operators: rows G of B^-1 A
       for (int a = 0; a < g; ++a)
         for (int j = 0; j < m; ++j) {
@@ -185,13 +198,14 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
         for (auto& e : byrow[G[b]]) U.push_back(e.first);
       std::sort(U.begin(), U.end());
       U.erase(std::unique(U.begin(), U.end()), U.end());
-      if (U.empty()) continue;
+      if (U.empty()) return;
       std::vector<double> D((size_t)g * U.size(), 0.0);
       for (int b = 0; b < g; ++b)
         for (auto& e : byrow[G[b]]) {
           const size_t p = std::lower_bound(U.begin(), U.end(), e.first) - U.begin();
           D[(size_t)b * U.size() + p] += e.second;
         }
+      std::vector<Term>& out_terms = block_terms[bi];
       for (int a = 0; a < g; ++a)
         for (size_t p = 0; p < U.size(); ++p) {
           double s = 0;
@@ -203,11 +217,31 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
               any = true;
             }
           }
-          if (any && s != 0.0)
-            qterms.push_back(Term{G[a], (int32_t)(U[p] / m), (int32_t)(U[p] % m), s});
+          if (any && s != 0.0) out_terms.push_back(Term{G[a], (int32_t)(U[p] / m), (int32_t)(U[p] % m), s});
         }
+    };
+    {
+      std::atomic<size_t> next{0};
+      auto work = [&]() {
+        for (size_t bi = next.fetch_add(1); bi < block_list.size(); bi = next.fetch_add(1)) fold_block(bi);
+      };
+      const unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      std::vector<std::thread> pool;
+      for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(work);
+      work();
+      for (auto& th : pool) th.join();
     }
-
+    if (singular) fail(CA_ERR_INVALID, "ca_model_create: B is singular");
+    {
+      size_t total = 0;
+      for (auto& v : block_terms) total += v.size();
+      qterms.reserve(total);
+      for (auto& v : block_terms) {
+        qterms.insert(qterms.end(), v.begin(), v.end());
+        std::vector<Term>().swap(v);
+      }
+    }
+    tm.lap("fold B^-1");
     require_device();
     std::unique_ptr<ca_model> h(new ca_model);
     CA_CUDA(cudaGetDevice(&h->device));
@@ -220,6 +254,7 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
         if (hL1[i + (size_t)m * j] != 0.0 || hL2[i + (size_t)m * j] != 0.0) all.push_back(Term{i, j, m, 1.0});
     PackedHost P = pack_terms(std::move(all), m, /*symmetric=*/true, kNtMax, window_modes_for(m));
     h->qterms = std::move(qterms);
+    tm.lap("pack");
     std::vector<int64_t> pos;
     std::vector<double> l1, l2;
     // global (a, b) of the pair at position k of a tile; windowed packs store window-local indices
@@ -265,6 +300,7 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
       h->q_val.upload(qv.data(), qv.size());
       CA_CUDA(cudaStreamSynchronize(nullptr));
     }
+    tm.lap("slots+csr");
     h->nnz_lin = (int64_t)pos.size();
     h->op.upload(P);
     h->lin_pos.upload(pos.data(), pos.size());
@@ -286,6 +322,7 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
       CA_CUDA(cudaStreamSynchronize(nullptr));
     }
     CA_CUDA(cudaStreamSynchronize(nullptr));
+    tm.lap("upload");
     *out = h.release();
   });
 }

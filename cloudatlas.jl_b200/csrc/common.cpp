@@ -1,6 +1,7 @@
 #include "common.h"
 
 #include <cstring>
+#include <ctime>
 
 namespace ca {
 
@@ -16,6 +17,19 @@ void fail(int32_t code, const char* fmt, ...) {
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
   throw Error(code, buf);
+}
+
+static double now_s() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+PhaseTimer::PhaseTimer(const char* w) : what(w), t0(now_s()), on(getenv("CA_TIMING") != nullptr) {}
+void PhaseTimer::lap(const char* phase) {
+  if (!on) return;
+  const double t = now_s();
+  fprintf(stderr, "[ca timing] %s: %s %.3f s\n", what, phase, t - t0);
+  t0 = t;
 }
 
 void require_device() {

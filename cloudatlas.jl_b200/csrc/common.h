@@ -50,6 +50,15 @@ int32_t guarded(F&& body) {
   }
 }
 
+// Wall-clock phase timer, printed to stderr when CA_TIMING is set (host-side build diagnostics).
+struct PhaseTimer {
+  const char* what;
+  double t0;
+  bool on;
+  explicit PhaseTimer(const char* w);
+  void lap(const char* phase);
+};
+
 // Requires a CUDA device of compute capability 10.x; the library has no other code path.
 void require_device();
 

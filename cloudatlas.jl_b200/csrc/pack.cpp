@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <atomic>
+#include <thread>
 #include <unordered_set>
 
 #include "common.h"
@@ -46,14 +48,46 @@ std::vector<uint64_t> union_of(const std::vector<uint64_t>& a, const std::vector
 
 }  // namespace
 
-std::vector<Term> merge_terms(std::vector<Term> terms, bool symmetric) {
+void sort_terms(std::vector<Term>& terms, int32_t m) {
+  if (m <= 0) {
+    for (const Term& t : terms) m = std::max(m, t.i + 1);
+  }
+  if (terms.size() < (size_t)1 << 16) {
+    std::sort(terms.begin(), terms.end(), [](const Term& x, const Term& y) {
+      if (x.i != y.i) return x.i < y.i;
+      if (x.a != y.a) return x.a < y.a;
+      return x.b < y.b;
+    });
+    return;
+  }
+  std::vector<size_t> start((size_t)m + 1, 0);
+  for (const Term& t : terms) start[(size_t)t.i + 1]++;
+  for (int32_t i = 0; i < m; ++i) start[(size_t)i + 1] += start[i];
+  std::vector<Term> out(terms.size());
+  {
+    std::vector<size_t> at(start.begin(), start.end() - 1);
+    for (const Term& t : terms) out[at[t.i]++] = t;
+  }
+  terms.swap(out);
+  out.clear();
+  out.shrink_to_fit();
+  const unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  std::atomic<int32_t> next{0};
+  auto work = [&]() {
+    for (int32_t i = next.fetch_add(1); i < m; i = next.fetch_add(1))
+      std::sort(terms.begin() + (ptrdiff_t)start[i], terms.begin() + (ptrdiff_t)start[(size_t)i + 1],
+                [](const Term& x, const Term& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; });
+  };
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+}
+
+std::vector<Term> merge_terms(std::vector<Term> terms, bool symmetric, int32_t m) {
   for (auto& t : terms)
     if (symmetric && t.a > t.b) std::swap(t.a, t.b);
-  std::sort(terms.begin(), terms.end(), [](const Term& x, const Term& y) {
-    if (x.i != y.i) return x.i < y.i;
-    if (x.a != y.a) return x.a < y.a;
-    return x.b < y.b;
-  });
+  sort_terms(terms, m);
   std::vector<Term> out;
   out.reserve(terms.size());
   for (size_t r = 0; r < terms.size();) {
@@ -72,6 +106,7 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
   const int32_t nin = m + 1;
   if (nin > 32768) fail(CA_ERR_UNSUPPORTED, "pack_terms: m = %d exceeds the 15-bit mode index", m);
   if (nt_max < 1) nt_max = 1;
+  PhaseTimer tm("pack_terms");
   PackedHost P;
   P.m = m;
   P.nin = nin;
@@ -83,12 +118,9 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
       fail(CA_ERR_INVALID, "pack_terms: index out of range (i=%d a=%d b=%d, m=%d)", t.i, t.a, t.b, m);
     if (symmetric && t.a > t.b) std::swap(t.a, t.b);
   }
-  std::sort(terms.begin(), terms.end(), [](const Term& x, const Term& y) {
-    if (x.i != y.i) return x.i < y.i;
-    if (x.a != y.a) return x.a < y.a;
-    return x.b < y.b;
-  });
+  sort_terms(terms, m);
 
+  tm.lap("sort");
   std::vector<Row> rows(m);
   {
     size_t r = 0;
@@ -119,6 +151,7 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
     }
   }
 
+  tm.lap("rows+sketches");
   // ---- cluster rows with near-identical pair sets
   std::vector<int32_t> order(m);
   std::iota(order.begin(), order.end(), 0);
@@ -158,6 +191,7 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
     clusters.push_back(std::move(cl));
   }
 
+  tm.lap("cluster");
   // ---- split clusters into tiles of <= 8*nt_max rows, lay out fragments
   auto emit_tile = [&](const std::vector<int32_t>& trows) {
     TileDesc T{};
@@ -298,6 +332,7 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
       done += take;
     }
   }
+  tm.lap("emit tiles");
   // rows without any term still have to be written (as zeros)
   for (size_t e = 0; e < empties.size(); e += 8 * (size_t)nt_max) {
     size_t n = std::min(empties.size() - e, (size_t)8 * nt_max);

@@ -60,8 +60,11 @@ struct PackedHost {
   int64_t pair_products = 0;    // pair products formed per state (sum over tiles)
 };
 
+// In-place sort by (i, a, b): counting sort by output row, then per-row sorts on worker threads.
+void sort_terms(std::vector<Term>& terms, int32_t m);
+
 // Sorted by (i,a,b), duplicates summed, exact zeros dropped; symmetric: (a,b) canonicalised to a <= b first.
-std::vector<Term> merge_terms(std::vector<Term> terms, bool symmetric);
+std::vector<Term> merge_terms(std::vector<Term> terms, bool symmetric, int32_t m = -1);
 
 // Merges duplicate (i,a,b), drops exact zeros, clusters rows, lays out fragments.
 // symmetric: (a,b) and (b,a) are the same pair (u == w); ordered otherwise.

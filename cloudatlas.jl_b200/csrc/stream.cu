@@ -173,11 +173,7 @@ void StreamPack::build(std::vector<Term> terms, int32_t m_, bool symmetric_) {
   if (nin > 65536) fail(CA_ERR_UNSUPPORTED, "m = %d exceeds the 16-bit mode index", m);
   for (auto& t : terms)
     if (symmetric && t.a > t.b) std::swap(t.a, t.b);
-  std::sort(terms.begin(), terms.end(), [](const Term& x, const Term& y) {
-    if (x.i != y.i) return x.i < y.i;
-    if (x.a != y.a) return x.a < y.a;
-    return x.b < y.b;
-  });
+  sort_terms(terms, m);
   std::vector<uint32_t> hab;
   std::vector<double> hval;
   std::vector<int64_t> rowptr(m + 1, 0);
