@@ -22,6 +22,7 @@ namespace {
 
 constexpr double kAbsZero = 1e-15;  // ODEModels.jl:46
 constexpr double kRelZero = 1e-11;  // cancellation-aware: |sum| vs sum|terms|
+constexpr double kQuadZero = 1e-15; // quadrature result vs sum|w f g h|: below this it is an analytic zero
 
 struct DevBasis {
   int m, J, K, npid, nx, nz;
@@ -61,14 +62,21 @@ __global__ void y3_kernel(const double* __restrict__ F, const double* __restrict
   if (t >= total) return;
   const int r = (int)(t % npid), q = (int)((t / npid) % npid), p = (int)(t / ((int64_t)npid * npid));
   dd s{0.0, 0.0};
+  double mag = 0.0;
   if (parity[p] * parity[q] * parity[r] == 1) {  // odd integrands vanish exactly
     for (int n = 0; n < ny; ++n) {
       const dd fp{F[p * ny + n], Flo[p * ny + n]}, fq{F[q * ny + n], Flo[q * ny + n]},
           fr{F[r * ny + n], Flo[r * ny + n]}, wn{w[n], wlo[n]};
-      s = dd_add(s, dd_mul(dd_mul(wn, fp), dd_mul(fq, fr)));
+      const dd term = dd_mul(dd_mul(wn, fp), dd_mul(fq, fr));
+      s = dd_add(s, term);
+      mag += fabs(term.hi);
     }
   }
-  Y3[t] = s.hi + s.lo;
+  // Integrals that vanish analytically without being odd (orthogonality of the underlying Legendre
+  // factors) come out as ~1e-19 * sum|terms| (the node values carry a 64-bit mantissa): flush them to the
+  // exact zero the reference's polynomial algebra produces.
+  const double v = s.hi + s.lo;
+  Y3[t] = fabs(v) > kQuadZero * mag ? v : 0.0;
 }
 
 // one thread per (i,j): rows slab [r0,r1) x m, row-major

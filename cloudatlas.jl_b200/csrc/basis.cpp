@@ -230,12 +230,17 @@ BasisTables build_tables(double alpha, double gamma, const int64_t* ijkl, int64_
   T.Y2y.assign((size_t)T.npid * T.npid, 0.0);
   for (int p = 0; p < T.npid; ++p)
     for (int q = 0; q < T.npid; ++q) {
-      long double s = 0, sy = 0;
+      long double s = 0, sy = 0, mag = 0, magy = 0;
       for (int n = 0; n < T.ny; ++n) {
         const long double t = wl[n] * Fl[(size_t)p * T.ny + n] * Fl[(size_t)q * T.ny + n];
         s += t;
         sy += t * yl[n];
+        mag += fabsl(t);
+        magy += fabsl(t * yl[n]);
       }
+      // analytic zeros that are not parity zeros come out as rounding noise of the quadrature: flush them
+      if (fabsl(s) <= 1e-16L * mag) s = 0;
+      if (fabsl(sy) <= 1e-16L * magy) sy = 0;
       const int par = T.parity[p] * T.parity[q];
       T.Y2[(size_t)p * T.npid + q] = par == 1 ? (double)s : 0.0;    // odd integrand: exactly zero
       T.Y2y[(size_t)p * T.npid + q] = par == -1 ? (double)sy : 0.0;

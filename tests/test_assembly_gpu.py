@@ -133,3 +133,26 @@ def test_full_model_17d_known_answers(ca, known):
     lam = np.linalg.eigvals(modeln.Df(xs, 200.0))
     for re, im in known["m17_normalized"]["eigs_top"]:
         assert np.min(np.abs(lam - complex(re, im))) < 1e-9
+
+
+def test_m999_pattern_and_values_on_sampled_rows(ca, nagata_H):
+    """BASELINE.json configs[3]: the ~1000-mode basis (J,K,L = 5,5,16).  Total count and a sample of output rows
+    against the vectorised exact-table tier; two rows against all-rational arithmetic."""
+    from oracle.exact import assemble_N_exact
+    from oracle.fastfloat import FloatTables, assemble_N_float
+    ijkl = ca.basisIndices(5, 5, 16, lib_H(ca))
+    assert ijkl.shape[0] == 999
+    slab = ca.AssemblySlab(1.0, 2.0, ijkl)
+    assert slab.nnz == 23608304
+    ijk, val = slab.coo_host()
+    assert np.all(np.diff(ijk[:, 0]) >= 0)                       # lexicographic: i non-decreasing
+    rows = list(range(0, 999, 53))
+    fijk, fval = assemble_N_float(1, 2, ijkl, rows=rows, tables=FloatTables(1, 2, ijkl))
+    sel = np.isin(ijk[:, 0] - 1, rows)
+    assert np.array_equal(ijk[sel], fijk)
+    assert maxrel(val[sel], fval) < TOL
+    eijk, evals = assemble_N_exact(1, 2, ijkl, rows=[0, 998])
+    sel = np.isin(ijk[:, 0] - 1, [0, 998])
+    assert np.array_equal(ijk[sel], eijk)
+    ev = np.array([float(v) for v in evals])
+    assert np.max(np.abs(val[sel] - ev)) / np.max(np.abs(ev)) < TOL
