@@ -284,7 +284,8 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "model_build": {"seconds_total": build_s, "assembly_device_seconds": model.assembly_stats["device_seconds"],
-                        "world": world, "note": "index set + GPU assembly (+ all-gather) + B^-1 folding + DMMA packing"},
+                        "world": world, "note": "index set + GPU assembly (+ all-gather) + host B^-1 folding + DMMA packing"},
+        "kernel_path": model.kernel_path(n)[0],
     }
 
     if rank == 0 and world == 1 and not args.no_extras:
@@ -331,7 +332,9 @@ def hbm_case(ca, H, hbm_peak):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     gbs = 16 * m * n / (ms * 1e-3) / 1e9
-    return {"workload": "ensemble RHS, 17-mode model (J,K,L=1,1,3), 10^7 states", "bound": "hbm",
+    path, _, jitlog = model.kernel_path(n)
+    return {"workload": "ensemble RHS, 17-mode model (J,K,L=1,1,3), 10^7 states", "bound": "hbm", "kernel": path,
+            "note": "m <= 48: model-specialised straight-line kernel (NVRTC, sm_100a), x in registers",
             "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
             "evals_per_sec": n / (ms * 1e-3), "kernel_ms": ms, "algorithmic_bytes_per_state": 16 * m}
 
