@@ -310,6 +310,12 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
     h->L2.upload(hL2.data(), hL2.size());
     h->hL1 = hL1;
     h->hL2 = hL2;
+    h->hB.assign(B, B + (size_t)m * m);
+    h->hA1.assign(A1, A1 + (size_t)m * m);
+    h->hA2.assign(A2, A2 + (size_t)m * m);
+    h->ncoo.resize((size_t)nnz);
+    for (int64_t r = 0; r < nnz; ++r)
+      h->ncoo[(size_t)r] = Term{(int32_t)(ijk[r] - 1), (int32_t)(ijk[r + nnz] - 1), (int32_t)(ijk[r + 2 * nnz] - 1), val[r]};
     {
       std::vector<double> r1((size_t)m * m), r2((size_t)m * m);
       for (int i = 0; i < m; ++i)
@@ -429,5 +435,129 @@ extern "C" int32_t ca_model_kernel_path(ca_model* h, int64_t nstates, int32_t* p
     else *path = 1;
     if (source) *source = h->small.source.c_str();
     if (log) *log = h->small.log.c_str();
+  });
+}
+
+// ------------------------------------------------------------------------------------------ cnab2
+namespace {
+
+// g = c1 * n1 + c0 * n0, written into columns [m, 2m) of the stacked ensemble buffer
+__global__ void cnab2_combine_kernel(const double* __restrict__ n1, const double* __restrict__ n0, double c1,
+                                     double c0, int64_t count, double* __restrict__ g) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count) g[t] = fma(c1, n1[t], c0 * n0[t]);
+}
+
+// dense inverse by LU with partial pivoting (column-major m x m), host
+void dense_inverse(std::vector<double> A, int m, std::vector<double>& inv) {
+  std::vector<double> rm((size_t)m * m);
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) rm[(size_t)i * m + j] = A[i + (size_t)m * j];
+  std::vector<double> out;
+  invert_block(rm, m, out);  // row-major in, row-major out
+  inv.resize((size_t)m * m);
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) inv[i + (size_t)m * j] = out[(size_t)i * m + j];
+}
+
+void eval_pack(const DevicePack& dp, const StreamPack& sp, const double* dX, int64_t nstates, int64_t ldx,
+               double* dOUT, int64_t ldo, cudaStream_t st) {
+  if (nstates > kStreamMaxStates && batched_fits(dp, MODE_QUAD)) launch_batched(dp, MODE_QUAD, dX, nullptr, nstates, ldx, dOUT, ldo, st);
+  else launch_stream(sp, MODE_QUAD, dX, nullptr, nstates, ldx, dOUT, ldo, nullptr, nullptr, 0.0, st);
+}
+
+}  // namespace
+
+extern "C" int32_t ca_model_cnab2_batched_dev(ca_model* h, const double* dX0, int64_t nstates, int64_t ld, double R,
+                                              double dt, int64_t nsteps, int64_t nsave, double* dXsave,
+                                              double* dXfinal, void* stream) {
+  return guarded([&] {
+    if (!h || !dX0) fail(CA_ERR_INVALID, "null argument");
+    if (nstates <= 0 || ld < nstates) fail(CA_ERR_INVALID, "bad ensemble shape");
+    if (!(R != 0.0) || !(dt > 0.0) || nsteps < 0 || nsave <= 0) fail(CA_ERR_INVALID, "bad time-stepping parameters");
+    h->bind();
+    cudaStream_t st = (cudaStream_t)stream;
+    const int m = (int)h->m;
+    const bool few = nstates <= kStreamMaxStates;
+    // ---- N(x): raw operator
+    if (few ? !h->nraw_stream_built : !h->nraw_built) {
+      if (few) {
+        h->nraw_stream.build(h->ncoo, m, true);
+        h->nraw_stream_built = true;
+      } else {
+        h->nraw.upload(pack_terms(h->ncoo, m, true, kNtMax, window_modes_for(m)));
+        h->nraw_built = true;
+        if (!batched_fits(h->nraw, MODE_QUAD) && !h->nraw_stream_built) {
+          h->nraw_stream.build(h->ncoo, m, true);
+          h->nraw_stream_built = true;
+        }
+      }
+    }
+    // ---- [M1 M2] for this (R, dt):  LHS = B - dt/2 A, RHS = B + dt/2 A   (ODEModels.jl:149-155)
+    if (!h->cn_built || h->cn_R != R || h->cn_dt != dt) {
+      CA_CUDA(cudaDeviceSynchronize());
+      std::vector<double> lhs((size_t)m * m), rhs((size_t)m * m), M2, M1((size_t)m * m, 0.0);
+      for (size_t e = 0; e < (size_t)m * m; ++e) {
+        const double a = h->hA1[e] + (1.0 / R) * h->hA2[e];
+        lhs[e] = h->hB[e] - (dt / 2) * a;
+        rhs[e] = h->hB[e] + (dt / 2) * a;
+      }
+      dense_inverse(lhs, m, M2);
+      for (int j = 0; j < m; ++j)
+        for (int k = 0; k < m; ++k) {
+          const double r = rhs[k + (size_t)m * j];
+          if (r == 0.0) continue;
+          for (int i = 0; i < m; ++i) M1[i + (size_t)m * j] += M2[i + (size_t)m * k] * r;
+        }
+      std::vector<Term> lin;
+      lin.reserve((size_t)2 * m * m);
+      for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) {
+          if (M1[i + (size_t)m * j] != 0.0) lin.push_back(Term{i, j, 2 * m, M1[i + (size_t)m * j]});
+          if (M2[i + (size_t)m * j] != 0.0) lin.push_back(Term{i, m + j, 2 * m, M2[i + (size_t)m * j]});
+        }
+      h->cn_lin_stream.build_rect(lin, m, 2 * m);
+      h->cn_lin.upload(pack_terms(std::move(lin), m, true, kNtMax, window_modes_for(2 * m), 2 * m));
+      h->cn_R = R;
+      h->cn_dt = dt;
+      h->cn_built = true;
+    }
+    // ---- buffers: stacked [x; g] ensembles (nstates x 2m), N(x_n), N(x_{n-1})
+    const size_t per = (size_t)nstates * m;
+    for (int b = 0; b < 2; ++b) {
+      if (h->cn_buf[b].count < 2 * per) h->cn_buf[b].alloc(2 * per);
+      if (h->cn_n[b].count < per) h->cn_n[b].alloc(per);
+    }
+    double* cur = h->cn_buf[0].ptr;
+    double* nxt = h->cn_buf[1].ptr;
+    double* ncur = h->cn_n[0].ptr;
+    double* nprev = h->cn_n[1].ptr;
+    CA_CUDA(cudaMemcpy2DAsync(cur, (size_t)nstates * 8, dX0, (size_t)ld * 8, (size_t)nstates * 8, (size_t)m,
+                              cudaMemcpyDeviceToDevice, st));
+    auto evalN = [&](const double* x, double* out) {
+      eval_pack(h->nraw, h->nraw_stream, x, nstates, nstates, out, nstates, st);
+    };
+    evalN(cur, ncur);  // Nxn = N(x0); Nxn1 = N(x0)
+    int64_t k = 0;
+    const int64_t nsaves = nsteps / nsave;
+    for (int64_t n = 1; n <= nsteps; ++n) {
+      if (n > 1) {
+        std::swap(ncur, nprev);  // Nxn1 <- Nxn
+        evalN(cur, ncur);        // Nxn <- N(xn)
+      }
+      const double* n0 = n > 1 ? nprev : ncur;
+      cnab2_combine_kernel<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(ncur, n0, 1.5 * dt, -0.5 * dt, (int64_t)per,
+                                                                        cur + per);
+      CA_CUDA(cudaGetLastError());
+      count_launch();
+      eval_pack(h->cn_lin, h->cn_lin_stream, cur, nstates, nstates, nxt, nstates, st);
+      std::swap(cur, nxt);
+      if (n % nsave == 0 && dXsave && k < nsaves) {
+        CA_CUDA(cudaMemcpyAsync(dXsave + (size_t)k * per, cur, per * 8, cudaMemcpyDeviceToDevice, st));
+        ++k;
+      }
+    }
+    if (dXfinal) CA_CUDA(cudaMemcpyAsync(dXfinal, cur, per * 8, cudaMemcpyDeviceToDevice, st));
+    CA_CUDA(cudaStreamSynchronize(st));  // the stacked buffers belong to the handle
   });
 }

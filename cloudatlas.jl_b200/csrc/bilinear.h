@@ -68,6 +68,8 @@ struct StreamPack {
   mutable std::map<cudaStream_t, std::unique_ptr<DeviceBuffer<double>>> partials;
   double* partial_for(cudaStream_t st) const;
   void build(std::vector<Term> terms, int32_t m, bool symmetric);
+  // rectangular operator: m outputs, n_inputs input modes (the constant-one pseudo mode is n_inputs)
+  void build_rect(std::vector<Term> terms, int32_t m, int32_t n_inputs);
 };
 // Optional dense linear part (row-major L1r, L2r, value L1 + L2*invR), may be null.
 void launch_stream(const StreamPack& sp, int mode, const double* dX, const double* dY, int64_t nstates,

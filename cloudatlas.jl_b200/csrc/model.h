@@ -16,6 +16,17 @@ struct ca_model {
   ca::SmallKernel small;         // model-specialised ensemble kernel for small m, compiled on first use
   bool small_tried = false;
   std::vector<double> hL1, hL2;  // host copies (column-major) for re-targeting R
+  // raw (unfolded) operators for the time stepper cnab2, which needs N(x) and B separately
+  std::vector<double> hB, hA1, hA2;   // column-major host copies
+  std::vector<ca::Term> ncoo;         // N as given
+  ca::DevicePack nraw;                // symmetric pack of N, built on first use
+  ca::StreamPack nraw_stream;
+  bool nraw_built = false, nraw_stream_built = false;
+  ca::DevicePack cn_lin;              // dense [M1 M2] acting on [x; g] (2m inputs), per (R, dt)
+  ca::StreamPack cn_lin_stream;
+  double cn_R = 0.0, cn_dt = 0.0;
+  bool cn_built = false;
+  ca::DeviceBuffer<double> cn_buf[2], cn_n[2];
   ca::StreamPack stream;         // few-state streaming form of Q, built on first use
   bool stream_built = false;
   ca::DeviceBuffer<double> L1r, L2r;  // row-major copies of L1, L2 for the streaming kernel's dense part

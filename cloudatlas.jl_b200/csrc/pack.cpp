@@ -101,9 +101,10 @@ std::vector<Term> merge_terms(std::vector<Term> terms, bool symmetric, int32_t m
   return out;
 }
 
-PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt_max, int window_modes) {
+PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt_max, int window_modes,
+                      int32_t n_inputs) {
   if (m <= 0) fail(CA_ERR_INVALID, "pack_terms: m must be positive");
-  const int32_t nin = m + 1;
+  const int32_t nin = (n_inputs > 0 ? n_inputs : m) + 1;
   if (nin > 32768) fail(CA_ERR_UNSUPPORTED, "pack_terms: m = %d exceeds the 15-bit mode index", m);
   if (nt_max < 1) nt_max = 1;
   PhaseTimer tm("pack_terms");

@@ -68,6 +68,8 @@ std::vector<Term> merge_terms(std::vector<Term> terms, bool symmetric, int32_t m
 
 // Merges duplicate (i,a,b), drops exact zeros, clusters rows, lays out fragments.
 // symmetric: (a,b) and (b,a) are the same pair (u == w); ordered otherwise.
-PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt_max, int window_modes = 0);
+// n_inputs: number of input modes (default: m, a square operator); the constant-one pseudo mode is n_inputs.
+PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt_max, int window_modes = 0,
+                      int32_t n_inputs = -1);
 
 }  // namespace ca

@@ -166,6 +166,12 @@ void launch_mode(const StreamPack& sp, const double* dX, const double* dY, int64
 
 }  // namespace
 
+void StreamPack::build_rect(std::vector<Term> terms, int32_t m_, int32_t n_inputs) {
+  build(std::move(terms), m_, true);
+  nin = n_inputs + 1;
+  if (nin > 65536) fail(CA_ERR_UNSUPPORTED, "%d inputs exceed the 16-bit mode index", n_inputs);
+}
+
 void StreamPack::build(std::vector<Term> terms, int32_t m_, bool symmetric_) {
   m = m_;
   nin = m + 1;

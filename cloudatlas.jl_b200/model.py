@@ -16,6 +16,8 @@ _rhs_b = _sig("ca_model_rhs_batched", vp, c_f64p, C.c_int64, C.c_double, c_f64p)
 _rhs_b_dev = _sig("ca_model_rhs_batched_dev", vp, vp, C.c_int64, C.c_int64, C.c_double, vp, C.c_int64, vp)
 _jac = _sig("ca_model_jac", vp, c_f64p, C.c_double, c_f64p)
 _jac_dev = _sig("ca_model_jac_dev", vp, vp, C.c_double, vp, vp)
+_cnab2 = _sig("ca_model_cnab2_batched_dev", vp, vp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int64,
+              C.c_int64, vp, vp, vp)
 _jvp_b_dev = _sig("ca_model_jvp_batched_dev", vp, vp, vp, C.c_int64, C.c_int64, C.c_double, vp, C.c_int64, vp)
 
 
@@ -119,6 +121,32 @@ class ModelOperators:
         OUT = ensemble_empty(n, self.m, X.device)
         check(_jvp_b_dev(self._h, vp(X.data_ptr()), vp(V.data_ptr()), n, ld, float(R), vp(OUT.data_ptr()), n, _stream()))
         return OUT
+
+
+def cnab2(x0, odemodel, R, dt, Nsteps, nsave, verbosity=0):
+    """cnab2(x0, odemodel, R, dt, Nsteps, nsave) -> (t, X)  --  ODEModels.jl:147-181.
+
+    x0 1-D: one trajectory, X is Nsave x m like the reference's (including its quirks: t = (0:Nsave-1)*dt, and
+    row 0 is the first SAVED step because the reference overwrites its x0 row).  x0 2-D (nstates x m, numpy or
+    column-major CUDA tensor): an ensemble of trajectories, X is Nsave x nstates x m."""
+    import torch
+    Nsave = int(Nsteps) // int(nsave)
+    single = (x0.dim() if _is_torch(x0) else np.ndim(x0)) == 1
+    if _is_torch(x0):
+        X0 = x0.reshape(1, -1) if single else x0
+    else:
+        X0 = torch.from_numpy(np.ascontiguousarray(np.atleast_2d(np.asarray(x0, dtype=np.float64)).T)).cuda().t()
+    X0, n, ld = _colmajor_ensemble(X0)
+    if X0.shape[1] != odemodel.m:
+        raise CloudAtlasError(1, f"x0 has {X0.shape[1]} columns, expected {odemodel.m}")
+    save = torch.empty((max(Nsave, 1), odemodel.m, n), dtype=torch.float64, device=X0.device)
+    check(_cnab2(odemodel._h, vp(X0.data_ptr()), n, ld, float(R), float(dt), int(Nsteps), int(nsave),
+                 vp(save.data_ptr()), None, _stream()))
+    X = save[:Nsave].permute(0, 2, 1)                      # Nsave x nstates x m (views of column-major snapshots)
+    t = np.arange(Nsave) * dt
+    if not _is_torch(x0):
+        X = X.cpu().numpy()
+    return (t, X[:, 0, :]) if single else (t, X)
 
 
 class ODEModel(ModelOperators):

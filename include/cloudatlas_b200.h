@@ -163,6 +163,19 @@ int32_t ca_assembly_get_linear_dev(ca_assembly* h, double* dB, double* dA1, doub
 int32_t ca_assembly_get_coo_dev(ca_assembly* h, int64_t* d_i, int64_t* d_j, int64_t* d_k, double* d_val,
                                 void* stream);
 
+/* cnab2(x0, odemodel, R, dt, Nsteps, nsave) -- src/ODEModels.jl:147-181 (Crank-Nicolson / Adams-Bashforth 2)
+ * for an ensemble of initial conditions, on the device:
+ *     (B - dt/2 A) x_{n+1} = (B + dt/2 A) x_n + (3dt/2) N(x_n) - (dt/2) N(x_{n-1}),   A = A1 + A2/R,
+ * with N(x_{-1}) := N(x_0) as in the reference (:158-159).  Per step: one pass of the sparse-bilinear kernel
+ * for N(x_n) and one pass of a dense [M1 M2] operator with M1 = LHS^-1 RHS, M2 = LHS^-1 (factored on the
+ * host once per (R, dt)).  dX0: nstates x m (leading dimension ld).  dXsave: Nsave = Nsteps / nsave
+ * snapshots, each nstates x m contiguous (leading dimension nstates); snapshot k (0-based) is the state after
+ * (k+1)*nsave steps -- the reference stores x0 in row 1 and then overwrites it with its first save because its
+ * row counter starts at 1 (:164-177); that behaviour is reproduced.  dXfinal (may be NULL): state after Nsteps. */
+int32_t ca_model_cnab2_batched_dev(ca_model* h, const double* dX0, int64_t nstates, int64_t ld, double R,
+                                   double dt, int64_t nsteps, int64_t nsave, double* dXsave, double* dXfinal,
+                                   void* stream);
+
 /* ---- Newton-hookstep (reference: src/Hookstep.jl) --------------------------------------------- */
 /* SearchParams -- Hookstep.jl:6-14, same fields, order and defaults
  * (ftol = xtol = 1e-8, delta = 0.02, Nnewton = 20, Nhook = 4, Nmusearch = 6, verbosity = 0). */

@@ -83,3 +83,29 @@ class ODEModel:
     def Df(self, x, R):
         x = np.asarray(x, dtype=np.float64)
         return np.linalg.solve(self.B, self.A1 + (1.0 / R) * self.A2 + self.N.derivative(x))
+
+
+def cnab2(x0, model: ODEModel, R, dt, Nsteps, nsave):
+    """Crank-Nicolson / Adams-Bashforth-2 time stepping  --  ODEModels.jl:147-181, quirks included:
+    t = (0:Nsave-1)*dt (not nsave*dt), and the row counter starts at 1, so X[0] = x0 is overwritten by the
+    first saved step (:164-177)."""
+    A = model.A1 + (1.0 / R) * model.A2
+    LHS = model.B - (dt / 2) * A
+    RHS = model.B + (dt / 2) * A
+    xn = np.asarray(x0, dtype=np.float64).copy()
+    Nxn1 = model.N(xn)
+    Nxn = model.N(xn)
+    Nsave = Nsteps // nsave
+    X = np.zeros((Nsave, len(xn)))
+    t = np.arange(Nsave) * dt
+    if Nsave > 0:
+        X[0] = xn
+    k = 0
+    for n in range(1, Nsteps + 1):
+        Nxn1 = Nxn
+        Nxn = model.N(xn)
+        xn = np.linalg.solve(LHS, RHS @ xn + (3 * dt / 2) * Nxn - (dt / 2) * Nxn1)
+        if n % nsave == 0:
+            X[k] = xn
+            k += 1
+    return t, X
