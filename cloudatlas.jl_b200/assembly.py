@@ -15,6 +15,8 @@ _info = _sig("ca_assembly_info", vp, c_i64p, c_i64p, c_i64p, c_i64p, c_f64p)
 _get_linear = _sig("ca_assembly_get_linear", vp, c_f64p, c_f64p, c_f64p)
 _get_coo = _sig("ca_assembly_get_coo", vp, c_i64p, c_f64p)
 _get_linear_dev = _sig("ca_assembly_get_linear_dev", vp, vp, vp, vp, vp)
+_get_diss = _sig("ca_assembly_get_dissipation", vp, c_f64p)
+_get_diss_dev = _sig("ca_assembly_get_dissipation_dev", vp, vp, vp)
 _get_coo_dev = _sig("ca_assembly_get_coo_dev", vp, vp, vp, vp, vp, vp)
 
 
@@ -57,6 +59,11 @@ class AssemblySlab:
         check(_get_linear(self._h, *(a.ctypes.data_as(c_f64p) for a in (B, A1, A2))))
         return B, A1, A2
 
+    def dissipation_host(self):
+        D = np.zeros((self.m, self.m), order="F")
+        check(_get_diss(self._h, D.ctypes.data_as(c_f64p)))
+        return D
+
     def coo_host(self):
         ijk = np.zeros((self.nnz, 3), dtype=np.int64, order="F")
         val = np.zeros(self.nnz)
@@ -64,14 +71,16 @@ class AssemblySlab:
         return ijk, val
 
     def to_torch(self):
-        """Slab as CUDA tensors: linear [3, rows, m] float64 (row-major), idx [3, nnz] int64, val [nnz]."""
+        """Slab as CUDA tensors: linear [4, rows, m] float64 (row-major; B, A1, A2, D), idx [3, nnz] int64, val [nnz]."""
         import torch
         rows = self.row_end - self.row_begin
-        lin = torch.empty((3, rows, self.m), dtype=torch.float64, device="cuda")
+        lin = torch.empty((4, rows, self.m), dtype=torch.float64, device="cuda")
         idx = torch.empty((3, self.nnz), dtype=torch.int64, device="cuda")
         val = torch.empty((self.nnz,), dtype=torch.float64, device="cuda")
         st = vp(torch.cuda.current_stream().cuda_stream)
         check(_get_linear_dev(self._h, vp(lin[0].data_ptr()), vp(lin[1].data_ptr()), vp(lin[2].data_ptr()), st))
+        if rows:
+            check(_get_diss_dev(self._h, vp(lin[3].data_ptr()), st))
         check(_get_coo_dev(self._h, vp(idx[0].data_ptr()), vp(idx[1].data_ptr()), vp(idx[2].data_ptr()),
                            vp(val.data_ptr()), st))
         return lin, idx, val
@@ -80,7 +89,7 @@ class AssemblySlab:
 def all_gather_slabs(lin, idx, val, m, group=None):
     """The one collective of the assembly path: every rank ends up with the full operators.
 
-    lin: [3, rows_r, m], idx: [3, nnz_r], val: [nnz_r] torch tensors of this rank (any device the
+    lin: [nmat, rows_r, m], idx: [3, nnz_r], val: [nnz_r] torch tensors of this rank (any device the
     process group supports).  Slab sizes differ per rank, so sizes are exchanged first and the payload
     is padded to the largest slab.  Concatenation in rank order reproduces the reference's
     lexicographic (i,j,k) order because ranks own contiguous, increasing ranges of i."""
@@ -88,15 +97,16 @@ def all_gather_slabs(lin, idx, val, m, group=None):
     import torch.distributed as dist
     world = dist.get_world_size(group)
     dev = val.device
+    nmat = lin.shape[0]
     sizes = torch.tensor([lin.shape[1], val.shape[0]], dtype=torch.int64, device=dev)
     all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
     dist.all_gather(all_sizes, sizes, group=group)
     all_sizes = torch.stack(all_sizes).cpu()
     max_rows, max_nnz = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
     # one payload per dtype: [3*max_rows*m] doubles + [max_nnz] doubles ; [3*max_nnz] int64
-    fbuf = torch.zeros(3 * max_rows * m + max_nnz, dtype=torch.float64, device=dev)
-    fbuf[:3 * max_rows * m].view(3, max_rows, m)[:, :lin.shape[1]] = lin
-    fbuf[3 * max_rows * m:3 * max_rows * m + val.shape[0]] = val
+    fbuf = torch.zeros(nmat * max_rows * m + max_nnz, dtype=torch.float64, device=dev)
+    fbuf[:nmat * max_rows * m].view(nmat, max_rows, m)[:, :lin.shape[1]] = lin
+    fbuf[nmat * max_rows * m:nmat * max_rows * m + val.shape[0]] = val
     ibuf = torch.zeros(3 * max_nnz, dtype=torch.int64, device=dev)
     ibuf.view(3, max_nnz)[:, :idx.shape[1]] = idx
     fall = torch.empty(world * fbuf.numel(), dtype=torch.float64, device=dev)
@@ -108,8 +118,8 @@ def all_gather_slabs(lin, idx, val, m, group=None):
     lins, idxs, vals = [], [], []
     for r in range(world):
         rows_r, nnz_r = int(all_sizes[r, 0]), int(all_sizes[r, 1])
-        lins.append(fall[r, :3 * max_rows * m].view(3, max_rows, m)[:, :rows_r])
-        vals.append(fall[r, 3 * max_rows * m:3 * max_rows * m + nnz_r])
+        lins.append(fall[r, :nmat * max_rows * m].view(nmat, max_rows, m)[:, :rows_r])
+        vals.append(fall[r, nmat * max_rows * m:nmat * max_rows * m + nnz_r])
         idxs.append(iall[r, :, :nnz_r])
     return torch.cat(lins, dim=1), torch.cat(idxs, dim=1), torch.cat(vals)
 
@@ -129,7 +139,8 @@ def assemble(alpha, gamma, ijkl, normalize=False, group=None, distributed=None):
         slab = AssemblySlab(alpha, gamma, ijkl, normalize)
         B, A1, A2 = slab.linear_host()
         ijk, val = slab.coo_host()
-        return B, A1, A2, ijk, val, {"device_seconds": slab.device_seconds, "world": 1, "nnz_local": slab.nnz}
+        return B, A1, A2, ijk, val, {"device_seconds": slab.device_seconds, "world": 1, "nnz_local": slab.nnz,
+                                     "D": slab.dissipation_host()}
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     bounds = row_partition(m, world)
@@ -137,7 +148,7 @@ def assemble(alpha, gamma, ijkl, normalize=False, group=None, distributed=None):
     lin, idx, val = slab.to_torch()
     lin, idx, val = all_gather_slabs(lin, idx, val, m, group)
     lin = lin.cpu().numpy()
-    B, A1, A2 = (np.asfortranarray(lin[q]) for q in range(3))
+    B, A1, A2, D = (np.asfortranarray(lin[q]) for q in range(4))
     ijk = np.asfortranarray(idx.t().cpu().numpy())
     return B, A1, A2, ijk, val.cpu().numpy(), {"device_seconds": slab.device_seconds, "world": world,
-                                               "nnz_local": slab.nnz}
+                                               "nnz_local": slab.nnz, "D": D}

@@ -87,3 +87,15 @@ def basisComponents(alpha, gamma, ijkl, normalize=False):
     check(_components(float(alpha), float(gamma), ijkl.ctypes.data_as(c_i64p), m, int(bool(normalize)),
                       coef.ctypes.data_as(c_f64p), *[a.ctypes.data_as(c_i32p) for a in ints]))
     return {"coef": coef, "jx": ints[0], "kz": ints[1], "l": ints[2], "d": ints[3]}
+
+
+_shear = _sig("ca_basis_shear", C.c_double, C.c_double, c_i64p, C.c_int64, C.c_int32, c_f64p)
+
+
+def shearVector(alpha, gamma, ijkl, normalize=False):
+    """Psi_shear of shear_function (ODEModels.jl:65-78): shear(x) = 1 + dot(x, Psi_shear)."""
+    ijkl = np.asfortranarray(ijkl, dtype=np.int64)
+    out = np.zeros(ijkl.shape[0])
+    check(_shear(float(alpha), float(gamma), ijkl.ctypes.data_as(c_i64p), ijkl.shape[0], int(bool(normalize)),
+                 out.ctypes.data_as(c_f64p)))
+    return out

@@ -561,3 +561,33 @@ extern "C" int32_t ca_model_cnab2_batched_dev(ca_model* h, const double* dX0, in
     CA_CUDA(cudaStreamSynchronize(st));  // the stacked buffers belong to the handle
   });
 }
+
+// ------------------------------------------------------------------------------------ observables
+extern "C" int32_t ca_model_set_observables(ca_model* h, const double* shear, const double* D) {
+  return guarded([&] {
+    if (!h || !shear || !D) fail(CA_ERR_INVALID, "null argument");
+    h->bind();
+    const int m = (int)h->m;
+    std::vector<Term> t;
+    t.push_back(Term{0, m, m, 1.0});  // the constant 1 of shear(x) = 1 + dot(x, shear)
+    t.push_back(Term{1, m, m, 1.0});  // and of dissipation(x) = 1 + x' D x
+    for (int i = 0; i < m; ++i)
+      if (shear[i] != 0.0) t.push_back(Term{0, i, m, shear[i]});
+    for (int j = 0; j < m; ++j)
+      for (int i = 0; i < m; ++i)
+        if (D[i + (size_t)m * j] != 0.0) t.push_back(Term{1, i, j, D[i + (size_t)m * j]});
+    h->obs_stream.build_rect(t, 2, m);
+    h->obs.upload(pack_terms(std::move(t), 2, true, kNtMax, window_modes_for(m), m));
+    h->obs_set = true;
+  });
+}
+
+extern "C" int32_t ca_model_observables_batched_dev(ca_model* h, const double* dX, int64_t nstates, int64_t ld,
+                                                    double* dOUT, void* stream) {
+  return guarded([&] {
+    if (!h || !dX || !dOUT) fail(CA_ERR_INVALID, "null argument");
+    if (!h->obs_set) fail(CA_ERR_INVALID, "observables not set (ca_model_set_observables)");
+    h->bind();
+    eval_pack(h->obs, h->obs_stream, dX, nstates, ld, dOUT, nstates, (cudaStream_t)stream);
+  });
+}

@@ -26,6 +26,7 @@ constexpr double kQuadZero = 1e-15; // quadrature result vs sum|w f g h|: below 
 
 struct DevBasis {
   int m, J, K, npid, nx, nz;
+  double alpha, gamma;
   const double* coef;   // [m][3]
   const int32_t* jx;    // [m][3], shifted by +J
   const int32_t* kz;    // [m][3], shifted by +K
@@ -79,9 +80,25 @@ __global__ void y3_kernel(const double* __restrict__ F, const double* __restrict
   Y3[t] = fabs(v) > kQuadZero * mag ? v : 0.0;
 }
 
+// <d_p f, d_q g> for component ca of mode i and component cb of mode j; p, q in {0: none, 1: d/dx, 2: d/dy,
+// 3: d/dz}.  d/dx E_a = alpha a E_{-a}; the shifted index of -a is 2J - (a+J).
+__device__ __forceinline__ double comp_ip(const DevBasis& b, int i, int ca, int p, int j, int cb, int q) {
+  const double ci = b.coef[i * 3 + ca], cj = b.coef[j * 3 + cb];
+  if (ci == 0.0 || cj == 0.0) return 0.0;
+  int xi = b.jx[i * 3 + ca], xj = b.jx[j * 3 + cb], zi = b.kz[i * 3 + ca], zj = b.kz[j * 3 + cb];
+  double f = ci * cj;
+  if (p == 1) { f *= b.alpha * (xi - b.J); xi = 2 * b.J - xi; }
+  if (q == 1) { f *= b.alpha * (xj - b.J); xj = 2 * b.J - xj; }
+  if (p == 3) { f *= b.gamma * (zi - b.K); zi = 2 * b.K - zi; }
+  if (q == 3) { f *= b.gamma * (zj - b.K); zj = 2 * b.K - zj; }
+  const double xz = b.X2[(xi * b.nx + xj) * 2] * b.Z2[(zi * b.nz + zj) * 2];
+  if (f == 0.0 || xz == 0.0) return 0.0;
+  return f * xz * b.Y2[(b.pid[i * 3 + ca] + (p == 2)) * b.npid + b.pid[j * 3 + cb] + (q == 2)];
+}
+
 // one thread per (i,j): rows slab [r0,r1) x m, row-major
 __global__ void linear_kernel(DevBasis b, int r0, int r1, double* __restrict__ B, double* __restrict__ A1,
-                              double* __restrict__ A2) {
+                              double* __restrict__ A2, double* __restrict__ D) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)(r1 - r0) * b.m) return;
   const int i = r0 + (int)(t / b.m), j = (int)(t % b.m);
@@ -112,6 +129,14 @@ __global__ void linear_kernel(DevBasis b, int r0, int r1, double* __restrict__ B
   B[t] = vb;
   A1[t] = va1;
   A2[t] = va2;
+  // D_ij = <curl Psi_i, curl Psi_j>, expanded as in dissipation_term (ODEModels.jl:87-127); u,v,w = 0,1,2
+  const double wx = comp_ip(b, i, 2, 2, j, 2, 2) - comp_ip(b, i, 2, 2, j, 1, 3) - comp_ip(b, i, 1, 3, j, 2, 2) +
+                    comp_ip(b, i, 1, 3, j, 1, 3);
+  const double wy = comp_ip(b, i, 0, 3, j, 0, 3) - comp_ip(b, i, 0, 3, j, 2, 1) - comp_ip(b, i, 2, 1, j, 0, 3) +
+                    comp_ip(b, i, 2, 1, j, 2, 1);
+  const double wz = comp_ip(b, i, 1, 1, j, 1, 1) - comp_ip(b, i, 1, 1, j, 0, 2) - comp_ip(b, i, 0, 2, j, 1, 1) +
+                    comp_ip(b, i, 0, 2, j, 0, 2);
+  D[t] = wx + wy + wz;
 }
 
 struct IJ {  // warp-uniform factors of one (i,j) pair: the 9 (c,a) combinations
@@ -204,7 +229,7 @@ struct ca_assembly {
   int device = 0;
   int64_t m = 0, r0 = 0, r1 = 0, nnz = 0;
   double seconds = 0;
-  DeviceBuffer<double> B, A1, A2;  // (r1-r0) x m row-major
+  DeviceBuffer<double> B, A1, A2, D;  // (r1-r0) x m row-major; D = <curl, curl> (dissipation)
   DeviceBuffer<int64_t> oi, oj, ok;
   DeviceBuffer<double> oval;
   void bind() const { CA_CUDA(cudaSetDevice(device)); }
@@ -272,14 +297,15 @@ int32_t ca_assemble(double alpha, double gamma, const int64_t* ijkl, int64_t m64
     CA_CUDA(cudaGetLastError());
     count_launch();
 
-    DevBasis b{m, T.J, T.K, T.npid, 2 * T.J + 1, 2 * T.K + 1, dcoef.ptr, djx.ptr, dkz.ptr, dpid.ptr, dk2.ptr,
+    DevBasis b{m, T.J, T.K, T.npid, 2 * T.J + 1, 2 * T.K + 1, T.alpha, T.gamma, dcoef.ptr, djx.ptr, dkz.ptr, dpid.ptr, dk2.ptr,
                dX2.ptr, dZ2.ptr, dX3.ptr, dZ3.ptr, dY2.ptr, dY2y.ptr, dY3.ptr};
     const int64_t nij = (int64_t)rows * m;
     if (nij > 0) {
       h->B.alloc((size_t)nij);
       h->A1.alloc((size_t)nij);
       h->A2.alloc((size_t)nij);
-      linear_kernel<<<(unsigned)((nij + 255) / 256), 256>>>(b, r0, r1, h->B.ptr, h->A1.ptr, h->A2.ptr);
+      h->D.alloc((size_t)nij);
+      linear_kernel<<<(unsigned)((nij + 255) / 256), 256>>>(b, r0, r1, h->B.ptr, h->A1.ptr, h->A2.ptr, h->D.ptr);
       CA_CUDA(cudaGetLastError());
       count_launch();
 
@@ -356,6 +382,15 @@ int32_t ca_assembly_get_linear_dev(ca_assembly* h, double* dB, double* dA1, doub
   });
 }
 
+int32_t ca_assembly_get_dissipation_dev(ca_assembly* h, double* dD, void* stream) {
+  return guarded([&] {
+    if (!h || !dD) fail(CA_ERR_INVALID, "null argument");
+    h->bind();
+    const size_t bytes = (size_t)(h->r1 - h->r0) * h->m * sizeof(double);
+    if (bytes) CA_CUDA(cudaMemcpyAsync(dD, h->D.ptr, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  });
+}
+
 int32_t ca_assembly_get_coo_dev(ca_assembly* h, int64_t* d_i, int64_t* d_j, int64_t* d_k, double* d_val,
                                 void* stream) {
   return guarded([&] {
@@ -385,6 +420,19 @@ int32_t ca_assembly_get_linear(ca_assembly* h, double* B, double* A1, double* A2
       for (int64_t r = 0; r < rows; ++r)
         for (int64_t j = 0; j < m; ++j) dst[q][(h->r0 + r) + m * j] = slab[(size_t)r * m + j];
     }
+  });
+}
+
+int32_t ca_assembly_get_dissipation(ca_assembly* h, double* D) {
+  return guarded([&] {
+    if (!h || !D) fail(CA_ERR_INVALID, "null argument");
+    h->bind();
+    const int64_t rows = h->r1 - h->r0, m = h->m;
+    if (rows == 0) return;
+    std::vector<double> slab((size_t)rows * m);
+    CA_CUDA(cudaMemcpy(slab.data(), h->D.ptr, slab.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int64_t r = 0; r < rows; ++r)
+      for (int64_t j = 0; j < m; ++j) D[(h->r0 + r) + m * j] = slab[(size_t)r * m + j];
   });
 }
 

@@ -182,13 +182,21 @@ BasisTables build_tables(double alpha, double gamma, const int64_t* ijkl, int64_
   T.ny = (3 * (L + 3)) / 2 + 2;  // exact for degree 3(L+3)+1 <= 2 ny - 1
   std::vector<long double> yl, wl;
   gauss_legendre(T.ny, yl, wl);
+  yl.push_back(1.0L);   // two extra evaluation points (not quadrature nodes): the walls y = +1, -1
+  yl.push_back(-1.0L);
   for (auto& w : wl) w *= 0.5L;  // inner products are (1/2) int_{-1}^{1}   (BasisFunctions.jl:284)
+  const int nyw = T.ny + 2;  // nodes + the two walls
+  std::vector<long double> Fw((size_t)T.npid * 2, 0.0L);
   std::vector<long double> Fl((size_t)T.npid * T.ny, 0.0L);
   T.parity.assign(T.npid, 0);
   for (int l = 0; l <= L; ++l)
     for (int d = 0; d < 4; ++d) T.parity[4 * l + d] = (int8_t)(((l + 1 + d) % 2 == 0) ? 1 : -1);
-  for (int q = 0; q < T.ny; ++q) {
-    const long double y = yl[q];
+  for (int qq = 0; qq < nyw; ++qq) {
+    const long double y = yl[qq];
+    const bool wall = qq >= T.ny;
+    const int q = wall ? qq - T.ny : qq;
+    long double* dst = wall ? Fw.data() : Fl.data();
+    const int stride = wall ? 2 : T.ny;
     // Legendre values and first three derivatives: P'_n = P'_{n-2} + (2n-1) P_{n-1}, same one order up
     std::vector<long double> P(L + 1, 0), P1(L + 1, 0), P2(L + 1, 0), P3(L + 1, 0);
     P[0] = 1;
@@ -200,18 +208,20 @@ BasisTables build_tables(double alpha, double gamma, const int64_t* ijkl, int64_
       P3[n] = P3[n - 2] + (2 * n - 1) * P2[n - 1];
     }
     const long double u0 = (1 - y * y) * (1 - y * y), u1 = -4 * y + 4 * y * y * y, u2 = -4 + 12 * y * y, u3 = 24 * y;
-    Fl[(size_t)0 * T.ny + q] = y - y * y * y / 3;
-    Fl[(size_t)1 * T.ny + q] = 1 - y * y;
-    Fl[(size_t)2 * T.ny + q] = -2 * y;
-    Fl[(size_t)3 * T.ny + q] = -2.0L;
+    dst[(size_t)0 * stride + q] = y - y * y * y / 3;
+    dst[(size_t)1 * stride + q] = 1 - y * y;
+    dst[(size_t)2 * stride + q] = -2 * y;
+    dst[(size_t)3 * stride + q] = -2.0L;
     for (int l = 1; l <= L; ++l) {
       const long double p = P[l - 1], p1 = P1[l - 1], p2 = P2[l - 1], p3 = P3[l - 1];
-      Fl[(size_t)(4 * l + 0) * T.ny + q] = u0 * p;
-      Fl[(size_t)(4 * l + 1) * T.ny + q] = u1 * p + u0 * p1;
-      Fl[(size_t)(4 * l + 2) * T.ny + q] = u2 * p + 2 * u1 * p1 + u0 * p2;
-      Fl[(size_t)(4 * l + 3) * T.ny + q] = u3 * p + 3 * u2 * p1 + 3 * u1 * p2 + u0 * p3;
+      dst[(size_t)(4 * l + 0) * stride + q] = u0 * p;
+      dst[(size_t)(4 * l + 1) * stride + q] = u1 * p + u0 * p1;
+      dst[(size_t)(4 * l + 2) * stride + q] = u2 * p + 2 * u1 * p1 + u0 * p2;
+      dst[(size_t)(4 * l + 3) * stride + q] = u3 * p + 3 * u2 * p1 + 3 * u1 * p2 + u0 * p3;
     }
   }
+  T.wall_avg.resize(T.npid);
+  for (int p = 0; p < T.npid; ++p) T.wall_avg[p] = (double)((Fw[(size_t)p * 2] + Fw[(size_t)p * 2 + 1]) / 2);
   T.nodes.resize(T.ny);
   T.weights.resize(T.ny);
   T.wlo.resize(T.ny);
@@ -283,6 +293,18 @@ int32_t ca_basis_indices(int32_t J, int32_t K, int32_t L, const ca_symmetry* H, 
         for (int c = 0; c < 4; ++c) ijkl_out[n + c * m] = rows[(size_t)n * 4 + c];
     }
     *m_inout = m;
+  });
+}
+
+int32_t ca_basis_shear(double alpha, double gamma, const int64_t* ijkl, int64_t m, int32_t normalize,
+                       double* shear_out) {
+  return ca::guarded([&] {
+    if (!shear_out) ca::fail(CA_ERR_INVALID, "ca_basis_shear: null output");
+    ca::BasisTables T = ca::build_tables(alpha, gamma, ijkl, m, normalize != 0);
+    for (int64_t n = 0; n < m; ++n) {
+      const ca::Component& u = T.comp[(size_t)n * 3];  // the u component
+      shear_out[n] = (u.coef != 0.0 && u.jx == 0 && u.kz == 0) ? u.coef * T.wall_avg[4 * u.l + u.d + 1] : 0.0;
+    }
   });
 }
 

@@ -38,6 +38,7 @@ struct BasisTables {
   std::vector<double> Y2, Y2y;         // [npid][npid]: <F_p F_q>, <y F_p F_q>  (exact zeros by parity)
   // Fourier tables, index j+J (k+K): pair  <E_a, d^d E_b>  [n][n][2],  triple  <E_a, E_b d^d E_c>  [n][n][n][2]
   std::vector<double> X2, Z2, X3, Z3;
+  std::vector<double> wall_avg;        // [npid] (F_p(1) + F_p(-1)) / 2, for the wall shear rate
 };
 
 // normalize: scale each mode by 1/sqrt(<Psi,Psi>)  (BasisFunctions.jl:697-699)

@@ -27,6 +27,9 @@ struct ca_model {
   double cn_R = 0.0, cn_dt = 0.0;
   bool cn_built = false;
   ca::DeviceBuffer<double> cn_buf[2], cn_n[2];
+  ca::DevicePack obs;                 // two output rows: shear and dissipation (ODEModels.jl:65-137)
+  ca::StreamPack obs_stream;
+  bool obs_set = false;
   ca::StreamPack stream;         // few-state streaming form of Q, built on first use
   bool stream_built = false;
   ca::DeviceBuffer<double> L1r, L2r;  // row-major copies of L1, L2 for the streaming kernel's dense part

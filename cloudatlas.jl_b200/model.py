@@ -18,6 +18,8 @@ _jac = _sig("ca_model_jac", vp, c_f64p, C.c_double, c_f64p)
 _jac_dev = _sig("ca_model_jac_dev", vp, vp, C.c_double, vp, vp)
 _cnab2 = _sig("ca_model_cnab2_batched_dev", vp, vp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int64,
               C.c_int64, vp, vp, vp)
+_set_obs = _sig("ca_model_set_observables", vp, c_f64p, c_f64p)
+_obs_dev = _sig("ca_model_observables_batched_dev", vp, vp, C.c_int64, C.c_int64, vp, vp)
 _jvp_b_dev = _sig("ca_model_jvp_batched_dev", vp, vp, vp, C.c_int64, C.c_int64, C.c_double, vp, C.c_int64, vp)
 
 
@@ -170,6 +172,37 @@ class ODEModel(ModelOperators):
         B, A1, A2, ijk, val, self.assembly_stats = assemble(self.alpha, self.gamma, self.ijkl, normalize, group)
         super().__init__(B, A1, A2, ijk, val)
         self._N = None
+        from .basis import shearVector
+        self.Psishear = shearVector(self.alpha, self.gamma, self.ijkl, normalize)   # ODEModels.jl:65-78
+        self.D = self.assembly_stats.pop("D")                                        # ODEModels.jl:129-137
+        check(_set_obs(self._h, _f64(self.Psishear), _f64(np.asfortranarray(self.D))))
+
+    def observables(self, x):
+        """(shear, dissipation) of shear_function / dissipation_function (ODEModels.jl:65-137) for one state
+        (returns two floats) or an ensemble nstates x m (returns an nstates x 2 array: numpy in -> numpy out,
+        column-major CUDA tensor in -> CUDA tensor out)."""
+        import torch
+        if _is_torch(x):
+            X = x.reshape(1, -1) if x.dim() == 1 else x
+        else:
+            X = torch.from_numpy(np.ascontiguousarray(np.atleast_2d(np.asarray(x, dtype=np.float64)).T)).cuda().t()
+        X, n, ld = _colmajor_ensemble(X)
+        OUT = ensemble_empty(n, 2, X.device)
+        check(_obs_dev(self._h, vp(X.data_ptr()), n, ld, vp(OUT.data_ptr()), _stream()))
+        if _is_torch(x):
+            return OUT[0] if x.dim() == 1 else OUT
+        out = OUT.cpu().numpy()
+        return (float(out[0, 0]), float(out[0, 1])) if np.ndim(x) == 1 else out
+
+    def shear(self, x):
+        """shear(x) = 1 + dot(x, Psi_shear): the wall shear rate I of the notebooks' bifurcation diagrams."""
+        o = self.observables(x)
+        return o[0] if isinstance(o, tuple) else o[..., 0]
+
+    def dissipation(self, x):
+        """dissipation(x) = 1 + x' D x."""
+        o = self.observables(x)
+        return o[1] if isinstance(o, tuple) else o[..., 1]
 
     @property
     def N(self) -> SparseBilinear:

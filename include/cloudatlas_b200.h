@@ -78,6 +78,10 @@ int32_t ca_basis_indices(int32_t J, int32_t K, int32_t L, const ca_symmetry* H, 
 int32_t ca_basis_components(double alpha, double gamma, const int64_t* ijkl, int64_t m, int32_t normalize,
                             double* coef, int32_t* jx, int32_t* kz, int32_t* l, int32_t* d);
 
+/* Psi_shear of shear_function (ODEModels.jl:65-78): shear(x) = 1 + dot(x, Psi_shear).  Host only. */
+int32_t ca_basis_shear(double alpha, double gamma, const int64_t* ijkl, int64_t m, int32_t normalize,
+                       double* shear_out);
+
 /* ---- SparseBilinear (reference: src/SparseBilinear.jl) -------------------------------------- */
 /* SparseBilinear(ijk, val, m)  -- SparseBilinear.jl:7-11.  ijk: nnz x 3 column-major, 1-based.
  * Copies the COO, builds the device packing.  Fails with CA_ERR_INVALID where the reference
@@ -158,8 +162,12 @@ int32_t ca_assembly_info(const ca_assembly* h, int64_t* m, int64_t* row_begin, i
 int32_t ca_assembly_get_linear(ca_assembly* h, double* B, double* A1, double* A2);
 /* ijk: nnz x 3 column-major, 1-based; val: nnz */
 int32_t ca_assembly_get_coo(ca_assembly* h, int64_t* ijk, double* val);
+/* D_ij = <curl Psi_i, curl Psi_j> of dissipation_function (ODEModels.jl:87-137), rows [row_begin,row_end),
+ * m x m column-major host array (computed with B, A1, A2) */
+int32_t ca_assembly_get_dissipation(ca_assembly* h, double* D);
 /* device copies for the all-gather: linear slabs are (row_end-row_begin) x m ROW-major */
 int32_t ca_assembly_get_linear_dev(ca_assembly* h, double* dB, double* dA1, double* dA2, void* stream);
+int32_t ca_assembly_get_dissipation_dev(ca_assembly* h, double* dD, void* stream);
 int32_t ca_assembly_get_coo_dev(ca_assembly* h, int64_t* d_i, int64_t* d_j, int64_t* d_k, double* d_val,
                                 void* stream);
 
@@ -175,6 +183,13 @@ int32_t ca_assembly_get_coo_dev(ca_assembly* h, int64_t* d_i, int64_t* d_j, int6
 int32_t ca_model_cnab2_batched_dev(ca_model* h, const double* dX0, int64_t nstates, int64_t ld, double R,
                                    double dt, int64_t nsteps, int64_t nsave, double* dXsave, double* dXfinal,
                                    void* stream);
+
+/* Observables of ODEModels.jl:65-137 for ensembles: OUT[s,0] = shear(x_s) = 1 + dot(x_s, shear),
+ * OUT[s,1] = dissipation(x_s) = 1 + x_s' D x_s.  ca_model_set_observables copies shear (m) and D (m x m
+ * column-major, host) into the handle; OUT is nstates x 2 column-major on the device. */
+int32_t ca_model_set_observables(ca_model* h, const double* shear, const double* D);
+int32_t ca_model_observables_batched_dev(ca_model* h, const double* dX, int64_t nstates, int64_t ld,
+                                         double* dOUT, void* stream);
 
 /* ---- Newton-hookstep (reference: src/Hookstep.jl) --------------------------------------------- */
 /* SearchParams -- Hookstep.jl:6-14, same fields, order and defaults

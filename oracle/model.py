@@ -109,3 +109,31 @@ def cnab2(x0, model: ODEModel, R, dt, Nsteps, nsave):
             X[k] = xn
             k += 1
     return t, X
+
+
+def shear_vector(Psi):
+    """Psi_shear of shear_function  --  ODEModels.jl:65-78 (shear(x) = 1 + dot(x, Psi_shear))."""
+    from .algebra import bc_yderivative
+    out = np.zeros(len(Psi))
+    for i, f in enumerate(Psi):
+        u = f[0]
+        if u.ejx.waveindex == 0 and u.ekz.waveindex == 0:
+            d = bc_yderivative(u)
+            out[i] = u.coeff * (d.p(1.0) + d.p(-1.0)) / 2
+    return out
+
+
+def dissipation_matrix(Psi):
+    """D_ij = <curl Psi_i, curl Psi_j>  --  ODEModels.jl:87-137 (dissipation(x) = 1 + x' D x)."""
+    from .algebra import bc_innerproduct as ip, bc_xderivative as dx, bc_yderivative as dy, bc_zderivative as dz
+    m = len(Psi)
+    D = np.zeros((m, m))
+    for j in range(m):
+        g = Psi[j]
+        for i in range(j + 1):
+            f = Psi[i]
+            vx = (ip(dy(f[2]), dy(g[2])) - ip(dy(f[2]), dz(g[1])) - ip(dz(f[1]), dy(g[2])) + ip(dz(f[1]), dz(g[1])))
+            vy = (ip(dz(f[0]), dz(g[0])) - ip(dz(f[0]), dx(g[2])) - ip(dx(f[2]), dz(g[0])) + ip(dx(f[2]), dx(g[2])))
+            vz = (ip(dx(f[1]), dx(g[1])) - ip(dx(f[1]), dy(g[0])) - ip(dy(f[0]), dx(g[1])) + ip(dy(f[0]), dy(g[0])))
+            D[i, j] = D[j, i] = vx + vy + vz
+    return D
