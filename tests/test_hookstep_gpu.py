@@ -120,3 +120,30 @@ def test_too_large_for_shared_memory(ca, H):
     assert model.m > 95
     with pytest.raises(ca.CloudAtlasError, match="closure form"):
         ca.hookstepsolve(model, 200.0, np.zeros(model.m))
+
+
+def test_re_continuation_of_the_27d_lower_branch(ca, known, H):
+    """continue-eqb.ipynb:654-668 without BifurcationKit: natural-parameter sweep and pseudo-arclength continuation
+    of the 27d equilibrium (config 2 of BASELINE.json runs this loop)."""
+    model = ca.ODEModel(1.0, 2.0, 1, 2, 3, H)
+    x0, ok = ca.hookstepsolve(model, 200.0, read_asc(known["m27"]["guess_file"]))
+    Rs = np.linspace(200.0, 300.0, 11)
+    X, good, shear = ca.natural_continuation(model, x0, Rs, ca.SearchParams(Nnewton=30))
+    assert good.all()
+    for R, x in zip(Rs, X):
+        assert np.linalg.norm(model.f(x, R)) < 1e-8
+    assert abs(shear[0] / 1.646052703437098 - 1) < 1e-8       # continue-eqb.ipynb:179
+    # pseudo-arclength towards lower Re: the branch turns back at a saddle-node (the notebook's plot spans
+    # 150 < Re < 300) and returns to higher Re on the other side with a different shear
+    br = ca.pseudo_arclength_continuation(model, x0, 200.0, ds=0.02, nsteps=400, direction=-1, R_max=260.0,
+                                          ds_max=0.2, tol=1e-10)
+    assert br["residual"].max() < 1e-8
+    Rmin = br["R"].min()
+    assert 100.0 < Rmin < 200.0
+    assert br["R"][-1] > Rmin + 20.0                            # went around the fold
+    k = np.argmin(br["R"])
+    assert 0 < k < len(br["R"]) - 1
+    after = br["R"][k:] > 199.0
+    if after.any():                                             # the other branch at Re ~ 200 is a different state
+        j = k + np.argmax(after)
+        assert abs(br["shear"][j] - br["shear"][0]) > 1e-3
