@@ -284,7 +284,8 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
         }
       }
     // CSR of the symmetrised Q by output row, for the in-kernel evaluation of the device-resident solver
-    {
+    // (only models small enough for that solver: 3 m^2 doubles must fit in shared memory)
+    if (m <= 96) {
       const std::vector<Term> sym = merge_terms(h->qterms, true);
       std::vector<int32_t> rowptr(m + 1, 0);
       std::vector<uint32_t> ab(sym.size());

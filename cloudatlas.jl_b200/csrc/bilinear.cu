@@ -200,26 +200,19 @@ jacobian_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restrict
 
 void JacobianPack::build(const std::vector<Term>& coo, int32_t m_) {
   m = m_;
+  // contributions keyed by output entry (column j, row i) so that the threaded row-bucketed sort applies and
+  // consecutive outputs are consecutive rows of one column (coalesced stores): Term{i = column, a = row, b = source}
   struct E { int64_t out; int32_t src; double v; };
-  std::vector<E> es;
+  std::vector<Term> es;
   es.reserve(coo.size() * 2);
   for (const Term& t : coo) {
-    es.push_back({(int64_t)t.i + (int64_t)m * t.a, t.b, t.v});  // DN[i,j] += v * x[k]
-    es.push_back({(int64_t)t.i + (int64_t)m * t.b, t.a, t.v});  // DN[i,k] += v * x[j]
+    es.push_back(Term{t.a, t.i, t.b, t.v});  // DN[i,j] += v * x[k]
+    es.push_back(Term{t.b, t.i, t.a, t.v});  // DN[i,k] += v * x[j]
   }
-  std::sort(es.begin(), es.end(), [](const E& a, const E& b) {
-    return a.out != b.out ? a.out < b.out : a.src < b.src;
-  });
-  // merge duplicates
-  std::vector<E> mg;
-  mg.reserve(es.size());
-  for (size_t r = 0; r < es.size();) {
-    size_t e = r;
-    double s = 0;
-    while (e < es.size() && es[e].out == es[r].out && es[e].src == es[r].src) s += es[e++].v;
-    mg.push_back({es[r].out, es[r].src, s});
-    r = e;
-  }
+  const std::vector<Term> merged = merge_terms(std::move(es), /*symmetric=*/false, m);
+  std::vector<E> mg(merged.size());
+  for (size_t r = 0; r < merged.size(); ++r)
+    mg[r] = E{(int64_t)merged[r].a + (int64_t)m * merged[r].i, merged[r].b, merged[r].v};
   nentries = (int64_t)mg.size();
   // outputs and their ranges
   std::vector<int64_t> ostart;

@@ -74,9 +74,11 @@ void sort_terms(std::vector<Term>& terms, int32_t m) {
   const unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   std::atomic<int32_t> next{0};
   auto work = [&]() {
-    for (int32_t i = next.fetch_add(1); i < m; i = next.fetch_add(1))
-      std::sort(terms.begin() + (ptrdiff_t)start[i], terms.begin() + (ptrdiff_t)start[(size_t)i + 1],
-                [](const Term& x, const Term& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; });
+    auto less = [](const Term& x, const Term& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; };
+    for (int32_t i = next.fetch_add(1); i < m; i = next.fetch_add(1)) {
+      auto b = terms.begin() + (ptrdiff_t)start[i], e = terms.begin() + (ptrdiff_t)start[(size_t)i + 1];
+      if (!std::is_sorted(b, e, less)) std::sort(b, e, less);  // assembly and folding emit rows already sorted
+    }
   };
   std::vector<std::thread> pool;
   for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(work);

@@ -19,6 +19,7 @@ from ._lib import CloudAtlasError, _sig, c_f64p, c_i32p, check, vp
 from .model import ModelOperators
 
 CA_LOG_STEPS = 64
+DEVICE_RESIDENT_MAX_M = 95   # 3 m^2 + 9 m doubles of shared memory (include/cloudatlas_b200.h)
 
 
 @dataclass
@@ -65,6 +66,12 @@ def hookstepsolve_model(model: ModelOperators, R, xguess, params: SearchParams |
     params = params or SearchParams()
     X = np.asarray(xguess, dtype=np.float64)
     single = X.ndim == 1
+    if model.m > DEVICE_RESIDENT_MAX_M:
+        # 3 m^2 doubles no longer fit in one CTA's shared memory: host-driven search, every f / Df on the device
+        if not single:
+            raise CloudAtlasError(5, f"batched searches need m <= {DEVICE_RESIDENT_MAX_M}")
+        x, ok = _hookstepsolve_closures(lambda v: model.f(v, float(R)), lambda v: model.Df(v, float(R)), X, params)
+        return (x, ok, {"exit_reason": "host_driven", "device_seconds": None}) if return_log else (x, ok)
     X = np.asfortranarray(X.reshape(1, -1) if single else X)
     if X.shape[1] != model.m:
         raise CloudAtlasError(1, f"xguess has {X.shape[1]} columns, expected {model.m}")

@@ -115,11 +115,23 @@ def test_batched_searches_re_sweep(ca, known, model17):
     assert np.array_equal(single, X[2])           # bit-reproducible, independent of the batch
 
 
-def test_too_large_for_shared_memory(ca, H):
+def test_larger_models_use_the_host_driven_search(ca, known, H):
+    """m > 95: the C entry point refuses (shared memory), the mirror drives Hookstep.jl's loop from the host with every
+    f and Df evaluated on the device.  The 44d equilibrium, prolonged to a 111-mode basis, converges there."""
     model = ca.ODEModel(1.0, 2.0, 3, 3, 4, H)
     assert model.m > 95
-    with pytest.raises(ca.CloudAtlasError, match="closure form"):
-        ca.hookstepsolve(model, 200.0, np.zeros(model.m))
+    from cloudatlas_b200.hookstep import _solve, _CParams
+    import ctypes as C
+    small = ca.ODEModel(1.0, 2.0, 2, 2, 3, H)
+    x44, ok = ca.hookstepsolve(small, 200.0, read_asc(known["m44"]["guess_file"]))
+    xg = ca.changebasis(x44, small.ijkl, model.ijkl)
+    x, ok = ca.hookstepsolve(model, 200.0, xg, ca.SearchParams(Nnewton=30))
+    assert np.linalg.norm(model.f(x, 200.0)) / np.linalg.norm(x) < 1e-8
+    out, succ = np.zeros(model.m), np.zeros(1, dtype=np.int32)
+    Rv, cp = np.array([200.0]), _CParams(1e-8, 1e-8, 0.02, 20, 4, 6, 0)
+    st = _solve(model._h, Rv.ctypes.data_as(C.POINTER(C.c_double)), xg.ctypes.data_as(C.POINTER(C.c_double)), 1,
+                C.byref(cp), out.ctypes.data_as(C.POINTER(C.c_double)), succ.ctypes.data_as(C.POINTER(C.c_int32)), None)
+    assert st == 5   # CA_ERR_UNSUPPORTED
 
 
 def test_re_continuation_of_the_27d_lower_branch(ca, known, H):

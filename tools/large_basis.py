@@ -49,6 +49,19 @@ for spec in args:
             out[name + "_executed_tflops"] = 2 * info["padded_fma_per_state"] * nstates / (ms * 1e-3) / 1e12
             if nstates <= 16:  # streaming kernel: one pass of the operator per <= 8 states
                 out[name + "_stream_gbs"] = out["stream_bytes_per_pass"] * ((nstates + 7) // 8) / (ms * 1e-3) / 1e9
+        if nstates == nstates_list[0] and m <= 1200:   # dense Jacobian Df(x,R): sliced-ELL stream (K3)
+            x1 = X[0].contiguous()
+            model.Df(x1, 200.0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                D = model.Df(x1, 200.0)
+            e1.record()
+            torch.cuda.synchronize()
+            out["jac_ms"] = e0.elapsed_time(e1) / 3
+            out["jac_vs_jvp"] = float(torch.linalg.norm(D @ V[0] - model.Df_action(X[:1], V[:1], 200.0)[0]) /
+                                      torch.linalg.norm(D @ V[0]))
         # consistency: JVP against a central difference of the RHS on a few states
         eps = 1e-6
         fd = (model.f((X[:64] + eps * V[:64]).t().contiguous().t(), 200.0) -
