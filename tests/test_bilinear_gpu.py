@@ -182,3 +182,40 @@ def test_windowed_model_rhs(ca, nagata_H, monkeypatch):
         got = dev.f(X, R)
         want = np.stack([ref.f(x, R) for x in X[:30]])
         assert relerr(got[:30], want) < 1e-13 * max(1.0, np.linalg.cond(ref.B) / 10)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_fuzz_all_kernel_paths_agree(ca, seed, monkeypatch):
+    """Random operators (duplicates, empty rows, dense-ish and very sparse), ensembles on both sides of the
+    streaming / DMMA threshold, padded leading dimensions: every path against the oracle loop."""
+    import torch
+    from oracle.bilinear import SparseBilinear as Ref, eval_batched
+    rng = np.random.default_rng(100 + seed)
+    m = int(rng.integers(2, 120))
+    nnz = int(rng.integers(1, 6 * m * m))
+    ijk = rng.integers(1, m + 1, size=(nnz, 3))
+    if seed % 2:
+        ijk[:, 0] = rng.integers(1, max(2, m // 3) + 1, size=nnz)
+    val = rng.standard_normal(nnz)
+    if seed == 3:
+        monkeypatch.setenv("CA_FORCE_WINDOW_MODES", "16")
+    N, ref = ca.SparseBilinear(ijk, val, m), Ref(ijk, val, m)
+    for nstates in (1, 2, 5, 16, 17, 40, 301):
+        X = rng.standard_normal((nstates, m))
+        Y = rng.standard_normal((nstates, m))
+        want = eval_batched(ref, X)
+        assert relerr(N(X), want) < TOL, (m, nnz, nstates)
+        ld = nstates + 3                                              # padded leading dimension on the device
+        buf = torch.zeros((m, ld), dtype=torch.float64, device="cuda")
+        buf[:, :nstates] = torch.from_numpy(X.T)
+        dX = buf.t()[:nstates]
+        assert relerr(N(dX).cpu().numpy(), want) < TOL
+        bufy = torch.zeros((m, ld), dtype=torch.float64, device="cuda")
+        bufy[:, :nstates] = torch.from_numpy(Y.T)
+        dY = bufy.t()[:nstates]
+        want2 = np.stack([ref(X[s], Y[s]) for s in range(min(nstates, 6))])
+        assert relerr(N(dX, dY).cpu().numpy()[:6], want2) < TOL
+        wantj = np.stack([ref.derivative(X[s]) @ Y[s] for s in range(min(nstates, 6))])
+        assert relerr(N.jvp(dX, dY).cpu().numpy()[:6], wantj) < TOL
+    x = rng.standard_normal(m)
+    assert relerr(N.derivative(x), ref.derivative(x)) < TOL
