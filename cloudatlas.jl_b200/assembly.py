@@ -10,6 +10,9 @@ from ._lib import CloudAtlasError, _sig, c_f64p, c_i64p, check, vp
 
 _assemble = _sig("ca_assemble", C.c_double, C.c_double, c_i64p, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
                  C.POINTER(vp))
+_assemble_dense = _sig("ca_assemble_dense", C.c_double, C.c_double, c_i64p, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
+                       C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp))
+_dense_info = _sig("ca_assembly_dense_info", vp, C.POINTER(C.c_int32), c_f64p, c_f64p)
 _destroy = _sig("ca_assembly_destroy", vp)
 _info = _sig("ca_assembly_info", vp, c_i64p, c_i64p, c_i64p, c_i64p, c_f64p)
 _get_linear = _sig("ca_assembly_get_linear", vp, c_f64p, c_f64p, c_f64p)
@@ -32,15 +35,21 @@ def row_partition(m: int, world: int):
 class AssemblySlab:
     """Rows [row_begin, row_end) of B, A1, A2 and the N entries with i in that range, on the device."""
 
-    def __init__(self, alpha, gamma, ijkl, normalize=False, row_begin=0, row_end=None):
+    def __init__(self, alpha, gamma, ijkl, normalize=False, row_begin=0, row_end=None, dense=False, grid=(0, 0, 0)):
+        """dense=True: N by brute-force quadrature on the tensor grid ``grid`` = (Nx, Ny, Nz), 0 = smallest exact
+        (the FP64-roofline path, ``ca_assemble_dense``); default: the separable path."""
         ijkl = np.asfortranarray(ijkl, dtype=np.int64)
         if ijkl.ndim != 2 or ijkl.shape[1] != 4:
             raise CloudAtlasError(1, "ijkl must have four columns")
         self.m = ijkl.shape[0]
         row_end = self.m if row_end is None else row_end
         h = vp()
-        check(_assemble(float(alpha), float(gamma), ijkl.ctypes.data_as(c_i64p), self.m, int(bool(normalize)),
-                        int(row_begin), int(row_end), C.byref(h)))
+        if dense:
+            check(_assemble_dense(float(alpha), float(gamma), ijkl.ctypes.data_as(c_i64p), self.m, int(bool(normalize)),
+                                  int(row_begin), int(row_end), int(grid[0]), int(grid[1]), int(grid[2]), C.byref(h)))
+        else:
+            check(_assemble(float(alpha), float(gamma), ijkl.ctypes.data_as(c_i64p), self.m, int(bool(normalize)),
+                            int(row_begin), int(row_end), C.byref(h)))
         self._h = h
         v = [C.c_int64() for _ in range(4)]
         sec = C.c_double()
@@ -53,6 +62,14 @@ class AssemblySlab:
         if h and _destroy is not None:  # module globals may already be gone at interpreter exit
             _destroy(h)
             self._h = None
+
+    def dense_info(self):
+        """{grid, contract_seconds, contract_flops, tflops} of the dense quadrature contraction."""
+        g = (C.c_int32 * 3)()
+        sec, fl = C.c_double(), C.c_double()
+        check(_dense_info(self._h, g, C.byref(sec), C.byref(fl)))
+        return {"grid": list(g), "contract_seconds": sec.value, "contract_flops": fl.value,
+                "tflops": fl.value / sec.value / 1e12 if sec.value > 0 else None}
 
     def linear_host(self):
         B, A1, A2 = (np.zeros((self.m, self.m), order="F") for _ in range(3))

@@ -22,6 +22,7 @@ namespace {
 
 constexpr double kAbsZero = 1e-15;  // ODEModels.jl:46
 constexpr double kRelZero = 1e-11;  // cancellation-aware: |sum| vs sum|terms|
+constexpr double kDenseRelZero = 1e-13;  // dense path: |N| vs max|N| (quadrature noise ~1e-16, true entries >= ~1e-10)
 constexpr double kQuadZero = 1e-15; // quadrature result vs sum|w f g h|: below this it is an analytic zero
 
 struct DevBasis {
@@ -225,20 +226,231 @@ n_kernel(DevBasis b, int r0, int r1, int64_t* __restrict__ counts, const int64_t
 
 }  // namespace
 
+
+// ================================================================================================
+// Dense quadrature contraction ("K1a"): the same tensor by brute force on the FP64 tensor pipe.
+//
+//   N_ijk = - sum_q sum_c  W_q Phi_ic(q) * G_jkc(q),      G_jkc(q) = sum_a Phi_ja(q) d_a Phi_kc(q)
+//
+// on the exact tensor grid (uniform in x and z, Gauss-Legendre in y): a GEMM with M = m (i), N = m^2 (j,k) and
+// K = 3 Nq whose B operand is generated on the fly in shared memory and never stored.  One CTA owns a
+// 128 (i) x 128 (8 j x 16 k) tile of the output; per chunk of 16 grid points it stages the pre-tiled A block with
+// cp.async (double buffered), generates the 48 x 128 B block from 8 x 16 x 3 values of Phi_j and 16 x 16 x 9 of
+// grad Phi_k, and its 16 warps issue 16 DMMAs per k-step each (4 x 4 fragments, A and B fragments read
+// conflict-free as [k-step][row][4]).  The dense result goes to a scratch slab and is compacted to the
+// reference's COO order.  This path exists for the FP64 roofline and as an independent check of the separable
+// path; it does ~2000x more arithmetic for the same numbers.
+constexpr int kDI = 128, kDJ = 8, kDK = 16, kDCols = kDJ * kDK, kDQ = 16, kDKc = 3 * kDQ, kDThreads = 512;
+
+struct DenseTables {
+  int m, mpad, nq, nchunks;
+  const double* U;   // [mpad][nq][3]      Phi_{n,a}(q)
+  const double* G9;  // [mpad][nq][9]      d_a Phi_{n,c}(q), index a*3+c
+  const double* A;   // [mpad/128][nchunks][12][128][4]   W_q Phi_{i,c}(q), k = q_local*3 + c
+};
+
+// one thread per (mode, grid point): fills U, G9 and the tiled A
+__global__ void dense_tables_kernel(DevBasis b, int mpad, int nxg, int nyg, int nzg, int nq,
+                                    const double* __restrict__ Ex, const double* __restrict__ Exd,
+                                    const double* __restrict__ Ez, const double* __restrict__ Ezd,
+                                    const double* __restrict__ F, int ny_tab, const double* __restrict__ wq,
+                                    double* __restrict__ U, double* __restrict__ G9, double* __restrict__ A,
+                                    int nchunks) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)mpad * nq) return;
+  const int n = (int)(t / nq), q = (int)(t % nq);
+  double u[3] = {0, 0, 0}, g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double w = 0.0;
+  const int nreal = nxg * nyg * nzg;
+  if (n < b.m && q < nreal) {
+    const int ix = q / (nyg * nzg), iy = (q / nzg) % nyg, iz = q % nzg;
+    w = wq[q];
+    for (int c = 0; c < 3; ++c) {
+      const double cf = b.coef[n * 3 + c];
+      if (cf == 0.0) continue;
+      const int jx = b.jx[n * 3 + c], kz = b.kz[n * 3 + c], pid = b.pid[n * 3 + c];
+      const double ex = Ex[jx * nxg + ix], exd = Exd[jx * nxg + ix], ez = Ez[kz * nzg + iz], ezd = Ezd[kz * nzg + iz];
+      const double f = F[pid * ny_tab + iy], fd = F[(pid + 1) * ny_tab + iy];
+      u[c] = cf * ex * ez * f;
+      g[0 * 3 + c] = cf * exd * ez * f;
+      g[1 * 3 + c] = cf * ex * ez * fd;
+      g[2 * 3 + c] = cf * ex * ezd * f;
+    }
+  }
+  for (int c = 0; c < 3; ++c) U[((size_t)n * nq + q) * 3 + c] = u[c];
+  for (int e = 0; e < 9; ++e) G9[((size_t)n * nq + q) * 9 + e] = g[e];
+  const int it = n / kDI, il = n % kDI, chunk = q / kDQ, ql = q % kDQ;
+  for (int c = 0; c < 3; ++c) {
+    const int k = ql * 3 + c;
+    A[((((size_t)it * nchunks + chunk) * (kDKc / 4) + k / 4) * kDI + il) * 4 + k % 4] = w * u[c];
+  }
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(kDThreads, 1)
+dense_contract_kernel(DenseTables T, int it0, int njt, double* __restrict__ Nd /* [rows][m][m] */, int row0, int row1) {
+  extern __shared__ __align__(16) double sm[];
+  double* Abuf = sm;                                  // [2][12*128*4]
+  double* Bbuf = Abuf + 2 * (kDKc * kDI);             // [12*128*4]
+  double* Utb = Bbuf + kDKc * kDCols;                 // [2][8][16][3]
+  double* Gtb = Utb + 2 * (kDJ * kDQ * 3);            // [2][16][16][9]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = lane >> 2, c = lane & 3;
+  const int it = it0 + blockIdx.y;
+  const int jt = blockIdx.x % njt, kt = blockIdx.x / njt;
+  const int j0 = jt * kDJ, k0 = kt * kDK;
+  const int wi = warp >> 2, wc = warp & 3;
+
+  auto stage = [&](int chunk, int buf) {
+    const double* src = T.A + ((size_t)it * T.nchunks + chunk) * (kDKc * kDI);
+    double* dst = Abuf + buf * (kDKc * kDI);
+    for (int e = tid; e < kDKc * kDI / 2; e += kDThreads) cp_async16(dst + 2 * e, src + 2 * e);
+    // U: 8 modes x (16 q x 3) contiguous doubles; G9: 16 modes x (16 q x 9)
+    for (int e = tid; e < kDJ * kDQ * 3 / 2; e += kDThreads) {
+      const int jj = (2 * e) / (kDQ * 3), off = (2 * e) % (kDQ * 3);
+      cp_async16(Utb + buf * (kDJ * kDQ * 3) + jj * (kDQ * 3) + off,
+                 T.U + ((size_t)(j0 + jj) * T.nq + (size_t)chunk * kDQ) * 3 + off);
+    }
+    for (int e = tid; e < kDK * kDQ * 9 / 2; e += kDThreads) {
+      const int kk = (2 * e) / (kDQ * 9), off = (2 * e) % (kDQ * 9);
+      cp_async16(Gtb + buf * (kDK * kDQ * 9) + kk * (kDQ * 9) + off,
+                 T.G9 + ((size_t)(k0 + kk) * T.nq + (size_t)chunk * kDQ) * 9 + off);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  stage(0, 0);
+  for (int chunk = 0; chunk < T.nchunks; ++chunk) {
+    const int buf = chunk & 1;
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();  // chunk's A and tables have landed; everyone finished the previous chunk's DMMAs
+    if (chunk + 1 < T.nchunks) stage(chunk + 1, buf ^ 1);
+    {  // generate B[k = q*3 + c][col = jj*16 + kk] = sum_a U[jj][q][a] * G9[kk][q][a][c]
+      const int col = tid % kDCols, kg = tid / kDCols;  // kg 0..3 -> k in [12 kg, 12 kg + 12) = q in [4 kg, 4 kg + 4)
+      const int jj = col / kDK, kk = col % kDK;
+      const double* u = Utb + buf * (kDJ * kDQ * 3) + jj * (kDQ * 3);
+      const double* g = Gtb + buf * (kDK * kDQ * 9) + kk * (kDQ * 9);
+#pragma unroll
+      for (int ql = 0; ql < 4; ++ql) {
+        const int q = kg * 4 + ql;
+        const double u0 = u[q * 3], u1 = u[q * 3 + 1], u2 = u[q * 3 + 2];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          const double v = u0 * g[q * 9 + cc] + u1 * g[q * 9 + 3 + cc] + u2 * g[q * 9 + 6 + cc];
+          const int k = q * 3 + cc;
+          Bbuf[((k >> 2) * kDCols + col) * 4 + (k & 3)] = v;
+        }
+      }
+    }
+    __syncthreads();
+    const double* Ab = Abuf + buf * (kDKc * kDI);
+#pragma unroll 4
+    for (int ks = 0; ks < kDKc / 4; ++ks) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) af[mt] = Ab[(ks * kDI + wi * 32 + mt * 8 + r) * 4 + c];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) bf[nt] = Bbuf[(ks * kDCols + wc * 32 + nt * 8 + r) * 4 + c];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                       : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
+                       : "d"(af[mt]), "d"(bf[nt]));
+        }
+    }
+  }
+  // epilogue: N = -C into the dense slab
+  const int m = T.m;
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    const int i = it * kDI + wi * 32 + mt * 8 + r;
+    if (i >= m || i < row0 || i >= row1) continue;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = wc * 32 + nt * 8 + 2 * c + e;
+        const int j = j0 + col / kDK, k = k0 + col % kDK;
+        if (j < m && k < m) Nd[((size_t)(i - row0) * m + j) * m + k] = -acc[mt][nt][e];
+      }
+  }
+}
+
+__global__ void absmax_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
+  double mx = 0.0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+    mx = fmax(mx, fabs(v[t]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.0)
+    atomicMax((unsigned long long*)out, (unsigned long long)__double_as_longlong(mx));  // non-negative doubles order as integers
+}
+
+// compaction of the dense slab to COO in (i,j,k) order: same two-pass structure as n_kernel
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+dense_compact_kernel(const double* __restrict__ Nd, int m, int r0, int r1, double thr, int64_t* __restrict__ counts,
+                     const int64_t* __restrict__ offs, int64_t* __restrict__ oi, int64_t* __restrict__ oj,
+                     int64_t* __restrict__ ok, double* __restrict__ oval) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t npairs = (int64_t)(r1 - r0) * m;
+  for (int64_t t = warp; t < npairs; t += nwarps) {
+    const int i = r0 + (int)(t / m), j = (int)(t % m);
+    const double* row = Nd + (size_t)t * m;
+    int64_t n = 0;
+    const int64_t base = FILL ? offs[t] : 0;
+    for (int k0 = 0; k0 < m; k0 += 32) {
+      const int k = k0 + lane;
+      const double v = k < m ? row[k] : 0.0;
+      const bool keep = fabs(v) > thr;
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      if (FILL && keep) {
+        const int64_t at = base + n + __popc(mask & ((1u << lane) - 1));
+        oi[at] = i + 1;
+        oj[at] = j + 1;
+        ok[at] = k + 1;
+        oval[at] = v;
+      }
+      n += __popc(mask);
+    }
+    if (!FILL && lane == 0) counts[t] = n;
+  }
+}
+
 struct ca_assembly {
   int device = 0;
   int64_t m = 0, r0 = 0, r1 = 0, nnz = 0;
   double seconds = 0;
+  double contract_seconds = 0, contract_flops = 0;  // dense path: the GEMM kernel alone, 2 * rows * m^2 * 3 Nq
+  int32_t grid[3] = {0, 0, 0};
   DeviceBuffer<double> B, A1, A2, D;  // (r1-r0) x m row-major; D = <curl, curl> (dissipation)
   DeviceBuffer<int64_t> oi, oj, ok;
   DeviceBuffer<double> oval;
   void bind() const { CA_CUDA(cudaSetDevice(device)); }
 };
 
-extern "C" {
+namespace {
+struct DenseOpts {
+  bool dense = false;
+  int nx = 0, ny = 0, nz = 0;
+};
+}  // namespace
 
-int32_t ca_assemble(double alpha, double gamma, const int64_t* ijkl, int64_t m64, int32_t normalize,
-                    int64_t row_begin, int64_t row_end, ca_assembly** out) {
+static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, int64_t m64, int32_t normalize,
+                             int64_t row_begin, int64_t row_end, const DenseOpts& dopt, ca_assembly** out) {
   return guarded([&] {
     if (!out) fail(CA_ERR_INVALID, "ca_assemble: out is null");
     *out = nullptr;
@@ -246,7 +458,7 @@ int32_t ca_assemble(double alpha, double gamma, const int64_t* ijkl, int64_t m64
     if (row_begin < 0 || row_end > m64 || row_begin > row_end)
       fail(CA_ERR_INVALID, "ca_assemble: row range [%lld,%lld) outside 0:%lld", (long long)row_begin, (long long)row_end, (long long)m64);
     if (m64 > 46000) fail(CA_ERR_UNSUPPORTED, "ca_assemble: m too large");
-    BasisTables T = build_tables(alpha, gamma, ijkl, m64, normalize != 0);
+    BasisTables T = build_tables(alpha, gamma, ijkl, m64, normalize != 0, dopt.dense ? dopt.ny : 0);
     require_device();
     std::unique_ptr<ca_assembly> h(new ca_assembly);
     CA_CUDA(cudaGetDevice(&h->device));
@@ -316,7 +528,85 @@ int32_t ca_assemble(double alpha, double gamma, const int64_t* ijkl, int64_t m64
       int sms = 0;
       CA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
       const unsigned grid = (unsigned)std::min<int64_t>((nij + 7) / 8, (int64_t)sms * 16);
-      n_kernel<false><<<grid, 256>>>(b, r0, r1, counts.ptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+      DeviceBuffer<double> Nd;  // dense path: [rows][m][m] scratch slab
+      double thr = 0.0;
+      if (dopt.dense) {
+        // ---- tensor grid: uniform in x, z (exact for trigonometric degree 3J, 3K), Gauss-Legendre in y
+        const int nxg = dopt.nx > 0 ? dopt.nx : 3 * T.J + 1, nzg = dopt.nz > 0 ? dopt.nz : 3 * T.K + 1, nyg = T.ny;
+        if (nxg <= 3 * T.J || nzg <= 3 * T.K)
+          fail(CA_ERR_INVALID, "grid %d x %d x %d is not exact for J, K = %d, %d (need Nx > 3J, Nz > 3K)", nxg, nyg, nzg, T.J, T.K);
+        const int nreal = nxg * nyg * nzg, nq = (nreal + kDQ - 1) / kDQ * kDQ, nchunks = nq / kDQ;
+        const int mpad = (m + kDI - 1) / kDI * kDI;
+        if ((double)rows * m * m * 8.0 > 100e9)
+          fail(CA_ERR_UNSUPPORTED, "dense scratch for %d rows of a %d-mode basis exceeds 100 GB: assemble in row slabs", rows, m);
+        h->grid[0] = nxg; h->grid[1] = nyg; h->grid[2] = nzg;
+        const double two_pi = 6.283185307179586476925286766559;
+        auto trig_table = [&](int Jmax, int n, double wn, std::vector<double>& e, std::vector<double>& ed) {
+          e.assign((size_t)(2 * Jmax + 1) * n, 0.0);
+          ed.assign((size_t)(2 * Jmax + 1) * n, 0.0);
+          for (int js = 0; js <= 2 * Jmax; ++js)
+            for (int ix = 0; ix < n; ++ix) {
+              const int j = js - Jmax;
+              const double th = two_pi * ix / n;
+              double v = 1.0, d = 0.0;
+              if (j < 0) { v = std::cos(-j * th); d = -wn * (-j) * std::sin(-j * th); }
+              if (j > 0) { v = std::sin(j * th); d = wn * j * std::cos(j * th); }
+              e[(size_t)js * n + ix] = v;
+              ed[(size_t)js * n + ix] = d;
+            }
+        };
+        std::vector<double> ex, exd, ez, ezd, wq((size_t)nq, 0.0);
+        trig_table(T.J, nxg, T.alpha, ex, exd);
+        trig_table(T.K, nzg, T.gamma, ez, ezd);
+        for (int q = 0; q < nreal; ++q) wq[q] = T.weights[(q / nzg) % nyg] / ((double)nxg * nzg);
+        DeviceBuffer<double> dex, dexd, dez, dezd, dwq, dU, dG9, dA, dmax;
+        dex.upload(ex.data(), ex.size());
+        dexd.upload(exd.data(), exd.size());
+        dez.upload(ez.data(), ez.size());
+        dezd.upload(ezd.data(), ezd.size());
+        dwq.upload(wq.data(), wq.size());
+        dU.alloc((size_t)mpad * nq * 3);
+        dG9.alloc((size_t)mpad * nq * 9);
+        dA.alloc((size_t)mpad * nq * 3);
+        dmax.alloc(1);
+        Nd.alloc((size_t)rows * m * m);
+        CA_CUDA(cudaMemsetAsync(dmax.ptr, 0, sizeof(double)));
+        const int64_t ntab = (int64_t)mpad * nq;
+        dense_tables_kernel<<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr,
+                                                                    dezd.ptr, dF.ptr, T.ny, dwq.ptr, dU.ptr, dG9.ptr,
+                                                                    dA.ptr, nchunks);
+        CA_CUDA(cudaGetLastError());
+        count_launch();
+        DenseTables DT{m, mpad, nq, nchunks, dU.ptr, dG9.ptr, dA.ptr};
+        const int it0 = r0 / kDI, nit = (r1 + kDI - 1) / kDI - it0;
+        const int njt = (m + kDJ - 1) / kDJ, nkt = (m + kDK - 1) / kDK;
+        const size_t smem = (size_t)(2 * kDKc * kDI + kDKc * kDCols + 2 * kDJ * kDQ * 3 + 2 * kDK * kDQ * 9) * sizeof(double);
+        CA_CUDA(cudaFuncSetAttribute(dense_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaEvent_t c0, c1;
+        CA_CUDA(cudaEventCreate(&c0));
+        CA_CUDA(cudaEventCreate(&c1));
+        CA_CUDA(cudaEventRecord(c0));
+        dense_contract_kernel<<<dim3((unsigned)(njt * nkt), (unsigned)nit), kDThreads, smem>>>(DT, it0, njt, Nd.ptr, r0, r1);
+        CA_CUDA(cudaGetLastError());
+        count_launch();
+        CA_CUDA(cudaEventRecord(c1));
+        CA_CUDA(cudaEventSynchronize(c1));
+        float cms = 0;
+        CA_CUDA(cudaEventElapsedTime(&cms, c0, c1));
+        cudaEventDestroy(c0);
+        cudaEventDestroy(c1);
+        h->contract_seconds = cms * 1e-3;
+        h->contract_flops = 2.0 * rows * (double)m * m * 3.0 * nreal;
+        absmax_kernel<<<sms * 8, 256>>>(Nd.ptr, (int64_t)rows * m * m, dmax.ptr);
+        CA_CUDA(cudaGetLastError());
+        count_launch();
+        double gmax = 0.0;
+        CA_CUDA(cudaMemcpy(&gmax, dmax.ptr, sizeof(double), cudaMemcpyDeviceToHost));
+        thr = std::max(kAbsZero, kDenseRelZero * gmax);
+        dense_compact_kernel<false><<<grid, 256>>>(Nd.ptr, m, r0, r1, thr, counts.ptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+      } else {
+        n_kernel<false><<<grid, 256>>>(b, r0, r1, counts.ptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+      }
       CA_CUDA(cudaGetLastError());
       count_launch();
       size_t tmp_bytes = 0;
@@ -333,7 +623,10 @@ int32_t ca_assemble(double alpha, double gamma, const int64_t* ijkl, int64_t m64
         h->oj.alloc((size_t)nnz);
         h->ok.alloc((size_t)nnz);
         h->oval.alloc((size_t)nnz);
-        n_kernel<true><<<grid, 256>>>(b, r0, r1, nullptr, offs.ptr, h->oi.ptr, h->oj.ptr, h->ok.ptr, h->oval.ptr);
+        if (dopt.dense)
+          dense_compact_kernel<true><<<grid, 256>>>(Nd.ptr, m, r0, r1, thr, nullptr, offs.ptr, h->oi.ptr, h->oj.ptr, h->ok.ptr, h->oval.ptr);
+        else
+          n_kernel<true><<<grid, 256>>>(b, r0, r1, nullptr, offs.ptr, h->oi.ptr, h->oj.ptr, h->ok.ptr, h->oval.ptr);
         CA_CUDA(cudaGetLastError());
         count_launch();
       }
@@ -346,6 +639,32 @@ int32_t ca_assemble(double alpha, double gamma, const int64_t* ijkl, int64_t m64
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *out = h.release();
+  });
+}
+
+extern "C" {
+
+int32_t ca_assemble(double alpha, double gamma, const int64_t* ijkl, int64_t m, int32_t normalize,
+                    int64_t row_begin, int64_t row_end, ca_assembly** out) {
+  return assemble_impl(alpha, gamma, ijkl, m, normalize, row_begin, row_end, DenseOpts{}, out);
+}
+
+int32_t ca_assemble_dense(double alpha, double gamma, const int64_t* ijkl, int64_t m, int32_t normalize,
+                          int64_t row_begin, int64_t row_end, int32_t nx, int32_t ny, int32_t nz, ca_assembly** out) {
+  DenseOpts d;
+  d.dense = true;
+  d.nx = nx;
+  d.ny = ny;
+  d.nz = nz;
+  return assemble_impl(alpha, gamma, ijkl, m, normalize, row_begin, row_end, d, out);
+}
+
+int32_t ca_assembly_dense_info(const ca_assembly* h, int32_t* grid3, double* contract_seconds, double* contract_flops) {
+  return guarded([&] {
+    if (!h) fail(CA_ERR_INVALID, "null handle");
+    if (grid3) { grid3[0] = h->grid[0]; grid3[1] = h->grid[1]; grid3[2] = h->grid[2]; }
+    if (contract_seconds) *contract_seconds = h->contract_seconds;
+    if (contract_flops) *contract_flops = h->contract_flops;
   });
 }
 

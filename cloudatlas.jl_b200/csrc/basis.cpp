@@ -147,7 +147,8 @@ std::vector<int64_t> basis_indices(int J, int K, int L, const ca_symmetry* H, in
   return out;
 }
 
-BasisTables build_tables(double alpha, double gamma, const int64_t* ijkl, int64_t m64, bool normalize) {
+BasisTables build_tables(double alpha, double gamma, const int64_t* ijkl, int64_t m64, bool normalize,
+                         int ny_override) {
   if (m64 <= 0 || !ijkl) fail(CA_ERR_INVALID, "basis: empty index set");
   BasisTables T;
   const int m = T.m = (int)m64;
@@ -180,6 +181,10 @@ BasisTables build_tables(double alpha, double gamma, const int64_t* ijkl, int64_
   const int L = T.L;
   T.npid = 4 * (L + 1);
   T.ny = (3 * (L + 3)) / 2 + 2;  // exact for degree 3(L+3)+1 <= 2 ny - 1
+  if (ny_override > 0) {
+    if (ny_override < T.ny) fail(CA_ERR_INVALID, "ny = %d is not exact for L = %d (need >= %d)", ny_override, L, T.ny);
+    T.ny = ny_override;
+  }
   std::vector<long double> yl, wl;
   gauss_legendre(T.ny, yl, wl);
   yl.push_back(1.0L);   // two extra evaluation points (not quadrature nodes): the walls y = +1, -1

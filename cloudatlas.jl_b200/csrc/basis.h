@@ -42,7 +42,8 @@ struct BasisTables {
 };
 
 // normalize: scale each mode by 1/sqrt(<Psi,Psi>)  (BasisFunctions.jl:697-699)
+// ny_override > 0: number of Gauss-Legendre nodes (must be at least the default exact count)
 BasisTables build_tables(double alpha, double gamma, const int64_t* ijkl /*m x 4 column-major*/, int64_t m,
-                         bool normalize);
+                         bool normalize, int ny_override = 0);
 
 }  // namespace ca

@@ -155,6 +155,18 @@ int32_t ca_model_jvp_batched_dev(ca_model* h, const double* dX, const double* dV
  * Slabs of different ranks concatenate, in rank order, to the full operator (sharding by i). */
 int32_t ca_assemble(double alpha, double gamma, const int64_t* ijkl /* m x 4 column-major */, int64_t m,
                     int32_t normalize, int64_t row_begin, int64_t row_end, ca_assembly** out);
+/* The same operators with N computed by brute-force quadrature on the exact tensor grid (uniform Nx > 3J,
+ * Nz > 3K points in x, z; ny >= (3L+13)/2 Gauss-Legendre nodes in y; 0 = smallest exact): a dense FP64
+ * contraction  N_ijk = -sum_q W_q Phi_i(q) . (Phi_j . grad) Phi_k (q)  on the tensor pipe, B operand generated on
+ * the fly, result compacted to the same COO.  ~2000x the arithmetic of ca_assemble for the same numbers: it is
+ * the FP64-roofline benchmark of the assembly stage and an independent check.  An entry is kept iff
+ * |N| > max(1e-15, 1e-13 max|N|).  The dense scratch is (row_end-row_begin) m^2 doubles (<= 100 GB). */
+int32_t ca_assemble_dense(double alpha, double gamma, const int64_t* ijkl, int64_t m, int32_t normalize,
+                          int64_t row_begin, int64_t row_end, int32_t nx, int32_t ny, int32_t nz,
+                          ca_assembly** out);
+/* grid used, CUDA-event seconds of the contraction kernel alone and its algorithmic flops 2 rows m^2 3 Nq */
+int32_t ca_assembly_dense_info(const ca_assembly* h, int32_t* grid3, double* contract_seconds,
+                               double* contract_flops);
 int32_t ca_assembly_destroy(ca_assembly* h);
 int32_t ca_assembly_info(const ca_assembly* h, int64_t* m, int64_t* row_begin, int64_t* row_end,
                          int64_t* nnz, double* device_seconds);

@@ -156,3 +156,32 @@ def test_m999_pattern_and_values_on_sampled_rows(ca, nagata_H):
     assert np.array_equal(ijk[sel], eijk)
     ev = np.array([float(v) for v in evals])
     assert np.max(np.abs(val[sel] - ev)) / np.max(np.abs(ev)) < TOL
+
+
+@pytest.mark.parametrize("JKL,grid", [((1, 1, 3), (0, 0, 0)), ((2, 2, 3), (0, 0, 0)), ((2, 2, 3), (9, 12, 8)),
+                                      ((3, 3, 12), (0, 0, 0))], ids=["17d", "44d", "44d-finer-grid", "307"])
+def test_dense_quadrature_path_matches_separable_path(ca, JKL, grid):
+    """The brute-force tensor-grid contraction (FP64 tensor pipe) reproduces the separable assembly: same COO
+    pattern and order, values to 1e-12 of the largest entry."""
+    ijkl = ca.basisIndices(*JKL, lib_H(ca))
+    a = ca.AssemblySlab(1.0, 2.0, ijkl)
+    b = ca.AssemblySlab(1.0, 2.0, ijkl, dense=True, grid=grid)
+    (ia, va), (ib, vb) = a.coo_host(), b.coo_host()
+    assert a.nnz == b.nnz and np.array_equal(ia, ib)
+    assert maxrel(vb, va) < TOL
+    info = b.dense_info()
+    J, K, L = JKL
+    assert info["grid"][0] > 3 * J and info["grid"][2] > 3 * K and info["grid"][1] >= (3 * L + 13) // 2
+    assert info["contract_seconds"] > 0
+    for x, y in zip(a.linear_host(), b.linear_host()):
+        assert np.array_equal(x, y)
+    with pytest.raises(ca.CloudAtlasError, match="not exact"):
+        ca.AssemblySlab(1.0, 2.0, ijkl, dense=True, grid=(3 * J, 0, 0))
+
+
+def test_dense_quadrature_row_slabs(ca):
+    ijkl = ca.basisIndices(2, 2, 3, lib_H(ca))
+    full = ca.AssemblySlab(1.0, 2.0, ijkl, dense=True).coo_host()
+    parts = [ca.AssemblySlab(1.0, 2.0, ijkl, False, r0, r1, dense=True).coo_host() for r0, r1 in ((0, 13), (13, 44))]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), full[0])
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), full[1])
