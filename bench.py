@@ -288,6 +288,10 @@ def run_b200(args):
         "kernel_path": model.kernel_path(n)[0],
     }
 
+    if not args.no_extras:
+        dense = dense_assembly_case(ca, H, world, rank, max_over_ranks, barrier, dmma_peak)
+        if rank == 0:
+            line["roofline_assembly"] = dense
     if rank == 0 and world == 1 and not args.no_extras:
         line["assembly"] = assembly_sweep(ca, H)
         line["roofline_hbm_case"] = hbm_case(ca, H, hbm_peak)
@@ -297,6 +301,30 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def dense_assembly_case(ca, H, world, rank, max_over_ranks, barrier, dmma_peak):
+    """BASELINE.json configs[3]: Q-tensor assembly of the ~1000-mode basis (J,K,L = 5,5,16) by dense quadrature on the
+    16 x 33 x 16 tensor grid, sharded by output mode over the ranks (the FP64-roofline formulation of the assembly;
+    the separable path gives the same tensor in ~25 ms, see `assembly`)."""
+    ijkl = ca.basisIndices(5, 5, 16, H)
+    m = ijkl.shape[0]
+    bounds = ca.row_partition(m, world)
+    barrier()
+    t0 = time.perf_counter()
+    slab = ca.AssemblySlab(ALPHA, GAMMA, ijkl, False, bounds[rank], bounds[rank + 1], dense=True, grid=(16, 33, 16))
+    barrier()
+    wall = max_over_ranks(time.perf_counter() - t0)
+    info = slab.dense_info()
+    sec = max_over_ranks(info["contract_seconds"])
+    flops_total = 2.0 * m * m * m * 3 * 16 * 33 * 16
+    nnz = slab.nnz
+    del slab
+    return {"workload": "dense quadrature assembly of N, m=999 (J,K,L=5,5,16), grid 16x33x16, rows sharded over ranks",
+            "bound": "tensor", "pipe": "fp64 DMMA", "achieved": flops_total / sec / 1e12 / world, "peak": dmma_peak,
+            "unit": "TFLOP/s per GPU", "frac": flops_total / sec / 1e12 / world / dmma_peak,
+            "contract_seconds": sec, "wall_seconds": wall, "algorithmic_flops": flops_total, "n_gpus": world,
+            "nnz_rank0": int(nnz), "kernel": "dense_contract_kernel"}
 
 
 def assembly_sweep(ca, H):

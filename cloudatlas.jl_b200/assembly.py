@@ -141,7 +141,7 @@ def all_gather_slabs(lin, idx, val, m, group=None):
     return torch.cat(lins, dim=1), torch.cat(idxs, dim=1), torch.cat(vals)
 
 
-def assemble(alpha, gamma, ijkl, normalize=False, group=None, distributed=None):
+def assemble(alpha, gamma, ijkl, normalize=False, group=None, distributed=None, dense=False, grid=(0, 0, 0)):
     """Full B, A1, A2 (m x m, column-major numpy) and N's COO (ijk nnz x 3 1-based, val) on every rank.
 
     With torch.distributed initialised (or ``distributed=True``) each rank assembles its range of output
@@ -153,19 +153,20 @@ def assemble(alpha, gamma, ijkl, normalize=False, group=None, distributed=None):
         import torch.distributed as dist
         distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     if not distributed:
-        slab = AssemblySlab(alpha, gamma, ijkl, normalize)
+        slab = AssemblySlab(alpha, gamma, ijkl, normalize, dense=dense, grid=grid)
         B, A1, A2 = slab.linear_host()
         ijk, val = slab.coo_host()
         return B, A1, A2, ijk, val, {"device_seconds": slab.device_seconds, "world": 1, "nnz_local": slab.nnz,
-                                     "D": slab.dissipation_host()}
+                                     "D": slab.dissipation_host(), "dense": slab.dense_info() if dense else None}
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     bounds = row_partition(m, world)
-    slab = AssemblySlab(alpha, gamma, ijkl, normalize, bounds[rank], bounds[rank + 1])
+    slab = AssemblySlab(alpha, gamma, ijkl, normalize, bounds[rank], bounds[rank + 1], dense=dense, grid=grid)
     lin, idx, val = slab.to_torch()
     lin, idx, val = all_gather_slabs(lin, idx, val, m, group)
     lin = lin.cpu().numpy()
     B, A1, A2, D = (np.asfortranarray(lin[q]) for q in range(4))
     ijk = np.asfortranarray(idx.t().cpu().numpy())
     return B, A1, A2, ijk, val.cpu().numpy(), {"device_seconds": slab.device_seconds, "world": world,
-                                               "nnz_local": slab.nnz, "D": D}
+                                               "nnz_local": slab.nnz, "D": D,
+                                               "dense": slab.dense_info() if dense else None}

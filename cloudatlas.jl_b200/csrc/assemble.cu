@@ -244,8 +244,9 @@ constexpr int kDI = 128, kDJ = 8, kDK = 16, kDCols = kDJ * kDK, kDQ = 16, kDKc =
 
 struct DenseTables {
   int m, mpad, nq, nchunks;
-  const double* U;   // [mpad][nq][3]      Phi_{n,a}(q)
-  const double* G9;  // [mpad][nq][9]      d_a Phi_{n,c}(q), index a*3+c
+  const double* U;   // [mpad/8][nchunks][16 q][3 a][8 modes]        Phi_{n,a}(q): one contiguous block per (j-tile, chunk)
+  const double* G9;  // [mpad/16][nchunks][16 q][9 (a*3+c)][16 modes]  d_a Phi_{n,c}(q): mode index fastest, so that the
+                     //                                               B generation reads shared memory conflict-free
   const double* A;   // [mpad/128][nchunks][12][128][4]   W_q Phi_{i,c}(q), k = q_local*3 + c
 };
 
@@ -277,9 +278,11 @@ __global__ void dense_tables_kernel(DevBasis b, int mpad, int nxg, int nyg, int 
       g[2 * 3 + c] = cf * ex * ezd * f;
     }
   }
-  for (int c = 0; c < 3; ++c) U[((size_t)n * nq + q) * 3 + c] = u[c];
-  for (int e = 0; e < 9; ++e) G9[((size_t)n * nq + q) * 9 + e] = g[e];
   const int it = n / kDI, il = n % kDI, chunk = q / kDQ, ql = q % kDQ;
+  for (int c = 0; c < 3; ++c)
+    U[((((size_t)(n / kDJ) * nchunks + chunk) * kDQ + ql) * 3 + c) * kDJ + n % kDJ] = u[c];
+  for (int e = 0; e < 9; ++e)
+    G9[((((size_t)(n / kDK) * nchunks + chunk) * kDQ + ql) * 9 + e) * kDK + n % kDK] = g[e];
   for (int c = 0; c < 3; ++c) {
     const int k = ql * 3 + c;
     A[((((size_t)it * nchunks + chunk) * (kDKc / 4) + k / 4) * kDI + il) * 4 + k % 4] = w * u[c];
@@ -308,17 +311,11 @@ dense_contract_kernel(DenseTables T, int it0, int njt, double* __restrict__ Nd /
     const double* src = T.A + ((size_t)it * T.nchunks + chunk) * (kDKc * kDI);
     double* dst = Abuf + buf * (kDKc * kDI);
     for (int e = tid; e < kDKc * kDI / 2; e += kDThreads) cp_async16(dst + 2 * e, src + 2 * e);
-    // U: 8 modes x (16 q x 3) contiguous doubles; G9: 16 modes x (16 q x 9)
-    for (int e = tid; e < kDJ * kDQ * 3 / 2; e += kDThreads) {
-      const int jj = (2 * e) / (kDQ * 3), off = (2 * e) % (kDQ * 3);
-      cp_async16(Utb + buf * (kDJ * kDQ * 3) + jj * (kDQ * 3) + off,
-                 T.U + ((size_t)(j0 + jj) * T.nq + (size_t)chunk * kDQ) * 3 + off);
-    }
-    for (int e = tid; e < kDK * kDQ * 9 / 2; e += kDThreads) {
-      const int kk = (2 * e) / (kDQ * 9), off = (2 * e) % (kDQ * 9);
-      cp_async16(Gtb + buf * (kDK * kDQ * 9) + kk * (kDQ * 9) + off,
-                 T.G9 + ((size_t)(k0 + kk) * T.nq + (size_t)chunk * kDQ) * 9 + off);
-    }
+    // the (j-tile, chunk) block of U and the (k-tile, chunk) block of G9 are contiguous in global memory
+    const double* usrc = T.U + ((size_t)jt * T.nchunks + chunk) * (kDJ * kDQ * 3);
+    for (int e = tid; e < kDJ * kDQ * 3 / 2; e += kDThreads) cp_async16(Utb + buf * (kDJ * kDQ * 3) + 2 * e, usrc + 2 * e);
+    const double* gsrc = T.G9 + ((size_t)kt * T.nchunks + chunk) * (kDK * kDQ * 9);
+    for (int e = tid; e < kDK * kDQ * 9 / 2; e += kDThreads) cp_async16(Gtb + buf * (kDK * kDQ * 9) + 2 * e, gsrc + 2 * e);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   };
 
@@ -337,15 +334,15 @@ dense_contract_kernel(DenseTables T, int it0, int njt, double* __restrict__ Nd /
     {  // generate B[k = q*3 + c][col = jj*16 + kk] = sum_a U[jj][q][a] * G9[kk][q][a][c]
       const int col = tid % kDCols, kg = tid / kDCols;  // kg 0..3 -> k in [12 kg, 12 kg + 12) = q in [4 kg, 4 kg + 4)
       const int jj = col / kDK, kk = col % kDK;
-      const double* u = Utb + buf * (kDJ * kDQ * 3) + jj * (kDQ * 3);
-      const double* g = Gtb + buf * (kDK * kDQ * 9) + kk * (kDQ * 9);
+      const double* u = Utb + buf * (kDJ * kDQ * 3) + jj;   // [q][a][8 modes]
+      const double* g = Gtb + buf * (kDK * kDQ * 9) + kk;   // [q][a*3+c][16 modes]
 #pragma unroll
       for (int ql = 0; ql < 4; ++ql) {
         const int q = kg * 4 + ql;
-        const double u0 = u[q * 3], u1 = u[q * 3 + 1], u2 = u[q * 3 + 2];
+        const double u0 = u[(q * 3) * kDJ], u1 = u[(q * 3 + 1) * kDJ], u2 = u[(q * 3 + 2) * kDJ];
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
-          const double v = u0 * g[q * 9 + cc] + u1 * g[q * 9 + 3 + cc] + u2 * g[q * 9 + 6 + cc];
+          const double v = u0 * g[(q * 9 + cc) * kDK] + u1 * g[(q * 9 + 3 + cc) * kDK] + u2 * g[(q * 9 + 6 + cc) * kDK];
           const int k = q * 3 + cc;
           Bbuf[((k >> 2) * kDCols + col) * 4 + (k & 3)] = v;
         }

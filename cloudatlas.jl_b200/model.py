@@ -158,7 +158,8 @@ class ODEModel(ModelOperators):
     tabular basis, ``Bfact`` is folded into the device operators).  The constructor is the assembly
     driver: index set -> basis tables -> Galerkin assembly on the GPU(s) -> device packing."""
 
-    def __init__(self, alpha, gamma, J, K, L, H, normalize=False, ijkl=None, group=None, verbose=False):
+    def __init__(self, alpha, gamma, J, K, L, H, normalize=False, ijkl=None, group=None, verbose=False,
+                 dense_assembly=False, grid=(0, 0, 0)):
         from .assembly import assemble
         from .basis import basisComponents, basisIndices
         self.alpha, self.gamma = float(alpha), float(gamma)
@@ -169,7 +170,8 @@ class ODEModel(ModelOperators):
             print(f"J,K,L,m == {J},{K},{L},{m}")
             print(f"(2J+1)(2K+1)(2L+1) + 1 == {(2 * J + 1) * (2 * K + 1) * (2 * L + 1) + 1}")
         self.Psi = basisComponents(self.alpha, self.gamma, self.ijkl, normalize)
-        B, A1, A2, ijk, val, self.assembly_stats = assemble(self.alpha, self.gamma, self.ijkl, normalize, group)
+        B, A1, A2, ijk, val, self.assembly_stats = assemble(self.alpha, self.gamma, self.ijkl, normalize, group,
+                                                            dense=dense_assembly, grid=grid)
         super().__init__(B, A1, A2, ijk, val)
         self._N = None
         from .basis import shearVector
