@@ -159,3 +159,20 @@ def test_re_continuation_of_the_27d_lower_branch(ca, known, H):
     if after.any():                                             # the other branch at Re ~ 200 is a different state
         j = k + np.argmax(after)
         assert abs(br["shear"][j] - br["shear"][0]) > 1e-3
+
+
+def test_newton_krylov_with_matrix_free_jacobian_actions(ca, known, H):
+    """Newton-GMRES on device Jacobian actions (config 4's evaluation path) reaches the same equilibria as the
+    hookstep search with the dense Jacobian."""
+    small = ca.ODEModel(1.0, 2.0, 2, 2, 3, H)
+    x44, ok = ca.hookstepsolve(small, 200.0, read_asc(known["m44"]["guess_file"]))
+    xk, conv, info = ca.newton_krylov(small, 200.0, read_asc(known["m44"]["guess_file"]), ftol=1e-11)
+    assert conv and np.linalg.norm(xk - x44) / np.linalg.norm(x44) < 1e-8
+    model = ca.ODEModel(1.0, 2.0, 3, 3, 4, H)                      # 111 modes
+    xg = ca.changebasis(x44, small.ijkl, model.ijkl)
+    xh, _ = ca.hookstepsolve(model, 200.0, xg, ca.SearchParams(Nnewton=30))
+    xk, conv, info = ca.newton_krylov(model, 200.0, xg, ftol=1e-11)
+    assert conv, info
+    assert np.linalg.norm(model.f(xk, 200.0)) < 1e-10
+    assert np.linalg.norm(xk - xh) / np.linalg.norm(xh) < 1e-7
+    assert info["jvps"] > 0
