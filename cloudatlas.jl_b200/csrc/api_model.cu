@@ -225,7 +225,7 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
       auto work = [&]() {
         for (size_t bi = next.fetch_add(1); bi < block_list.size(); bi = next.fetch_add(1)) fold_block(bi);
       };
-      const unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      const unsigned nthreads = ca::worker_threads();
       std::vector<std::thread> pool;
       for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(work);
       work();

@@ -1,6 +1,8 @@
 #include "common.h"
 
+#include <algorithm>
 #include <cstring>
+#include <thread>
 #include <ctime>
 
 namespace ca {
@@ -30,6 +32,14 @@ void PhaseTimer::lap(const char* phase) {
   const double t = now_s();
   fprintf(stderr, "[ca timing] %s: %s %.3f s\n", what, phase, t - t0);
   t0 = t;
+}
+
+unsigned worker_threads() {
+  if (const char* e = getenv("CA_NUM_THREADS")) {
+    const int v = atoi(e);
+    if (v >= 1) return (unsigned)std::min(v, 64);
+  }
+  return std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
 }
 
 void require_device() {

@@ -50,6 +50,9 @@ int32_t guarded(F&& body) {
   }
 }
 
+// Host worker threads for the build stages: CA_NUM_THREADS, else min(16, hardware threads).
+unsigned worker_threads();
+
 // Wall-clock phase timer, printed to stderr when CA_TIMING is set (host-side build diagnostics).
 struct PhaseTimer {
   const char* what;

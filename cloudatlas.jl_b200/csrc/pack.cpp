@@ -71,7 +71,7 @@ void sort_terms(std::vector<Term>& terms, int32_t m) {
   terms.swap(out);
   out.clear();
   out.shrink_to_fit();
-  const unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const unsigned nthreads = ca::worker_threads();
   std::atomic<int32_t> next{0};
   auto work = [&]() {
     auto less = [](const Term& x, const Term& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; };
