@@ -24,5 +24,9 @@ Modules
   bilinear.py   SparseBilinear COO container, N(x,y), derivative(N,x)
   hookstep.py   Newton-hookstep state machine
   exact.py      fast exact-rational assembly by separable tabulation (any L)
-  csrc/         plain-C restatement of the hot loops (timed as the CPU baseline)
+  fastfloat.py  the same tables rounded once to Float64, vectorised (N at m = 307 / 999 in seconds)
+  cref.py       ctypes front end of csrc/
+  csrc/         plain-C restatement of the evaluation loops (COO N(x), derivative, f with LU solve; pthreads over
+                states) -- timed as the CPU baseline by bench.py
+  model.py also restates cnab2, shear_function and dissipation_function (ODEModels.jl:65-181).
 """
