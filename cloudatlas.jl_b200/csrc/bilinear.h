@@ -39,8 +39,8 @@ void eval_batched_host(const LaunchFn& launch, cudaStream_t streams[2], DeviceBu
                        int64_t m_in, int64_t m_out);
 
 // Packing policy: operators whose two-vector state tile (x and y/v, 32 states) fits in shared memory use
-// whole-tile packing; larger ones are packed in windows of kWindowModes modes.
-constexpr int kWindowModes = 96;
+// whole-tile packing; larger ones are packed in windows of kWindowModes modes (128: two CTAs per SM still fit for one-vector evaluation).
+constexpr int kWindowModes = 128;
 int window_modes_for(int32_t m);
 
 // true if the DMMA ensemble kernel can hold a state tile of this operator in shared memory
