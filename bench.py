@@ -252,6 +252,7 @@ def run_b200(args):
     except OSError:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_peak_source = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("rhs_m307_bytes_per_launch")
@@ -265,7 +266,8 @@ def run_b200(args):
         "kernel": "bilinear_batched_kernel<4,0>", "kernel_ms": kernel_ms,
         "algorithmic_flops_per_state": flops_state, "executed_fma_per_state": info["padded_fma_per_state"],
         "algorithmic_bytes_per_state": bytes_state,
-        "hbm_view": {"achieved": bytes_state * n / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "hbm_view": {"achieved": bytes_state * n / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                     "peak_source": hbm_peak_source, "unit": "GB/s",
                      "frac": bytes_state * n / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                      "note": "arithmetic intensity ~340 flop/B: this config is FP64-bound, not HBM-bound"},
     }
