@@ -17,8 +17,8 @@ struct ca_bilinear {
   std::unique_ptr<JacobianPack> jac;    // built on first use
   std::unique_ptr<StreamPack> ssym, sord;  // few-state streaming form, built on first use
   // staging for the host-pointer entry points
-  cudaStream_t streams[2] = {nullptr, nullptr};
-  DeviceBuffer<double> stage_in[2], stage_out[2], small_x, small_y, small_out, jac_out;
+  cudaStream_t streams[kStage] = {nullptr, nullptr, nullptr};
+  DeviceBuffer<double> stage_in[kStage], stage_out[kStage], small_x, small_y, small_out, jac_out;
   ~ca_bilinear() {
     for (auto& s : streams)
       if (s) cudaStreamDestroy(s);
@@ -78,21 +78,28 @@ namespace ca {
 // Shared with the model code: evaluates a packed operator for a host ensemble, chunked and
 // double-buffered (H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c when the
 // host buffers are page-locked, see ca_pin).
-void eval_batched_host(const LaunchFn& launch, cudaStream_t streams[2], DeviceBuffer<double> in[2],
-                       DeviceBuffer<double> out[2], const double* X, int64_t nstates, double* OUT,
+void eval_batched_host(const LaunchFn& launch, cudaStream_t streams[kStage], DeviceBuffer<double> in[kStage],
+                       DeviceBuffer<double> out[kStage], const double* X, int64_t nstates, double* OUT,
                        int64_t m_in, int64_t m_out) {
   if (nstates <= 0) return;
   const int64_t bytes_per_state = (m_in + m_out) * (int64_t)sizeof(double);
-  int64_t chunk = std::max<int64_t>(4096, (256ll << 20) / bytes_per_state);
-  chunk = std::min(chunk, nstates);
-  chunk = (chunk + 31) / 32 * 32;
-  for (int b = 0; b < 2; ++b) {
+  // ~128 MB of traffic per chunk (short exposed head and tail of the copy/compute pipeline), rounded to whole
+  // waves of the persistent ensemble kernel (SMs x 2 CTAs x 32 states) so that no chunk ends in a partial wave
+  int sms = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int64_t wave = (int64_t)sms * 2 * 32;
+  int64_t chunk = std::max<int64_t>(wave, (128ll << 20) / bytes_per_state / wave * wave);
+  chunk = std::min(chunk, (nstates + 31) / 32 * 32);
+  for (int b = 0; b < kStage; ++b) {
     if (in[b].count < (size_t)(chunk * m_in)) in[b].alloc((size_t)(chunk * m_in));
     if (out[b].count < (size_t)(chunk * m_out)) out[b].alloc((size_t)(chunk * m_out));
   }
   int c = 0;
   for (int64_t s0 = 0; s0 < nstates; s0 += chunk, ++c) {
-    const int b = c & 1;
+    const int b = c % kStage;
     const int64_t n = std::min(chunk, nstates - s0);
     cudaStream_t st = streams[b];
     CA_CUDA(cudaMemcpy2DAsync(in[b].ptr, (size_t)n * sizeof(double), X + s0,
@@ -103,8 +110,7 @@ void eval_batched_host(const LaunchFn& launch, cudaStream_t streams[2], DeviceBu
                               (size_t)n * sizeof(double), (size_t)n * sizeof(double), (size_t)m_out,
                               cudaMemcpyDeviceToHost, st));
   }
-  CA_CUDA(cudaStreamSynchronize(streams[0]));
-  CA_CUDA(cudaStreamSynchronize(streams[1]));
+  for (int b = 0; b < kStage; ++b) CA_CUDA(cudaStreamSynchronize(streams[b]));
 }
 
 }  // namespace ca

@@ -32,10 +32,14 @@ struct DevicePack {
 void launch_batched(const DevicePack& op, int mode, const double* dX, const double* dY,
                     int64_t nstates, int64_t ldx, double* dOUT, int64_t ldo, cudaStream_t stream);
 
+// Host ensembles are processed in chunks on kStage streams with their own staging buffers: with three stages the
+// H2D of chunk c+1 and the D2H of chunk c-1 both overlap the kernel of chunk c with no bubble (with two, every
+// other kernel waits for a D2H + H2D pair on its own stream).
+constexpr int kStage = 3;
 // launches one chunk of a host ensemble: (dX, nstates (= leading dimension), dOUT, stream)
 using LaunchFn = std::function<void(const double*, int64_t, double*, cudaStream_t)>;
-void eval_batched_host(const LaunchFn& launch, cudaStream_t streams[2], DeviceBuffer<double> in[2],
-                       DeviceBuffer<double> out[2], const double* X, int64_t nstates, double* OUT,
+void eval_batched_host(const LaunchFn& launch, cudaStream_t streams[kStage], DeviceBuffer<double> in[kStage],
+                       DeviceBuffer<double> out[kStage], const double* X, int64_t nstates, double* OUT,
                        int64_t m_in, int64_t m_out);
 
 // Packing policy: operators whose two-vector state tile (x and y/v, 32 states) fits in shared memory use

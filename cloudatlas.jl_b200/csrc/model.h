@@ -58,8 +58,8 @@ struct ca_model {
   ca::DeviceBuffer<int64_t> lin_pos;          // linear slots inside op.vals
   ca::DeviceBuffer<double> lin_l1, lin_l2;
   double cur_invR = std::nan("");
-  cudaStream_t streams[2] = {nullptr, nullptr};
-  ca::DeviceBuffer<double> stage_in[2], stage_out[2], small_x, small_out, jac_out;
+  cudaStream_t streams[ca::kStage] = {nullptr, nullptr, nullptr};
+  ca::DeviceBuffer<double> stage_in[ca::kStage], stage_out[ca::kStage], small_x, small_out, jac_out;
   ~ca_model() {
     for (auto& s : streams)
       if (s) cudaStreamDestroy(s);
