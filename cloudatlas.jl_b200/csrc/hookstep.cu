@@ -103,13 +103,16 @@ __device__ void warp_lu(double* W, int* piv, int m, int* flag) {
         W[at + m * j] = t;
       }
     __syncwarp();
+    // multipliers of this lane's (at most two, m <= 64) rows stay in registers; one pass over the columns
     const double pivot = W[k + m * k];
-    for (int r = k + 1 + lane; r < m; r += 32) W[r + m * k] /= pivot;
-    __syncwarp();
-    const int n = m - k - 1;
-    for (int idx = lane; idx < n * n; idx += 32) {
-      const int r = k + 1 + idx % n, c = k + 1 + idx / n;
-      W[r + m * c] = fma(-W[r + m * k], W[k + m * c], W[r + m * c]);
+    const int r0 = k + 1 + lane, r1 = r0 + 32;
+    double l0 = 0.0, l1 = 0.0;
+    if (r0 < m) { l0 = W[r0 + m * k] / pivot; W[r0 + m * k] = l0; }
+    if (r1 < m) { l1 = W[r1 + m * k] / pivot; W[r1 + m * k] = l1; }
+    for (int c = k + 1; c < m; ++c) {
+      const double u = W[k + m * c];  // broadcast read
+      if (r0 < m) W[r0 + m * c] = fma(-l0, u, W[r0 + m * c]);
+      if (r1 < m) W[r1 + m * c] = fma(-l1, u, W[r1 + m * c]);
     }
     __syncwarp();
   }
@@ -336,11 +339,13 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
         bool singular = false;
         for (int it = 0; it < a.p.Nmusearch; ++it) {
           const double phi = norm_dx - delta;
-          // phi' = -(1/norm_dx) * dot(dx, (H + mu I) \ dx)
-          for (int e = tid; e < m * m; e += kHookThreads) W[e] = H[e] + ((e % m) == (e / m) ? mu : 0.0);
+          // phi' = -(1/norm_dx) * dot(dx, (H + mu I) \ dx).  After the first pass W already holds the LU of
+          // H + mu I: it was factored for this mu at the end of the previous pass (the reference factors twice).
+          if (it == 0)
+            for (int e = tid; e < m * m; e += kHookThreads) W[e] = H[e] + ((e % m) == (e / m) ? mu : 0.0);
           for (int i = tid; i < m; i += kHookThreads) t1[i] = dx[i];
           __syncthreads();
-          if (!block_lu(W, piv, m, flag)) { singular = true; break; }
+          if (it == 0 && !block_lu(W, piv, m, flag)) { singular = true; break; }
           block_lu_solve(W, piv, t1, m);
           const double phiprime = -(1.0 / norm_dx) * block_dot(dx, t1, m, scratch);
           mu = mu - (norm_dx / delta) * (phi / phiprime);
