@@ -219,3 +219,9 @@ def test_fuzz_all_kernel_paths_agree(ca, seed, monkeypatch):
         assert relerr(N.jvp(dX, dY).cpu().numpy()[:6], wantj) < TOL
     x = rng.standard_normal(m)
     assert relerr(N.derivative(x), ref.derivative(x)) < TOL
+
+
+def test_operator_without_terms(ca):
+    N = ca.SparseBilinear(np.zeros((0, 3), dtype=np.int64), np.zeros(0), 5)
+    X = np.random.default_rng(0).standard_normal((40, 5))
+    assert np.all(N(X) == 0.0) and np.all(N(X[0]) == 0.0) and np.all(N.derivative(X[0]) == 0.0)

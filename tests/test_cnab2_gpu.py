@@ -50,3 +50,18 @@ def test_ensemble_of_trajectories(ca, pair, known):
     # few-state path (<= 16 states: streaming kernels) agrees with the ensemble path
     _, Xf = ca.cnab2(X0[:3], dev, 200.0, 0.05, 20, 10)
     assert np.max(np.abs(Xf - X[:, :3, :])) < 1e-13
+
+
+def test_ensemble_with_windowed_operators(ca, nagata_H, known, monkeypatch):
+    """Larger models pack N and the dense [M1 M2] operator (2m inputs) in windows; force that layout on the 44d model."""
+    from oracle.model import ODEModel, cnab2 as ref_cnab2
+    monkeypatch.setenv("CA_FORCE_WINDOW_MODES", "24")
+    ref = ODEModel(1.0, 2.0, 2, 2, 3, nagata_H)
+    dev = ca.ModelOperators(ref.B, ref.A1, ref.A2, ref.N.ijk, ref.N.val)
+    rng = np.random.default_rng(9)
+    X0 = 0.05 * rng.standard_normal((70, 44))
+    t, X = ca.cnab2(X0, dev, 250.0, 0.02, 12, 4)
+    assert X.shape == (3, 70, 44)
+    for s in (0, 33, 69):
+        _, Xr = ref_cnab2(X0[s], ref, 250.0, 0.02, 12, 4)
+        assert np.max(np.abs(X[:, s, :] - Xr)) / np.max(np.abs(Xr)) < 1e-11
