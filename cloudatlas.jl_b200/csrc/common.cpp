@@ -89,6 +89,24 @@ int32_t ca_device_info(int32_t* ndevices, int32_t* sm_count, int32_t* cc_major, 
   });
 }
 
+int32_t ca_set_device(int32_t device) {
+  return ca::guarded([&] {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) ca::fail(CA_ERR_NODEVICE, "no CUDA device available");
+    if (device < 0 || device >= n) ca::fail(CA_ERR_INVALID, "device %d out of range 0:%d", device, n - 1);
+    CA_CUDA(cudaSetDevice(device));
+  });
+}
+
+int32_t ca_get_device(int32_t* device) {
+  return ca::guarded([&] {
+    if (!device) ca::fail(CA_ERR_INVALID, "null argument");
+    int d = 0;
+    CA_CUDA(cudaGetDevice(&d));
+    *device = d;
+  });
+}
+
 int32_t ca_pin(void* host_ptr, int64_t bytes) {
   return ca::guarded([&] {
     if (!host_ptr || bytes <= 0) ca::fail(CA_ERR_INVALID, "ca_pin: null pointer or non-positive size");

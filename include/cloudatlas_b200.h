@@ -54,6 +54,11 @@ int32_t ca_version(void);
 /* number of CUDA devices visible, name + SM count + compute capability of the current one */
 int32_t ca_device_info(int32_t* ndevices, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,
                        char* name, int32_t name_len);
+/* select / query the CUDA device of the calling host thread (cudaSetDevice / cudaGetDevice): handles are created
+ * on the current device, so a single process drives several GPUs by calling this before ca_*_create / ca_assemble,
+ * one host thread (Julia task) per device */
+int32_t ca_set_device(int32_t device);
+int32_t ca_get_device(int32_t* device);
 /* page-lock / unlock a caller-owned host buffer so the host-pointer entry points can overlap
  * copies with kernels (Julia: call on the Array's pointer; optional, results identical) */
 int32_t ca_pin(void* host_ptr, int64_t bytes);

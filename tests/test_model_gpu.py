@@ -102,3 +102,36 @@ def test_small_model_large_ensemble_uses_specialised_kernel(ca, nagata_H):
             want = np.stack([ref.f(x, R) for x in X[:40]])
             assert relerr(got[:40], want) < 1e-13 * max(1.0, np.linalg.cond(ref.B) / 10)
         assert relerr(dev.f(X, 200.0)[:100], small) < 1e-14
+
+
+def test_full_size_ensemble_properties(ca, nagata_H):
+    """BASELINE.json configs[2] at full size (10^6 states, 307 modes): size-independent properties -- results do not
+    depend on where a state sits in the ensemble (bit-exact under permutation), the host-pointer path equals the
+    device path bit for bit, and a random sample agrees with the CPU port of the reference loops."""
+    import torch
+    from oracle.cref import CRefModel
+    sx, sy, sz, tx, tz = ca.halfbox_symmetries()
+    model = ca.ODEModel(1.0, 2.0, 3, 3, 12, [sx * sy * sz, sz * tx * tz])
+    n, m = 1_000_000, model.m
+    gen = torch.Generator(device="cuda").manual_seed(20251029)
+    X = (0.1 * torch.randn((m, n), dtype=torch.float64, device="cuda", generator=gen)).t()
+    F = model.f(X, 200.0)
+    perm = torch.randperm(n, device="cuda", generator=gen)
+    Xp = X.t()[:, perm].contiguous().t()
+    Fp = model.f(Xp, 200.0)
+    assert torch.equal(Fp, F.t()[:, perm].t())
+    # host path on a slice (pageable memory): same bits
+    sl = slice(123_456, 323_456)
+    Fh = model.f(np.asfortranarray(X[sl].cpu().numpy()), 200.0)
+    assert np.array_equal(Fh, F[sl].cpu().numpy())
+    # reference loops on a sample
+    idx = torch.randint(0, n, (96,), device="cuda", generator=gen)
+    ref = CRefModel(model.B, model.A1, model.A2, model.ijk, model.val)
+    want = ref.f_ensemble(np.asfortranarray(X[idx].cpu().numpy()), 200.0, threads=8)
+    got = F[idx].cpu().numpy()
+    tol = 1e-13 * max(1.0, np.linalg.cond(model.B) / 10)
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < tol
+    # backward parity independent of cond(B): B f = A1 x + A2 x / R + N(x)
+    xs = X[idx].cpu().numpy()
+    rhs = np.stack([model.A1 @ x + (model.A2 @ x) / 200.0 + ref.N(x) for x in xs])
+    assert np.linalg.norm(got @ model.B.T - rhs) / np.linalg.norm(rhs) < 1e-13
