@@ -592,3 +592,49 @@ extern "C" int32_t ca_model_observables_batched_dev(ca_model* h, const double* d
     eval_pack(h->obs, h->obs_stream, dX, nstates, ld, dOUT, nstates, (cudaStream_t)stream);
   });
 }
+
+// ------------------------------------------------------------------ host-pointer convenience forms
+extern "C" int32_t ca_model_jvp_batched(ca_model* h, const double* X, const double* V, int64_t nstates, double R,
+                                        double* OUT) {
+  return guarded([&] {
+    if (!h || !X || !V || !OUT || nstates <= 0) fail(CA_ERR_INVALID, "bad argument");
+    h->bind();
+    const size_t n = (size_t)nstates * h->m;
+    DeviceBuffer<double> dX, dV, dO;
+    dX.upload(X, n);
+    dV.upload(V, n);
+    dO.alloc(n);
+    h->eval_dev(MODE_JVP, dX.ptr, dV.ptr, nstates, nstates, R, dO.ptr, nstates, nullptr);
+    CA_CUDA(cudaMemcpy(OUT, dO.ptr, n * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+extern "C" int32_t ca_model_cnab2_batched(ca_model* h, const double* X0, int64_t nstates, double R, double dt,
+                                          int64_t nsteps, int64_t nsave, double* Xsave, double* Xfinal) {
+  return guarded([&] {
+    if (!h || !X0 || nstates <= 0 || nsave <= 0 || nsteps < 0) fail(CA_ERR_INVALID, "bad argument");
+    h->bind();
+    const size_t n = (size_t)nstates * h->m, nsaves = (size_t)(nsteps / nsave);
+    DeviceBuffer<double> dX, dS, dF;
+    dX.upload(X0, n);
+    if (Xsave && nsaves) dS.alloc(n * nsaves);
+    if (Xfinal) dF.alloc(n);
+    const int32_t st = ca_model_cnab2_batched_dev(h, dX.ptr, nstates, nstates, R, dt, nsteps, nsave, dS.ptr, dF.ptr, nullptr);
+    if (st != CA_OK) fail(st, "%s", ca_last_error());
+    if (Xsave && nsaves) CA_CUDA(cudaMemcpy(Xsave, dS.ptr, n * nsaves * sizeof(double), cudaMemcpyDeviceToHost));
+    if (Xfinal) CA_CUDA(cudaMemcpy(Xfinal, dF.ptr, n * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+extern "C" int32_t ca_model_observables_batched(ca_model* h, const double* X, int64_t nstates, double* OBS) {
+  return guarded([&] {
+    if (!h || !X || !OBS || nstates <= 0) fail(CA_ERR_INVALID, "bad argument");
+    h->bind();
+    DeviceBuffer<double> dX, dO;
+    dX.upload(X, (size_t)nstates * h->m);
+    dO.alloc((size_t)nstates * 2);
+    const int32_t st = ca_model_observables_batched_dev(h, dX.ptr, nstates, nstates, dO.ptr, nullptr);
+    if (st != CA_OK) fail(st, "%s", ca_last_error());
+    CA_CUDA(cudaMemcpy(OBS, dO.ptr, (size_t)nstates * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}

@@ -127,6 +127,26 @@ function B200Model(α::Float64, γ::Float64, J::Int, K::Int, L::Int, H::Vector{S
     _model_from_operators(ijkl, B, A1, A2, SparseBilinear(ijk, val, m))
 end
 
+"cnab2(x₀, model, R, Δt, Nsteps, nsave) for one trajectory (Vector) or an ensemble (Matrix, one state per row) -- ODEModels.jl:147"
+function CloudAtlas.cnab2(x0::VecOrMat{Float64}, model::B200Model, R, Δt, Nsteps, nsave)
+    X0 = x0 isa Vector ? reshape(x0, 1, :) : x0
+    ns, Nsave = size(X0, 1), Nsteps ÷ nsave
+    Xsave = Array{Float64}(undef, ns, model.m, Nsave)
+    check(ccall((:ca_model_cnab2_batched, lib), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Float64, Float64, Int64, Int64, Ptr{Float64}, Ptr{Float64}),
+                model.handle, X0, ns, R, Δt, Nsteps, nsave, Xsave, C_NULL))
+    t = (0:Nsave-1) * Δt                                   # as the reference (ODEModels.jl:162)
+    x0 isa Vector ? (t, permutedims(Xsave[1, :, :])) : (t, Xsave)
+end
+
+"(shear, dissipation) per state -- shear_function / dissipation_function, ODEModels.jl:65-137; needs ca_model_set_observables"
+function observables(model::B200Model, X::Matrix{Float64})
+    OBS = Matrix{Float64}(undef, size(X, 1), 2)
+    check(ccall((:ca_model_observables_batched, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}),
+                model.handle, X, size(X, 1), OBS))
+    OBS
+end
+
 Base.length(model::B200Model) = model.m                                 # ODEModels.jl:63
 
 # ---- Newton-hookstep (src/Hookstep.jl) -----------------------------------------------------------------------

@@ -20,6 +20,10 @@ _cnab2 = _sig("ca_model_cnab2_batched_dev", vp, vp, C.c_int64, C.c_int64, C.c_do
               C.c_int64, vp, vp, vp)
 _set_obs = _sig("ca_model_set_observables", vp, c_f64p, c_f64p)
 _obs_dev = _sig("ca_model_observables_batched_dev", vp, vp, C.c_int64, C.c_int64, vp, vp)
+_jvp_b_host = _sig("ca_model_jvp_batched", vp, c_f64p, c_f64p, C.c_int64, C.c_double, c_f64p)
+_cnab2_host = _sig("ca_model_cnab2_batched", vp, c_f64p, C.c_int64, C.c_double, C.c_double, C.c_int64, C.c_int64,
+                   c_f64p, c_f64p)
+_obs_host = _sig("ca_model_observables_batched", vp, c_f64p, C.c_int64, c_f64p)
 _jvp_b_dev = _sig("ca_model_jvp_batched_dev", vp, vp, vp, C.c_int64, C.c_int64, C.c_double, vp, C.c_int64, vp)
 
 
@@ -115,7 +119,13 @@ class ModelOperators:
         return D
 
     def Df_action(self, X, V, R):
-        """Df(x_s, R) v_s for CUDA ensembles (matrix-free)."""
+        """Df(x_s, R) v_s, matrix-free: CUDA ensembles (device path) or numpy ensembles (host-pointer path)."""
+        if not _is_torch(X):
+            Xh = np.asfortranarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))
+            Vh = np.asfortranarray(np.atleast_2d(np.asarray(V, dtype=np.float64)))
+            OUT = np.empty(Xh.shape, order="F")
+            check(_jvp_b_host(self._h, _f64(Xh), _f64(Vh), Xh.shape[0], float(R), _f64(OUT)))
+            return OUT[0] if np.ndim(X) == 1 else OUT
         X, n, ld = _colmajor_ensemble(X)
         V, n2, ld2 = _colmajor_ensemble(V)
         if (n2, ld2) != (n, ld):

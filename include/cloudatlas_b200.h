@@ -208,6 +208,13 @@ int32_t ca_model_set_observables(ca_model* h, const double* shear, const double*
 int32_t ca_model_observables_batched_dev(ca_model* h, const double* dX, int64_t nstates, int64_t ld,
                                          double* dOUT, void* stream);
 
+/* Host-pointer forms of the three entry points above (Julia Arrays are host memory): plain copies around the
+ * device calls.  X, V, OUT: nstates x m column-major; Xsave: Nsave snapshots of nstates x m; OBS: nstates x 2. */
+int32_t ca_model_jvp_batched(ca_model* h, const double* X, const double* V, int64_t nstates, double R, double* OUT);
+int32_t ca_model_cnab2_batched(ca_model* h, const double* X0, int64_t nstates, double R, double dt, int64_t nsteps,
+                               int64_t nsave, double* Xsave, double* Xfinal);
+int32_t ca_model_observables_batched(ca_model* h, const double* X, int64_t nstates, double* OBS);
+
 /* ---- Newton-hookstep (reference: src/Hookstep.jl) --------------------------------------------- */
 /* SearchParams -- Hookstep.jl:6-14, same fields, order and defaults
  * (ftol = xtol = 1e-8, delta = 0.02, Nnewton = 20, Nhook = 4, Nmusearch = 6, verbosity = 0). */

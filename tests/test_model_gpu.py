@@ -135,3 +135,27 @@ def test_full_size_ensemble_properties(ca, nagata_H):
     xs = X[idx].cpu().numpy()
     rhs = np.stack([model.A1 @ x + (model.A2 @ x) / 200.0 + ref.N(x) for x in xs])
     assert np.linalg.norm(got @ model.B.T - rhs) / np.linalg.norm(rhs) < 1e-13
+
+
+def test_host_pointer_forms_of_jvp_cnab2_observables(ca, nagata_H):
+    """The host-array entry points a Julia binding uses (no device pointers) agree with the device-pointer forms."""
+    import ctypes as C
+    import torch
+    from cloudatlas_b200.model import _cnab2_host, _obs_host
+    from cloudatlas_b200._lib import c_f64p, check
+    sx, sy, sz, tx, tz = ca.halfbox_symmetries()
+    model = ca.ODEModel(1.0, 2.0, 2, 2, 3, [sx * sy * sz, sz * tx * tz])
+    rng = np.random.default_rng(2)
+    X = np.asfortranarray(0.1 * rng.standard_normal((50, 44)))
+    V = np.asfortranarray(rng.standard_normal((50, 44)))
+    dX, dV = (torch.from_numpy(A.T.copy()).cuda().t() for A in (X, V))
+    assert np.array_equal(model.Df_action(X, V, 210.0), model.Df_action(dX, dV, 210.0).cpu().numpy())
+    t, Xs = ca.cnab2(X, model, 210.0, 0.05, 6, 3)
+    save = np.empty((2, 44, 50))
+    final = np.empty((50, 44), order="F")
+    check(_cnab2_host(model._h, X.ctypes.data_as(c_f64p), 50, 210.0, 0.05, 6, 3, save.ctypes.data_as(c_f64p),
+                      final.ctypes.data_as(c_f64p)))
+    assert np.array_equal(save.transpose(0, 2, 1), Xs) and np.array_equal(final, Xs[-1])
+    obs = np.empty((50, 2), order="F")
+    check(_obs_host(model._h, X.ctypes.data_as(c_f64p), 50, obs.ctypes.data_as(c_f64p)))
+    assert np.array_equal(obs, model.observables(X))
