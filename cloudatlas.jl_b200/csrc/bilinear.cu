@@ -26,6 +26,10 @@ void DevicePack::upload(const PackedHost& P) {
   for (const WindowDesc& W : P.windows) nwin_nt2 += P.tiles[W.tile].nt == 2;
   windows.upload(P.windows.data(), P.windows.size());
   modes.upload(P.modes.data(), P.modes.size());
+  sched.upload(P.sched.data(), P.sched.size());
+  for (int w = 0; w < 9; ++w) sched_off[w] = P.sched_off[w];
+  for (int w = 0; w < 8; ++w) sched_nt2[w] = P.sched_nt2[w];
+  sched_imbalance = P.sched_imbalance;
   host_pairs = P.pairs;
   for (auto& b : pairs_mt) b.release();
   vals.upload(P.vals.data(), P.vals.size());
@@ -74,9 +78,36 @@ const LaunchCfg& device_cfg() {
   return cfg;
 }
 
+// whole tiles per warp when the packer's LPT schedule is balanced (no reduction, no per-tile barriers)
+constexpr double kMaxSchedImbalance = 1.08;
+
+template <int MT, int MODE>
+void launch_warptile(const DevicePack& op, const double* dX, const double* dY, int64_t nstates, int64_t ldx,
+                     double* dOUT, int64_t ldo, cudaStream_t stream) {
+  auto kern = bilinear_warptile_kernel<MT, MODE>;
+  const size_t smem = warptile_smem_bytes<MT, MODE>(op.nin);
+  CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  if (per_sm < 1) fail(CA_ERR_UNSUPPORTED, "warp-tile kernel does not fit (smem %zu B)", smem);
+  const int64_t nblocks = (nstates + 8 * MT - 1) / (8 * MT);
+  const int grid = (int)std::min<int64_t>(nblocks, (int64_t)device_cfg().sms * per_sm);
+  WarpSchedule ws;
+  for (int w = 0; w < 9; ++w) ws.off[w] = op.sched_off[w];
+  for (int w = 0; w < 8; ++w) ws.nt2[w] = op.sched_nt2[w];
+  kern<<<grid, kThreads, smem, stream>>>(op.tiles.ptr, op.sched.ptr, ws, op.pairs_for(MT), op.vals.ptr, op.rows.ptr,
+                                         op.nin, dX, dY, nstates, ldx, dOUT, ldo);
+  CA_CUDA(cudaGetLastError());
+  count_launch();
+}
+
 template <int MT, int MODE>
 void launch_one(const DevicePack& op, const double* dX, const double* dY, int64_t nstates, int64_t ldx,
                 double* dOUT, int64_t ldo, cudaStream_t stream) {
+  if (op.sched_imbalance <= kMaxSchedImbalance && !getenv("CA_FORCE_KSPLIT")) {
+    launch_warptile<MT, MODE>(op, dX, dY, nstates, ldx, dOUT, ldo, stream);
+    return;
+  }
   auto kern = bilinear_batched_kernel<MT, MODE>;
   const size_t smem = batched_smem_bytes<MT, MODE>(op.nin);
   CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -21,6 +21,10 @@ struct DevicePack {
   const uint2* pairs_for(int mt) const;
   DeviceBuffer<double> vals;
   DeviceBuffer<int32_t> rows;
+  // whole-tile-per-warp schedule (pack.h)
+  DeviceBuffer<int32_t> sched;
+  int32_t sched_off[9] = {0}, sched_nt2[8] = {0};
+  double sched_imbalance = 1e9;
   // windowed packs (large m): pair words hold window-local rows
   int32_t window_modes = 0, nwin = 0, nwin_nt2 = 0, max_window_modes = 0;
   DeviceBuffer<WindowDesc> windows;

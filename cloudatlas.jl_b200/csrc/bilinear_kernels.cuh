@@ -66,6 +66,11 @@ __device__ __forceinline__ void prefetch_vals(double (&bv)[NT], const double* vp
 
 // This warp's contiguous share [k0, k1) of a range of nks k-steps.
 __device__ __forceinline__ void warp_share(int nks, int warp, int& k0, int& k1) {
+  if (warp < 0) {  // the whole range belongs to the calling warp (whole-tile-per-warp schedule)
+    k0 = 0;
+    k1 = nks;
+    return;
+  }
   k0 = (int)(((int64_t)nks * warp) / kWarps);
   k1 = (int)(((int64_t)nks * (warp + 1)) / kWarps);
 }
@@ -206,6 +211,102 @@ __device__ __forceinline__ void run_tiles(const TileDesc* __restrict__ tiles, in
     }
     tile_reduce_store<MT, NT>(done, rows, red, acc, warp, lane, s0, nstates, OUT, ldo);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Whole-tile-per-warp variant: the packer assigns complete tiles to warps (LPT), so a warp owns every k-step of its
+// tiles, keeps the accumulators to the end and writes its 32 x 8nt outputs straight from the C fragments.  No
+// cross-warp reduction, no per-tile barrier, no reduction buffer; the only barriers are the two around the load
+// of a state tile.
+struct WarpSchedule {
+  int32_t off[9];
+  int32_t nt2[8];
+};
+
+template <int MT, int NT>
+__device__ __forceinline__ void tile_store_direct(const TileDesc& T, const int32_t* __restrict__ rows,
+                                                  const double (&acc)[MT][NT][2], int lane, int64_t s0,
+                                                  int64_t nstates, double* __restrict__ OUT, int64_t ldo) {
+  const int r = lane >> 2, c = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int row = __ldg(rows + T.rows_off + nt * 8 + 2 * c + e);
+      if (row < 0) continue;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int64_t s = s0 + mt * 8 + r;
+        if (s < nstates) OUT[s + ldo * (int64_t)row] = acc[mt][nt][e];
+      }
+    }
+}
+
+template <int MT, int NT, int MODE>
+__device__ __forceinline__ void run_my_tiles(const TileDesc* __restrict__ tiles, const int32_t* __restrict__ sched,
+                                             int b, int e, const uint2* __restrict__ pairs,
+                                             const double* __restrict__ vals, const int32_t* __restrict__ rows,
+                                             const double* xs, const double* ys, int lane, int64_t s0,
+                                             int64_t nstates, double* __restrict__ OUT, int64_t ldo) {
+  if (b >= e) return;
+  Prefetch<NT> pf;
+  TileDesc T = tiles[__ldg(sched + b)];
+  range_prologue<NT>(pairs + (size_t)T.ks_begin * 4, vals + T.vals_off, T.nks, -1, lane, pf);
+  for (int t = b; t < e; ++t) {
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    range_accumulate<MT, NT, MODE>(pairs + (size_t)T.ks_begin * 4, vals + T.vals_off, T.nks, xs, ys, -1, lane, pf, acc);
+    const TileDesc done = T;
+    if (t + 1 < e) {
+      T = tiles[__ldg(sched + t + 1)];
+      range_prologue<NT>(pairs + (size_t)T.ks_begin * 4, vals + T.vals_off, T.nks, -1, lane, pf);
+    }
+    tile_store_direct<MT, NT>(done, rows, acc, lane, s0, nstates, OUT, ldo);
+  }
+}
+
+template <int MT, int MODE>
+__global__ void __launch_bounds__(kThreads, 2)
+bilinear_warptile_kernel(const TileDesc* __restrict__ tiles, const int32_t* __restrict__ sched, WarpSchedule ws,
+                         const uint2* __restrict__ pairs, const double* __restrict__ vals,
+                         const int32_t* __restrict__ rows, int nin, const double* __restrict__ X,
+                         const double* __restrict__ Y, int64_t nstates, int64_t ldx, double* __restrict__ OUT,
+                         int64_t ldo) {
+  constexpr int ROW = 8 * MT;
+  extern __shared__ __align__(16) double smem[];
+  double* xs = smem;
+  double* ys = MODE == MODE_QUAD ? smem : smem + (size_t)nin * ROW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t nblocks = (nstates + ROW - 1) / ROW;
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int64_t s0 = blk * ROW;
+    __syncthreads();  // everyone is done with the previous block's state tile
+    for (int o = threadIdx.x; o < nin * ROW; o += kThreads) {
+      const int j = o / ROW, s = o % ROW;
+      double vx = 0.0, vy = 0.0;
+      if (j == nin - 1) {
+        vx = 1.0;
+        vy = MODE == MODE_JVP ? 0.0 : 1.0;
+      } else if (s0 + s < nstates) {
+        vx = X[(s0 + s) + ldx * (int64_t)j];
+        if (MODE != MODE_QUAD) vy = Y[(s0 + s) + ldx * (int64_t)j];
+      }
+      xs[j * ROW + (s ^ swz<MT>(j))] = vx;
+      if (MODE != MODE_QUAD) ys[j * ROW + (s ^ swz<MT>(j))] = vy;
+    }
+    __syncthreads();
+    const int b = ws.off[warp], mid = b + ws.nt2[warp], e = ws.off[warp + 1];
+    run_my_tiles<MT, 2, MODE>(tiles, sched, b, mid, pairs, vals, rows, xs, ys, lane, s0, nstates, OUT, ldo);
+    run_my_tiles<MT, 1, MODE>(tiles, sched, mid, e, pairs, vals, rows, xs, ys, lane, s0, nstates, OUT, ldo);
+  }
+}
+
+template <int MT, int MODE>
+inline size_t warptile_smem_bytes(int nin) {
+  return (MODE == MODE_QUAD ? 1 : 2) * (size_t)nin * 8 * MT * sizeof(double);
 }
 
 // X, Y: nstates x (nin-1) column-major with leading dimension ldx; OUT: nstates x m, ldo.

@@ -379,6 +379,35 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
     }
   }
   P.tiles = std::move(sorted);
+  {  // LPT schedule of whole tiles onto 8 warps (weight = DMMAs per state tile)
+    std::vector<int32_t> idx(P.tiles.size());
+    std::iota(idx.begin(), idx.end(), 0);
+    auto weight = [&](int32_t t) { return (int64_t)P.tiles[t].nks * P.tiles[t].nt + 1; };
+    std::stable_sort(idx.begin(), idx.end(), [&](int32_t x, int32_t y) { return weight(x) > weight(y); });
+    int64_t load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<int32_t> bins[8];
+    for (int32_t t : idx) {
+      int w = 0;
+      for (int q = 1; q < 8; ++q)
+        if (load[q] < load[w]) w = q;
+      load[w] += weight(t);
+      bins[w].push_back(t);
+    }
+    int64_t total = 0, worst = 0;
+    for (int w = 0; w < 8; ++w) {
+      total += load[w];
+      worst = std::max(worst, load[w]);
+      std::stable_sort(bins[w].begin(), bins[w].end(), [&](int32_t x, int32_t y) { return P.tiles[x].nt > P.tiles[y].nt; });
+      P.sched_off[w] = (int32_t)P.sched.size();
+      P.sched_nt2[w] = 0;
+      for (int32_t t : bins[w]) {
+        P.sched.push_back(t);
+        P.sched_nt2[w] += P.tiles[t].nt == 2;
+      }
+    }
+    P.sched_off[8] = (int32_t)P.sched.size();
+    P.sched_imbalance = total > 0 ? (double)worst * 8.0 / (double)total : 1e9;
+  }
   return P;
 }
 

@@ -54,6 +54,14 @@ struct PackedHost {
   std::vector<WindowDesc> windows;  // in tile order
   std::vector<int32_t> modes;       // global mode index of every local row of every window
   int32_t max_window_modes = 0;
+  // Whole-tile-per-warp schedule (longest-processing-time assignment of tiles to the 8 warps of a CTA): warp w
+  // runs tiles sched[sched_off[w] .. sched_off[w+1]), the first sched_nt2[w] of them have nt == 2.  With it a
+  // warp owns all k-steps of its tiles: no cross-warp reduction, no per-tile barrier.  sched_imbalance =
+  // heaviest warp / mean; the kernel falls back to splitting k-steps across warps when it is poor.
+  std::vector<int32_t> sched;
+  int32_t sched_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int32_t sched_nt2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double sched_imbalance = 0.0;
   int64_t nterms = 0;           // merged non-zero terms
   int64_t npairs_distinct = 0;  // distinct (a,b) over the whole operator
   int64_t padded_fma = 0;       // FMAs the tiles execute per state (incl. padding)
