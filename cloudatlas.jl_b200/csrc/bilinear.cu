@@ -28,7 +28,12 @@ void DevicePack::upload(const PackedHost& P) {
   modes.upload(P.modes.data(), P.modes.size());
   sched.upload(P.sched.data(), P.sched.size());
   for (int w = 0; w < 9; ++w) sched_off[w] = P.sched_off[w];
-  for (int w = 0; w < 8; ++w) sched_nt2[w] = P.sched_nt2[w];
+  for (int w = 0; w < 8; ++w) {
+    sched_nt2[w] = P.sched_nt2[w];
+    sched_ks2[w] = P.sched_ks2[w];
+    sched_ks1[w] = P.sched_ks1[w];
+  }
+  stream_layout = P.stream_layout;
   sched_imbalance = P.sched_imbalance;
   host_pairs = P.pairs;
   for (auto& b : pairs_mt) b.release();
@@ -41,7 +46,7 @@ const uint2* DevicePack::pairs_for(int mt) const {
   const int slot = mt == 4 ? 2 : (mt == 2 ? 1 : 0);
   DeviceBuffer<uint2>& buf = pairs_mt[slot];
   if (!buf.ptr && !host_pairs.empty()) {
-    std::vector<uint2> w(host_pairs.size());
+    std::vector<uint2> w(host_pairs.size() + 64, make_uint2(0, 0));  // + one cp.async batch of padding (PairRing)
     for (size_t e = 0; e < host_pairs.size(); ++e) {
       const int a = host_pairs[e] & 0x7fff, b = host_pairs[e] >> 16;
       const uint32_t flag = (host_pairs[e] & 0x8000u) ? kSameA : 0u;
@@ -94,7 +99,11 @@ void launch_warptile(const DevicePack& op, const double* dX, const double* dY, i
   const int grid = (int)std::min<int64_t>(nblocks, (int64_t)device_cfg().sms * per_sm);
   WarpSchedule ws;
   for (int w = 0; w < 9; ++w) ws.off[w] = op.sched_off[w];
-  for (int w = 0; w < 8; ++w) ws.nt2[w] = op.sched_nt2[w];
+  for (int w = 0; w < 8; ++w) {
+    ws.nt2[w] = op.sched_nt2[w];
+    ws.ks2[w] = op.sched_ks2[w];
+    ws.ks1[w] = op.sched_ks1[w];
+  }
   kern<<<grid, kThreads, smem, stream>>>(op.tiles.ptr, op.sched.ptr, ws, op.pairs_for(MT), op.vals.ptr, op.rows.ptr,
                                          op.nin, dX, dY, nstates, ldx, dOUT, ldo);
   CA_CUDA(cudaGetLastError());
@@ -104,7 +113,7 @@ void launch_warptile(const DevicePack& op, const double* dX, const double* dY, i
 template <int MT, int MODE>
 void launch_one(const DevicePack& op, const double* dX, const double* dY, int64_t nstates, int64_t ldx,
                 double* dOUT, int64_t ldo, cudaStream_t stream) {
-  if (op.sched_imbalance <= kMaxSchedImbalance && !getenv("CA_FORCE_KSPLIT")) {
+  if (op.stream_layout && op.sched_imbalance <= kMaxSchedImbalance && !getenv("CA_FORCE_KSPLIT")) {
     launch_warptile<MT, MODE>(op, dX, dY, nstates, ldx, dOUT, ldo, stream);
     return;
   }

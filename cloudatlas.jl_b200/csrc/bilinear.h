@@ -23,7 +23,8 @@ struct DevicePack {
   DeviceBuffer<int32_t> rows;
   // whole-tile-per-warp schedule (pack.h)
   DeviceBuffer<int32_t> sched;
-  int32_t sched_off[9] = {0}, sched_nt2[8] = {0};
+  int32_t sched_off[9] = {0}, sched_nt2[8] = {0}, sched_ks2[8] = {0}, sched_ks1[8] = {0};
+  bool stream_layout = false;
   double sched_imbalance = 1e9;
   // windowed packs (large m): pair words hold window-local rows
   int32_t window_modes = 0, nwin = 0, nwin_nt2 = 0, max_window_modes = 0;

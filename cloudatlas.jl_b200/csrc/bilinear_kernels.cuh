@@ -221,7 +221,89 @@ __device__ __forceinline__ void run_tiles(const TileDesc* __restrict__ tiles, in
 struct WarpSchedule {
   int32_t off[9];
   int32_t nt2[8];
+  int32_t ks2[8], ks1[8];  // k-steps of the warp's nt == 2 and nt == 1 streams (contiguous in memory, pack.h)
 };
+
+// Pair words of a warp's stream go through a small per-warp ring in shared memory, filled with cp.async 24 k-steps
+// ahead and across tile boundaries: they are the first thing a k-step needs (address arithmetic), and fetching them
+// four k-steps ahead into registers left ~14 % of the issue slots waiting on L2.  Operator values are consumed last
+// in a k-step (by the DMMAs) and stay register-prefetched.
+constexpr int kPairBatch = 8;                    // k-steps per cp.async group (256 B)
+constexpr int kPairBatches = 4;                  // ring = 4 batches = 32 k-steps = 1 KB per warp
+constexpr int kPairRingBytes = kPairBatch * kPairBatches * 32;
+
+struct PairRing {
+  const uint2* stream;  // first pair word of the warp's stream
+  char* ring;           // this warp's kPairRingBytes
+  int total;            // k-steps in the stream
+  int g;                // next k-step to consume
+
+  __device__ __forceinline__ void issue_batch(int batch, int lane) const {
+    if (batch * kPairBatch < total && lane < 16) {  // 16 lanes x 16 B = one batch; reading past the stream's end by
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(ring + (batch % kPairBatches) * (kPairBatch * 32) + lane * 16);
+      const char* src = reinterpret_cast<const char*>(stream + (size_t)batch * kPairBatch * 4) + lane * 16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");  // < 256 B stays inside the pairs array + pad
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  __device__ __forceinline__ void begin(int lane) {
+    g = 0;
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < kPairBatches - 1; ++b) issue_batch(b, lane);
+  }
+  // pair word of k-step g for this lane's column; refills one batch ahead at batch boundaries
+  __device__ __forceinline__ uint2 next(int lane) {
+    if ((g & (kPairBatch - 1)) == 0) {  // warp-uniform
+      __syncwarp();                     // the batch slot refilled now was consumed by every lane
+      issue_batch(g / kPairBatch + kPairBatches - 1, lane);
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(kPairBatches - 1) : "memory");
+      __syncwarp();                     // batch g / kPairBatch has landed for all lanes
+    }
+    const uint2 w = reinterpret_cast<const uint2*>(ring)[(g & (kPairBatch * kPairBatches - 1)) * 4 + (lane & 3)];
+    ++g;
+    return w;
+  }
+  __device__ __forceinline__ void end() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+};
+
+// values-only register prefetch for the ring variant
+template <int NT>
+struct ValPrefetch {
+  double bv[kPrefetch][NT];
+};
+
+template <int MT, int NT, int MODE>
+__device__ __forceinline__ void tile_accumulate_ring(const double* __restrict__ vals0, int nks, const double* xs,
+                                                     const double* ys, int lane, PairRing& pr, ValPrefetch<NT>& pf,
+                                                     double (&acc)[MT][NT][2]) {
+  const uint32_t r8 = 8u * (lane >> 2);
+  const double* vp = vals0 + lane;
+  const char* xsb = reinterpret_cast<const char*>(xs);
+  const char* ysb = reinterpret_cast<const char*>(ys);
+  double xa[MT], va[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) xa[mt] = va[mt] = 0.0;
+  int i = 0;
+  for (; i + kPrefetch <= nks; i += kPrefetch) {
+#pragma unroll
+    for (int u = 0; u < kPrefetch; ++u) {
+      uint2 pw = pr.next(lane);
+      if (i + u == 0) pw.x &= ~kSameA;  // first k-step of a tile loads its first factors
+      kstep<MT, NT, MODE>(pw, pf.bv[u], xsb, ysb, r8, xa, va, acc);
+      prefetch_vals<NT>(pf.bv[u], vp, min(i + u + kPrefetch, nks - 1));
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kPrefetch - 1; ++u) {
+    if (i + u < nks) {
+      uint2 pw = pr.next(lane);
+      if (i + u == 0) pw.x &= ~kSameA;
+      kstep<MT, NT, MODE>(pw, pf.bv[u], xsb, ysb, r8, xa, va, acc);
+    }
+  }
+}
+
 
 template <int MT, int NT>
 __device__ __forceinline__ void tile_store_direct(const TileDesc& T, const int32_t* __restrict__ rows,
@@ -244,28 +326,37 @@ __device__ __forceinline__ void tile_store_direct(const TileDesc& T, const int32
 
 template <int MT, int NT, int MODE>
 __device__ __forceinline__ void run_my_tiles(const TileDesc* __restrict__ tiles, const int32_t* __restrict__ sched,
-                                             int b, int e, const uint2* __restrict__ pairs,
+                                             int b, int e, int total, const uint2* __restrict__ pairs,
                                              const double* __restrict__ vals, const int32_t* __restrict__ rows,
-                                             const double* xs, const double* ys, int lane, int64_t s0,
+                                             const double* xs, const double* ys, char* ring, int lane, int64_t s0,
                                              int64_t nstates, double* __restrict__ OUT, int64_t ldo) {
   if (b >= e) return;
-  Prefetch<NT> pf;
   TileDesc T = tiles[__ldg(sched + b)];
-  range_prologue<NT>(pairs + (size_t)T.ks_begin * 4, vals + T.vals_off, T.nks, -1, lane, pf);
+  PairRing pr{pairs + (size_t)T.ks_begin * 4, ring, total, 0};
+  pr.begin(lane);
+  ValPrefetch<NT> pf;
+  auto prologue = [&](const TileDesc& Tn) {
+    const double* vp = vals + Tn.vals_off + lane;
+#pragma unroll
+    for (int u = 0; u < kPrefetch; ++u)
+      if (Tn.nks > 0) prefetch_vals<NT>(pf.bv[u], vp, min(u, Tn.nks - 1));
+  };
+  prologue(T);
   for (int t = b; t < e; ++t) {
     double acc[MT][NT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-    range_accumulate<MT, NT, MODE>(pairs + (size_t)T.ks_begin * 4, vals + T.vals_off, T.nks, xs, ys, -1, lane, pf, acc);
+    tile_accumulate_ring<MT, NT, MODE>(vals + T.vals_off, T.nks, xs, ys, lane, pr, pf, acc);
     const TileDesc done = T;
     if (t + 1 < e) {
       T = tiles[__ldg(sched + t + 1)];
-      range_prologue<NT>(pairs + (size_t)T.ks_begin * 4, vals + T.vals_off, T.nks, -1, lane, pf);
+      prologue(T);
     }
     tile_store_direct<MT, NT>(done, rows, acc, lane, s0, nstates, OUT, ldo);
   }
+  pr.end();
 }
 
 template <int MT, int MODE>
@@ -280,6 +371,8 @@ bilinear_warptile_kernel(const TileDesc* __restrict__ tiles, const int32_t* __re
   double* xs = smem;
   double* ys = MODE == MODE_QUAD ? smem : smem + (size_t)nin * ROW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t tile_doubles = ((MODE == MODE_QUAD ? 1 : 2) * (size_t)nin * ROW + 1) & ~(size_t)1;
+  char* ring = reinterpret_cast<char*>(smem + tile_doubles) + warp * kPairRingBytes;
   const int64_t nblocks = (nstates + ROW - 1) / ROW;
   for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
     const int64_t s0 = blk * ROW;
@@ -299,14 +392,15 @@ bilinear_warptile_kernel(const TileDesc* __restrict__ tiles, const int32_t* __re
     }
     __syncthreads();
     const int b = ws.off[warp], mid = b + ws.nt2[warp], e = ws.off[warp + 1];
-    run_my_tiles<MT, 2, MODE>(tiles, sched, b, mid, pairs, vals, rows, xs, ys, lane, s0, nstates, OUT, ldo);
-    run_my_tiles<MT, 1, MODE>(tiles, sched, mid, e, pairs, vals, rows, xs, ys, lane, s0, nstates, OUT, ldo);
+    run_my_tiles<MT, 2, MODE>(tiles, sched, b, mid, ws.ks2[warp], pairs, vals, rows, xs, ys, ring, lane, s0, nstates, OUT, ldo);
+    run_my_tiles<MT, 1, MODE>(tiles, sched, mid, e, ws.ks1[warp], pairs, vals, rows, xs, ys, ring, lane, s0, nstates, OUT, ldo);
   }
 }
 
 template <int MT, int MODE>
 inline size_t warptile_smem_bytes(int nin) {
-  return (MODE == MODE_QUAD ? 1 : 2) * (size_t)nin * 8 * MT * sizeof(double);
+  const size_t tile_doubles = ((MODE == MODE_QUAD ? 1 : 2) * (size_t)nin * 8 * MT + 1) & ~(size_t)1;
+  return tile_doubles * sizeof(double) + (size_t)kWarps * kPairRingBytes;
 }
 
 // X, Y: nstates x (nin-1) column-major with leading dimension ldx; OUT: nstates x m, ldo.

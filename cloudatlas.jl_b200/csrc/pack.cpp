@@ -382,7 +382,8 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
   {  // LPT schedule of whole tiles onto 8 warps (weight = DMMAs per state tile)
     std::vector<int32_t> idx(P.tiles.size());
     std::iota(idx.begin(), idx.end(), 0);
-    auto weight = [&](int32_t t) { return (int64_t)P.tiles[t].nks * P.tiles[t].nt + 1; };
+    // cycles of the FP64 pipe per k-step: 4 nt DMMAs x 16 plus the four pair products (tools/dmma_dmul_mix.cu)
+    auto weight = [&](int32_t t) { return (int64_t)P.tiles[t].nks * (P.tiles[t].nt == 2 ? 144 : 82) + 40; };
     std::stable_sort(idx.begin(), idx.end(), [&](int32_t x, int32_t y) { return weight(x) > weight(y); });
     int64_t load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<int32_t> bins[8];
@@ -407,6 +408,27 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
     }
     P.sched_off[8] = (int32_t)P.sched.size();
     P.sched_imbalance = total > 0 ? (double)worst * 8.0 / (double)total : 1e9;
+    if (window_modes <= 0) {  // physical re-layout in schedule order: one contiguous stream per warp and nt class
+      std::vector<uint32_t> np;
+      std::vector<double> nv;
+      np.reserve(P.pairs.size());
+      nv.reserve(P.vals.size());
+      for (int w = 0; w < 8; ++w) {
+        P.sched_ks2[w] = P.sched_ks1[w] = 0;
+        for (int q = P.sched_off[w]; q < P.sched_off[w + 1]; ++q) {
+          TileDesc& T = P.tiles[P.sched[q]];
+          const size_t p0 = (size_t)T.ks_begin * 4, v0 = (size_t)T.vals_off;
+          T.ks_begin = (int32_t)(np.size() / 4);
+          T.vals_off = (int64_t)nv.size();
+          np.insert(np.end(), P.pairs.begin() + p0, P.pairs.begin() + p0 + (size_t)T.nks * 4);
+          nv.insert(nv.end(), P.vals.begin() + v0, P.vals.begin() + v0 + (size_t)T.nks * T.nt * 32);
+          (T.nt == 2 ? P.sched_ks2[w] : P.sched_ks1[w]) += T.nks;
+        }
+      }
+      P.pairs.swap(np);
+      P.vals.swap(nv);
+      P.stream_layout = true;
+    }
   }
   return P;
 }

@@ -62,6 +62,10 @@ struct PackedHost {
   int32_t sched_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   int32_t sched_nt2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double sched_imbalance = 0.0;
+  // When the pack is not windowed the tiles of a warp are laid out contiguously in schedule order, so that a warp's
+  // pairs and values form one stream per nt class (sched_ks2 / sched_ks1 k-steps) that can be prefetched across tiles.
+  int32_t sched_ks2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sched_ks1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool stream_layout = false;
   int64_t nterms = 0;           // merged non-zero terms
   int64_t npairs_distinct = 0;  // distinct (a,b) over the whole operator
   int64_t padded_fma = 0;       // FMAs the tiles execute per state (incl. padding)
