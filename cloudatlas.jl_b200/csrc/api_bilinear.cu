@@ -325,6 +325,22 @@ extern "C" int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64
         fprintf(stderr, "r=%zu got (%d,%d,%d,%g) want (%d,%d,%d,%g) sizes %zu %zu\n", r, got[r].i, got[r].a, got[r].b, got[r].v, wm[r].i, wm[r].a, wm[r].b, wm[r].v, got.size(), wm.size()); }
     for (size_t r = 0; r < std::min(got.size(), wm.size()); ++r)
       bad += got[r].i != wm[r].i || got[r].a != wm[r].a || got[r].b != wm[r].b || got[r].v != wm[r].v;
+    {  // the warp schedule covers every tile exactly once, nt == 2 tiles first, and its stream lengths add up
+      std::vector<int> seen(P.tiles.size(), 0);
+      for (int w = 0; w < 8; ++w) {
+        int64_t ks2 = 0, ks1 = 0;
+        for (int q = P.sched_off[w]; q < P.sched_off[w + 1]; ++q) {
+          const int32_t t = P.sched[(size_t)q];
+          if (t < 0 || t >= (int32_t)P.tiles.size()) { ++bad; continue; }
+          seen[(size_t)t]++;
+          const bool first_part = q < P.sched_off[w] + P.sched_nt2[w];
+          bad += first_part != (P.tiles[(size_t)t].nt == 2);
+          (P.tiles[(size_t)t].nt == 2 ? ks2 : ks1) += P.tiles[(size_t)t].nks;
+        }
+        if (P.stream_layout) bad += ks2 != P.sched_ks2[w] || ks1 != P.sched_ks1[w];
+      }
+      for (int v : seen) bad += v != 1;
+    }
     if (ntiles) *ntiles = (int64_t)P.tiles.size();
     if (nterms) *nterms = P.nterms;
     if (padded_fma) *padded_fma = P.padded_fma;
