@@ -311,7 +311,7 @@ def dense_assembly_case(ca, H, world, rank, max_over_ranks, barrier, dmma_peak):
     the separable path gives the same tensor in ~25 ms, see `assembly`)."""
     ijkl = ca.basisIndices(5, 5, 16, H)
     m = ijkl.shape[0]
-    bounds = ca.row_partition(m, world)
+    bounds = ca.row_partition(m, world, 128)          # whole 128-row output tiles per rank
     barrier()
     t0 = time.perf_counter()
     slab = ca.AssemblySlab(ALPHA, GAMMA, ijkl, False, bounds[rank], bounds[rank + 1], dense=True, grid=(16, 33, 16))

@@ -23,12 +23,16 @@ _get_diss_dev = _sig("ca_assembly_get_dissipation_dev", vp, vp, vp)
 _get_coo_dev = _sig("ca_assembly_get_coo_dev", vp, vp, vp, vp, vp, vp)
 
 
-def row_partition(m: int, world: int):
-    """Contiguous ranges of output modes per rank: rank r owns [bounds[r], bounds[r+1])."""
-    base, extra = divmod(m, world)
+def row_partition(m: int, world: int, align: int = 1):
+    """Contiguous ranges of output modes per rank: rank r owns [bounds[r], bounds[r+1]).
+    ``align``: range boundaries fall on multiples of it (the dense path computes whole 128-row output tiles, so its
+    slabs should not cut a tile in two); trailing ranks may be empty."""
+    units = -(-m // align)
+    base, extra = divmod(units, world)
     bounds = [0]
     for r in range(world):
-        bounds.append(bounds[-1] + base + (1 if r < extra else 0))
+        bounds.append(min(m, bounds[-1] + (base + (1 if r < extra else 0)) * align))
+    bounds[-1] = m
     return bounds
 
 
@@ -160,7 +164,7 @@ def assemble(alpha, gamma, ijkl, normalize=False, group=None, distributed=None, 
                                      "D": slab.dissipation_host(), "dense": slab.dense_info() if dense else None}
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    bounds = row_partition(m, world)
+    bounds = row_partition(m, world, 128 if dense else 1)
     slab = AssemblySlab(alpha, gamma, ijkl, normalize, bounds[rank], bounds[rank + 1], dense=dense, grid=grid)
     lin, idx, val = slab.to_torch()
     lin, idx, val = all_gather_slabs(lin, idx, val, m, group)

@@ -60,3 +60,14 @@ def test_all_gather_slabs_gloo(world):
     L, I, V = np.concatenate(lins, axis=1), np.concatenate(idxs, axis=1), np.concatenate(vals)
     for _, l, i, v in results:
         assert np.array_equal(l, L) and np.array_equal(i, I) and np.array_equal(v, V)
+
+
+def test_row_partition_alignment():
+    import __graft_entry__ as g
+    ca = g.load_package()
+    for m, world, align in ((999, 8, 128), (999, 4, 128), (307, 8, 128), (44, 3, 1), (2962, 8, 128), (17, 8, 1)):
+        b = ca.row_partition(m, world, align)
+        assert len(b) == world + 1 and b[0] == 0 and b[-1] == m
+        assert all(x <= y for x, y in zip(b, b[1:]))
+        assert all(x % align == 0 or x == m for x in b)
+    assert ca.row_partition(999, 8, 128) == [0, 128, 256, 384, 512, 640, 768, 896, 999]
