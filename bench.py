@@ -281,7 +281,7 @@ def run_b200(args):
                    "layout": "nstates x m column-major (state index fastest)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * m * n, "d2h_bytes_per_step": 8 * m * n,
-                "steps": e2e_steps, "path": "ca_model_rhs_batched (host pointers, page-locked, chunked double buffering)",
+                "steps": e2e_steps, "path": "ca_model_rhs_batched (host pointers, page-locked, chunks of whole kernel waves on three streams)",
                 "agrees_with_device_path": e2e_check},
         "gpu_launches": int(launches),
         "roofline": roofline,

@@ -100,7 +100,7 @@ int32_t ca_bilinear_info(const ca_bilinear* h, int64_t* m, int64_t* nnz, int64_t
  * = N(x,x) (SparseBilinear.jl:70).  x, y, out: m doubles on the host. */
 int32_t ca_bilinear_eval(ca_bilinear* h, const double* x, const double* y, double* out);
 /* N(x_s) for every row s of X (additive entry point: the reference evaluates one state per call).
- * X, OUT: nstates x m column-major, host.  Chunked, copies overlapped with kernels. */
+ * X, OUT: nstates x m column-major, host.  Chunks of whole kernel waves on three streams: copies overlap kernels. */
 int32_t ca_bilinear_eval_batched(ca_bilinear* h, const double* X, int64_t nstates, double* OUT);
 /* same on device memory; ldx/ldo = leading dimensions (>= nstates) */
 int32_t ca_bilinear_eval_batched_dev(ca_bilinear* h, const double* dX, int64_t nstates, int64_t ldx,
@@ -246,7 +246,7 @@ typedef struct ca_solve_log {
  * hookstep() :21-74 -- as ONE persistent kernel: a single CTA keeps x, f(x), Df(x), Df'Df and the LU
  * workspaces in shared memory for the whole search (no launches, no host round trips inside the
  * loop).  Same decision tree, constants and exit flags as the reference.  m is limited by shared
- * memory (3 m^2 + 12 m doubles <= 227 KB, m <= 95); larger models return CA_ERR_UNSUPPORTED.
+ * memory (3 m^2 + 9 m doubles <= 227 KB, m <= 95); larger models return CA_ERR_UNSUPPORTED.
  * nsolve independent searches (own R, own guess; one CTA each) run in one launch:
  * R: nsolve, Xguess / X_out: nsolve x m column-major, success / logs: nsolve (logs may be NULL). */
 int32_t ca_hookstep_solve_model(ca_model* h, const double* R, const double* Xguess, int64_t nsolve,
