@@ -160,7 +160,7 @@ __device__ __forceinline__ void range_accumulate(const uint2* __restrict__ pairs
 }
 
 template <int MT, int NT>
-__device__ __forceinline__ void tile_reduce_store(const TileDesc& T, const int32_t* __restrict__ rows,
+__device__ __forceinline__ void tile_reduce_store(int rows_off, const int32_t* __restrict__ rows,
                                                   double* red, const double (&acc)[MT][NT][2],
                                                   int warp, int lane, int64_t s0, int64_t nstates,
                                                   double* __restrict__ OUT, int64_t ldo) {
@@ -178,7 +178,7 @@ __device__ __forceinline__ void tile_reduce_store(const TileDesc& T, const int32
   __syncthreads();
   for (int o = threadIdx.x; o < NT * 8 * ROW; o += kThreads) {
     const int n = o / ROW, s = o % ROW;
-    const int row = __ldg(rows + T.rows_off + n);
+    const int row = __ldg(rows + rows_off + n);
     double sum = 0.0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) sum += red[w * (kNtMax * 8 * ROW) + o];
@@ -209,7 +209,7 @@ __device__ __forceinline__ void run_tiles(const TileDesc* __restrict__ tiles, in
       T = tiles[t + 1];
       range_prologue<NT>(pairs + (size_t)T.ks_begin * 4, vals + T.vals_off, T.nks, warp, lane, pf);
     }
-    tile_reduce_store<MT, NT>(done, rows, red, acc, warp, lane, s0, nstates, OUT, ldo);
+    tile_reduce_store<MT, NT>(done.rows_off, rows, red, acc, warp, lane, s0, nstates, OUT, ldo);
   }
 }
 
@@ -446,117 +446,275 @@ bilinear_batched_kernel(const TileDesc* __restrict__ tiles, int ntiles, int nt2_
 // modes one WINDOW of k-steps touches (<= wmax, see pack.h), gathered with cp.async into a double
 // buffer while the previous window is being multiplied.  One barrier per window; accumulators live
 // across the windows of a tile.  Footprint: 2 x wmax x 256 B per vector, independent of m.
+//
+// Everything a window needs arrives through the same cp.async pipeline, so no warp ever waits on a
+// dependent L2 load: at the top of window g (right after its barrier) the CTA issues
+//   the state rows and the pair words of window g+1   (their descriptor and mode list are already in smem),
+//   the mode list of window g+2                       (its descriptor is already in smem),
+//   the descriptor of window g+3,
+// and the next barrier's cp.async.wait_all makes all of it visible.  Operator values stay in registers,
+// prefetched kPrefetch k-steps ahead with loads that are pinned in program order (volatile asm: the
+// compiler otherwise sinks them to the end of the unrolled body and exposes the L2 latency).
 constexpr int kWinMT = 4;
+constexpr int kDescRing = 4;
 
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, int src_bytes) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+constexpr int kValSlotBytes = 2048;               // one batch of operator values: 4 k-steps (nt = 2) or 8 (nt = 1)
+constexpr int kValRingBytes = 2 * kValSlotBytes;  // per warp
+
+struct WinSmem {
+  double* bufs;      // [2][bufstride] state rows of the current / next window; a finished tile's reduction reuses the current one
+  uint2* pairs;      // [2][kWindowMaxKs * 4] pair words of the current / next window
+  WindowDesc* desc;  // ring of kDescRing descriptors: windows g .. g+3
+  int32_t* modes;    // [2][wpad] mode lists of windows g+1 / g+2
+  char* vring;       // [kWarps][kValRingBytes] operator values, two batches per warp
+  int wmax, wpad;
+  size_t bufstride;  // doubles
+};
+
 template <int MODE>
-__device__ __forceinline__ void gather_window(const WindowDesc& W, const int32_t* __restrict__ modes,
-                                              double* xbuf, double* ybuf, const double* __restrict__ X,
-                                              const double* __restrict__ Y, int64_t s0, int64_t nstates,
-                                              int64_t ldx, int one_mode) {
+__host__ __device__ inline size_t window_buf_doubles(int wmax) {
+  const size_t row = 8 * kWinMT;
+  const size_t states = (size_t)(MODE == MODE_QUAD ? 1 : 2) * wmax * row;
+  const size_t red = (size_t)kWarps * kNtMax * 8 * row;
+  return states > red ? states : red;
+}
+
+template <int MODE>
+__host__ __device__ inline size_t windowed_smem_bytes(int wmax) {
+  const size_t wpad = ((size_t)wmax + 3) & ~(size_t)3;
+  return 2 * window_buf_doubles<MODE>(wmax) * sizeof(double) + (size_t)2 * kWindowMaxKs * 4 * sizeof(uint2) +
+         kDescRing * sizeof(WindowDesc) + 2 * wpad * sizeof(int32_t) + (size_t)kWarps * kValRingBytes;
+}
+
+template <int MODE>
+__device__ __forceinline__ WinSmem carve_window_smem(double* smem, int wmax) {
+  WinSmem S;
+  S.wmax = wmax;
+  S.wpad = (wmax + 3) & ~3;
+  S.bufstride = window_buf_doubles<MODE>(wmax);
+  S.bufs = smem;
+  S.pairs = reinterpret_cast<uint2*>(smem + 2 * S.bufstride);
+  S.desc = reinterpret_cast<WindowDesc*>(S.pairs + (size_t)2 * kWindowMaxKs * 4);
+  S.modes = reinterpret_cast<int32_t*>(S.desc + kDescRing);
+  S.vring = reinterpret_cast<char*>(S.modes + 2 * S.wpad);
+  return S;
+}
+
+// Issued by the whole CTA right after the barrier of window g (g == -1: block prologue).
+template <int MODE>
+__device__ __forceinline__ void stage_ahead(int g, int gtotal, const WindowDesc* __restrict__ windows,
+                                            const int32_t* __restrict__ modes, const uint2* __restrict__ pairs,
+                                            const WinSmem& S, int one_mode, const double* __restrict__ X,
+                                            const double* __restrict__ Y, int64_t s0, int64_t nstates, int64_t ldx) {
   constexpr int ROW = 8 * kWinMT;
-  for (int idx = threadIdx.x; idx < W.nmodes * ROW; idx += kThreads) {
-    const int l = idx / ROW, s = idx % ROW;
-    const int g = __ldg(modes + W.modes_off + l);
-    const int slot = l * ROW + (s ^ swz<kWinMT>(l));
-    if (g == one_mode) {
-      xbuf[slot] = 1.0;
-      if (MODE != MODE_QUAD) ybuf[slot] = MODE == MODE_JVP ? 0.0 : 1.0;
-    } else {
-      const bool ok = s0 + s < nstates;
-      const int64_t off = ok ? (s0 + s) + ldx * (int64_t)g : 0;
-      cp_async8(xbuf + slot, X + off, ok ? 8 : 0);
-      if (MODE != MODE_QUAD) cp_async8(ybuf + slot, Y + off, ok ? 8 : 0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (g + 1 < gtotal) {
+    const WindowDesc& W = S.desc[(g + 1) & (kDescRing - 1)];
+    const int nks = W.nks, nmodes = W.nmodes;
+    const char* psrc = reinterpret_cast<const char*>(pairs + (size_t)W.ks_begin * 4);
+    char* pdst = reinterpret_cast<char*>(S.pairs + (size_t)((g + 1) & 1) * kWindowMaxKs * 4);
+    for (int c = tid; c < nks * 2; c += kThreads) cp_async16(pdst + c * 16, psrc + c * 16);
+    // one state row (32 states = 256 B) per warp instruction; the lane is the state
+    const bool ok = s0 + lane < nstates;
+    const double* xg = X + (ok ? s0 + lane : 0);
+    const double* yg = MODE == MODE_QUAD ? nullptr : Y + (ok ? s0 + lane : 0);
+    const int32_t* md = S.modes + ((g + 1) & 1) * S.wpad;
+    double* xb = S.bufs + (size_t)((g + 1) & 1) * S.bufstride;
+    double* yb = xb + (size_t)S.wmax * ROW;
+#pragma unroll 4
+    for (int l = warp; l < nmodes; l += kWarps) {
+      const int gm = md[l];
+      const int slot = l * ROW + (lane ^ swz<kWinMT>(l));
+      if (gm == one_mode) {
+        xb[slot] = 1.0;
+        if (MODE != MODE_QUAD) yb[slot] = MODE == MODE_JVP ? 0.0 : 1.0;
+      } else {
+        const int64_t off = ldx * (int64_t)gm;
+        cp_async8(xb + slot, xg + off, ok ? 8 : 0);
+        if (MODE != MODE_QUAD) cp_async8(yb + slot, yg + off, ok ? 8 : 0);
+      }
     }
   }
+  if (g + 2 < gtotal) {
+    const WindowDesc& W2 = S.desc[(g + 2) & (kDescRing - 1)];
+    const int nmodes = W2.nmodes;
+    const int32_t* src = modes + W2.modes_off;
+    int32_t* md = S.modes + ((g + 2) & 1) * S.wpad;
+    for (int l = tid; l < nmodes; l += kThreads) cp_async4(md + l, src + l);
+  }
+  if (g + 3 < gtotal && tid < (int)(sizeof(WindowDesc) / 16))
+    cp_async16(reinterpret_cast<char*>(S.desc + ((g + 3) & (kDescRing - 1))) + tid * 16,
+               reinterpret_cast<const char*>(windows + g + 3) + tid * 16);
   cp_async_commit();
+}
+
+// Operator values of a warp's share of a window go through a two-slot ring in shared memory, one cp.async group per
+// batch: ptxas keeps LDGSTS / commit / wait in program order, whereas plain register prefetch loads (having no
+// consumer inside the unrolled body) get sunk to the end of the body, right in front of their use.
+template <int NT>
+struct ValRing {
+  static constexpr int KB = kValSlotBytes / (NT * 256);  // k-steps per batch
+  char* ring;       // this warp's kValRingBytes
+  const char* src;  // the share's first value
+  int n;            // k-steps in the share
+
+  __device__ __forceinline__ void issue(int b, int lane) const {
+    const int bytes = min(KB, n - b * KB) * (NT * 256);  // <= 0 past the end: an empty group keeps the count uniform
+    const char* s = src + (size_t)b * kValSlotBytes;
+    char* d = ring + (b & 1) * kValSlotBytes;
+#pragma unroll
+    for (int c = 0; c < kValSlotBytes / 512; ++c) {
+      const int o = c * 512 + lane * 16;
+      if (o < bytes) cp_async16(d + o, s + o);
+    }
+    cp_async_commit();
+  }
+  // batches 0 and 1 of this warp's share of a window; issued before the previous window's barrier
+  __device__ __forceinline__ void begin(const double* __restrict__ vals0, int nks, int warp, int lane) {
+    int k0, k1;
+    warp_share(nks, warp, k0, k1);
+    n = k1 - k0;
+    src = reinterpret_cast<const char*>(vals0 + (size_t)k0 * NT * 32);
+    __syncwarp();  // every lane is done reading the previous share's slots
+    issue(0, lane);
+    issue(1, lane);
+  }
+};
+
+// ps: the window's pair words in shared memory
+template <int MT, int NT, int MODE>
+__device__ __forceinline__ void window_accumulate(const uint2* ps, int nks, const double* xs, const double* ys,
+                                                  int warp, int lane, const ValRing<NT>& vr,
+                                                  double (&acc)[MT][NT][2]) {
+  constexpr int KB = ValRing<NT>::KB;
+  const uint32_t r8 = 8u * (lane >> 2);
+  int k0, k1;
+  warp_share(nks, warp, k0, k1);
+  const int n = k1 - k0;
+  if (n <= 0) return;
+  const uint2* pp = ps + (size_t)k0 * 4 + (lane & 3);
+  const char* vb = vr.ring + lane * 8;
+  const char* xsb = reinterpret_cast<const char*>(xs);
+  const char* ysb = reinterpret_cast<const char*>(ys);
+  double xa[MT], va[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) xa[mt] = va[mt] = 0.0;
+  auto step = [&](int k, const char* slot, int kk) {
+    uint2 pw = pp[(size_t)k * 4];
+    if (k == 0) pw.x &= ~kSameA;  // the first k-step of a share always loads its first factors
+    double bv[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) bv[nt] = *reinterpret_cast<const double*>(slot + (kk * NT + nt) * 256);
+    kstep<MT, NT, MODE>(pw, bv, xsb, ysb, r8, xa, va, acc);
+  };
+  const int nb = (n + KB - 1) / KB;
+  for (int b = 0; b < nb; ++b) {
+    if (b >= 2) {  // batches 0 and 1 landed before the window's barrier
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+      __syncwarp();
+    }
+    const char* slot = vb + (b & 1) * kValSlotBytes;
+    const int cnt = min(KB, n - b * KB);
+    if (cnt == KB) {
+#pragma unroll
+      for (int kk = 0; kk < KB; ++kk) step(b * KB + kk, slot, kk);
+    } else {
+      for (int kk = 0; kk < cnt; ++kk) step(b * KB + kk, slot, kk);
+    }
+    __syncwarp();  // the slot is refilled now
+    vr.issue(b + 2, lane);
+  }
 }
 
 // windows [gb, ge) all belong to tiles with NT n-tiles; gtotal = number of windows of the operator
 template <int NT, int MODE>
-__device__ __forceinline__ void run_windows(const TileDesc* __restrict__ tiles, const WindowDesc* __restrict__ windows,
-                                            int gb, int ge, int gtotal, const int32_t* __restrict__ modes,
-                                            const uint2* __restrict__ pairs, const double* __restrict__ vals,
-                                            const int32_t* __restrict__ rows, double* bufs, int wmax, int one_mode,
-                                            double* red, int warp, int lane, const double* __restrict__ X,
-                                            const double* __restrict__ Y, int64_t s0, int64_t nstates, int64_t ldx,
-                                            double* __restrict__ OUT, int64_t ldo) {
+__device__ __forceinline__ void run_windows(const WindowDesc* __restrict__ windows, int gb, int ge, int gtotal,
+                                            const int32_t* __restrict__ modes, const uint2* __restrict__ pairs,
+                                            const double* __restrict__ vals, const int32_t* __restrict__ rows,
+                                            const WinSmem& S, int one_mode, int warp, int lane,
+                                            const double* __restrict__ X, const double* __restrict__ Y, int64_t s0,
+                                            int64_t nstates, int64_t ldx, double* __restrict__ OUT, int64_t ldo) {
   constexpr int MT = kWinMT, ROW = 8 * MT;
-  constexpr int NVEC = MODE == MODE_QUAD ? 1 : 2;
   if (gb >= ge) return;
-  Prefetch<NT> pf;
+  ValRing<NT> vr;
+  vr.ring = S.vring + warp * kValRingBytes;
   double acc[MT][NT][2];
-  WindowDesc W = windows[gb];
-  TileDesc T = tiles[W.tile];
-  range_prologue<NT>(pairs + (size_t)W.ks_begin * 4, vals + T.vals_off + (size_t)(W.ks_begin - T.ks_begin) * NT * 32,
-                     W.nks, warp, lane, pf);
+  {
+    const WindowDesc& W0 = S.desc[gb & (kDescRing - 1)];
+    vr.begin(vals + W0.vals_off, W0.nks, warp, lane);
+  }
   bool fresh = true;
   for (int g = gb; g < ge; ++g) {
     cp_async_wait_all();
-    __syncthreads();  // window g has landed; everyone is done with window g-1, whose buffer is now free
-    if (g + 1 < gtotal) {
-      double* nb = bufs + (size_t)((g + 1) & 1) * NVEC * wmax * ROW;
-      gather_window<MODE>(windows[g + 1], modes, nb, nb + (size_t)wmax * ROW, X, Y, s0, nstates, ldx, one_mode);
-    }
+    __syncthreads();  // window g (+ mode list g+1, descriptor g+2) has landed; window g-1's buffers are free
+    stage_ahead<MODE>(g, gtotal, windows, modes, pairs, S, one_mode, X, Y, s0, nstates, ldx);
     if (fresh) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
     }
-    const double* xs = bufs + (size_t)(g & 1) * NVEC * wmax * ROW;
-    const double* ys = MODE == MODE_QUAD ? xs : xs + (size_t)wmax * ROW;
-    range_accumulate<MT, NT, MODE>(pairs + (size_t)W.ks_begin * 4,
-                                   vals + T.vals_off + (size_t)(W.ks_begin - T.ks_begin) * NT * 32, W.nks, xs, ys,
-                                   warp, lane, pf, acc);
+    const WindowDesc& W = S.desc[g & (kDescRing - 1)];
+    const int nks = W.nks, rows_off = W.rows_off;
     const bool last = W.last != 0;
-    const TileDesc done = T;
+    double* cur = S.bufs + (size_t)(g & 1) * S.bufstride;
+    const double* xs = cur;
+    const double* ys = MODE == MODE_QUAD ? xs : xs + (size_t)S.wmax * ROW;
+    window_accumulate<MT, NT, MODE>(S.pairs + (size_t)(g & 1) * kWindowMaxKs * 4, nks, xs, ys, warp, lane, vr, acc);
     if (g + 1 < ge) {
-      W = windows[g + 1];
-      T = tiles[W.tile];
-      range_prologue<NT>(pairs + (size_t)W.ks_begin * 4,
-                         vals + T.vals_off + (size_t)(W.ks_begin - T.ks_begin) * NT * 32, W.nks, warp, lane, pf);
+      const WindowDesc& Wn = S.desc[(g + 1) & (kDescRing - 1)];
+      vr.begin(vals + Wn.vals_off, Wn.nks, warp, lane);
     }
-    if (last) tile_reduce_store<MT, NT>(done, rows, red, acc, warp, lane, s0, nstates, OUT, ldo);
+    // the reduction buffer is the finished window's state buffer: its first barrier frees it, and the next
+    // window's barrier comes before anything is staged into it again
+    if (last) tile_reduce_store<MT, NT>(rows_off, rows, cur, acc, warp, lane, s0, nstates, OUT, ldo);
     fresh = last;
   }
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, MODE == MODE_QUAD ? 2 : 1)
-bilinear_windowed_kernel(const TileDesc* __restrict__ tiles, const WindowDesc* __restrict__ windows, int nwin,
-                         int nwin_nt2, const int32_t* __restrict__ modes, const uint2* __restrict__ pairs,
+bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, int nwin, int nwin_nt2,
+                         const int32_t* __restrict__ modes, const uint2* __restrict__ pairs,
                          const double* __restrict__ vals, const int32_t* __restrict__ rows, int wmax, int one_mode,
                          const double* __restrict__ X, const double* __restrict__ Y, int64_t nstates, int64_t ldx,
                          double* __restrict__ OUT, int64_t ldo) {
   constexpr int ROW = 8 * kWinMT;
-  constexpr int NVEC = MODE == MODE_QUAD ? 1 : 2;
   extern __shared__ __align__(16) double smem[];
-  double* bufs = smem;
-  double* red = smem + (size_t)2 * NVEC * wmax * ROW;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const WinSmem S = carve_window_smem<MODE>(smem, wmax);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t nblocks = (nstates + ROW - 1) / ROW;
+  if (nwin <= 0) return;
   for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
     const int64_t s0 = blk * ROW;
     __syncthreads();  // the previous block's last window and reduction are finished
-    if (nwin > 0) gather_window<MODE>(windows[0], modes, bufs, bufs + (size_t)wmax * ROW, X, Y, s0, nstates, ldx, one_mode);
-    run_windows<2, MODE>(tiles, windows, 0, nwin_nt2, nwin, modes, pairs, vals, rows, bufs, wmax, one_mode, red, warp,
-                         lane, X, Y, s0, nstates, ldx, OUT, ldo);
-    run_windows<1, MODE>(tiles, windows, nwin_nt2, nwin, nwin, modes, pairs, vals, rows, bufs, wmax, one_mode, red,
-                         warp, lane, X, Y, s0, nstates, ldx, OUT, ldo);
+    constexpr int kDescWords = sizeof(WindowDesc) / 4;
+    if (tid < 2 * kDescWords && tid / kDescWords < nwin)  // descriptors 0 and 1 directly
+      reinterpret_cast<uint32_t*>(S.desc)[tid] = __ldg(reinterpret_cast<const uint32_t*>(windows) + tid);
+    __syncthreads();
+    for (int l = tid; l < S.desc[0].nmodes; l += kThreads) S.modes[l] = __ldg(modes + S.desc[0].modes_off + l);
+    __syncthreads();
+    stage_ahead<MODE>(-1, nwin, windows, modes, pairs, S, one_mode, X, Y, s0, nstates, ldx);
+    run_windows<2, MODE>(windows, 0, nwin_nt2, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane, X, Y, s0,
+                         nstates, ldx, OUT, ldo);
+    run_windows<1, MODE>(windows, nwin_nt2, nwin, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane, X, Y, s0,
+                         nstates, ldx, OUT, ldo);
   }
-}
-
-template <int MODE>
-inline size_t windowed_smem_bytes(int wmax) {
-  const size_t row = 8 * kWinMT;
-  return ((size_t)2 * (MODE == MODE_QUAD ? 1 : 2) * wmax * row + (size_t)kWarps * kNtMax * 8 * row) * sizeof(double);
 }
 
 template <int MT, int MODE>

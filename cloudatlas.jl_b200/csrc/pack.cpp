@@ -296,6 +296,10 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
             close_window();
             u = add;
           }
+          if (wpairs.size() + (q1 - q) > (size_t)4 * kWindowMaxKs) {  // pair words of a window are staged in smem
+            close_window();
+            u = add;
+          }
           wmodes = std::move(u);
           for (size_t z = q; z < q1; ++z) wpairs.push_back(z);
           q = q1;
@@ -374,11 +378,25 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
       }
       for (WindowDesc W : ws) {
         W.tile = (int32_t)t;
+        W.rows_off = sorted[t].rows_off;
+        W.nt = sorted[t].nt;
+        W.vals_off = sorted[t].vals_off + (int64_t)(W.ks_begin - sorted[t].ks_begin) * sorted[t].nt * 32;
         P.windows.push_back(W);
       }
     }
   }
   P.tiles = std::move(sorted);
+  if (window_modes > 0 && getenv("CA_TIMING")) {
+    int64_t ks = 0, md = 0, small = 0;
+    for (const WindowDesc& W : P.windows) {
+      ks += W.nks;
+      md += W.nmodes;
+      small += W.nks < 64;
+    }
+    const double n = std::max<double>(1.0, (double)P.windows.size());
+    fprintf(stderr, "[ca timing] pack_terms: %zu tiles, %zu windows, %.1f k-steps and %.1f modes per window, %lld windows < 64 k-steps\n",
+            P.tiles.size(), P.windows.size(), ks / n, md / n, (long long)small);
+  }
   {  // LPT schedule of whole tiles onto 8 warps (weight = DMMAs per state tile)
     std::vector<int32_t> idx(P.tiles.size());
     std::iota(idx.begin(), idx.end(), 0);

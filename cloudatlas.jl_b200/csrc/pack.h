@@ -33,14 +33,20 @@ struct TileDesc {
 // modes; the windowed kernel gathers exactly those rows of the state tile into shared memory (double
 // buffered), so its footprint no longer grows with m.  Pair words of a windowed pack hold LOCAL row
 // indices into the window's mode list.
-struct WindowDesc {
+struct alignas(16) WindowDesc {
   int32_t ks_begin;   // first k-step (global index, as TileDesc::ks_begin)
-  int32_t nks;
+  int32_t nks;        // <= kWindowMaxKs
   int32_t modes_off;  // offset into PackedHost::modes
   int32_t nmodes;
   int32_t tile;       // owning tile
   int32_t last;       // 1 if this is the last window of its tile
+  int32_t rows_off;   // the owning tile's TileDesc::rows_off and nt, repeated here so that the kernel
+  int32_t nt;         // needs no dependent second descriptor load
+  int64_t vals_off;   // offset (doubles) of this window's first k-step in `vals`
+  int64_t pad_;
 };
+static_assert(sizeof(WindowDesc) == 48, "the windowed kernel copies descriptors as three 16-byte words");
+constexpr int kWindowMaxKs = 224;  // k-steps per window (the kernel stages a window's pair words in shared memory)
 
 struct PackedHost {
   int32_t m = 0;    // outputs
