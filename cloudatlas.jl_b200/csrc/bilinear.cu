@@ -174,11 +174,12 @@ void launch_windowed(const DevicePack& op, const double* dX, const double* dY, i
   const size_t smem = windowed_smem_bytes<MODE>(wmax);
   CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  constexpr int threads = WinCfg<MODE>::NW * 32;
+  CA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) fail(CA_ERR_UNSUPPORTED, "windowed kernel does not fit (smem %zu B)", smem);
   const int64_t nblocks = (nstates + 8 * kWinMT - 1) / (8 * kWinMT);
   const int grid = (int)std::min<int64_t>(nblocks, (int64_t)device_cfg().sms * per_sm);
-  kern<<<grid, kThreads, smem, stream>>>(op.windows.ptr, op.nwin, op.nwin_nt2, op.modes.ptr, op.pairs_for(kWinMT),
+  kern<<<grid, threads, smem, stream>>>(op.windows.ptr, op.nwin, op.nwin_nt2, op.modes.ptr, op.pairs_for(kWinMT),
                                          op.vals.ptr, op.rows.ptr, wmax, op.nin - 1, dX, dY, nstates, ldx, dOUT, ldo);
   CA_CUDA(cudaGetLastError());
   count_launch();

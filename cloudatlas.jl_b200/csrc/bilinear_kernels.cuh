@@ -65,14 +65,15 @@ __device__ __forceinline__ void prefetch_vals(double (&bv)[NT], const double* vp
 }
 
 // This warp's contiguous share [k0, k1) of a range of nks k-steps.
+template <int NW = kWarps>
 __device__ __forceinline__ void warp_share(int nks, int warp, int& k0, int& k1) {
   if (warp < 0) {  // the whole range belongs to the calling warp (whole-tile-per-warp schedule)
     k0 = 0;
     k1 = nks;
     return;
   }
-  k0 = (int)(((int64_t)nks * warp) / kWarps);
-  k1 = (int)(((int64_t)nks * (warp + 1)) / kWarps);
+  k0 = (int)(((int64_t)nks * warp) / NW);
+  k1 = (int)(((int64_t)nks * (warp + 1)) / NW);
 }
 
 // Loads the first k-steps of this warp's share of a k-step range (a whole tile, or one window of it);
@@ -159,7 +160,7 @@ __device__ __forceinline__ void range_accumulate(const uint2* __restrict__ pairs
   }
 }
 
-template <int MT, int NT>
+template <int MT, int NT, int NW = kWarps>
 __device__ __forceinline__ void tile_reduce_store(int rows_off, const int32_t* __restrict__ rows,
                                                   double* red, const double (&acc)[MT][NT][2],
                                                   int warp, int lane, int64_t s0, int64_t nstates,
@@ -176,12 +177,12 @@ __device__ __forceinline__ void tile_reduce_store(int rows_off, const int32_t* _
       mine[(nt * 8 + c * 2 + 1) * ROW + mt * 8 + r] = acc[mt][nt][1];
     }
   __syncthreads();
-  for (int o = threadIdx.x; o < NT * 8 * ROW; o += kThreads) {
+  for (int o = threadIdx.x; o < NT * 8 * ROW; o += NW * 32) {
     const int n = o / ROW, s = o % ROW;
     const int row = __ldg(rows + rows_off + n);
     double sum = 0.0;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) sum += red[w * (kNtMax * 8 * ROW) + o];
+    for (int w = 0; w < NW; ++w) sum += red[w * (kNtMax * 8 * ROW) + o];
     if (row >= 0 && s0 + s < nstates) OUT[(s0 + s) + ldo * (int64_t)row] = sum;
   }
 }
@@ -481,16 +482,24 @@ struct WinSmem {
   uint2* pairs;      // [2][kWindowMaxKs * 4] pair words of the current / next window
   WindowDesc* desc;  // ring of kDescRing descriptors: windows g .. g+3
   int32_t* modes;    // [2][wpad] mode lists of windows g+1 / g+2
-  char* vring;       // [kWarps][kValRingBytes] operator values, two batches per warp
+  char* vring;       // [NW][kValRingBytes] operator values, two batches per warp
   int wmax, wpad;
   size_t bufstride;  // doubles
+};
+
+// warps per CTA: two CTAs of 8 warps per SM for one-vector evaluation; the two-vector modes need twice the window
+// buffers, so one CTA of 16 warps shares them
+template <int MODE>
+struct WinCfg {
+  static constexpr int NW = MODE == MODE_QUAD ? 8 : 16;
+  static constexpr int CTAS = MODE == MODE_QUAD ? 2 : 1;
 };
 
 template <int MODE>
 __host__ __device__ inline size_t window_buf_doubles(int wmax) {
   const size_t row = 8 * kWinMT;
   const size_t states = (size_t)(MODE == MODE_QUAD ? 1 : 2) * wmax * row;
-  const size_t red = (size_t)kWarps * kNtMax * 8 * row;
+  const size_t red = (size_t)WinCfg<MODE>::NW * kNtMax * 8 * row;
   return states > red ? states : red;
 }
 
@@ -498,7 +507,7 @@ template <int MODE>
 __host__ __device__ inline size_t windowed_smem_bytes(int wmax) {
   const size_t wpad = ((size_t)wmax + 3) & ~(size_t)3;
   return 2 * window_buf_doubles<MODE>(wmax) * sizeof(double) + (size_t)2 * kWindowMaxKs * 4 * sizeof(uint2) +
-         kDescRing * sizeof(WindowDesc) + 2 * wpad * sizeof(int32_t) + (size_t)kWarps * kValRingBytes;
+         kDescRing * sizeof(WindowDesc) + 2 * wpad * sizeof(int32_t) + (size_t)WinCfg<MODE>::NW * kValRingBytes;
 }
 
 template <int MODE>
@@ -522,13 +531,14 @@ __device__ __forceinline__ void stage_ahead(int g, int gtotal, const WindowDesc*
                                             const WinSmem& S, int one_mode, const double* __restrict__ X,
                                             const double* __restrict__ Y, int64_t s0, int64_t nstates, int64_t ldx) {
   constexpr int ROW = 8 * kWinMT;
+  constexpr int NW = WinCfg<MODE>::NW, NTHR = NW * 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (g + 1 < gtotal) {
     const WindowDesc& W = S.desc[(g + 1) & (kDescRing - 1)];
     const int nks = W.nks, nmodes = W.nmodes;
     const char* psrc = reinterpret_cast<const char*>(pairs + (size_t)W.ks_begin * 4);
     char* pdst = reinterpret_cast<char*>(S.pairs + (size_t)((g + 1) & 1) * kWindowMaxKs * 4);
-    for (int c = tid; c < nks * 2; c += kThreads) cp_async16(pdst + c * 16, psrc + c * 16);
+    for (int c = tid; c < nks * 2; c += NTHR) cp_async16(pdst + c * 16, psrc + c * 16);
     // one state row (32 states = 256 B) per warp instruction; the lane is the state
     const bool ok = s0 + lane < nstates;
     const double* xg = X + (ok ? s0 + lane : 0);
@@ -537,7 +547,7 @@ __device__ __forceinline__ void stage_ahead(int g, int gtotal, const WindowDesc*
     double* xb = S.bufs + (size_t)((g + 1) & 1) * S.bufstride;
     double* yb = xb + (size_t)S.wmax * ROW;
 #pragma unroll 4
-    for (int l = warp; l < nmodes; l += kWarps) {
+    for (int l = warp; l < nmodes; l += NW) {
       const int gm = md[l];
       const int slot = l * ROW + (lane ^ swz<kWinMT>(l));
       if (gm == one_mode) {
@@ -555,7 +565,7 @@ __device__ __forceinline__ void stage_ahead(int g, int gtotal, const WindowDesc*
     const int nmodes = W2.nmodes;
     const int32_t* src = modes + W2.modes_off;
     int32_t* md = S.modes + ((g + 2) & 1) * S.wpad;
-    for (int l = tid; l < nmodes; l += kThreads) cp_async4(md + l, src + l);
+    for (int l = tid; l < nmodes; l += NTHR) cp_async4(md + l, src + l);
   }
   if (g + 3 < gtotal && tid < (int)(sizeof(WindowDesc) / 16))
     cp_async16(reinterpret_cast<char*>(S.desc + ((g + 3) & (kDescRing - 1))) + tid * 16,
@@ -566,7 +576,7 @@ __device__ __forceinline__ void stage_ahead(int g, int gtotal, const WindowDesc*
 // Operator values of a warp's share of a window go through a two-slot ring in shared memory, one cp.async group per
 // batch: ptxas keeps LDGSTS / commit / wait in program order, whereas plain register prefetch loads (having no
 // consumer inside the unrolled body) get sunk to the end of the body, right in front of their use.
-template <int NT>
+template <int NT, int NW>
 struct ValRing {
   static constexpr int KB = kValSlotBytes / (NT * 256);  // k-steps per batch
   char* ring;       // this warp's kValRingBytes
@@ -587,7 +597,7 @@ struct ValRing {
   // batches 0 and 1 of this warp's share of a window; issued before the previous window's barrier
   __device__ __forceinline__ void begin(const double* __restrict__ vals0, int nks, int warp, int lane) {
     int k0, k1;
-    warp_share(nks, warp, k0, k1);
+    warp_share<NW>(nks, warp, k0, k1);
     n = k1 - k0;
     src = reinterpret_cast<const char*>(vals0 + (size_t)k0 * NT * 32);
     __syncwarp();  // every lane is done reading the previous share's slots
@@ -599,12 +609,12 @@ struct ValRing {
 // ps: the window's pair words in shared memory
 template <int MT, int NT, int MODE>
 __device__ __forceinline__ void window_accumulate(const uint2* ps, int nks, const double* xs, const double* ys,
-                                                  int warp, int lane, const ValRing<NT>& vr,
+                                                  int warp, int lane, const ValRing<NT, WinCfg<MODE>::NW>& vr,
                                                   double (&acc)[MT][NT][2]) {
-  constexpr int KB = ValRing<NT>::KB;
+  constexpr int KB = ValRing<NT, WinCfg<MODE>::NW>::KB;
   const uint32_t r8 = 8u * (lane >> 2);
   int k0, k1;
-  warp_share(nks, warp, k0, k1);
+  warp_share<WinCfg<MODE>::NW>(nks, warp, k0, k1);
   const int n = k1 - k0;
   if (n <= 0) return;
   const uint2* pp = ps + (size_t)k0 * 4 + (lane & 3);
@@ -651,7 +661,7 @@ __device__ __forceinline__ void run_windows(const WindowDesc* __restrict__ windo
                                             int64_t nstates, int64_t ldx, double* __restrict__ OUT, int64_t ldo) {
   constexpr int MT = kWinMT, ROW = 8 * MT;
   if (gb >= ge) return;
-  ValRing<NT> vr;
+  ValRing<NT, WinCfg<MODE>::NW> vr;
   vr.ring = S.vring + warp * kValRingBytes;
   double acc[MT][NT][2];
   {
@@ -682,13 +692,13 @@ __device__ __forceinline__ void run_windows(const WindowDesc* __restrict__ windo
     }
     // the reduction buffer is the finished window's state buffer: its first barrier frees it, and the next
     // window's barrier comes before anything is staged into it again
-    if (last) tile_reduce_store<MT, NT>(rows_off, rows, cur, acc, warp, lane, s0, nstates, OUT, ldo);
+    if (last) tile_reduce_store<MT, NT, WinCfg<MODE>::NW>(rows_off, rows, cur, acc, warp, lane, s0, nstates, OUT, ldo);
     fresh = last;
   }
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, MODE == MODE_QUAD ? 2 : 1)
+__global__ void __launch_bounds__(WinCfg<MODE>::NW * 32, WinCfg<MODE>::CTAS)
 bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, int nwin, int nwin_nt2,
                          const int32_t* __restrict__ modes, const uint2* __restrict__ pairs,
                          const double* __restrict__ vals, const int32_t* __restrict__ rows, int wmax, int one_mode,
@@ -707,7 +717,7 @@ bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, int nwin, int n
     if (tid < 2 * kDescWords && tid / kDescWords < nwin)  // descriptors 0 and 1 directly
       reinterpret_cast<uint32_t*>(S.desc)[tid] = __ldg(reinterpret_cast<const uint32_t*>(windows) + tid);
     __syncthreads();
-    for (int l = tid; l < S.desc[0].nmodes; l += kThreads) S.modes[l] = __ldg(modes + S.desc[0].modes_off + l);
+    for (int l = tid; l < S.desc[0].nmodes; l += WinCfg<MODE>::NW * 32) S.modes[l] = __ldg(modes + S.desc[0].modes_off + l);
     __syncthreads();
     stage_ahead<MODE>(-1, nwin, windows, modes, pairs, S, one_mode, X, Y, s0, nstates, ldx);
     run_windows<2, MODE>(windows, 0, nwin_nt2, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane, X, Y, s0,

@@ -1,5 +1,5 @@
 """Small single-purpose runs for ncu captures of the secondary kernels.
-    python tools/profile_cases.py small17 | stream999 | windowed999"""
+    python tools/profile_cases.py small17 | stream999 | windowed999 | windowed999jvp"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -20,7 +20,12 @@ else:
 m = model.m
 X = (0.1 * torch.randn((m, n), dtype=torch.float64, device="cuda")).t()
 OUT = ca.ensemble_empty(n, m)
-for _ in range(4):
-    model.f(X, 200.0, out=OUT)
+if case == "windowed999jvp":
+    V = torch.randn((m, n), dtype=torch.float64, device="cuda").t()
+    for _ in range(4):
+        OUT = model.Df_action(X, V, 200.0)
+else:
+    for _ in range(4):
+        model.f(X, 200.0, out=OUT)
 torch.cuda.synchronize()
 print(case, model.kernel_path(n)[0], float(OUT.abs().max()))
