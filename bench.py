@@ -27,6 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+KERNEL_NAMES = {"dmma_row_tiles": "bilinear_warptile_kernel<4,0>", "dmma_row_tiles_ksplit": "bilinear_batched_kernel<4,0>",
+                "dmma_row_tiles_windowed": "bilinear_windowed_kernel<0>"}
 METRIC = "batched_rhs_evals_per_sec"
 UNIT = "evals/s"
 JKL = (3, 3, 12)
@@ -234,7 +236,7 @@ def run_b200(args):
                       torch.linalg.norm(OUT.t()[:, :1000]))
     del Xh, Oh, Xh_np, Oh_np
 
-    # ---- roofline of the dominant (only) kernel of the step: bilinear_batched_kernel<4, MODE_QUAD>
+    # ---- roofline of the dominant (only) kernel of the step: the DMMA ensemble kernel in MODE_QUAD
     ijk = model.ijk
     a, b = np.minimum(ijk[:, 1], ijk[:, 2]), np.maximum(ijk[:, 1], ijk[:, 2])
     key = (ijk[:, 0] * (m + 1) + a) * (m + 1) + b
@@ -263,7 +265,7 @@ def run_b200(args):
         "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
         "peak_source": "measured in this run (ca_measure_fp64_peak: DMMA loop); MEASURED_PEAKS.json has no FP64 entry",
         "dfma_peak": dfma_peak, "traffic": traffic,
-        "kernel": "bilinear_batched_kernel<4,0>", "kernel_ms": kernel_ms,
+        "kernel": KERNEL_NAMES.get(model.kernel_path(n)[0], model.kernel_path(n)[0]), "kernel_ms": kernel_ms,
         "algorithmic_flops_per_state": flops_state, "executed_fma_per_state": info["padded_fma_per_state"],
         "algorithmic_bytes_per_state": bytes_state,
         "hbm_view": {"achieved": bytes_state * n / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak,

@@ -159,6 +159,11 @@ int window_modes_for(int32_t m) {
   return batched_smem_bytes<4, MODE_JVP>(m + 1) <= (size_t)227 * 1024 ? 0 : kWindowModes;
 }
 
+int batched_variant(const DevicePack& op) {
+  if (op.window_modes > 0) return 4;
+  return op.stream_layout && op.sched_imbalance <= kMaxSchedImbalance && !getenv("CA_FORCE_KSPLIT") ? 0 : 3;
+}
+
 bool batched_fits(const DevicePack& op, int mode) {
   if (op.window_modes > 0) return true;  // windowed packs have an m-independent footprint
   const size_t cap = device_cfg().smem_optin;

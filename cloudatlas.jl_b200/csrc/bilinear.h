@@ -54,6 +54,8 @@ int window_modes_for(int32_t m);
 
 // true if the DMMA ensemble kernel can hold a state tile of this operator in shared memory
 bool batched_fits(const DevicePack& op, int mode);
+// which DMMA ensemble kernel launch_batched picks: 0 whole tiles per warp, 3 k-steps split across warps, 4 windowed
+int batched_variant(const DevicePack& op);
 constexpr int64_t kStreamMaxStates = 16;  // at or below this many states the streaming kernel is used
 
 // Row-chunked CSR for the few-state ("streaming") evaluation: the operator is read once from HBM per pass

@@ -1,5 +1,6 @@
 // Model-specialised ensemble kernel for small m (<= kJitMaxM): one thread per state, the state's
-// coefficients in registers, the operator baked into the instruction stream (NVRTC, sm_100a).
+// coefficients streamed through a per-thread cp.async ring into registers, the operator baked into the
+// instruction stream (NVRTC, sm_100a).
 //
 // For m = 17 the ensemble RHS is HBM-bound (272 B and ~1.3 kFLOP per state); the DMMA row-tile
 // kernel wastes most of its tensor work on padding at such sizes (fill 18 %), whereas straight-line code
@@ -27,6 +28,8 @@ struct SmallKernel {
   cudaKernel_t kern = nullptr;
   double* dLC = nullptr;       // device address of the module's __constant__ linear coefficients
   std::vector<int32_t> lin_i, lin_j;  // pattern of the linear part (row, column), order of LC
+  int threads = 0, stages = 0;  // CTA shape of the generated kernel (jit_small.cu: small_shape)
+  size_t smem_bytes = 0;
   double cur_invR = 0.0;
   bool lc_set = false;
   ~SmallKernel();

@@ -74,7 +74,8 @@ class ModelOperators:
         fn = _sig("ca_model_kernel_path", vp, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p))
         path, src, log = C.c_int32(), C.c_char_p(), C.c_char_p()
         check(fn(self._h, int(nstates), C.byref(path), C.byref(src), C.byref(log)))
-        names = {0: "dmma_row_tiles", 1: "csr_stream", 2: "nvrtc_straight_line"}
+        names = {0: "dmma_row_tiles", 1: "csr_stream", 2: "nvrtc_straight_line", 3: "dmma_row_tiles_ksplit",
+                 4: "dmma_row_tiles_windowed"}
         return names[path.value], (src.value or b"").decode(), (log.value or b"").decode()
 
     def f(self, x, R, out=None):

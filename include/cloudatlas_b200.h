@@ -130,8 +130,9 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
 int32_t ca_model_destroy(ca_model* h);
 int32_t ca_model_info(const ca_model* h, int64_t* m, int64_t* nnz_q_sym, int64_t* nnz_lin,
                       int64_t* npairs, int64_t* padded_fma_per_state, int64_t* nblocks_B);
-/* Which kernel serves an ensemble of nstates states: 0 = DMMA row tiles, 1 = few-state CSR stream,
- * 2 = model-specialised straight-line kernel (NVRTC, m <= 48).  *source / *log (may be NULL) receive
+/* Which kernel serves an ensemble of nstates states: 0 = DMMA row tiles, whole tiles per warp; 1 = few-state CSR
+ * stream; 2 = model-specialised straight-line kernel (NVRTC, m <= 48); 3 = DMMA row tiles, k-steps split across
+ * warps (unbalanced tile schedules); 4 = windowed DMMA row tiles (large m).  *source / *log (may be NULL) receive
  * pointers to the generated CUDA source and the NVRTC log of path 2, valid while the handle lives. */
 int32_t ca_model_kernel_path(ca_model* h, int64_t nstates, int32_t* path, const char** source, const char** log);
 /* f(x,R) = Bfact \ (A1*x + (1/R)*(A2*x) + N(x))  -- ODEModels.jl:57.  Host pointers, one state. */
