@@ -28,7 +28,7 @@ struct SmallKernel {
   cudaKernel_t kern = nullptr;
   double* dLC = nullptr;       // device address of the module's __constant__ linear coefficients
   std::vector<int32_t> lin_i, lin_j;  // pattern of the linear part (row, column), order of LC
-  int threads = 0, stages = 0;  // CTA shape of the generated kernel (jit_small.cu: small_shape)
+  int threads = 0, stages = 0, ctas_per_sm = 2;  // CTA shape of the generated kernel (jit_small.cu: small_shape)
   size_t smem_bytes = 0;
   double cur_invR = 0.0;
   bool lc_set = false;
