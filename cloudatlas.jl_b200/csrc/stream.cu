@@ -85,30 +85,57 @@ stream_kernel(const uint32_t* __restrict__ ab, const double* __restrict__ val,
   }
 }
 
-// out[s, row] = sum of the row's chunk partials (+ dense linear part: one warp per row)
+// Dense linear part (L1 + L2/R) v, one warp per (row, chunk of kLinCols columns): every row of L1r / L2r is read once,
+// coalesced, and applied to all nb states; partials go next to the quadratic chunk partials.
+constexpr int kLinCols = 512;
+
 template <int MODE>
 __global__ void __launch_bounds__(kStreamThreads)
-stream_combine_kernel(const double* __restrict__ partial, const int32_t* __restrict__ row_chunk_ptr, int m,
-                      int nb, const double* __restrict__ L1r, const double* __restrict__ L2r, double invR,
-                      const double* __restrict__ X, const double* __restrict__ Y, int64_t ldx,
-                      double* __restrict__ OUT, int64_t ldo) {
+stream_linear_kernel(const double* __restrict__ L1r, const double* __restrict__ L2r, double invR, int m, int nb,
+                     int nlc, const double* __restrict__ X, const double* __restrict__ Y, int64_t ldx,
+                     double* __restrict__ lin_partial) {
   const int lane = threadIdx.x & 31;
-  const int row = (int)(((int64_t)blockIdx.x * kStreamThreads + threadIdx.x) >> 5);
-  if (row >= m) return;
-  for (int s = 0; s < nb; ++s) {
-    double acc = 0.0;
-    if (L1r) {  // (L1 + L2/R) x ; for the Jacobian action the linear part acts on the direction
-      const double* V = MODE == MODE_JVP ? Y : X;
-      for (int j = lane; j < m; j += 32)
-        acc = fma(fma(L2r[(size_t)row * m + j], invR, L1r[(size_t)row * m + j]), V[s + ldx * (int64_t)j], acc);
+  const int64_t w = ((int64_t)blockIdx.x * kStreamThreads + threadIdx.x) >> 5;
+  if (w >= (int64_t)m * nlc) return;
+  const int row = (int)(w / nlc), j0 = (int)(w % nlc) * kLinCols, j1 = min(m, j0 + kLinCols);
+  const double* V = MODE == MODE_JVP ? Y : X;  // for the Jacobian action the linear part acts on the direction
+  const double* l1 = L1r + (size_t)row * m;
+  const double* l2 = L2r + (size_t)row * m;
+  double acc[8];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    }
-    if (lane == 0) {
-      for (int c = row_chunk_ptr[row]; c < row_chunk_ptr[row + 1]; ++c) acc += partial[(int64_t)c * 8 + s];
-      OUT[s + ldo * (int64_t)row] = acc;
-    }
+  for (int s = 0; s < 8; ++s) acc[s] = 0.0;
+#pragma unroll 4
+  for (int j = j0 + lane; j < j1; j += 32) {
+    const double l = fma(__ldg(l2 + j), invR, __ldg(l1 + j));
+    const double* v = V + ldx * (int64_t)j;
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      if (s < nb) acc[s] = fma(l, v[s], acc[s]);
   }
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < 8; ++s) lin_partial[w * 8 + s] = acc[s];
+  }
+}
+
+// out[s, row] = sum of the row's chunk partials (+ the partials of the dense linear part), in fixed order
+__global__ void __launch_bounds__(kStreamThreads)
+stream_combine_kernel(const double* __restrict__ partial, const int32_t* __restrict__ row_chunk_ptr, int m,
+                      int nb, const double* __restrict__ lin_partial, int nlc, double* __restrict__ OUT,
+                      int64_t ldo) {
+  const int64_t t = (int64_t)blockIdx.x * kStreamThreads + threadIdx.x;
+  const int row = (int)(t >> 3), s = (int)(t & 7);
+  if (row >= m || s >= nb) return;
+  double acc = 0.0;
+  if (lin_partial)
+    for (int c = 0; c < nlc; ++c) acc += lin_partial[((int64_t)row * nlc + c) * 8 + s];
+  for (int c = row_chunk_ptr[row]; c < row_chunk_ptr[row + 1]; ++c) acc += partial[(int64_t)c * 8 + s];
+  OUT[s + ldo * (int64_t)row] = acc;
 }
 
 template <int NB, int MODE>
@@ -126,15 +153,25 @@ void launch_nb(const StreamPack& sp, const double* dX, const double* dY, int nb,
   double* partial = sp.partial_for(st);
   if (sp.nchunks > 0) {
     const int64_t want = (sp.nchunks + kStreamThreads / 32 - 1) / (kStreamThreads / 32);
+    if (const char* e = getenv("CA_STREAM_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));  // tuning hook
     const int grid = (int)std::min<int64_t>(want, (int64_t)sms * per_sm);
     kern<<<grid, kStreamThreads, smem, st>>>(sp.ab.ptr, sp.val.ptr, sp.chunks.ptr, sp.nchunks, sp.nin, dX, dY,
                                              ldx, nb, partial);
     CA_CUDA(cudaGetLastError());
     count_launch();
   }
-  const int grid2 = (sp.m * 32 + kStreamThreads - 1) / kStreamThreads;
-  stream_combine_kernel<MODE><<<grid2, kStreamThreads, 0, st>>>(partial, sp.row_chunk_ptr.ptr, sp.m, nb,
-                                                               L1r, L2r, invR, dX, dY, ldx, dOUT, ldo);
+  const int nlc = (sp.m + kLinCols - 1) / kLinCols;
+  double* lin_partial = L1r ? partial + (size_t)std::max<int64_t>(sp.nchunks, 1) * 8 : nullptr;
+  if (L1r) {
+    const int64_t warps = (int64_t)sp.m * nlc;
+    const int gridl = (int)((warps * 32 + kStreamThreads - 1) / kStreamThreads);
+    stream_linear_kernel<MODE><<<gridl, kStreamThreads, 0, st>>>(L1r, L2r, invR, sp.m, nb, nlc, dX, dY, ldx, lin_partial);
+    CA_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  const int grid2 = (sp.m * 8 + kStreamThreads - 1) / kStreamThreads;
+  stream_combine_kernel<<<grid2, kStreamThreads, 0, st>>>(partial, sp.row_chunk_ptr.ptr, sp.m, nb, lin_partial, nlc,
+                                                          dOUT, ldo);
   CA_CUDA(cudaGetLastError());
   count_launch();
 }
@@ -223,7 +260,8 @@ double* StreamPack::partial_for(cudaStream_t st) const {
   auto& slot = partials[st];
   if (!slot) {
     slot.reset(new DeviceBuffer<double>);
-    slot->alloc((size_t)std::max<int64_t>(nchunks, 1) * 8);
+    // chunk partials, then the partials of the dense linear part (stream_linear_kernel)
+    slot->alloc(((size_t)std::max<int64_t>(nchunks, 1) + (size_t)m * ((m + 511) / 512)) * 8);
   }
   return slot->ptr;
 }
