@@ -126,32 +126,52 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
   tm.lap("sort");
   std::vector<Row> rows(m);
   {
-    size_t r = 0;
-    while (r < terms.size()) {
-      size_t e = r;
-      double s = 0;
-      while (e < terms.size() && terms[e].i == terms[r].i && terms[e].a == terms[r].a &&
-             terms[e].b == terms[r].b)
-        s += terms[e++].v;
-      if (s != 0.0) {
-        rows[terms[r].i].keys.push_back((uint64_t)terms[r].a * nin + terms[r].b);
-        rows[terms[r].i].vals.push_back(s);
-        ++P.nterms;
+    // terms are sorted by (i, a, b): rows are contiguous ranges, built (merge duplicates, min-hash sketch) on
+    // worker threads
+    std::vector<size_t> start((size_t)m + 1, 0);
+    for (const Term& t : terms) start[(size_t)t.i + 1]++;
+    for (int32_t i = 0; i < m; ++i) start[(size_t)i + 1] += start[i];
+    std::vector<int64_t> kept(m, 0);
+    std::atomic<int32_t> next{0};
+    auto work = [&]() {
+      for (int32_t i = next.fetch_add(1); i < m; i = next.fetch_add(1)) {
+        Row& rw = rows[i];
+        size_t r = start[i];
+        const size_t end = start[(size_t)i + 1];
+        rw.keys.reserve(end - r);
+        rw.vals.reserve(end - r);
+        while (r < end) {
+          size_t e = r;
+          double sum = 0;
+          while (e < end && terms[e].a == terms[r].a && terms[e].b == terms[r].b) sum += terms[e++].v;
+          if (sum != 0.0) {
+            rw.keys.push_back((uint64_t)terms[r].a * nin + terms[r].b);
+            rw.vals.push_back(sum);
+          }
+          r = e;
+        }
+        kept[i] = (int64_t)rw.keys.size();
+        for (int h = 0; h < kSketch; ++h) {
+          uint64_t best = ~0ull;
+          for (uint64_t k : rw.keys) best = std::min(best, mix64(k * 0x100000001b3ull + h * 0x51ed27ull));
+          rw.sketch[h] = best;
+        }
       }
-      r = e;
-    }
+    };
+    const unsigned nthreads = terms.size() < ((size_t)1 << 16) ? 1u : ca::worker_threads();
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    for (int32_t i = 0; i < m; ++i) P.nterms += kept[i];
   }
-  {
-    std::unordered_set<uint64_t> all;
-    for (auto& rw : rows) all.insert(rw.keys.begin(), rw.keys.end());
-    P.npairs_distinct = (int64_t)all.size();
-  }
-  for (auto& rw : rows) {
-    for (int h = 0; h < kSketch; ++h) {
-      uint64_t best = ~0ull;
-      for (uint64_t k : rw.keys) best = std::min(best, mix64(k * 0x100000001b3ull + h * 0x51ed27ull));
-      rw.sketch[h] = best;
-    }
+  {  // distinct (a, b) over the whole operator: one bit per possible pair
+    std::vector<uint64_t> seen(((size_t)nin * nin + 63) / 64, 0);
+    for (auto& rw : rows)
+      for (uint64_t k : rw.keys) seen[k >> 6] |= 1ull << (k & 63);
+    int64_t n = 0;
+    for (uint64_t w : seen) n += __builtin_popcountll(w);
+    P.npairs_distinct = n;
   }
 
   tm.lap("rows+sketches");

@@ -143,6 +143,31 @@ def test_m307_ensemble(ca, nagata_H):
     assert relerr(N.derivative(x), ref.derivative(x)) < TOL
 
 
+def test_windowed_kernel_full_size_windows_m307(ca, nagata_H, monkeypatch):
+    """Windows of the production size (128 modes) on the 307-mode operator: long windows are cut at the k-step cap of
+    the shared-memory pair staging, tiles span several windows, the ensemble is ragged (not a multiple of 32)."""
+    import torch
+    from oracle.bilinear import SparseBilinear as Ref, eval_batched
+    ijk, val, m = model_coo((3, 3, 12), nagata_H)
+    ref = Ref(ijk, val, m)
+    whole = ca.SparseBilinear(ijk, val, m)
+    rng = np.random.default_rng(8)
+    X = 0.1 * rng.standard_normal((2087, m))
+    V = rng.standard_normal((2087, m))
+    want_whole = whole(X)                                   # whole-tile kernel, same operator
+    monkeypatch.setenv("CA_FORCE_WINDOW_MODES", "128")
+    N = ca.SparseBilinear(ijk, val, m)
+    got = N(X)
+    idx = np.arange(0, 2087, 97)
+    assert relerr(got[idx], eval_batched(ref, X[idx])) < TOL
+    assert relerr(got, want_whole) < TOL
+    dX = torch.from_numpy(X.T.copy()).cuda().t()
+    dV = torch.from_numpy(V.T.copy()).cuda().t()
+    sub = [0, 31, 32, 1055, 2080, 2086]
+    assert relerr(N.jvp(dX, dV).cpu().numpy()[sub], np.stack([ref.derivative(X[s]) @ V[s] for s in sub])) < TOL
+    assert relerr(N(dX, dV).cpu().numpy()[sub], np.stack([ref(X[s], V[s]) for s in sub])) < TOL
+
+
 @pytest.mark.parametrize("wm", [8, 24, 96])
 def test_windowed_kernel_forced_at_small_m(ca, nagata_H, wm, monkeypatch):
     """The large-m (windowed, cp.async double-buffered) kernel, forced onto small operators."""
