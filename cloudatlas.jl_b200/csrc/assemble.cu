@@ -498,9 +498,29 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
     const int64_t ny3 = (int64_t)T.npid * T.npid * T.npid;
     dY3.alloc((size_t)ny3);
 
-    cudaEvent_t e0, e1;
+    // Device time = the kernels of the two passes (tables + count + scan, then fill).  Buffers whose size is known are
+    // allocated before the first event and the output arrays between the two timed spans: cudaMalloc is synchronous
+    // and its cost varies by milliseconds from call to call.
+    const int64_t nij_pre = (int64_t)rows * m;
+    DeviceBuffer<int64_t> counts, offs;
+    DeviceBuffer<char> tmp;
+    size_t tmp_bytes = 0;
+    if (nij_pre > 0) {
+      h->B.alloc((size_t)nij_pre);
+      h->A1.alloc((size_t)nij_pre);
+      h->A2.alloc((size_t)nij_pre);
+      h->D.alloc((size_t)nij_pre);
+      counts.alloc((size_t)nij_pre + 1);
+      offs.alloc((size_t)nij_pre + 1);
+      CA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.ptr, offs.ptr, (int)(nij_pre + 1)));
+      tmp.alloc(tmp_bytes);
+    }
+    cudaEvent_t e0, e1, e2, e3;
     CA_CUDA(cudaEventCreate(&e0));
     CA_CUDA(cudaEventCreate(&e1));
+    CA_CUDA(cudaEventCreate(&e2));
+    CA_CUDA(cudaEventCreate(&e3));
+    bool fill_timed = false;
     CA_CUDA(cudaEventRecord(e0));
     y3_kernel<<<(unsigned)((ny3 + 255) / 256), 256>>>(dF.ptr, dFlo.ptr, dw.ptr, dwlo.ptr, dpar.ptr, T.npid, T.ny, dY3.ptr);
     CA_CUDA(cudaGetLastError());
@@ -510,17 +530,10 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
                dX2.ptr, dZ2.ptr, dX3.ptr, dZ3.ptr, dY2.ptr, dY2y.ptr, dY3.ptr};
     const int64_t nij = (int64_t)rows * m;
     if (nij > 0) {
-      h->B.alloc((size_t)nij);
-      h->A1.alloc((size_t)nij);
-      h->A2.alloc((size_t)nij);
-      h->D.alloc((size_t)nij);
       linear_kernel<<<(unsigned)((nij + 255) / 256), 256>>>(b, r0, r1, h->B.ptr, h->A1.ptr, h->A2.ptr, h->D.ptr);
       CA_CUDA(cudaGetLastError());
       count_launch();
 
-      DeviceBuffer<int64_t> counts, offs;
-      counts.alloc((size_t)nij + 1);
-      offs.alloc((size_t)nij + 1);
       CA_CUDA(cudaMemsetAsync(counts.ptr, 0, ((size_t)nij + 1) * sizeof(int64_t)));
       int sms = 0;
       CA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
@@ -606,12 +619,9 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
       }
       CA_CUDA(cudaGetLastError());
       count_launch();
-      size_t tmp_bytes = 0;
-      CA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.ptr, offs.ptr, (int)(nij + 1)));
-      DeviceBuffer<char> tmp;
-      tmp.alloc(tmp_bytes);
       CA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.ptr, tmp_bytes, counts.ptr, offs.ptr, (int)(nij + 1)));
       count_launch();
+      CA_CUDA(cudaEventRecord(e1));
       int64_t nnz = 0;
       CA_CUDA(cudaMemcpy(&nnz, offs.ptr + nij, sizeof(int64_t), cudaMemcpyDeviceToHost));
       h->nnz = nnz;
@@ -620,21 +630,28 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
         h->oj.alloc((size_t)nnz);
         h->ok.alloc((size_t)nnz);
         h->oval.alloc((size_t)nnz);
+        CA_CUDA(cudaEventRecord(e2));
         if (dopt.dense)
           dense_compact_kernel<true><<<grid, 256>>>(Nd.ptr, m, r0, r1, thr, nullptr, offs.ptr, h->oi.ptr, h->oj.ptr, h->ok.ptr, h->oval.ptr);
         else
           n_kernel<true><<<grid, 256>>>(b, r0, r1, nullptr, offs.ptr, h->oi.ptr, h->oj.ptr, h->ok.ptr, h->oval.ptr);
         CA_CUDA(cudaGetLastError());
         count_launch();
+        CA_CUDA(cudaEventRecord(e3));
+        fill_timed = true;
       }
+    } else {
+      CA_CUDA(cudaEventRecord(e1));
     }
-    CA_CUDA(cudaEventRecord(e1));
-    CA_CUDA(cudaEventSynchronize(e1));
-    float ms = 0;
+    CA_CUDA(cudaDeviceSynchronize());
+    float ms = 0, ms2 = 0;
     CA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    h->seconds = ms * 1e-3;
+    if (fill_timed) CA_CUDA(cudaEventElapsedTime(&ms2, e2, e3));
+    h->seconds = (ms + ms2) * 1e-3;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    cudaEventDestroy(e3);
     *out = h.release();
   });
 }
