@@ -309,7 +309,13 @@ extern "C" int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64
         int ks = P.tiles[ti].ks_begin;
         bool last_seen = false;
         for (; w < P.windows.size() && P.windows[w].tile == (int32_t)ti; ++w) {
-          bad += P.windows[w].ks_begin != ks || P.windows[w].nmodes > window_modes || last_seen;
+          const WindowDesc& W = P.windows[w];
+          const TileDesc& T = P.tiles[ti];
+          bad += W.ks_begin != ks || W.nmodes > window_modes || last_seen;
+          // what the kernel stages per window: at most kWindowMaxKs k-steps of pair words, and the tile's value /
+          // row offsets repeated in the descriptor
+          bad += W.nks > kWindowMaxKs || W.nt != T.nt || W.rows_off != T.rows_off ||
+                 W.vals_off != T.vals_off + (int64_t)(W.ks_begin - T.ks_begin) * T.nt * 32;
           ks += P.windows[w].nks;
           last_seen = P.windows[w].last != 0;
         }

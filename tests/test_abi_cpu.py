@@ -96,3 +96,8 @@ def test_pack_fill_at_307(nagata_H):
     sw = pack_stats(ijk, val, 307, 1, 96)
     assert sw["mismatches"] == 0 and sw["max_window_modes"] <= 96
     assert sw["padded_fma"] < 1.05 * st["padded_fma"]
+    # production window size: long windows are cut at the k-step cap of the kernel's pair staging (checked inside
+    # the self test together with the per-window value / row offsets)
+    s128 = pack_stats(ijk, val, 307, 1, 128)
+    assert s128["mismatches"] == 0 and s128["max_window_modes"] <= 128
+    assert s128["nwindows"] > sw["ntiles"] and s128["padded_fma"] < 1.05 * st["padded_fma"]
