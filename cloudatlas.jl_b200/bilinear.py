@@ -17,6 +17,8 @@ _eval2_b_dev = _sig("ca_bilinear_eval2_batched_dev", vp, vp, vp, C.c_int64, C.c_
 _jvp_b_dev = _sig("ca_bilinear_jvp_batched_dev", vp, vp, vp, C.c_int64, C.c_int64, vp, C.c_int64, vp)
 _jac = _sig("ca_bilinear_jacobian", vp, c_f64p, c_f64p)
 _jac_dev = _sig("ca_bilinear_jacobian_dev", vp, vp, vp, vp)
+_jac_b = _sig("ca_bilinear_jacobian_batched", vp, c_f64p, C.c_int64, c_f64p)
+_jac_b_dev = _sig("ca_bilinear_jacobian_batched_dev", vp, vp, C.c_int64, C.c_int64, vp, C.c_int64, vp)
 
 
 def _f64(a):
@@ -41,6 +43,17 @@ def _colmajor_ensemble(X):
         raise CloudAtlasError(1, "ensemble must be nstates x m with unit stride along states "
                                  "(column-major, as a Julia Matrix); use ensemble_empty() or X.t().contiguous().t()")
     return X, X.shape[0], max(X.stride(1), X.shape[0])
+
+
+def jacobian_ensemble(X, m, call):
+    """Shared device path of the batched dense Jacobians: (nstates, m, m) CUDA tensor with strides (1, n, n*m)."""
+    import torch
+    X, n, ld = _colmajor_ensemble(X)
+    if X.shape[1] != m:
+        raise CloudAtlasError(1, f"ensemble has {X.shape[1]} columns, expected {m}")
+    D = torch.empty((m, m, n), dtype=torch.float64, device=X.device).permute(2, 1, 0)
+    check(call(vp(X.data_ptr()), n, ld, vp(D.data_ptr())))
+    return D
 
 
 def ensemble_empty(nstates, m, device="cuda"):
@@ -146,7 +159,17 @@ class SparseBilinear:
         return OUT
 
     def derivative(self, x):
-        """derivative(N, x): dense m x m  (SparseBilinear.jl:75-91)."""
+        """derivative(N, x): dense m x m  (SparseBilinear.jl:75-91).  A 2-d ``x`` (nstates x m) is an ensemble: the
+        result is nstates x m x m with the state index fastest in memory (a Julia ``Array{Float64,3}``)."""
+        if _is_torch(x) and x.dim() == 2:
+            return jacobian_ensemble(x, self.m, lambda X, n, ld, D: _jac_b_dev(self._h, X, n, ld, D, n, _stream()))
+        if not _is_torch(x) and np.ndim(x) == 2:
+            X = np.asfortranarray(np.asarray(x, dtype=np.float64))
+            if X.shape[1] != self.m:
+                raise CloudAtlasError(1, f"ensemble has {X.shape[1]} columns, expected {self.m}")
+            DN = np.empty((X.shape[0], self.m, self.m), order="F")
+            check(_jac_b(self._h, _f64(X), X.shape[0], _f64(DN)))
+            return DN
         if _is_torch(x):
             import torch
             DN = torch.empty((self.m, self.m), dtype=torch.float64, device=x.device).t()  # column-major

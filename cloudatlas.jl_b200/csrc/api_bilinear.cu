@@ -226,6 +226,29 @@ int32_t ca_bilinear_jacobian_dev(ca_bilinear* h, const double* dx, double* dDN, 
   });
 }
 
+int32_t ca_bilinear_jacobian_batched_dev(ca_bilinear* h, const double* dX, int64_t nstates, int64_t ldx, double* dDN,
+                                         int64_t ldo, void* stream) {
+  return guarded([&] {
+    if (!h || (nstates > 0 && (!dX || !dDN))) fail(CA_ERR_INVALID, "null argument");
+    h->bind();
+    launch_jacobian_batched(h->jacobian(), dX, nstates, ldx, nullptr, nullptr, 0.0, dDN, ldo, (cudaStream_t)stream);
+  });
+}
+
+int32_t ca_bilinear_jacobian_batched(ca_bilinear* h, const double* X, int64_t nstates, double* DN) {
+  return guarded([&] {
+    if (!h || (nstates > 0 && (!X || !DN))) fail(CA_ERR_INVALID, "null argument");
+    if (nstates <= 0) return;
+    h->bind();
+    const size_t m = (size_t)h->m, n = (size_t)nstates;
+    DeviceBuffer<double> dX, dD;
+    dX.upload(X, n * m);
+    dD.alloc(n * m * m);
+    launch_jacobian_batched(h->jacobian(), dX.ptr, nstates, nstates, nullptr, nullptr, 0.0, dD.ptr, nstates, nullptr);
+    CA_CUDA(cudaMemcpy(DN, dD.ptr, n * m * m * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
 int32_t ca_bilinear_jacobian(ca_bilinear* h, const double* x, double* DN) {
   return guarded([&] {
     if (!h || !x || !DN) fail(CA_ERR_INVALID, "null argument");

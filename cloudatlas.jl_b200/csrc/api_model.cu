@@ -412,6 +412,31 @@ int32_t ca_model_jac_dev(ca_model* h, const double* dx, double R, double* dDf, v
   });
 }
 
+int32_t ca_model_jac_batched_dev(ca_model* h, const double* dX, int64_t nstates, int64_t ldx, double R, double* dDf,
+                                 int64_t ldo, void* stream) {
+  return guarded([&] {
+    if (!h || (nstates > 0 && (!dX || !dDf))) fail(CA_ERR_INVALID, "null argument");
+    if (!(R != 0.0)) fail(CA_ERR_INVALID, "R must be non-zero");
+    h->bind();
+    launch_jacobian_batched(h->jacobian(), dX, nstates, ldx, h->L1.ptr, h->L2.ptr, 1.0 / R, dDf, ldo, (cudaStream_t)stream);
+  });
+}
+
+int32_t ca_model_jac_batched(ca_model* h, const double* X, int64_t nstates, double R, double* Df) {
+  return guarded([&] {
+    if (!h || (nstates > 0 && (!X || !Df))) fail(CA_ERR_INVALID, "null argument");
+    if (!(R != 0.0)) fail(CA_ERR_INVALID, "R must be non-zero");
+    if (nstates <= 0) return;
+    h->bind();
+    const size_t m = (size_t)h->m, n = (size_t)nstates;
+    DeviceBuffer<double> dX, dD;
+    dX.upload(X, n * m);
+    dD.alloc(n * m * m);
+    launch_jacobian_batched(h->jacobian(), dX.ptr, nstates, nstates, h->L1.ptr, h->L2.ptr, 1.0 / R, dD.ptr, nstates, nullptr);
+    CA_CUDA(cudaMemcpy(Df, dD.ptr, n * m * m * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
 int32_t ca_model_jac(ca_model* h, const double* x, double R, double* Df) {
   return guarded([&] {
     if (!h || !x || !Df) fail(CA_ERR_INVALID, "null argument");

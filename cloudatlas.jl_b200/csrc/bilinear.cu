@@ -303,11 +303,83 @@ void JacobianPack::build(const std::vector<Term>& coo, int32_t m_) {
         hval[at] = mg[r].v;
       }
     }
+  std::vector<int32_t> eo((size_t)m * m, -1);
+  for (size_t e = 0; e < pos.size(); ++e)
+    if (pos[e] >= 0) eo[(size_t)pos[e]] = (int32_t)e;
+  entry_of.upload(eo.data(), eo.size());
   slice_off.upload(soff.data(), soff.size());
   out_pos.upload(pos.data(), pos.size());
   src.upload(hsrc.data(), hsrc.size());
   val.upload(hval.data(), hval.size());
   CA_CUDA(cudaStreamSynchronize(nullptr));
+}
+
+// Ensemble version: a CTA holds the coefficients of 32 states in shared memory ([mode][state]); a warp takes one
+// output entry at a time, its lanes are the 32 states: the entry's (source, value) list is a warp-uniform broadcast
+// read of the same sliced-ELL structure, the state values and the output row are 256-byte coalesced segments.
+// Bound: HBM write of 8 m^2 bytes per state (small m) / issue rate of the contribution loop (m >~ 100).
+template <bool LINEAR>
+__global__ void __launch_bounds__(256)
+jacobian_batched_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restrict__ entry_of,
+                        const uint16_t* __restrict__ src, const double* __restrict__ val, int m,
+                        const double* __restrict__ X, int64_t nstates, int64_t ldx, const double* __restrict__ L1,
+                        const double* __restrict__ L2, double invR, double* __restrict__ OUT, int64_t ldo,
+                        int64_t ochunk) {
+  extern __shared__ double xs[];  // [m][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t s0 = (int64_t)blockIdx.x * 32;
+  for (int idx = threadIdx.x; idx < m * 32; idx += 256) {
+    const int j = idx >> 5, s = idx & 31;
+    xs[idx] = s0 + s < nstates ? X[(s0 + s) + ldx * (int64_t)j] : 0.0;
+  }
+  __syncthreads();
+  const int64_t mm = (int64_t)m * m;
+  const int64_t ob = (int64_t)blockIdx.y * ochunk, oe = min(mm, ob + ochunk);
+  const bool ok = s0 + lane < nstates;
+  for (int64_t o = ob + warp; o < oe; o += 8) {
+    const int32_t e = __ldg(entry_of + o);
+    double acc0 = 0.0, acc1 = 0.0;
+    if (e >= 0) {
+      const int64_t b = __ldg(slice_off + (e >> 5)), end = __ldg(slice_off + (e >> 5) + 1);
+      int64_t p = b + (e & 31);
+      for (; p + 32 < end; p += 64) {
+        acc0 = fma(__ldg(val + p), xs[(int)__ldg(src + p) * 32 + lane], acc0);
+        acc1 = fma(__ldg(val + p + 32), xs[(int)__ldg(src + p + 32) * 32 + lane], acc1);
+      }
+      if (p < end) acc0 = fma(__ldg(val + p), xs[(int)__ldg(src + p) * 32 + lane], acc0);
+    }
+    double r = acc0 + acc1;
+    if (LINEAR) r += fma(__ldg(L2 + o), invR, __ldg(L1 + o));
+    if (ok) OUT[(s0 + lane) + ldo * o] = r;
+  }
+}
+
+void launch_jacobian_batched(const JacobianPack& J, const double* dX, int64_t nstates, int64_t ldx, const double* L1,
+                             const double* L2, double invR, double* dOUT, int64_t ldo, cudaStream_t stream) {
+  if (nstates <= 0 || J.m <= 0) return;
+  if (ldx < nstates || ldo < nstates) fail(CA_ERR_INVALID, "leading dimension smaller than nstates");
+  const size_t smem = (size_t)J.m * 32 * sizeof(double);
+  if (smem > device_cfg().smem_optin) fail(CA_ERR_UNSUPPORTED, "batched dense Jacobian: m = %d does not fit in shared memory", J.m);
+  const int64_t nsb = (nstates + 31) / 32, mm = (int64_t)J.m * J.m;
+  if (nsb > 2147483647LL) fail(CA_ERR_UNSUPPORTED, "too many states for one launch");
+  // enough CTAs to fill the machine a few times over, at least 64 outputs (8 per warp) each
+  int64_t ychunks = std::max<int64_t>(1, std::min<int64_t>((4 * (int64_t)device_cfg().sms + nsb - 1) / nsb, (mm + 63) / 64));
+  ychunks = std::min<int64_t>(ychunks, 65535);
+  const int64_t ochunk = (mm + ychunks - 1) / ychunks;
+  const dim3 grid((unsigned)nsb, (unsigned)((mm + ochunk - 1) / ochunk));
+  if (L1) {
+    auto kern = jacobian_batched_kernel<true>;
+    CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, stream>>>(J.slice_off.ptr, J.entry_of.ptr, J.src.ptr, J.val.ptr, J.m, dX, nstates, ldx, L1, L2,
+                                      invR, dOUT, ldo, ochunk);
+  } else {
+    auto kern = jacobian_batched_kernel<false>;
+    CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, stream>>>(J.slice_off.ptr, J.entry_of.ptr, J.src.ptr, J.val.ptr, J.m, dX, nstates, ldx,
+                                      nullptr, nullptr, 0.0, dOUT, ldo, ochunk);
+  }
+  CA_CUDA(cudaGetLastError());
+  count_launch();
 }
 
 void launch_jacobian(const JacobianPack& J, const double* dx, double* dDN, cudaStream_t stream) {

@@ -97,8 +97,13 @@ struct JacobianPack {
   DeviceBuffer<int32_t> out_pos;    // [nslices*32] linear index i + m*j of each lane's output (-1 pad)
   DeviceBuffer<uint16_t> src;       // [entries] column-major inside a slice
   DeviceBuffer<double> val;
+  DeviceBuffer<int32_t> entry_of;   // [m*m] slice*32 + lane of output i + m*j, -1 where DN is structurally zero
   void build(const std::vector<Term>& coo, int32_t m);
 };
+// Dense Jacobians of an ensemble: OUT[s + ldo * (i + m*j)] = DN(x_s)[i,j] (+ L1[i,j] + L2[i,j]*invR when L1 != null),
+// X nstates x m column-major with leading dimension ldx.  State index fastest, like every ensemble of the library.
+void launch_jacobian_batched(const JacobianPack& J, const double* dX, int64_t nstates, int64_t ldx, const double* L1,
+                             const double* L2, double invR, double* dOUT, int64_t ldo, cudaStream_t stream);
 
 // DN = A_lin + derivative: dDN must hold m*m doubles; it is overwritten.
 void launch_jacobian(const JacobianPack& J, const double* dx, double* dDN, cudaStream_t stream);

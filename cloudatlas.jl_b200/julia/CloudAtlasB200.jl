@@ -67,6 +67,14 @@ function derivative(N::B200Bilinear, x::Vector{Float64})               # SparseB
     DN
 end
 
+function derivative(N::B200Bilinear, X::Matrix{Float64})               # ensemble: DN[s,:,:] = derivative(N, X[s,:])
+    size(X, 2) == N.m || error("ensemble has $(size(X,2)) columns, expected $(N.m)")
+    DN = Array{Float64,3}(undef, size(X, 1), N.m, N.m)
+    check(ccall((:ca_bilinear_jacobian_batched, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}),
+                N.handle, X, size(X, 1), DN))
+    DN
+end
+
 # ---- ODEModel (src/ODEModels.jl:6-63) ------------------------------------------------------------------------
 mutable struct B200Model
     handle::Ptr{Cvoid}
@@ -99,6 +107,12 @@ function _model_from_operators(ijkl, B, A1, A2, N::SparseBilinear{Float64})
     function Df(x::Vector{Float64}, R)                                 # ODEModels.jl:58
         D = Matrix{Float64}(undef, m, m)
         check(ccall((:ca_model_jac, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Float64, Ptr{Float64}), handle, x, R, D))
+        D
+    end
+    function Df(X::Matrix{Float64}, R)                                 # ensemble: D[s,:,:] = Df(X[s,:], R)
+        D = Array{Float64,3}(undef, size(X, 1), m, m)
+        check(ccall((:ca_model_jac_batched, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Float64, Ptr{Float64}),
+                    handle, X, size(X, 1), R, D))
         D
     end
     obj = B200Model(handle, m, ijkl, B, A1, A2, N, f, Df)

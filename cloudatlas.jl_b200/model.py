@@ -16,6 +16,8 @@ _rhs_b = _sig("ca_model_rhs_batched", vp, c_f64p, C.c_int64, C.c_double, c_f64p)
 _rhs_b_dev = _sig("ca_model_rhs_batched_dev", vp, vp, C.c_int64, C.c_int64, C.c_double, vp, C.c_int64, vp)
 _jac = _sig("ca_model_jac", vp, c_f64p, C.c_double, c_f64p)
 _jac_dev = _sig("ca_model_jac_dev", vp, vp, C.c_double, vp, vp)
+_jac_b = _sig("ca_model_jac_batched", vp, c_f64p, C.c_int64, C.c_double, c_f64p)
+_jac_b_dev = _sig("ca_model_jac_batched_dev", vp, vp, C.c_int64, C.c_int64, C.c_double, vp, C.c_int64, vp)
 _cnab2 = _sig("ca_model_cnab2_batched_dev", vp, vp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int64,
               C.c_int64, vp, vp, vp)
 _set_obs = _sig("ca_model_set_observables", vp, c_f64p, c_f64p)
@@ -109,6 +111,17 @@ class ModelOperators:
         return OUT
 
     def Df(self, x, R):
+        """Df(x,R) (ODEModels.jl:58); a 2-d ``x`` (nstates x m) gives nstates x m x m, state index fastest."""
+        if _is_torch(x) and x.dim() == 2:
+            from .bilinear import jacobian_ensemble
+            return jacobian_ensemble(x, self.m, lambda X, n, ld, D: _jac_b_dev(self._h, X, n, ld, float(R), D, n, _stream()))
+        if not _is_torch(x) and np.ndim(x) == 2:
+            X = np.asfortranarray(np.asarray(x, dtype=np.float64))
+            if X.shape[1] != self.m:
+                raise CloudAtlasError(1, f"ensemble has {X.shape[1]} columns, expected {self.m}")
+            D = np.empty((X.shape[0], self.m, self.m), order="F")
+            check(_jac_b(self._h, _f64(X), X.shape[0], float(R), _f64(D)))
+            return D
         if _is_torch(x):
             import torch
             D = torch.empty((self.m, self.m), dtype=torch.float64, device=x.device).t()

@@ -113,6 +113,12 @@ int32_t ca_bilinear_eval2_batched_dev(ca_bilinear* h, const double* dX, const do
  * -- SparseBilinear.jl:75-91.  Host pointers. */
 int32_t ca_bilinear_jacobian(ca_bilinear* h, const double* x, double* DN);
 int32_t ca_bilinear_jacobian_dev(ca_bilinear* h, const double* dx, double* dDN, void* stream);
+/* derivative(N, x_s) for every state of an ensemble (additive: the reference evaluates one state at a time,
+ * SparseBilinear.jl:75-91).  X: nstates x m column-major; DN: nstates x m x m column-major, i.e.
+ * DN[s + ld*(i + m*j)] = derivative(N, X[s,:])[i,j] -- the state index is the fastest, like every ensemble here. */
+int32_t ca_bilinear_jacobian_batched(ca_bilinear* h, const double* X, int64_t nstates, double* DN);
+int32_t ca_bilinear_jacobian_batched_dev(ca_bilinear* h, const double* dX, int64_t nstates, int64_t ldx,
+                                         double* dDN, int64_t ldo, void* stream);
 /* matrix-free Jacobian action  DN(x) v = N(x,v) + N(v,x)  for ensembles (Newton-Krylov at m ~ 3000) */
 int32_t ca_bilinear_jvp_batched_dev(ca_bilinear* h, const double* dX, const double* dV,
                                     int64_t nstates, int64_t ld, double* dOUT, int64_t ldo,
@@ -144,6 +150,10 @@ int32_t ca_model_rhs_batched_dev(ca_model* h, const double* dX, int64_t nstates,
 /* Df(x,R) = Bfact \ (A1 + (1/R)*A2 + derivative(N,x))  -- ODEModels.jl:58.  m x m column-major. */
 int32_t ca_model_jac(ca_model* h, const double* x, double R, double* Df);
 int32_t ca_model_jac_dev(ca_model* h, const double* dx, double R, double* dDf, void* stream);
+/* Df(x_s,R) for every state of an ensemble, dense: Df[s + ld*(i + m*j)] (nstates x m x m column-major). */
+int32_t ca_model_jac_batched(ca_model* h, const double* X, int64_t nstates, double R, double* Df);
+int32_t ca_model_jac_batched_dev(ca_model* h, const double* dX, int64_t nstates, int64_t ldx, double R,
+                                 double* dDf, int64_t ldo, void* stream);
 /* Df(x_s,R) v_s for ensembles, matrix-free */
 int32_t ca_model_jvp_batched_dev(ca_model* h, const double* dX, const double* dV, int64_t nstates,
                                  int64_t ld, double R, double* dOUT, int64_t ldo, void* stream);

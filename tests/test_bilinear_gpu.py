@@ -84,6 +84,39 @@ def test_jacobian(pair):
     assert relerr(DN @ x, 2 * ref(x)) < 1e-12
 
 
+@pytest.mark.parametrize("nstates", [1, 31, 77])
+def test_jacobian_of_an_ensemble(pair, nstates):
+    """derivative(N, X) for an ensemble: nstates x m x m, one reference derivative per state (host and device forms,
+    ragged ensemble sizes, padded leading dimension); bit-identical to the single-state kernel's entries."""
+    import torch
+    N, ref = pair
+    m = N.m
+    X = 0.1 * np.random.default_rng(40 + nstates).standard_normal((nstates, m))
+    want = np.stack([ref.derivative(x) for x in X])
+    got = N.derivative(X)
+    assert got.shape == (nstates, m, m) and got.flags.f_contiguous
+    assert relerr(got, want) < TOL
+    ld = nstates + 5
+    buf = torch.zeros((m, ld), dtype=torch.float64, device="cuda")
+    buf[:, :nstates] = torch.from_numpy(X.T)
+    D = N.derivative(buf.t()[:nstates])
+    assert tuple(D.shape) == (nstates, m, m) and D.stride() == (1, nstates, nstates * m)
+    assert relerr(D.cpu().numpy(), want) < TOL
+    assert relerr(D[0].cpu().numpy(), N.derivative(X[0])) < 1e-15
+    # structurally zero entries are written as exact zeros (no memset needed by the caller)
+    assert np.all(D.cpu().numpy()[:, np.all(want == 0.0, axis=0)] == 0.0)
+
+
+def test_jacobian_of_an_ensemble_m307(ca, nagata_H):
+    from oracle.bilinear import SparseBilinear as Ref
+    ijk, val, m = model_coo((3, 3, 12), nagata_H)
+    N, ref = ca.SparseBilinear(ijk, val, m), Ref(ijk, val, m)
+    X = 0.1 * np.random.default_rng(12).standard_normal((37, m))
+    got = N.derivative(X)
+    for s in (0, 17, 36):
+        assert relerr(got[s], ref.derivative(X[s])) < TOL
+
+
 def test_jvp_matches_jacobian(pair, ca):
     import torch
     N, ref = pair

@@ -54,6 +54,22 @@ def test_jacobian(pair):
     assert relerr(fd, dev.Df(x, 200.0)) < 1e-5
 
 
+def test_jacobian_of_an_ensemble(pair):
+    """Df(X, R) for an ensemble (nstates x m x m), host and device forms, against the reference closure per state."""
+    import torch
+    dev, ref = pair
+    X = 0.1 * np.random.default_rng(9).standard_normal((45, dev.m))
+    tol = 1e-13 * max(1.0, np.linalg.cond(ref.B) / 10)
+    for R in (200.0, 320.0):
+        want = np.stack([ref.Df(x, R) for x in X])
+        got = dev.Df(X, R)
+        assert got.shape == (45, dev.m, dev.m)
+        assert relerr(got, want) < tol
+        dX = torch.from_numpy(X.T.copy()).cuda().t()
+        assert relerr(dev.Df(dX, R).cpu().numpy(), want) < tol
+    assert relerr(dev.Df(X, 200.0)[3], dev.Df(X[3], 200.0)) < 1e-15
+
+
 def test_jvp(pair, ca):
     import torch
     dev, ref = pair
