@@ -303,10 +303,18 @@ void JacobianPack::build(const std::vector<Term>& coo, int32_t m_) {
         hval[at] = mg[r].v;
       }
     }
-  std::vector<int32_t> eo((size_t)m * m, -1);
-  for (size_t e = 0; e < pos.size(); ++e)
-    if (pos[e] >= 0) eo[(size_t)pos[e]] = (int32_t)e;
-  entry_of.upload(eo.data(), eo.size());
+  // host mirror for the ensemble kernel's output-major copy -- only where that kernel can run at all (its tile of
+  // 32 states has to fit in shared memory)
+  const bool mirror = (size_t)m * 32 * sizeof(double) <= (size_t)227 * 1024;
+  h_out.resize(mirror ? mg.size() : 0);
+  h_src.resize(h_out.size());
+  h_val.resize(h_out.size());
+  for (size_t r = 0; r < h_out.size(); ++r) {
+    h_out[r] = mg[r].out;
+    h_src[r] = (uint16_t)mg[r].src;
+    h_val[r] = mg[r].v;
+  }
+  optr.release();
   slice_off.upload(soff.data(), soff.size());
   out_pos.upload(pos.data(), pos.size());
   src.upload(hsrc.data(), hsrc.size());
@@ -314,53 +322,70 @@ void JacobianPack::build(const std::vector<Term>& coo, int32_t m_) {
   CA_CUDA(cudaStreamSynchronize(nullptr));
 }
 
-// Ensemble version: a CTA holds the coefficients of 32 states in shared memory ([mode][state]); a warp takes one
-// output entry at a time, its lanes are the 32 states: the entry's (source, value) list is a warp-uniform broadcast
-// read of the same sliced-ELL structure, the state values and the output row are 256-byte coalesced segments.
+// Ensemble version: a CTA holds the coefficients of 32*SPL states in shared memory ([mode][state]); a warp takes one
+// output entry at a time, each lane carries SPL states (lane, lane + 32, ...): the entry's (source, value) list is a
+// warp-uniform broadcast read of the same sliced-ELL structure -- amortised over SPL states, four contributions in
+// flight -- and the state values and the output rows are 256-byte coalesced segments.
 // Bound: HBM write of 8 m^2 bytes per state (small m) / issue rate of the contribution loop (m >~ 100).
-template <bool LINEAR>
+template <int SPL, bool LINEAR>
 __global__ void __launch_bounds__(256)
-jacobian_batched_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restrict__ entry_of,
-                        const uint16_t* __restrict__ src, const double* __restrict__ val, int m,
+jacobian_batched_kernel(const int64_t* __restrict__ optr, const uint16_t* __restrict__ src,
+                        const double* __restrict__ val, int m,
                         const double* __restrict__ X, int64_t nstates, int64_t ldx, const double* __restrict__ L1,
                         const double* __restrict__ L2, double invR, double* __restrict__ OUT, int64_t ldo,
                         int64_t ochunk) {
-  extern __shared__ double xs[];  // [m][32]
+  constexpr int SB = 32 * SPL;
+  extern __shared__ double xs[];  // [m][SB]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t s0 = (int64_t)blockIdx.x * 32;
-  for (int idx = threadIdx.x; idx < m * 32; idx += 256) {
-    const int j = idx >> 5, s = idx & 31;
+  const int64_t s0 = (int64_t)blockIdx.x * SB;
+  for (int idx = threadIdx.x; idx < m * SB; idx += 256) {
+    const int j = idx / SB, s = idx % SB;
     xs[idx] = s0 + s < nstates ? X[(s0 + s) + ldx * (int64_t)j] : 0.0;
   }
   __syncthreads();
   const int64_t mm = (int64_t)m * m;
   const int64_t ob = (int64_t)blockIdx.y * ochunk, oe = min(mm, ob + ochunk);
-  const bool ok = s0 + lane < nstates;
+  const double* xl = xs + lane;
   for (int64_t o = ob + warp; o < oe; o += 8) {
-    const int32_t e = __ldg(entry_of + o);
-    double acc0 = 0.0, acc1 = 0.0;
-    if (e >= 0) {
-      const int64_t b = __ldg(slice_off + (e >> 5)), end = __ldg(slice_off + (e >> 5) + 1);
-      int64_t p = b + (e & 31);
-      for (; p + 32 < end; p += 64) {
-        acc0 = fma(__ldg(val + p), xs[(int)__ldg(src + p) * 32 + lane], acc0);
-        acc1 = fma(__ldg(val + p + 32), xs[(int)__ldg(src + p + 32) * 32 + lane], acc1);
+    double acc[SPL];
+#pragma unroll
+    for (int q = 0; q < SPL; ++q) acc[q] = 0.0;
+    int64_t p = __ldg(optr + o);
+    const int64_t end = __ldg(optr + o + 1);  // structurally zero outputs have empty lists and are written as zeros
+    for (; p + 4 <= end; p += 4) {
+      double v[4];
+      int sc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u] = __ldg(val + p + u);
+        sc[u] = (int)__ldg(src + p + u) * SB;
       }
-      if (p < end) acc0 = fma(__ldg(val + p), xs[(int)__ldg(src + p) * 32 + lane], acc0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) acc[q] = fma(v[u], xl[sc[u] + 32 * q], acc[q]);
     }
-    double r = acc0 + acc1;
-    if (LINEAR) r += fma(__ldg(L2 + o), invR, __ldg(L1 + o));
-    if (ok) OUT[(s0 + lane) + ldo * o] = r;
+    for (; p < end; ++p) {
+      const double v = __ldg(val + p);
+      const int sc = (int)__ldg(src + p) * SB;
+#pragma unroll
+      for (int q = 0; q < SPL; ++q) acc[q] = fma(v, xl[sc + 32 * q], acc[q]);
+    }
+    const double lin = LINEAR ? fma(__ldg(L2 + o), invR, __ldg(L1 + o)) : 0.0;
+    double* out = OUT + s0 + lane + ldo * o;
+#pragma unroll
+    for (int q = 0; q < SPL; ++q)
+      if (s0 + lane + 32 * q < nstates) out[32 * q] = acc[q] + lin;
   }
 }
 
-void launch_jacobian_batched(const JacobianPack& J, const double* dX, int64_t nstates, int64_t ldx, const double* L1,
-                             const double* L2, double invR, double* dOUT, int64_t ldo, cudaStream_t stream) {
-  if (nstates <= 0 || J.m <= 0) return;
-  if (ldx < nstates || ldo < nstates) fail(CA_ERR_INVALID, "leading dimension smaller than nstates");
-  const size_t smem = (size_t)J.m * 32 * sizeof(double);
-  if (smem > device_cfg().smem_optin) fail(CA_ERR_UNSUPPORTED, "batched dense Jacobian: m = %d does not fit in shared memory", J.m);
-  const int64_t nsb = (nstates + 31) / 32, mm = (int64_t)J.m * J.m;
+template <int SPL>
+static void launch_jacobian_batched_spl(const JacobianPack& J, const double* dX, int64_t nstates, int64_t ldx,
+                                        const double* L1, const double* L2, double invR, double* dOUT, int64_t ldo,
+                                        cudaStream_t stream) {
+  constexpr int SB = 32 * SPL;
+  const size_t smem = (size_t)J.m * SB * sizeof(double);
+  const int64_t nsb = (nstates + SB - 1) / SB, mm = (int64_t)J.m * J.m;
   if (nsb > 2147483647LL) fail(CA_ERR_UNSUPPORTED, "too many states for one launch");
   // enough CTAs to fill the machine a few times over, at least 64 outputs (8 per warp) each
   int64_t ychunks = std::max<int64_t>(1, std::min<int64_t>((4 * (int64_t)device_cfg().sms + nsb - 1) / nsb, (mm + 63) / 64));
@@ -368,18 +393,51 @@ void launch_jacobian_batched(const JacobianPack& J, const double* dX, int64_t ns
   const int64_t ochunk = (mm + ychunks - 1) / ychunks;
   const dim3 grid((unsigned)nsb, (unsigned)((mm + ochunk - 1) / ochunk));
   if (L1) {
-    auto kern = jacobian_batched_kernel<true>;
+    auto kern = jacobian_batched_kernel<SPL, true>;
     CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 256, smem, stream>>>(J.slice_off.ptr, J.entry_of.ptr, J.src.ptr, J.val.ptr, J.m, dX, nstates, ldx, L1, L2,
-                                      invR, dOUT, ldo, ochunk);
+    kern<<<grid, 256, smem, stream>>>(J.optr.ptr, J.osrc.ptr, J.oval.ptr, J.m, dX, nstates, ldx, L1, L2, invR, dOUT, ldo,
+                                      ochunk);
   } else {
-    auto kern = jacobian_batched_kernel<false>;
+    auto kern = jacobian_batched_kernel<SPL, false>;
     CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 256, smem, stream>>>(J.slice_off.ptr, J.entry_of.ptr, J.src.ptr, J.val.ptr, J.m, dX, nstates, ldx,
-                                      nullptr, nullptr, 0.0, dOUT, ldo, ochunk);
+    kern<<<grid, 256, smem, stream>>>(J.optr.ptr, J.osrc.ptr, J.oval.ptr, J.m, dX, nstates, ldx, nullptr, nullptr, 0.0,
+                                      dOUT, ldo, ochunk);
   }
   CA_CUDA(cudaGetLastError());
   count_launch();
+}
+
+void JacobianPack::ensure_output_major() const {
+  if (optr.ptr) return;
+  if (h_out.size() != (size_t)nentries)
+    fail(CA_ERR_UNSUPPORTED, "batched dense Jacobian: m = %d does not fit in shared memory", m);
+  const int64_t mm = (int64_t)m * m;
+  std::vector<int64_t> ptr((size_t)mm + 1, 0);
+  for (int64_t o : h_out) ptr[(size_t)o + 1]++;  // h_out is sorted: the lists are already contiguous
+  for (int64_t o = 0; o < mm; ++o) ptr[(size_t)o + 1] += ptr[(size_t)o];
+  optr.upload(ptr.data(), ptr.size());
+  osrc.upload(h_src.data(), h_src.size());
+  oval.upload(h_val.data(), h_val.size());
+  CA_CUDA(cudaStreamSynchronize(nullptr));
+  std::vector<int64_t>().swap(h_out);
+  std::vector<uint16_t>().swap(h_src);
+  std::vector<double>().swap(h_val);
+}
+
+void launch_jacobian_batched(const JacobianPack& J, const double* dX, int64_t nstates, int64_t ldx, const double* L1,
+                             const double* L2, double invR, double* dOUT, int64_t ldo, cudaStream_t stream) {
+  if (nstates <= 0 || J.m <= 0) return;
+  J.ensure_output_major();
+  if (ldx < nstates || ldo < nstates) fail(CA_ERR_INVALID, "leading dimension smaller than nstates");
+  const size_t per32 = (size_t)J.m * 32 * sizeof(double);
+  if (per32 > device_cfg().smem_optin) fail(CA_ERR_UNSUPPORTED, "batched dense Jacobian: m = %d does not fit in shared memory", J.m);
+  int spl = 8;  // states per lane: as many as keep >= 2 CTAs per SM and have states to work on
+  if (const char* e = getenv("CA_JAC_SPL")) spl = atoi(e);  // tuning hook
+  while (spl > 1 && (per32 * spl > (size_t)100 * 1024 || nstates <= 16 * spl)) spl /= 2;
+  if (spl >= 8) launch_jacobian_batched_spl<8>(J, dX, nstates, ldx, L1, L2, invR, dOUT, ldo, stream);
+  else if (spl >= 4) launch_jacobian_batched_spl<4>(J, dX, nstates, ldx, L1, L2, invR, dOUT, ldo, stream);
+  else if (spl == 2) launch_jacobian_batched_spl<2>(J, dX, nstates, ldx, L1, L2, invR, dOUT, ldo, stream);
+  else launch_jacobian_batched_spl<1>(J, dX, nstates, ldx, L1, L2, invR, dOUT, ldo, stream);
 }
 
 void launch_jacobian(const JacobianPack& J, const double* dx, double* dDN, cudaStream_t stream) {

@@ -97,7 +97,16 @@ struct JacobianPack {
   DeviceBuffer<int32_t> out_pos;    // [nslices*32] linear index i + m*j of each lane's output (-1 pad)
   DeviceBuffer<uint16_t> src;       // [entries] column-major inside a slice
   DeviceBuffer<double> val;
-  DeviceBuffer<int32_t> entry_of;   // [m*m] slice*32 + lane of output i + m*j, -1 where DN is structurally zero
+  // Output-major copy for ensembles (launch_jacobian_batched; built on its first use from the host mirror below):
+  // the contributions of output o = i + m*j are the contiguous range [optr[o], optr[o+1]) of (osrc, oval), so that a
+  // warp walking one output reads its list as a sequential, line-reusing, warp-uniform stream.
+  mutable DeviceBuffer<int64_t> optr;
+  mutable DeviceBuffer<uint16_t> osrc;
+  mutable DeviceBuffer<double> oval;
+  mutable std::vector<int64_t> h_out;     // host mirror: output index of every merged contribution (sorted)
+  mutable std::vector<uint16_t> h_src;
+  mutable std::vector<double> h_val;
+  void ensure_output_major() const;
   void build(const std::vector<Term>& coo, int32_t m);
 };
 // Dense Jacobians of an ensemble: OUT[s + ldo * (i + m*j)] = DN(x_s)[i,j] (+ L1[i,j] + L2[i,j]*invR when L1 != null),
