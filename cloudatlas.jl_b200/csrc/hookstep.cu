@@ -76,8 +76,23 @@ __device__ void block_gemv(const double* A, const double* x, double* y, int m, b
 // more than a whole column step at these sizes (4 barriers per column made a 17 x 17 LU ~20x slower).
 constexpr int kWarpLuMax = 64;
 
-__device__ void warp_lu(double* W, int* piv, int m, int* flag) {
+// argmax of the lanes' (best, at) with the smallest row winning ties, in three redux ops: the bit pattern of a
+// non-negative double is monotonic in its value.  best < 0 marks a lane without rows.
+__device__ __forceinline__ void warp_argmax(double best, int at, double& gbest, int& gat) {
+  const unsigned long long key = best < 0.0 ? 0ull : (unsigned long long)__double_as_longlong(best) + 1ull;
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+  gat = (int)__reduce_min_sync(0xffffffffu, (hi == mhi && lo == mlo) ? (unsigned)at : 0xffffffffu);
+  const unsigned long long gk = ((unsigned long long)mhi << 32) | mlo;
+  gbest = gk == 0ull ? -1.0 : __longlong_as_double((long long)(gk - 1ull));
+}
+
+// perm: the row permutation of the factorisation as one gather (b <- b[perm]), kept next to LAPACK-style piv
+__device__ void warp_lu(double* W, int* piv, int* perm, int m, int* flag) {
   const int lane = threadIdx.x & 31;
+  for (int i = lane; i < m; i += 32) perm[i] = i;
+  __syncwarp();
   for (int k = 0; k < m; ++k) {
     double best = -1.0;
     int at = k;
@@ -85,17 +100,17 @@ __device__ void warp_lu(double* W, int* piv, int m, int* flag) {
       const double v = fabs(W[r + m * k]);
       if (v > best) { best = v; at = r; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oa = __shfl_xor_sync(0xffffffffu, at, o);
-      if (ob > best || (ob == best && oa < at)) { best = ob; at = oa; }
-    }
+    warp_argmax(best, at, best, at);
     if (best == 0.0) {
       if (lane == 0) *flag = 1;
       return;
     }
-    if (lane == 0) piv[k] = at;
+    if (lane == 0) {
+      piv[k] = at;
+      const int t = perm[k];
+      perm[k] = perm[at];
+      perm[at] = t;
+    }
     if (at != k)
       for (int j = lane; j < m; j += 32) {
         const double t = W[k + m * j];
@@ -109,43 +124,65 @@ __device__ void warp_lu(double* W, int* piv, int m, int* flag) {
     double l0 = 0.0, l1 = 0.0;
     if (r0 < m) { l0 = W[r0 + m * k] / pivot; W[r0 + m * k] = l0; }
     if (r1 < m) { l1 = W[r1 + m * k] / pivot; W[r1 + m * k] = l1; }
-    for (int c = k + 1; c < m; ++c) {
-      const double u = W[k + m * c];  // broadcast read
-      if (r0 < m) W[r0 + m * c] = fma(-l0, u, W[r0 + m * c]);
-      if (r1 < m) W[r1 + m * c] = fma(-l1, u, W[r1 + m * c]);
+    // four columns per pass, all loads before the stores: row k is never written here, but the compiler cannot know
+    // that and would otherwise serialise every column behind the previous column's store
+    const bool h0 = r0 < m, h1 = r1 < m;
+    int c = k + 1;
+    for (; c + 4 <= m; c += 4) {
+      double u[4], w0[4], w1[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        u[q] = W[k + m * (c + q)];  // broadcast read
+        w0[q] = h0 ? W[r0 + m * (c + q)] : 0.0;
+        w1[q] = h1 ? W[r1 + m * (c + q)] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (h0) W[r0 + m * (c + q)] = fma(-l0, u[q], w0[q]);
+        if (h1) W[r1 + m * (c + q)] = fma(-l1, u[q], w1[q]);
+      }
+    }
+    for (; c < m; ++c) {
+      const double u = W[k + m * c];
+      if (h0) W[r0 + m * c] = fma(-l0, u, W[r0 + m * c]);
+      if (h1) W[r1 + m * c] = fma(-l1, u, W[r1 + m * c]);
     }
     __syncwarp();
   }
 }
 
-__device__ void warp_lu_solve(const double* W, const int* piv, double* b, int m) {
+// b <- (LU)^-1 b with b in registers (lane owns rows lane and lane + 32): the same operations in the same order as
+// the shared-memory loops of block_lu_solve, minus their per-column round trips and barriers.
+__device__ void warp_lu_solve(const double* W, const int* perm, double* b, int m) {
   const int lane = threadIdx.x & 31;
-  if (lane == 0)
-    for (int k = 0; k < m; ++k) {
-      const int p = piv[k];
-      if (p != k) { const double t = b[k]; b[k] = b[p]; b[p] = t; }
-    }
+  const int r0 = lane, r1 = lane + 32;
+  double b0 = r0 < m ? b[perm[r0]] : 0.0, b1 = r1 < m ? b[perm[r1]] : 0.0;
   __syncwarp();
   for (int c = 0; c < m; ++c) {
-    const double f = b[c];
-    for (int r = c + 1 + lane; r < m; r += 32) b[r] = fma(-W[r + m * c], f, b[r]);
-    __syncwarp();
+    const double f = __shfl_sync(0xffffffffu, c < 32 ? b0 : b1, c & 31);
+    if (r0 > c && r0 < m) b0 = fma(-W[r0 + m * c], f, b0);
+    if (r1 > c && r1 < m) b1 = fma(-W[r1 + m * c], f, b1);
   }
   for (int c = m - 1; c >= 0; --c) {
-    if (lane == 0) b[c] /= W[c + m * c];
-    __syncwarp();
-    const double f = b[c];
-    for (int r = lane; r < c; r += 32) b[r] = fma(-W[r + m * c], f, b[r]);
-    __syncwarp();
+    double mine = c < 32 ? b0 : b1;
+    if (lane == (c & 31)) mine /= W[c + m * c];
+    const double f = __shfl_sync(0xffffffffu, mine, c & 31);
+    if (r0 == c) b0 = f;
+    if (r1 == c) b1 = f;
+    if (r0 < c) b0 = fma(-W[r0 + m * c], f, b0);
+    if (r1 < c && r1 < m) b1 = fma(-W[r1 + m * c], f, b1);
   }
+  if (r0 < m) b[r0] = b0;
+  if (r1 < m) b[r1] = b1;
+  __syncwarp();
 }
 
 // In-place LU with partial pivoting (first maximal |entry| wins, like LAPACK's idamax).  Returns false
 // on an exactly zero pivot.
-__device__ bool block_lu(double* W, int* piv, int m, int* flag) {
+__device__ bool block_lu(double* W, int* piv, int* perm, int m, int* flag) {
   const int tid = threadIdx.x, lane = tid & 31;
   if (m <= kWarpLuMax) {
-    if (tid < 32) warp_lu(W, piv, m, flag);
+    if (tid < 32) warp_lu(W, piv, perm, m, flag);
     __syncthreads();
     return *flag == 0;
   }
@@ -192,10 +229,10 @@ __device__ bool block_lu(double* W, int* piv, int m, int* flag) {
 }
 
 // b <- (LU)^-1 b
-__device__ void block_lu_solve(const double* W, const int* piv, double* b, int m) {
+__device__ void block_lu_solve(const double* W, const int* piv, const int* perm, double* b, int m) {
   const int tid = threadIdx.x;
   if (m <= kWarpLuMax) {
-    if (tid < 32) warp_lu_solve(W, piv, b, m);
+    if (tid < 32) warp_lu_solve(W, perm, b, m);
     __syncthreads();
     return;
   }
@@ -251,7 +288,18 @@ __device__ void eval_Df(const SolverArgs& a, double invR, const double* x, doubl
   __syncthreads();
 }
 
+#ifdef CA_HOOK_PROFILE
+#define TIC long long t__ = clock64()
+#define TOC(slot) prof[slot] += clock64() - t__
+#else
+#define TIC
+#define TOC(slot)
+#endif
 __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a) {
+#ifdef CA_HOOK_PROFILE
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long tstart = clock64();
+#endif
   extern __shared__ __align__(16) double sm[];
   const int m = a.m, tid = threadIdx.x;
   const int64_t s = blockIdx.x;
@@ -269,7 +317,8 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
   double* t2 = t1 + m;
   double* scratch = t2 + m;          // 8 doubles
   int* piv = (int*)(scratch + 8);    // m ints
-  int* flag = piv + m;
+  int* perm = piv + m;               // m ints
+  int* flag = perm + m;
 
   const double invR = 1.0 / a.R[s];
   const double ftol = a.p.ftol, xtol = a.p.xtol;
@@ -285,7 +334,7 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
   __syncthreads();
 
   for (int n = 0; n < a.p.Nnewton; ++n) {
-    eval_f(a, invR, x, fx);
+    { TIC; eval_f(a, invR, x, fx); TOC(0); }
     ++nf;
     const double rx = 0.5 * block_dot(fx, fx, m, scratch);
     last_res = sqrt(2 * rx);
@@ -294,14 +343,14 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
     if (last_res <= ftol) { exit_reason = CA_EXIT_CONVERGED; break; }
     nsteps = n + 1;
 
-    eval_Df(a, invR, x, Df);
+    { TIC; eval_Df(a, invR, x, Df); TOC(1); }
     ++ndf;
     // Newton step: dx = -Df \ fx
     for (int e = tid; e < m * m; e += kHookThreads) W[e] = Df[e];
     for (int i = tid; i < m; i += kHookThreads) dx[i] = -fx[i];
     __syncthreads();
-    if (!block_lu(W, piv, m, flag)) { exit_reason = CA_EXIT_SINGULAR; break; }
-    block_lu_solve(W, piv, dx, m);
+    { TIC; const bool okk = block_lu(W, piv, perm, m, flag); TOC(2); if (!okk) { exit_reason = CA_EXIT_SINGULAR; break; } }
+    { TIC; block_lu_solve(W, piv, perm, dx, m); TOC(3); }
     const double norm_dx_newt = sqrt(block_dot(dx, dx, m, scratch));
     block_gemv(Df, dx, t1, m, false);  // Df dx
     if (block_dot(fx, t1, m, scratch) >= 0.0) { exit_reason = CA_EXIT_RESIDUAL_UP; break; }
@@ -322,6 +371,7 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
       if (norm_dx_newt > delta) {
         // ---- hookstep(fx, Dfx, delta, dx_newt): Newton iteration on mu for norm(dx(mu)) = delta
         if (!have_H) {
+          TIC;
           for (int e = tid; e < m * m; e += kHookThreads) {
             const int r = e % m, c = e / m;
             double sum = 0.0;
@@ -331,6 +381,7 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
           __syncthreads();
           block_gemv(Df, fx, g, m, true);  // Df' fx
           have_H = true;
+          TOC(4);
         }
         double mu = 1e-6;
         double norm_dx = norm_dx_newt;
@@ -345,16 +396,16 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
             for (int e = tid; e < m * m; e += kHookThreads) W[e] = H[e] + ((e % m) == (e / m) ? mu : 0.0);
           for (int i = tid; i < m; i += kHookThreads) t1[i] = dx[i];
           __syncthreads();
-          if (it == 0 && !block_lu(W, piv, m, flag)) { singular = true; break; }
-          block_lu_solve(W, piv, t1, m);
+          { TIC; const bool okk = it != 0 || block_lu(W, piv, perm, m, flag); TOC(2); if (!okk) { singular = true; break; } }
+          { TIC; block_lu_solve(W, piv, perm, t1, m); TOC(3); }
           const double phiprime = -(1.0 / norm_dx) * block_dot(dx, t1, m, scratch);
           mu = mu - (norm_dx / delta) * (phi / phiprime);
           // dx = -(H + mu I) \ (Df' fx)
           for (int e = tid; e < m * m; e += kHookThreads) W[e] = H[e] + ((e % m) == (e / m) ? mu : 0.0);
           for (int i = tid; i < m; i += kHookThreads) dx[i] = -g[i];
           __syncthreads();
-          if (!block_lu(W, piv, m, flag)) { singular = true; break; }
-          block_lu_solve(W, piv, dx, m);
+          { TIC; const bool okk = block_lu(W, piv, perm, m, flag); TOC(2); if (!okk) { singular = true; break; } }
+          { TIC; block_lu_solve(W, piv, perm, dx, m); TOC(3); }
           norm_dx = sqrt(block_dot(dx, dx, m, scratch));
           if (fabs(norm_dx - delta) / delta <= 1e-4) break;
         }
@@ -372,7 +423,7 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
       const bool within = norm_dx_newt <= delta;
       for (int i = tid; i < m; i += kHookThreads) xh[i] = x[i] + dx[i];
       __syncthreads();
-      eval_f(a, invR, xh, fh);
+      { TIC; eval_f(a, invR, xh, fh); TOC(0); }
       ++nf;
       const double r_hook = 0.5 * block_dot(fh, fh, m, scratch);
       const double r_linear = rx + block_dot(fx, t1, m, scratch);
@@ -413,6 +464,11 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
     __syncthreads();
   }
 
+#ifdef CA_HOOK_PROFILE
+  if (tid == 0 && s == 0)
+    printf("[hook profile] total %lld cycles: f %lld  Df %lld  LU %lld  solve %lld  H+g %lld\n", clock64() - tstart, prof[0],
+           prof[1], prof[2], prof[3], prof[4]);
+#endif
   for (int i = tid; i < m; i += kHookThreads) a.Xout[s + a.nsolve * i] = x[i];
   if (tid == 0) {
     a.success[s] = exit_reason == CA_EXIT_CONVERGED ? 1 : 0;
@@ -443,7 +499,7 @@ extern "C" int32_t ca_hookstep_solve_model(ca_model* h, const double* R, const d
       if (!(R[s] != 0.0)) fail(CA_ERR_INVALID, "R must be non-zero");
     h->bind();
     const int m = (int)h->m;
-    const size_t smem = ((size_t)3 * m * m + 9 * (size_t)m + 8) * sizeof(double) + ((size_t)m + 4) * sizeof(int);
+    const size_t smem = ((size_t)3 * m * m + 9 * (size_t)m + 8) * sizeof(double) + (2 * (size_t)m + 4) * sizeof(int);
     int optin = 0;
     CA_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     if (smem > (size_t)optin)
