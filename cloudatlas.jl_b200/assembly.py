@@ -86,8 +86,8 @@ class AssemblySlab:
         return D
 
     def coo_host(self):
-        ijk = np.zeros((self.nnz, 3), dtype=np.int64, order="F")
-        val = np.zeros(self.nnz)
+        ijk = np.empty((self.nnz, 3), dtype=np.int64, order="F")
+        val = np.empty(self.nnz)
         check(_get_coo(self._h, ijk.ctypes.data_as(c_i64p), val.ctypes.data_as(c_f64p)))
         return ijk, val
 

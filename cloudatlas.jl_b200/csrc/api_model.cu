@@ -156,10 +156,30 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
 
     // ---- N grouped by output row
     std::vector<std::vector<std::pair<uint64_t, double>>> byrow(m);
-    for (int64_t r = 0; r < nnz; ++r) {
-      const int i = (int)ijk[r] - 1;
-      const uint64_t j = (uint64_t)ijk[r + nnz] - 1, k = (uint64_t)ijk[r + 2 * nnz] - 1;
-      byrow[i].push_back({j * (uint64_t)m + k, val[r]});
+    {
+      // the reference's COO is sorted by (i, j, k) (SparseBilinear.jl:24-49): rows are contiguous ranges, filled on
+      // worker threads; anything else goes through the serial scatter
+      bool sorted_rows = true;
+      for (int64_t r = 1; r < nnz && sorted_rows; ++r) sorted_rows = ijk[r] >= ijk[r - 1];
+      if (sorted_rows && nnz > (1 << 16)) {
+        std::vector<int64_t> row_start((size_t)m + 1, 0);
+        for (int64_t r = 0; r < nnz; ++r) row_start[(size_t)ijk[r]]++;  // 1-based i lands at index i
+        for (int i = 0; i < m; ++i) row_start[(size_t)i + 1] += row_start[i];
+        parallel_chunks((size_t)m, (size_t)m, [&](size_t b, size_t e, size_t) {
+          for (size_t i = b; i < e; ++i) {
+            auto& row = byrow[i];
+            row.reserve((size_t)(row_start[i + 1] - row_start[i]));
+            for (int64_t r = row_start[i]; r < row_start[i + 1]; ++r)
+              row.push_back({((uint64_t)ijk[r + nnz] - 1) * (uint64_t)m + ((uint64_t)ijk[r + 2 * nnz] - 1), val[r]});
+          }
+        });
+      } else {
+        for (int64_t r = 0; r < nnz; ++r) {
+          const int i = (int)ijk[r] - 1;
+          const uint64_t j = (uint64_t)ijk[r + nnz] - 1, k = (uint64_t)ijk[r + 2 * nnz] - 1;
+          byrow[i].push_back({j * (uint64_t)m + k, val[r]});
+        }
+      }
     }
     tm.lap("blocks+byrow");
     std::vector<Term> qterms;  // folded Q = B^-1 N, ordered (j,k)
@@ -194,17 +214,40 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
         }
       // quadratic operator: dense [g x |union of pairs|] times Binv
       std::vector<uint64_t> U;
-      for (int b = 0; b < g; ++b)
-        for (auto& e : byrow[G[b]]) U.push_back(e.first);
-      std::sort(U.begin(), U.end());
-      U.erase(std::unique(U.begin(), U.end()), U.end());
+      bool rows_sorted = true;  // (j,k)-sorted rows (the reference's COO order): the union is a sequence of merges
+      for (int b = 0; b < g && rows_sorted; ++b) {
+        const auto& row = byrow[G[b]];
+        for (size_t e = 1; e < row.size() && rows_sorted; ++e) rows_sorted = row[e - 1].first <= row[e].first;
+      }
+      if (rows_sorted) {
+        std::vector<uint64_t> keys, merged;
+        for (int b = 0; b < g; ++b) {
+          keys.clear();
+          for (auto& e : byrow[G[b]])
+            if (keys.empty() || keys.back() != e.first) keys.push_back(e.first);
+          merged.clear();
+          std::set_union(U.begin(), U.end(), keys.begin(), keys.end(), std::back_inserter(merged));
+          U.swap(merged);
+        }
+      } else {
+        for (int b = 0; b < g; ++b)
+          for (auto& e : byrow[G[b]]) U.push_back(e.first);
+        std::sort(U.begin(), U.end());
+        U.erase(std::unique(U.begin(), U.end()), U.end());
+      }
       if (U.empty()) return;
       std::vector<double> D((size_t)g * U.size(), 0.0);
-      for (int b = 0; b < g; ++b)
+      for (int b = 0; b < g; ++b) {
+        size_t p = 0;
         for (auto& e : byrow[G[b]]) {
-          const size_t p = std::lower_bound(U.begin(), U.end(), e.first) - U.begin();
+          if (rows_sorted) {
+            while (U[p] != e.first) ++p;  // both ascending; the row's keys are a subset of U
+          } else {
+            p = std::lower_bound(U.begin(), U.end(), e.first) - U.begin();
+          }
           D[(size_t)b * U.size() + p] += e.second;
         }
+      }
       std::vector<Term>& out_terms = block_terms[bi];
       for (int a = 0; a < g; ++a)
         for (size_t p = 0; p < U.size(); ++p) {
@@ -252,6 +295,7 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
     for (int j = 0; j < m; ++j)
       for (int i = 0; i < m; ++i)
         if (hL1[i + (size_t)m * j] != 0.0 || hL2[i + (size_t)m * j] != 0.0) all.push_back(Term{i, j, m, 1.0});
+    tm.lap("term list");
     PackedHost P = pack_terms(std::move(all), m, /*symmetric=*/true, kNtMax, window_modes_for(m));
     h->qterms = std::move(qterms);
     tm.lap("pack");
@@ -315,8 +359,13 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
     h->hA1.assign(A1, A1 + (size_t)m * m);
     h->hA2.assign(A2, A2 + (size_t)m * m);
     h->ncoo.resize((size_t)nnz);
-    for (int64_t r = 0; r < nnz; ++r)
-      h->ncoo[(size_t)r] = Term{(int32_t)(ijk[r] - 1), (int32_t)(ijk[r + nnz] - 1), (int32_t)(ijk[r + 2 * nnz] - 1), val[r]};
+    {
+      ca_model* hp = h.get();
+      parallel_chunks((size_t)nnz, 64, [&](size_t b, size_t e, size_t) {
+        for (size_t r = b; r < e; ++r)
+          hp->ncoo[r] = Term{(int32_t)(ijk[r] - 1), (int32_t)(ijk[r + nnz] - 1), (int32_t)(ijk[r + 2 * nnz] - 1), val[r]};
+      });
+    }
     {
       std::vector<double> r1((size_t)m * m), r2((size_t)m * m);
       for (int i = 0; i < m; ++i)

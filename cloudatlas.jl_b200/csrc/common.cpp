@@ -1,4 +1,6 @@
 #include "common.h"
+#include <vector>
+#include <atomic>
 
 #include <algorithm>
 #include <cstring>
@@ -40,6 +42,20 @@ unsigned worker_threads() {
     if (v >= 1) return (unsigned)std::min(v, 64);
   }
   return std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+}
+
+void parallel_chunks(size_t n, size_t chunks, const std::function<void(size_t, size_t, size_t)>& fn) {
+  if (n == 0) return;
+  chunks = std::max<size_t>(1, std::min(chunks, n));
+  const unsigned nthreads = (unsigned)std::min<size_t>(worker_threads(), chunks);
+  std::atomic<size_t> next{0};
+  auto work = [&]() {
+    for (size_t c = next.fetch_add(1); c < chunks; c = next.fetch_add(1)) fn(n * c / chunks, n * (c + 1) / chunks, c);
+  };
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
 }
 
 void require_device() {

@@ -1,5 +1,6 @@
 // Shared helpers for libcloudatlas_b200: status codes, thread-local error text, CUDA checks.
 #pragma once
+#include <functional>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -52,6 +53,8 @@ int32_t guarded(F&& body) {
 
 // Host worker threads for the build stages: CA_NUM_THREADS, else min(16, hardware threads).
 unsigned worker_threads();
+// fn(begin, end, chunk) over [0, n) cut into `chunks` contiguous pieces, on the worker threads (dynamic assignment)
+void parallel_chunks(size_t n, size_t chunks, const std::function<void(size_t, size_t, size_t)>& fn);
 
 // Wall-clock phase timer, printed to stderr when CA_TIMING is set (host-side build diagnostics).
 struct PhaseTimer {

@@ -60,17 +60,48 @@ void sort_terms(std::vector<Term>& terms, int32_t m) {
     });
     return;
   }
+  // Runs of equal output row (assembly, folding and Julia's COO all emit whole rows): found chunk-wise in parallel,
+  // then moved as blocks.  Input without such runs degenerates to one run per term and costs a little more than the
+  // element-wise scatter it replaces.
+  const size_t n = terms.size();
+  const size_t nchunks = 64;
+  std::vector<std::vector<size_t>> chunk_runs(nchunks);
+  parallel_chunks(n, nchunks, [&](size_t b, size_t e, size_t c) {
+    std::vector<size_t>& r = chunk_runs[c];
+    for (size_t q = b; q < e; ++q)
+      if (q == 0 || terms[q].i != terms[q - 1].i) r.push_back(q);
+  });
+  std::vector<size_t> run_begin;
+  for (auto& r : chunk_runs) run_begin.insert(run_begin.end(), r.begin(), r.end());
+  run_begin.push_back(n);
+  const size_t nruns = run_begin.size() - 1;
   std::vector<size_t> start((size_t)m + 1, 0);
-  for (const Term& t : terms) start[(size_t)t.i + 1]++;
+  for (size_t r = 0; r < nruns; ++r) start[(size_t)terms[run_begin[r]].i + 1] += run_begin[r + 1] - run_begin[r];
   for (int32_t i = 0; i < m; ++i) start[(size_t)i + 1] += start[i];
-  std::vector<Term> out(terms.size());
-  {
+  bool in_place = true;  // already grouped by ascending row: nothing to move
+  for (size_t r = 1; r < nruns && in_place; ++r) in_place = terms[run_begin[r]].i > terms[run_begin[r - 1]].i;
+  if (!in_place && nruns > n / 8) {  // no runs to speak of: element-wise counting sort
+    std::vector<Term> out(n);
     std::vector<size_t> at(start.begin(), start.end() - 1);
     for (const Term& t : terms) out[at[t.i]++] = t;
+    terms.swap(out);
+  } else if (!in_place) {
+    std::vector<size_t> dest(nruns);
+    {
+      std::vector<size_t> at(start.begin(), start.end() - 1);
+      for (size_t r = 0; r < nruns; ++r) {
+        dest[r] = at[terms[run_begin[r]].i];
+        at[terms[run_begin[r]].i] += run_begin[r + 1] - run_begin[r];
+      }
+    }
+    std::vector<Term> out(n);
+    parallel_chunks(nruns, std::min<size_t>(nruns, 1024), [&](size_t b, size_t e, size_t) {
+      for (size_t r = b; r < e; ++r)
+        std::copy(terms.begin() + (ptrdiff_t)run_begin[r], terms.begin() + (ptrdiff_t)run_begin[r + 1],
+                  out.begin() + (ptrdiff_t)dest[r]);
+    });
+    terms.swap(out);
   }
-  terms.swap(out);
-  out.clear();
-  out.shrink_to_fit();
   const unsigned nthreads = ca::worker_threads();
   std::atomic<int32_t> next{0};
   auto work = [&]() {
@@ -116,10 +147,19 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
   P.symmetric = symmetric;
   P.window_modes = window_modes;
 
-  for (auto& t : terms) {
-    if (t.i < 0 || t.i >= m || t.a < 0 || t.a >= nin || t.b < 0 || t.b >= nin)
+  {
+    std::atomic<long long> bad{-1};
+    parallel_chunks(terms.size(), 64, [&](size_t b, size_t e, size_t) {
+      for (size_t q = b; q < e; ++q) {
+        Term& t = terms[q];
+        if (t.i < 0 || t.i >= m || t.a < 0 || t.a >= nin || t.b < 0 || t.b >= nin) bad = (long long)q;
+        else if (symmetric && t.a > t.b) std::swap(t.a, t.b);
+      }
+    });
+    if (bad >= 0) {
+      const Term& t = terms[(size_t)bad.load()];
       fail(CA_ERR_INVALID, "pack_terms: index out of range (i=%d a=%d b=%d, m=%d)", t.i, t.a, t.b, m);
-    if (symmetric && t.a > t.b) std::swap(t.a, t.b);
+    }
   }
   sort_terms(terms, m);
 
@@ -216,7 +256,8 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
 
   tm.lap("cluster");
   // ---- split clusters into tiles of <= 8*nt_max rows, lay out fragments
-  auto emit_tile = [&](const std::vector<int32_t>& trows) {
+  // (P here is the tile's own container: tiles are laid out independently on worker threads and appended in order)
+  auto emit_tile = [&rows, nin, window_modes](const std::vector<int32_t>& trows, PackedHost& P) {
     TileDesc T{};
     T.nrows = (int32_t)trows.size();
     T.nt = (T.nrows + 7) / 8;
@@ -347,6 +388,7 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
     P.tiles.push_back(T);
   };
 
+  std::vector<std::vector<int32_t>> tile_rows;
   for (auto& cl : clusters) {
     const int n = (int)cl.size();
     const int slots = (n + 7) / 8;                     // n-tiles needed
@@ -355,8 +397,38 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
     for (int t = 0; t < ntiles; ++t) {
       const int remaining_tiles = ntiles - t;
       const int take = (n - done + remaining_tiles - 1) / remaining_tiles;  // even split, <= 8*nt_max
-      emit_tile(std::vector<int32_t>(cl.begin() + done, cl.begin() + done + take));
+      tile_rows.emplace_back(cl.begin() + done, cl.begin() + done + take);
       done += take;
+    }
+  }
+  {
+    std::vector<PackedHost> parts(tile_rows.size());
+    parallel_chunks(tile_rows.size(), tile_rows.size(), [&](size_t b, size_t e, size_t) {
+      for (size_t t = b; t < e; ++t) emit_tile(tile_rows[t], parts[t]);
+    });
+    for (PackedHost& Q : parts) {
+      const int32_t ks_base = (int32_t)(P.pairs.size() / 4), rows_base = (int32_t)P.rows.size();
+      const int32_t modes_base = (int32_t)P.modes.size(), tile_index = (int32_t)P.tiles.size();
+      const int64_t vals_base = (int64_t)P.vals.size();
+      TileDesc T = Q.tiles[0];
+      T.ks_begin += ks_base;
+      T.vals_off += vals_base;
+      T.rows_off += rows_base;
+      P.tiles.push_back(T);
+      for (WindowDesc W : Q.windows) {
+        W.ks_begin += ks_base;
+        W.modes_off += modes_base;
+        W.tile = tile_index;
+        P.windows.push_back(W);
+      }
+      P.pairs.insert(P.pairs.end(), Q.pairs.begin(), Q.pairs.end());
+      P.vals.insert(P.vals.end(), Q.vals.begin(), Q.vals.end());
+      P.rows.insert(P.rows.end(), Q.rows.begin(), Q.rows.end());
+      P.modes.insert(P.modes.end(), Q.modes.begin(), Q.modes.end());
+      P.max_window_modes = std::max(P.max_window_modes, Q.max_window_modes);
+      P.padded_fma += Q.padded_fma;
+      P.pair_products += Q.pair_products;
+      Q = PackedHost();  // free the tile's copy
     }
   }
   tm.lap("emit tiles");
@@ -468,6 +540,12 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
       P.stream_layout = true;
     }
   }
+  tm.lap("schedule");
+  {  // the row lists and the term list are gigabytes at m ~ 3000: release them here, inside the timed phases
+    std::vector<Row>().swap(rows);
+    std::vector<Term>().swap(terms);
+  }
+  tm.lap("release");
   return P;
 }
 
