@@ -9,6 +9,7 @@
 // an exact Gauss-Legendre contraction done once per basis on the device.  N is produced directly in
 // the reference's COO order by a count pass, a device scan and a fill pass: no m^3 scratch array.
 #include <algorithm>
+#include <numeric>
 #include <cub/device/device_scan.cuh>
 
 #include <memory>
@@ -35,6 +36,9 @@ struct DevBasis {
   const int32_t* pid;   // [m][3]
   const double* k2;     // [m][3]  (alpha jx)^2 + (gamma kz)^2
   const double *X2, *Z2, *X3, *Z3, *Y2, *Y2y, *Y3;
+  // component-major copies for the lanes of n_kernel (consecutive modes -> consecutive addresses):
+  const double* coefT;    // [3][m]
+  const uint32_t* packT;  // [3][m]  jx | kz << 10 | pid << 20
 };
 
 // double-double helpers (error-free transformations): the wall-normal integrals must be accurate
@@ -141,46 +145,62 @@ __global__ void linear_kernel(DevBasis b, int r0, int r1, double* __restrict__ B
   D[t] = wx + wy + wz;
 }
 
-struct IJ {  // warp-uniform factors of one (i,j) pair: the 9 (c,a) combinations
-  double cij[9];
-  const double* x3[9];  // X3 + ((xi*nx + xj)*nx)*2 + dx, indexed by xk*2
-  const double* z3[9];
-  const double* y3[9];  // Y3 + (pi*npid + pj)*npid + dy, indexed by pk
-  unsigned live;        // bitmask of combinations with non-zero coefficient product
+struct IJ {  // warp-uniform data of one (i,j) pair, kept small (30 registers): the kernel is latency-bound on the
+             // per-pair set-up and wants occupancy more than it wants precomputed table pointers
+  double ci[3], cj[3];
+  int xi[3], xj[3], zi[3], zj[3], pi[3], pj[3];
+  unsigned live;  // bitmask over (c, a) of combinations with non-zero coefficient product
 };
 
 __device__ __forceinline__ void load_ij(const DevBasis& b, int i, int j, IJ& u) {
   u.live = 0;
 #pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    u.ci[c] = b.coef[i * 3 + c];
+    u.cj[c] = b.coef[j * 3 + c];
+    u.xi[c] = b.jx[i * 3 + c];
+    u.xj[c] = b.jx[j * 3 + c];
+    u.zi[c] = b.kz[i * 3 + c];
+    u.zj[c] = b.kz[j * 3 + c];
+    u.pi[c] = b.pid[i * 3 + c];
+    u.pj[c] = b.pid[j * 3 + c];
+  }
+#pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const int q = c * 3 + a;
-      const double ci = b.coef[i * 3 + c], cj = b.coef[j * 3 + a];
-      u.cij[q] = ci * cj;
-      if (u.cij[q] != 0.0) u.live |= 1u << q;
-      u.x3[q] = b.X3 + ((size_t)(b.jx[i * 3 + c] * b.nx + b.jx[j * 3 + a]) * b.nx) * 2 + (a == 0 ? 1 : 0);
-      u.z3[q] = b.Z3 + ((size_t)(b.kz[i * 3 + c] * b.nz + b.kz[j * 3 + a]) * b.nz) * 2 + (a == 2 ? 1 : 0);
-      u.y3[q] = b.Y3 + ((size_t)(b.pid[i * 3 + c] * b.npid + b.pid[j * 3 + a]) * b.npid) + (a == 1 ? 1 : 0);
-    }
+    for (int a = 0; a < 3; ++a)
+      if (u.ci[c] * u.cj[a] != 0.0) u.live |= 1u << (c * 3 + a);
 }
 
+// predicated load: issues only for pred != 0, and never turns into a branch
+__device__ __forceinline__ double ldg_if(const double* p, bool pred) {
+  double v = 0.0;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}" : "+d"(v) : "l"(p), "r"((int)pred));
+  return v;
+}
+
+// Straight-line: the 9 x 2 Fourier factors (small tables, L1) decide which (c, a) combinations survive, the survivors'
+// wall-normal integrals (Y3 is megabytes: L2) are fetched with predicated loads, all nine chains in flight together.
+// As a chain of "if (x3 == 0) continue; if (z3 == 0) continue; ... Y3 ..." the same lookups were up to 27 dependent
+// round trips per candidate, nine of them to L2.  Dead combinations add an exact zero, so the sum is unchanged.
 __device__ __forceinline__ bool entry(const DevBasis& b, const IJ& u, int k, double& val) {
   double s = 0.0, mag = 0.0;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const double ck = b.coef[k * 3 + c];
-    if (ck == 0.0) continue;
-    const int xk = b.jx[k * 3 + c], zk = b.kz[k * 3 + c], pk = b.pid[k * 3 + c];
+    if (!(u.live >> (3 * c) & 7u)) continue;  // warp-uniform: component c of Psi_i (or all of Psi_j) is absent
+    const double ck = __ldg(b.coefT + (size_t)c * b.m + k);
+    const uint32_t pk3 = __ldg(b.packT + (size_t)c * b.m + k);
+    const int xk = pk3 & 1023, zk = (pk3 >> 10) & 1023, pk = pk3 >> 20;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       const int q = c * 3 + a;
-      if (!(u.live >> q & 1)) continue;
-      const double x3 = u.x3[q][xk * 2];
-      if (x3 == 0.0) continue;
-      const double z3 = u.z3[q][zk * 2];
-      if (z3 == 0.0) continue;
-      const double t = u.cij[q] * ck * x3 * z3 * u.y3[q][pk];
+      if (!(u.live >> q & 1)) continue;  // warp-uniform
+      // <E_i, E_j d^dx E_k>: derivative flag set for the advection direction a == 0 (x), a == 2 (z), a == 1 (y: pid + 1)
+      const double x3 = b.X3[((size_t)(u.xi[c] * b.nx + u.xj[a]) * b.nx + xk) * 2 + (a == 0 ? 1 : 0)];
+      const double z3 = b.Z3[((size_t)(u.zi[c] * b.nz + u.zj[a]) * b.nz + zk) * 2 + (a == 2 ? 1 : 0)];
+      const bool alive = ck != 0.0 && x3 != 0.0 && z3 != 0.0;
+      const double y3 = ldg_if(b.Y3 + ((size_t)(u.pi[c] * b.npid + u.pj[a]) * b.npid) + (a == 1 ? 1 : 0) + pk, alive);
+      const double t = alive ? (u.ci[c] * u.cj[a]) * ck * x3 * z3 * y3 : 0.0;
       s -= t;
       mag += fabs(t);
     }
@@ -192,19 +212,20 @@ __device__ __forceinline__ bool entry(const DevBasis& b, const IJ& u, int k, dou
 // Candidate third factors of a pair (i, j).  The Fourier triple averages vanish unless the wavenumber magnitudes of
 // k are |j_i| +- |j_j| in x and |k_i| +- |k_j| in z, so only the modes of at most four (|j|, |k|) groups can
 // contribute; the index set lists the modes of one signed (j, k) contiguously, which makes those candidates a few
-// contiguous ranges of k.  Per pair of groups the host stores the sorted, disjoint ranges; scanning them in order
-// keeps the (i, j, k) order of the output.  (Scanning all m values of k made the O(m^3) selection-rule lookups the
+// short contiguous ranges of k.  Per pair of groups the host stores the candidates as one ascending list (lanes take
+// consecutive list positions: a range per signed (j, k) is only a handful of modes and would leave most of a warp
+// idle); scanning it in order keeps the (i, j, k) order of the output.  (Scanning all m values of k made the O(m^3) selection-rule lookups the
 // whole cost of the assembly: 0.62 s at m = 2962.)
 struct Candidates {
   const int32_t* group;     // [m] group of every mode: |j| * (K + 1) + |k|
-  const int32_t* pair_off;  // [G * G + 1]
-  const int2* ranges;       // [lo, hi)
+  const int32_t* pair_off;  // [G * G + 1] offsets into list
+  const int32_t* list;      // ascending candidate k of every pair of groups
   int G;
 };
 
 // FILL = false: counts[(i-r0)*m + j] = number of kept k;  FILL = true: writes the entries at offs[...]
 template <bool FILL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 n_kernel(DevBasis b, Candidates cd, int r0, int r1, int64_t* __restrict__ counts, const int64_t* __restrict__ offs,
          int64_t* __restrict__ oi, int64_t* __restrict__ oj, int64_t* __restrict__ ok,
          double* __restrict__ oval) {
@@ -220,22 +241,30 @@ n_kernel(DevBasis b, Candidates cd, int r0, int r1, int64_t* __restrict__ counts
     const int64_t base = FILL ? offs[t] : 0;
     if (u.live) {
       const int gp = cd.group[i] * cd.G + cd.group[j];
-      for (int r = cd.pair_off[gp]; r < cd.pair_off[gp + 1]; ++r) {
-        const int2 rg = cd.ranges[r];
-        for (int k0 = rg.x; k0 < rg.y; k0 += 32) {
-          const int k = k0 + lane;
-          double v = 0.0;
-          const bool keep = k < rg.y && entry(b, u, k, v);
-          const unsigned mask = __ballot_sync(0xffffffffu, keep);
-          if (FILL && keep) {
-            const int64_t at = base + n + __popc(mask & ((1u << lane) - 1));
-            oi[at] = i + 1;
-            oj[at] = j + 1;
-            ok[at] = k + 1;
-            oval[at] = v;
-          }
-          n += __popc(mask);
+      const int qe = cd.pair_off[gp + 1];
+      for (int q0 = cd.pair_off[gp]; q0 < qe; q0 += 64) {  // two chunks of 32 candidates, evaluated before either is emitted
+        const int qa = q0 + lane, qb = qa + 32;
+        const int ka = qa < qe ? __ldg(cd.list + qa) : -1, kb = qb < qe ? __ldg(cd.list + qb) : -1;
+        double va = 0.0, vb = 0.0;
+        const bool keepa = ka >= 0 && entry(b, u, ka, va);
+        const bool keepb = kb >= 0 && entry(b, u, kb, vb);
+        const unsigned maska = __ballot_sync(0xffffffffu, keepa), maskb = __ballot_sync(0xffffffffu, keepb);
+        if (FILL && keepa) {
+          const int64_t at = base + n + __popc(maska & ((1u << lane) - 1));
+          oi[at] = i + 1;
+          oj[at] = j + 1;
+          ok[at] = ka + 1;
+          oval[at] = va;
         }
+        n += __popc(maska);
+        if (FILL && keepb) {
+          const int64_t at = base + n + __popc(maskb & ((1u << lane) - 1));
+          oi[at] = i + 1;
+          oj[at] = j + 1;
+          ok[at] = kb + 1;
+          oval[at] = vb;
+        }
+        n += __popc(maskb);
       }
     }
     if (!FILL && lane == 0) counts[t] = n;
@@ -502,6 +531,20 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
     djx.upload(jx.data(), jx.size());
     dkz.upload(kz.data(), kz.size());
     dpid.upload(pid.data(), pid.size());
+    std::vector<double> coefT((size_t)m * 3);
+    std::vector<uint32_t> packT((size_t)m * 3);
+    for (int n = 0; n < m; ++n)
+      for (int c = 0; c < 3; ++c) {
+        const size_t at = (size_t)n * 3 + c;
+        if (jx[at] < 0 || jx[at] >= 1024 || kz[at] < 0 || kz[at] >= 1024 || pid[at] < 0 || pid[at] >= 4096)
+          fail(CA_ERR_UNSUPPORTED, "ca_assemble: J, K < 512 and L < 1024 are required");
+        coefT[(size_t)c * m + n] = coef[at];
+        packT[(size_t)c * m + n] = (uint32_t)jx[at] | ((uint32_t)kz[at] << 10) | ((uint32_t)pid[at] << 20);
+      }
+    DeviceBuffer<double> dcoefT;
+    DeviceBuffer<uint32_t> dpackT;
+    dcoefT.upload(coefT.data(), coefT.size());
+    dpackT.upload(packT.data(), packT.size());
     dX2.upload(T.X2.data(), T.X2.size());
     dZ2.upload(T.Z2.data(), T.Z2.size());
     dX3.upload(T.X3.data(), T.X3.size());
@@ -533,14 +576,14 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
       if (jm > T.J || km > T.K) uniform = false;
       group[n] = jm < 0 ? 0 : jm * ngz + km;
     }
-    std::vector<int32_t> pair_off;
-    std::vector<int2> ranges;
+    std::vector<int32_t> pair_off, list;
     int Geff = G;
     if (!uniform) {
       Geff = 1;
       std::fill(group.begin(), group.end(), 0);
-      pair_off = {0, 1};
-      ranges.push_back(make_int2(0, m));
+      pair_off = {0, m};
+      list.resize((size_t)m);
+      std::iota(list.begin(), list.end(), 0);
     } else {
       std::vector<std::vector<int2>> of_group((size_t)G);  // contiguous index ranges of every group
       for (int n = 0; n < m;) {
@@ -562,21 +605,16 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
           std::vector<int2> rs;
           for (int g : gs) rs.insert(rs.end(), of_group[g].begin(), of_group[g].end());
           std::sort(rs.begin(), rs.end(), [](const int2& x, const int2& y) { return x.x < y.x; });
-          std::vector<int2> merged;
-          for (const int2& r : rs) {
-            if (!merged.empty() && merged.back().y == r.x) merged.back().y = r.y;
-            else merged.push_back(r);
-          }
-          ranges.insert(ranges.end(), merged.begin(), merged.end());
-          pair_off[(size_t)ga * G + gb + 1] = (int32_t)ranges.size();
+          for (const int2& r : rs)
+            for (int k = r.x; k < r.y; ++k) list.push_back(k);
+          pair_off[(size_t)ga * G + gb + 1] = (int32_t)list.size();
         }
     }
-    DeviceBuffer<int32_t> dgroup, dpair_off;
-    DeviceBuffer<int2> dranges;
+    DeviceBuffer<int32_t> dgroup, dpair_off, dlist;
     dgroup.upload(group.data(), group.size());
     dpair_off.upload(pair_off.data(), pair_off.size());
-    dranges.upload(ranges.data(), ranges.size());
-    const Candidates cand{dgroup.ptr, dpair_off.ptr, dranges.ptr, Geff};
+    dlist.upload(list.data(), list.size());
+    const Candidates cand{dgroup.ptr, dpair_off.ptr, dlist.ptr, Geff};
 
     // Device time = the kernels of the two passes (tables + count + scan, then fill).  Buffers whose size is known are
     // allocated before the first event and the output arrays between the two timed spans: cudaMalloc is synchronous
@@ -607,7 +645,7 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
     count_launch();
 
     DevBasis b{m, T.J, T.K, T.npid, 2 * T.J + 1, 2 * T.K + 1, T.alpha, T.gamma, dcoef.ptr, djx.ptr, dkz.ptr, dpid.ptr, dk2.ptr,
-               dX2.ptr, dZ2.ptr, dX3.ptr, dZ3.ptr, dY2.ptr, dY2y.ptr, dY3.ptr};
+               dX2.ptr, dZ2.ptr, dX3.ptr, dZ3.ptr, dY2.ptr, dY2y.ptr, dY3.ptr, dcoefT.ptr, dpackT.ptr};
     const int64_t nij = (int64_t)rows * m;
     if (nij > 0) {
       linear_kernel<<<(unsigned)((nij + 255) / 256), 256>>>(b, r0, r1, h->B.ptr, h->A1.ptr, h->A2.ptr, h->D.ptr);
@@ -618,6 +656,8 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
       int sms = 0;
       CA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
       const unsigned grid = (unsigned)std::min<int64_t>((nij + 7) / 8, (int64_t)sms * 16);
+      // separable path: 128-thread CTAs (92 registers: five CTAs = 20 warps per SM instead of two x eight)
+      const unsigned ngrid = (unsigned)std::min<int64_t>((nij + 3) / 4, (int64_t)sms * 40);
       DeviceBuffer<double> Nd;  // dense path: [rows][m][m] scratch slab
       double thr = 0.0;
       if (dopt.dense) {
@@ -695,7 +735,7 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
         thr = std::max(kAbsZero, kDenseRelZero * gmax);
         dense_compact_kernel<false><<<grid, 256>>>(Nd.ptr, m, r0, r1, thr, counts.ptr, nullptr, nullptr, nullptr, nullptr, nullptr);
       } else {
-        n_kernel<false><<<grid, 256>>>(b, cand, r0, r1, counts.ptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        n_kernel<false><<<ngrid, 128>>>(b, cand, r0, r1, counts.ptr, nullptr, nullptr, nullptr, nullptr, nullptr);
       }
       CA_CUDA(cudaGetLastError());
       count_launch();
@@ -714,7 +754,7 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
         if (dopt.dense)
           dense_compact_kernel<true><<<grid, 256>>>(Nd.ptr, m, r0, r1, thr, nullptr, offs.ptr, h->oi.ptr, h->oj.ptr, h->ok.ptr, h->oval.ptr);
         else
-          n_kernel<true><<<grid, 256>>>(b, cand, r0, r1, nullptr, offs.ptr, h->oi.ptr, h->oj.ptr, h->ok.ptr, h->oval.ptr);
+          n_kernel<true><<<ngrid, 128>>>(b, cand, r0, r1, nullptr, offs.ptr, h->oi.ptr, h->oj.ptr, h->ok.ptr, h->oval.ptr);
         CA_CUDA(cudaGetLastError());
         count_launch();
         CA_CUDA(cudaEventRecord(e3));
