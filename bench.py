@@ -366,7 +366,7 @@ def hbm_case(ca, H, hbm_peak):
     gbs = 16 * m * n / (ms * 1e-3) / 1e9
     path, _, jitlog = model.kernel_path(n)
     return {"workload": "ensemble RHS, 17-mode model (J,K,L=1,1,3), 10^7 states", "bound": "hbm", "kernel": path,
-            "note": "m <= 48: model-specialised straight-line kernel (NVRTC, sm_100a), x in registers",
+            "note": "m <= 48: model-specialised straight-line kernel (NVRTC, sm_100a), states through a per-thread cp.async ring",
             "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
             "evals_per_sec": n / (ms * 1e-3), "kernel_ms": ms, "algorithmic_bytes_per_state": 16 * m}
 

@@ -5,9 +5,14 @@
 // (layout [mode][state], state slot XOR-swizzled by mode parity so that the four modes a k-step
 // touches fall into different bank halves).  The operator is streamed from L2 as row tiles
 // (pack.h): per k-step a warp forms 4 pairs x 8*MT states of products u_a*w_b -> A fragments,
-// loads NT B fragments of operator values (coalesced 256 B each, prefetched 4 k-steps ahead) and
-// issues MT*NT DMMAs.  The 8 warps of the CTA split the k-steps of a tile and their partial
-// accumulators are summed in a fixed order through shared memory: no atomics, bit-reproducible.
+// loads NT B fragments of operator values (coalesced 256 B each) and issues MT*NT DMMAs.
+// Three kernels share these k-steps:
+//   bilinear_warptile_kernel  whole tiles per warp (LPT schedule from the packer): no reduction, no per-tile barrier;
+//   bilinear_batched_kernel   the warps of a CTA split every tile's k-steps and sum their partial accumulators in a
+//                             fixed order through shared memory (unbalanced tile schedules);
+//   bilinear_windowed_kernel  large m: only the rows of the state tile that a window of k-steps touches are resident,
+//                             everything streams through one cp.async pipeline.
+// No atomics anywhere: results are bit-reproducible.
 #pragma once
 #include <cuda_runtime.h>
 
