@@ -81,6 +81,24 @@ def test_pack_roundtrip_random(seed):
             assert st["mismatches"] == 0 and st["max_window_modes"] <= wm
 
 
+def test_pack_sort_paths_above_the_small_input_cutoff():
+    """>= 65536 terms: (a) terms in random order (no runs of equal output row: element-wise counting sort),
+    (b) whole rows in shuffled order (runs moved as blocks on worker threads).  Both must reproduce the input."""
+    rng = np.random.default_rng(11)
+    m, nnz = 60, 100_000
+    ijk = rng.integers(1, m + 1, size=(nnz, 3))
+    val = rng.integers(1, 9, size=nnz).astype(np.float64)   # duplicates abound: small integers sum exactly in any order
+    for sym in (1, 0):
+        assert pack_stats(ijk, val, m, sym)["mismatches"] == 0
+    order = np.lexsort((ijk[:, 2], ijk[:, 1], ijk[:, 0]))                 # (i, j, k) order ...
+    ijk_s, val_s = ijk[order], val[order]
+    rows = [np.flatnonzero(ijk_s[:, 0] == i) for i in rng.permutation(np.arange(1, m + 1))]
+    perm = np.concatenate(rows)                                           # ... with the rows shuffled as blocks
+    for sym in (1, 0):
+        for wm in (0, 24):
+            assert pack_stats(ijk_s[perm], val_s[perm], m, sym, wm)["mismatches"] == 0
+
+
 def test_pack_fill_at_307(nagata_H):
     """The clustering finds the wavenumber/parity classes: >= 75 % of the executed FMAs are real."""
     from oracle.basis import basisIndices
