@@ -255,46 +255,149 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
   }
 
   tm.lap("cluster");
+  if (getenv("CA_TIMING") && clusters.size() > 8) {
+    int hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // rows per cluster: 1-8, 9-16, 17-24, ...
+    for (auto& cl : clusters) hist[std::min<size_t>(7, (cl.size() - 1) / 8)]++;
+    fprintf(stderr, "[ca timing] pack_terms: %zu row clusters; sizes 1-8: %d, 9-16: %d, 17-24: %d, 25-32: %d, more: %d\n",
+            clusters.size(), hist[0], hist[1], hist[2], hist[3], hist[4] + hist[5] + hist[6] + hist[7]);
+  }
   // ---- split clusters into tiles of <= 8*nt_max rows, lay out fragments
   // (P here is the tile's own container: tiles are laid out independently on worker threads and appended in order)
-  auto emit_tile = [&rows, nin, window_modes](const std::vector<int32_t>& trows, PackedHost& P) {
+  // Blocked pair order (see emit_tile) for whole-tile packs: +1 % on the 307-mode ensemble kernel (67.9 -> 67.2 ms).
+  // Windowed packs keep the a-major order: blocks make windows of fewer k-steps (147 instead of 197 at m = 999), and
+  // the per-window barrier and the shorter per-warp shares cost more than the saved shared-memory wavefronts bring
+  // (m = 999: RHS 13.8 vs 13.3 ms, JVP 19.7 vs 18.3 ms).  CA_PACK_AMAJOR / CA_PACK_BLOCKED force either.
+  const bool blocked = getenv("CA_PACK_BLOCKED") != nullptr || (window_modes <= 0 && getenv("CA_PACK_AMAJOR") == nullptr);
+  auto emit_tile = [&rows, nin, window_modes, blocked](const std::vector<int32_t>& trows, PackedHost& P) {
     TileDesc T{};
     T.nrows = (int32_t)trows.size();
     T.nt = (T.nrows + 7) / 8;
     std::vector<uint64_t> U;
     for (int32_t r : trows) U = U.empty() ? rows[r].keys : union_of(U, rows[r].keys);
     T.npairs = (int32_t)U.size();
-    T.ks_begin = (int32_t)(P.pairs.size() / 4);
-    T.vals_off = (int64_t)P.vals.size();
-    T.rows_off = (int32_t)P.rows.size();
+    T.ks_begin = 0;
+    T.vals_off = 0;
+    T.rows_off = 0;
     for (int n = 0; n < 8 * T.nt; ++n) P.rows.push_back(n < T.nrows ? trows[n] : -1);
     const uint32_t ONE = (uint32_t)(nin - 1);
+    const int cap = window_modes > 0 ? window_modes - 1 : 1 << 30;  // leave room for the padding pseudo mode
+    const size_t max_pairs = window_modes > 0 ? (size_t)4 * kWindowMaxKs : ~(size_t)0;
+
+    // ---- emission order of the pairs, as SEGMENTS (units that a window never splits).
+    // Blocked segments first: first factors whose second-factor lists coincide (the modes of one wavenumber group and
+    // parity all pair with the same modes) are taken four at a time, and a k-step holds (a0,b), (a1,b), (a2,b), (a3,b)
+    // for one b: the four a stay in registers over the whole run of b (kSameA), and the four lanes of a state read the
+    // SAME second factor -- one shared-memory wavefront instead of two per load.  A segment is (quads of a) x (chunk
+    // of b), sized so that it fits a window: q quads and nb second factors touch only 4q + nb modes for q * nb k-steps.
+    // What does not fit the pattern (first factors left over, triangular parts) follows a-major, four consecutive
+    // pairs per k-step as before.
+    struct Seg { std::vector<size_t> idx; };
+    std::vector<Seg> segs;
+    std::vector<char> taken(U.size(), 0);
+    if (blocked && U.size() >= 16 && cap >= 11) {
+      // runs of equal first factor
+      struct Run { uint32_t a; size_t b, e; uint64_t sig; };
+      std::vector<Run> runs;
+      for (size_t r = 0; r < U.size();) {
+        size_t e = r;
+        const uint32_t a = (uint32_t)(U[r] / nin);
+        uint64_t sig = 0x9e3779b97f4a7c15ull;
+        while (e < U.size() && (uint32_t)(U[e] / nin) == a) sig = mix64(sig ^ (U[e++] % nin));
+        runs.push_back({a, r, e, sig});
+        r = e;
+      }
+      std::vector<size_t> order(runs.size());
+      std::iota(order.begin(), order.end(), 0);
+      std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+        if (runs[x].e - runs[x].b != runs[y].e - runs[y].b) return runs[x].e - runs[x].b > runs[y].e - runs[y].b;
+        return runs[x].sig < runs[y].sig;
+      });
+      auto same_list = [&](const Run& x, const Run& y) {
+        if (x.e - x.b != y.e - y.b || x.sig != y.sig) return false;
+        for (size_t q = 0; q < x.e - x.b; ++q)
+          if (U[x.b + q] % nin != U[y.b + q] % nin) return false;
+        return true;
+      };
+      for (size_t c0 = 0; c0 < order.size();) {
+        size_t c1 = c0 + 1;
+        while (c1 < order.size() && same_list(runs[order[c0]], runs[order[c1]])) ++c1;
+        const size_t nq = (c1 - c0) / 4, nb = runs[order[c0]].e - runs[order[c0]].b;
+        if (nq >= 1 && nb >= 2) {
+          std::vector<size_t> cls(order.begin() + (ptrdiff_t)c0, order.begin() + (ptrdiff_t)(c0 + 4 * nq));
+          std::sort(cls.begin(), cls.end());  // ascending first factor
+          // window shape: nbc second factors x qw quads with 4 qw + nbc <= cap and qw * nbc <= kWindowMaxKs
+          size_t nbc = nb, qw = nq;
+          if (window_modes > 0) {  // near-equal chunks of <= min(cap / 2, kWindowMaxKs / 4) second factors
+            const size_t lim = std::max<size_t>(1, std::min<size_t>((size_t)cap / 2, (size_t)kWindowMaxKs / 4));
+            const size_t nchunks = (nb + lim - 1) / lim;
+            nbc = (nb + nchunks - 1) / nchunks;
+            qw = std::max<size_t>(1, std::min<size_t>({nq, ((size_t)cap - nbc) / 4, (size_t)kWindowMaxKs / nbc}));
+          }
+          for (size_t b0 = 0; b0 < nb; b0 += nbc)
+            for (size_t q0 = 0; q0 < nq; q0 += qw) {
+              Seg sg;
+              for (size_t q = q0; q < std::min(nq, q0 + qw); ++q)
+                for (size_t bb = b0; bb < std::min(nb, b0 + nbc); ++bb)
+                  for (int c = 0; c < 4; ++c) {
+                    const size_t at = runs[cls[4 * q + c]].b + bb;
+                    sg.idx.push_back(at);
+                    taken[at] = 1;
+                  }
+              segs.push_back(std::move(sg));
+            }
+        }
+        c0 = c1;
+      }
+    }
+    {  // a-major remainder: runs of equal first factor, split where a run alone exceeds a window
+      const size_t run_cap = window_modes > 0 ? (size_t)std::max(cap - 1, 1) : ~(size_t)0;
+      for (size_t r = 0; r < U.size();) {
+        size_t e = r;
+        const uint32_t a = (uint32_t)(U[r] / nin);
+        Seg sg;
+        while (e < U.size() && (uint32_t)(U[e] / nin) == a) {
+          if (!taken[e]) {
+            if (sg.idx.size() == run_cap) {
+              segs.push_back(std::move(sg));
+              sg = Seg();
+            }
+            sg.idx.push_back(e);
+          }
+          ++e;
+        }
+        if (!sg.idx.empty()) segs.push_back(std::move(sg));
+        r = e;
+      }
+    }
+
+    for (char t : taken) P.blocked_pairs += t;
     // position of every pair of U in the emitted (padded) pair sequence
     std::vector<int32_t> where(U.size());
-    if (window_modes <= 0) {
-      T.nks = (T.npairs + 3) / 4;
-      for (int k = 0; k < 4 * T.nks; ++k) {
-        if (k < T.npairs) {
-          where[k] = k;
-          P.pairs.push_back((uint32_t)(U[k] / nin) | ((uint32_t)(U[k] % nin) << 16));
-        } else {
-          P.pairs.push_back(ONE | (ONE << 16));
-        }
-      }
-      for (int ks = 1; ks < T.nks; ++ks) {
-        uint32_t* cur = &P.pairs[((size_t)T.ks_begin + ks) * 4];
+    auto mark_same_a = [&](size_t first_word, int nks) {
+      for (int ks = 1; ks < nks; ++ks) {
+        uint32_t* cur = &P.pairs[first_word + (size_t)ks * 4];
         const uint32_t* prev = cur - 4;
         bool same = true;
         for (int c = 0; c < 4; ++c) same = same && ((cur[c] & 0x7fffu) == (prev[c] & 0x7fffu));
         if (same)
           for (int c = 0; c < 4; ++c) cur[c] |= 0x8000u;
       }
+    };
+    if (window_modes <= 0) {
+      T.nks = (T.npairs + 3) / 4;
+      int k = 0;
+      for (const Seg& sg : segs)
+        for (size_t at : sg.idx) {
+          where[at] = k++;
+          P.pairs.push_back((uint32_t)(U[at] / nin) | ((uint32_t)(U[at] % nin) << 16));
+        }
+      for (; k < 4 * T.nks; ++k) P.pairs.push_back(ONE | (ONE << 16));
+      mark_same_a(0, T.nks);
     } else {
-      // ---- windows: runs of equal first factor are appended while the window's mode set stays small
-      const int tile_index = (int)P.tiles.size();
-      std::vector<uint32_t> wmodes;            // sorted global modes of the open window
-      std::vector<size_t> wpairs;              // indices into U
-      int emitted = 0;                         // pairs emitted so far in this tile (incl. padding)
+      // ---- windows: segments are appended while the window's mode set and k-step count stay within the caps
+      std::vector<uint32_t> wmodes;  // sorted global modes of the open window
+      std::vector<size_t> wpairs;    // indices into U
+      int emitted = 0;               // pairs emitted so far in this tile (incl. padding)
       auto close_window = [&]() {
         if (wpairs.empty()) return;
         const bool pad = wpairs.size() % 4 != 0;
@@ -303,11 +406,11 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
           std::sort(wmodes.begin(), wmodes.end());
         }
         WindowDesc W{};
-        W.ks_begin = T.ks_begin + emitted / 4;
+        W.ks_begin = emitted / 4;
         W.nks = (int32_t)((wpairs.size() + 3) / 4);
         W.modes_off = (int32_t)P.modes.size();
         W.nmodes = (int32_t)wmodes.size();
-        W.tile = tile_index;
+        W.tile = 0;
         W.last = 0;
         for (uint32_t g : wmodes) P.modes.push_back((int32_t)g);
         auto local = [&](uint32_t g) { return (uint32_t)(std::lower_bound(wmodes.begin(), wmodes.end(), g) - wmodes.begin()); };
@@ -321,51 +424,30 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
             P.pairs.push_back(local(ONE) | (local(ONE) << 16));
           }
         }
-        for (int ks = 1; ks < W.nks; ++ks) {
-          uint32_t* cur = &P.pairs[first_word + (size_t)ks * 4];
-          const uint32_t* prev = cur - 4;
-          bool same = true;
-          for (int c = 0; c < 4; ++c) same = same && ((cur[c] & 0x7fffu) == (prev[c] & 0x7fffu));
-          if (same)
-            for (int c = 0; c < 4; ++c) cur[c] |= 0x8000u;
-        }
+        mark_same_a(first_word, W.nks);
         emitted += W.nks * 4;
         P.max_window_modes = std::max(P.max_window_modes, W.nmodes);
         P.windows.push_back(W);
         wmodes.clear();
         wpairs.clear();
       };
-      auto merged_size = [&](const std::vector<uint32_t>& add) {
+      for (const Seg& sg : segs) {
+        std::vector<uint32_t> add;
+        for (size_t at : sg.idx) {
+          add.push_back((uint32_t)(U[at] / nin));
+          add.push_back((uint32_t)(U[at] % nin));
+        }
+        std::sort(add.begin(), add.end());
+        add.erase(std::unique(add.begin(), add.end()), add.end());
         std::vector<uint32_t> u;
         std::set_union(wmodes.begin(), wmodes.end(), add.begin(), add.end(), std::back_inserter(u));
-        return u;
-      };
-      const int cap = window_modes - 1;  // leave room for the padding pseudo mode
-      for (size_t r = 0; r < U.size();) {
-        size_t e = r;
-        const uint32_t a = (uint32_t)(U[r] / nin);
-        while (e < U.size() && (uint32_t)(U[e] / nin) == a) ++e;
-        // the run [r, e) shares its first factor; split it if it alone exceeds the cap
-        for (size_t q = r; q < e;) {
-          size_t q1 = std::min(e, q + (size_t)std::max(cap - 1, 1));
-          std::vector<uint32_t> add{a};
-          for (size_t z = q; z < q1; ++z) add.push_back((uint32_t)(U[z] % nin));
-          std::sort(add.begin(), add.end());
-          add.erase(std::unique(add.begin(), add.end()), add.end());
-          std::vector<uint32_t> u = merged_size(add);
-          if ((int)u.size() > cap && !wpairs.empty()) {
-            close_window();
-            u = add;
-          }
-          if (wpairs.size() + (q1 - q) > (size_t)4 * kWindowMaxKs) {  // pair words of a window are staged in smem
-            close_window();
-            u = add;
-          }
-          wmodes = std::move(u);
-          for (size_t z = q; z < q1; ++z) wpairs.push_back(z);
-          q = q1;
+        // (blocked segments are whole k-steps and all come before the a-major remainder, so they stay aligned)
+        if (!wpairs.empty() && ((int)u.size() > cap || wpairs.size() + sg.idx.size() > max_pairs)) {
+          close_window();
+          u = add;
         }
-        r = e;
+        wmodes = std::move(u);
+        wpairs.insert(wpairs.end(), sg.idx.begin(), sg.idx.end());
       }
       close_window();
       if (emitted > 0) P.windows.back().last = 1;
@@ -428,6 +510,7 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
       P.max_window_modes = std::max(P.max_window_modes, Q.max_window_modes);
       P.padded_fma += Q.padded_fma;
       P.pair_products += Q.pair_products;
+      P.blocked_pairs += Q.blocked_pairs;
       Q = PackedHost();  // free the tile's copy
     }
   }
@@ -540,6 +623,9 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
       P.stream_layout = true;
     }
   }
+  if (getenv("CA_TIMING") && P.pair_products > 0)
+    fprintf(stderr, "[ca timing] pack_terms: %.1f %% of the pair products in (4 first factors) x (second factor) blocks\n",
+            100.0 * (double)P.blocked_pairs / (double)P.pair_products);
   tm.lap("schedule");
   {  // the row lists and the term list are gigabytes at m ~ 3000: release them here, inside the timed phases
     std::vector<Row>().swap(rows);

@@ -76,6 +76,7 @@ struct PackedHost {
   int64_t npairs_distinct = 0;  // distinct (a,b) over the whole operator
   int64_t padded_fma = 0;       // FMAs the tiles execute per state (incl. padding)
   int64_t pair_products = 0;    // pair products formed per state (sum over tiles)
+  int64_t blocked_pairs = 0;    // of these, in (4 first factors) x (one second factor) k-steps
 };
 
 // In-place sort by (i, a, b): counting sort by output row, then per-row sorts on worker threads.
