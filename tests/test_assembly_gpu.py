@@ -53,6 +53,37 @@ def test_small_models_against_float_restatement_and_exact(ca, nagata_H, JKL, nor
     assert len(got) <= ref.N.nnz
 
 
+@pytest.mark.parametrize("case", ["no-symmetry", "one-generator", "nagata-wide-z", "nagata-alpha-gamma"])
+def test_candidate_pruning_changes_nothing(ca, case, monkeypatch):
+    """The assembly scans only the third factors of the wavenumber groups that the Fourier selection rules allow.  On
+    bases outside the Nagata subspace too (no symmetry at all, a single generator, unequal J and K, other alpha and
+    gamma) the result must be bit-identical to scanning every k, and agree with the float restatement of the reference."""
+    from oracle.basis import basisIndices as ref_indices
+    from oracle.fastfloat import assemble_N_float
+    sx, sy, sz, tx, tz = ca.halfbox_symmetries()
+    alpha, gamma = (1.0, 2.0)
+    if case == "no-symmetry":
+        ijkl = ca.basisIndices(1, 1, 2)
+    elif case == "one-generator":
+        ijkl = ca.basisIndices(2, 1, 3, [sx * sy * sz])
+    elif case == "nagata-wide-z":
+        ijkl = ca.basisIndices(1, 3, 4, lib_H(ca))
+    else:
+        ijkl, alpha, gamma = ca.basisIndices(2, 2, 4, lib_H(ca)), 0.75, 1.625
+    slab = ca.AssemblySlab(alpha, gamma, ijkl)
+    ijk, val = slab.coo_host()
+    B, A1, A2 = slab.linear_host()
+    monkeypatch.setenv("CA_ASSEMBLE_NOPRUNE", "1")
+    full = ca.AssemblySlab(alpha, gamma, ijkl)
+    ijk_f, val_f = full.coo_host()
+    assert np.array_equal(ijk, ijk_f) and np.array_equal(val, val_f)
+    for X, Y in zip((B, A1, A2), full.linear_host()):
+        assert np.array_equal(X, Y)
+    rijk, rval = assemble_N_float(alpha, gamma, np.asarray(ijkl))
+    assert np.array_equal(ijk, rijk)
+    assert maxrel(val, rval) < TOL
+
+
 def test_nnz_of_the_baseline_configs(ca):
     H = lib_H(ca)
     for JKL, m, nnz in [((1, 1, 3), 17, 396), ((1, 2, 3), 27, 1500), ((2, 2, 3), 44, 5654)]:
