@@ -120,6 +120,30 @@ def test_small_model_large_ensemble_uses_specialised_kernel(ca, nagata_H):
         assert relerr(dev.f(X, 200.0)[:100], small) < 1e-14
 
 
+def test_specialised_kernel_padded_leading_dimension_and_ragged_sizes(ca, nagata_H):
+    """The generated kernel's per-thread cp.async ring with a padded leading dimension on both sides and ensemble
+    sizes that are not multiples of the CTA width: same numbers as the contiguous call, nothing written past the end."""
+    import torch
+    from oracle.model import ODEModel
+    ref = ODEModel(1.0, 2.0, 1, 2, 3, nagata_H)
+    dev = ca.ModelOperators(ref.B, ref.A1, ref.A2, ref.N.ijk, ref.N.val)
+    m = dev.m
+    rng = np.random.default_rng(17)
+    for n in (4096, 4097, 9999):
+        X = 0.1 * rng.standard_normal((n, m))
+        ld = n + 7
+        xin = torch.zeros((m, ld), dtype=torch.float64, device="cuda")
+        xin[:, :n] = torch.from_numpy(X.T)
+        out = torch.full((m, ld), 123.0, dtype=torch.float64, device="cuda")
+        got = dev.f(xin.t()[:n], 200.0, out=out.t()[:n])
+        assert dev.kernel_path(n)[0] == "nvrtc_straight_line"
+        want = dev.f(X, 200.0)
+        assert np.array_equal(got.cpu().numpy(), want)
+        assert torch.all(out[:, n:] == 123.0)
+        sample = [0, n // 2, n - 1]
+        assert relerr(want[sample], np.stack([ref.f(X[s], 200.0) for s in sample])) < 1e-13 * max(1.0, np.linalg.cond(ref.B) / 10)
+
+
 def test_full_size_ensemble_properties(ca, nagata_H):
     """BASELINE.json configs[2] at full size (10^6 states, 307 modes): size-independent properties -- results do not
     depend on where a state sits in the ensemble (bit-exact under permutation), the host-pointer path equals the
