@@ -227,6 +227,7 @@ struct Candidates {
   int G, S;
 };
 
+// Two-pass form, kept for candidate sets too large for a scratch slot each (no pruning: every k is a candidate).
 // FILL = false: counts[(i-r0)*m + j] = number of kept k;  FILL = true: writes the entries at offs[...]
 template <bool FILL>
 __global__ void __launch_bounds__(128)
@@ -272,6 +273,80 @@ n_kernel(DevBasis b, Candidates cd, int r0, int r1, int64_t* __restrict__ counts
       }
     }
     if (!FILL && lane == 0) counts[t] = n;
+  }
+}
+
+// Every candidate is evaluated ONCE: the kept entries of a pair (i, j) are written, compacted, into the pair's segment
+// of a scratch array (its offset is the running sum of the pairs' candidate counts, known without evaluating anything),
+// counts[(i-r0)*m + j] gets their number; after the scan of the counts a copy kernel moves the segments to their final
+// places in (i, j, k) order.  (Two evaluating passes -- count, then fill -- cost twice the table lookups.)
+__global__ void __launch_bounds__(256)
+cand_count_kernel(Candidates cd, int m, int r0, int64_t npairs, int64_t* __restrict__ cnum) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npairs) return;
+  const int i = r0 + (int)(t / m), j = (int)(t % m);
+  const int gp = ((cd.group[i] * cd.G + cd.group[j]) * cd.S + cd.pclass[i]) * cd.S + cd.pclass[j];
+  cnum[t] = cd.pair_off[gp + 1] - cd.pair_off[gp];
+}
+
+__global__ void __launch_bounds__(128)
+n_eval_kernel(DevBasis b, Candidates cd, int r0, int r1, const int64_t* __restrict__ coffs, int64_t* __restrict__ counts,
+              int32_t* __restrict__ tk, double* __restrict__ tv) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t npairs = (int64_t)(r1 - r0) * b.m;
+  for (int64_t t = warp; t < npairs; t += nwarps) {
+    const int i = r0 + (int)(t / b.m), j = (int)(t % b.m);
+    IJ u;
+    load_ij(b, i, j, u);
+    int64_t n = 0;
+    const int64_t base = coffs[t];
+    if (u.live) {
+      const int gp = ((cd.group[i] * cd.G + cd.group[j]) * cd.S + cd.pclass[i]) * cd.S + cd.pclass[j];
+      const int qe = cd.pair_off[gp + 1];
+      for (int q0 = cd.pair_off[gp]; q0 < qe; q0 += 64) {  // two chunks of 32 candidates, evaluated before either is emitted
+        const int qa = q0 + lane, qb = qa + 32;
+        const int ka = qa < qe ? __ldg(cd.list + qa) : -1, kb = qb < qe ? __ldg(cd.list + qb) : -1;
+        double va = 0.0, vb = 0.0;
+        const bool keepa = ka >= 0 && entry(b, u, ka, va);
+        const bool keepb = kb >= 0 && entry(b, u, kb, vb);
+        const unsigned maska = __ballot_sync(0xffffffffu, keepa), maskb = __ballot_sync(0xffffffffu, keepb);
+        if (keepa) {
+          const int64_t at = base + n + __popc(maska & ((1u << lane) - 1));
+          tk[at] = ka;
+          tv[at] = va;
+        }
+        n += __popc(maska);
+        if (keepb) {
+          const int64_t at = base + n + __popc(maskb & ((1u << lane) - 1));
+          tk[at] = kb;
+          tv[at] = vb;
+        }
+        n += __popc(maskb);
+      }
+    }
+    if (lane == 0) counts[t] = n;
+  }
+}
+
+// one warp per pair (i, j): its kept entries from the scratch segment to offs[t] of the output arrays
+__global__ void __launch_bounds__(256)
+n_copy_kernel(int m, int r0, int64_t npairs, const int64_t* __restrict__ coffs, const int64_t* __restrict__ offs,
+              const int32_t* __restrict__ tk, const double* __restrict__ tv, int64_t* __restrict__ oi,
+              int64_t* __restrict__ oj, int64_t* __restrict__ ok, double* __restrict__ oval) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t t = warp; t < npairs; t += nwarps) {
+    const int64_t dst = offs[t], n = offs[t + 1] - dst, src = coffs[t];
+    const int64_t i1 = r0 + t / m + 1, j1 = t % m + 1;
+    for (int64_t e = lane; e < n; e += 32) {
+      oi[dst + e] = i1;
+      oj[dst + e] = j1;
+      ok[dst + e] = (int64_t)tk[src + e] + 1;
+      oval[dst + e] = tv[src + e];
+    }
   }
 }
 
@@ -692,6 +767,34 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
       CA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.ptr, offs.ptr, (int)(nij_pre + 1)));
       tmp.alloc(tmp_bytes);
     }
+    // separable path: scratch for the single evaluating pass -- one slot per candidate, counted on the host from the
+    // list lengths (modes per (group, parity class) x list length of the class pair)
+    bool single_pass = false;
+    DeviceBuffer<int64_t> cnum, coffs;
+    DeviceBuffer<int32_t> tk;
+    DeviceBuffer<double> tv;
+    if (nij_pre > 0 && !dopt.dense) {
+      const int Sx = uniform ? S : 1;
+      std::vector<int64_t> members((size_t)Geff * Sx, 0);
+      for (int n = 0; n < m; ++n) members[(size_t)group[n] * Sx + pclass[n]]++;
+      int64_t ncand = 0;
+      for (int i = r0; i < r1; ++i) {
+        const size_t ci = (size_t)group[i] * Sx + pclass[i];
+        for (int gb = 0; gb < Geff; ++gb)
+          for (int sj = 0; sj < Sx; ++sj) {
+            const size_t gp = (((size_t)group[i] * Geff + gb) * Sx + pclass[i]) * Sx + sj;
+            ncand += members[(size_t)gb * Sx + sj] * (int64_t)(pair_off[gp + 1] - pair_off[gp]);
+          }
+        (void)ci;
+      }
+      single_pass = ncand * 12 <= ((int64_t)16 << 30);  // otherwise: two evaluating passes, no scratch
+      if (single_pass) {
+        cnum.alloc((size_t)nij_pre + 1);
+        coffs.alloc((size_t)nij_pre + 1);
+        tk.alloc((size_t)std::max<int64_t>(ncand, 1));
+        tv.alloc((size_t)std::max<int64_t>(ncand, 1));
+      }
+    }
     cudaEvent_t e0, e1, e2, e3;
     CA_CUDA(cudaEventCreate(&e0));
     CA_CUDA(cudaEventCreate(&e1));
@@ -793,8 +896,16 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
         CA_CUDA(cudaMemcpy(&gmax, dmax.ptr, sizeof(double), cudaMemcpyDeviceToHost));
         thr = std::max(kAbsZero, kDenseRelZero * gmax);
         dense_compact_kernel<false><<<grid, 256>>>(Nd.ptr, m, r0, r1, thr, counts.ptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-      } else {
+      } else if (!single_pass) {
         n_kernel<false><<<ngrid, 128>>>(b, cand, r0, r1, counts.ptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+      } else {
+        CA_CUDA(cudaMemsetAsync(cnum.ptr + nij, 0, sizeof(int64_t)));
+        cand_count_kernel<<<(unsigned)((nij + 255) / 256), 256>>>(cand, m, r0, nij, cnum.ptr);
+        CA_CUDA(cudaGetLastError());
+        count_launch();
+        CA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.ptr, tmp_bytes, cnum.ptr, coffs.ptr, (int)(nij + 1)));
+        count_launch();
+        n_eval_kernel<<<ngrid, 128>>>(b, cand, r0, r1, coffs.ptr, counts.ptr, tk.ptr, tv.ptr);
       }
       CA_CUDA(cudaGetLastError());
       count_launch();
@@ -812,8 +923,11 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
         CA_CUDA(cudaEventRecord(e2));
         if (dopt.dense)
           dense_compact_kernel<true><<<grid, 256>>>(Nd.ptr, m, r0, r1, thr, nullptr, offs.ptr, h->oi.ptr, h->oj.ptr, h->ok.ptr, h->oval.ptr);
-        else
+        else if (!single_pass)
           n_kernel<true><<<ngrid, 128>>>(b, cand, r0, r1, nullptr, offs.ptr, h->oi.ptr, h->oj.ptr, h->ok.ptr, h->oval.ptr);
+        else
+          n_copy_kernel<<<(unsigned)std::min<int64_t>((nij + 7) / 8, (int64_t)sms * 32), 256>>>(
+              m, r0, nij, coffs.ptr, offs.ptr, tk.ptr, tv.ptr, h->oi.ptr, h->oj.ptr, h->ok.ptr, h->oval.ptr);
         CA_CUDA(cudaGetLastError());
         count_launch();
         CA_CUDA(cudaEventRecord(e3));
