@@ -31,7 +31,7 @@ struct ca_bilinear {
   DevicePack& ordered() {
     if (!ord) {
       ord.reset(new DevicePack);
-      ord->upload(pack_terms(coo, (int32_t)m, /*symmetric=*/false, kNtMax, window_modes_for((int32_t)m)));
+      ord->upload(pack_terms(coo, (int32_t)m, /*symmetric=*/false, nt_max_for(window_modes_for((int32_t)m)), window_modes_for((int32_t)m)));
     }
     return *ord;
   }
@@ -138,7 +138,7 @@ int32_t ca_bilinear_create(const int64_t* ijk, const double* val, int64_t nnz, i
     }
     require_device();
     CA_CUDA(cudaGetDevice(&h->device));
-    h->sym.upload(pack_terms(h->coo, (int32_t)m, /*symmetric=*/true, kNtMax, window_modes_for((int32_t)m)));
+    h->sym.upload(pack_terms(h->coo, (int32_t)m, /*symmetric=*/true, nt_max_for(window_modes_for((int32_t)m)), window_modes_for((int32_t)m)));
     *out = h.release();
   });
 }
@@ -271,7 +271,7 @@ extern "C" int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64
     std::vector<Term> coo((size_t)nnz);
     for (int64_t r = 0; r < nnz; ++r)
       coo[(size_t)r] = Term{(int32_t)(ijk[r] - 1), (int32_t)(ijk[r + nnz] - 1), (int32_t)(ijk[r + 2 * nnz] - 1), val[r]};
-    PackedHost P = pack_terms(coo, (int32_t)m, symmetric != 0, kNtMax, window_modes);
+    PackedHost P = pack_terms(coo, (int32_t)m, symmetric != 0, nt_max_for(window_modes), window_modes);
     // expected: merged terms
     struct K { int32_t i, a, b; double v; };
     auto less = [](const K& x, const K& y) {
@@ -363,7 +363,7 @@ extern "C" int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64
           if (t < 0 || t >= (int32_t)P.tiles.size()) { ++bad; continue; }
           seen[(size_t)t]++;
           const bool first_part = q < P.sched_off[w] + P.sched_nt2[w];
-          bad += first_part != (P.tiles[(size_t)t].nt == 2);
+          bad += first_part != (P.tiles[(size_t)t].nt >= 2);  // (three n-tiles only occur in windowed packs, which do not use the schedule)
           (P.tiles[(size_t)t].nt == 2 ? ks2 : ks1) += P.tiles[(size_t)t].nks;
         }
         if (P.stream_layout) bad += ks2 != P.sched_ks2[w] || ks1 != P.sched_ks1[w];

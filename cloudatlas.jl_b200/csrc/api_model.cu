@@ -317,7 +317,7 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
       for (int i = 0; i < m; ++i)
         if (hL1[i + (size_t)m * j] != 0.0 || hL2[i + (size_t)m * j] != 0.0) all.push_back(Term{i, j, m, 1.0});
     tm.lap("term list");
-    PackedHost P = pack_terms(std::move(all), m, /*symmetric=*/true, kNtMax, window_modes_for(m));
+    PackedHost P = pack_terms(std::move(all), m, /*symmetric=*/true, nt_max_for(window_modes_for(m)), window_modes_for(m));
     h->qterms = std::move(qterms);
     tm.lap("pack");
     std::vector<int64_t> pos;
@@ -581,7 +581,7 @@ extern "C" int32_t ca_model_cnab2_batched_dev(ca_model* h, const double* dX0, in
         h->nraw_stream.build(h->ncoo, m, true);
         h->nraw_stream_built = true;
       } else {
-        h->nraw.upload(pack_terms(h->ncoo, m, true, kNtMax, window_modes_for(m)));
+        h->nraw.upload(pack_terms(h->ncoo, m, true, nt_max_for(window_modes_for(m)), window_modes_for(m)));
         h->nraw_built = true;
         if (!batched_fits(h->nraw, MODE_QUAD) && !h->nraw_stream_built) {
           h->nraw_stream.build(h->ncoo, m, true);
@@ -613,7 +613,7 @@ extern "C" int32_t ca_model_cnab2_batched_dev(ca_model* h, const double* dX0, in
           if (M2[i + (size_t)m * j] != 0.0) lin.push_back(Term{i, m + j, 2 * m, M2[i + (size_t)m * j]});
         }
       h->cn_lin_stream.build_rect(lin, m, 2 * m);
-      h->cn_lin.upload(pack_terms(std::move(lin), m, true, kNtMax, window_modes_for(2 * m), 2 * m));
+      h->cn_lin.upload(pack_terms(std::move(lin), m, true, nt_max_for(window_modes_for(2 * m)), window_modes_for(2 * m), 2 * m));
       h->cn_R = R;
       h->cn_dt = dt;
       h->cn_built = true;
@@ -673,7 +673,7 @@ extern "C" int32_t ca_model_set_observables(ca_model* h, const double* shear, co
       for (int i = 0; i < m; ++i)
         if (D[i + (size_t)m * j] != 0.0) t.push_back(Term{1, i, j, D[i + (size_t)m * j]});
     h->obs_stream.build_rect(t, 2, m);
-    h->obs.upload(pack_terms(std::move(t), 2, true, kNtMax, window_modes_for(m), m));
+    h->obs.upload(pack_terms(std::move(t), 2, true, nt_max_for(window_modes_for(m)), window_modes_for(m), m));
     h->obs_set = true;
   });
 }

@@ -22,8 +22,11 @@ void DevicePack::upload(const PackedHost& P) {
   window_modes = P.window_modes;
   max_window_modes = P.max_window_modes;
   nwin = (int32_t)P.windows.size();
-  nwin_nt2 = 0;
-  for (const WindowDesc& W : P.windows) nwin_nt2 += P.tiles[W.tile].nt == 2;
+  nwin_nt3 = nwin_nt2 = 0;
+  for (const WindowDesc& W : P.windows) {
+    nwin_nt3 += P.tiles[W.tile].nt == 3;
+    nwin_nt2 += P.tiles[W.tile].nt == 2;
+  }
   windows.upload(P.windows.data(), P.windows.size());
   modes.upload(P.modes.data(), P.modes.size());
   sched.upload(P.sched.data(), P.sched.size());
@@ -164,6 +167,8 @@ int batched_variant(const DevicePack& op) {
   return op.stream_layout && op.sched_imbalance <= kMaxSchedImbalance && !getenv("CA_FORCE_KSPLIT") ? 0 : 3;
 }
 
+int nt_max_for(int window_modes) { return window_modes > 0 && getenv("CA_NT3") ? 3 : kNtMax; }
+
 bool batched_fits(const DevicePack& op, int mode) {
   if (op.window_modes > 0) return true;  // windowed packs have an m-independent footprint
   const size_t cap = device_cfg().smem_optin;
@@ -171,10 +176,10 @@ bool batched_fits(const DevicePack& op, int mode) {
 }
 
 namespace {
-template <int MODE>
-void launch_windowed(const DevicePack& op, const double* dX, const double* dY, int64_t nstates, int64_t ldx,
-                     double* dOUT, int64_t ldo, cudaStream_t stream) {
-  auto kern = bilinear_windowed_kernel<MODE>;
+template <int MODE, bool NT3>
+void launch_windowed_nt(const DevicePack& op, const double* dX, const double* dY, int64_t nstates, int64_t ldx,
+                        double* dOUT, int64_t ldo, cudaStream_t stream) {
+  auto kern = bilinear_windowed_kernel<MODE, NT3>;
   const int wmax = std::max(op.max_window_modes, 1);
   const size_t smem = windowed_smem_bytes<MODE>(wmax);
   CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -184,10 +189,17 @@ void launch_windowed(const DevicePack& op, const double* dX, const double* dY, i
   if (per_sm < 1) fail(CA_ERR_UNSUPPORTED, "windowed kernel does not fit (smem %zu B)", smem);
   const int64_t nblocks = (nstates + 8 * kWinMT - 1) / (8 * kWinMT);
   const int grid = (int)std::min<int64_t>(nblocks, (int64_t)device_cfg().sms * per_sm);
-  kern<<<grid, threads, smem, stream>>>(op.windows.ptr, op.nwin, op.nwin_nt2, op.modes.ptr, op.pairs_for(kWinMT),
-                                         op.vals.ptr, op.rows.ptr, wmax, op.nin - 1, dX, dY, nstates, ldx, dOUT, ldo);
+  kern<<<grid, threads, smem, stream>>>(op.windows.ptr, op.nwin, op.nwin_nt3, op.nwin_nt2, op.modes.ptr, op.pairs_for(kWinMT),
+                                        op.vals.ptr, op.rows.ptr, wmax, op.nin - 1, dX, dY, nstates, ldx, dOUT, ldo);
   CA_CUDA(cudaGetLastError());
   count_launch();
+}
+
+template <int MODE>
+void launch_windowed(const DevicePack& op, const double* dX, const double* dY, int64_t nstates, int64_t ldx,
+                     double* dOUT, int64_t ldo, cudaStream_t stream) {
+  if (op.nwin_nt3 > 0) launch_windowed_nt<MODE, true>(op, dX, dY, nstates, ldx, dOUT, ldo, stream);
+  else launch_windowed_nt<MODE, false>(op, dX, dY, nstates, ldx, dOUT, ldo, stream);
 }
 }  // namespace
 

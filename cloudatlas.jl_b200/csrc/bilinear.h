@@ -27,7 +27,7 @@ struct DevicePack {
   bool stream_layout = false;
   double sched_imbalance = 1e9;
   // windowed packs (large m): pair words hold window-local rows
-  int32_t window_modes = 0, nwin = 0, nwin_nt2 = 0, max_window_modes = 0;
+  int32_t window_modes = 0, nwin = 0, nwin_nt3 = 0, nwin_nt2 = 0, max_window_modes = 0;
   DeviceBuffer<WindowDesc> windows;
   DeviceBuffer<int32_t> modes;
   void upload(const PackedHost& P);
@@ -51,6 +51,9 @@ void eval_batched_host(const LaunchFn& launch, cudaStream_t streams[kStage], Dev
 // whole-tile packing; larger ones are packed in windows of kWindowModes modes (128: two CTAs per SM still fit for one-vector evaluation).
 constexpr int kWindowModes = 128;
 int window_modes_for(int32_t m);
+// n-tiles (of 8 output rows) per tile: 2; windowed packs take 3 when CA_NT3 is set (row clusters of 17-24 rows -- most of
+// a 3000-mode model -- then form one tile instead of two half-empty ones; experimental until measured)
+int nt_max_for(int window_modes);
 
 // true if the DMMA ensemble kernel can hold a state tile of this operator in shared memory
 bool batched_fits(const DevicePack& op, int mode);

@@ -165,30 +165,45 @@ __device__ __forceinline__ void range_accumulate(const uint2* __restrict__ pairs
   }
 }
 
-template <int MT, int NT, int NW = kWarps>
-__device__ __forceinline__ void tile_reduce_store(int rows_off, const int32_t* __restrict__ rows,
-                                                  double* red, const double (&acc)[MT][NT][2],
-                                                  int warp, int lane, int64_t s0, int64_t nstates,
-                                                  double* __restrict__ OUT, int64_t ldo) {
+// n-tiles [NT0, NT0 + NTC) of an accumulator with NTA n-tiles (NTC <= kNtMax: the reduction buffer holds two)
+template <int MT, int NTA, int NT0, int NTC, int NW>
+__device__ __forceinline__ void tile_reduce_store_part(int rows_off, const int32_t* __restrict__ rows,
+                                                       double* red, const double (&acc)[MT][NTA][2],
+                                                       int warp, int lane, int64_t s0, int64_t nstates,
+                                                       double* __restrict__ OUT, int64_t ldo) {
+  static_assert(NTC <= kNtMax && NT0 + NTC <= NTA, "slice of the accumulator");
   constexpr int ROW = 8 * MT;
   const int r = lane >> 2, c = lane & 3;
   __syncthreads();  // previous tile's readers are done with `red`
   double* mine = red + warp * (kNtMax * 8 * ROW);
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt)
+  for (int nt = 0; nt < NTC; ++nt)
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      mine[(nt * 8 + c * 2 + 0) * ROW + mt * 8 + r] = acc[mt][nt][0];
-      mine[(nt * 8 + c * 2 + 1) * ROW + mt * 8 + r] = acc[mt][nt][1];
+      mine[(nt * 8 + c * 2 + 0) * ROW + mt * 8 + r] = acc[mt][NT0 + nt][0];
+      mine[(nt * 8 + c * 2 + 1) * ROW + mt * 8 + r] = acc[mt][NT0 + nt][1];
     }
   __syncthreads();
-  for (int o = threadIdx.x; o < NT * 8 * ROW; o += NW * 32) {
+  for (int o = threadIdx.x; o < NTC * 8 * ROW; o += NW * 32) {
     const int n = o / ROW, s = o % ROW;
-    const int row = __ldg(rows + rows_off + n);
+    const int row = __ldg(rows + rows_off + NT0 * 8 + n);
     double sum = 0.0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) sum += red[w * (kNtMax * 8 * ROW) + o];
     if (row >= 0 && s0 + s < nstates) OUT[(s0 + s) + ldo * (int64_t)row] = sum;
+  }
+}
+
+template <int MT, int NT, int NW = kWarps>
+__device__ __forceinline__ void tile_reduce_store(int rows_off, const int32_t* __restrict__ rows,
+                                                  double* red, const double (&acc)[MT][NT][2],
+                                                  int warp, int lane, int64_t s0, int64_t nstates,
+                                                  double* __restrict__ OUT, int64_t ldo) {
+  if constexpr (NT <= kNtMax) {
+    tile_reduce_store_part<MT, NT, 0, NT, NW>(rows_off, rows, red, acc, warp, lane, s0, nstates, OUT, ldo);
+  } else {  // three n-tiles: two passes through the two-tile reduction buffer
+    tile_reduce_store_part<MT, NT, 0, kNtMax, NW>(rows_off, rows, red, acc, warp, lane, s0, nstates, OUT, ldo);
+    tile_reduce_store_part<MT, NT, kNtMax, NT - kNtMax, NW>(rows_off, rows, red, acc, warp, lane, s0, nstates, OUT, ldo);
   }
 }
 
@@ -590,7 +605,7 @@ struct ValRing {
 
   __device__ __forceinline__ void issue(int b, int lane) const {
     const int bytes = min(KB, n - b * KB) * (NT * 256);  // <= 0 past the end: an empty group keeps the count uniform
-    const char* s = src + (size_t)b * kValSlotBytes;
+    const char* s = src + (size_t)b * KB * (NT * 256);  // (a batch fills the whole slot only for NT = 1, 2)
     char* d = ring + (b & 1) * kValSlotBytes;
 #pragma unroll
     for (int c = 0; c < kValSlotBytes / 512; ++c) {
@@ -702,9 +717,11 @@ __device__ __forceinline__ void run_windows(const WindowDesc* __restrict__ windo
   }
 }
 
-template <int MODE>
+// NT3: the pack has tiles of three n-tiles (CA_NT3); a separate instantiation, so that the register allocation of the
+// two-n-tile kernel does not change with it
+template <int MODE, bool NT3>
 __global__ void __launch_bounds__(WinCfg<MODE>::NW * 32, WinCfg<MODE>::CTAS)
-bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, int nwin, int nwin_nt2,
+bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, int nwin, int nwin_nt3, int nwin_nt2,
                          const int32_t* __restrict__ modes, const uint2* __restrict__ pairs,
                          const double* __restrict__ vals, const int32_t* __restrict__ rows, int wmax, int one_mode,
                          const double* __restrict__ X, const double* __restrict__ Y, int64_t nstates, int64_t ldx,
@@ -725,10 +742,13 @@ bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, int nwin, int n
     for (int l = tid; l < S.desc[0].nmodes; l += WinCfg<MODE>::NW * 32) S.modes[l] = __ldg(modes + S.desc[0].modes_off + l);
     __syncthreads();
     stage_ahead<MODE>(-1, nwin, windows, modes, pairs, S, one_mode, X, Y, s0, nstates, ldx);
-    run_windows<2, MODE>(windows, 0, nwin_nt2, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane, X, Y, s0,
-                         nstates, ldx, OUT, ldo);
-    run_windows<1, MODE>(windows, nwin_nt2, nwin, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane, X, Y, s0,
-                         nstates, ldx, OUT, ldo);
+    if constexpr (NT3)
+      run_windows<3, MODE>(windows, 0, nwin_nt3, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane, X, Y, s0,
+                           nstates, ldx, OUT, ldo);
+    run_windows<2, MODE>(windows, nwin_nt3, nwin_nt3 + nwin_nt2, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane,
+                         X, Y, s0, nstates, ldx, OUT, ldo);
+    run_windows<1, MODE>(windows, nwin_nt3 + nwin_nt2, nwin, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane, X, Y,
+                         s0, nstates, ldx, OUT, ldo);
   }
 }
 

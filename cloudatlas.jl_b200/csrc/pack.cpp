@@ -596,7 +596,7 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
       P.sched_nt2[w] = 0;
       for (int32_t t : bins[w]) {
         P.sched.push_back(t);
-        P.sched_nt2[w] += P.tiles[t].nt == 2;
+        P.sched_nt2[w] += P.tiles[t].nt >= 2;
       }
     }
     P.sched_off[8] = (int32_t)P.sched.size();
