@@ -167,7 +167,11 @@ int batched_variant(const DevicePack& op) {
   return op.stream_layout && op.sched_imbalance <= kMaxSchedImbalance && !getenv("CA_FORCE_KSPLIT") ? 0 : 3;
 }
 
-int nt_max_for(int window_modes) { return window_modes > 0 && getenv("CA_NT3") ? 3 : kNtMax; }
+int nt_max_for(int window_modes) {
+  if (window_modes <= 0) return kNtMax;
+  const char* e = getenv("CA_NT3");  // "0": never, anything else: always, unset: the packer decides (pack.cpp)
+  return e && e[0] == '0' ? kNtMax : 3;
+}
 
 bool batched_fits(const DevicePack& op, int mode) {
   if (op.window_modes > 0) return true;  // windowed packs have an m-independent footprint
@@ -181,10 +185,10 @@ void launch_windowed_nt(const DevicePack& op, const double* dX, const double* dY
                         double* dOUT, int64_t ldo, cudaStream_t stream) {
   auto kern = bilinear_windowed_kernel<MODE, NT3>;
   const int wmax = std::max(op.max_window_modes, 1);
-  const size_t smem = windowed_smem_bytes<MODE>(wmax);
+  const size_t smem = windowed_smem_bytes<MODE, NT3>(wmax);
   CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  constexpr int threads = WinCfg<MODE>::NW * 32;
+  constexpr int threads = WinCfg<MODE, NT3>::NW * 32;
   CA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) fail(CA_ERR_UNSUPPORTED, "windowed kernel does not fit (smem %zu B)", smem);
   const int64_t nblocks = (nstates + 8 * kWinMT - 1) / (8 * kWinMT);

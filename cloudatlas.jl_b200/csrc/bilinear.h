@@ -51,8 +51,9 @@ void eval_batched_host(const LaunchFn& launch, cudaStream_t streams[kStage], Dev
 // whole-tile packing; larger ones are packed in windows of kWindowModes modes (128: two CTAs per SM still fit for one-vector evaluation).
 constexpr int kWindowModes = 128;
 int window_modes_for(int32_t m);
-// n-tiles (of 8 output rows) per tile: 2; windowed packs take 3 when CA_NT3 is set (row clusters of 17-24 rows -- most of
-// a 3000-mode model -- then form one tile instead of two half-empty ones; experimental until measured)
+// n-tiles (of 8 output rows) a tile may have: 2; windowed packs may take 3 (row clusters of 17-24 rows -- most of a
+// 3000-mode model -- then form one tile instead of two half-empty ones); the packer uses that only where such clusters
+// hold most of the rows, because the three-n-tile kernel runs one CTA of 8 warps per SM
 int nt_max_for(int window_modes);
 
 // true if the DMMA ensemble kernel can hold a state tile of this operator in shared memory

@@ -509,33 +509,35 @@ struct WinSmem {
 
 // warps per CTA: two CTAs of 8 warps per SM for one-vector evaluation; the two-vector modes need twice the window
 // buffers, so one CTA of 16 warps shares them
-template <int MODE>
+// NT3 (tiles of three n-tiles, CA_NT3): 24 accumulator doubles per thread need more than 128 registers, so that
+// variant runs one CTA of 8 warps per SM in every mode.
+template <int MODE, bool NT3 = false>
 struct WinCfg {
-  static constexpr int NW = MODE == MODE_QUAD ? 8 : 16;
-  static constexpr int CTAS = MODE == MODE_QUAD ? 2 : 1;
+  static constexpr int NW = (MODE == MODE_QUAD || NT3) ? 8 : 16;
+  static constexpr int CTAS = (MODE == MODE_QUAD && !NT3) ? 2 : 1;
 };
 
-template <int MODE>
+template <int MODE, bool NT3 = false>
 __host__ __device__ inline size_t window_buf_doubles(int wmax) {
   const size_t row = 8 * kWinMT;
   const size_t states = (size_t)(MODE == MODE_QUAD ? 1 : 2) * wmax * row;
-  const size_t red = (size_t)WinCfg<MODE>::NW * kNtMax * 8 * row;
+  const size_t red = (size_t)WinCfg<MODE, NT3>::NW * kNtMax * 8 * row;
   return states > red ? states : red;
 }
 
-template <int MODE>
+template <int MODE, bool NT3 = false>
 __host__ __device__ inline size_t windowed_smem_bytes(int wmax) {
   const size_t wpad = ((size_t)wmax + 3) & ~(size_t)3;
-  return 2 * window_buf_doubles<MODE>(wmax) * sizeof(double) + (size_t)2 * kWindowMaxKs * 4 * sizeof(uint2) +
-         kDescRing * sizeof(WindowDesc) + 2 * wpad * sizeof(int32_t) + (size_t)WinCfg<MODE>::NW * kValRingBytes;
+  return 2 * window_buf_doubles<MODE, NT3>(wmax) * sizeof(double) + (size_t)2 * kWindowMaxKs * 4 * sizeof(uint2) +
+         kDescRing * sizeof(WindowDesc) + 2 * wpad * sizeof(int32_t) + (size_t)WinCfg<MODE, NT3>::NW * kValRingBytes;
 }
 
-template <int MODE>
+template <int MODE, bool NT3 = false>
 __device__ __forceinline__ WinSmem carve_window_smem(double* smem, int wmax) {
   WinSmem S;
   S.wmax = wmax;
   S.wpad = (wmax + 3) & ~3;
-  S.bufstride = window_buf_doubles<MODE>(wmax);
+  S.bufstride = window_buf_doubles<MODE, NT3>(wmax);
   S.bufs = smem;
   S.pairs = reinterpret_cast<uint2*>(smem + 2 * S.bufstride);
   S.desc = reinterpret_cast<WindowDesc*>(S.pairs + (size_t)2 * kWindowMaxKs * 4);
@@ -545,13 +547,13 @@ __device__ __forceinline__ WinSmem carve_window_smem(double* smem, int wmax) {
 }
 
 // Issued by the whole CTA right after the barrier of window g (g == -1: block prologue).
-template <int MODE>
+template <int MODE, bool NT3 = false>
 __device__ __forceinline__ void stage_ahead(int g, int gtotal, const WindowDesc* __restrict__ windows,
                                             const int32_t* __restrict__ modes, const uint2* __restrict__ pairs,
                                             const WinSmem& S, int one_mode, const double* __restrict__ X,
                                             const double* __restrict__ Y, int64_t s0, int64_t nstates, int64_t ldx) {
   constexpr int ROW = 8 * kWinMT;
-  constexpr int NW = WinCfg<MODE>::NW, NTHR = NW * 32;
+  constexpr int NW = WinCfg<MODE, NT3>::NW, NTHR = NW * 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (g + 1 < gtotal) {
     const WindowDesc& W = S.desc[(g + 1) & (kDescRing - 1)];
@@ -627,14 +629,14 @@ struct ValRing {
 };
 
 // ps: the window's pair words in shared memory
-template <int MT, int NT, int MODE>
+template <int MT, int NT, int MODE, bool NT3 = false>
 __device__ __forceinline__ void window_accumulate(const uint2* ps, int nks, const double* xs, const double* ys,
-                                                  int warp, int lane, const ValRing<NT, WinCfg<MODE>::NW>& vr,
+                                                  int warp, int lane, const ValRing<NT, WinCfg<MODE, NT3>::NW>& vr,
                                                   double (&acc)[MT][NT][2]) {
-  constexpr int KB = ValRing<NT, WinCfg<MODE>::NW>::KB;
+  constexpr int KB = ValRing<NT, WinCfg<MODE, NT3>::NW>::KB;
   const uint32_t r8 = 8u * (lane >> 2);
   int k0, k1;
-  warp_share<WinCfg<MODE>::NW>(nks, warp, k0, k1);
+  warp_share<WinCfg<MODE, NT3>::NW>(nks, warp, k0, k1);
   const int n = k1 - k0;
   if (n <= 0) return;
   const uint2* pp = ps + (size_t)k0 * 4 + (lane & 3);
@@ -672,7 +674,7 @@ __device__ __forceinline__ void window_accumulate(const uint2* ps, int nks, cons
 }
 
 // windows [gb, ge) all belong to tiles with NT n-tiles; gtotal = number of windows of the operator
-template <int NT, int MODE>
+template <int NT, int MODE, bool NT3 = false>
 __device__ __forceinline__ void run_windows(const WindowDesc* __restrict__ windows, int gb, int ge, int gtotal,
                                             const int32_t* __restrict__ modes, const uint2* __restrict__ pairs,
                                             const double* __restrict__ vals, const int32_t* __restrict__ rows,
@@ -681,7 +683,7 @@ __device__ __forceinline__ void run_windows(const WindowDesc* __restrict__ windo
                                             int64_t nstates, int64_t ldx, double* __restrict__ OUT, int64_t ldo) {
   constexpr int MT = kWinMT, ROW = 8 * MT;
   if (gb >= ge) return;
-  ValRing<NT, WinCfg<MODE>::NW> vr;
+  ValRing<NT, WinCfg<MODE, NT3>::NW> vr;
   vr.ring = S.vring + warp * kValRingBytes;
   double acc[MT][NT][2];
   {
@@ -692,7 +694,7 @@ __device__ __forceinline__ void run_windows(const WindowDesc* __restrict__ windo
   for (int g = gb; g < ge; ++g) {
     cp_async_wait_all();
     __syncthreads();  // window g (+ mode list g+1, descriptor g+2) has landed; window g-1's buffers are free
-    stage_ahead<MODE>(g, gtotal, windows, modes, pairs, S, one_mode, X, Y, s0, nstates, ldx);
+    stage_ahead<MODE, NT3>(g, gtotal, windows, modes, pairs, S, one_mode, X, Y, s0, nstates, ldx);
     if (fresh) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
@@ -705,14 +707,14 @@ __device__ __forceinline__ void run_windows(const WindowDesc* __restrict__ windo
     double* cur = S.bufs + (size_t)(g & 1) * S.bufstride;
     const double* xs = cur;
     const double* ys = MODE == MODE_QUAD ? xs : xs + (size_t)S.wmax * ROW;
-    window_accumulate<MT, NT, MODE>(S.pairs + (size_t)(g & 1) * kWindowMaxKs * 4, nks, xs, ys, warp, lane, vr, acc);
+    window_accumulate<MT, NT, MODE, NT3>(S.pairs + (size_t)(g & 1) * kWindowMaxKs * 4, nks, xs, ys, warp, lane, vr, acc);
     if (g + 1 < ge) {
       const WindowDesc& Wn = S.desc[(g + 1) & (kDescRing - 1)];
       vr.begin(vals + Wn.vals_off, Wn.nks, warp, lane);
     }
     // the reduction buffer is the finished window's state buffer: its first barrier frees it, and the next
     // window's barrier comes before anything is staged into it again
-    if (last) tile_reduce_store<MT, NT, WinCfg<MODE>::NW>(rows_off, rows, cur, acc, warp, lane, s0, nstates, OUT, ldo);
+    if (last) tile_reduce_store<MT, NT, WinCfg<MODE, NT3>::NW>(rows_off, rows, cur, acc, warp, lane, s0, nstates, OUT, ldo);
     fresh = last;
   }
 }
@@ -720,7 +722,7 @@ __device__ __forceinline__ void run_windows(const WindowDesc* __restrict__ windo
 // NT3: the pack has tiles of three n-tiles (CA_NT3); a separate instantiation, so that the register allocation of the
 // two-n-tile kernel does not change with it
 template <int MODE, bool NT3>
-__global__ void __launch_bounds__(WinCfg<MODE>::NW * 32, WinCfg<MODE>::CTAS)
+__global__ void __launch_bounds__(WinCfg<MODE, NT3>::NW * 32, WinCfg<MODE, NT3>::CTAS)
 bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, int nwin, int nwin_nt3, int nwin_nt2,
                          const int32_t* __restrict__ modes, const uint2* __restrict__ pairs,
                          const double* __restrict__ vals, const int32_t* __restrict__ rows, int wmax, int one_mode,
@@ -728,7 +730,7 @@ bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, int nwin, int n
                          double* __restrict__ OUT, int64_t ldo) {
   constexpr int ROW = 8 * kWinMT;
   extern __shared__ __align__(16) double smem[];
-  const WinSmem S = carve_window_smem<MODE>(smem, wmax);
+  const WinSmem S = carve_window_smem<MODE, NT3>(smem, wmax);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t nblocks = (nstates + ROW - 1) / ROW;
   if (nwin <= 0) return;
@@ -739,15 +741,15 @@ bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, int nwin, int n
     if (tid < 2 * kDescWords && tid / kDescWords < nwin)  // descriptors 0 and 1 directly
       reinterpret_cast<uint32_t*>(S.desc)[tid] = __ldg(reinterpret_cast<const uint32_t*>(windows) + tid);
     __syncthreads();
-    for (int l = tid; l < S.desc[0].nmodes; l += WinCfg<MODE>::NW * 32) S.modes[l] = __ldg(modes + S.desc[0].modes_off + l);
+    for (int l = tid; l < S.desc[0].nmodes; l += WinCfg<MODE, NT3>::NW * 32) S.modes[l] = __ldg(modes + S.desc[0].modes_off + l);
     __syncthreads();
-    stage_ahead<MODE>(-1, nwin, windows, modes, pairs, S, one_mode, X, Y, s0, nstates, ldx);
+    stage_ahead<MODE, NT3>(-1, nwin, windows, modes, pairs, S, one_mode, X, Y, s0, nstates, ldx);
     if constexpr (NT3)
-      run_windows<3, MODE>(windows, 0, nwin_nt3, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane, X, Y, s0,
+      run_windows<3, MODE, NT3>(windows, 0, nwin_nt3, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane, X, Y, s0,
                            nstates, ldx, OUT, ldo);
-    run_windows<2, MODE>(windows, nwin_nt3, nwin_nt3 + nwin_nt2, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane,
+    run_windows<2, MODE, NT3>(windows, nwin_nt3, nwin_nt3 + nwin_nt2, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane,
                          X, Y, s0, nstates, ldx, OUT, ldo);
-    run_windows<1, MODE>(windows, nwin_nt3 + nwin_nt2, nwin, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane, X, Y,
+    run_windows<1, MODE, NT3>(windows, nwin_nt3 + nwin_nt2, nwin, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane, X, Y,
                          s0, nstates, ldx, OUT, ldo);
   }
 }

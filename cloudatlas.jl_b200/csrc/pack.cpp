@@ -254,6 +254,15 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
     clusters.push_back(std::move(cl));
   }
 
+  if (nt_max >= 3) {
+    // Three n-tiles only where they pay: measured at m = 2962 (86 % of the rows in clusters of 17-24 rows) the windowed
+    // kernel gains 13 % (f) and 28 % (Jacobian action), at m = 999 (50 %) it loses 14 % to the single CTA per SM.
+    const char* force = getenv("CA_NT3");
+    int64_t wide_rows = 0;
+    for (auto& cl : clusters)
+      if (cl.size() > 16 && cl.size() <= 24) wide_rows += (int64_t)cl.size();
+    if (!(force && force[0] != '0') && (double)wide_rows < 0.7 * (double)m) nt_max = 2;
+  }
   tm.lap("cluster");
   if (getenv("CA_TIMING") && clusters.size() > 8) {
     int hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // rows per cluster: 1-8, 9-16, 17-24, ...

@@ -99,6 +99,29 @@ def test_pack_sort_paths_above_the_small_input_cutoff():
             assert pack_stats(ijk_s[perm], val_s[perm], m, sym, wm)["mismatches"] == 0
 
 
+def test_pack_three_n_tiles_for_wide_row_clusters(monkeypatch):
+    """Windowed packs whose rows mostly sit in clusters of 17-24 rows (the 3000-mode models) get one tile of three
+    n-tiles per cluster instead of two half-empty tiles; narrower structures and whole-tile packs keep two."""
+    rng = np.random.default_rng(5)
+    m, rows_per_cluster = 66, 22
+    ijk, val = [], []
+    for c in range(3):
+        pairs = rng.integers(1, m + 1, size=(90, 2))
+        for i in range(c * rows_per_cluster, (c + 1) * rows_per_cluster):
+            for j, k in pairs:
+                ijk.append((i + 1, j, k))
+                val.append(float(rng.integers(1, 9)))
+    ijk, val = np.array(ijk), np.array(val)
+    wide = pack_stats(ijk, val, m, 1, 32)
+    assert wide["mismatches"] == 0 and wide["ntiles"] == 3
+    monkeypatch.setenv("CA_NT3", "0")
+    narrow = pack_stats(ijk, val, m, 1, 32)
+    assert narrow["mismatches"] == 0 and narrow["ntiles"] == 6
+    assert wide["padded_fma"] < narrow["padded_fma"] and wide["pair_products"] < narrow["pair_products"]
+    monkeypatch.delenv("CA_NT3")
+    assert pack_stats(ijk, val, m, 1, 0)["ntiles"] == 6        # whole-tile packs: two n-tiles at most
+
+
 def test_pack_fill_at_307(nagata_H):
     """The clustering finds the wavenumber/parity classes: >= 75 % of the executed FMAs are real."""
     from oracle.basis import basisIndices
