@@ -144,6 +144,30 @@ def test_specialised_kernel_padded_leading_dimension_and_ragged_sizes(ca, nagata
         assert relerr(want[sample], np.stack([ref.f(X[s], 200.0) for s in sample])) < 1e-13 * max(1.0, np.linalg.cond(ref.B) / 10)
 
 
+def test_three_n_tile_windowed_model_matches_whole_tile_model(ca, monkeypatch):
+    """The folded 307-mode model through the windowed kernel with tiles of three n-tiles (forced: the packer would pick
+    them only for ~3000-mode models) against the same model through the whole-tile kernel: f, the Jacobian action and
+    re-targeting R (the linear slots sit in three-n-tile fragments) agree to rounding."""
+    import torch
+    sx, sy, sz, tx, tz = ca.halfbox_symmetries()
+    H = [sx * sy * sz, sz * tx * tz]
+    base = ca.ODEModel(1.0, 2.0, 3, 3, 12, H)
+    monkeypatch.setenv("CA_FORCE_WINDOW_MODES", "128")
+    monkeypatch.setenv("CA_NT3", "1")
+    wide = ca.ODEModel(1.0, 2.0, 3, 3, 12, H)
+    assert wide.kernel_path(1000)[0] == "dmma_row_tiles_windowed"
+    assert wide.info()["padded_fma_per_state"] != base.info()["padded_fma_per_state"]
+    rng = np.random.default_rng(23)
+    n = 1000 + 13
+    X = torch.from_numpy((0.1 * rng.standard_normal((base.m, n)))).cuda().t()
+    V = torch.from_numpy(rng.standard_normal((base.m, n))).cuda().t()
+    for R in (200.0, 417.0):
+        a, b = base.f(X, R).cpu().numpy(), wide.f(X, R).cpu().numpy()
+        assert relerr(b, a) < 1e-13
+        a, b = base.Df_action(X, V, R).cpu().numpy(), wide.Df_action(X, V, R).cpu().numpy()
+        assert relerr(b, a) < 1e-13
+
+
 def test_full_size_ensemble_properties(ca, nagata_H):
     """BASELINE.json configs[2] at full size (10^6 states, 307 modes): size-independent properties -- results do not
     depend on where a state sits in the ensemble (bit-exact under permutation), the host-pointer path equals the
