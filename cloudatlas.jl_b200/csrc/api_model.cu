@@ -297,11 +297,15 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
     {
       size_t total = 0;
       for (auto& v : block_terms) total += v.size();
-      qterms.reserve(total);
-      for (auto& v : block_terms) {
-        qterms.insert(qterms.end(), v.begin(), v.end());
-        std::vector<Term>().swap(v);
-      }
+      std::vector<size_t> at(block_terms.size() + 1, 0);
+      for (size_t bi = 0; bi < block_terms.size(); ++bi) at[bi + 1] = at[bi] + block_terms[bi].size();
+      qterms.resize(total);  // (Term() does not zero-fill) the blocks are copied into place on worker threads
+      parallel_chunks(block_terms.size(), block_terms.size(), [&](size_t b, size_t e, size_t) {
+        for (size_t bi = b; bi < e; ++bi) {
+          std::copy(block_terms[bi].begin(), block_terms[bi].end(), qterms.begin() + (ptrdiff_t)at[bi]);
+          std::vector<Term>().swap(block_terms[bi]);
+        }
+      });
     }
     tm.lap("fold B^-1");
     require_device();
@@ -312,7 +316,10 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
     // linear placeholders (value 1) mark the slots that set_R patches
     std::vector<Term> all;
     all.reserve(qterms.size() + (size_t)m * m);  // one allocation: growing a multi-gigabyte copy by push_back copies it again
-    all.insert(all.end(), qterms.begin(), qterms.end());
+    all.resize(qterms.size());
+    parallel_chunks(qterms.size(), 64, [&](size_t b, size_t e, size_t) {
+      std::copy(qterms.begin() + (ptrdiff_t)b, qterms.begin() + (ptrdiff_t)e, all.begin() + (ptrdiff_t)b);
+    });
     for (int j = 0; j < m; ++j)
       for (int i = 0; i < m; ++i)
         if (hL1[i + (size_t)m * j] != 0.0 || hL2[i + (size_t)m * j] != 0.0) all.push_back(Term{i, j, m, 1.0});
