@@ -159,12 +159,15 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
     {
       // the reference's COO is sorted by (i, j, k) (SparseBilinear.jl:24-49): rows are contiguous ranges, filled on
       // worker threads; anything else goes through the serial scatter
-      bool sorted_rows = true;
-      for (int64_t r = 1; r < nnz && sorted_rows; ++r) sorted_rows = ijk[r] >= ijk[r - 1];
+      std::atomic<int> unsorted{0};
+      parallel_chunks((size_t)nnz, 64, [&](size_t b, size_t e, size_t) {
+        for (size_t r = std::max<size_t>(b, 1); r < e; ++r)
+          if (ijk[r] < ijk[r - 1]) { unsorted = 1; return; }
+      });
+      const bool sorted_rows = unsorted == 0;
       if (sorted_rows && nnz > (1 << 16)) {
-        std::vector<int64_t> row_start((size_t)m + 1, 0);
-        for (int64_t r = 0; r < nnz; ++r) row_start[(size_t)ijk[r]]++;  // 1-based i lands at index i
-        for (int i = 0; i < m; ++i) row_start[(size_t)i + 1] += row_start[i];
+        std::vector<int64_t> row_start((size_t)m + 1, 0);  // sorted by i: the rows are found by bisection
+        for (int i = 0; i <= m; ++i) row_start[(size_t)i] = std::lower_bound(ijk, ijk + nnz, (int64_t)i + 1) - ijk;
         parallel_chunks((size_t)m, (size_t)m, [&](size_t b, size_t e, size_t) {
           for (size_t i = b; i < e; ++i) {
             auto& row = byrow[i];
