@@ -532,6 +532,29 @@ int32_t ca_model_jac(ca_model* h, const double* x, double R, double* Df) {
 
 }  // extern "C"
 
+// Host-only diagnostic: generates and NVRTC-compiles the model-specialised kernel for a symmetrised quadratic operator
+// (+ a dense linear pattern) without creating a model; loading the cubin needs a device and is not attempted here.
+extern "C" int32_t ca_selftest_small_kernel(const int64_t* ijk, const double* val, int64_t nnz, int64_t m,
+                                            int64_t* cubin_bytes, int32_t* threads, int32_t* stages,
+                                            int64_t* source_bytes) {
+  return guarded([&] {
+    if (m <= 0 || m > kJitMaxM || (nnz > 0 && (!ijk || !val))) fail(CA_ERR_INVALID, "ca_selftest_small_kernel: bad arguments");
+    std::vector<Term> q((size_t)nnz);
+    for (int64_t r = 0; r < nnz; ++r)
+      q[(size_t)r] = Term{(int32_t)(ijk[r] - 1), (int32_t)(ijk[r + nnz] - 1), (int32_t)(ijk[r + 2 * nnz] - 1), val[r]};
+    std::vector<int32_t> li, lj;
+    for (int j = 0; j < (int)m; ++j)
+      for (int i = 0; i < (int)m; ++i) { li.push_back(i); lj.push_back(j); }
+    SmallKernel k;
+    k.build(merge_terms(std::move(q), true, (int32_t)m), li, lj, (int)m);
+    if (k.cubin_bytes == 0) fail(CA_ERR_UNSUPPORTED, "generated kernel did not compile: %s", k.log.c_str());
+    if (cubin_bytes) *cubin_bytes = (int64_t)k.cubin_bytes;
+    if (threads) *threads = k.threads;
+    if (stages) *stages = k.stages;
+    if (source_bytes) *source_bytes = (int64_t)k.source.size();
+  });
+}
+
 extern "C" int32_t ca_model_kernel_path(ca_model* h, int64_t nstates, int32_t* path, const char** source,
                                         const char** log) {
   return guarded([&] {

@@ -30,6 +30,7 @@ struct SmallKernel {
   std::vector<int32_t> lin_i, lin_j;  // pattern of the linear part (row, column), order of LC
   int threads = 0, stages = 0, ctas_per_sm = 2;  // CTA shape of the generated kernel (jit_small.cu: small_shape)
   size_t smem_bytes = 0;
+  size_t cubin_bytes = 0;      // > 0 once NVRTC has compiled the generated source
   double cur_invR = 0.0;
   bool lc_set = false;
   ~SmallKernel();

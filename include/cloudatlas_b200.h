@@ -275,6 +275,12 @@ int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64_t nnz, int
                          int64_t* pair_products, int64_t* mismatches, int64_t* nwindows,
                          int64_t* max_window_modes);
 
+/* Generates the model-specialised ensemble kernel (m <= 48) for a quadratic operator plus a dense linear pattern and
+ * compiles it with NVRTC for sm_100a; reports the cubin size and the CTA shape.  No device needed: the module is
+ * not loaded.  Fails with CA_ERR_UNSUPPORTED (and the NVRTC log as error text) if the source does not compile. */
+int32_t ca_selftest_small_kernel(const int64_t* ijk, const double* val, int64_t nnz, int64_t m,
+                                 int64_t* cubin_bytes, int32_t* threads, int32_t* stages, int64_t* source_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,6 +122,26 @@ def test_pack_three_n_tiles_for_wide_row_clusters(monkeypatch):
     assert pack_stats(ijk, val, m, 1, 0)["ntiles"] == 6        # whole-tile packs: two n-tiles at most
 
 
+@pytest.mark.parametrize("JKL", [(1, 1, 3), (1, 2, 3), (2, 2, 3)], ids=["17d", "27d", "44d"])
+def test_generated_small_model_kernel_compiles(JKL, nagata_H):
+    """The NVRTC source generated for the reference's small models compiles for sm_100a (no device needed for that),
+    with the measured CTA shapes: 128 threads x 2 stages at 17 modes, 256 x 2 up to 27, 128 x 2 beyond."""
+    from oracle.basis import basisIndices
+    from oracle.fastfloat import assemble_N_float
+    ijkl = basisIndices(*JKL, nagata_H)
+    m = ijkl.shape[0]
+    ijk, val = assemble_N_float(1, 2, ijkl)
+    ijk = np.asfortranarray(ijk, dtype=np.int64)
+    fn = _sig("ca_selftest_small_kernel", c_i64p, c_f64p, C.c_int64, C.c_int64, c_i64p, C.POINTER(C.c_int32),
+              C.POINTER(C.c_int32), c_i64p)
+    cubin, src = C.c_int64(), C.c_int64()
+    threads, stages = C.c_int32(), C.c_int32()
+    check(fn(ijk.ctypes.data_as(c_i64p), np.ascontiguousarray(val).ctypes.data_as(c_f64p), len(val), m,
+             C.byref(cubin), C.byref(threads), C.byref(stages), C.byref(src)))
+    assert cubin.value > 10_000 and src.value > 1_000
+    assert (threads.value, stages.value) == {17: (128, 2), 27: (256, 2), 44: (128, 2)}[m]
+
+
 def test_pack_fill_at_307(nagata_H):
     """The clustering finds the wavenumber/parity classes: >= 75 % of the executed FMAs are real."""
     from oracle.basis import basisIndices
