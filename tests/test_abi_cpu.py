@@ -142,6 +142,27 @@ def test_generated_small_model_kernel_compiles(JKL, nagata_H):
     assert (threads.value, stages.value) == {17: (128, 2), 27: (256, 2), 44: (128, 2)}[m]
 
 
+def test_sass_of_the_hot_kernels():
+    """The library is compiled for sm_100a only, its ensemble kernels issue FP64 tensor instructions (DMMA.8x8x4) and
+    stream through cp.async (LDGSTS); checked on the SASS of the built library, no device needed."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    libpath = ca.LIB_PATH
+    arch = subprocess.run(["cuobjdump", "-lelf", libpath], capture_output=True, text=True).stdout
+    assert "sm_100a" in arch and "sm_90" not in arch and "sm_80" not in arch
+    sass = subprocess.run(["cuobjdump", "-sass", libpath], capture_output=True, text=True).stdout
+    for pattern, need in (("bilinear_warptile_kernel", ("DMMA.8x8x4", "LDGSTS")),
+                          ("bilinear_windowed_kernel", ("DMMA.8x8x4", "LDGSTS", "LDGDEPBAR")),
+                          ("dense_contract_kernel", ("DMMA.8x8x4", "LDGSTS"))):
+        blocks = [b for b in sass.split("Function : ")[1:] if pattern in b.split("\n", 1)[0]]
+        assert blocks, pattern
+        for b in blocks:
+            for mnemonic in need:
+                assert mnemonic in b, (pattern, mnemonic)
+
+
 def test_pack_fill_at_307(nagata_H):
     """The clustering finds the wavenumber/parity classes: >= 75 % of the executed FMAs are real."""
     from oracle.basis import basisIndices
