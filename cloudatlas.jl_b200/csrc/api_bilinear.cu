@@ -263,6 +263,18 @@ int32_t ca_bilinear_jacobian(ca_bilinear* h, const double* x, double* DN) {
 
 }  // extern "C"
 
+extern "C" int32_t ca_selftest_pack_digest(const int64_t* ijk, const double* val, int64_t nnz, int64_t m,
+                                           int32_t symmetric, int32_t window_modes, uint64_t* digest8) {
+  return guarded([&] {
+    if (!digest8 || m <= 0 || (nnz > 0 && (!ijk || !val))) fail(CA_ERR_INVALID, "ca_selftest_pack_digest: bad arguments");
+    std::vector<Term> coo((size_t)nnz);
+    for (int64_t r = 0; r < nnz; ++r)
+      coo[(size_t)r] = Term{(int32_t)(ijk[r] - 1), (int32_t)(ijk[r + nnz] - 1), (int32_t)(ijk[r + 2 * nnz] - 1), val[r]};
+    const PackedHost P = pack_terms(std::move(coo), (int32_t)m, symmetric != 0, nt_max_for(window_modes), window_modes);
+    pack_digest(P, digest8);
+  });
+}
+
 extern "C" int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64_t nnz, int64_t m,
                                     int32_t symmetric, int32_t window_modes, int64_t* ntiles, int64_t* nterms,
                                     int64_t* padded_fma, int64_t* pair_products, int64_t* mismatches,

@@ -11,13 +11,13 @@
 #include <algorithm>
 #include <array>
 #include <numeric>
-#include <cub/device/device_scan.cuh>
 
 #include <memory>
 #include <vector>
 
 #include "basis.h"
 #include "common.h"
+#include "scan.cuh"
 
 using namespace ca;
 
@@ -755,8 +755,7 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
     // and its cost varies by milliseconds from call to call.
     const int64_t nij_pre = (int64_t)rows * m;
     DeviceBuffer<int64_t> counts, offs;
-    DeviceBuffer<char> tmp;
-    size_t tmp_bytes = 0;
+    ScanScratch scan_tmp;
     if (nij_pre > 0) {
       h->B.alloc((size_t)nij_pre);
       h->A1.alloc((size_t)nij_pre);
@@ -764,8 +763,7 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
       h->D.alloc((size_t)nij_pre);
       counts.alloc((size_t)nij_pre + 1);
       offs.alloc((size_t)nij_pre + 1);
-      CA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.ptr, offs.ptr, (int)(nij_pre + 1)));
-      tmp.alloc(tmp_bytes);
+      scan_tmp.sums.alloc((size_t)(nij_pre + 1) / kScanTile + kScanTile + 16);  // allocated outside the timed spans
     }
     // separable path: scratch for the single evaluating pass -- one slot per candidate, counted on the host from the
     // list lengths (modes per (group, parity class) x list length of the class pair)
@@ -903,14 +901,12 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
         cand_count_kernel<<<(unsigned)((nij + 255) / 256), 256>>>(cand, m, r0, nij, cnum.ptr);
         CA_CUDA(cudaGetLastError());
         count_launch();
-        CA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.ptr, tmp_bytes, cnum.ptr, coffs.ptr, (int)(nij + 1)));
-        count_launch();
+        exclusive_scan(cnum.ptr, coffs.ptr, nij + 1, scan_tmp, nullptr);
         n_eval_kernel<<<ngrid, 128>>>(b, cand, r0, r1, coffs.ptr, counts.ptr, tk.ptr, tv.ptr);
       }
       CA_CUDA(cudaGetLastError());
       count_launch();
-      CA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.ptr, tmp_bytes, counts.ptr, offs.ptr, (int)(nij + 1)));
-      count_launch();
+      exclusive_scan(counts.ptr, offs.ptr, nij + 1, scan_tmp, nullptr);
       CA_CUDA(cudaEventRecord(e1));
       int64_t nnz = 0;
       CA_CUDA(cudaMemcpy(&nnz, offs.ptr + nij, sizeof(int64_t), cudaMemcpyDeviceToHost));

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <numeric>
 #include <atomic>
 #include <thread>
@@ -46,7 +47,127 @@ std::vector<uint64_t> union_of(const std::vector<uint64_t>& a, const std::vector
   return out;
 }
 
+
+// Row key sets as the host packer holds them: sorted vectors.
+struct HostRowSets final : RowSetOps {
+  const std::vector<Row>& rows;
+  std::vector<uint64_t> U;
+  explicit HostRowSets(const std::vector<Row>& r) : rows(r) {}
+  int32_t nrows() const override { return (int32_t)rows.size(); }
+  int64_t nkeys(int32_t r) const override { return (int64_t)rows[r].keys.size(); }
+  const uint64_t* sketch(int32_t r) const override { return rows[r].sketch; }
+  int batch_hint() const override { return 1; }
+  void open(int32_t seed) override { U = rows[seed].keys; }
+  int64_t open_size() const override { return (int64_t)U.size(); }
+  void union_sizes(const int32_t* cand, int n, int64_t* out) override {
+    for (int q = 0; q < n; ++q) out[q] = (int64_t)union_size(U, rows[cand[q]].keys);
+  }
+  void absorb(int32_t r) override { U = union_of(U, rows[r].keys); }
+};
+
 }  // namespace
+
+uint64_t fnv1a(const void* data, size_t bytes, uint64_t h) {
+  // 8 bytes at a time (the arrays digested are gigabytes at m ~ 3000), remainder bytewise
+  const unsigned char* p = (const unsigned char*)data;
+  size_t q = 0;
+  for (; q + 8 <= bytes; q += 8) {
+    uint64_t w;
+    memcpy(&w, p + q, 8);
+    h = (h ^ w) * 0x100000001b3ull;
+  }
+  for (; q < bytes; ++q) h = (h ^ p[q]) * 0x100000001b3ull;
+  return h;
+}
+
+void pack_digest(const PackedHost& P, uint64_t out[8]) {
+  // descriptors are hashed field by field (struct padding is not part of a pack)
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (const TileDesc& T : P.tiles) {
+    const int64_t f[7] = {T.ks_begin, T.nks, T.vals_off, T.rows_off, T.nt, T.nrows, T.npairs};
+    h = fnv1a(f, sizeof f, h);
+  }
+  out[0] = h;
+  out[1] = fnv1a(P.pairs.data(), P.pairs.size() * sizeof(uint32_t));
+  out[2] = fnv1a(P.vals.data(), P.vals.size() * sizeof(double));
+  out[3] = fnv1a(P.rows.data(), P.rows.size() * sizeof(int32_t));
+  h = 0xcbf29ce484222325ull;
+  for (const WindowDesc& W : P.windows) {
+    const int64_t f[9] = {W.ks_begin, W.nks, W.modes_off, W.nmodes, W.tile, W.last, W.rows_off, W.nt, W.vals_off};
+    h = fnv1a(f, sizeof f, h);
+  }
+  out[4] = h;
+  out[5] = fnv1a(P.modes.data(), P.modes.size() * sizeof(int32_t));
+  h = fnv1a(P.sched.data(), P.sched.size() * sizeof(int32_t));
+  h = fnv1a(P.sched_off, sizeof P.sched_off, h);
+  h = fnv1a(P.sched_nt2, sizeof P.sched_nt2, h);
+  h = fnv1a(P.sched_ks2, sizeof P.sched_ks2, h);
+  h = fnv1a(P.sched_ks1, sizeof P.sched_ks1, h);
+  const int64_t sl = P.stream_layout;
+  out[6] = fnv1a(&sl, sizeof sl, h);
+  const int64_t c[9] = {P.m, P.nin, P.symmetric, P.window_modes, P.max_window_modes, P.nterms, P.npairs_distinct,
+                        P.padded_fma, P.pair_products};
+  out[7] = fnv1a(c, sizeof c);
+}
+
+void cluster_rows(RowSetOps& sets, std::vector<std::vector<int32_t>>& clusters, std::vector<int32_t>& empties) {
+  const int32_t m = sets.nrows();
+  std::vector<int32_t> order(m);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return sets.nkeys(x) > sets.nkeys(y); });
+  std::vector<char> assigned(m, 0);
+  const int batch = std::max(1, sets.batch_hint());
+  std::vector<int32_t> cq;
+  std::vector<int64_t> usz;
+  for (int32_t seed : order) {
+    if (assigned[seed]) continue;
+    assigned[seed] = 1;
+    if (sets.nkeys(seed) == 0) {
+      empties.push_back(seed);
+      continue;
+    }
+    std::vector<int32_t> cl{seed};
+    sets.open(seed);
+    int64_t usize = sets.nkeys(seed);
+    std::vector<std::pair<int, int32_t>> cand;
+    const uint64_t* ss = sets.sketch(seed);
+    for (int32_t r = 0; r < m; ++r) {
+      if (assigned[r] || sets.nkeys(r) == 0) continue;
+      const uint64_t* sr = sets.sketch(r);
+      int agree = 0;
+      for (int h = 0; h < kSketch; ++h) agree += sr[h] == ss[h];
+      if (agree >= kSketch / 2) cand.push_back({-agree, r});
+    }
+    std::sort(cand.begin(), cand.end());
+    // union sizes are asked for in batches against the open set; a batch is void as soon as the open set grows
+    size_t next = 0;
+    while (next < cand.size()) {
+      const size_t n = std::min(cand.size() - next, (size_t)batch);
+      cq.resize(n);
+      usz.resize(n);
+      for (size_t q = 0; q < n; ++q) cq[q] = cand[next + q].second;
+      sets.union_sizes(cq.data(), (int)n, usz.data());
+      size_t q = 0;
+      for (; q < n; ++q) {
+        const int64_t k = sets.nkeys(cq[q]);
+        const int64_t u = usz[q];
+        if ((double)u <= 1.2 * (double)std::max(usize, k)) {
+          cl.push_back(cq[q]);
+          assigned[cq[q]] = 1;
+          if (u != usize) {  // the open set grows: the remaining sizes of this batch are stale
+            sets.absorb(cq[q]);
+            usize = u;
+            ++q;
+            break;
+          }
+        }
+      }
+      next += q;
+    }
+    std::sort(cl.begin(), cl.end());
+    clusters.push_back(std::move(cl));
+  }
+}
 
 void sort_terms(std::vector<Term>& terms, int32_t m) {
   if (m <= 0) {
@@ -216,44 +337,62 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
 
   tm.lap("rows+sketches");
   // ---- cluster rows with near-identical pair sets
-  std::vector<int32_t> order(m);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
-    return rows[x].keys.size() > rows[y].keys.size();
-  });
-  std::vector<char> assigned(m, 0);
+  HostRowSets host_sets(rows);
   std::vector<std::vector<int32_t>> clusters;
   std::vector<int32_t> empties;
-  for (int32_t seed : order) {
-    if (assigned[seed]) continue;
-    assigned[seed] = 1;
-    if (rows[seed].keys.empty()) {
-      empties.push_back(seed);
-      continue;
-    }
-    std::vector<int32_t> cl{seed};
-    std::vector<uint64_t> U = rows[seed].keys;
-    std::vector<std::pair<int, int32_t>> cand;
-    for (int32_t r = 0; r < m; ++r) {
-      if (assigned[r] || rows[r].keys.empty()) continue;
-      int agree = 0;
-      for (int h = 0; h < kSketch; ++h) agree += rows[r].sketch[h] == rows[seed].sketch[h];
-      if (agree >= kSketch / 2) cand.push_back({-agree, r});
-    }
-    std::sort(cand.begin(), cand.end());
-    for (auto& c : cand) {
-      const auto& k = rows[c.second].keys;
-      size_t u = union_size(U, k);
-      if ((double)u <= 1.2 * (double)std::max(U.size(), k.size())) {
-        U = union_of(U, k);
-        cl.push_back(c.second);
-        assigned[c.second] = 1;
+  cluster_rows(host_sets, clusters, empties);
+
+  nt_max = decide_nt_max(clusters, m, nt_max);
+  tm.lap("cluster");
+  if (getenv("CA_TIMING") && clusters.size() > 8) {
+    int hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // rows per cluster: 1-8, 9-16, 17-24, ...
+    for (auto& cl : clusters) hist[std::min<size_t>(7, (cl.size() - 1) / 8)]++;
+    fprintf(stderr, "[ca timing] pack_terms: %zu row clusters; sizes 1-8: %d, 9-16: %d, 17-24: %d, 25-32: %d, more: %d\n",
+            clusters.size(), hist[0], hist[1], hist[2], hist[3], hist[4] + hist[5] + hist[6] + hist[7]);
+  }
+  // ---- split clusters into tiles of <= 8*nt_max rows, lay out fragments
+  // (tiles are laid out independently on worker threads, each into its own container, and appended in order)
+  const bool blocked = pack_blocked_order(window_modes);
+  const std::vector<std::vector<int32_t>> tile_rows = split_clusters(clusters, nt_max);
+  std::vector<PackedHost> parts(tile_rows.size());
+  parallel_chunks(tile_rows.size(), tile_rows.size(), [&](size_t b, size_t e, size_t) {
+    for (size_t t = b; t < e; ++t) {
+      const std::vector<int32_t>& trows = tile_rows[t];
+      PackedHost& Q = parts[t];
+      std::vector<uint64_t> U;
+      for (int32_t r : trows) U = U.empty() ? rows[r].keys : union_of(U, rows[r].keys);
+      std::vector<int32_t> where;
+      layout_tile(trows, U.data(), U.size(), nin, window_modes, blocked, Q, where);
+      const TileDesc& T = Q.tiles[0];
+      Q.vals.assign((size_t)Q.vals_count, 0.0);
+      double* V = Q.vals.data();
+      for (int n = 0; n < T.nrows; ++n) {
+        const Row& rw = rows[trows[n]];
+        size_t pos = 0;
+        for (size_t e2 = 0; e2 < rw.keys.size(); ++e2) {
+          while (U[pos] != rw.keys[e2]) ++pos;  // both sorted; rw.keys is a subset of U
+          const int at = where[pos];
+          const int ks = at / 4, kk = at % 4, nt = n / 8, nn = n % 8;
+          V[((size_t)ks * T.nt + nt) * 32 + nn * 4 + kk] = rw.vals[e2];  // lane = (n%8)*4 + (k%4)
+        }
       }
     }
-    std::sort(cl.begin(), cl.end());
-    clusters.push_back(std::move(cl));
+  });
+  tm.lap("emit tiles");
+  P = finalize_pack(std::move(P), parts, empties, nt_max);
+  if (getenv("CA_TIMING") && P.pair_products > 0)
+    fprintf(stderr, "[ca timing] pack_terms: %.1f %% of the pair products in (4 first factors) x (second factor) blocks\n",
+            100.0 * (double)P.blocked_pairs / (double)P.pair_products);
+  tm.lap("schedule");
+  {  // the row lists and the term list are gigabytes at m ~ 3000: release them here, inside the timed phases
+    std::vector<Row>().swap(rows);
+    std::vector<Term>().swap(terms);
   }
+  tm.lap("release");
+  return P;
+}
 
+int decide_nt_max(const std::vector<std::vector<int32_t>>& clusters, int32_t m, int nt_max) {
   if (nt_max >= 3) {
     // Three n-tiles only where they pay: measured at m = 2962 (86 % of the rows in clusters of 17-24 rows) the windowed
     // kernel gains 13 % (f) and 28 % (Jacobian action), at m = 999 (50 %) it loses 14 % to the single CTA per SM.
@@ -263,26 +402,47 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
       if (cl.size() > 16 && cl.size() <= 24) wide_rows += (int64_t)cl.size();
     if (!(force && force[0] != '0') && (double)wide_rows < 0.7 * (double)m) nt_max = 2;
   }
-  tm.lap("cluster");
-  if (getenv("CA_TIMING") && clusters.size() > 8) {
-    int hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // rows per cluster: 1-8, 9-16, 17-24, ...
-    for (auto& cl : clusters) hist[std::min<size_t>(7, (cl.size() - 1) / 8)]++;
-    fprintf(stderr, "[ca timing] pack_terms: %zu row clusters; sizes 1-8: %d, 9-16: %d, 17-24: %d, 25-32: %d, more: %d\n",
-            clusters.size(), hist[0], hist[1], hist[2], hist[3], hist[4] + hist[5] + hist[6] + hist[7]);
+  return nt_max;
+}
+
+std::vector<std::vector<int32_t>> split_clusters(const std::vector<std::vector<int32_t>>& clusters, int nt_max) {
+  std::vector<std::vector<int32_t>> tile_rows;
+  for (auto& cl : clusters) {
+    const int n = (int)cl.size();
+    const int slots = (n + 7) / 8;                     // n-tiles needed
+    const int ntiles = (slots + nt_max - 1) / nt_max;  // tiles needed
+    int done = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      const int remaining_tiles = ntiles - t;
+      const int take = (n - done + remaining_tiles - 1) / remaining_tiles;  // even split, <= 8*nt_max
+      tile_rows.emplace_back(cl.begin() + done, cl.begin() + done + take);
+      done += take;
+    }
   }
-  // ---- split clusters into tiles of <= 8*nt_max rows, lay out fragments
-  // (P here is the tile's own container: tiles are laid out independently on worker threads and appended in order)
-  // Blocked pair order (see emit_tile) for whole-tile packs: +1 % on the 307-mode ensemble kernel (67.9 -> 67.2 ms).
-  // Windowed packs keep the a-major order: blocks make windows of fewer k-steps (147 instead of 197 at m = 999), and
-  // the per-window barrier and the shorter per-warp shares cost more than the saved shared-memory wavefronts bring
-  // (m = 999: RHS 13.8 vs 13.3 ms, JVP 19.7 vs 18.3 ms).  CA_PACK_AMAJOR / CA_PACK_BLOCKED force either.
-  const bool blocked = getenv("CA_PACK_BLOCKED") != nullptr || (window_modes <= 0 && getenv("CA_PACK_AMAJOR") == nullptr);
-  auto emit_tile = [&rows, nin, window_modes, blocked](const std::vector<int32_t>& trows, PackedHost& P) {
+  return tile_rows;
+}
+
+// Blocked pair order (see layout_tile) for whole-tile packs: +1 % on the 307-mode ensemble kernel (67.9 -> 67.2 ms).
+// Windowed packs keep the a-major order: blocks make windows of fewer k-steps (147 instead of 197 at m = 999), and
+// the per-window barrier and the shorter per-warp shares cost more than the saved shared-memory wavefronts bring
+// (m = 999: RHS 13.8 vs 13.3 ms, JVP 19.7 vs 18.3 ms).  CA_PACK_AMAJOR / CA_PACK_BLOCKED force either.
+bool pack_blocked_order(int window_modes) {
+  return getenv("CA_PACK_BLOCKED") != nullptr || (window_modes <= 0 && getenv("CA_PACK_AMAJOR") == nullptr);
+}
+
+void layout_tile(const std::vector<int32_t>& trows, const uint64_t* U_ptr, size_t nU, int32_t nin, int window_modes,
+                 bool blocked, PackedHost& P, std::vector<int32_t>& where_out) {
+  struct USpan {  // read-only view with the vector interface the layout code uses
+    const uint64_t* p;
+    size_t n;
+    size_t size() const { return n; }
+    const uint64_t& operator[](size_t q) const { return p[q]; }
+  };
+  const USpan U{U_ptr, nU};
+  {
     TileDesc T{};
     T.nrows = (int32_t)trows.size();
     T.nt = (T.nrows + 7) / 8;
-    std::vector<uint64_t> U;
-    for (int32_t r : trows) U = U.empty() ? rows[r].keys : union_of(U, rows[r].keys);
     T.npairs = (int32_t)U.size();
     T.ks_begin = 0;
     T.vals_off = 0;
@@ -462,45 +622,23 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
       if (emitted > 0) P.windows.back().last = 1;
       T.nks = emitted / 4;
     }
-    P.vals.resize(P.vals.size() + (size_t)T.nks * T.nt * 32, 0.0);
-    double* V = P.vals.data() + T.vals_off;
-    for (int n = 0; n < T.nrows; ++n) {
-      const Row& rw = rows[trows[n]];
-      size_t pos = 0;
-      for (size_t e = 0; e < rw.keys.size(); ++e) {
-        while (U[pos] != rw.keys[e]) ++pos;  // both sorted; rw.keys is a subset of U
-        const int at = where[pos];
-        const int ks = at / 4, kk = at % 4, nt = n / 8, nn = n % 8;
-        V[((size_t)ks * T.nt + nt) * 32 + nn * 4 + kk] = rw.vals[e];  // lane = (n%8)*4 + (k%4)
-      }
-    }
+    P.vals_count = (int64_t)T.nks * T.nt * 32;
     P.padded_fma += (int64_t)T.nks * 4 * T.nt * 8;
     P.pair_products += (int64_t)T.nks * 4;
     P.tiles.push_back(T);
-  };
-
-  std::vector<std::vector<int32_t>> tile_rows;
-  for (auto& cl : clusters) {
-    const int n = (int)cl.size();
-    const int slots = (n + 7) / 8;                     // n-tiles needed
-    const int ntiles = (slots + nt_max - 1) / nt_max;  // tiles needed
-    int done = 0;
-    for (int t = 0; t < ntiles; ++t) {
-      const int remaining_tiles = ntiles - t;
-      const int take = (n - done + remaining_tiles - 1) / remaining_tiles;  // even split, <= 8*nt_max
-      tile_rows.emplace_back(cl.begin() + done, cl.begin() + done + take);
-      done += take;
-    }
+    where_out.swap(where);
   }
+}
+
+PackedHost finalize_pack(PackedHost P, std::vector<PackedHost>& parts, const std::vector<int32_t>& empties, int nt_max) {
+  const int window_modes = P.window_modes;
+  const bool have_vals = !parts.empty() && (int64_t)parts[0].vals.size() == parts[0].vals_count;
   {
-    std::vector<PackedHost> parts(tile_rows.size());
-    parallel_chunks(tile_rows.size(), tile_rows.size(), [&](size_t b, size_t e, size_t) {
-      for (size_t t = b; t < e; ++t) emit_tile(tile_rows[t], parts[t]);
-    });
+    int64_t vals_total = 0;
     for (PackedHost& Q : parts) {
       const int32_t ks_base = (int32_t)(P.pairs.size() / 4), rows_base = (int32_t)P.rows.size();
       const int32_t modes_base = (int32_t)P.modes.size(), tile_index = (int32_t)P.tiles.size();
-      const int64_t vals_base = (int64_t)P.vals.size();
+      const int64_t vals_base = vals_total;
       TileDesc T = Q.tiles[0];
       T.ks_begin += ks_base;
       T.vals_off += vals_base;
@@ -513,7 +651,8 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
         P.windows.push_back(W);
       }
       P.pairs.insert(P.pairs.end(), Q.pairs.begin(), Q.pairs.end());
-      P.vals.insert(P.vals.end(), Q.vals.begin(), Q.vals.end());
+      if (have_vals) P.vals.insert(P.vals.end(), Q.vals.begin(), Q.vals.end());
+      vals_total += Q.vals_count;
       P.rows.insert(P.rows.end(), Q.rows.begin(), Q.rows.end());
       P.modes.insert(P.modes.end(), Q.modes.begin(), Q.modes.end());
       P.max_window_modes = std::max(P.max_window_modes, Q.max_window_modes);
@@ -522,8 +661,8 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
       P.blocked_pairs += Q.blocked_pairs;
       Q = PackedHost();  // free the tile's copy
     }
+    P.vals_count = vals_total;
   }
-  tm.lap("emit tiles");
   // rows without any term still have to be written (as zeros)
   for (size_t e = 0; e < empties.size(); e += 8 * (size_t)nt_max) {
     size_t n = std::min(empties.size() - e, (size_t)8 * nt_max);
@@ -533,7 +672,7 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
     T.nks = 0;
     T.npairs = 0;
     T.ks_begin = (int32_t)(P.pairs.size() / 4);
-    T.vals_off = (int64_t)P.vals.size();
+    T.vals_off = P.vals_count;
     T.rows_off = (int32_t)P.rows.size();
     for (int k = 0; k < 8 * T.nt; ++k) P.rows.push_back(k < T.nrows ? empties[e + k] : -1);
     P.tiles.push_back(T);
@@ -614,33 +753,26 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
       std::vector<uint32_t> np;
       std::vector<double> nv;
       np.reserve(P.pairs.size());
-      nv.reserve(P.vals.size());
+      if (have_vals) nv.reserve(P.vals.size());
+      int64_t vals_at = 0;
       for (int w = 0; w < 8; ++w) {
         P.sched_ks2[w] = P.sched_ks1[w] = 0;
         for (int q = P.sched_off[w]; q < P.sched_off[w + 1]; ++q) {
           TileDesc& T = P.tiles[P.sched[q]];
           const size_t p0 = (size_t)T.ks_begin * 4, v0 = (size_t)T.vals_off;
           T.ks_begin = (int32_t)(np.size() / 4);
-          T.vals_off = (int64_t)nv.size();
+          T.vals_off = vals_at;
+          vals_at += (int64_t)T.nks * T.nt * 32;
           np.insert(np.end(), P.pairs.begin() + p0, P.pairs.begin() + p0 + (size_t)T.nks * 4);
-          nv.insert(nv.end(), P.vals.begin() + v0, P.vals.begin() + v0 + (size_t)T.nks * T.nt * 32);
+          if (have_vals) nv.insert(nv.end(), P.vals.begin() + v0, P.vals.begin() + v0 + (size_t)T.nks * T.nt * 32);
           (T.nt == 2 ? P.sched_ks2[w] : P.sched_ks1[w]) += T.nks;
         }
       }
       P.pairs.swap(np);
-      P.vals.swap(nv);
+      if (have_vals) P.vals.swap(nv);
       P.stream_layout = true;
     }
   }
-  if (getenv("CA_TIMING") && P.pair_products > 0)
-    fprintf(stderr, "[ca timing] pack_terms: %.1f %% of the pair products in (4 first factors) x (second factor) blocks\n",
-            100.0 * (double)P.blocked_pairs / (double)P.pair_products);
-  tm.lap("schedule");
-  {  // the row lists and the term list are gigabytes at m ~ 3000: release them here, inside the timed phases
-    std::vector<Row>().swap(rows);
-    std::vector<Term>().swap(terms);
-  }
-  tm.lap("release");
   return P;
 }
 

@@ -79,7 +79,56 @@ struct PackedHost {
   int64_t padded_fma = 0;       // FMAs the tiles execute per state (incl. padding)
   int64_t pair_products = 0;    // pair products formed per state (sum over tiles)
   int64_t blocked_pairs = 0;    // of these, in (4 first factors) x (one second factor) k-steps
+  int64_t vals_count = 0;       // value slots ([k-step][n-tile][lane]); == vals.size() when the values are held here
 };
+
+// ---- staged interface (the device model build, model_build.cu, runs the bulk data movement of these stages on
+// the GPU and reuses the decision logic below verbatim, so that both builds produce the same pack bit for bit)
+
+constexpr int kPackSketch = 8;  // min-hash values per row
+// hash h (0..kPackSketch-1) of pair id key = a * nin + b; a row's sketch is the minimum over its keys
+inline uint64_t pack_sketch_hash_host(uint64_t key, int h) {
+  uint64_t x = key * 0x100000001b3ull + (uint64_t)h * 0x51ed27ull;
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+
+// The packer's view of the rows' pair sets during clustering: sizes, sketches and unions against one open set.
+struct RowSetOps {
+  virtual ~RowSetOps() {}
+  virtual int32_t nrows() const = 0;
+  virtual int64_t nkeys(int32_t r) const = 0;
+  virtual const uint64_t* sketch(int32_t r) const = 0;  // kPackSketch values
+  virtual int batch_hint() const = 0;                    // how many union sizes to ask for at once
+  virtual void open(int32_t seed) = 0;                   // open set U := keys(seed)
+  virtual int64_t open_size() const = 0;
+  virtual void union_sizes(const int32_t* cand, int n, int64_t* out) = 0;  // |U + keys(cand[q])|
+  virtual void absorb(int32_t r) = 0;                    // U := U + keys(r)
+};
+// Greedy clustering of rows with near-identical pair sets (seeds by descending size; candidates agreeing in at least half
+// of the sketch; accepted while the union stays within 1.2 x the larger set).  Clusters hold ascending row indices.
+void cluster_rows(RowSetOps& sets, std::vector<std::vector<int32_t>>& clusters, std::vector<int32_t>& empties);
+// The rule for tiles of three n-tiles (windowed packs): only where clusters of 17-24 rows hold >= 70 % of the rows.
+int decide_nt_max(const std::vector<std::vector<int32_t>>& clusters, int32_t m, int nt_max);
+// Cuts clusters into tiles of <= 8 * nt_max rows (even split).
+std::vector<std::vector<int32_t>> split_clusters(const std::vector<std::vector<int32_t>>& clusters, int nt_max);
+// Pair sequence of one tile: given the sorted union U of the tile's pair ids (a * nin + b), emits into P (which must be
+// empty) the tile descriptor, its rows, pair words, windows and window mode lists -- everything but the values -- and
+// where[q] = position of U[q] in the emitted (padded) pair sequence.  P.vals_count is the number of value slots.
+void layout_tile(const std::vector<int32_t>& trows, const uint64_t* U, size_t nU, int32_t nin, int window_modes,
+                 bool blocked, PackedHost& P, std::vector<int32_t>& where);
+bool pack_blocked_order(int window_modes);
+// Appends the per-tile parts (in order), adds the empty-row tiles, sorts tiles and windows, builds the warp schedule and
+// (whole-tile packs) the schedule-order layout.  When the parts carry values they are moved along; otherwise only the
+// offsets are computed (vals_count / TileDesc::vals_off) and the caller places the values itself.
+PackedHost finalize_pack(PackedHost P, std::vector<PackedHost>& parts, const std::vector<int32_t>& empties, int nt_max);
+
+// FNV-1a digests of the arrays of a pack, in the order: tiles, pairs, vals, rows, windows, modes, sched (+ schedule
+// scalars), counters.  Two packs are the same pack iff all eight agree (diagnostics: host packer vs device build).
+void pack_digest(const PackedHost& P, uint64_t out[8]);
+uint64_t fnv1a(const void* data, size_t bytes, uint64_t h = 0xcbf29ce484222325ull);
 
 // In-place sort by (i, a, b): counting sort by output row, then per-row sorts on worker threads.
 void sort_terms(std::vector<Term>& terms, int32_t m);

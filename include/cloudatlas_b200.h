@@ -275,6 +275,12 @@ int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64_t nnz, int
                          int64_t* pair_products, int64_t* mismatches, int64_t* nwindows,
                          int64_t* max_window_modes);
 
+/* FNV-1a digests of the eight parts of the pack ca_bilinear_create would build (tile descriptors, pair words, values,
+ * row lists, window descriptors, window mode lists, warp schedule, counters): two packs are identical iff all agree.
+ * Used to show that the device model build (ca_model_create_dev) and the host packer produce the same pack. */
+int32_t ca_selftest_pack_digest(const int64_t* ijk, const double* val, int64_t nnz, int64_t m, int32_t symmetric,
+                                int32_t window_modes, uint64_t* digest8);
+
 /* Generates the model-specialised ensemble kernel (m <= 48) for a quadratic operator plus a dense linear pattern and
  * compiles it with NVRTC for sm_100a; reports the cubin size and the CTA shape.  No device needed: the module is
  * not loaded.  Fails with CA_ERR_UNSUPPORTED (and the NVRTC log as error text) if the source does not compile. */
