@@ -149,6 +149,42 @@ def all_gather_slabs(lin, idx, val, m, group=None):
     return lin_all, idx_all, val_all
 
 
+def assemble_device(alpha, gamma, ijkl, normalize=False, group=None, distributed=None, dense=False, grid=(0, 0, 0)):
+    """The assembled operators as CUDA tensors, for ``ModelOperators.from_device``: (lin, idx, val, stats) with
+    ``lin`` [4, m, m] (B, A1, A2, D; each COLUMN-major, i.e. ``lin[q].t()`` is the matrix), ``idx`` [3, nnz] int64
+    (1-based i, j, k in the reference's lexicographic order) and ``val`` [nnz].  With torch.distributed initialised
+    every rank assembles its range of output modes and the slabs are exchanged with one all-gather over NCCL; the
+    gathered operator stays on the device -- the host sees none of it."""
+    import time
+    import torch
+    m = np.asarray(ijkl).shape[0]
+    if distributed is None:
+        import torch.distributed as dist
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    stats = {"world": 1, "gather_seconds": 0.0, "gather_bytes": 0}
+    if not distributed:
+        slab = AssemblySlab(alpha, gamma, ijkl, normalize, dense=dense, grid=grid)
+        lin, idx, val = slab.to_torch()
+    else:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        bounds = row_partition(m, world, 128 if dense else 1)
+        slab = AssemblySlab(alpha, gamma, ijkl, normalize, bounds[rank], bounds[rank + 1], dense=dense, grid=grid)
+        lin, idx, val = slab.to_torch()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        lin, idx, val = all_gather_slabs(lin, idx, val, m, group)
+        ev1.record()
+        torch.cuda.synchronize()
+        stats.update(world=world, gather_seconds=ev0.elapsed_time(ev1) * 1e-3, gather_wall_seconds=time.perf_counter() - t0,
+                     gather_bytes=int(lin.numel() * 8 + idx.numel() * 8 + val.numel() * 8))
+    stats.update(device_seconds=slab.device_seconds, nnz_local=slab.nnz, dense=slab.dense_info() if dense else None)
+    lin = lin.transpose(1, 2).contiguous()   # row-major slabs -> column-major matrices (4 m^2 doubles, on the device)
+    return lin, idx, val, stats
+
+
 def assemble(alpha, gamma, ijkl, normalize=False, group=None, distributed=None, dense=False, grid=(0, 0, 0)):
     """Full B, A1, A2 (m x m, column-major numpy) and N's COO (ijk nnz x 3 1-based, val) on every rank.
 

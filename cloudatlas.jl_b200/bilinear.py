@@ -34,9 +34,25 @@ def _stream():
     return vp(torch.cuda.current_stream().cuda_stream)
 
 
-def _colmajor_ensemble(X):
-    """torch CUDA ensemble -> (tensor, nstates, ld).  Accepts an (nstates, m) tensor whose
-    memory is column-major (stride (1, ld)), which is what Julia hands over."""
+def _check_device_tensor(X):
+    """The library dereferences raw pointers: only float64 tensors on the current CUDA device may reach it."""
+    import torch
+    if not X.is_cuda:
+        raise CloudAtlasError(1, "expected a CUDA tensor (host data goes through the numpy entry points)")
+    if X.dtype != torch.float64:
+        raise CloudAtlasError(1, f"expected a float64 tensor, got {X.dtype}")
+    if X.device.index != torch.cuda.current_device():
+        raise CloudAtlasError(1, f"tensor is on cuda:{X.device.index}, the current device is "
+                                 f"cuda:{torch.cuda.current_device()} (handles live on the device that was current "
+                                 "when they were created)")
+
+
+def _colmajor_ensemble(X, m=None):
+    """torch CUDA ensemble -> (tensor, nstates, ld).  Accepts an (nstates, m) float64 tensor on the current device
+    whose memory is column-major (stride (1, ld)), which is what Julia hands over; ``m``: required column count."""
+    _check_device_tensor(X)
+    if m is not None and (X.dim() != 2 or X.shape[1] != m):
+        raise CloudAtlasError(1, f"ensemble has shape {tuple(X.shape)}, expected nstates x {m}")
     if X.dim() == 2 and X.shape[0] == 1:  # a single state: any stride along the (length-1) state axis
         return X, 1, max(X.stride(1), 1)
     if X.dim() != 2 or X.stride(0) != 1:
@@ -119,6 +135,8 @@ class SparseBilinear:
             x = np.ascontiguousarray(x)
             out = np.empty(self.m)
             yy = None if y is None else np.ascontiguousarray(y, dtype=np.float64)
+            if yy is not None and yy.shape != (self.m,):
+                raise CloudAtlasError(1, f"y has shape {yy.shape}, expected ({self.m},)")
             check(_eval(self._h, _f64(x), None if yy is None else _f64(yy), _f64(out)))
             return out
         if y is not None:
@@ -142,7 +160,7 @@ class SparseBilinear:
         if Y is None:
             check(_eval_b_dev(self._h, vp(X.data_ptr()), n, ld, vp(OUT.data_ptr()), n, _stream()))
         else:
-            Y, n2, ld2 = _colmajor_ensemble(Y)
+            Y, n2, ld2 = _colmajor_ensemble(Y, self.m)
             if n2 != n or ld2 != ld:
                 raise CloudAtlasError(1, "X and Y must have the same shape and leading dimension")
             check(_eval2_b_dev(self._h, vp(X.data_ptr()), vp(Y.data_ptr()), n, ld, vp(OUT.data_ptr()), n, _stream()))
@@ -150,8 +168,8 @@ class SparseBilinear:
 
     def jvp(self, X, V):
         """DN(x_s) v_s = N(x_s, v_s) + N(v_s, x_s) for CUDA ensembles (matrix-free Jacobian action)."""
-        X, n, ld = _colmajor_ensemble(X)
-        V, n2, ld2 = _colmajor_ensemble(V)
+        X, n, ld = _colmajor_ensemble(X, self.m)
+        V, n2, ld2 = _colmajor_ensemble(V, self.m)
         if n2 != n or ld2 != ld:
             raise CloudAtlasError(1, "X and V must have the same shape and leading dimension")
         OUT = ensemble_empty(n, self.m, X.device)
@@ -172,6 +190,9 @@ class SparseBilinear:
             return DN
         if _is_torch(x):
             import torch
+            _check_device_tensor(x)
+            if x.dim() != 1 or x.numel() != self.m:
+                raise CloudAtlasError(1, f"x has {x.numel()} elements, expected {self.m}")
             DN = torch.empty((self.m, self.m), dtype=torch.float64, device=x.device).t()  # column-major
             check(_jac_dev(self._h, vp(x.contiguous().data_ptr()), vp(DN.data_ptr()), _stream()))
             return DN

@@ -95,6 +95,8 @@ void ca_model::eval_dev(int mode, const double* dX, const double* dV, int64_t ns
   if (mode == MODE_QUAD && m <= kJitMaxM && nstates >= kJitMinStates && !small.failed) {
     if (!small_tried) {
       small_tried = true;
+      host_linear();
+      host_qterms();
       std::vector<int32_t> li, lj;
       for (int j = 0; j < (int)m; ++j)
         for (int i = 0; i < (int)m; ++i)
@@ -127,19 +129,41 @@ void ca_model::eval_dev(int mode, const double* dX, const double* dV, int64_t ns
 
 extern "C" {
 
-int32_t ca_model_create(const double* B, const double* A1, const double* A2, int64_t m64,
-                        const int64_t* ijk, const double* val, int64_t nnz, ca_model** out) {
-  return guarded([&] {
-    if (!out) fail(CA_ERR_INVALID, "ca_model_create: out is null");
-    *out = nullptr;
-    if (m64 <= 0 || !B || !A1 || !A2) fail(CA_ERR_INVALID, "ca_model_create: bad operator arguments");
-    if (nnz < 0 || (nnz > 0 && (!ijk || !val))) fail(CA_ERR_INVALID, "ijk and val must have same number of rows");
-    const int m = (int)m64;
-    for (int64_t r = 0; r < nnz; ++r)
-      for (int c = 0; c < 3; ++c)
-        if (ijk[r + c * nnz] < 1 || ijk[r + c * nnz] > m64)
-          fail(CA_ERR_INVALID, "ca_model_create: N entry %lld has an index outside 1:%lld", (long long)r + 1, (long long)m64);
+}  // extern "C"
 
+// Solver CSR of the symmetrised folded Q by output row, for the in-kernel evaluation of the device-resident
+// Newton-hookstep (only models small enough for that solver: 3 m^2 doubles must fit in shared memory)
+static void build_solver_csr(ca_model* h) {
+  const int m = (int)h->m;
+  if (m > 96) return;
+  const std::vector<Term> sym = merge_terms(h->host_qterms(), true);
+  std::vector<int32_t> rowptr(m + 1, 0);
+  std::vector<uint32_t> ab(sym.size());
+  std::vector<double> qv(sym.size());
+  for (size_t e = 0; e < sym.size(); ++e) {
+    ab[e] = (uint32_t)sym[e].a | ((uint32_t)sym[e].b << 16);
+    qv[e] = sym[e].v;
+    rowptr[sym[e].i + 1]++;
+  }
+  for (int i = 0; i < m; ++i) rowptr[i + 1] += rowptr[i];
+  h->q_rowptr.upload(rowptr.data(), rowptr.size());
+  h->q_ab.upload(ab.data(), ab.size());
+  h->q_val.upload(qv.data(), qv.size());
+  CA_CUDA(cudaStreamSynchronize(nullptr));
+}
+
+bool build_model_on_device(ca_model* h, const double* dB, const double* dA1, const double* dA2, int64_t m64,
+                           const int64_t* di, const int64_t* dj, const int64_t* dk, const double* dval, int64_t nnz,
+                           cudaStream_t st);
+
+// The host build: B^-1 folding, row clustering and fragment layout on worker threads (the round-1 path; kept for
+// operators the device build does not take -- unsorted or duplicated COO, large blocks of B -- and as its checker).
+static void build_model_on_host(ca_model* hmodel, const double* B, const double* A1, const double* A2, int64_t m64,
+                                const int64_t* ijk, const double* val, int64_t nnz) {
+  {
+    ca_model* h = hmodel;
+    const int m = (int)m64;
+    const double t_start_host = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }();
     PhaseTimer tm("ca_model_create");
     // ---- blocks of B = connected components of its non-zero pattern
     std::vector<int> comp(m);
@@ -311,10 +335,6 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
       });
     }
     tm.lap("fold B^-1");
-    require_device();
-    std::unique_ptr<ca_model> h(new ca_model);
-    CA_CUDA(cudaGetDevice(&h->device));
-    h->m = m;
     h->nblocks = (int64_t)blocks.size();
     // linear placeholders (value 1) mark the slots that set_R patches
     std::vector<Term> all;
@@ -358,25 +378,7 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
           l2.push_back(hL2[row + (size_t)m * a]);
         }
       }
-    // CSR of the symmetrised Q by output row, for the in-kernel evaluation of the device-resident solver
-    // (only models small enough for that solver: 3 m^2 doubles must fit in shared memory)
-    if (m <= 96) {
-      const std::vector<Term> sym = merge_terms(h->qterms, true);
-      std::vector<int32_t> rowptr(m + 1, 0);
-      std::vector<uint32_t> ab(sym.size());
-      std::vector<double> qv(sym.size());
-      for (size_t e = 0; e < sym.size(); ++e) {
-        ab[e] = (uint32_t)sym[e].a | ((uint32_t)sym[e].b << 16);
-        qv[e] = sym[e].v;
-        rowptr[sym[e].i + 1]++;
-      }
-      for (int i = 0; i < m; ++i) rowptr[i + 1] += rowptr[i];
-      h->q_rowptr.upload(rowptr.data(), rowptr.size());
-      h->q_ab.upload(ab.data(), ab.size());
-      h->q_val.upload(qv.data(), qv.size());
-      CA_CUDA(cudaStreamSynchronize(nullptr));
-    }
-    tm.lap("slots+csr");
+    tm.lap("slots");
     h->nnz_lin = (int64_t)pos.size();
     h->op.upload(P);
     h->lin_pos.upload(pos.data(), pos.size());
@@ -391,7 +393,7 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
     h->hA2.assign(A2, A2 + (size_t)m * m);
     h->ncoo.resize((size_t)nnz);
     {
-      ca_model* hp = h.get();
+      ca_model* hp = h;
       parallel_chunks((size_t)nnz, 64, [&](size_t b, size_t e, size_t) {
         for (size_t r = b; r < e; ++r)
           hp->ncoo[r] = Term{(int32_t)(ijk[r] - 1), (int32_t)(ijk[r + nnz] - 1), (int32_t)(ijk[r + 2 * nnz] - 1), val[r]};
@@ -410,7 +412,189 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
     }
     CA_CUDA(cudaStreamSynchronize(nullptr));
     tm.lap("upload");
+    h->build_stats = ModelBuildStats();
+    h->build_stats.total = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }() - t_start_host;
+    h->build_stats.ntiles = (int64_t)P.tiles.size();
+    h->build_stats.nterms = P.nterms;
+  }
+}
+
+// column-major m x m device copy of a host matrix etc.: the host entry point feeds the device build
+extern "C" {
+
+int32_t ca_model_create(const double* B, const double* A1, const double* A2, int64_t m64,
+                        const int64_t* ijk, const double* val, int64_t nnz, ca_model** out) {
+  return guarded([&] {
+    if (!out) fail(CA_ERR_INVALID, "ca_model_create: out is null");
+    *out = nullptr;
+    if (m64 <= 0 || !B || !A1 || !A2) fail(CA_ERR_INVALID, "ca_model_create: bad operator arguments");
+    if (nnz < 0 || (nnz > 0 && (!ijk || !val))) fail(CA_ERR_INVALID, "ijk and val must have same number of rows");
+    require_device();
+    std::unique_ptr<ca_model> h(new ca_model);
+    CA_CUDA(cudaGetDevice(&h->device));
+    h->m = m64;
+    bool built = false;
+    if (!getenv("CA_BUILD_HOST") && m64 + 1 <= 32768) {
+      const size_t mm = (size_t)m64 * (size_t)m64;
+      DeviceBuffer<double> dB, dA1, dA2, dv;
+      DeviceBuffer<int64_t> dijk;
+      dB.upload(B, mm);
+      dA1.upload(A1, mm);
+      dA2.upload(A2, mm);
+      dijk.upload(ijk, (size_t)nnz * 3);
+      dv.upload(val, (size_t)nnz);
+      built = build_model_on_device(h.get(), dB.ptr, dA1.ptr, dA2.ptr, m64, dijk.ptr, dijk.ptr + nnz, dijk.ptr + 2 * nnz,
+                                    dv.ptr, nnz, nullptr);
+      if (!built) {
+        h.reset(new ca_model);
+        CA_CUDA(cudaGetDevice(&h->device));
+        h->m = m64;
+      }
+    }
+    if (!built) {
+      for (int64_t r = 0; r < nnz; ++r)  // (the device build checks the indices itself)
+        for (int c = 0; c < 3; ++c)
+          if (ijk[r + c * nnz] < 1 || ijk[r + c * nnz] > m64)
+            fail(CA_ERR_INVALID, "ca_model_create: N entry %lld has an index outside 1:%lld", (long long)r + 1, (long long)m64);
+      build_model_on_host(h.get(), B, A1, A2, m64, ijk, val, nnz);
+    }
+    build_solver_csr(h.get());
     *out = h.release();
+  });
+}
+
+int32_t ca_model_create_dev(const double* dB, const double* dA1, const double* dA2, int64_t m64, const int64_t* d_i,
+                            const int64_t* d_j, const int64_t* d_k, const double* d_val, int64_t nnz, void* stream,
+                            ca_model** out) {
+  return guarded([&] {
+    if (!out) fail(CA_ERR_INVALID, "ca_model_create_dev: out is null");
+    *out = nullptr;
+    if (m64 <= 0 || !dB || !dA1 || !dA2) fail(CA_ERR_INVALID, "ca_model_create_dev: bad operator arguments");
+    if (nnz < 0 || (nnz > 0 && (!d_i || !d_j || !d_k || !d_val))) fail(CA_ERR_INVALID, "ijk and val must have same number of rows");
+    require_device();
+    std::unique_ptr<ca_model> h(new ca_model);
+    CA_CUDA(cudaGetDevice(&h->device));
+    h->m = m64;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool built = !getenv("CA_BUILD_HOST") &&
+                 build_model_on_device(h.get(), dB, dA1, dA2, m64, d_i, d_j, d_k, d_val, nnz, st);
+    if (!built) {  // operators the device build does not take: through the host build
+      h.reset(new ca_model);
+      CA_CUDA(cudaGetDevice(&h->device));
+      h->m = m64;
+      const size_t mm = (size_t)m64 * (size_t)m64;
+      std::vector<double> B(mm), A1(mm), A2(mm), val((size_t)nnz);
+      std::vector<int64_t> ijk((size_t)nnz * 3);
+      CA_CUDA(cudaStreamSynchronize(st));
+      CA_CUDA(cudaMemcpy(B.data(), dB, mm * sizeof(double), cudaMemcpyDeviceToHost));
+      CA_CUDA(cudaMemcpy(A1.data(), dA1, mm * sizeof(double), cudaMemcpyDeviceToHost));
+      CA_CUDA(cudaMemcpy(A2.data(), dA2, mm * sizeof(double), cudaMemcpyDeviceToHost));
+      if (nnz > 0) {
+        CA_CUDA(cudaMemcpy(ijk.data(), d_i, (size_t)nnz * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        CA_CUDA(cudaMemcpy(ijk.data() + nnz, d_j, (size_t)nnz * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        CA_CUDA(cudaMemcpy(ijk.data() + 2 * nnz, d_k, (size_t)nnz * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        CA_CUDA(cudaMemcpy(val.data(), d_val, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost));
+      }
+      build_model_on_host(h.get(), B.data(), A1.data(), A2.data(), m64, ijk.data(), val.data(), nnz);
+    }
+    build_solver_csr(h.get());
+    *out = h.release();
+  });
+}
+
+// Digests of the model's device-resident build products (diagnostics: device build vs host build).  [0..7]: the packed
+// operator as pack_digest(); [8], [9]: L1, L2; [10]: linear slots (sorted by position); [11]: streaming form of Q, row
+// by row (built if absent).
+int32_t ca_model_digest(ca_model* h, uint64_t* digest12) {
+  return guarded([&] {
+    if (!h || !digest12) fail(CA_ERR_INVALID, "null argument");
+    h->bind();
+    CA_CUDA(cudaDeviceSynchronize());
+    auto fetch = [](auto& vec, const auto& buf, size_t n) {
+      vec.resize(n);
+      if (n) CA_CUDA(cudaMemcpy(vec.data(), buf.ptr, n * sizeof(vec[0]), cudaMemcpyDeviceToHost));
+    };
+    const DevicePack& op = h->op;
+    PackedHost P;
+    P.m = op.m;
+    P.nin = op.nin;
+    P.symmetric = op.symmetric;
+    P.window_modes = op.window_modes;
+    P.max_window_modes = op.max_window_modes;
+    P.nterms = op.nterms;
+    P.npairs_distinct = op.npairs_distinct;
+    P.padded_fma = op.padded_fma;
+    P.pair_products = op.pair_products;
+    P.stream_layout = op.stream_layout;
+    for (int w = 0; w < 9; ++w) P.sched_off[w] = op.sched_off[w];
+    for (int w = 0; w < 8; ++w) {
+      P.sched_nt2[w] = op.sched_nt2[w];
+      P.sched_ks2[w] = op.sched_ks2[w];
+      P.sched_ks1[w] = op.sched_ks1[w];
+    }
+    fetch(P.tiles, op.tiles, (size_t)op.ntiles);
+    P.pairs = op.host_pairs;
+    fetch(P.rows, op.rows, op.rows.count);
+    fetch(P.windows, op.windows, (size_t)op.nwin);
+    fetch(P.modes, op.modes, op.modes.count);
+    fetch(P.sched, op.sched, op.sched.count);
+    int64_t nvals = 0;
+    for (const TileDesc& T : P.tiles) nvals = std::max<int64_t>(nvals, T.vals_off + (int64_t)T.nks * T.nt * 32);
+    fetch(P.vals, op.vals, (size_t)nvals);
+    // R-dependent linear slots: digest the pack as built (slots hold the placeholder 1) -- restore them first
+    std::vector<int64_t> pos;
+    std::vector<double> l1, l2;
+    fetch(pos, h->lin_pos, (size_t)h->nnz_lin);
+    fetch(l1, h->lin_l1, (size_t)h->nnz_lin);
+    fetch(l2, h->lin_l2, (size_t)h->nnz_lin);
+    for (int64_t p : pos) P.vals[(size_t)p] = 1.0;
+    pack_digest(P, digest12);
+    std::vector<double> M;
+    fetch(M, h->L1, (size_t)h->m * h->m);
+    digest12[8] = fnv1a(M.data(), M.size() * sizeof(double));
+    fetch(M, h->L2, (size_t)h->m * h->m);
+    digest12[9] = fnv1a(M.data(), M.size() * sizeof(double));
+    std::vector<size_t> ord(pos.size());
+    std::iota(ord.begin(), ord.end(), 0);
+    std::sort(ord.begin(), ord.end(), [&](size_t x, size_t y) { return pos[x] < pos[y]; });
+    uint64_t hs = fnv1a(nullptr, 0);
+    for (size_t o : ord) {
+      hs = fnv1a(&pos[o], 8, hs);
+      hs = fnv1a(&l1[o], 8, hs);
+      hs = fnv1a(&l2[o], 8, hs);
+    }
+    digest12[10] = hs;
+    const StreamPack& sp = h->streaming();
+    std::vector<StreamChunk> ch;
+    std::vector<uint32_t> ab;
+    std::vector<double> sv;
+    fetch(ch, sp.chunks, (size_t)sp.nchunks);
+    fetch(ab, sp.ab, sp.ab.count);
+    fetch(sv, sp.val, sp.val.count);
+    hs = fnv1a(nullptr, 0);
+    for (const StreamChunk& c : ch) {
+      const int64_t f[2] = {c.row, c.count};
+      hs = fnv1a(f, sizeof f, hs);
+      hs = fnv1a(ab.data() + c.begin, (size_t)c.count * sizeof(uint32_t), hs);
+      hs = fnv1a(sv.data() + c.begin, (size_t)c.count * sizeof(double), hs);
+    }
+    digest12[11] = hs;
+  });
+}
+
+int32_t ca_model_build_info(const ca_model* h, int32_t* on_device, double* seconds9, int64_t* nclusters,
+                            int64_t* ntiles, int64_t* nterms) {
+  return guarded([&] {
+    if (!h) fail(CA_ERR_INVALID, "null handle");
+    const ModelBuildStats& S = h->build_stats;
+    if (on_device) *on_device = S.on_device;
+    if (seconds9) {
+      const double v[9] = {S.total, S.blocks, S.fold, S.symmetrise, S.cluster, S.tile_unions, S.layout, S.place, S.stream};
+      for (int q = 0; q < 9; ++q) seconds9[q] = v[q];
+    }
+    if (nclusters) *nclusters = S.nclusters;
+    if (ntiles) *ntiles = S.ntiles;
+    if (nterms) *nterms = S.nterms;
   });
 }
 
@@ -608,16 +792,17 @@ extern "C" int32_t ca_model_cnab2_batched_dev(ca_model* h, const double* dX0, in
     cudaStream_t st = (cudaStream_t)stream;
     const int m = (int)h->m;
     const bool few = nstates <= kStreamMaxStates;
+    h->host_linear();
     // ---- N(x): raw operator
     if (few ? !h->nraw_stream_built : !h->nraw_built) {
       if (few) {
-        h->nraw_stream.build(h->ncoo, m, true);
+        h->nraw_stream.build(h->host_ncoo(), m, true);
         h->nraw_stream_built = true;
       } else {
-        h->nraw.upload(pack_terms(h->ncoo, m, true, nt_max_for(window_modes_for(m)), window_modes_for(m)));
+        h->nraw.upload(pack_terms(h->host_ncoo(), m, true, nt_max_for(window_modes_for(m)), window_modes_for(m)));
         h->nraw_built = true;
         if (!batched_fits(h->nraw, MODE_QUAD) && !h->nraw_stream_built) {
-          h->nraw_stream.build(h->ncoo, m, true);
+          h->nraw_stream.build(h->host_ncoo(), m, true);
           h->nraw_stream_built = true;
         }
       }

@@ -8,6 +8,12 @@
 namespace ca {
 
 void DevicePack::upload(const PackedHost& P) {
+  upload_meta(P);
+  vals.upload(P.vals.data(), P.vals.size());
+  CA_CUDA(cudaStreamSynchronize(nullptr));  // the host vectors may die after we return
+}
+
+void DevicePack::upload_meta(const PackedHost& P) {
   m = P.m;
   nin = P.nin;
   ntiles = (int32_t)P.tiles.size();
@@ -40,7 +46,6 @@ void DevicePack::upload(const PackedHost& P) {
   sched_imbalance = P.sched_imbalance;
   host_pairs = P.pairs;
   for (auto& b : pairs_mt) b.release();
-  vals.upload(P.vals.data(), P.vals.size());
   rows.upload(P.rows.data(), P.rows.size());
   CA_CUDA(cudaStreamSynchronize(nullptr));  // the host vectors may die after we return
 }

@@ -31,6 +31,8 @@ struct DevicePack {
   DeviceBuffer<WindowDesc> windows;
   DeviceBuffer<int32_t> modes;
   void upload(const PackedHost& P);
+  // everything but the values (device build: the values are placed on the device, DevicePack::vals is filled there)
+  void upload_meta(const PackedHost& P);
 };
 
 // mode: MODE_QUAD (Y ignored), MODE_ORDERED (u = X, w = Y), MODE_JVP (X = state, Y = direction).
@@ -85,6 +87,9 @@ struct StreamPack {
   void build(std::vector<Term> terms, int32_t m, bool symmetric);
   // rectangular operator: m outputs, n_inputs input modes (the constant-one pseudo mode is n_inputs)
   void build_rect(std::vector<Term> terms, int32_t m, int32_t n_inputs);
+  // takes device arrays of entries (a | b << 16, value) whose rows are the ranges [row_begin[i], row_end[i]) (host)
+  void adopt(DeviceBuffer<uint32_t>&& ab_, DeviceBuffer<double>&& val_, const std::vector<int64_t>& row_begin,
+             const std::vector<int64_t>& row_end, int32_t m, bool symmetric);
 };
 // Optional dense linear part (row-major L1r, L2r, value L1 + L2*invR), may be null.
 void launch_stream(const StreamPack& sp, int mode, const double* dX, const double* dY, int64_t nstates,

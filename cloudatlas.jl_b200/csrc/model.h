@@ -5,6 +5,29 @@
 #include "bilinear.h"
 #include "jit_small.h"
 
+namespace ca {
+
+// Seconds per phase of the model build (ca_model_build_info); on_device = 1 for the device build (model_build.cu).
+struct ModelBuildStats {
+  double blocks = 0, fold = 0, symmetrise = 0, cluster = 0, tile_unions = 0, layout = 0, place = 0, stream = 0, total = 0;
+  int32_t on_device = 0;
+  int64_t nclusters = 0, ntiles = 0, nterms = 0;
+};
+
+// The folded quadratic operator Q = B^-1 N of a device-built model, block-dense and device-resident: block b holds
+// g_b rows x |U_b| ordered pairs (j * m + k, ascending) of values, zeros included.  Expanded into host terms only when
+// a lazily built structure needs them (Df pattern, generated small kernel, in-kernel solver CSR).
+struct FoldedDevice {
+  int64_t total_u = 0;
+  std::vector<int64_t> u_off, dense_off;  // [nb+1] offsets into ukeys / R
+  std::vector<int32_t> row_off, rows;     // members of the blocks
+  DeviceBuffer<uint32_t> ukeys;
+  DeviceBuffer<double> R;
+  void to_host_terms(std::vector<Term>& out, int32_t m) const;
+};
+
+}  // namespace ca
+
 struct ca_model {
   int device = 0;
   int64_t m = 0;
@@ -13,6 +36,41 @@ struct ca_model {
   ca::JacobianPack jac;        // of Q, built on first use (Df, device-resident solver)
   bool jac_built = false;
   std::vector<ca::Term> qterms;  // folded Q = B^-1 N (ordered j,k), kept on the host for the lazy builds
+  // device build: the folded operator, N as given and A1, A2 stay on the device; host copies are fetched on first use
+  ca::FoldedDevice folded;
+  bool qterms_on_device = false, ncoo_on_device = false, linear_on_device = false;
+  ca::DeviceBuffer<ca::Term> dncoo;
+  ca::DeviceBuffer<double> dA1, dA2;
+  ca::ModelBuildStats build_stats;
+  const std::vector<ca::Term>& host_qterms() {
+    if (qterms_on_device) {
+      folded.to_host_terms(qterms, (int32_t)m);
+      qterms_on_device = false;
+    }
+    return qterms;
+  }
+  const std::vector<ca::Term>& host_ncoo() {
+    if (ncoo_on_device) {
+      ncoo.resize(dncoo.count);
+      if (dncoo.count) CA_CUDA(cudaMemcpy(ncoo.data(), dncoo.ptr, dncoo.count * sizeof(ca::Term), cudaMemcpyDeviceToHost));
+      ncoo_on_device = false;
+    }
+    return ncoo;
+  }
+  // fills hB, hA1, hA2, hL1, hL2 (column-major)
+  void host_linear() {
+    if (!linear_on_device) return;
+    const size_t mm = (size_t)m * m;
+    hA1.resize(mm);
+    hA2.resize(mm);
+    hL1.resize(mm);
+    hL2.resize(mm);
+    CA_CUDA(cudaMemcpy(hA1.data(), dA1.ptr, mm * sizeof(double), cudaMemcpyDeviceToHost));
+    CA_CUDA(cudaMemcpy(hA2.data(), dA2.ptr, mm * sizeof(double), cudaMemcpyDeviceToHost));
+    CA_CUDA(cudaMemcpy(hL1.data(), L1.ptr, mm * sizeof(double), cudaMemcpyDeviceToHost));
+    CA_CUDA(cudaMemcpy(hL2.data(), L2.ptr, mm * sizeof(double), cudaMemcpyDeviceToHost));
+    linear_on_device = false;
+  }
   ca::SmallKernel small;         // model-specialised ensemble kernel for small m, compiled on first use
   bool small_tried = false;
   std::vector<double> hL1, hL2;  // host copies (column-major) for re-targeting R
@@ -35,7 +93,7 @@ struct ca_model {
   ca::DeviceBuffer<double> L1r, L2r;  // row-major copies of L1, L2 for the streaming kernel's dense part
   ca::StreamPack& streaming() {
     if (!stream_built) {
-      stream.build(qterms, (int32_t)m, true);
+      stream.build(host_qterms(), (int32_t)m, true);
       stream_built = true;
     }
     return stream;
@@ -46,7 +104,7 @@ struct ca_model {
                 double* dOUT, int64_t ldo, cudaStream_t st);
   ca::JacobianPack& jacobian() {
     if (!jac_built) {
-      jac.build(qterms, (int32_t)m);
+      jac.build(host_qterms(), (int32_t)m);
       jac_built = true;
     }
     return jac;

@@ -17,7 +17,7 @@ namespace ca {
 struct Term {
   int32_t i, a, b;  // output row, first and second factor (0-based; a or b == m means the constant 1)
   double v;
-  Term() {}  // deliberately empty: std::vector<Term>(n) must not zero-fill gigabytes that are overwritten right away
+  __host__ __device__ Term() {}  // deliberately empty: std::vector<Term>(n) must not zero-fill gigabytes that are overwritten right away
   Term(int32_t i_, int32_t a_, int32_t b_, double v_) : i(i_), a(a_), b(b_), v(v_) {}
 };
 

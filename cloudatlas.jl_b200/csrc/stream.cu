@@ -256,6 +256,35 @@ void StreamPack::build(std::vector<Term> terms, int32_t m_, bool symmetric_) {
   CA_CUDA(cudaStreamSynchronize(nullptr));
 }
 
+void StreamPack::adopt(DeviceBuffer<uint32_t>&& ab_, DeviceBuffer<double>&& val_, const std::vector<int64_t>& row_begin,
+                       const std::vector<int64_t>& row_end, int32_t m_, bool symmetric_) {
+  m = m_;
+  nin = m + 1;
+  symmetric = symmetric_;
+  if (nin > 65536) fail(CA_ERR_UNSUPPORTED, "m = %d exceeds the 16-bit mode index", m);
+  nentries = 0;
+  for (int i = 0; i < m; ++i) nentries += row_end[(size_t)i] - row_begin[(size_t)i];
+  int64_t clen = nentries / (148 * 64);  // same chunking rule as build()
+  clen = std::max<int64_t>(128, std::min<int64_t>(4096, clen));
+  clen = (clen + 31) / 32 * 32;
+  std::vector<StreamChunk> hchunks;
+  std::vector<int32_t> rcp((size_t)m + 1, 0);
+  for (int i = 0; i < m; ++i) {
+    for (int64_t b = row_begin[(size_t)i]; b < row_end[(size_t)i]; b += clen)
+      hchunks.push_back(StreamChunk{i, (int32_t)std::min<int64_t>(clen, row_end[(size_t)i] - b), b});
+    rcp[(size_t)i + 1] = (int32_t)hchunks.size();
+  }
+  nchunks = (int64_t)hchunks.size();
+  std::swap(ab.ptr, ab_.ptr);
+  std::swap(ab.count, ab_.count);
+  std::swap(val.ptr, val_.ptr);
+  std::swap(val.count, val_.count);
+  chunks.upload(hchunks.data(), hchunks.size());
+  row_chunk_ptr.upload(rcp.data(), rcp.size());
+  partials.clear();
+  CA_CUDA(cudaStreamSynchronize(nullptr));
+}
+
 double* StreamPack::partial_for(cudaStream_t st) const {
   auto& slot = partials[st];
   if (!slot) {

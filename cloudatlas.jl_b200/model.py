@@ -6,9 +6,13 @@ import ctypes as C
 import numpy as np
 
 from ._lib import CloudAtlasError, _sig, c_f64p, c_i64p, check, vp
-from .bilinear import SparseBilinear, _colmajor_ensemble, _f64, _is_torch, _stream, ensemble_empty
+from .bilinear import (SparseBilinear, _check_device_tensor, _colmajor_ensemble, _f64, _is_torch, _stream,
+                       ensemble_empty)
 
 _create = _sig("ca_model_create", c_f64p, c_f64p, c_f64p, C.c_int64, c_i64p, c_f64p, C.c_int64, C.POINTER(vp))
+_create_dev = _sig("ca_model_create_dev", vp, vp, vp, C.c_int64, vp, vp, vp, vp, C.c_int64, vp, C.POINTER(vp))
+_build_info = _sig("ca_model_build_info", vp, C.POINTER(C.c_int32), c_f64p, c_i64p, c_i64p, c_i64p)
+_digest = _sig("ca_model_digest", vp, C.POINTER(C.c_uint64))
 _destroy = _sig("ca_model_destroy", vp)
 _info = _sig("ca_model_info", vp, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p)
 _rhs = _sig("ca_model_rhs", vp, c_f64p, C.c_double, c_f64p)
@@ -37,24 +41,93 @@ class ModelOperators:
     """
 
     def __init__(self, B, A1, A2, ijk, val):
-        self.B = np.asfortranarray(B, dtype=np.float64)
-        self.A1 = np.asfortranarray(A1, dtype=np.float64)
-        self.A2 = np.asfortranarray(A2, dtype=np.float64)
-        m = self.B.shape[0]
-        if self.B.shape != (m, m) or self.A1.shape != (m, m) or self.A2.shape != (m, m):
+        self._dev = None
+        self._B = np.asfortranarray(B, dtype=np.float64)
+        self._A1 = np.asfortranarray(A1, dtype=np.float64)
+        self._A2 = np.asfortranarray(A2, dtype=np.float64)
+        m = self._B.shape[0]
+        if self._B.shape != (m, m) or self._A1.shape != (m, m) or self._A2.shape != (m, m):
             raise CloudAtlasError(1, "B, A1, A2 must be square and of equal size")
         ijk = np.asarray(ijk)
         if ijk.ndim != 2 or ijk.shape[1] != 3:
             raise CloudAtlasError(1, "ijk must have three columns")
-        self.ijk = np.asfortranarray(ijk, dtype=np.int64)
-        self.val = np.ascontiguousarray(val, dtype=np.float64)
-        if self.ijk.shape[0] != self.val.shape[0]:
+        self._ijk = np.asfortranarray(ijk, dtype=np.int64)
+        self._val = np.ascontiguousarray(val, dtype=np.float64)
+        if self._ijk.shape[0] != self._val.shape[0]:
             raise CloudAtlasError(1, "ijk and val must have same number of rows")
         self.m = m
         h = vp()
-        check(_create(_f64(self.B), _f64(self.A1), _f64(self.A2), m, self.ijk.ctypes.data_as(c_i64p),
-                      _f64(self.val), self.ijk.shape[0], C.byref(h)))
+        check(_create(_f64(self._B), _f64(self._A1), _f64(self._A2), m, self._ijk.ctypes.data_as(c_i64p),
+                      _f64(self._val), self._ijk.shape[0], C.byref(h)))
         self._h = h
+
+    @classmethod
+    def from_device(cls, B, A1, A2, idx, val):
+        """Model from operators that are already on the GPU (``ca_model_create_dev``): B, A1, A2 column-major m x m
+        CUDA tensors (stride (1, m)), ``idx`` [3, nnz] int64 (rows i, j, k; 1-based, lexicographic), ``val`` [nnz].
+        Nothing passes through the host; numpy copies (``.B``, ``.ijk``, ...) are fetched only if asked for."""
+        import torch
+        self = cls.__new__(cls)
+        m = B.shape[0]
+        for M in (B, A1, A2):
+            if not (M.is_cuda and M.dtype == torch.float64 and tuple(M.shape) == (m, m) and (m == 1 or M.stride() == (1, m))):
+                raise CloudAtlasError(1, "B, A1, A2 must be column-major m x m float64 CUDA tensors")
+        if not (idx.is_cuda and idx.dtype == torch.int64 and idx.dim() == 2 and idx.shape[0] == 3 and idx.is_contiguous()):
+            raise CloudAtlasError(1, "idx must be a contiguous [3, nnz] int64 CUDA tensor")
+        if not (val.is_cuda and val.dtype == torch.float64 and val.dim() == 1 and val.is_contiguous()
+                and val.shape[0] == idx.shape[1]):
+            raise CloudAtlasError(1, "ijk and val must have same number of rows")
+        self.m = m
+        self._dev = (B, A1, A2, idx, val)
+        self._B = self._A1 = self._A2 = self._ijk = self._val = None
+        nnz = int(val.shape[0])
+        h = vp()
+        check(_create_dev(vp(B.data_ptr()), vp(A1.data_ptr()), vp(A2.data_ptr()), m, vp(idx[0].data_ptr()),
+                          vp(idx[1].data_ptr()), vp(idx[2].data_ptr()), vp(val.data_ptr()), nnz, _stream(), C.byref(h)))
+        torch.cuda.current_stream().synchronize()
+        self._h = h
+        return self
+
+    def release_device_inputs(self):
+        """Drops the CUDA tensors ``from_device`` was given (the library keeps its own compact copies)."""
+        if self._dev is not None:
+            self.B, self.A1, self.A2, self.ijk, self.val  # noqa: B018  (materialise the host copies first)
+            self._dev = None
+
+    def _host(self, name, q):
+        v = getattr(self, name)
+        if v is None and self._dev is not None:
+            t = self._dev[q]
+            if q < 3:
+                v = np.asfortranarray(t.cpu().numpy())
+            elif q == 3:
+                v = np.asfortranarray(t.t().cpu().numpy())
+            else:
+                v = t.cpu().numpy()
+            setattr(self, name, v)
+        return v
+
+    B = property(lambda self: self._host("_B", 0))
+    A1 = property(lambda self: self._host("_A1", 1))
+    A2 = property(lambda self: self._host("_A2", 2))
+    ijk = property(lambda self: self._host("_ijk", 3))
+    val = property(lambda self: self._host("_val", 4))
+
+    def build_info(self):
+        """How the model was built (``ca_model_build_info``): device or host path and seconds per phase."""
+        on = C.c_int32()
+        sec = (C.c_double * 9)()
+        ncl, nt, ntm = C.c_int64(), C.c_int64(), C.c_int64()
+        check(_build_info(self._h, C.byref(on), sec, C.byref(ncl), C.byref(nt), C.byref(ntm)))
+        names = ("total", "blocks", "fold", "symmetrise", "cluster", "tile_unions", "layout_host", "place", "stream")
+        return {"on_device": bool(on.value), "seconds": dict(zip(names, (float(v) for v in sec))),
+                "nclusters": ncl.value, "ntiles": nt.value, "nterms": ntm.value}
+
+    def digest(self):
+        """Twelve FNV-1a digests of the build products (``ca_model_digest``)."""
+        d = (C.c_uint64 * 12)()
+        check(_digest(self._h, d))
+        return [int(v) for v in d]
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -84,9 +157,9 @@ class ModelOperators:
         if _is_torch(x):
             single = x.dim() == 1
             X = x.reshape(1, -1) if single else x
-            X, n, ld = _colmajor_ensemble(X)
+            X, n, ld = _colmajor_ensemble(X, self.m)
             OUT = ensemble_empty(n, self.m, X.device) if out is None else out
-            _, n_o, ldo = _colmajor_ensemble(OUT)
+            _, n_o, ldo = _colmajor_ensemble(OUT, self.m)
             if n_o != n or OUT.shape[1] != self.m:
                 raise CloudAtlasError(1, "out must be nstates x m, column-major")
             check(_rhs_b_dev(self._h, vp(X.data_ptr()), n, ld, float(R), vp(OUT.data_ptr()), ldo, _stream()))
@@ -107,6 +180,12 @@ class ModelOperators:
 
     def f_into(self, X, R, OUT):
         """Host ensemble into a caller-owned (e.g. page-locked) column-major buffer."""
+        for A, name in ((X, "X"), (OUT, "OUT")):
+            if not (isinstance(A, np.ndarray) and A.dtype == np.float64 and A.ndim == 2 and A.shape[1] == self.m
+                    and (A.flags.f_contiguous or A.shape[0] == 1)):
+                raise CloudAtlasError(1, f"{name} must be a column-major float64 array with {self.m} columns")
+        if OUT.shape != X.shape:
+            raise CloudAtlasError(1, "OUT must have the shape of X")
         check(_rhs_b(self._h, _f64(X), X.shape[0], float(R), _f64(OUT)))
         return OUT
 
@@ -124,10 +203,15 @@ class ModelOperators:
             return D
         if _is_torch(x):
             import torch
+            _check_device_tensor(x)
+            if x.dim() != 1 or x.numel() != self.m:
+                raise CloudAtlasError(1, f"x has {x.numel()} elements, expected {self.m}")
             D = torch.empty((self.m, self.m), dtype=torch.float64, device=x.device).t()
             check(_jac_dev(self._h, vp(x.contiguous().data_ptr()), float(R), vp(D.data_ptr()), _stream()))
             return D
         x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.shape != (self.m,):
+            raise CloudAtlasError(1, f"x has shape {x.shape}, expected ({self.m},)")
         D = np.empty((self.m, self.m), order="F")
         check(_jac(self._h, _f64(x), float(R), _f64(D)))
         return D
@@ -137,11 +221,13 @@ class ModelOperators:
         if not _is_torch(X):
             Xh = np.asfortranarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))
             Vh = np.asfortranarray(np.atleast_2d(np.asarray(V, dtype=np.float64)))
+            if Xh.shape[1] != self.m or Vh.shape != Xh.shape:
+                raise CloudAtlasError(1, f"X and V must both be nstates x {self.m}")
             OUT = np.empty(Xh.shape, order="F")
             check(_jvp_b_host(self._h, _f64(Xh), _f64(Vh), Xh.shape[0], float(R), _f64(OUT)))
             return OUT[0] if np.ndim(X) == 1 else OUT
-        X, n, ld = _colmajor_ensemble(X)
-        V, n2, ld2 = _colmajor_ensemble(V)
+        X, n, ld = _colmajor_ensemble(X, self.m)
+        V, n2, ld2 = _colmajor_ensemble(V, self.m)
         if (n2, ld2) != (n, ld):
             raise CloudAtlasError(1, "X and V must have the same shape and leading dimension")
         OUT = ensemble_empty(n, self.m, X.device)
@@ -162,9 +248,7 @@ def cnab2(x0, odemodel, R, dt, Nsteps, nsave, verbosity=0):
         X0 = x0.reshape(1, -1) if single else x0
     else:
         X0 = torch.from_numpy(np.ascontiguousarray(np.atleast_2d(np.asarray(x0, dtype=np.float64)).T)).cuda().t()
-    X0, n, ld = _colmajor_ensemble(X0)
-    if X0.shape[1] != odemodel.m:
-        raise CloudAtlasError(1, f"x0 has {X0.shape[1]} columns, expected {odemodel.m}")
+    X0, n, ld = _colmajor_ensemble(X0, odemodel.m)
     save = torch.empty((max(Nsave, 1), odemodel.m, n), dtype=torch.float64, device=X0.device)
     check(_cnab2(odemodel._h, vp(X0.data_ptr()), n, ld, float(R), float(dt), int(Nsteps), int(nsave),
                  vp(save.data_ptr()), None, _stream()))
@@ -184,7 +268,7 @@ class ODEModel(ModelOperators):
 
     def __init__(self, alpha, gamma, J, K, L, H, normalize=False, ijkl=None, group=None, verbose=False,
                  dense_assembly=False, grid=(0, 0, 0)):
-        from .assembly import assemble
+        from .assembly import assemble_device
         from .basis import basisComponents, basisIndices
         self.alpha, self.gamma = float(alpha), float(gamma)
         self.H = None if H is None else list(H)
@@ -194,14 +278,17 @@ class ODEModel(ModelOperators):
             print(f"J,K,L,m == {J},{K},{L},{m}")
             print(f"(2J+1)(2K+1)(2L+1) + 1 == {(2 * J + 1) * (2 * K + 1) * (2 * L + 1) + 1}")
         self.Psi = basisComponents(self.alpha, self.gamma, self.ijkl, normalize)
-        B, A1, A2, ijk, val, self.assembly_stats = assemble(self.alpha, self.gamma, self.ijkl, normalize, group,
-                                                            dense=dense_assembly, grid=grid)
-        super().__init__(B, A1, A2, ijk, val)
+        lin, idx, val, self.assembly_stats = assemble_device(self.alpha, self.gamma, self.ijkl, normalize, group,
+                                                             dense=dense_assembly, grid=grid)
+        # lin[q] holds a column-major matrix: its transpose VIEW is the m x m tensor with stride (1, m)
+        built = ModelOperators.from_device(lin[0].t(), lin[1].t(), lin[2].t(), idx, val)
+        self.__dict__.update(built.__dict__)
+        built._h = None   # the handle now belongs to this object
         self._N = None
         from .basis import shearVector
         self.Psishear = shearVector(self.alpha, self.gamma, self.ijkl, normalize)   # ODEModels.jl:65-78
-        self.D = self.assembly_stats.pop("D")                                        # ODEModels.jl:129-137
-        check(_set_obs(self._h, _f64(self.Psishear), _f64(np.asfortranarray(self.D))))
+        self.D = np.asfortranarray(lin[3].t().cpu().numpy())                         # ODEModels.jl:129-137
+        check(_set_obs(self._h, _f64(self.Psishear), _f64(self.D)))
 
     def observables(self, x):
         """(shear, dissipation) of shear_function / dissipation_function (ODEModels.jl:65-137) for one state
@@ -212,7 +299,7 @@ class ODEModel(ModelOperators):
             X = x.reshape(1, -1) if x.dim() == 1 else x
         else:
             X = torch.from_numpy(np.ascontiguousarray(np.atleast_2d(np.asarray(x, dtype=np.float64)).T)).cuda().t()
-        X, n, ld = _colmajor_ensemble(X)
+        X, n, ld = _colmajor_ensemble(X, self.m)
         OUT = ensemble_empty(n, 2, X.device)
         check(_obs_dev(self._h, vp(X.data_ptr()), n, ld, vp(OUT.data_ptr()), _stream()))
         if _is_torch(x):

@@ -133,6 +133,23 @@ int32_t ca_bilinear_jvp_batched_dev(ca_bilinear* h, const double* dX, const doub
  * is ONE pass of the batched kernel: each state is read once and written once. */
 int32_t ca_model_create(const double* B, const double* A1, const double* A2, int64_t m,
                         const int64_t* ijk, const double* val, int64_t nnz, ca_model** out);
+/* The same from DEVICE arrays (as ca_assembly_get_*_dev / the all-gathered slabs deliver them; B, A1, A2 m x m
+ * column-major, the COO as three index arrays, 1-based, in the reference's lexicographic (i,j,k) order): the operator
+ * never passes through the host.  Folding, symmetrisation, pair-set unions and the placement of the values into the
+ * DMMA fragment layout run on the device; the packer's decisions (row clustering, windows, warp schedule) are made by
+ * the same host code as in ca_model_create on descriptors of a few MB, so both entry points build the same pack bit for
+ * bit.  ca_model_create itself uploads its arguments and takes this path; operators it does not cover (COO not in
+ * ascending (i,j,k) order or with duplicates, a block of B with more than 64 modes) go through the host build. */
+int32_t ca_model_create_dev(const double* dB, const double* dA1, const double* dA2, int64_t m, const int64_t* d_i,
+                            const int64_t* d_j, const int64_t* d_k, const double* d_val, int64_t nnz, void* stream,
+                            ca_model** out);
+/* How the model was built: *on_device = 1 for the device build; seconds9 = wall seconds {total, blocks of B, fold,
+ * symmetrise + CSR, sketches + clustering, tile unions, layout (host), value placement, streaming form}. */
+int32_t ca_model_build_info(const ca_model* h, int32_t* on_device, double* seconds9, int64_t* nclusters,
+                            int64_t* ntiles, int64_t* nterms);
+/* FNV-1a digests of the build products (diagnostics; device build vs host build must agree in all twelve):
+ * [0..7] the packed operator (as ca_selftest_pack_digest), [8] L1, [9] L2, [10] linear slots, [11] streaming form. */
+int32_t ca_model_digest(ca_model* h, uint64_t* digest12);
 int32_t ca_model_destroy(ca_model* h);
 int32_t ca_model_info(const ca_model* h, int64_t* m, int64_t* nnz_q_sym, int64_t* nnz_lin,
                       int64_t* npairs, int64_t* padded_fma_per_state, int64_t* nblocks_B);
