@@ -80,8 +80,9 @@ namespace ca {
 // host buffers are page-locked, see ca_pin).
 void eval_batched_host(const LaunchFn& launch, cudaStream_t streams[kStage], DeviceBuffer<double> in[kStage],
                        DeviceBuffer<double> out[kStage], const double* X, int64_t nstates, double* OUT,
-                       int64_t m_in, int64_t m_out) {
+                       int64_t m_in, int64_t m_out, int64_t ld_host) {
   if (nstates <= 0) return;
+  if (ld_host < nstates) ld_host = nstates;
   const int64_t bytes_per_state = (m_in + m_out) * (int64_t)sizeof(double);
   // ~128 MB of traffic per chunk (short exposed head and tail of the copy/compute pipeline), rounded to whole
   // waves of the persistent ensemble kernel (SMs x 2 CTAs x 32 states) so that no chunk ends in a partial wave
@@ -103,10 +104,10 @@ void eval_batched_host(const LaunchFn& launch, cudaStream_t streams[kStage], Dev
     const int64_t n = std::min(chunk, nstates - s0);
     cudaStream_t st = streams[b];
     CA_CUDA(cudaMemcpy2DAsync(in[b].ptr, (size_t)n * sizeof(double), X + s0,
-                              (size_t)nstates * sizeof(double), (size_t)n * sizeof(double),
+                              (size_t)ld_host * sizeof(double), (size_t)n * sizeof(double),
                               (size_t)m_in, cudaMemcpyHostToDevice, st));
     launch(in[b].ptr, n, out[b].ptr, st);
-    CA_CUDA(cudaMemcpy2DAsync(OUT + s0, (size_t)nstates * sizeof(double), out[b].ptr,
+    CA_CUDA(cudaMemcpy2DAsync(OUT + s0, (size_t)ld_host * sizeof(double), out[b].ptr,
                               (size_t)n * sizeof(double), (size_t)n * sizeof(double), (size_t)m_out,
                               cudaMemcpyDeviceToHost, st));
   }

@@ -7,8 +7,10 @@
 #include <map>
 #include <memory>
 #include <numeric>
+#include <string>
 #include <vector>
 
+#include "assembly.h"
 #include "bilinear.h"
 #include "bilinear_kernels.cuh"
 #include "model.h"
@@ -24,6 +26,17 @@ __global__ void patch_linear_kernel(double* __restrict__ vals, const int64_t* __
                                     int64_t n, double invR) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) vals[pos[t]] = fma(l2[t], invR, l1[t]);
+}
+
+// out (column-major m x m) = in (row-major m x m), i.e. a plain transpose of the memory image
+__global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int m) {
+  __shared__ double tile[32][33];
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8)
+    if (y0 + r < m && x0 + threadIdx.x < m) tile[r][threadIdx.x] = in[(size_t)(y0 + r) * m + x0 + threadIdx.x];
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8)
+    if (x0 + r < m && y0 + threadIdx.x < m) out[(size_t)(x0 + r) * m + y0 + threadIdx.x] = tile[threadIdx.x][r];
 }
 
 // Df[i,j] += L1[i,j] + L2[i,j] * invR
@@ -582,6 +595,43 @@ int32_t ca_model_digest(ca_model* h, uint64_t* digest12) {
   });
 }
 
+// ODEModel straight from a full assembly (ca_assemble over all rows, or the gathered result of ca_assemble_sharded)
+// on the assembly's device: the operator never leaves the GPU.  Also installs the observables (shear vector, D).
+int32_t ca_model_create_from_assembly(ca_assembly* a, ca_model** out) {
+  return guarded([&] {
+    if (!a || !out) fail(CA_ERR_INVALID, "ca_model_create_from_assembly: null argument");
+    *out = nullptr;
+    if (a->r0 != 0 || a->r1 != a->m) fail(CA_ERR_INVALID, "ca_model_create_from_assembly: the assembly covers rows [%lld,%lld) of %lld; gather the slabs first",
+                                          (long long)a->r0, (long long)a->r1, (long long)a->m);
+    a->bind();
+    const int64_t m = a->m;
+    const size_t mm = (size_t)m * m;
+    DeviceBuffer<double> cB, cA1, cA2, cD;  // column-major copies (the slabs are row-major)
+    const double* src[4] = {a->B.ptr, a->A1.ptr, a->A2.ptr, a->D.ptr};
+    DeviceBuffer<double>* dst[4] = {&cB, &cA1, &cA2, &cD};
+    const dim3 grid((unsigned)((m + 31) / 32), (unsigned)((m + 31) / 32));
+    for (int q = 0; q < 4; ++q) {
+      dst[q]->alloc(mm);
+      transpose_kernel<<<grid, dim3(32, 8)>>>(src[q], dst[q]->ptr, (int)m);
+      CA_CUDA(cudaGetLastError());
+      count_launch();
+    }
+    ca_model* h = nullptr;
+    const int32_t st = ca_model_create_dev(cB.ptr, cA1.ptr, cA2.ptr, m, a->oi.ptr, a->oj.ptr, a->ok.ptr, a->oval.ptr, a->nnz, nullptr, &h);
+    if (st != CA_OK) fail(st, "%s", ca_last_error());
+    std::unique_ptr<ca_model> guard(h);
+    std::vector<double> D(mm);
+    CA_CUDA(cudaMemcpy(D.data(), cD.ptr, mm * sizeof(double), cudaMemcpyDeviceToHost));
+    if (a->shear.size() == (size_t)m) {
+      h->obs_shear = a->shear;
+      h->obs_D.swap(D);
+      h->obs_set = true;
+      h->obs_built = false;
+    }
+    *out = guard.release();
+  });
+}
+
 int32_t ca_model_build_info(const ca_model* h, int32_t* on_device, double* seconds9, int64_t* nclusters,
                             int64_t* ntiles, int64_t* nterms) {
   return guarded([&] {
@@ -647,6 +697,48 @@ int32_t ca_model_rhs_batched(ca_model* h, const double* X, int64_t nstates, doub
     eval_batched_host([&](const double* dX, int64_t n, double* dOUT, cudaStream_t st) {
       h->eval_dev(MODE_QUAD, dX, nullptr, n, n, R, dOUT, n, st);
     }, h->streams, h->stage_in, h->stage_out, X, nstates, OUT, h->m, h->m);
+  });
+}
+
+// f(x_s, R) of one host ensemble on several devices of this process: models[d] is the same model built on device d
+// (ca_assemble_sharded + ca_model_create_from_assembly); the states are split evenly, every device runs the
+// host-pointer pipeline of ca_model_rhs_batched on its range from its own host thread.  No collective: outputs are
+// disjoint ranges of OUT ("ensemble RHS shards by state").
+int32_t ca_models_rhs_batched(ca_model** models, int32_t nmodels, const double* X, int64_t nstates, double R, double* OUT) {
+  return guarded([&] {
+    if (!models || nmodels < 1 || (nstates > 0 && (!X || !OUT))) fail(CA_ERR_INVALID, "ca_models_rhs_batched: bad arguments");
+    for (int d = 0; d < nmodels; ++d)
+      if (!models[d] || models[d]->m != models[0]->m) fail(CA_ERR_INVALID, "ca_models_rhs_batched: models must be replicas of one model");
+    if (nstates <= 0) return;
+    std::vector<int32_t> codes((size_t)nmodels, CA_OK);
+    std::vector<std::string> errors((size_t)nmodels);
+    std::vector<std::thread> pool;
+    // ranges in whole 32-state tiles so that only the last device sees a ragged tail
+    const int64_t tiles = (nstates + 31) / 32;
+    for (int d = 0; d < nmodels; ++d) {
+      const int64_t s0 = std::min(nstates, tiles * d / nmodels * 32), s1 = std::min(nstates, tiles * (d + 1) / nmodels * 32);
+      if (s1 <= s0) continue;
+      pool.emplace_back([&, d, s0, s1] {
+        try {
+          ca_model* h = models[d];
+          h->bind();
+          h->need_streams();
+          h->set_R(R, h->streams[0]);
+          eval_batched_host([&](const double* dX, int64_t n, double* dOUT, cudaStream_t st) {
+            h->eval_dev(MODE_QUAD, dX, nullptr, n, n, R, dOUT, n, st);
+          }, h->streams, h->stage_in, h->stage_out, X + s0, s1 - s0, OUT + s0, h->m, h->m, nstates);
+        } catch (const Error& e) {
+          codes[(size_t)d] = e.code;
+          errors[(size_t)d] = e.what();
+        } catch (const std::exception& e) {
+          codes[(size_t)d] = CA_ERR_INVALID;
+          errors[(size_t)d] = e.what();
+        }
+      });
+    }
+    for (auto& t : pool) t.join();
+    for (int d = 0; d < nmodels; ++d)
+      if (codes[(size_t)d] != CA_OK) fail(codes[(size_t)d], "device of model %d: %s", d, errors[(size_t)d].c_str());
   });
 }
 
@@ -877,23 +969,35 @@ extern "C" int32_t ca_model_cnab2_batched_dev(ca_model* h, const double* dX0, in
 }
 
 // ------------------------------------------------------------------------------------ observables
+// The pack of the two observable rows is built on the first evaluation, not here: at m ~ 3000 packing the m^2 terms
+// of D costs more than the whole device model build, and constructors set the observables unconditionally.
 extern "C" int32_t ca_model_set_observables(ca_model* h, const double* shear, const double* D) {
   return guarded([&] {
     if (!h || !shear || !D) fail(CA_ERR_INVALID, "null argument");
-    h->bind();
-    const int m = (int)h->m;
-    std::vector<Term> t;
-    t.push_back(Term{0, m, m, 1.0});  // the constant 1 of shear(x) = 1 + dot(x, shear)
-    t.push_back(Term{1, m, m, 1.0});  // and of dissipation(x) = 1 + x' D x
-    for (int i = 0; i < m; ++i)
-      if (shear[i] != 0.0) t.push_back(Term{0, i, m, shear[i]});
-    for (int j = 0; j < m; ++j)
-      for (int i = 0; i < m; ++i)
-        if (D[i + (size_t)m * j] != 0.0) t.push_back(Term{1, i, j, D[i + (size_t)m * j]});
-    h->obs_stream.build_rect(t, 2, m);
-    h->obs.upload(pack_terms(std::move(t), 2, true, nt_max_for(window_modes_for(m)), window_modes_for(m), m));
+    const size_t m = (size_t)h->m;
+    h->obs_shear.assign(shear, shear + m);
+    h->obs_D.assign(D, D + m * m);
     h->obs_set = true;
+    h->obs_built = false;
   });
+}
+
+static void build_observables(ca_model* h) {
+  if (h->obs_built) return;
+  const int m = (int)h->m;
+  const double* shear = h->obs_shear.data();
+  const double* D = h->obs_D.data();
+  std::vector<Term> t;
+  t.push_back(Term{0, m, m, 1.0});  // the constant 1 of shear(x) = 1 + dot(x, shear)
+  t.push_back(Term{1, m, m, 1.0});  // and of dissipation(x) = 1 + x' D x
+  for (int i = 0; i < m; ++i)
+    if (shear[i] != 0.0) t.push_back(Term{0, i, m, shear[i]});
+  for (int j = 0; j < m; ++j)
+    for (int i = 0; i < m; ++i)
+      if (D[i + (size_t)m * j] != 0.0) t.push_back(Term{1, i, j, D[i + (size_t)m * j]});
+  h->obs_stream.build_rect(t, 2, m);
+  h->obs.upload(pack_terms(std::move(t), 2, true, nt_max_for(window_modes_for(m)), window_modes_for(m), m));
+  h->obs_built = true;
 }
 
 extern "C" int32_t ca_model_observables_batched_dev(ca_model* h, const double* dX, int64_t nstates, int64_t ld,
@@ -902,6 +1006,7 @@ extern "C" int32_t ca_model_observables_batched_dev(ca_model* h, const double* d
     if (!h || !dX || !dOUT) fail(CA_ERR_INVALID, "null argument");
     if (!h->obs_set) fail(CA_ERR_INVALID, "observables not set (ca_model_set_observables)");
     h->bind();
+    build_observables(h);
     eval_pack(h->obs, h->obs_stream, dX, nstates, ld, dOUT, nstates, (cudaStream_t)stream);
   });
 }

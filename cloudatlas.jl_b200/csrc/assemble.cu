@@ -15,9 +15,11 @@
 #include <memory>
 #include <vector>
 
+#include "assembly.h"
 #include "basis.h"
 #include "common.h"
 #include "scan.cuh"
+#include "dgemm.cuh"
 
 using namespace ca;
 
@@ -382,14 +384,22 @@ __global__ void dense_tables_kernel(DevBasis b, int mpad, int nxg, int nyg, int 
                                     const double* __restrict__ Ez, const double* __restrict__ Ezd,
                                     const double* __restrict__ F, int ny_tab, const double* __restrict__ wq,
                                     double* __restrict__ U, double* __restrict__ G9, double* __restrict__ A,
-                                    int nchunks) {
+                                    int nchunks, double* __restrict__ raw, const double* __restrict__ mixed) {
+  // raw != null: the 12 planes (u_c, d_a u_c) are written as raw[(plane * nq + q) * m + n] for the mixing GEMM and
+  // nothing else; mixed != null: the planes are read from there (Phi = Psi C) instead of being evaluated
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)mpad * nq) return;
   const int n = (int)(t / nq), q = (int)(t % nq);
   double u[3] = {0, 0, 0}, g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   double w = 0.0;
   const int nreal = nxg * nyg * nzg;
-  if (n < b.m && q < nreal) {
+  if (mixed) {
+    if (n < b.m && q < nreal) {
+      w = wq[q];
+      for (int c = 0; c < 3; ++c) u[c] = mixed[((int64_t)c * nq + q) * b.m + n];
+      for (int e = 0; e < 9; ++e) g[e] = mixed[((int64_t)(3 + e) * nq + q) * b.m + n];
+    }
+  } else if (n < b.m && q < nreal) {
     const int ix = q / (nyg * nzg), iy = (q / nzg) % nyg, iz = q % nzg;
     w = wq[q];
     for (int c = 0; c < 3; ++c) {
@@ -403,6 +413,13 @@ __global__ void dense_tables_kernel(DevBasis b, int mpad, int nxg, int nyg, int 
       g[1 * 3 + c] = cf * ex * ez * fd;
       g[2 * 3 + c] = cf * ex * ezd * f;
     }
+  }
+  if (raw) {
+    if (n < b.m) {
+      for (int c = 0; c < 3; ++c) raw[((int64_t)c * nq + q) * b.m + n] = u[c];
+      for (int e = 0; e < 9; ++e) raw[((int64_t)(3 + e) * nq + q) * b.m + n] = g[e];
+    }
+    return;
   }
   const int it = n / kDI, il = n % kDI, chunk = q / kDQ, ql = q % kDQ;
   for (int c = 0; c < 3; ++c)
@@ -553,27 +570,8 @@ dense_compact_kernel(const double* __restrict__ Nd, int m, int r0, int r1, doubl
   }
 }
 
-struct ca_assembly {
-  int device = 0;
-  int64_t m = 0, r0 = 0, r1 = 0, nnz = 0;
-  double seconds = 0;
-  double contract_seconds = 0, contract_flops = 0;  // dense path: the GEMM kernel alone, 2 * rows * m^2 * 3 Nq
-  int32_t grid[3] = {0, 0, 0};
-  DeviceBuffer<double> B, A1, A2, D;  // (r1-r0) x m row-major; D = <curl, curl> (dissipation)
-  DeviceBuffer<int64_t> oi, oj, ok;
-  DeviceBuffer<double> oval;
-  void bind() const { CA_CUDA(cudaSetDevice(device)); }
-};
-
-namespace {
-struct DenseOpts {
-  bool dense = false;
-  int nx = 0, ny = 0, nz = 0;
-};
-}  // namespace
-
-static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, int64_t m64, int32_t normalize,
-                             int64_t row_begin, int64_t row_end, const DenseOpts& dopt, ca_assembly** out) {
+int32_t ca::assemble_slab(double alpha, double gamma, const int64_t* ijkl, int64_t m64, int32_t normalize,
+                          int64_t row_begin, int64_t row_end, const AssembleOpts& dopt, ca_assembly** out) {
   return guarded([&] {
     if (!out) fail(CA_ERR_INVALID, "ca_assemble: out is null");
     *out = nullptr;
@@ -582,6 +580,14 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
       fail(CA_ERR_INVALID, "ca_assemble: row range [%lld,%lld) outside 0:%lld", (long long)row_begin, (long long)row_end, (long long)m64);
     if (m64 > 46000) fail(CA_ERR_UNSUPPORTED, "ca_assemble: m too large");
     BasisTables T = build_tables(alpha, gamma, ijkl, m64, normalize != 0, dopt.dense ? dopt.ny : 0);
+    if (dopt.mix && !dopt.dense)
+      fail(CA_ERR_INVALID, "ca_assemble: a mixed basis (Phi = Psi C) has no factorised modes; use the dense quadrature path");
+    if (dopt.mode_scale)
+      for (int64_t n = 0; n < m64; ++n) {
+        if (!(dopt.mode_scale[n] != 0.0) || !std::isfinite(dopt.mode_scale[n]))
+          fail(CA_ERR_INVALID, "ca_assemble: mode_scale[%lld] must be finite and non-zero", (long long)n);
+        for (int c = 0; c < 3; ++c) T.comp[(size_t)n * 3 + c].coef *= dopt.mode_scale[n];
+      }
     require_device();
     std::unique_ptr<ca_assembly> h(new ca_assembly);
     CA_CUDA(cudaGetDevice(&h->device));
@@ -589,6 +595,17 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
     h->m = m;
     h->r0 = r0;
     h->r1 = r1;
+    h->shear.assign((size_t)m, 0.0);
+    for (int n = 0; n < m; ++n) {
+      const Component& u = T.comp[(size_t)n * 3];  // the u component (mode_scale already applied)
+      if (u.coef != 0.0 && u.jx == 0 && u.kz == 0) h->shear[(size_t)n] = u.coef * T.wall_avg[4 * u.l + u.d + 1];
+    }
+    if (dopt.mix) {  // Phi_n = sum_p Psi_p C[p,n]: the shear functional is linear in the mode
+      std::vector<double> mixed((size_t)m, 0.0);
+      for (int n = 0; n < m; ++n)
+        for (int p2 = 0; p2 < m; ++p2) mixed[(size_t)n] += h->shear[(size_t)p2] * dopt.mix[p2 + (size_t)m * n];
+      h->shear.swap(mixed);
+    }
 
     // ---- upload the tabular basis
     std::vector<double> coef((size_t)m * 3), k2((size_t)m * 3);
@@ -808,9 +825,27 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
                dX2.ptr, dZ2.ptr, dX3.ptr, dZ3.ptr, dY2.ptr, dY2y.ptr, dY3.ptr, dcoefT.ptr, dpackT.ptr};
     const int64_t nij = (int64_t)rows * m;
     if (nij > 0) {
-      linear_kernel<<<(unsigned)((nij + 255) / 256), 256>>>(b, r0, r1, h->B.ptr, h->A1.ptr, h->A2.ptr, h->D.ptr);
-      CA_CUDA(cudaGetLastError());
-      count_launch();
+      DeviceBuffer<double> dmix;
+      if (dopt.mix) {
+        // B' = C' B C (likewise A1, A2, D): the four matrices of the plain basis in full, then two small GEMMs each
+        dmix.upload(dopt.mix, (size_t)m * m);
+        DeviceBuffer<double> full[4], t1;
+        for (auto& f : full) f.alloc((size_t)m * m);
+        t1.alloc((size_t)m * m);
+        linear_kernel<<<(unsigned)(((int64_t)m * m + 255) / 256), 256>>>(b, 0, m, full[0].ptr, full[1].ptr, full[2].ptr, full[3].ptr);
+        CA_CUDA(cudaGetLastError());
+        count_launch();
+        double* dst[4] = {h->B.ptr, h->A1.ptr, h->A2.ptr, h->D.ptr};
+        for (int q = 0; q < 4; ++q) {
+          launch_dgemm(m, m, m, 1.0, rowmajor(full[q].ptr, m), colmajor(dmix.ptr, m), 0.0, t1.ptr, m, 1, nullptr);
+          launch_dgemm(rows, m, m, 1.0, MatView{dmix.ptr + (size_t)m * r0, m, 1}, rowmajor(t1.ptr, m), 0.0, dst[q], m, 1, nullptr);
+        }
+        CA_CUDA(cudaStreamSynchronize(nullptr));
+      } else {
+        linear_kernel<<<(unsigned)((nij + 255) / 256), 256>>>(b, r0, r1, h->B.ptr, h->A1.ptr, h->A2.ptr, h->D.ptr);
+        CA_CUDA(cudaGetLastError());
+        count_launch();
+      }
 
       CA_CUDA(cudaMemsetAsync(counts.ptr, 0, ((size_t)nij + 1) * sizeof(int64_t)));
       int sms = 0;
@@ -862,11 +897,31 @@ static int32_t assemble_impl(double alpha, double gamma, const int64_t* ijkl, in
         Nd.alloc((size_t)rows * m * m);
         CA_CUDA(cudaMemsetAsync(dmax.ptr, 0, sizeof(double)));
         const int64_t ntab = (int64_t)mpad * nq;
-        dense_tables_kernel<<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr,
-                                                                    dezd.ptr, dF.ptr, T.ny, dwq.ptr, dU.ptr, dG9.ptr,
-                                                                    dA.ptr, nchunks);
-        CA_CUDA(cudaGetLastError());
-        count_launch();
+        if (dopt.mix) {
+          // Phi = Psi C on the grid: 12 planes (u_c, d_a u_c) of the plain basis, one GEMM [12 nq x m] . [m x m], then the
+          // tiled operand layouts from the mixed planes.  ~0.5 % of the contraction's arithmetic.
+          DeviceBuffer<double> raw, mixed;
+          raw.alloc((size_t)12 * nq * m);
+          mixed.alloc((size_t)12 * nq * m);
+          dense_tables_kernel<<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr,
+                                                                      dezd.ptr, dF.ptr, T.ny, dwq.ptr, dU.ptr, dG9.ptr,
+                                                                      dA.ptr, nchunks, raw.ptr, nullptr);
+          CA_CUDA(cudaGetLastError());
+          count_launch();
+          launch_dgemm(12 * nq, m, m, 1.0, rowmajor(raw.ptr, m), colmajor(dmix.ptr, m), 0.0, mixed.ptr, m, 1, nullptr);
+          dense_tables_kernel<<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr,
+                                                                      dezd.ptr, dF.ptr, T.ny, dwq.ptr, dU.ptr, dG9.ptr,
+                                                                      dA.ptr, nchunks, nullptr, mixed.ptr);
+          CA_CUDA(cudaGetLastError());
+          count_launch();
+          CA_CUDA(cudaStreamSynchronize(nullptr));  // raw / mixed are released here
+        } else {
+          dense_tables_kernel<<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr,
+                                                                      dezd.ptr, dF.ptr, T.ny, dwq.ptr, dU.ptr, dG9.ptr,
+                                                                      dA.ptr, nchunks, nullptr, nullptr);
+          CA_CUDA(cudaGetLastError());
+          count_launch();
+        }
         DenseTables DT{m, mpad, nq, nchunks, dU.ptr, dG9.ptr, dA.ptr};
         const int it0 = r0 / kDI, nit = (r1 + kDI - 1) / kDI - it0;
         const int njt = (m + kDJ - 1) / kDJ, nkt = (m + kDK - 1) / kDK;
@@ -949,17 +1004,30 @@ extern "C" {
 
 int32_t ca_assemble(double alpha, double gamma, const int64_t* ijkl, int64_t m, int32_t normalize,
                     int64_t row_begin, int64_t row_end, ca_assembly** out) {
-  return assemble_impl(alpha, gamma, ijkl, m, normalize, row_begin, row_end, DenseOpts{}, out);
+  return assemble_slab(alpha, gamma, ijkl, m, normalize, row_begin, row_end, AssembleOpts{}, out);
 }
 
 int32_t ca_assemble_dense(double alpha, double gamma, const int64_t* ijkl, int64_t m, int32_t normalize,
                           int64_t row_begin, int64_t row_end, int32_t nx, int32_t ny, int32_t nz, ca_assembly** out) {
-  DenseOpts d;
+  AssembleOpts d;
   d.dense = true;
   d.nx = nx;
   d.ny = ny;
   d.nz = nz;
-  return assemble_impl(alpha, gamma, ijkl, m, normalize, row_begin, row_end, d, out);
+  return assemble_slab(alpha, gamma, ijkl, m, normalize, row_begin, row_end, d, out);
+}
+
+int32_t ca_assemble_basis(double alpha, double gamma, const int64_t* ijkl, int64_t m, int32_t normalize,
+                          const double* mode_scale, const double* mix, int32_t dense, int32_t nx, int32_t ny, int32_t nz,
+                          int64_t row_begin, int64_t row_end, ca_assembly** out) {
+  AssembleOpts d;
+  d.dense = dense != 0;
+  d.nx = nx;
+  d.ny = ny;
+  d.nz = nz;
+  d.mode_scale = mode_scale;
+  d.mix = mix;
+  return assemble_slab(alpha, gamma, ijkl, m, normalize, row_begin, row_end, d, out);
 }
 
 int32_t ca_assembly_dense_info(const ca_assembly* h, int32_t* grid3, double* contract_seconds, double* contract_flops) {

@@ -47,7 +47,7 @@ constexpr int kStage = 3;
 using LaunchFn = std::function<void(const double*, int64_t, double*, cudaStream_t)>;
 void eval_batched_host(const LaunchFn& launch, cudaStream_t streams[kStage], DeviceBuffer<double> in[kStage],
                        DeviceBuffer<double> out[kStage], const double* X, int64_t nstates, double* OUT,
-                       int64_t m_in, int64_t m_out);
+                       int64_t m_in, int64_t m_out, int64_t ld_host = -1 /* leading dimension of X and OUT; default nstates */);
 
 // Packing policy: operators whose two-vector state tile (x and y/v, 32 states) fits in shared memory use
 // whole-tile packing; larger ones are packed in windows of kWindowModes modes (128: two CTAs per SM still fit for one-vector evaluation).

@@ -486,6 +486,9 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
 
 }  // namespace
 
+void hookstep_solve_large(ca_model* h, const double* R, const double* Xguess, int64_t nsolve, const ca_search_params& p,
+                          double* X_out, int32_t* success, ca_solve_log* logs);
+
 extern "C" int32_t ca_hookstep_solve_model(ca_model* h, const double* R, const double* Xguess, int64_t nsolve,
                                            const ca_search_params* params, double* X_out, int32_t* success,
                                            ca_solve_log* logs) {
@@ -502,9 +505,10 @@ extern "C" int32_t ca_hookstep_solve_model(ca_model* h, const double* R, const d
     const size_t smem = ((size_t)3 * m * m + 9 * (size_t)m + 8) * sizeof(double) + (2 * (size_t)m + 4) * sizeof(int);
     int optin = 0;
     CA_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    if (smem > (size_t)optin)
-      fail(CA_ERR_UNSUPPORTED, "device-resident hookstep needs %zu B of shared memory for m = %d (limit %d); "
-           "use the closure form of hookstepsolve with model.f / model.Df", smem, m, optin);
+    if (smem > (size_t)optin || getenv("CA_HOOK_LARGE")) {  // beyond the one-CTA solver: global-memory solver, still device-resident
+      hookstep_solve_large(h, R, Xguess, nsolve, p, X_out, success, logs);
+      return;
+    }
     CA_CUDA(cudaFuncSetAttribute(hookstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     DeviceBuffer<double> dR, dX, dOut;

@@ -87,7 +87,8 @@ struct ca_model {
   ca::DeviceBuffer<double> cn_buf[2], cn_n[2];
   ca::DevicePack obs;                 // two output rows: shear and dissipation (ODEModels.jl:65-137)
   ca::StreamPack obs_stream;
-  bool obs_set = false;
+  bool obs_set = false, obs_built = false;
+  std::vector<double> obs_shear, obs_D;  // as given to ca_model_set_observables; packed on first use
   ca::StreamPack stream;         // few-state streaming form of Q, built on first use
   bool stream_built = false;
   ca::DeviceBuffer<double> L1r, L2r;  // row-major copies of L1, L2 for the streaming kernel's dense part

@@ -66,12 +66,9 @@ def hookstepsolve_model(model: ModelOperators, R, xguess, params: SearchParams |
     params = params or SearchParams()
     X = np.asarray(xguess, dtype=np.float64)
     single = X.ndim == 1
-    if model.m > DEVICE_RESIDENT_MAX_M:
-        # 3 m^2 doubles no longer fit in one CTA's shared memory: host-driven search, every f / Df on the device
-        if not single:
-            raise CloudAtlasError(5, f"batched searches need m <= {DEVICE_RESIDENT_MAX_M}")
-        x, ok = _hookstepsolve_closures(lambda v: model.f(v, float(R)), lambda v: model.Df(v, float(R)), X, params)
-        return (x, ok, {"exit_reason": "host_driven", "device_seconds": None}) if return_log else (x, ok)
+    # any m goes through the library: up to DEVICE_RESIDENT_MAX_M modes one persistent CTA per search; beyond that the
+    # global-memory solver (csrc/hookstep_large.cu: blocked LU, Df'Df and all vectors on the device, searches one after
+    # the other)
     X = np.asfortranarray(X.reshape(1, -1) if single else X)
     if X.shape[1] != model.m:
         raise CloudAtlasError(1, f"xguess has {X.shape[1]} columns, expected {model.m}")

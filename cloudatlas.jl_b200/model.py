@@ -11,6 +11,7 @@ from .bilinear import (SparseBilinear, _check_device_tensor, _colmajor_ensemble,
 
 _create = _sig("ca_model_create", c_f64p, c_f64p, c_f64p, C.c_int64, c_i64p, c_f64p, C.c_int64, C.POINTER(vp))
 _create_dev = _sig("ca_model_create_dev", vp, vp, vp, C.c_int64, vp, vp, vp, vp, C.c_int64, vp, C.POINTER(vp))
+_create_from_assembly = _sig("ca_model_create_from_assembly", vp, C.POINTER(vp))
 _build_info = _sig("ca_model_build_info", vp, C.POINTER(C.c_int32), c_f64p, c_i64p, c_i64p, c_i64p)
 _digest = _sig("ca_model_digest", vp, C.POINTER(C.c_uint64))
 _destroy = _sig("ca_model_destroy", vp)
@@ -88,6 +89,21 @@ class ModelOperators:
         self._h = h
         return self
 
+    @classmethod
+    def from_assembly(cls, slab):
+        """Model straight from a full assembly handle (``ca_model_create_from_assembly``): assembled operator ->
+        folded, packed model on the assembly's device; the observables come along.  Host copies of the operators are
+        fetched from the assembly only if asked for."""
+        self = cls.__new__(cls)
+        self.m = slab.m
+        self._dev = None
+        self._slab = slab
+        self._B = self._A1 = self._A2 = self._ijk = self._val = None
+        h = vp()
+        check(_create_from_assembly(slab._h, C.byref(h)))
+        self._h = h
+        return self
+
     def release_device_inputs(self):
         """Drops the CUDA tensors ``from_device`` was given (the library keeps its own compact copies)."""
         if self._dev is not None:
@@ -96,6 +112,12 @@ class ModelOperators:
 
     def _host(self, name, q):
         v = getattr(self, name)
+        if v is None and getattr(self, "_slab", None) is not None:
+            if q < 3:
+                self._B, self._A1, self._A2 = self._slab.linear_host()
+            else:
+                self._ijk, self._val = self._slab.coo_host()
+            return getattr(self, name)
         if v is None and self._dev is not None:
             t = self._dev[q]
             if q < 3:
@@ -267,8 +289,8 @@ class ODEModel(ModelOperators):
     driver: index set -> basis tables -> Galerkin assembly on the GPU(s) -> device packing."""
 
     def __init__(self, alpha, gamma, J, K, L, H, normalize=False, ijkl=None, group=None, verbose=False,
-                 dense_assembly=False, grid=(0, 0, 0)):
-        from .assembly import assemble_device
+                 dense_assembly=False, grid=(0, 0, 0), mode_scale=None):
+        from .assembly import assemble_full
         from .basis import basisComponents, basisIndices
         self.alpha, self.gamma = float(alpha), float(gamma)
         self.H = None if H is None else list(H)
@@ -278,17 +300,18 @@ class ODEModel(ModelOperators):
             print(f"J,K,L,m == {J},{K},{L},{m}")
             print(f"(2J+1)(2K+1)(2L+1) + 1 == {(2 * J + 1) * (2 * K + 1) * (2 * L + 1) + 1}")
         self.Psi = basisComponents(self.alpha, self.gamma, self.ijkl, normalize)
-        lin, idx, val, self.assembly_stats = assemble_device(self.alpha, self.gamma, self.ijkl, normalize, group,
-                                                             dense=dense_assembly, grid=grid)
-        # lin[q] holds a column-major matrix: its transpose VIEW is the m x m tensor with stride (1, m)
-        built = ModelOperators.from_device(lin[0].t(), lin[1].t(), lin[2].t(), idx, val)
+        slab, self.assembly_stats = assemble_full(self.alpha, self.gamma, self.ijkl, normalize, group,
+                                                  dense=dense_assembly, grid=grid, mode_scale=mode_scale)
+        self.mode_scale = None if mode_scale is None else np.asarray(mode_scale, dtype=np.float64)
+        built = ModelOperators.from_assembly(slab)   # installs the observables as well
         self.__dict__.update(built.__dict__)
         built._h = None   # the handle now belongs to this object
         self._N = None
         from .basis import shearVector
         self.Psishear = shearVector(self.alpha, self.gamma, self.ijkl, normalize)   # ODEModels.jl:65-78
-        self.D = np.asfortranarray(lin[3].t().cpu().numpy())                         # ODEModels.jl:129-137
-        check(_set_obs(self._h, _f64(self.Psishear), _f64(self.D)))
+        if self.mode_scale is not None:
+            self.Psishear = self.Psishear * self.mode_scale
+        self.D = slab.dissipation_host()                                             # ODEModels.jl:129-137
 
     def observables(self, x):
         """(shear, dissipation) of shear_function / dissipation_function (ODEModels.jl:65-137) for one state

@@ -70,6 +70,23 @@ int32_t ca_measure_fp64_peak(double* dmma_tflops, double* dfma_tflops);
 /* number of kernels launched by this library in the calling process so far (bench bookkeeping) */
 int64_t ca_launch_count(void);
 
+/* ---- several GPUs of one box ---------------------------------------------------------------- */
+/* A communicator over NCCL (resolved at run time: dlopen of libnccl.so.2; single-GPU use never loads it).
+ *   ca_comm_init_all: ONE process drives ngpus devices (devices == NULL: 0..ngpus-1) -- the Julia case, no NCCL.jl
+ *     needed; handles come back one per device, in device order.
+ *   ca_comm_unique_id / ca_comm_init_rank: one process per GPU (torchrun, MPI); rank 0 creates the 128-byte id, the
+ *     launcher's own transport delivers it, every rank joins with the device that is current in its process.
+ * ca_init(ngpus) / ca_shutdown keep a process-wide default communicator that entry points taking `comm == NULL` use
+ * (SURVEY.md 8b). */
+typedef struct ca_comm ca_comm;
+int32_t ca_init(int32_t ngpus);
+int32_t ca_shutdown(void);
+int32_t ca_comm_init_all(int32_t ngpus, const int32_t* devices, ca_comm** out);
+int32_t ca_comm_unique_id(char* id128);
+int32_t ca_comm_init_rank(int32_t nranks, int32_t rank, const char* id128, ca_comm** out);
+int32_t ca_comm_info(const ca_comm* c, int32_t* nranks, int32_t* nlocal, int32_t* first_rank, int32_t* nccl_version);
+int32_t ca_comm_destroy(ca_comm* c);
+
 /* ---- index sets and basis (reference: src/BasisFunctions.jl, src/Symmetries.jl) --------------- */
 /* basisIndices(J,K,L[,H]) -- BasisFunctions.jl:489-574 with the symmetric() filter of
  * Symmetries.jl:25-60.  Host only, integer only, bit-exact incl. row order.  nH = 0: unfiltered.
@@ -143,6 +160,13 @@ int32_t ca_model_create(const double* B, const double* A1, const double* A2, int
 int32_t ca_model_create_dev(const double* dB, const double* dA1, const double* dA2, int64_t m, const int64_t* d_i,
                             const int64_t* d_j, const int64_t* d_k, const double* d_val, int64_t nnz, void* stream,
                             ca_model** out);
+/* ODEModel straight from a full assembly (all rows: ca_assemble(..., 0, m) or an output of ca_assemble_sharded), on
+ * the assembly's device: assembled operator -> folded, packed model without leaving the GPU; also installs the
+ * observables (shear vector and D of ODEModels.jl:65-137) that the assembly computed. */
+int32_t ca_model_create_from_assembly(ca_assembly* a, ca_model** out);
+/* f(x_s, R) of ONE host ensemble on several devices of this process: models[d] are replicas of one model on different
+ * devices; states are split evenly, one host thread and one copy/compute pipeline per device, no collective. */
+int32_t ca_models_rhs_batched(ca_model** models, int32_t nmodels, const double* X, int64_t nstates, double R, double* OUT);
 /* How the model was built: *on_device = 1 for the device build; seconds9 = wall seconds {total, blocks of B, fold,
  * symmetrise + CSR, sketches + clustering, tile unions, layout (host), value placement, streaming form}. */
 int32_t ca_model_build_info(const ca_model* h, int32_t* on_device, double* seconds9, int64_t* nclusters,
@@ -197,6 +221,26 @@ int32_t ca_assemble(double alpha, double gamma, const int64_t* ijkl /* m x 4 col
 int32_t ca_assemble_dense(double alpha, double gamma, const int64_t* ijkl, int64_t m, int32_t normalize,
                           int64_t row_begin, int64_t row_end, int32_t nx, int32_t ny, int32_t nz,
                           ca_assembly** out);
+/* Both paths for a basis with coefficients -- the reference's data model  c * Psi  (BasisFunctions.jl:417; its
+ * normalisation :697-699 is the special case c_n = 1/||Psi_n||):
+ *   mode_scale (m values, may be NULL): Psi_n -> s_n Psi_n, hence N'_ijk = s_i s_j s_k N_ijk, B'_ij = s_i s_j B_ij;
+ *   mix (m x m column-major C, may be NULL, dense != 0 only): Phi_n = sum_p Psi_p C[p,n], a basis whose members do
+ *   not factorise in x, y, z -- only the dense quadrature applies; N' = N x1 C x2 C x3 C is dense, so assemble row
+ *   slabs.  B', A1', A2', D' = C' (.) C.
+ * dense = 0: ca_assemble; dense != 0: ca_assemble_dense on the grid nx, ny, nz (0 = smallest exact). */
+int32_t ca_assemble_basis(double alpha, double gamma, const int64_t* ijkl, int64_t m, int32_t normalize,
+                          const double* mode_scale, const double* mix, int32_t dense, int32_t nx, int32_t ny, int32_t nz,
+                          int64_t row_begin, int64_t row_end, ca_assembly** out);
+/* The assembly sharded by output mode i over the ranks of `comm` (NULL: the ca_init communicator) with its single
+ * collective: every rank assembles a contiguous range of rows, slab sizes are exchanged, and all pieces
+ * of all slabs are broadcast into place inside ONE NCCL group over NVLink.  out[d], d < nlocal, receives for local
+ * device d a FULL assembly (rows 0..m, lexicographic COO identical on every device and identical to the single-GPU
+ * result) -- ready for ca_model_create_from_assembly.  dense != 0: the quadrature path (slabs aligned to 128 rows). */
+int32_t ca_assemble_sharded(ca_comm* comm, double alpha, double gamma, const int64_t* ijkl, int64_t m,
+                            int32_t normalize, const double* mode_scale, int32_t dense, int32_t nx, int32_t ny,
+                            int32_t nz, ca_assembly** out);
+/* ranks that took part, CUDA-event seconds of the collective on this device, bytes of the gathered operator */
+int32_t ca_assembly_gather_info(const ca_assembly* h, int32_t* world, double* gather_seconds, int64_t* gather_bytes);
 /* grid used, CUDA-event seconds of the contraction kernel alone and its algorithmic flops 2 rows m^2 3 Nq */
 int32_t ca_assembly_dense_info(const ca_assembly* h, int32_t* grid3, double* contract_seconds,
                                double* contract_flops);
@@ -273,9 +317,11 @@ typedef struct ca_solve_log {
 /* hookstepsolve(x -> model.f(x,R), x -> model.Df(x,R), xguess, params) -- Hookstep.jl:109-352 with
  * hookstep() :21-74 -- as ONE persistent kernel: a single CTA keeps x, f(x), Df(x), Df'Df and the LU
  * workspaces in shared memory for the whole search (no launches, no host round trips inside the
- * loop).  Same decision tree, constants and exit flags as the reference.  m is limited by shared
- * memory (3 m^2 + 9 m doubles <= 227 KB, m <= 95); larger models return CA_ERR_UNSUPPORTED.
- * nsolve independent searches (own R, own guess; one CTA each) run in one launch:
+ * loop).  Same decision tree, constants and exit flags as the reference.  The one-CTA solver is limited by shared
+ * memory (3 m^2 + 9 m doubles <= 227 KB, m <= 95); larger models run the same search with f, Df, Df'Df, the LU factors
+ * and every vector in device global memory (blocked LU with partial pivoting, csrc/hookstep_large.cu): the host only
+ * sees the scalars the decision tree branches on.
+ * nsolve independent searches (own R, own guess; one CTA each, or one after the other for m > 95) run in one call:
  * R: nsolve, Xguess / X_out: nsolve x m column-major, success / logs: nsolve (logs may be NULL). */
 int32_t ca_hookstep_solve_model(ca_model* h, const double* R, const double* Xguess, int64_t nsolve,
                                 const ca_search_params* params, double* X_out, int32_t* success,
@@ -297,6 +343,11 @@ int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64_t nnz, int
  * Used to show that the device model build (ca_model_create_dev) and the host packer produce the same pack. */
 int32_t ca_selftest_pack_digest(const int64_t* ijk, const double* val, int64_t nnz, int64_t m, int32_t symmetric,
                                 int32_t window_modes, uint64_t* digest8);
+
+/* The blocked LU of the large-model solver on a caller-supplied dense system (column-major m x m, host): A is
+ * overwritten by its factors (unit lower L below the diagonal, U on and above; rows interchanged as LAPACK's getrf
+ * does), b by the solution of A x = b. */
+int32_t ca_selftest_lu_solve(double* A, int64_t m, double* b, int32_t* singular);
 
 /* Generates the model-specialised ensemble kernel (m <= 48) for a quadratic operator plus a dense linear pattern and
  * compiles it with NVRTC for sm_100a; reports the cubin size and the CTA shape.  No device needed: the module is

@@ -216,3 +216,62 @@ def test_dense_quadrature_row_slabs(ca):
     parts = [ca.AssemblySlab(1.0, 2.0, ijkl, False, r0, r1, dense=True).coo_host() for r0, r1 in ((0, 13), (13, 44))]
     assert np.array_equal(np.concatenate([p[0] for p in parts]), full[0])
     assert np.array_equal(np.concatenate([p[1] for p in parts]), full[1])
+
+
+def test_random_coefficient_basis_mode_scale(ca):
+    """north_star: "random-coefficient bases" = the reference's data model c * Psi (BasisFunctions.jl:417) with
+    s_n ~ U(0.5, 2), seed 20251029: N'_ijk = s_i s_j s_k N_ijk, B'_ij = s_i s_j B_ij, same pattern; both
+    assembly paths; the model built on the scaled basis satisfies f'(x) = S^-1 f(S x)."""
+    rng = np.random.default_rng(20251029)
+    for JKL in ((2, 2, 3), (3, 3, 12)):
+        ijkl = ca.basisIndices(*JKL, lib_H(ca))
+        m = ijkl.shape[0]
+        s = rng.uniform(0.5, 2.0, m)
+        plain = ca.AssemblySlab(1.0, 2.0, ijkl)
+        scaled = ca.AssemblySlab(1.0, 2.0, ijkl, mode_scale=s)
+        (ijk, v), (ijk2, v2) = plain.coo_host(), scaled.coo_host()
+        assert np.array_equal(ijk, ijk2)
+        want = v * s[ijk[:, 0] - 1] * s[ijk[:, 1] - 1] * s[ijk[:, 2] - 1]
+        assert maxrel(v2, want) < 1e-13                              # the assembly metric: max-abs over max-abs
+        assert np.max(np.abs(v2 - want) / np.abs(want)) < 1e-10      # entrywise (entries are sums with cancellation)
+        for P, Q in zip(plain.linear_host(), scaled.linear_host()):
+            assert maxrel(Q, P * np.outer(s, s)) < 1e-13
+        if m < 100:
+            dense = ca.AssemblySlab(1.0, 2.0, ijkl, dense=True, mode_scale=s)
+            assert np.array_equal(dense.coo_host()[0], ijk)
+            assert maxrel(dense.coo_host()[1], want) < TOL
+    with pytest.raises(ca.CloudAtlasError, match="non-zero"):
+        ca.AssemblySlab(1.0, 2.0, ijkl, mode_scale=np.zeros(m))
+    # the ODE of the scaled basis is the same flow in rescaled coordinates: x' = S^-1 x
+    H = lib_H(ca)
+    s = rng.uniform(0.5, 2.0, 44)
+    a = ca.ODEModel(1.0, 2.0, 2, 2, 3, H)
+    b = ca.ODEModel(1.0, 2.0, 2, 2, 3, H, mode_scale=s)
+    x = 0.1 * rng.standard_normal(44)
+    assert maxrel(b.f(x / s, 200.0) * s, a.f(x, 200.0)) < 1e-11
+    assert abs(b.shear(x / s) - a.shear(x)) < 1e-13 and abs(b.dissipation(x / s) - a.dissipation(x)) < 1e-12
+
+
+def test_mixed_basis_dense_quadrature(ca):
+    """The dense quadrature path on a basis that does NOT factorise: Phi = Psi C, C = I + 0.1 G, G_ij ~ N(0,1)
+    (SURVEY 8d).  N' = N x1 C x2 C x3 C and B' = C' B C against numpy contractions of the separable result."""
+    rng = np.random.default_rng(20251029)
+    for JKL, slab in (((1, 1, 3), (0, 17)), ((2, 2, 3), (0, 44)), ((2, 2, 3), (13, 30))):
+        ijkl = ca.basisIndices(*JKL, lib_H(ca))
+        m = ijkl.shape[0]
+        Cm = np.eye(m) + 0.1 * rng.standard_normal((m, m))
+        plain = ca.AssemblySlab(1.0, 2.0, ijkl)
+        ijk, v = plain.coo_host()
+        N = np.zeros((m, m, m))
+        N[ijk[:, 0] - 1, ijk[:, 1] - 1, ijk[:, 2] - 1] = v
+        want = np.einsum("ia,jb,kc,ijk->abc", Cm, Cm, Cm, N, optimize=True)
+        mixed = ca.AssemblySlab(1.0, 2.0, ijkl, False, slab[0], slab[1], dense=True, mix=Cm)
+        mijk, mv = mixed.coo_host()
+        got = np.zeros((m, m, m))
+        got[mijk[:, 0] - 1, mijk[:, 1] - 1, mijk[:, 2] - 1] = mv
+        assert np.all(mijk[:, 0] - 1 >= slab[0]) and np.all(mijk[:, 0] - 1 < slab[1])
+        assert np.max(np.abs(got[slab[0]:slab[1]] - want[slab[0]:slab[1]])) / np.max(np.abs(want)) < TOL
+        for P, Q in zip(plain.linear_host(), mixed.linear_host()):
+            assert maxrel(Q[slab[0]:slab[1]], (Cm.T @ P @ Cm)[slab[0]:slab[1]]) < 1e-13
+    with pytest.raises(ca.CloudAtlasError, match="dense"):
+        ca.AssemblySlab(1.0, 2.0, ijkl, mix=Cm)
