@@ -234,7 +234,30 @@ def run_b200(args):
     e2e_value = world * n * e2e_steps / e2e_s
     e2e_check = float(torch.linalg.norm(Oh[:, :1000].cuda() - OUT.t()[:, :1000]) /
                       torch.linalg.norm(OUT.t()[:, :1000]))
-    del Xh, Oh, Xh_np, Oh_np
+    # ---- the ceiling of that path: the same bytes as plain page-locked copies, H2D and D2H concurrently, every
+    # rank at once (what the host's memory system and the PCIe links give N ranks together)
+    copy_bytes = min(8 * m * n, 1 << 30)
+    dbuf = torch.empty(copy_bytes // 8, dtype=torch.float64, device="cuda")
+    dbuf2 = torch.empty(copy_bytes // 8, dtype=torch.float64, device="cuda")
+    hin, hout = Xh.view(-1)[: copy_bytes // 8], Oh.view(-1)[: copy_bytes // 8]
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    def copies():
+        with torch.cuda.stream(s_in):
+            dbuf.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hout.copy_(dbuf2, non_blocking=True)
+    copies()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        copies()
+    barrier()
+    copy_s = max_over_ranks(time.perf_counter() - t0) / 3
+    ceiling = world * (copy_bytes / (8 * m)) / copy_s          # evals/s if the step were nothing but its copies
+    e2e_ceiling = {"value": ceiling, "unit": UNIT, "per_rank_GBs_each_way": copy_bytes / copy_s / 1e9,
+                   "bytes_each_way": copy_bytes,
+                   "how": "page-locked cudaMemcpyAsync H2D and D2H on two streams, all ranks concurrently, barrier on both sides"}
+    del Xh, Oh, Xh_np, Oh_np, dbuf, dbuf2, hin, hout
 
     # ---- roofline of the dominant (only) kernel of the step: the DMMA ensemble kernel in MODE_QUAD
     ijk = model.ijk
@@ -265,6 +288,8 @@ def run_b200(args):
         "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
         "peak_source": "measured in this run (ca_measure_fp64_peak: DMMA loop); MEASURED_PEAKS.json has no FP64 entry",
         "dfma_peak": dfma_peak, "traffic": traffic,
+        "traffic_source": "stored ncu --set full capture (profiles/ncu_traffic.json, profiles/r01_rhs307_ncu_raw.csv): "
+                          "dram__bytes_read.sum + dram__bytes_write.sum of one launch scaled to this launch's states; not re-measured in this run",
         "kernel": KERNEL_NAMES.get(model.kernel_path(n)[0], model.kernel_path(n)[0]), "kernel_ms": kernel_ms,
         "algorithmic_flops_per_state": flops_state, "executed_fma_per_state": info["padded_fma_per_state"],
         "algorithmic_bytes_per_state": bytes_state,
@@ -284,22 +309,36 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * m * n, "d2h_bytes_per_step": 8 * m * n,
                 "steps": e2e_steps, "path": "ca_model_rhs_batched (host pointers, page-locked, chunks of whole kernel waves on three streams)",
-                "agrees_with_device_path": e2e_check},
+                "agrees_with_device_path": e2e_check, "copy_ceiling": e2e_ceiling,
+                "frac_of_copy_ceiling": e2e_value / ceiling, "frac_of_device_rate": e2e_value / value},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "model_build": {"seconds_total": build_s, "assembly_device_seconds": model.assembly_stats["device_seconds"],
-                        "world": world, "note": "index set + GPU assembly (+ all-gather) + host B^-1 folding + DMMA packing"},
+                        "gather_seconds": model.assembly_stats.get("gather_seconds", 0.0),
+                        "model_create": model.build_info(), "world": world,
+                        "note": "ODEModel(alpha,gamma,J,K,L,H): index set + basis tables + GPU assembly (+ library-side NCCL "
+                                "all-gather) + device model build (B^-1 folding, symmetrisation, DMMA packing on the GPU); "
+                                "first call in the process, includes CUDA context / NCCL set-up"},
         "kernel_path": model.kernel_path(n)[0],
     }
 
     if not args.no_extras:
+        del X, OUT
+        torch.cuda.empty_cache()
         dense = dense_assembly_case(ca, H, world, rank, max_over_ranks, barrier, dmma_peak)
+        c4 = large_basis_case(ca, H, (5, 5, 16), world, rank, max_over_ranks, barrier, dmma_peak, hbm_peak)
+        c5 = large_basis_case(ca, H, (8, 8, 20), world, rank, max_over_ranks, barrier, dmma_peak, hbm_peak)
         if rank == 0:
             line["roofline_assembly"] = dense
+            line["config4"] = c4
+            line["config5"] = c5
     if rank == 0 and world == 1 and not args.no_extras:
         line["assembly"] = assembly_sweep(ca, H)
+        line["roofline_assembly_mixed"] = mixed_basis_case(ca, H, dmma_peak)
         line["roofline_hbm_case"] = hbm_case(ca, H, hbm_peak)
+        line["hookstep"] = hookstep_cases(ca, H)
         line["cpu_baseline"] = cpu_baseline(model, args)
+        line["cpu_baseline_assembly"] = cpu_baseline_assembly()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -331,18 +370,214 @@ def dense_assembly_case(ca, H, world, rank, max_over_ranks, barrier, dmma_peak):
             "nnz_rank0": int(nnz), "kernel": "dense_contract_kernel"}
 
 
-def assembly_sweep(ca, H):
-    """Q-assembly seconds vs basis size (second half of BASELINE.json's metric)."""
-    out = []
-    for jkl in [(1, 1, 3), (2, 2, 3), (3, 3, 12), (5, 5, 16)]:
-        ijkl = ca.basisIndices(*jkl, H)
-        ca.AssemblySlab(ALPHA, GAMMA, ijkl)                      # warm-up (first launch, allocator)
+NVLINK_BUSBW_MEASURED = 725.0   # GB/s, all-gather bus bandwidth measured on this pool's 8 x B200 boxes
+
+
+def large_basis_case(ca, H, jkl, world, rank, max_over_ranks, barrier, dmma_peak, hbm_peak, nstates=9472):
+    """BASELINE.json configs[3] / [4] end to end at N GPUs: assembly sharded by output mode through the library's own
+    NCCL communicator (one grouped all-gather), device model build from the gathered operator, then ensemble f and
+    Jacobian actions (the Newton-Krylov evaluation) with states sharded over the ranks, and single-state f / Jacobian
+    action (HBM-bound stream of the operator)."""
+    import numpy as np
+    import torch
+    ijkl = ca.basisIndices(*jkl, H)
+    m = ijkl.shape[0]
+    passes = []
+    for rep in range(2):        # the first pass pays for NCCL channel set-up and first-touch allocations
+        barrier()
         t0 = time.perf_counter()
-        slab = ca.AssemblySlab(ALPHA, GAMMA, ijkl)
+        slab, st = ca.assemble_full(ALPHA, GAMMA, ijkl)
+        barrier()
+        t1 = time.perf_counter()
+        model = ca.ModelOperators.from_assembly(slab)
+        x1 = torch.zeros(m, dtype=torch.float64, device="cuda")
+        model.f(x1, R)
+        barrier()
+        t2 = time.perf_counter()
+        bi = model.build_info()
+        passes.append({"assembly_wall_seconds": max_over_ranks(t1 - t0), "slab_device_seconds": max_over_ranks(st["device_seconds"]),
+                       "all_gather_seconds": max_over_ranks(st["gather_seconds"]), "all_gather_bytes": st["gather_bytes"],
+                       "model_create_seconds": max_over_ranks(bi["seconds"]["total"]),
+                       "time_to_first_eval_seconds": max_over_ranks(t2 - t0)})
+        nnz = slab.nnz
+        if rep == 0:
+            del model, slab
+    gs = passes[1]["all_gather_seconds"]
+    busbw = passes[1]["all_gather_bytes"] * (world - 1) / world / gs / 1e9 if world > 1 and gs > 0 else None
+    info = model.info()
+    gen = torch.Generator(device="cuda").manual_seed(SEED + 100 + rank)
+    X = (0.1 * torch.randn((m, nstates), dtype=torch.float64, device="cuda", generator=gen)).t()
+    V = torch.randn((m, nstates), dtype=torch.float64, device="cuda", generator=gen).t()
+
+    def timed(fn, reps):
+        fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / reps
+
+    rhs_ms = timed(lambda: model.f(X, R), 2)
+    jvp_ms = timed(lambda: model.Df_action(X, V, R), 2)
+    x0, v0 = X[0].contiguous(), V[0].contiguous()
+    rhs1_ms = timed(lambda: model.f(x0, R), 10)
+    jvp1_ms = timed(lambda: model.Df_action(X[:1], V[:1], R), 10)
+    fma = info["padded_fma_per_state"]
+    exec_tf = 2.0 * fma * nstates / (rhs_ms * 1e-3) / 1e12
+    stream_bytes = 12 * info["nnz_q_sym"] + 16 * m * m       # streamed operator: 12 B per entry + the dense linear part
+    out = {"workload": f"m={m} (J,K,L={jkl[0]},{jkl[1]},{jkl[2]}): sharded assembly + all-gather + device model build + "
+                       f"{nstates} states per GPU of f and Jacobian actions",
+           "m": int(m), "nnz_N": int(nnz), "n_gpus": world, "first_pass": passes[0], "steady_pass": passes[1],
+           "all_gather_busbw_GBs": busbw, "nvlink_busbw_measured_GBs": NVLINK_BUSBW_MEASURED,
+           "all_gather_frac_of_measured": (busbw / NVLINK_BUSBW_MEASURED) if busbw else None,
+           "collective": "ca_assemble_sharded: slab sizes (8-byte all-gather), then every piece of every slab broadcast in place "
+                         "inside one ncclGroup (csrc/comm.cu)" if world > 1 else "none (one GPU)",
+           "rhs_evals_per_sec": world * nstates / (rhs_ms * 1e-3), "jvp_per_sec": world * nstates / (jvp_ms * 1e-3),
+           "rhs_ms": rhs_ms, "jvp_ms": jvp_ms, "kernel_path": model.kernel_path(nstates)[0],
+           "executed_fma_per_state": fma, "rhs_executed_tflops_per_gpu": exec_tf, "rhs_executed_frac_of_dmma_peak": exec_tf / dmma_peak,
+           "jvp_executed_frac_of_dmma_peak": 2.0 * fma * nstates / (jvp_ms * 1e-3) / 1e12 / dmma_peak,
+           "single_state": {"rhs_ms": rhs1_ms, "jvp_ms": jvp1_ms, "bound": "hbm", "algorithmic_bytes": stream_bytes,
+                            "rhs_GBs": stream_bytes / (rhs1_ms * 1e-3) / 1e9,
+                            "rhs_frac_of_hbm": stream_bytes / (rhs1_ms * 1e-3) / 1e9 / hbm_peak}}
+    del model, slab, X, V
+    torch.cuda.empty_cache()
+    return out
+
+
+def mixed_basis_case(ca, H, dmma_peak):
+    """The dense quadrature path on a basis that does not factorise in x, y, z -- Phi = Psi C, C = I + 0.1 G,
+    G_ij ~ N(0,1), seed 20251029, on top of mode scales s_n ~ U(0.5, 2): one 128-row slab of the
+    999-mode basis on the 16 x 33 x 16 grid.  The separable path cannot assemble such a basis at all."""
+    import numpy as np
+    ijkl = ca.basisIndices(5, 5, 16, H)
+    m = ijkl.shape[0]
+    rng = np.random.default_rng(SEED)
+    s = rng.uniform(0.5, 2.0, m)
+    Cm = np.eye(m) + 0.1 * rng.standard_normal((m, m))
+    t0 = time.perf_counter()
+    slab = ca.AssemblySlab(ALPHA, GAMMA, ijkl, False, 384, 512, dense=True, grid=(16, 33, 16), mode_scale=s, mix=Cm)
+    wall = time.perf_counter() - t0
+    info = slab.dense_info()
+    tf = info["contract_flops"] / info["contract_seconds"] / 1e12
+    out = {"workload": "dense quadrature assembly of N on a mixed random-coefficient basis Phi = (Psi diag(s)) C, m=999, rows 384:512, grid 16x33x16",
+           "bound": "tensor", "pipe": "fp64 DMMA", "achieved": tf, "peak": dmma_peak, "unit": "TFLOP/s", "frac": tf / dmma_peak,
+           "contract_seconds": info["contract_seconds"], "wall_seconds": wall, "nnz_slab": int(slab.nnz),
+           "dense_fraction_of_slab": slab.nnz / (128.0 * m * m), "kernel": "dense_contract_kernel"}
+    del slab
+    return out
+
+
+def hookstep_cases(ca, H):
+    """BASELINE.json configs[0] / [1]: the Newton-hookstep search of the find-eqb / continue-eqb notebooks, device
+    resident, beside the same search on the host (oracle/hookstep.py: Hookstep.jl restated in numpy on the oracle's
+    CPU model -- LAPACK solves, one core)."""
+    import numpy as np
+    from oracle.hookstep import hookstepsolve as ref_solve
+    golden = os.path.join(ROOT, "tests", "golden")
+    known = json.load(open(os.path.join(golden, "reference_known_answers.json")))
+
+    def read_asc(name):
+        return np.array([float(t) for t in open(os.path.join(golden, name)).read().split("\n") if t.strip() and not t.startswith("%")])
+
+    out = []
+    x44 = None
+    for name, jkl, guess in (("17d", (1, 1, 3), np.array(known["m17_unnormalized"]["xguess"])),
+                             ("44d", (2, 2, 3), read_asc(known["m44"]["guess_file"])), ("307", (3, 3, 12), None)):
+        model = ca.ODEModel(ALPHA, GAMMA, *jkl, H)
+        if guess is None:
+            guess = ca.changebasis(x44, small_ijkl, model.ijkl)
+        params = ca.SearchParams(Nnewton=30)
+        ca.hookstepsolve(model, R, guess, params)                                   # warm-up (lazy structures, first launch)
+        t0 = time.perf_counter()
+        x, ok, log = ca.hookstepsolve(model, R, guess, params, return_log=True)
         wall = time.perf_counter() - t0
-        out.append({"JKL": list(jkl), "m": int(slab.m), "nnz": int(slab.nnz),
-                    "device_seconds": slab.device_seconds, "wall_seconds_incl_tables": wall})
-        del slab
+        if name == "44d":
+            x44, small_ijkl = x, model.ijkl
+        from oracle.cref import CRefModel
+        ref = CRefModel(model.B, model.A1, model.A2, model.ijk, model.val)
+        from oracle.hookstep import SearchParams as RP
+        Bf = np.linalg.inv(model.B)
+        fcpu = lambda v: ref.f(v, R)
+        Dfcpu = lambda v: Bf @ (model.A1 + model.A2 / R + ref.derivative(v))
+        t0 = time.perf_counter()
+        xr, okr = ref_solve(fcpu, Dfcpu, guess, RP(Nnewton=30))
+        cpu = time.perf_counter() - t0
+        entry = {"model": name, "m": int(model.m), "converged": bool(ok), "newton_steps": log["newton_steps"],
+                 "device_seconds": log["device_seconds"], "wall_seconds": wall,
+                 "solver": "one persistent CTA (shared memory)" if model.m <= 95 else "global-memory solver (blocked LU, csrc/hookstep_large.cu)",
+                 "cpu_baseline": {"seconds": cpu, "cores": 1, "kind": "port",
+                                  "what": "Hookstep.jl:109-352 restated in numpy, f / derivative by the reference's COO loops in C, LAPACK solves"},
+                 "agrees_with_cpu": float(np.linalg.norm(x - xr) / np.linalg.norm(xr))}
+        if model.m <= 95:   # batches of independent searches: what the one-CTA solver is for
+            nb = 128
+            Rs = np.linspace(R - 5, R + 5, nb)
+            t0 = time.perf_counter()
+            X, good = ca.hookstepsolve(model, Rs, np.tile(x, (nb, 1)), params)
+            entry["batch_of_128"] = {"wall_seconds": time.perf_counter() - t0, "converged": int(good.sum()),
+                                     "seconds_per_search": (time.perf_counter() - t0) / nb}
+        out.append(entry)
+        del model
+    return out
+
+
+def cpu_baseline_assembly():
+    """The reference's assembly algorithm on one host core (Julia unavailable): the oracle's restatement of
+    ODEModels.jl:31-51 at the sizes it finishes in seconds, an m^3 extrapolation (labelled) beyond, and the oracle's
+    vectorised exact-table tier at m = 307."""
+    from oracle.basis import basisIndices, halfbox_symmetries
+    from oracle.fastfloat import FloatTables, assemble_N_float
+    from oracle.model import ODEModel as RefModel
+    import numpy as np
+    sx, sy, sz, tx, tz = halfbox_symmetries()
+    Hs = [sx * sy * sz, sz * tx * tz]
+    rows, per = [], []
+    for jkl in ((1, 1, 3), (1, 2, 3), (2, 2, 3)):
+        t0 = time.perf_counter()
+        mdl = RefModel(ALPHA, GAMMA, *jkl, Hs)
+        dt = time.perf_counter() - t0
+        mm = int(mdl.B.shape[0])
+        rows.append({"m": mm, "seconds": dt, "measured": True})
+        per.append(dt / mm ** 3)
+    c = float(np.median(per))
+    for mm in (307, 999, 2962):
+        rows.append({"m": mm, "seconds": c * mm ** 3, "measured": False, "how": "extrapolated ~ m^3 from the measured sizes"})
+    ijkl = np.array(basisIndices(3, 3, 12, Hs))
+    t0 = time.perf_counter()
+    assemble_N_float(ALPHA, GAMMA, ijkl, tables=FloatTables(ALPHA, GAMMA, ijkl))
+    vec = time.perf_counter() - t0
+    return {"cores": 1, "kind": "port", "rows": rows,
+            "vectorised_tier_m307_seconds": vec,
+            "what": "oracle/model.py (the reference's m^2 + m^3 inner-product loops, ODEModels.jl:31-51) on one core; "
+                    "oracle/fastfloat.py is the oracle's numpy-vectorised separable formulation"}
+
+
+def assembly_sweep(ca, H):
+    """Q-assembly seconds vs basis size (second half of BASELINE.json's metric) on random-coefficient bases
+    (Psi_n -> s_n Psi_n, s_n ~ U(0.5, 2), seed 20251029: SURVEY.md 8d), and what a user waits for: assembly wall time
+    plus the device model build (ca_model_create_from_assembly)."""
+    import numpy as np
+    import torch
+    out = []
+    rng = np.random.default_rng(SEED)
+    for jkl in [(1, 1, 3), (2, 2, 3), (3, 3, 12), (5, 5, 16), (8, 8, 20)]:
+        ijkl = ca.basisIndices(*jkl, H)
+        s = rng.uniform(0.5, 2.0, ijkl.shape[0])
+        ca.AssemblySlab(ALPHA, GAMMA, ijkl, mode_scale=s)        # warm-up (first launch, allocator)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        slab = ca.AssemblySlab(ALPHA, GAMMA, ijkl, mode_scale=s)
+        t1 = time.perf_counter()
+        model = ca.ModelOperators.from_assembly(slab)
+        t2 = time.perf_counter()
+        out.append({"JKL": list(jkl), "m": int(slab.m), "nnz": int(slab.nnz), "basis": "random-coefficient (mode scales)",
+                    "device_seconds": slab.device_seconds, "wall_seconds_incl_tables": t1 - t0,
+                    "model_create_seconds": t2 - t1, "wall_seconds_incl_model": t2 - t0,
+                    "model_create_phases": model.build_info()["seconds"]})
+        del model, slab
+        torch.cuda.empty_cache()
     return out
 
 

@@ -115,23 +115,93 @@ def test_batched_searches_re_sweep(ca, known, model17):
     assert np.array_equal(single, X[2])           # bit-reproducible, independent of the batch
 
 
-def test_larger_models_use_the_host_driven_search(ca, known, H):
-    """m > 95: the C entry point refuses (shared memory), the mirror drives Hookstep.jl's loop from the host with every
-    f and Df evaluated on the device.  The 44d equilibrium, prolonged to a 111-mode basis, converges there."""
-    model = ca.ODEModel(1.0, 2.0, 3, 3, 4, H)
-    assert model.m > 95
-    from cloudatlas_b200.hookstep import _solve, _CParams
+def test_blocked_lu_of_the_large_solver(ca):
+    """The device LU (panel of 16 columns, row interchanges, block-row triangular solve, DGEMM trailing update) and
+    the blocked substitutions against LAPACK: same pivots, factors and solutions."""
     import ctypes as C
+    from scipy.linalg import lu_factor
+    from cloudatlas_b200._lib import _sig, c_f64p, c_i32p, check
+    fn = _sig("ca_selftest_lu_solve", c_f64p, C.c_int64, c_f64p, c_i32p)
+    rng = np.random.default_rng(7)
+    for m in (1, 5, 16, 17, 33, 100, 333, 1000):
+        A = np.asfortranarray(rng.standard_normal((m, m)))
+        b = rng.standard_normal(m)
+        lu, piv = lu_factor(A)
+        want = np.linalg.solve(A, b)
+        Ad, bd, sing = A.copy(order="F"), b.copy(), C.c_int32(0)
+        check(fn(Ad.ctypes.data_as(c_f64p), m, bd.ctypes.data_as(c_f64p), C.byref(sing)))
+        assert sing.value == 0
+        assert np.max(np.abs(Ad - lu)) / np.max(np.abs(lu)) < 1e-11 * max(1, m / 10)
+        assert np.linalg.norm(bd - want) / np.linalg.norm(want) < 1e-13 * np.linalg.cond(A)
+    Z = np.zeros((4, 4), order="F")
+    sing = C.c_int32(0)
+    check(fn(Z.ctypes.data_as(c_f64p), 4, np.zeros(4).ctypes.data_as(c_f64p), C.byref(sing)))
+    assert sing.value == 1
+
+
+def test_large_solver_follows_the_oracle_step_by_step(ca, known, model17n, nagata_H, monkeypatch):
+    """The global-memory solver (forced onto the 17-mode model) makes the same decisions as Hookstep.jl's restatement:
+    per-step residuals, trust radii and hookstep counts; and returns what the one-CTA solver returns."""
+    from oracle.hookstep import SearchParams as RP, hookstepsolve as ref_solve
+    from oracle.model import ODEModel as Ref
+    ref = Ref(1.0, 2.0, 1, 1, 3, nagata_H, normalize=True)
+    xg = np.array(known["m17_normalized"]["xguess"])
+    for delta in (0.02, 0.01, 0.1, 0.003):
+        rlog = []
+        xr, okr = ref_solve(lambda x: ref.f(x, 200.0), lambda x: ref.Df(x, 200.0), xg, RP(delta=delta), log=rlog)
+        xs, oks = ca.hookstepsolve(model17n, 200.0, xg, ca.SearchParams(delta=delta))
+        monkeypatch.setenv("CA_HOOK_LARGE", "1")
+        x, ok, log = ca.hookstepsolve(model17n, 200.0, xg, ca.SearchParams(delta=delta), return_log=True)
+        monkeypatch.delenv("CA_HOOK_LARGE")
+        assert ok == okr == oks
+        assert np.linalg.norm(x - xr) / np.linalg.norm(xr) < 1e-9
+        assert np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-9
+        assert len(rlog) == len(log["residual"])
+        for (res, dl, nh), r2, d2, n2 in zip(rlog, log["residual"], log["delta"], log["hooksteps"]):
+            assert abs(res - r2) <= 1e-6 * max(res, 1e-12) + 1e-13
+            assert abs(dl - d2) <= 1e-6 * dl
+            assert nh == n2
+        assert log["device_seconds"] > 0
+
+
+def test_larger_models_search_on_the_device(ca, known, H):
+    """m > 95: ca_hookstep_solve_model runs the global-memory solver (no CA_ERR_UNSUPPORTED, no host linear algebra).
+    The 44d equilibrium prolonged to 111 modes (per-entry Jacobian kernel) and to 307 modes converges to what the
+    closure form of hookstepsolve (Hookstep.jl:109 on device closures, LAPACK solves) finds."""
     small = ca.ODEModel(1.0, 2.0, 2, 2, 3, H)
     x44, ok = ca.hookstepsolve(small, 200.0, read_asc(known["m44"]["guess_file"]))
+    assert ok
+    for JKL in ((3, 3, 4), (3, 3, 12)):
+        model = ca.ODEModel(1.0, 2.0, *JKL, H)
+        assert model.m > 95
+        xg = ca.changebasis(x44, small.ijkl, model.ijkl)
+        x, ok, log = ca.hookstepsolve(model, 200.0, xg, ca.SearchParams(Nnewton=30), return_log=True)
+        assert ok, log
+        assert np.linalg.norm(model.f(x, 200.0)) <= 1e-8
+        xc, okc = ca.hookstepsolve(lambda v: model.f(v, 200.0), lambda v: model.Df(v, 200.0), xg, ca.SearchParams(Nnewton=30))
+        assert okc and np.linalg.norm(x - xc) / np.linalg.norm(xc) < 1e-7
+        # a sweep of searches through the same entry point (one after the other at this size)
+        Rs = np.array([195.0, 205.0])
+        X, good = ca.hookstepsolve(model, Rs, np.tile(x, (2, 1)), ca.SearchParams(Nnewton=30))
+        assert good.all()
+
+
+def test_large_solver_with_jacobian_by_ensemble_action(ca, H):
+    """m > 400: Df comes from the Jacobian action on the unit vectors through the windowed DMMA ensemble kernel.  A
+    587-mode model: the search started near an equilibrium of the model (the prolonged 44d state, converged with the
+    closure form) returns to it."""
+    small = ca.ODEModel(1.0, 2.0, 2, 2, 3, H)
+    x44, ok = ca.hookstepsolve(small, 200.0, read_asc("xeq1projection-Re200-2-2-3-44d.asc"))
+    model = ca.ODEModel(1.0, 2.0, 4, 4, 14, H)
+    assert model.m > 400
     xg = ca.changebasis(x44, small.ijkl, model.ijkl)
-    x, ok = ca.hookstepsolve(model, 200.0, xg, ca.SearchParams(Nnewton=30))
-    assert np.linalg.norm(model.f(x, 200.0)) / np.linalg.norm(x) < 1e-8
-    out, succ = np.zeros(model.m), np.zeros(1, dtype=np.int32)
-    Rv, cp = np.array([200.0]), _CParams(1e-8, 1e-8, 0.02, 20, 4, 6, 0)
-    st = _solve(model._h, Rv.ctypes.data_as(C.POINTER(C.c_double)), xg.ctypes.data_as(C.POINTER(C.c_double)), 1,
-                C.byref(cp), out.ctypes.data_as(C.POINTER(C.c_double)), succ.ctypes.data_as(C.POINTER(C.c_int32)), None)
-    assert st == 5   # CA_ERR_UNSUPPORTED
+    x, ok, log = ca.hookstepsolve(model, 200.0, xg, ca.SearchParams(Nnewton=40), return_log=True)
+    assert ok, log
+    assert np.linalg.norm(model.f(x, 200.0)) <= 1e-8
+    D = model.Df(x, 200.0)                                         # per-entry kernel; the solver used the ensemble action
+    v = np.random.default_rng(0).standard_normal(model.m)
+    jv = model.Df_action(x, v, 200.0)
+    assert np.linalg.norm(D @ v - jv) / np.linalg.norm(jv) < 1e-12
 
 
 def test_re_continuation_of_the_27d_lower_branch(ca, known, H):
