@@ -58,6 +58,9 @@ def _sym_array(H):
     return arr, len(H)
 
 
+_symmetric = _sig("ca_symmetric", c_i64p, C.POINTER(_CSym), C.c_int32, C.POINTER(C.c_int32))
+
+
 def basisIndices(J: int, K: int, L: int, H=None) -> np.ndarray:
     """m x 4 int64 matrix of (i,j,k,l) -- BasisFunctions.jl:489-574."""
     arr, nH = _sym_array(H)
@@ -69,13 +72,13 @@ def basisIndices(J: int, K: int, L: int, H=None) -> np.ndarray:
 
 
 def symmetric(ijkl, sigma) -> bool:
-    """symmetric(ijkl, sigma) for one Symmetry or a list of generators -- Symmetries.jl:25-60.
-    Implemented by asking the library to filter a one-mode box that contains the row."""
-    i, j, k, l = (int(v) for v in ijkl)
-    if not 1 <= i <= 6:
-        raise CloudAtlasError(1, f"invalid index i = {i} not in 1:6")
-    rows = basisIndices(abs(j), abs(k), max(l, 0), sigma)
-    return bool(np.any(np.all(rows == np.array([i, j, k, l]), axis=1)))
+    """symmetric(ijkl, sigma) for one Symmetry or a list of generators -- Symmetries.jl:25-60: the sign computation
+    on the row itself (``ca_symmetric``), for any (i,j,k,l) with i in 1:6."""
+    row = np.ascontiguousarray([int(v) for v in ijkl], dtype=np.int64)
+    arr, nH = _sym_array(sigma)
+    out = C.c_int32(0)
+    check(_symmetric(row.ctypes.data_as(c_i64p), arr, nH, C.byref(out)))
+    return bool(out.value)
 
 
 def basisComponents(alpha, gamma, ijkl, normalize=False):

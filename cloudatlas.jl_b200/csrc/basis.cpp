@@ -70,29 +70,40 @@ long double trig(int j, long double th) {
   return 1.0L;
 }
 
-double trig_average(int a, int b, int c, int npts) {
-  const long double two_pi = 6.283185307179586476925286766559L;
-  long double s = 0;
-  for (int n = 0; n < npts; ++n) {
-    const long double th = two_pi * (n + 0.25L) / npts;
-    s += trig(a, th) * trig(b, th) * trig(c, th);
+// trig(j, theta_n) for j = -J..J at the npts quadrature nodes, evaluated once (sinl / cosl dominated the table build:
+// 0.5 s at J = K = 8 when every average recomputed them)
+struct TrigNodes {
+  int J, npts;
+  std::vector<long double> v;  // [2J+1][npts]
+  TrigNodes(int J_, int npts_) : J(J_), npts(npts_), v((size_t)(2 * J_ + 1) * npts_) {
+    const long double two_pi = 6.283185307179586476925286766559L;
+    for (int j = -J; j <= J; ++j)
+      for (int n = 0; n < npts; ++n) v[(size_t)(j + J) * npts + n] = trig(j, two_pi * (n + 0.25L) / npts);
   }
-  return (double)(roundl(4 * s / npts) / 4);
+  const long double* of(int j) const { return v.data() + (size_t)(j + J) * npts; }
+};
+
+double trig_average(const TrigNodes& t, int a, int b, int c) {
+  const long double *ta = t.of(a), *tb = t.of(b), *tc = t.of(c);
+  long double s = 0;
+  for (int n = 0; n < t.npts; ++n) s += ta[n] * tb[n] * tc[n];
+  return (double)(roundl(4 * s / t.npts) / 4);
 }
 
 void fourier_tables(double wn, int J, std::vector<double>& pair2, std::vector<double>& triple3) {
   const int n = 2 * J + 1, npts = 6 * J + 8;
+  const TrigNodes t(J, npts);
   pair2.assign((size_t)n * n * 2, 0.0);
   triple3.assign((size_t)n * n * n * 2, 0.0);
   // d/dx E_c = wn * c * E_{-c}
   for (int a = -J; a <= J; ++a)
     for (int b = -J; b <= J; ++b) {
-      pair2[((size_t)(a + J) * n + (b + J)) * 2 + 0] = trig_average(a, b, 0, npts);
-      pair2[((size_t)(a + J) * n + (b + J)) * 2 + 1] = wn * b * trig_average(a, -b, 0, npts);
+      pair2[((size_t)(a + J) * n + (b + J)) * 2 + 0] = trig_average(t, a, b, 0);
+      pair2[((size_t)(a + J) * n + (b + J)) * 2 + 1] = wn * b * trig_average(t, a, -b, 0);
       for (int c = -J; c <= J; ++c) {
         const size_t at = (((size_t)(a + J) * n + (b + J)) * n + (c + J)) * 2;
-        triple3[at + 0] = trig_average(a, b, c, npts);
-        triple3[at + 1] = wn * c * trig_average(a, b, -c, npts);
+        triple3[at + 0] = trig_average(t, a, b, c);
+        triple3[at + 1] = wn * c * trig_average(t, a, b, -c);
       }
     }
 }
@@ -123,6 +134,8 @@ void gauss_legendre(int n, std::vector<long double>& x, std::vector<long double>
 }
 
 }  // namespace
+
+bool invariant_under_row(const ca_symmetry& g, int fam, int j, int k, int l) { return invariant_under(g, fam, j, k, l); }
 
 std::vector<int64_t> basis_indices(int J, int K, int L, const ca_symmetry* H, int nH) {
   if (J < 0 || K < 0 || L < 0) fail(CA_ERR_INVALID, "basisIndices: J, K, L must be non-negative");
@@ -309,6 +322,23 @@ int32_t ca_basis_shear(double alpha, double gamma, const int64_t* ijkl, int64_t 
     for (int64_t n = 0; n < m; ++n) {
       const ca::Component& u = T.comp[(size_t)n * 3];  // the u component
       shear_out[n] = (u.coef != 0.0 && u.jx == 0 && u.kz == 0) ? u.coef * T.wall_avg[4 * u.l + u.d + 1] : 0.0;
+    }
+  });
+}
+
+int32_t ca_symmetric(const int64_t* ijkl4, const ca_symmetry* H, int32_t nH, int32_t* out) {
+  return ca::guarded([&] {
+    if (!ijkl4 || !out || nH < 0 || (nH > 0 && !H)) ca::fail(CA_ERR_INVALID, "ca_symmetric: bad arguments");
+    const int fam = (int)ijkl4[0], j = (int)ijkl4[1], k = (int)ijkl4[2], l = (int)ijkl4[3];
+    *out = 1;
+    for (int n = 0; n < nH; ++n) {
+      // the reference raises for i outside 1:6 only where a parity table is consulted (x / z reflections)
+      if ((fam < 1 || fam > 6) && (H[n].sx == -1 || H[n].sz == -1))
+        ca::fail(CA_ERR_INVALID, "invalid index i = %d not in 1:6", fam);
+      if (!ca::invariant_under_row(H[n], fam, j, k, l)) {
+        *out = 0;
+        return;
+      }
     }
   });
 }

@@ -18,6 +18,9 @@ namespace ca {
 // symmetry generators (Symmetries.jl:25-60, parity tables BasisFunctions.jl:847-907).
 std::vector<int64_t> basis_indices(int J, int K, int L, const ca_symmetry* H, int nH);  // row-major m x 4
 
+// sigma Psi_ijkl == Psi_ijkl for one generator (Symmetries.jl:25-49); fam = i in 1..6
+bool invariant_under_row(const ca_symmetry& g, int fam, int j, int k, int l);
+
 struct Component {
   double coef;  // 0 = component absent
   int32_t jx, kz;

@@ -94,6 +94,9 @@ int32_t ca_comm_destroy(ca_comm* c);
  * in rows on entry and the row count on exit; ijkl_out is m x 4 column-major. */
 int32_t ca_basis_indices(int32_t J, int32_t K, int32_t L, const ca_symmetry* H, int32_t nH,
                          int64_t* ijkl_out, int64_t* m_inout);
+/* symmetric(ijkl, H) -- Symmetries.jl:25-60: *out = 1 iff sigma Psi_ijkl = Psi_ijkl for every generator.  A pure sign
+ * computation on one row (i,j,k,l), defined for any row with i in 1:6 whether or not basisIndices would emit it. */
+int32_t ca_symmetric(const int64_t* ijkl4, const ca_symmetry* H, int32_t nH, int32_t* out);
 /* basisSet(alpha, gamma, ijkl; normalize) in tabular form -- BasisFunctions.jl:630-702: per mode and
  * velocity component (u,v,w) the factor  coef * E_jx(x) E_kz(z) S_l^(d)(y).  Arrays are m x 3
  * column-major; d = 0 for S_l, 1 for S_l'; coef == 0 marks an absent component. */

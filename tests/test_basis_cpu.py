@@ -84,3 +84,23 @@ def test_normalized_coefficients_of_the_notebook(known):
         assert abs(T["coef"][n, 0] / k["psi_coeffs_first5"][n] - 1) < 1e-14
     assert abs(T["coef"][4, 1] / k["psi_coeffs_first5"][4][0] - 1) < 1e-14
     assert abs(T["coef"][4, 2] / k["psi_coeffs_first5"][4][1] - 1) < 1e-14
+
+
+def test_symmetric_on_rows_outside_the_generated_set(nagata_H):
+    """Symmetries.jl:25-60 is a sign computation on the row: it answers for any (i,j,k,l) with i in 1:6, also rows
+    basisIndices never emits (family 1 with j != 0, l = 0 of the families that start at l = 1), and raises for i
+    outside 1:6 where a parity table is consulted."""
+    import pytest
+    from oracle.basis import symmetric as ref_sym
+    sx, sy, sz, tx, tz = ca.halfbox_symmetries()
+    rsx, rsy, rsz, rtx, rtz = __import__("oracle.basis", fromlist=["halfbox_symmetries"]).halfbox_symmetries()
+    gens = [(sx, rsx), (sy, rsy), (sz, rsz), (tx, rtx), (tz, rtz), (sx * sy * sz, rsx * rsy * rsz), (sz * tx * tz, rsz * rtx * rtz)]
+    for i in range(1, 7):
+        for j in (-2, -1, 0, 1, 3):
+            for k in (-3, 0, 1, 2):
+                for l in (0, 1, 2, 5):
+                    for mine, theirs in gens:
+                        assert ca.symmetric((i, j, k, l), mine) == ref_sym((i, j, k, l), theirs), (i, j, k, l)
+    assert ca.symmetric((9, 0, 0, 2), sy) == ref_sym((9, 0, 0, 2), rsy)      # no parity table consulted: no error
+    with pytest.raises(ca.CloudAtlasError, match="not in 1:6"):
+        ca.symmetric((9, 0, 0, 2), sx)

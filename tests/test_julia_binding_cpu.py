@@ -72,3 +72,22 @@ def test_every_ccall_matches_the_header():
             elif jt not in ok:
                 problems.append(f"{name}: argument {pos + 1} is {jt}, header has '{cp}'")
     assert not problems, "\n".join(problems)
+
+
+def test_model_struct_has_the_reference_fields_in_order():
+    """src/ODEModels.jl:6-20: struct ODEModel has the fields α, γ, H, ijkl, Ψ, B, A1, A2, N, Bfact, f, Df.  The binding's
+    B200Model must start with exactly these, in this order (positional construction and field access in the notebooks)."""
+    src = open(JL).read()
+    body = re.search(r"mutable struct B200Model\{[^}]*\}\n(.*?)\nend", src, flags=re.S).group(1)
+    fields = [re.match(r"\s*([^\s:#]+)::", line).group(1) for line in body.split("\n") if re.match(r"\s*[^\s:#]+::", line)]
+    assert fields[:12] == ["α", "γ", "H", "ijkl", "Ψ", "B", "A1", "A2", "N", "Bfact", "f", "Df"]
+    # N is callable and carries SparseBilinear's fields (src/SparseBilinear.jl:3-6)
+    nb = re.search(r"mutable struct B200Bilinear <: Function\n(.*?)\n    function", src, flags=re.S).group(1)
+    nfields = [re.match(r"\s*([a-z]+)::", line).group(1) for line in nb.split("\n") if re.match(r"\s*[a-z]+::", line)]
+    assert nfields[:3] == ["ijk", "val", "m"]
+    # the reference's entry points the notebooks call are all defined for the binding's types
+    for needle in ("function ODEModel(α::Float64, γ::Float64, J::Int, K::Int, L::Int, H::Vector{Symmetry}; normalize=false",
+                   "function hookstepsolve(model::B200Model, R::Real, xguess::Vector{Float64}, params=SearchParams())",
+                   "Base.length(model::B200Model)", "function derivative(N::B200Bilinear, x::Vector{Float64})",
+                   "function CloudAtlas.cnab2(", "ca_pin", "ca_assemble_sharded", "ca_comm_init_all"):
+        assert needle in src, needle
