@@ -368,7 +368,24 @@ n_copy_kernel(int m, int r0, int64_t npairs, const int64_t* __restrict__ coffs, 
 // conflict-free as [k-step][row][4]).  The dense result goes to a scratch slab and is compacted to the
 // reference's COO order.  This path exists for the FP64 roofline and as an independent check of the separable
 // path; it does ~2000x more arithmetic for the same numbers.
-constexpr int kDI = 128, kDJ = 8, kDK = 16, kDCols = kDJ * kDK, kDQ = 16, kDKc = 3 * kDQ, kDThreads = 512;
+constexpr int kDI = 128, kDK = 16;
+// Tile shape of the contraction: an output tile is 128 (i) x DJ * 16 (DJ values of j x 16 of k); a chunk is DQ grid
+// points (K = 3 DQ); one thread per (column, quarter of the chunk's k range), i.e. 4 * DJ * 16 threads.
+//   DenseWide   128 x 128 tile, 16 warps, one CTA per SM, chunks of 12 points
+//   DenseTwin   128 x  64 tile,  8 warps, TWO CTAs per SM, chunks of 8 points: while one CTA drains into its per-chunk
+//               barrier the other keeps the tensor pipe fed (the barrier tail was the last large stall of the wide shape)
+template <int DJ, int DQ>
+struct DenseCfgT {
+  static constexpr int J = DJ, Q = DQ, Cols = DJ * kDK, Kc = 3 * DQ, Threads = 4 * Cols, Warps = Threads / 32;
+  static constexpr int WC = Cols / 32;          // warps along the columns; Warps / WC = 4 along the rows
+  static constexpr int Bld = Cols + 4;          // row stride of the generated B block: the 4 k-rows of a fragment land 8 banks apart
+  static constexpr int KS = Kc / 4;             // k-steps per chunk = values of B each thread generates per chunk
+  static constexpr int CTAs = Threads <= 256 ? 2 : 1;
+  static constexpr size_t SmemDoubles = 2 * ((size_t)Kc * kDI + (size_t)Kc * Bld + DJ * DQ * 3 + kDK * DQ * 9);
+  static_assert(KS % 3 == 0, "a thread's k range must start on a grid point");
+};
+using DenseWide = DenseCfgT<8, 12>;
+using DenseTwin = DenseCfgT<4, 8>;
 
 struct DenseTables {
   int m, mpad, nq, nchunks;
@@ -379,6 +396,7 @@ struct DenseTables {
 };
 
 // one thread per (mode, grid point): fills U, G9 and the tiled A
+template <class Cfg>
 __global__ void dense_tables_kernel(DevBasis b, int mpad, int nxg, int nyg, int nzg, int nq,
                                     const double* __restrict__ Ex, const double* __restrict__ Exd,
                                     const double* __restrict__ Ez, const double* __restrict__ Ezd,
@@ -421,6 +439,7 @@ __global__ void dense_tables_kernel(DevBasis b, int mpad, int nxg, int nyg, int 
     }
     return;
   }
+  constexpr int kDJ = Cfg::J, kDQ = Cfg::Q, kDKc = Cfg::Kc;
   const int it = n / kDI, il = n % kDI, chunk = q / kDQ, ql = q % kDQ;
   for (int c = 0; c < 3; ++c)
     U[((((size_t)(n / kDJ) * nchunks + chunk) * kDQ + ql) * 3 + c) * kDJ + n % kDJ] = u[c];
@@ -437,29 +456,58 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 
-__global__ void __launch_bounds__(kDThreads, 1)
+// Software pipeline (round 2; round 1 generated B and multiplied in two barrier-separated phases with a 4-way
+// conflicted B store: DMMA pipe 74 % busy, 0.71 of peak).  Per chunk of kDQ = 12 grid points (K = 36, nine k-steps):
+//   * A(c), B(c) are consumed by the DMMA loop while every thread generates ITS nine values of B(c+1), one per k-step,
+//     from the tables of chunk c+1 -- generation (2.3 % of the flops) hides under the tensor work instead of stalling it;
+//   * cp.async brings A(c+1) and the tables of chunk c+2 during the same iteration;
+//   * ONE barrier per chunk publishes all three.
+// B is stored [k][kDBld] (row of 128 columns padded to 132 doubles): the generating warp writes 32 consecutive doubles
+// (conflict-free), and the four k-rows of a B fragment start 8 banks apart, so fragment loads are conflict-free too.
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::Threads, Cfg::CTAs)
 dense_contract_kernel(DenseTables T, int it0, int njt, double* __restrict__ Nd /* [rows][m][m] */, int row0, int row1) {
+  constexpr int kDJ = Cfg::J, kDQ = Cfg::Q, kDKc = Cfg::Kc, kDCols = Cfg::Cols, kDThreads = Cfg::Threads, kDBld = Cfg::Bld;
+  constexpr int KS = Cfg::KS;
   extern __shared__ __align__(16) double sm[];
-  double* Abuf = sm;                                  // [2][12*128*4]
-  double* Bbuf = Abuf + 2 * (kDKc * kDI);             // [12*128*4]
-  double* Utb = Bbuf + kDKc * kDCols;                 // [2][8][16][3]
-  double* Gtb = Utb + 2 * (kDJ * kDQ * 3);            // [2][16][16][9]
+  double* Abuf = sm;                                  // [2][9 k-steps][128 rows][4]
+  double* Bbuf = Abuf + 2 * (kDKc * kDI);             // [2][36 k][132]
+  double* Utb = Bbuf + 2 * (kDKc * kDBld);            // [2][12 q][3 a][8 modes]
+  double* Gtb = Utb + 2 * (kDJ * kDQ * 3);            // [2][12 q][9 (a*3+c)][16 modes]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = lane >> 2, c = lane & 3;
   const int it = it0 + blockIdx.y;
   const int jt = blockIdx.x % njt, kt = blockIdx.x / njt;
   const int j0 = jt * kDJ, k0 = kt * kDK;
-  const int wi = warp >> 2, wc = warp & 3;
+  const int wi = warp / Cfg::WC, wc = warp % Cfg::WC;
+  const int nchunks = T.nchunks;
 
-  auto stage = [&](int chunk, int buf) {
-    const double* src = T.A + ((size_t)it * T.nchunks + chunk) * (kDKc * kDI);
-    double* dst = Abuf + buf * (kDKc * kDI);
+  auto stage_A = [&](int chunk) {
+    const double* src = T.A + ((size_t)it * nchunks + chunk) * (kDKc * kDI);
+    double* dst = Abuf + (chunk & 1) * (kDKc * kDI);
     for (int e = tid; e < kDKc * kDI / 2; e += kDThreads) cp_async16(dst + 2 * e, src + 2 * e);
+  };
+  auto stage_tables = [&](int chunk) {
     // the (j-tile, chunk) block of U and the (k-tile, chunk) block of G9 are contiguous in global memory
-    const double* usrc = T.U + ((size_t)jt * T.nchunks + chunk) * (kDJ * kDQ * 3);
-    for (int e = tid; e < kDJ * kDQ * 3 / 2; e += kDThreads) cp_async16(Utb + buf * (kDJ * kDQ * 3) + 2 * e, usrc + 2 * e);
-    const double* gsrc = T.G9 + ((size_t)kt * T.nchunks + chunk) * (kDK * kDQ * 9);
-    for (int e = tid; e < kDK * kDQ * 9 / 2; e += kDThreads) cp_async16(Gtb + buf * (kDK * kDQ * 9) + 2 * e, gsrc + 2 * e);
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    const double* usrc = T.U + ((size_t)jt * nchunks + chunk) * (kDJ * kDQ * 3);
+    for (int e = tid; e < kDJ * kDQ * 3 / 2; e += kDThreads) cp_async16(Utb + (chunk & 1) * (kDJ * kDQ * 3) + 2 * e, usrc + 2 * e);
+    const double* gsrc = T.G9 + ((size_t)kt * nchunks + chunk) * (kDK * kDQ * 9);
+    for (int e = tid; e < kDK * kDQ * 9 / 2; e += kDThreads) cp_async16(Gtb + (chunk & 1) * (kDK * kDQ * 9) + 2 * e, gsrc + 2 * e);
+  };
+  // this thread's share of a B block: column col, k in [KS kg, KS kg + KS) = KS / 3 grid points, all three c
+  const int col = tid % kDCols, kg = tid / kDCols;
+  const int jj = col / kDK, kk = col % kDK;
+  // value `step` of chunk `chunk`: B[k = KS kg + step][col] = sum_a U[q][a][jj] * G9[q][a*3+cc][kk]
+  auto generate = [&](int chunk, int step, double& u0, double& u1, double& u2) {
+    const int q = kg * (KS / 3) + step / 3, cc = step % 3;
+    const double* u = Utb + (chunk & 1) * (kDJ * kDQ * 3) + jj;
+    const double* g = Gtb + (chunk & 1) * (kDK * kDQ * 9) + kk;
+    if (cc == 0) {
+      u0 = u[(q * 3) * kDJ];
+      u1 = u[(q * 3 + 1) * kDJ];
+      u2 = u[(q * 3 + 2) * kDJ];
+    }
+    const double v = u0 * g[(q * 9 + cc) * kDK] + u1 * g[(q * 9 + 3 + cc) * kDK] + u2 * g[(q * 9 + 6 + cc) * kDK];
+    Bbuf[(chunk & 1) * (kDKc * kDBld) + (kg * KS + step) * kDBld + col] = v;
   };
 
   double acc[4][4][2];
@@ -468,38 +516,39 @@ dense_contract_kernel(DenseTables T, int it0, int njt, double* __restrict__ Nd /
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-  stage(0, 0);
-  for (int chunk = 0; chunk < T.nchunks; ++chunk) {
-    const int buf = chunk & 1;
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
-    __syncthreads();  // chunk's A and tables have landed; everyone finished the previous chunk's DMMAs
-    if (chunk + 1 < T.nchunks) stage(chunk + 1, buf ^ 1);
-    {  // generate B[k = q*3 + c][col = jj*16 + kk] = sum_a U[jj][q][a] * G9[kk][q][a][c]
-      const int col = tid % kDCols, kg = tid / kDCols;  // kg 0..3 -> k in [12 kg, 12 kg + 12) = q in [4 kg, 4 kg + 4)
-      const int jj = col / kDK, kk = col % kDK;
-      const double* u = Utb + buf * (kDJ * kDQ * 3) + jj;   // [q][a][8 modes]
-      const double* g = Gtb + buf * (kDK * kDQ * 9) + kk;   // [q][a*3+c][16 modes]
+  // prologue: tables(0), A(0); B(0) generated in full; tables(1) in flight
+  stage_tables(0);
+  stage_A(0);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  __syncthreads();
+  if (nchunks > 1) stage_tables(1);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  {
+    double u0 = 0, u1 = 0, u2 = 0;
 #pragma unroll
-      for (int ql = 0; ql < 4; ++ql) {
-        const int q = kg * 4 + ql;
-        const double u0 = u[(q * 3) * kDJ], u1 = u[(q * 3 + 1) * kDJ], u2 = u[(q * 3 + 2) * kDJ];
+    for (int step = 0; step < KS; ++step) generate(0, step, u0, u1, u2);
+  }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  __syncthreads();
+
+  for (int chunk = 0; chunk < nchunks; ++chunk) {
+    // here: A(chunk), B(chunk) and the tables of chunk+1 are in shared memory and visible
+    if (chunk + 1 < nchunks) stage_A(chunk + 1);       // into the buffer A(chunk-1) has left
+    if (chunk + 2 < nchunks) stage_tables(chunk + 2);  // into the buffer the tables of `chunk` have left
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    const bool gen = chunk + 1 < nchunks;
+    const double* Ab = Abuf + (chunk & 1) * (kDKc * kDI);
+    const double* Bb = Bbuf + (chunk & 1) * (kDKc * kDBld);
+    double u0 = 0, u1 = 0, u2 = 0;
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) {
-          const double v = u0 * g[(q * 9 + cc) * kDK] + u1 * g[(q * 9 + 3 + cc) * kDK] + u2 * g[(q * 9 + 6 + cc) * kDK];
-          const int k = q * 3 + cc;
-          Bbuf[((k >> 2) * kDCols + col) * 4 + (k & 3)] = v;
-        }
-      }
-    }
-    __syncthreads();
-    const double* Ab = Abuf + buf * (kDKc * kDI);
-#pragma unroll 4
     for (int ks = 0; ks < kDKc / 4; ++ks) {
       double af[4], bf[4];
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) af[mt] = Ab[(ks * kDI + wi * 32 + mt * 8 + r) * 4 + c];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) bf[nt] = Bbuf[(ks * kDCols + wc * 32 + nt * 8 + r) * 4 + c];
+      for (int nt = 0; nt < 4; ++nt) bf[nt] = Bb[(ks * 4 + c) * kDBld + wc * 32 + nt * 8 + r];
+      if (gen) generate(chunk + 1, ks, u0, u1, u2);
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
@@ -509,6 +558,8 @@ dense_contract_kernel(DenseTables T, int it0, int njt, double* __restrict__ Nd /
                        : "d"(af[mt]), "d"(bf[nt]));
         }
     }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();  // A(chunk+1), tables(chunk+2), B(chunk+1) published; everyone is done with A(chunk), B(chunk)
   }
   // epilogue: N = -C into the dense slab
   const int m = T.m;
@@ -520,8 +571,8 @@ dense_contract_kernel(DenseTables T, int it0, int njt, double* __restrict__ Nd /
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int col = wc * 32 + nt * 8 + 2 * c + e;
-        const int j = j0 + col / kDK, k = k0 + col % kDK;
+        const int ocol = wc * 32 + nt * 8 + 2 * c + e;
+        const int j = j0 + ocol / kDK, k = k0 + ocol % kDK;
         if (j < m && k < m) Nd[((size_t)(i - row0) * m + j) * m + k] = -acc[mt][nt][e];
       }
   }
@@ -860,6 +911,8 @@ int32_t ca::assemble_slab(double alpha, double gamma, const int64_t* ijkl, int64
         const int nxg = dopt.nx > 0 ? dopt.nx : 3 * T.J + 1, nzg = dopt.nz > 0 ? dopt.nz : 3 * T.K + 1, nyg = T.ny;
         if (nxg <= 3 * T.J || nzg <= 3 * T.K)
           fail(CA_ERR_INVALID, "grid %d x %d x %d is not exact for J, K = %d, %d (need Nx > 3J, Nz > 3K)", nxg, nyg, nzg, T.J, T.K);
+        const bool twin = !(getenv("CA_DENSE_CFG") && getenv("CA_DENSE_CFG")[0] == 'W');  // W: the wide one-CTA-per-SM shape
+        const int kDQ = twin ? DenseTwin::Q : DenseWide::Q, kDJ = twin ? DenseTwin::J : DenseWide::J;
         const int nreal = nxg * nyg * nzg, nq = (nreal + kDQ - 1) / kDQ * kDQ, nchunks = nq / kDQ;
         const int mpad = (m + kDI - 1) / kDI * kDI;
         if ((double)rows * m * m * 8.0 > 100e9)
@@ -903,35 +956,48 @@ int32_t ca::assemble_slab(double alpha, double gamma, const int64_t* ijkl, int64
           DeviceBuffer<double> raw, mixed;
           raw.alloc((size_t)12 * nq * m);
           mixed.alloc((size_t)12 * nq * m);
-          dense_tables_kernel<<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr,
-                                                                      dezd.ptr, dF.ptr, T.ny, dwq.ptr, dU.ptr, dG9.ptr,
-                                                                      dA.ptr, nchunks, raw.ptr, nullptr);
+          if (twin)
+            dense_tables_kernel<DenseTwin><<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr, dezd.ptr, dF.ptr,
+                                                                                   T.ny, dwq.ptr, dU.ptr, dG9.ptr, dA.ptr, nchunks, raw.ptr, nullptr);
+          else
+            dense_tables_kernel<DenseWide><<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr, dezd.ptr, dF.ptr,
+                                                                                   T.ny, dwq.ptr, dU.ptr, dG9.ptr, dA.ptr, nchunks, raw.ptr, nullptr);
           CA_CUDA(cudaGetLastError());
           count_launch();
           launch_dgemm(12 * nq, m, m, 1.0, rowmajor(raw.ptr, m), colmajor(dmix.ptr, m), 0.0, mixed.ptr, m, 1, nullptr);
-          dense_tables_kernel<<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr,
-                                                                      dezd.ptr, dF.ptr, T.ny, dwq.ptr, dU.ptr, dG9.ptr,
-                                                                      dA.ptr, nchunks, nullptr, mixed.ptr);
+          if (twin)
+            dense_tables_kernel<DenseTwin><<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr, dezd.ptr, dF.ptr,
+                                                                                   T.ny, dwq.ptr, dU.ptr, dG9.ptr, dA.ptr, nchunks, nullptr, mixed.ptr);
+          else
+            dense_tables_kernel<DenseWide><<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr, dezd.ptr, dF.ptr,
+                                                                                   T.ny, dwq.ptr, dU.ptr, dG9.ptr, dA.ptr, nchunks, nullptr, mixed.ptr);
           CA_CUDA(cudaGetLastError());
           count_launch();
           CA_CUDA(cudaStreamSynchronize(nullptr));  // raw / mixed are released here
         } else {
-          dense_tables_kernel<<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr,
-                                                                      dezd.ptr, dF.ptr, T.ny, dwq.ptr, dU.ptr, dG9.ptr,
-                                                                      dA.ptr, nchunks, nullptr, nullptr);
+          if (twin)
+            dense_tables_kernel<DenseTwin><<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr, dezd.ptr, dF.ptr,
+                                                                                   T.ny, dwq.ptr, dU.ptr, dG9.ptr, dA.ptr, nchunks, nullptr, nullptr);
+          else
+            dense_tables_kernel<DenseWide><<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr, dezd.ptr, dF.ptr,
+                                                                                   T.ny, dwq.ptr, dU.ptr, dG9.ptr, dA.ptr, nchunks, nullptr, nullptr);
           CA_CUDA(cudaGetLastError());
           count_launch();
         }
         DenseTables DT{m, mpad, nq, nchunks, dU.ptr, dG9.ptr, dA.ptr};
         const int it0 = r0 / kDI, nit = (r1 + kDI - 1) / kDI - it0;
         const int njt = (m + kDJ - 1) / kDJ, nkt = (m + kDK - 1) / kDK;
-        const size_t smem = (size_t)(2 * kDKc * kDI + kDKc * kDCols + 2 * kDJ * kDQ * 3 + 2 * kDK * kDQ * 9) * sizeof(double);
-        CA_CUDA(cudaFuncSetAttribute(dense_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t smem = (twin ? DenseTwin::SmemDoubles : DenseWide::SmemDoubles) * sizeof(double);
+        CA_CUDA(cudaFuncSetAttribute(dense_contract_kernel<DenseTwin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DenseTwin::SmemDoubles * sizeof(double))));
+        CA_CUDA(cudaFuncSetAttribute(dense_contract_kernel<DenseWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DenseWide::SmemDoubles * sizeof(double))));
         cudaEvent_t c0, c1;
         CA_CUDA(cudaEventCreate(&c0));
         CA_CUDA(cudaEventCreate(&c1));
         CA_CUDA(cudaEventRecord(c0));
-        dense_contract_kernel<<<dim3((unsigned)(njt * nkt), (unsigned)nit), kDThreads, smem>>>(DT, it0, njt, Nd.ptr, r0, r1);
+        if (twin)
+          dense_contract_kernel<DenseTwin><<<dim3((unsigned)(njt * nkt), (unsigned)nit), DenseTwin::Threads, smem>>>(DT, it0, njt, Nd.ptr, r0, r1);
+        else
+          dense_contract_kernel<DenseWide><<<dim3((unsigned)(njt * nkt), (unsigned)nit), DenseWide::Threads, smem>>>(DT, it0, njt, Nd.ptr, r0, r1);
         CA_CUDA(cudaGetLastError());
         count_launch();
         CA_CUDA(cudaEventRecord(c1));

@@ -43,9 +43,11 @@ void DevicePack::upload_meta(const PackedHost& P) {
     sched_ks1[w] = P.sched_ks1[w];
   }
   stream_layout = P.stream_layout;
+  pair_order = P.pair_order;
   sched_imbalance = P.sched_imbalance;
   host_pairs = P.pairs;
   for (auto& b : pairs_mt) b.release();
+  pairs_win.release();
   rows.upload(P.rows.data(), P.rows.size());
   CA_CUDA(cudaStreamSynchronize(nullptr));  // the host vectors may die after we return
 }
@@ -66,6 +68,20 @@ const uint2* DevicePack::pairs_for(int mt) const {
     CA_CUDA(cudaStreamSynchronize(nullptr));
   }
   return buf.ptr;
+}
+
+const uint32_t* DevicePack::pairs_windowed() const {
+  if (!pairs_win.ptr && !host_pairs.empty()) {
+    std::vector<uint32_t> w(host_pairs.size() + 64, 0u);
+    for (size_t e = 0; e < host_pairs.size(); ++e) {
+      const int a = host_pairs[e] & 0x7fff, b = host_pairs[e] >> 16;
+      if (a >= 256 || b >= 256) fail(CA_ERR_UNSUPPORTED, "windowed pack with more than 256 modes per window");
+      w[e] = pack_window_pair(a, b, (host_pairs[e] & 0x8000u) != 0);
+    }
+    pairs_win.upload(w.data(), w.size());
+    CA_CUDA(cudaStreamSynchronize(nullptr));
+  }
+  return pairs_win.ptr;
 }
 
 namespace {
@@ -94,10 +110,10 @@ const LaunchCfg& device_cfg() {
 // whole tiles per warp when the packer's LPT schedule is balanced (no reduction, no per-tile barriers)
 constexpr double kMaxSchedImbalance = 1.08;
 
-template <int MT, int MODE>
+template <int MT, int MODE, bool FACT = false>
 void launch_warptile(const DevicePack& op, const double* dX, const double* dY, int64_t nstates, int64_t ldx,
                      double* dOUT, int64_t ldo, cudaStream_t stream) {
-  auto kern = bilinear_warptile_kernel<MT, MODE>;
+  auto kern = bilinear_warptile_kernel<MT, MODE, FACT>;
   const size_t smem = warptile_smem_bytes<MT, MODE>(op.nin);
   CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -122,7 +138,11 @@ template <int MT, int MODE>
 void launch_one(const DevicePack& op, const double* dX, const double* dY, int64_t nstates, int64_t ldx,
                 double* dOUT, int64_t ldo, cudaStream_t stream) {
   if (op.stream_layout && op.sched_imbalance <= kMaxSchedImbalance && !getenv("CA_FORCE_KSPLIT")) {
-    launch_warptile<MT, MODE>(op, dX, dY, nstates, ldx, dOUT, ldo, stream);
+    // packs in factored pair order: the quadratic evaluation needs no pair products (bilinear_kernels.cuh)
+    if (MODE == MODE_QUAD && op.symmetric && op.pair_order == kOrderFactored && !getenv("CA_NO_FACTORED"))
+      launch_warptile<MT, MODE_QUAD, true>(op, dX, dY, nstates, ldx, dOUT, ldo, stream);
+    else
+      launch_warptile<MT, MODE>(op, dX, dY, nstates, ldx, dOUT, ldo, stream);
     return;
   }
   auto kern = bilinear_batched_kernel<MT, MODE>;
@@ -198,7 +218,7 @@ void launch_windowed_nt(const DevicePack& op, const double* dX, const double* dY
   if (per_sm < 1) fail(CA_ERR_UNSUPPORTED, "windowed kernel does not fit (smem %zu B)", smem);
   const int64_t nblocks = (nstates + 8 * kWinMT - 1) / (8 * kWinMT);
   const int grid = (int)std::min<int64_t>(nblocks, (int64_t)device_cfg().sms * per_sm);
-  kern<<<grid, threads, smem, stream>>>(op.windows.ptr, op.nwin, op.nwin_nt3, op.nwin_nt2, op.modes.ptr, op.pairs_for(kWinMT),
+  kern<<<grid, threads, smem, stream>>>(op.windows.ptr, op.nwin, op.nwin_nt3, op.nwin_nt2, op.modes.ptr, op.pairs_windowed(),
                                         op.vals.ptr, op.rows.ptr, wmax, op.nin - 1, dX, dY, nstates, ldx, dOUT, ldo);
   CA_CUDA(cudaGetLastError());
   count_launch();

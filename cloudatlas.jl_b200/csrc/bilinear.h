@@ -19,12 +19,15 @@ struct DevicePack {
   std::vector<uint32_t> host_pairs;      // a | flag << 15 | b << 16 (pack.h), kept to derive the per-MT form
   mutable DeviceBuffer<uint2> pairs_mt[3];  // address-word form for MT = 1, 2, 4 (built on first use)
   const uint2* pairs_for(int mt) const;
+  mutable DeviceBuffer<uint32_t> pairs_win;  // packed one-word form of windowed packs (built on first use)
+  const uint32_t* pairs_windowed() const;
   DeviceBuffer<double> vals;
   DeviceBuffer<int32_t> rows;
   // whole-tile-per-warp schedule (pack.h)
   DeviceBuffer<int32_t> sched;
   int32_t sched_off[9] = {0}, sched_nt2[8] = {0}, sched_ks2[8] = {0}, sched_ks1[8] = {0};
   bool stream_layout = false;
+  int32_t pair_order = 0;  // pack.h: kOrderFactored lets the quadratic evaluation run without pair products
   double sched_imbalance = 1e9;
   // windowed packs (large m): pair words hold window-local rows
   int32_t window_modes = 0, nwin = 0, nwin_nt3 = 0, nwin_nt2 = 0, max_window_modes = 0;

@@ -54,6 +54,10 @@ __host__ __device__ __forceinline__ uint32_t factor_word(int mode) {
   return (uint32_t)mode * (64u * MT) | ((uint32_t)swz<MT>(mode) << 3);
 }
 constexpr uint32_t kSameA = 1u;
+// windowed packs: rows are window-local (< 256), so both address words of a pair fit 16 bits and a pair is one word
+__host__ __device__ __forceinline__ uint32_t pack_window_pair(int a_local, int b_local, bool same_a) {
+  return (factor_word<4>(a_local) | (same_a ? kSameA : 0u)) | (factor_word<4>(b_local) << 16);
+}
 
 template <int NT>
 struct Prefetch {
@@ -129,6 +133,43 @@ __device__ __forceinline__ void kstep(const uint2 pw, const double (&bv)[NT], co
   for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], bv[nt]);
+}
+
+// Factored quadratic evaluation on packs in kOrderFactored (pack.cpp: every k-step has ONE first factor a):
+//   out_i = sum_a x_a * ( sum_b V_iab x_b )
+// The DMMAs accumulate y = sum_b V x_b with the plain second factors as A fragments -- no pair products -- and at the
+// end of a run of equal a the run's result enters the tile's accumulators with one DFMA per accumulator register:
+// MT * NT * 2 DFMAs per run instead of MT DMULs per k-step (runs are ~9 k-steps at 307 modes).
+template <int MT, int NT>
+__device__ __forceinline__ void flush_run(const double (&xa)[MT], double (&y)[MT][NT][2], double (&acc)[MT][NT][2]) {
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        acc[mt][nt][e] = fma(xa[mt], y[mt][nt][e], acc[mt][nt][e]);  // accumulator row = state 8 mt + (lane >> 2), as xa
+        y[mt][nt][e] = 0.0;
+      }
+}
+
+template <int MT, int NT>
+__device__ __forceinline__ void kstep_factored(const uint2 pw, const double (&bv)[NT], const char* xs, uint32_t r8,
+                                               double (&xa)[MT], double (&y)[MT][NT][2], double (&acc)[MT][NT][2]) {
+  if (!(pw.x & kSameA)) {  // warp-uniform: a new run
+    flush_run<MT, NT>(xa, y, acc);
+    const uint32_t wa = (pw.x & ~7u) ^ r8;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) xa[mt] = lds_state<MT>(xs, wa, mt);
+  }
+  const uint32_t wb = pw.y ^ r8;
+  double a[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) a[mt] = lds_state<MT>(xs, wb, mt);
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) dmma884(y[mt][nt][0], y[mt][nt][1], a[mt], bv[nt]);
 }
 
 template <int MT, int NT, int MODE>
@@ -294,7 +335,7 @@ struct ValPrefetch {
   double bv[kPrefetch][NT];
 };
 
-template <int MT, int NT, int MODE>
+template <int MT, int NT, int MODE, bool FACT = false>
 __device__ __forceinline__ void tile_accumulate_ring(const double* __restrict__ vals0, int nks, const double* xs,
                                                      const double* ys, int lane, PairRing& pr, ValPrefetch<NT>& pf,
                                                      double (&acc)[MT][NT][2]) {
@@ -303,15 +344,24 @@ __device__ __forceinline__ void tile_accumulate_ring(const double* __restrict__ 
   const char* xsb = reinterpret_cast<const char*>(xs);
   const char* ysb = reinterpret_cast<const char*>(ys);
   double xa[MT], va[MT];
+  double y[MT][FACT ? NT : 1][2];  // FACT: the open run's sum_b V x_b
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt) xa[mt] = va[mt] = 0.0;
+  for (int mt = 0; mt < MT; ++mt) {
+    xa[mt] = va[mt] = 0.0;
+#pragma unroll
+    for (int nt = 0; nt < (FACT ? NT : 1); ++nt) y[mt][nt][0] = y[mt][nt][1] = 0.0;
+  }
+  auto one = [&](uint2 pw, const double (&bv)[NT]) {
+    if constexpr (FACT) kstep_factored<MT, NT>(pw, bv, xsb, r8, xa, y, acc);
+    else kstep<MT, NT, MODE>(pw, bv, xsb, ysb, r8, xa, va, acc);
+  };
   int i = 0;
   for (; i + kPrefetch <= nks; i += kPrefetch) {
 #pragma unroll
     for (int u = 0; u < kPrefetch; ++u) {
       uint2 pw = pr.next(lane);
       if (i + u == 0) pw.x &= ~kSameA;  // first k-step of a tile loads its first factors
-      kstep<MT, NT, MODE>(pw, pf.bv[u], xsb, ysb, r8, xa, va, acc);
+      one(pw, pf.bv[u]);
       prefetch_vals<NT>(pf.bv[u], vp, min(i + u + kPrefetch, nks - 1));
     }
   }
@@ -320,9 +370,10 @@ __device__ __forceinline__ void tile_accumulate_ring(const double* __restrict__ 
     if (i + u < nks) {
       uint2 pw = pr.next(lane);
       if (i + u == 0) pw.x &= ~kSameA;
-      kstep<MT, NT, MODE>(pw, pf.bv[u], xsb, ysb, r8, xa, va, acc);
+      one(pw, pf.bv[u]);
     }
   }
+  if constexpr (FACT) flush_run<MT, NT>(xa, y, acc);  // the tile's last run
 }
 
 
@@ -345,7 +396,7 @@ __device__ __forceinline__ void tile_store_direct(const TileDesc& T, const int32
     }
 }
 
-template <int MT, int NT, int MODE>
+template <int MT, int NT, int MODE, bool FACT = false>
 __device__ __forceinline__ void run_my_tiles(const TileDesc* __restrict__ tiles, const int32_t* __restrict__ sched,
                                              int b, int e, int total, const uint2* __restrict__ pairs,
                                              const double* __restrict__ vals, const int32_t* __restrict__ rows,
@@ -369,7 +420,7 @@ __device__ __forceinline__ void run_my_tiles(const TileDesc* __restrict__ tiles,
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-    tile_accumulate_ring<MT, NT, MODE>(vals + T.vals_off, T.nks, xs, ys, lane, pr, pf, acc);
+    tile_accumulate_ring<MT, NT, MODE, FACT>(vals + T.vals_off, T.nks, xs, ys, lane, pr, pf, acc);
     const TileDesc done = T;
     if (t + 1 < e) {
       T = tiles[__ldg(sched + t + 1)];
@@ -380,7 +431,7 @@ __device__ __forceinline__ void run_my_tiles(const TileDesc* __restrict__ tiles,
   pr.end();
 }
 
-template <int MT, int MODE>
+template <int MT, int MODE, bool FACT = false>
 __global__ void __launch_bounds__(kThreads, 2)
 bilinear_warptile_kernel(const TileDesc* __restrict__ tiles, const int32_t* __restrict__ sched, WarpSchedule ws,
                          const uint2* __restrict__ pairs, const double* __restrict__ vals,
@@ -413,8 +464,8 @@ bilinear_warptile_kernel(const TileDesc* __restrict__ tiles, const int32_t* __re
     }
     __syncthreads();
     const int b = ws.off[warp], mid = b + ws.nt2[warp], e = ws.off[warp + 1];
-    run_my_tiles<MT, 2, MODE>(tiles, sched, b, mid, ws.ks2[warp], pairs, vals, rows, xs, ys, ring, lane, s0, nstates, OUT, ldo);
-    run_my_tiles<MT, 1, MODE>(tiles, sched, mid, e, ws.ks1[warp], pairs, vals, rows, xs, ys, ring, lane, s0, nstates, OUT, ldo);
+    run_my_tiles<MT, 2, MODE, FACT>(tiles, sched, b, mid, ws.ks2[warp], pairs, vals, rows, xs, ys, ring, lane, s0, nstates, OUT, ldo);
+    run_my_tiles<MT, 1, MODE, FACT>(tiles, sched, mid, e, ws.ks1[warp], pairs, vals, rows, xs, ys, ring, lane, s0, nstates, OUT, ldo);
   }
 }
 
@@ -499,7 +550,7 @@ constexpr int kValRingBytes = 2 * kValSlotBytes;  // per warp
 
 struct WinSmem {
   double* bufs;      // [2][bufstride] state rows of the current / next window; a finished tile's reduction reuses the current one
-  uint2* pairs;      // [2][kWindowMaxKs * 4] pair words of the current / next window
+  uint32_t* pairs;   // [2][kWindowMaxKs * 4] packed pair words (first | second << 16) of the current / next window
   WindowDesc* desc;  // ring of kDescRing descriptors: windows g .. g+3
   int32_t* modes;    // [2][wpad] mode lists of windows g+1 / g+2
   char* vring;       // [NW][kValRingBytes] operator values, two batches per warp
@@ -528,7 +579,7 @@ __host__ __device__ inline size_t window_buf_doubles(int wmax) {
 template <int MODE, bool NT3 = false>
 __host__ __device__ inline size_t windowed_smem_bytes(int wmax) {
   const size_t wpad = ((size_t)wmax + 3) & ~(size_t)3;
-  return 2 * window_buf_doubles<MODE, NT3>(wmax) * sizeof(double) + (size_t)2 * kWindowMaxKs * 4 * sizeof(uint2) +
+  return 2 * window_buf_doubles<MODE, NT3>(wmax) * sizeof(double) + (size_t)2 * kWindowMaxKs * 4 * sizeof(uint32_t) +
          kDescRing * sizeof(WindowDesc) + 2 * wpad * sizeof(int32_t) + (size_t)WinCfg<MODE, NT3>::NW * kValRingBytes;
 }
 
@@ -539,7 +590,7 @@ __device__ __forceinline__ WinSmem carve_window_smem(double* smem, int wmax) {
   S.wpad = (wmax + 3) & ~3;
   S.bufstride = window_buf_doubles<MODE, NT3>(wmax);
   S.bufs = smem;
-  S.pairs = reinterpret_cast<uint2*>(smem + 2 * S.bufstride);
+  S.pairs = reinterpret_cast<uint32_t*>(smem + 2 * S.bufstride);
   S.desc = reinterpret_cast<WindowDesc*>(S.pairs + (size_t)2 * kWindowMaxKs * 4);
   S.modes = reinterpret_cast<int32_t*>(S.desc + kDescRing);
   S.vring = reinterpret_cast<char*>(S.modes + 2 * S.wpad);
@@ -549,7 +600,7 @@ __device__ __forceinline__ WinSmem carve_window_smem(double* smem, int wmax) {
 // Issued by the whole CTA right after the barrier of window g (g == -1: block prologue).
 template <int MODE, bool NT3 = false>
 __device__ __forceinline__ void stage_ahead(int g, int gtotal, const WindowDesc* __restrict__ windows,
-                                            const int32_t* __restrict__ modes, const uint2* __restrict__ pairs,
+                                            const int32_t* __restrict__ modes, const uint32_t* __restrict__ pairs,
                                             const WinSmem& S, int one_mode, const double* __restrict__ X,
                                             const double* __restrict__ Y, int64_t s0, int64_t nstates, int64_t ldx) {
   constexpr int ROW = 8 * kWinMT;
@@ -560,7 +611,7 @@ __device__ __forceinline__ void stage_ahead(int g, int gtotal, const WindowDesc*
     const int nks = W.nks, nmodes = W.nmodes;
     const char* psrc = reinterpret_cast<const char*>(pairs + (size_t)W.ks_begin * 4);
     char* pdst = reinterpret_cast<char*>(S.pairs + (size_t)((g + 1) & 1) * kWindowMaxKs * 4);
-    for (int c = tid; c < nks * 2; c += NTHR) cp_async16(pdst + c * 16, psrc + c * 16);
+    for (int c = tid; c < nks; c += NTHR) cp_async16(pdst + c * 16, psrc + c * 16);  // one k-step = 4 packed pairs = 16 B
     // one state row (32 states = 256 B) per warp instruction; the lane is the state
     const bool ok = s0 + lane < nstates;
     const double* xg = X + (ok ? s0 + lane : 0);
@@ -630,7 +681,7 @@ struct ValRing {
 
 // ps: the window's pair words in shared memory
 template <int MT, int NT, int MODE, bool NT3 = false>
-__device__ __forceinline__ void window_accumulate(const uint2* ps, int nks, const double* xs, const double* ys,
+__device__ __forceinline__ void window_accumulate(const uint32_t* ps, int nks, const double* xs, const double* ys,
                                                   int warp, int lane, const ValRing<NT, WinCfg<MODE, NT3>::NW>& vr,
                                                   double (&acc)[MT][NT][2]) {
   constexpr int KB = ValRing<NT, WinCfg<MODE, NT3>::NW>::KB;
@@ -639,7 +690,7 @@ __device__ __forceinline__ void window_accumulate(const uint2* ps, int nks, cons
   warp_share<WinCfg<MODE, NT3>::NW>(nks, warp, k0, k1);
   const int n = k1 - k0;
   if (n <= 0) return;
-  const uint2* pp = ps + (size_t)k0 * 4 + (lane & 3);
+  const uint32_t* pp = ps + (size_t)k0 * 4 + (lane & 3);
   const char* vb = vr.ring + lane * 8;
   const char* xsb = reinterpret_cast<const char*>(xs);
   const char* ysb = reinterpret_cast<const char*>(ys);
@@ -647,7 +698,8 @@ __device__ __forceinline__ void window_accumulate(const uint2* ps, int nks, cons
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) xa[mt] = va[mt] = 0.0;
   auto step = [&](int k, const char* slot, int kk) {
-    uint2 pw = pp[(size_t)k * 4];
+    const uint32_t packed = pp[(size_t)k * 4];  // window-local rows: both address words fit 16 bits (pack_window_pair)
+    uint2 pw = make_uint2(packed & 0xffffu, packed >> 16);
     if (k == 0) pw.x &= ~kSameA;  // the first k-step of a share always loads its first factors
     double bv[NT];
 #pragma unroll
@@ -676,7 +728,7 @@ __device__ __forceinline__ void window_accumulate(const uint2* ps, int nks, cons
 // windows [gb, ge) all belong to tiles with NT n-tiles; gtotal = number of windows of the operator
 template <int NT, int MODE, bool NT3 = false>
 __device__ __forceinline__ void run_windows(const WindowDesc* __restrict__ windows, int gb, int ge, int gtotal,
-                                            const int32_t* __restrict__ modes, const uint2* __restrict__ pairs,
+                                            const int32_t* __restrict__ modes, const uint32_t* __restrict__ pairs,
                                             const double* __restrict__ vals, const int32_t* __restrict__ rows,
                                             const WinSmem& S, int one_mode, int warp, int lane,
                                             const double* __restrict__ X, const double* __restrict__ Y, int64_t s0,
@@ -724,7 +776,7 @@ __device__ __forceinline__ void run_windows(const WindowDesc* __restrict__ windo
 template <int MODE, bool NT3>
 __global__ void __launch_bounds__(WinCfg<MODE, NT3>::NW * 32, WinCfg<MODE, NT3>::CTAS)
 bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, int nwin, int nwin_nt3, int nwin_nt2,
-                         const int32_t* __restrict__ modes, const uint2* __restrict__ pairs,
+                         const int32_t* __restrict__ modes, const uint32_t* __restrict__ pairs,
                          const double* __restrict__ vals, const int32_t* __restrict__ rows, int wmax, int one_mode,
                          const double* __restrict__ X, const double* __restrict__ Y, int64_t nstates, int64_t ldx,
                          double* __restrict__ OUT, int64_t ldo) {

@@ -58,6 +58,61 @@ void parallel_chunks(size_t n, size_t chunks, const std::function<void(size_t, s
   for (auto& th : pool) th.join();
 }
 
+namespace {
+bool use_pool() {
+  static const bool on = getenv("CA_NO_POOL") == nullptr;
+  return on;
+}
+// raise the release threshold of the current device's default pool once per device
+void prepare_pool(int dev) {
+  static std::atomic<unsigned long long> done{0};
+  if (dev < 64 && (done.load() >> dev) & 1ull) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;  // never hand freed blocks back to the driver on synchronisation
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  if (dev < 64) done.fetch_or(1ull << dev);
+}
+}  // namespace
+
+void* device_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (!use_pool()) {
+    CA_CUDA(cudaMalloc(&p, bytes));
+    return p;
+  }
+  int dev = 0;
+  CA_CUDA(cudaGetDevice(&dev));
+  prepare_pool(dev);
+  cudaError_t e = cudaMallocAsync(&p, bytes, nullptr);
+  if (e == cudaErrorMemoryAllocation) {  // the pool holds blocks that do not fit: give them back and retry once
+    cudaGetLastError();
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      cudaDeviceSynchronize();
+      cudaMemPoolTrimTo(pool, 0);
+    }
+    e = cudaMallocAsync(&p, bytes, nullptr);
+  }
+  if (e != cudaSuccess) fail(e == cudaErrorMemoryAllocation ? CA_ERR_NOMEM : CA_ERR_CUDA, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+  CA_CUDA(cudaStreamSynchronize(nullptr));  // the block is usable from every stream from here on
+  return p;
+}
+
+void device_free(void* ptr) {
+  if (!ptr) return;
+  if (!use_pool()) {
+    cudaFree(ptr);
+    return;
+  }
+  cudaDeviceSynchronize();  // cudaFree's guarantee: nothing on any stream still touches the block
+  if (cudaFreeAsync(ptr, nullptr) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(ptr);
+  }
+}
+
 void require_device() {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);

@@ -68,6 +68,14 @@ struct PhaseTimer {
 // Requires a CUDA device of compute capability 10.x; the library has no other code path.
 void require_device();
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with the release threshold raised, so
+// that the multi-gigabyte temporaries of assembly and model build are recycled inside the process: returning them to
+// the driver with cudaFree and asking again costs up to a second per build at m ~ 3000 (fresh pages are mapped and
+// scrubbed).  Frees keep cudaFree's semantics -- the device is synchronised first, because handles use non-blocking
+// streams that the pool's stream order (legacy stream) does not see.  CA_NO_POOL=1 restores cudaMalloc / cudaFree.
+void* device_alloc(size_t bytes);
+void device_free(void* ptr);
+
 template <typename T>
 struct DeviceBuffer {
   T* ptr = nullptr;
@@ -77,14 +85,14 @@ struct DeviceBuffer {
   DeviceBuffer& operator=(const DeviceBuffer&) = delete;
   ~DeviceBuffer() { release(); }
   void release() {
-    if (ptr) cudaFree(ptr);
+    if (ptr) device_free(ptr);
     ptr = nullptr;
     count = 0;
   }
   void alloc(size_t n) {
     release();
     if (n == 0) return;
-    CA_CUDA(cudaMalloc(&ptr, n * sizeof(T)));
+    ptr = static_cast<T*>(device_alloc(n * sizeof(T)));
     count = n;
   }
   void upload(const T* host, size_t n, cudaStream_t s = nullptr) {

@@ -966,7 +966,8 @@ bool build_model_on_device(ca_model* h, const double* dB, const double* dA1, con
   std::vector<PackedHost> parts((size_t)ntiles);
   std::vector<int32_t> h_where((size_t)total_t);
   {
-    const bool blocked = pack_blocked_order(window_modes);
+    const int order = pack_pair_order(window_modes);
+    P.pair_order = order;
     parallel_chunks((size_t)ntiles, (size_t)ntiles, [&](size_t b0, size_t b1, size_t) {
       std::vector<uint64_t> U;
       std::vector<int32_t> where;
@@ -974,7 +975,7 @@ bool build_model_on_device(ca_model* h, const double* dB, const double* dA1, con
         const int64_t n = t_off[t + 1] - t_off[t];
         U.resize((size_t)n);
         for (int64_t q = 0; q < n; ++q) U[(size_t)q] = h_tkeys[(size_t)(t_off[t] + q)];
-        layout_tile(tile_rows[t], U.data(), U.size(), nin, window_modes, blocked, parts[t], where);
+        layout_tile(tile_rows[t], U.data(), U.size(), nin, window_modes, order, parts[t], where);
         std::copy(where.begin(), where.end(), h_where.begin() + (ptrdiff_t)t_off[t]);
       }
     });

@@ -352,7 +352,8 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
   }
   // ---- split clusters into tiles of <= 8*nt_max rows, lay out fragments
   // (tiles are laid out independently on worker threads, each into its own container, and appended in order)
-  const bool blocked = pack_blocked_order(window_modes);
+  const int order = pack_pair_order(window_modes);
+  P.pair_order = order;
   const std::vector<std::vector<int32_t>> tile_rows = split_clusters(clusters, nt_max);
   std::vector<PackedHost> parts(tile_rows.size());
   parallel_chunks(tile_rows.size(), tile_rows.size(), [&](size_t b, size_t e, size_t) {
@@ -362,7 +363,7 @@ PackedHost pack_terms(std::vector<Term> terms, int32_t m, bool symmetric, int nt
       std::vector<uint64_t> U;
       for (int32_t r : trows) U = U.empty() ? rows[r].keys : union_of(U, rows[r].keys);
       std::vector<int32_t> where;
-      layout_tile(trows, U.data(), U.size(), nin, window_modes, blocked, Q, where);
+      layout_tile(trows, U.data(), U.size(), nin, window_modes, order, Q, where);
       const TileDesc& T = Q.tiles[0];
       Q.vals.assign((size_t)Q.vals_count, 0.0);
       double* V = Q.vals.data();
@@ -422,16 +423,27 @@ std::vector<std::vector<int32_t>> split_clusters(const std::vector<std::vector<i
   return tile_rows;
 }
 
-// Blocked pair order (see layout_tile) for whole-tile packs: +1 % on the 307-mode ensemble kernel (67.9 -> 67.2 ms).
-// Windowed packs keep the a-major order: blocks make windows of fewer k-steps (147 instead of 197 at m = 999), and
-// the per-window barrier and the shorter per-warp shares cost more than the saved shared-memory wavefronts bring
-// (m = 999: RHS 13.8 vs 13.3 ms, JVP 19.7 vs 18.3 ms).  CA_PACK_AMAJOR / CA_PACK_BLOCKED force either.
-bool pack_blocked_order(int window_modes) {
-  return getenv("CA_PACK_BLOCKED") != nullptr || (window_modes <= 0 && getenv("CA_PACK_AMAJOR") == nullptr);
+// Order of the pairs inside a tile (see layout_tile):
+//   kOrderAMajor    runs of equal first factor, four consecutive pairs per k-step (windowed packs: blocks make windows
+//                   of fewer k-steps, and the per-window costs outweigh the saved shared-memory wavefronts)
+//   kOrderBlocked   (4 first factors) x (one second factor) k-steps where the second-factor lists coincide
+//   kOrderFactored  a-major with every run padded to whole k-steps, so that a k-step has ONE first factor: the
+//                   quadratic evaluation can then run as  out_i += x_a * (sum_b V_iab x_b)  without pair products
+//                   (bilinear_warptile_kernel<.., FACT>).  Measured at 307 modes (round 2): the runs are only ~4 k-steps
+//                   long, so the per-run DFMAs cost what the DMULs did, and the padding adds 8.7 % DMMAs: 80.7 ms
+//                   against 67.3 ms for the blocked order.  Kept as an option, not the default.
+// Default: blocked for whole-tile packs, a-major for windowed ones.  CA_PACK_AMAJOR / CA_PACK_BLOCKED /
+// CA_PACK_FACTORED force one.
+int pack_pair_order(int window_modes) {
+  if (getenv("CA_PACK_BLOCKED")) return kOrderBlocked;
+  if (getenv("CA_PACK_AMAJOR")) return kOrderAMajor;
+  if (getenv("CA_PACK_FACTORED") && getenv("CA_PACK_FACTORED")[0] != '0') return kOrderFactored;
+  return window_modes <= 0 ? kOrderBlocked : kOrderAMajor;
 }
 
 void layout_tile(const std::vector<int32_t>& trows, const uint64_t* U_ptr, size_t nU, int32_t nin, int window_modes,
-                 bool blocked, PackedHost& P, std::vector<int32_t>& where_out) {
+                 int order, PackedHost& P, std::vector<int32_t>& where_out) {
+  const bool blocked = order == kOrderBlocked, factored = order == kOrderFactored && window_modes <= 0;
   struct USpan {  // read-only view with the vector interface the layout code uses
     const uint64_t* p;
     size_t n;
@@ -553,13 +565,16 @@ void layout_tile(const std::vector<int32_t>& trows, const uint64_t* U_ptr, size_
       }
     };
     if (window_modes <= 0) {
-      T.nks = (T.npairs + 3) / 4;
       int k = 0;
-      for (const Seg& sg : segs)
+      for (const Seg& sg : segs) {
         for (size_t at : sg.idx) {
           where[at] = k++;
           P.pairs.push_back((uint32_t)(U[at] / nin) | ((uint32_t)(U[at] % nin) << 16));
         }
+        if (factored && !sg.idx.empty())  // whole k-steps per first factor; the padding pairs (a, ONE) carry zero values
+          for (const uint32_t a = (uint32_t)(U[sg.idx[0]] / nin); k % 4 != 0; ++k) P.pairs.push_back(a | (ONE << 16));
+      }
+      T.nks = (k + 3) / 4;
       for (; k < 4 * T.nks; ++k) P.pairs.push_back(ONE | (ONE << 16));
       mark_same_a(0, T.nks);
     } else {

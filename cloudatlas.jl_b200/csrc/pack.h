@@ -48,7 +48,7 @@ struct alignas(16) WindowDesc {
   int64_t pad_;
 };
 static_assert(sizeof(WindowDesc) == 48, "the windowed kernel copies descriptors as three 16-byte words");
-constexpr int kWindowMaxKs = 224;  // k-steps per window (the kernel stages a window's pair words in shared memory)
+constexpr int kWindowMaxKs = 448;  // k-steps per window (the kernel stages a window's pair words, 4 B per pair, in shared memory)
 
 struct PackedHost {
   int32_t m = 0;    // outputs
@@ -79,6 +79,7 @@ struct PackedHost {
   int64_t padded_fma = 0;       // FMAs the tiles execute per state (incl. padding)
   int64_t pair_products = 0;    // pair products formed per state (sum over tiles)
   int64_t blocked_pairs = 0;    // of these, in (4 first factors) x (one second factor) k-steps
+  int32_t pair_order = 0;       // kOrderAMajor / kOrderBlocked / kOrderFactored (pack_pair_order)
   int64_t vals_count = 0;       // value slots ([k-step][n-tile][lane]); == vals.size() when the values are held here
 };
 
@@ -118,8 +119,9 @@ std::vector<std::vector<int32_t>> split_clusters(const std::vector<std::vector<i
 // empty) the tile descriptor, its rows, pair words, windows and window mode lists -- everything but the values -- and
 // where[q] = position of U[q] in the emitted (padded) pair sequence.  P.vals_count is the number of value slots.
 void layout_tile(const std::vector<int32_t>& trows, const uint64_t* U, size_t nU, int32_t nin, int window_modes,
-                 bool blocked, PackedHost& P, std::vector<int32_t>& where);
-bool pack_blocked_order(int window_modes);
+                 int order, PackedHost& P, std::vector<int32_t>& where);
+enum : int { kOrderAMajor = 0, kOrderBlocked = 1, kOrderFactored = 2 };
+int pack_pair_order(int window_modes);
 // Appends the per-tile parts (in order), adds the empty-row tiles, sorts tiles and windows, builds the warp schedule and
 // (whole-tile packs) the schedule-order layout.  When the parts carry values they are moved along; otherwise only the
 // offsets are computed (vals_count / TileDesc::vals_off) and the caller places the values itself.
