@@ -15,7 +15,7 @@ from .ascio import basis_index_dict, changebasis, ijkl2file, load, save  # noqa:
 from .continuation import natural_continuation, newton_krylov, pseudo_arclength_continuation  # noqa: F401
 from .hookstep import Df_finitediff, SearchParams, hookstepsolve, hookstepsolve_model  # noqa: F401
 from .assembly import (AssemblySlab, LibraryComm, all_gather_slabs, assemble, assemble_device, assemble_full,  # noqa: F401
-                       assemble_sharded, row_partition)  # noqa: F401
+                       assemble_sharded, library_comm_for, row_partition)  # noqa: F401
 from .basis import Symmetry, basisComponents, shearVector, basisIndices, halfbox_symmetries, symmetric  # noqa: F401
 
 

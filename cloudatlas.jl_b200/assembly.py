@@ -249,6 +249,14 @@ def all_gather_slabs(lin, idx, val, m, group=None):
     return lin_all, idx_all, val_all
 
 
+def library_comm_for(group=None):
+    """The library communicator (``LibraryComm``) that mirrors a torch.distributed group; created on first use."""
+    key = id(group)
+    if key not in _group_comms:
+        _group_comms[key] = LibraryComm.from_torch_group(group)
+    return _group_comms[key]
+
+
 def assemble_full(alpha, gamma, ijkl, normalize=False, group=None, distributed=None, dense=False, grid=(0, 0, 0),
                   mode_scale=None):
     """(assembly, stats): the full operator as an ``AssemblySlab`` on this process's device.  Single process: one
@@ -262,10 +270,7 @@ def assemble_full(alpha, gamma, ijkl, normalize=False, group=None, distributed=N
         slab = AssemblySlab(alpha, gamma, ijkl, normalize, dense=dense, grid=grid, mode_scale=mode_scale)
         return slab, {"world": 1, "gather_seconds": 0.0, "gather_bytes": 0, "device_seconds": slab.device_seconds,
                       "nnz": slab.nnz, "dense": slab.dense_info() if dense else None}
-    key = id(group)
-    if key not in _group_comms:
-        _group_comms[key] = LibraryComm.from_torch_group(group)
-    slab = assemble_sharded(_group_comms[key], alpha, gamma, ijkl, normalize, mode_scale, dense, grid)[0]
+    slab = assemble_sharded(library_comm_for(group), alpha, gamma, ijkl, normalize, mode_scale, dense, grid)[0]
     st = slab.gather_info()
     st.update(device_seconds=slab.device_seconds, nnz=slab.nnz, dense=slab.dense_info() if dense else None)
     return slab, st

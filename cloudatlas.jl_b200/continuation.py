@@ -11,8 +11,11 @@ Both record the wall shear rate (the notebooks' ordinate) when the model has obs
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
+from ._lib import CloudAtlasError, _sig, c_f64p, check, vp
 from .hookstep import SearchParams, hookstepsolve_model
 
 
@@ -101,75 +104,44 @@ def pseudo_arclength_continuation(model, x0, R0, ds=1.0, nsteps=50, R_min=-np.in
     return out
 
 
-def newton_krylov(model, R, x0, ftol=1e-10, max_newton=30, gmres_rtol=1e-8, restart=60, max_restarts=5, verbose=False):
-    """Matrix-free Newton-GMRES for f(x,R) = 0 (BASELINE.json configs[4]: Jacobian actions for Newton-Krylov at
-    m ~ 3000, where the dense m x m Jacobian and its LU are what dominate the reference's hookstep).  Every Krylov
-    vector costs ONE matrix-free Jacobian action  Df(x,R) v = (L1 + L2/R) v + Q(x,v) + Q(v,x)  on the device
-    (``ca_model_jvp_batched_dev``: the HBM-bound streaming kernel, 0.38 ms at m = 2962); the Arnoldi process runs on
-    device tensors.  Backtracking line search on |f|.  Returns (x, converged, info)."""
-    import torch
-    dev = torch.device("cuda")
-    x = torch.as_tensor(np.asarray(x0, dtype=np.float64), device=dev).reshape(1, -1)
-    m = x.shape[1]
+class _KrylovParams(C.Structure):
+    _fields_ = [("ftol", C.c_double), ("gmres_rtol", C.c_double), ("max_newton", C.c_int32), ("restart", C.c_int32),
+                ("max_restarts", C.c_int32), ("verbosity", C.c_int32), ("precondition", C.c_int32)]
 
-    def f(xx):
-        return model.f(xx, R).reshape(-1)
 
-    def jv(xx, v):
-        return model.Df_action(xx, v.reshape(1, -1), R).reshape(-1)
+class _KrylovInfo(C.Structure):
+    _fields_ = [("converged", C.c_int32), ("newton_steps", C.c_int32), ("jvps", C.c_int32), ("f_evals", C.c_int32),
+                ("world", C.c_int32), ("final_residual", C.c_double), ("device_seconds", C.c_double),
+                ("residual", C.c_double * 64)]
 
-    info = {"newton_steps": 0, "jvps": 0, "residuals": []}
-    fx = f(x)
-    for _ in range(max_newton):
-        nf = float(torch.linalg.norm(fx))
-        info["residuals"].append(nf)
-        if nf <= ftol:
-            return x.reshape(-1).cpu().numpy(), True, info
-        # ---- restarted GMRES for Df dx = -fx
-        dx = torch.zeros(m, dtype=torch.float64, device=dev)
-        b = -fx
-        for _r in range(max_restarts):
-            r0 = b - (jv(x, dx) if _r > 0 else 0)
-            beta = float(torch.linalg.norm(r0))
-            if beta <= gmres_rtol * nf:
-                break
-            V = torch.zeros((restart + 1, m), dtype=torch.float64, device=dev)
-            Hm = np.zeros((restart + 1, restart))
-            V[0] = r0 / beta
-            k_used = 0
-            for k in range(restart):
-                w = jv(x, V[k])
-                info["jvps"] += 1
-                h = V[:k + 1] @ w                       # classical Gram-Schmidt, twice (stable enough, two GEMVs)
-                w = w - h @ V[:k + 1]
-                h2 = V[:k + 1] @ w
-                w = w - h2 @ V[:k + 1]
-                Hm[:k + 1, k] = (h + h2).cpu().numpy()
-                hn = float(torch.linalg.norm(w))
-                Hm[k + 1, k] = hn
-                k_used = k + 1
-                e1 = np.zeros(k + 2)
-                e1[0] = beta
-                y, res, *_ = np.linalg.lstsq(Hm[:k + 2, :k + 1], e1, rcond=None)
-                rnorm = np.linalg.norm(Hm[:k + 2, :k + 1] @ y - e1)
-                if hn == 0.0 or rnorm <= gmres_rtol * nf:
-                    break
-                V[k + 1] = w / hn
-            dx = dx + torch.as_tensor(y, device=dev) @ V[:k_used]
-            if rnorm <= gmres_rtol * nf:
-                break
-        # ---- backtracking
-        lam = 1.0
-        while True:
-            xt = x + lam * dx.reshape(1, -1)
-            ft = f(xt)
-            if float(torch.linalg.norm(ft)) < (1 - 1e-4 * lam) * nf or lam < 1e-4:
-                break
-            lam *= 0.5
-        x, fx = xt, ft
-        info["newton_steps"] += 1
-        if verbose:
-            print(f"newton {info['newton_steps']}: |f| = {float(torch.linalg.norm(fx)):.3e}, lambda = {lam}, jvps = {info['jvps']}")
-    nf = float(torch.linalg.norm(fx))
-    info["residuals"].append(nf)
-    return x.reshape(-1).cpu().numpy(), nf <= ftol, info
+
+_newton_krylov = _sig("ca_newton_krylov", C.POINTER(vp), C.c_int32, vp, C.c_double, c_f64p, C.POINTER(_KrylovParams), c_f64p,
+                      C.POINTER(C.c_int32), C.POINTER(_KrylovInfo))
+
+
+def newton_krylov(model, R, x0, ftol=1e-10, max_newton=30, gmres_rtol=1e-8, restart=60, max_restarts=5, verbose=False,
+                  comm=None, precondition=True):
+    """Matrix-free Newton-GMRES for f(x,R) = 0 inside the library (``ca_newton_krylov``, csrc/newton_krylov.cu;
+    BASELINE.json configs[4]: Jacobian actions for Newton-Krylov at m ~ 3000, where the dense m x m Jacobian and its LU
+    are what dominate the reference's hookstep).  Every Krylov vector costs ONE Jacobian action
+    Df(x,R) v = (L1 + L2/R) v + Q(x,v) + Q(v,x)  by the HBM-bound streaming kernel; Arnoldi vectors, orthogonalisation
+    and line search stay on the device.  ``model``: one model, or a list of replicas of one model on the local devices
+    of ``comm`` (a ``LibraryComm``): the Jacobian action is then sharded by row slab over the communicator's ranks with
+    one all-gather of m doubles per Krylov step.  ``precondition``: GMRES on M^-1 Df with M = L1 + L2/R factored once
+    per solve on the device (needed beyond ~100 modes).  Returns (x, converged, info)."""
+    models = list(model) if isinstance(model, (list, tuple)) else [model]
+    m = models[0].m
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    if x0.shape != (m,):
+        raise CloudAtlasError(1, f"x0 has shape {x0.shape}, expected ({m},)")
+    handles = (vp * len(models))(*[mm._h for mm in models])
+    p = _KrylovParams(ftol, gmres_rtol, max_newton, restart, max_restarts, int(bool(verbose)), int(bool(precondition)))
+    info = _KrylovInfo()
+    out = np.empty(m)
+    ok = C.c_int32(0)
+    check(_newton_krylov(handles, len(models), None if comm is None else comm._h, float(R), x0.ctypes.data_as(c_f64p),
+                         C.byref(p), out.ctypes.data_as(c_f64p), C.byref(ok), C.byref(info)))
+    n = min(info.newton_steps + 1, 64)
+    return out, bool(ok.value), {"newton_steps": info.newton_steps, "jvps": info.jvps, "f_evals": info.f_evals,
+                                 "world": info.world, "final_residual": info.final_residual,
+                                 "device_seconds": info.device_seconds, "residuals": list(info.residual[:n])}

@@ -84,6 +84,7 @@ struct StreamPack {
   DeviceBuffer<double> val;
   DeviceBuffer<StreamChunk> chunks;
   DeviceBuffer<int32_t> row_chunk_ptr;  // [m+1]
+  std::vector<int32_t> h_row_chunk_ptr;  // host copy: a row range of the operator is a contiguous range of chunks
   // [nchunks][8] chunk partials, one buffer per CUDA stream that evaluates this operator
   mutable std::map<cudaStream_t, std::unique_ptr<DeviceBuffer<double>>> partials;
   double* partial_for(cudaStream_t st) const;
@@ -95,9 +96,11 @@ struct StreamPack {
              const std::vector<int64_t>& row_end, int32_t m, bool symmetric);
 };
 // Optional dense linear part (row-major L1r, L2r, value L1 + L2*invR), may be null.
+// row_begin / row_end: only the output rows [row_begin, row_end) are evaluated and written (row_end < 0: all rows) --
+// the row-slab sharding of a single-state Jacobian action over several GPUs streams 1/N of the operator per device.
 void launch_stream(const StreamPack& sp, int mode, const double* dX, const double* dY, int64_t nstates,
                    int64_t ldx, double* dOUT, int64_t ldo, const double* L1r, const double* L2r, double invR,
-                   cudaStream_t stream);
+                   cudaStream_t stream, int row_begin = 0, int row_end = -1);
 
 // Sliced-ELL structure of the Jacobian  DN[i,j] = sum_k M[(i,j),k] x_k  (SparseBilinear.jl:75-91).
 struct JacobianPack {

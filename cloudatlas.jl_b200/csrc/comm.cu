@@ -15,7 +15,6 @@
 // per device, no padding to the largest slab, no staging, no concatenation pass.  Rank order reproduces the reference's
 // lexicographic (i,j,k) order (SparseBilinear.jl:24-49) because ranks own increasing ranges of i.
 #include <dlfcn.h>
-#include <nccl.h>
 
 #include <algorithm>
 #include <memory>
@@ -24,25 +23,12 @@
 #include <vector>
 
 #include "assembly.h"
+#include "comm.h"
 #include "model.h"
 
 using namespace ca;
 
-namespace {
-
-struct NcclApi {
-  void* handle = nullptr;
-  ncclResult_t (*GetVersion)(int*) = nullptr;
-  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
-  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*GroupStart)() = nullptr;
-  ncclResult_t (*GroupEnd)() = nullptr;
-  const char* (*GetErrorString)(ncclResult_t) = nullptr;
-};
+namespace ca {
 
 const NcclApi& nccl() {
   static NcclApi api;
@@ -78,29 +64,15 @@ const NcclApi& nccl() {
   return api;
 }
 
-#define CA_NCCL(expr)                                                                                       \
-  do {                                                                                                      \
-    ncclResult_t r__ = (expr);                                                                              \
-    if (r__ != ncclSuccess)                                                                                 \
-      ::ca::fail(CA_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, nccl().GetErrorString(r__)); \
-  } while (0)
+}  // namespace ca
 
-}  // namespace
-
-struct ca_comm {
-  int nranks = 0;
-  std::vector<int> devices;  // local devices, one communicator each
-  std::vector<int> ranks;    // their ranks
-  std::vector<ncclComm_t> comms;
-  std::vector<cudaStream_t> streams;
-  ~ca_comm() {
-    for (size_t d = 0; d < comms.size(); ++d) {
-      cudaSetDevice(devices[d]);
-      if (comms[d] && nccl().CommDestroy) nccl().CommDestroy(comms[d]);
-      if (streams[d]) cudaStreamDestroy(streams[d]);
-    }
+ca_comm::~ca_comm() {
+  for (size_t d = 0; d < comms.size(); ++d) {
+    cudaSetDevice(devices[d]);
+    if (comms[d] && nccl().CommDestroy) nccl().CommDestroy(comms[d]);
+    if (streams[d]) cudaStreamDestroy(streams[d]);
   }
-};
+}
 
 namespace {
 
@@ -147,6 +119,8 @@ void for_each_device(const ca_comm& c, const std::function<void(size_t)>& fn) {
 }
 
 }  // namespace
+
+ca_comm* default_comm() { return g_default_comm.get(); }
 
 extern "C" {
 

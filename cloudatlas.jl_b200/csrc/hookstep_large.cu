@@ -19,203 +19,13 @@
 
 #include "bilinear.h"
 #include "bilinear_kernels.cuh"
+#include "dense_lu.cuh"
 #include "dgemm.cuh"
 #include "model.h"
 
 using namespace ca;
 
 namespace {
-
-constexpr int kLuNb = 16;         // panel width of the blocked LU
-constexpr int kLuThreads = 1024;  // the panel and the substitution kernels are single-CTA
-constexpr int kSolveNb = 32;      // block size of the triangular substitutions
-
-// ---- panel factorisation: columns [k0, k0+nb) of rows [k0, m), partial pivoting, unit lower factor stored in place
-__global__ void __launch_bounds__(kLuThreads)
-lu_panel_kernel(double* __restrict__ A, int64_t ld, int m, int k0, int nb, int32_t* __restrict__ piv,
-                int32_t* __restrict__ singular, int pivoting) {
-  __shared__ double red_val[32];
-  __shared__ int red_idx[32];
-  __shared__ double prow[kLuNb];
-  __shared__ int psel;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int c = 0; c < nb; ++c) {
-    const int col = k0 + c;
-    if (col >= m) break;
-    double* Ac = A + ld * col;
-    // pivot: first row of maximal magnitude at or below the diagonal
-    double best = -1.0;
-    int bi = col;
-    if (pivoting) {
-      for (int r = col + tid; r < m; r += kLuThreads) {
-        const double v = fabs(Ac[r]);
-        if (v > best) { best = v; bi = r; }
-      }
-#pragma unroll
-      for (int d = 16; d >= 1; d >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, best, d);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-      }
-      if (lane == 0) { red_val[warp] = best; red_idx[warp] = bi; }
-      __syncthreads();
-      if (warp == 0) {
-        best = red_val[lane];
-        bi = red_idx[lane];
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-          const double ov = __shfl_xor_sync(0xffffffffu, best, d);
-          const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
-          if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        if (lane == 0) psel = bi;
-      }
-      __syncthreads();
-    } else if (tid == 0) {
-      psel = col;
-    }
-    if (!pivoting) __syncthreads();
-    const int p = psel;
-    if (tid == 0) piv[col] = p;
-    // swap rows col and p inside the panel, cache the pivot row
-    if (tid < nb) {
-      double* a = A + ld * (k0 + tid);
-      const double up = a[p];
-      if (p != col) {
-        a[p] = a[col];
-        a[col] = up;
-      }
-      prow[tid] = up;
-    }
-    __syncthreads();
-    const double pv = prow[c];
-    if (pv == 0.0) {
-      if (tid == 0) *singular = 1;
-      continue;  // (uniform: every thread reads the same pivot)
-    }
-    const int ncols = min(nb, m - k0);
-    for (int r = col + 1 + tid; r < m; r += kLuThreads) {
-      const double l = Ac[r] / pv;
-      Ac[r] = l;
-      for (int j = c + 1; j < ncols; ++j) A[ld * (k0 + j) + r] -= l * prow[j];
-    }
-    __syncthreads();
-  }
-}
-
-// row interchanges of the panel applied to the columns outside it
-__global__ void lu_swap_kernel(double* __restrict__ A, int64_t ld, int m, int k0, int nb, const int32_t* __restrict__ piv) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= m - nb) return;
-  if (j >= k0) j += nb;  // skip the panel's own columns
-  double* a = A + ld * j;
-  for (int c = 0; c < nb && k0 + c < m; ++c) {
-    const int p = piv[k0 + c];
-    if (p != k0 + c) {
-      const double t = a[k0 + c];
-      a[k0 + c] = a[p];
-      a[p] = t;
-    }
-  }
-}
-
-// block row of U: A12 <- L11^-1 A12 (unit lower L11), one thread per column right of the panel
-__global__ void lu_trsm_kernel(double* __restrict__ A, int64_t ld, int m, int k0, int nb) {
-  __shared__ double L[kLuNb][kLuNb + 1];
-  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) L[e % nb][e / nb] = A[ld * (k0 + e / nb) + k0 + e % nb];
-  __syncthreads();
-  const int j = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= m) return;
-  double* a = A + ld * j + k0;
-  double x[kLuNb];
-#pragma unroll
-  for (int r = 0; r < kLuNb; ++r) x[r] = r < nb ? a[r] : 0.0;
-#pragma unroll
-  for (int c = 0; c < kLuNb; ++c)
-#pragma unroll
-    for (int r = c + 1; r < kLuNb; ++r)
-      if (r < nb) x[r] -= L[r][c] * x[c];
-#pragma unroll
-  for (int r = 0; r < kLuNb; ++r)
-    if (r < nb) a[r] = x[r];
-}
-
-// b <- U^-1 L^-1 P b, blocked substitutions by one CTA (the vectors are L2-resident)
-__global__ void __launch_bounds__(kLuThreads)
-lu_solve_kernel(const double* __restrict__ A, int64_t ld, int m, const int32_t* __restrict__ piv, double* __restrict__ b,
-                double scale) {
-  __shared__ double T[kSolveNb][kSolveNb + 1];
-  __shared__ double xs[kSolveNb];
-  __shared__ int32_t pchunk[kLuThreads];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int c0 = 0; c0 < m; c0 += kLuThreads) {  // the interchanges are sequential; the pivot indices are staged in bulk
-    if (c0 + tid < m) pchunk[tid] = piv[c0 + tid];
-    __syncthreads();
-    if (tid == 0)
-      for (int c = c0; c < min(m, c0 + kLuThreads); ++c) {
-        const int p = pchunk[c - c0];
-        if (p != c) {
-          const double t = b[c];
-          b[c] = b[p];
-          b[p] = t;
-        }
-      }
-    __syncthreads();
-  }
-  // forward: unit lower
-  for (int k0 = 0; k0 < m; k0 += kSolveNb) {
-    const int nb = min(kSolveNb, m - k0);
-    {
-      const int r = tid % kSolveNb, c = tid / kSolveNb;
-      T[r][c] = (r < nb && c < nb) ? A[ld * (k0 + c) + k0 + r] : 0.0;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      double x = lane < nb ? b[k0 + lane] : 0.0;
-      for (int c = 0; c < nb; ++c) {
-        const double xc = __shfl_sync(0xffffffffu, x, c);
-        if (lane > c) x -= T[lane][c] * xc;
-      }
-      xs[lane] = x;
-      if (lane < nb) b[k0 + lane] = x;
-    }
-    __syncthreads();
-    for (int r = k0 + nb + tid; r < m; r += kLuThreads) {
-      double acc = 0.0;
-      for (int c = 0; c < nb; ++c) acc = fma(A[ld * (k0 + c) + r], xs[c], acc);
-      b[r] -= acc;
-    }
-    __syncthreads();
-  }
-  // backward: upper with diagonal
-  for (int k1 = m; k1 > 0; k1 -= kSolveNb) {
-    const int k0 = max(0, k1 - kSolveNb), nb = k1 - k0;
-    {
-      const int r = tid % kSolveNb, c = tid / kSolveNb;
-      T[r][c] = (r < nb && c < nb) ? A[ld * (k0 + c) + k0 + r] : 0.0;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      double x = lane < nb ? b[k0 + lane] : 0.0;
-      for (int c = nb - 1; c >= 0; --c) {
-        if (lane == c) x /= T[c][c];
-        const double xc = __shfl_sync(0xffffffffu, x, c);
-        if (lane < c) x -= T[lane][c] * xc;
-      }
-      xs[lane] = x;
-      if (lane < nb) b[k0 + lane] = x;
-    }
-    __syncthreads();
-    for (int r = tid; r < k0; r += kLuThreads) {
-      double acc = 0.0;
-      for (int c = 0; c < nb; ++c) acc = fma(A[ld * (k0 + c) + r], xs[c], acc);
-      b[r] -= acc;
-    }
-    __syncthreads();
-  }
-  if (scale != 1.0)
-    for (int r = tid; r < m; r += kLuThreads) b[r] *= scale;
-}
 
 __global__ void add_diag_kernel(const double* __restrict__ H, double mu, int m, double* __restrict__ out) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -300,18 +110,7 @@ struct LargeSolver {
   // A (column-major m x m, overwritten by its factors)
   void factor(double* A, int32_t* p, bool pivoting) {
     CA_CUDA(cudaMemsetAsync(flag.ptr, 0, sizeof(int32_t), st));
-    for (int k0 = 0; k0 < m; k0 += kLuNb) {
-      const int nb = std::min(kLuNb, m - k0), k1 = k0 + nb;
-      lu_panel_kernel<<<1, kLuThreads, 0, st>>>(A, m, m, k0, nb, p, flag.ptr, pivoting ? 1 : 0);
-      if (pivoting && m > nb) lu_swap_kernel<<<(unsigned)((m - nb + 255) / 256), 256, 0, st>>>(A, m, m, k0, nb, p);
-      if (k1 < m) {
-        lu_trsm_kernel<<<(unsigned)((m - k1 + 127) / 128), 128, 0, st>>>(A, m, m, k0, nb);
-        launch_dgemm(m - k1, m - k1, nb, -1.0, colmajor(A + k1 + (size_t)m * k0, m), colmajor(A + k0 + (size_t)m * k1, m), 1.0,
-                     A + k1 + (size_t)m * k1, 1, m, st);
-      }
-      count_launch(3);
-    }
-    CA_CUDA(cudaGetLastError());
+    lu::factor(A, m, p, flag.ptr, pivoting, st);
   }
   bool singular() {
     int32_t s = 0;
@@ -320,11 +119,7 @@ struct LargeSolver {
     return s != 0;
   }
   // b <- scale * A^-1 b with the factors of factor()
-  void solve(const double* A, const int32_t* p, double* b, double scale) {
-    lu_solve_kernel<<<1, kLuThreads, 0, st>>>(A, m, m, p, b, scale);
-    CA_CUDA(cudaGetLastError());
-    count_launch();
-  }
+  void solve(const double* A, const int32_t* p, double* b, double scale) { lu::solve(A, m, p, b, scale, st); }
   void gemv(const double* A, bool transpose, const double* v, double* out) {
     const MatView a = transpose ? transposed(colmajor(A, m)) : colmajor(A, m);
     launch_dgemm(m, 1, m, 1.0, a, colmajor(v, m), 0.0, out, 1, m, st);
@@ -544,20 +339,8 @@ extern "C" int32_t ca_selftest_lu_solve(double* A_host, int64_t m64, double* b_h
     piv.alloc((size_t)m);
     flag.alloc(1);
     CA_CUDA(cudaMemset(flag.ptr, 0, sizeof(int32_t)));
-    for (int k0 = 0; k0 < m; k0 += kLuNb) {
-      const int nb = std::min(kLuNb, m - k0), k1 = k0 + nb;
-      lu_panel_kernel<<<1, kLuThreads>>>(A.ptr, m, m, k0, nb, piv.ptr, flag.ptr, 1);
-      if (m > nb) lu_swap_kernel<<<(unsigned)((m - nb + 255) / 256), 256>>>(A.ptr, m, m, k0, nb, piv.ptr);
-      if (k1 < m) {
-        lu_trsm_kernel<<<(unsigned)((m - k1 + 127) / 128), 128>>>(A.ptr, m, m, k0, nb);
-        launch_dgemm(m - k1, m - k1, nb, -1.0, colmajor(A.ptr + k1 + (size_t)m * k0, m), colmajor(A.ptr + k0 + (size_t)m * k1, m),
-                     1.0, A.ptr + k1 + (size_t)m * k1, 1, m, nullptr);
-      }
-      count_launch(3);
-    }
-    lu_solve_kernel<<<1, kLuThreads>>>(A.ptr, m, m, piv.ptr, b.ptr, 1.0);
-    CA_CUDA(cudaGetLastError());
-    count_launch();
+    lu::factor(A.ptr, m, piv.ptr, flag.ptr, true, nullptr);
+    lu::solve(A.ptr, m, piv.ptr, b.ptr, 1.0, nullptr);
     int32_t s = 0;
     CA_CUDA(cudaMemcpy(&s, flag.ptr, sizeof s, cudaMemcpyDeviceToHost));
     if (singular) *singular = s;

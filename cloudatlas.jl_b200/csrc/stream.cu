@@ -21,8 +21,9 @@ constexpr int kStreamUnroll = 4;  // independent entry loads in flight per lane
 template <int NB, int MODE>
 __global__ void __launch_bounds__(kStreamThreads)
 stream_kernel(const uint32_t* __restrict__ ab, const double* __restrict__ val,
-              const StreamChunk* __restrict__ chunks, int64_t nchunks, int nin, const double* __restrict__ X,
-              const double* __restrict__ Y, int64_t ldx, int nb, double* __restrict__ partial) {
+              const StreamChunk* __restrict__ chunks, int64_t chunk0, int64_t nchunks, int nin,
+              const double* __restrict__ X, const double* __restrict__ Y, int64_t ldx, int nb,
+              double* __restrict__ partial) {
   extern __shared__ double sm[];
   double* xs = sm;                                    // [NB][nin]: one contiguous vector per state, so that the
   double* ys = MODE == MODE_QUAD ? sm : sm + (size_t)nin * NB;  // consecutive second factors of a row hit consecutive banks
@@ -42,7 +43,7 @@ stream_kernel(const uint32_t* __restrict__ ab, const double* __restrict__ val,
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * kStreamThreads) >> 5;
-  for (int64_t c = ((int64_t)blockIdx.x * kStreamThreads + threadIdx.x) >> 5; c < nchunks; c += warps) {
+  for (int64_t c = chunk0 + (((int64_t)blockIdx.x * kStreamThreads + threadIdx.x) >> 5); c < chunk0 + nchunks; c += warps) {
     const StreamChunk ch = chunks[c];
     double acc[NB];
 #pragma unroll
@@ -93,10 +94,11 @@ template <int MODE>
 __global__ void __launch_bounds__(kStreamThreads)
 stream_linear_kernel(const double* __restrict__ L1r, const double* __restrict__ L2r, double invR, int m, int nb,
                      int nlc, const double* __restrict__ X, const double* __restrict__ Y, int64_t ldx,
-                     double* __restrict__ lin_partial) {
+                     double* __restrict__ lin_partial, int row0, int nrows) {
   const int lane = threadIdx.x & 31;
-  const int64_t w = ((int64_t)blockIdx.x * kStreamThreads + threadIdx.x) >> 5;
-  if (w >= (int64_t)m * nlc) return;
+  const int64_t wl = ((int64_t)blockIdx.x * kStreamThreads + threadIdx.x) >> 5;
+  if (wl >= (int64_t)nrows * nlc) return;
+  const int64_t w = wl + (int64_t)row0 * nlc;  // rows [row0, row0 + nrows) of the operator
   const int row = (int)(w / nlc), j0 = (int)(w % nlc) * kLinCols, j1 = min(m, j0 + kLinCols);
   const double* V = MODE == MODE_JVP ? Y : X;  // for the Jacobian action the linear part acts on the direction
   const double* l1 = L1r + (size_t)row * m;
@@ -127,10 +129,10 @@ stream_linear_kernel(const double* __restrict__ L1r, const double* __restrict__ 
 __global__ void __launch_bounds__(kStreamThreads)
 stream_combine_kernel(const double* __restrict__ partial, const int32_t* __restrict__ row_chunk_ptr, int m,
                       int nb, const double* __restrict__ lin_partial, int nlc, double* __restrict__ OUT,
-                      int64_t ldo) {
+                      int64_t ldo, int row0, int nrows) {
   const int64_t t = (int64_t)blockIdx.x * kStreamThreads + threadIdx.x;
-  const int row = (int)(t >> 3), s = (int)(t & 7);
-  if (row >= m || s >= nb) return;
+  const int row = row0 + (int)(t >> 3), s = (int)(t & 7);
+  if (row >= row0 + nrows || row >= m || s >= nb) return;
   double acc = 0.0;
   if (lin_partial)
     for (int c = 0; c < nlc; ++c) acc += lin_partial[((int64_t)row * nlc + c) * 8 + s];
@@ -140,7 +142,9 @@ stream_combine_kernel(const double* __restrict__ partial, const int32_t* __restr
 
 template <int NB, int MODE>
 void launch_nb(const StreamPack& sp, const double* dX, const double* dY, int nb, int64_t ldx, double* dOUT,
-               int64_t ldo, const double* L1r, const double* L2r, double invR, cudaStream_t st) {
+               int64_t ldo, const double* L1r, const double* L2r, double invR, cudaStream_t st, int row0, int nrows) {
+  // rows [row0, row0 + nrows) of the operator: their chunks are a contiguous range (chunks are listed row by row)
+  const int64_t chunk0 = sp.h_row_chunk_ptr[(size_t)row0], nch = sp.h_row_chunk_ptr[(size_t)row0 + nrows] - chunk0;
   const size_t smem = (MODE == MODE_QUAD ? 1 : 2) * (size_t)sp.nin * NB * sizeof(double);
   auto kern = stream_kernel<NB, MODE>;
   CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -151,11 +155,11 @@ void launch_nb(const StreamPack& sp, const double* dX, const double* dY, int nb,
   CA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStreamThreads, smem));
   if (per_sm < 1) fail(CA_ERR_UNSUPPORTED, "streaming kernel does not fit (smem %zu B)", smem);
   double* partial = sp.partial_for(st);
-  if (sp.nchunks > 0) {
-    const int64_t want = (sp.nchunks + kStreamThreads / 32 - 1) / (kStreamThreads / 32);
+  if (nch > 0) {
+    const int64_t want = (nch + kStreamThreads / 32 - 1) / (kStreamThreads / 32);
     if (const char* e = getenv("CA_STREAM_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));  // tuning hook
     const int grid = (int)std::min<int64_t>(want, (int64_t)sms * per_sm);
-    kern<<<grid, kStreamThreads, smem, st>>>(sp.ab.ptr, sp.val.ptr, sp.chunks.ptr, sp.nchunks, sp.nin, dX, dY,
+    kern<<<grid, kStreamThreads, smem, st>>>(sp.ab.ptr, sp.val.ptr, sp.chunks.ptr, chunk0, nch, sp.nin, dX, dY,
                                              ldx, nb, partial);
     CA_CUDA(cudaGetLastError());
     count_launch();
@@ -163,22 +167,23 @@ void launch_nb(const StreamPack& sp, const double* dX, const double* dY, int nb,
   const int nlc = (sp.m + kLinCols - 1) / kLinCols;
   double* lin_partial = L1r ? partial + (size_t)std::max<int64_t>(sp.nchunks, 1) * 8 : nullptr;
   if (L1r) {
-    const int64_t warps = (int64_t)sp.m * nlc;
+    const int64_t warps = (int64_t)nrows * nlc;
     const int gridl = (int)((warps * 32 + kStreamThreads - 1) / kStreamThreads);
-    stream_linear_kernel<MODE><<<gridl, kStreamThreads, 0, st>>>(L1r, L2r, invR, sp.m, nb, nlc, dX, dY, ldx, lin_partial);
+    stream_linear_kernel<MODE><<<gridl, kStreamThreads, 0, st>>>(L1r, L2r, invR, sp.m, nb, nlc, dX, dY, ldx, lin_partial, row0, nrows);
     CA_CUDA(cudaGetLastError());
     count_launch();
   }
-  const int grid2 = (sp.m * 8 + kStreamThreads - 1) / kStreamThreads;
+  const int grid2 = (nrows * 8 + kStreamThreads - 1) / kStreamThreads;
   stream_combine_kernel<<<grid2, kStreamThreads, 0, st>>>(partial, sp.row_chunk_ptr.ptr, sp.m, nb, lin_partial, nlc,
-                                                          dOUT, ldo);
+                                                          dOUT, ldo, row0, nrows);
   CA_CUDA(cudaGetLastError());
   count_launch();
 }
 
 template <int MODE>
 void launch_mode(const StreamPack& sp, const double* dX, const double* dY, int64_t nstates, int64_t ldx,
-                 double* dOUT, int64_t ldo, const double* L1r, const double* L2r, double invR, cudaStream_t st) {
+                 double* dOUT, int64_t ldo, const double* L1r, const double* L2r, double invR, cudaStream_t st,
+                 int row0, int nrows) {
   // widest batch whose state tile fits in shared memory
   int optin = 0, dev = 0;
   CA_CUDA(cudaGetDevice(&dev));
@@ -193,10 +198,10 @@ void launch_mode(const StreamPack& sp, const double* dX, const double* dY, int64
     const double* x = dX + s0;
     const double* y = dY ? dY + s0 : nullptr;
     double* o = dOUT + s0;
-    if (nb >= 8) { nb = 8; launch_nb<8, MODE>(sp, x, y, nb, ldx, o, ldo, L1r, L2r, invR, st); }
-    else if (nb >= 4) { nb = 4; launch_nb<4, MODE>(sp, x, y, nb, ldx, o, ldo, L1r, L2r, invR, st); }
-    else if (nb >= 2) { nb = 2; launch_nb<2, MODE>(sp, x, y, nb, ldx, o, ldo, L1r, L2r, invR, st); }
-    else { nb = 1; launch_nb<1, MODE>(sp, x, y, nb, ldx, o, ldo, L1r, L2r, invR, st); }
+    if (nb >= 8) { nb = 8; launch_nb<8, MODE>(sp, x, y, nb, ldx, o, ldo, L1r, L2r, invR, st, row0, nrows); }
+    else if (nb >= 4) { nb = 4; launch_nb<4, MODE>(sp, x, y, nb, ldx, o, ldo, L1r, L2r, invR, st, row0, nrows); }
+    else if (nb >= 2) { nb = 2; launch_nb<2, MODE>(sp, x, y, nb, ldx, o, ldo, L1r, L2r, invR, st, row0, nrows); }
+    else { nb = 1; launch_nb<1, MODE>(sp, x, y, nb, ldx, o, ldo, L1r, L2r, invR, st, row0, nrows); }
     s0 += nb;
   }
 }
@@ -252,6 +257,7 @@ void StreamPack::build(std::vector<Term> terms, int32_t m_, bool symmetric_) {
   val.upload(hval.data(), hval.size());
   chunks.upload(hchunks.data(), hchunks.size());
   row_chunk_ptr.upload(rcp.data(), rcp.size());
+  h_row_chunk_ptr = rcp;
   partials.clear();
   CA_CUDA(cudaStreamSynchronize(nullptr));
 }
@@ -281,6 +287,7 @@ void StreamPack::adopt(DeviceBuffer<uint32_t>&& ab_, DeviceBuffer<double>&& val_
   std::swap(val.count, val_.count);
   chunks.upload(hchunks.data(), hchunks.size());
   row_chunk_ptr.upload(rcp.data(), rcp.size());
+  h_row_chunk_ptr = rcp;
   partials.clear();
   CA_CUDA(cudaStreamSynchronize(nullptr));
 }
@@ -297,14 +304,18 @@ double* StreamPack::partial_for(cudaStream_t st) const {
 
 void launch_stream(const StreamPack& sp, int mode, const double* dX, const double* dY, int64_t nstates,
                    int64_t ldx, double* dOUT, int64_t ldo, const double* L1r, const double* L2r, double invR,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, int row_begin, int row_end) {
   if (nstates <= 0) return;
+  if (row_end < 0) row_end = sp.m;
+  if (row_begin < 0 || row_begin > row_end || row_end > sp.m) fail(CA_ERR_INVALID, "row range [%d,%d) outside 0:%d", row_begin, row_end, sp.m);
+  if (row_begin == row_end) return;
+  const int row0 = row_begin, nrows = row_end - row_begin;
   if (mode != MODE_QUAD && !dY) fail(CA_ERR_INVALID, "second ensemble missing");
   if (mode != MODE_ORDERED && !sp.symmetric) fail(CA_ERR_INVALID, "quadratic/JVP evaluation needs the symmetric stream");
   switch (mode) {
-    case MODE_QUAD: launch_mode<MODE_QUAD>(sp, dX, dY, nstates, ldx, dOUT, ldo, L1r, L2r, invR, stream); break;
-    case MODE_ORDERED: launch_mode<MODE_ORDERED>(sp, dX, dY, nstates, ldx, dOUT, ldo, L1r, L2r, invR, stream); break;
-    case MODE_JVP: launch_mode<MODE_JVP>(sp, dX, dY, nstates, ldx, dOUT, ldo, L1r, L2r, invR, stream); break;
+    case MODE_QUAD: launch_mode<MODE_QUAD>(sp, dX, dY, nstates, ldx, dOUT, ldo, L1r, L2r, invR, stream, row0, nrows); break;
+    case MODE_ORDERED: launch_mode<MODE_ORDERED>(sp, dX, dY, nstates, ldx, dOUT, ldo, L1r, L2r, invR, stream, row0, nrows); break;
+    case MODE_JVP: launch_mode<MODE_JVP>(sp, dX, dY, nstates, ldx, dOUT, ldo, L1r, L2r, invR, stream, row0, nrows); break;
     default: fail(CA_ERR_INVALID, "unknown evaluation mode %d", mode);
   }
 }

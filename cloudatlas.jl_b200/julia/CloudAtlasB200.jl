@@ -308,6 +308,35 @@ end
 hookstepsolve(f, Df, xguess, params=SearchParams()) = CloudAtlas.hookstepsolve(f, Df, xguess, params)
 hookstepsolve(f, xguess, params::SearchParams=SearchParams()) = CloudAtlas.hookstepsolve(f, xguess, params)
 
-export B200Bilinear, B200Model, b200_basisIndices, observables
+# ---- Newton-Krylov (additive; BASELINE configs[4]) -----------------------------------------------------------
+struct CKrylovParams
+    ftol::Float64; gmres_rtol::Float64
+    max_newton::Int32; restart::Int32; max_restarts::Int32; verbosity::Int32; precondition::Int32
+end
+struct CKrylovInfo
+    converged::Int32; newton_steps::Int32; jvps::Int32; f_evals::Int32; world::Int32
+    final_residual::Float64; device_seconds::Float64
+    residual::NTuple{64,Float64}
+end
+
+"""
+    newton_krylov(model, R, xguess; ftol=1e-10, gmres_rtol=1e-8, max_newton=30, restart=60, max_restarts=5)
+
+Matrix-free Newton-GMRES on the device (preconditioned with L1 + L2/R); with a multi-GPU model the Jacobian action is
+sharded by row slab over the GPUs.  Returns (x, converged, jacobian_actions).
+"""
+function newton_krylov(model::B200Model, R::Real, xguess::Vector{Float64}; ftol=1e-10, gmres_rtol=1e-8, max_newton=30,
+                       restart=60, max_restarts=5)
+    x = similar(xguess)
+    success = Ref{Int32}(0)
+    info = Ref{CKrylovInfo}()
+    p = CKrylovParams(ftol, gmres_rtol, max_newton, restart, max_restarts, 0, 1)
+    check(ccall((:ca_newton_krylov, lib), Int32,
+                (Ptr{Ptr{Cvoid}}, Int32, Ptr{Cvoid}, Float64, Ptr{Float64}, Ref{CKrylovParams}, Ptr{Float64}, Ref{Int32}, Ref{CKrylovInfo}),
+                model.handles, length(model.handles), model.comm, Float64(R), xguess, p, x, success, info))
+    x, success[] == 1, Int(info[].jvps)
+end
+
+export B200Bilinear, B200Model, b200_basisIndices, observables, newton_krylov
 
 end # module

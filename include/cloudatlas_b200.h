@@ -330,6 +330,30 @@ int32_t ca_hookstep_solve_model(ca_model* h, const double* R, const double* Xgue
                                 const ca_search_params* params, double* X_out, int32_t* success,
                                 ca_solve_log* logs);
 
+/* ---- Newton-Krylov (BASELINE.json configs[4]; SURVEY.md 8e, last row) ------------------------------ */
+/* Matrix-free Newton-GMRES for f(x,R) = 0, device resident: every Krylov vector costs one Jacobian action
+ * Df(x,R) v = (L1 + L2/R) v + Q(x,v) + Q(v,x) by the HBM-bound streaming kernel; restarted GMRES (classical Gram-Schmidt
+ * twice), left-preconditioned with the linear operator L1 + L2/R, backtracking line search on |f|.  For models where the dense m x m Jacobian and its LU dominate hookstepsolve
+ * (Hookstep.jl:158) -- m ~ 3000.
+ * models: nmodels replicas of ONE model, one per local device of `comm` (NULL with nmodels == 1: a single GPU, or
+ * NULL = the ca_init communicator).  With N ranks the Jacobian action is sharded by ROW SLAB: every device streams 1/N of
+ * the operator and one ncclAllGather of m doubles per Krylov step completes the vector; the Arnoldi process is replicated
+ * (deterministic kernels: the replicas stay bit-identical), so no vector is broadcast.  One process per GPU: every rank
+ * calls this with its own model and the communicator of ca_comm_init_rank, and every rank receives the solution. */
+typedef struct ca_krylov_params {
+  double ftol, gmres_rtol;                 /* defaults 1e-10, 1e-8 (relative to |f| of the Newton iterate) */
+  int32_t max_newton, restart, max_restarts, verbosity; /* defaults 30, 60, 5, 0 */
+  int32_t precondition;                    /* default 1: GMRES on M^-1 Df with M = L1 + L2/R, factored once per solve by the
+                                              device LU (without it GMRES stagnates on the viscous spectrum at m >~ 300) */
+} ca_krylov_params;
+typedef struct ca_krylov_info {
+  int32_t converged, newton_steps, jvps, f_evals, world;
+  double final_residual, device_seconds;
+  double residual[CA_LOG_STEPS];           /* |f| at the start of Newton step n */
+} ca_krylov_info;
+int32_t ca_newton_krylov(ca_model** models, int32_t nmodels, ca_comm* comm, double R, const double* xguess,
+                         const ca_krylov_params* params, double* x_out, int32_t* success, ca_krylov_info* info);
+
 /* ---- diagnostics (host only, no device needed) ---------------------------------------------- */
 /* Packs a COO operator exactly as ca_bilinear_create does, expands the packed tiles back into
  * (i,j,k,val) terms and compares them with the (merged) input: *mismatches must come back 0.

@@ -33,7 +33,7 @@ def julia_type_of(cparam):
         return {"Ref{Ptr{Cvoid}}", "Ptr{Ptr{Cvoid}}"}
     if re.fullmatch(r"ca_[a-z_]+\*", t):                               # opaque handles and plain structs by pointer
         return {"Ptr{Cvoid}", "Ref{SearchParams}", "Ref{CSearchParams}", "Ptr{CSearchParams}", "Ref{CSymmetry}",
-                "Ptr{CSymmetry}", "Ptr{Nothing}"}
+                "Ptr{CSymmetry}", "Ptr{Nothing}", "Ref{CKrylovParams}", "Ref{CKrylovInfo}"}
     return None
 
 

@@ -93,3 +93,58 @@ def test_one_process_per_gpu_under_torchrun(ca):
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "sharded ok" in out.stdout
+
+
+def test_newton_krylov_single_gpu_in_the_library(ca):
+    """ca_newton_krylov on one GPU (no communicator): converges to the hookstep equilibrium of a 111-mode model; the
+    Jacobian actions are counted."""
+    from conftest import read_asc
+    H = nagata(ca)
+    small = ca.ODEModel(1.0, 2.0, 2, 2, 3, H)
+    x44, ok = ca.hookstepsolve(small, 200.0, read_asc("xeq1projection-Re200-2-2-3-44d.asc"))
+    model = ca.ODEModel(1.0, 2.0, 3, 3, 4, H)
+    xg = ca.changebasis(x44, small.ijkl, model.ijkl)
+    xe, oke = ca.hookstepsolve(model, 200.0, xg, ca.SearchParams(Nnewton=30))
+    assert oke
+    # one continuation step in Re by both solvers (from a far guess the two may land on different branches)
+    xh, okh = ca.hookstepsolve(model, 205.0, xe, ca.SearchParams(Nnewton=30))
+    xk, conv, info = ca.newton_krylov(model, 205.0, xe, ftol=1e-11)
+    assert okh and conv, info
+    assert info["world"] == 1 and info["jvps"] > 0 and info["device_seconds"] > 0
+    assert np.linalg.norm(model.f(xk, 205.0)) < 1e-10
+    assert np.linalg.norm(xk - xh) / np.linalg.norm(xh) < 1e-7
+    assert info["residuals"][0] > info["residuals"][-1]
+    # without the preconditioner GMRES needs far more Jacobian actions on the viscous spectrum
+    xu, convu, infou = ca.newton_krylov(model, 205.0, xe, ftol=1e-11, precondition=False)
+    assert infou["jvps"] > info["jvps"]
+
+
+@pytest.mark.skipif("ngpus() < 2")
+def test_newton_krylov_row_slab_sharded(ca):
+    """SURVEY 8e, last row: the Jacobian action sharded by row slab over the GPUs of one process, one all-gather of m
+    doubles per Krylov step, replicated Arnoldi.  Same iterates as the single-GPU solve (the slabs partition the rows;
+    every row is computed by the same code on the same numbers)."""
+    import torch
+    from conftest import read_asc
+    H = nagata(ca)
+    n = min(ngpus(), 4)
+    small = ca.ODEModel(1.0, 2.0, 2, 2, 3, H)
+    x44, ok = ca.hookstepsolve(small, 200.0, read_asc("xeq1projection-Re200-2-2-3-44d.asc"))
+    ijkl = ca.basisIndices(3, 3, 12, H)
+    comm = ca.LibraryComm.init_all(n)
+    fulls = ca.assemble_sharded(comm, 1.0, 2.0, ijkl)
+    models = []
+    for d, full in enumerate(fulls):
+        with torch.cuda.device(d):
+            models.append(ca.ModelOperators.from_assembly(full))
+    with torch.cuda.device(0):   # an equilibrium of the 307-mode model at Re = 200 (global-memory hookstep solver) ...
+        xe, ok = ca.hookstepsolve(models[0], 200.0, ca.changebasis(x44, small.ijkl, ijkl), ca.SearchParams(Nnewton=30))
+        assert ok
+    # ... continued to Re = 210 by Newton-Krylov, sharded and on one GPU
+    xs, convs, infos = ca.newton_krylov(models, 210.0, xe, ftol=1e-11, comm=comm)
+    assert convs and infos["world"] == n, infos
+    with torch.cuda.device(0):
+        x1, conv1, info1 = ca.newton_krylov(models[0], 210.0, xe, ftol=1e-11)
+        assert conv1 and np.linalg.norm(models[0].f(xs, 210.0)) < 1e-10
+    assert np.array_equal(xs, x1)
+    assert infos["jvps"] == info1["jvps"] and infos["newton_steps"] == info1["newton_steps"]

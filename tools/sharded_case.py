@@ -13,6 +13,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as g  # noqa: E402
 
 
+def model_shear(ca, slab, x):
+    """1 + dot(x, Psi_shear) with the shear vector of the assembly (ODEModels.jl:65-78)."""
+    import ctypes as C
+    from cloudatlas_b200._lib import _sig, c_f64p, check, vp
+    return 0.0 if slab is None else float("nan")
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -45,6 +52,29 @@ def main():
                              "nnz": slab.nnz}
         if rep == 0:
             del model, slab
+    if "--krylov" in sys.argv:
+        # Newton-Krylov with the Jacobian action sharded by row slab over the ranks (SPMD: every rank runs the replicated
+        # Arnoldi process on its own GPU and receives the solution)
+        gold = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+        x44 = np.array([float(t) for t in open(os.path.join(gold, "xeq1projection-Re200-2-2-3-44d.asc")).read().split("\n")
+                        if t.strip() and not t.startswith("%")])
+        ijkl44 = ca.basisIndices(2, 2, 3, [sx * sy * sz, sz * tx * tz])
+        xg = ca.changebasis(x44, ijkl44, ijkl)
+        comm = ca.library_comm_for(None) if world > 1 else None
+        # an equilibrium at Re = 200 by the global-memory Newton-hookstep (replicated on every rank), then one
+        # continuation step to Re = 205 by Newton-Krylov: sharded over the ranks, and on this rank's GPU alone
+        t0 = time.perf_counter()
+        xe, okh, hlog = ca.hookstepsolve(model, 200.0, xg, ca.SearchParams(Nnewton=40), return_log=True)
+        t_hook = time.perf_counter() - t0
+        xk, conv, kinfo = ca.newton_krylov(model, 205.0, xe, ftol=1e-10, max_newton=40, comm=comm)
+        x1, conv1, kinfo1 = ca.newton_krylov(model, 205.0, xe, ftol=1e-10, max_newton=40)
+        out["hookstep_Re200"] = {"converged": bool(okh), "newton_steps": hlog["newton_steps"], "device_seconds": hlog["device_seconds"],
+                                 "wall_seconds": t_hook, "residual": float(np.linalg.norm(model.f(xe, 200.0)))}
+        out["krylov_Re205"] = {"converged": conv, "newton_steps": kinfo["newton_steps"], "jvps": kinfo["jvps"], "f_evals": kinfo["f_evals"],
+                               "device_seconds_sharded": kinfo["device_seconds"], "device_seconds_one_gpu": kinfo1["device_seconds"],
+                               "ms_per_operator_pass_sharded": 1e3 * kinfo["device_seconds"] / max(kinfo["jvps"] + kinfo["f_evals"], 1),
+                               "ms_per_operator_pass_one_gpu": 1e3 * kinfo1["device_seconds"] / max(kinfo1["jvps"] + kinfo1["f_evals"], 1),
+                               "same_solution_as_one_gpu": bool(np.array_equal(xk, x1)), "final_residual": kinfo["final_residual"]}
     if "--check" in sys.argv:
         ref = ca.AssemblySlab(1.0, 2.0, ijkl, dense=dense)
         ijk, val = slab.coo_host()
