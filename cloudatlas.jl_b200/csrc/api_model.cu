@@ -13,6 +13,7 @@
 #include "assembly.h"
 #include "bilinear.h"
 #include "bilinear_kernels.cuh"
+#include "dense_lu.cuh"
 #include "model.h"
 
 using namespace ca;
@@ -853,16 +854,9 @@ __global__ void cnab2_combine_kernel(const double* __restrict__ n1, const double
   if (t < count) g[t] = fma(c1, n1[t], c0 * n0[t]);
 }
 
-// dense inverse by LU with partial pivoting (column-major m x m), host
-void dense_inverse(std::vector<double> A, int m, std::vector<double>& inv) {
-  std::vector<double> rm((size_t)m * m);
-  for (int i = 0; i < m; ++i)
-    for (int j = 0; j < m; ++j) rm[(size_t)i * m + j] = A[i + (size_t)m * j];
-  std::vector<double> out;
-  invert_block(rm, m, out);  // row-major in, row-major out
-  inv.resize((size_t)m * m);
-  for (int i = 0; i < m; ++i)
-    for (int j = 0; j < m; ++j) inv[i + (size_t)m * j] = out[(size_t)i * m + j];
+__global__ void set_identity_kernel(double* __restrict__ A, int m) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < (int64_t)m * m) A[t] = (t % m) == (t / m) ? 1.0 : 0.0;
 }
 
 void eval_pack(const DevicePack& dp, const StreamPack& sp, const double* dX, int64_t nstates, int64_t ldx,
@@ -899,31 +893,55 @@ extern "C" int32_t ca_model_cnab2_batched_dev(ca_model* h, const double* dX0, in
         }
       }
     }
-    // ---- [M1 M2] for this (R, dt):  LHS = B - dt/2 A, RHS = B + dt/2 A   (ODEModels.jl:149-155)
+    // ---- [M1 M2] for this (R, dt):  LHS = B - dt/2 A, RHS = B + dt/2 A   (ODEModels.jl:149-155).  The reference keeps
+    // lu(LHS); here M2 = LHS^-1 and M1 = M2 RHS are formed once per (R, dt) ON THE DEVICE (blocked LU of dense_lu.cuh,
+    // multi-right-hand-side substitution, one DGEMM) and applied every step: as a packed dense operator on the DMMA
+    // ensemble kernel up to kCnDenseMax modes, as two DGEMMs beyond (the term packer is limited to 32767 inputs and
+    // packing 2 m^2 terms costs more than it saves at m in the thousands).
+    constexpr int kCnDenseMax = 1024;
     if (!h->cn_built || h->cn_R != R || h->cn_dt != dt) {
       CA_CUDA(cudaDeviceSynchronize());
-      std::vector<double> lhs((size_t)m * m), rhs((size_t)m * m), M2, M1((size_t)m * m, 0.0);
-      for (size_t e = 0; e < (size_t)m * m; ++e) {
+      const size_t mm = (size_t)m * m;
+      std::vector<double> lhs(mm), rhs(mm);
+      for (size_t e = 0; e < mm; ++e) {
         const double a = h->hA1[e] + (1.0 / R) * h->hA2[e];
         lhs[e] = h->hB[e] - (dt / 2) * a;
         rhs[e] = h->hB[e] + (dt / 2) * a;
       }
-      dense_inverse(lhs, m, M2);
-      for (int j = 0; j < m; ++j)
-        for (int k = 0; k < m; ++k) {
-          const double r = rhs[k + (size_t)m * j];
-          if (r == 0.0) continue;
-          for (int i = 0; i < m; ++i) M1[i + (size_t)m * j] += M2[i + (size_t)m * k] * r;
-        }
-      std::vector<Term> lin;
-      lin.reserve((size_t)2 * m * m);
-      for (int j = 0; j < m; ++j)
-        for (int i = 0; i < m; ++i) {
-          if (M1[i + (size_t)m * j] != 0.0) lin.push_back(Term{i, j, 2 * m, M1[i + (size_t)m * j]});
-          if (M2[i + (size_t)m * j] != 0.0) lin.push_back(Term{i, m + j, 2 * m, M2[i + (size_t)m * j]});
-        }
-      h->cn_lin_stream.build_rect(lin, m, 2 * m);
-      h->cn_lin.upload(pack_terms(std::move(lin), m, true, nt_max_for(window_modes_for(2 * m)), window_modes_for(2 * m), 2 * m));
+      DeviceBuffer<double> dlhs, drhs;
+      DeviceBuffer<int32_t> piv, flag;
+      dlhs.upload(lhs.data(), mm, st);
+      drhs.upload(rhs.data(), mm, st);
+      piv.alloc((size_t)m);
+      flag.alloc(1);
+      h->cn_M1.alloc(mm);
+      h->cn_M2.alloc(mm);
+      CA_CUDA(cudaMemsetAsync(flag.ptr, 0, sizeof(int32_t), st));
+      set_identity_kernel<<<(unsigned)((mm + 255) / 256), 256, 0, st>>>(h->cn_M2.ptr, m);
+      CA_CUDA(cudaGetLastError());
+      count_launch();
+      lu::factor(dlhs.ptr, m, piv.ptr, flag.ptr, true, st);
+      lu::solve_many(dlhs.ptr, m, piv.ptr, h->cn_M2.ptr, m, st);                                   // M2 = LHS^-1
+      launch_dgemm(m, m, m, 1.0, colmajor(h->cn_M2.ptr, m), colmajor(drhs.ptr, m), 0.0, h->cn_M1.ptr, 1, m, st);  // M1 = M2 RHS
+      int32_t sing = 0;
+      CA_CUDA(cudaMemcpyAsync(&sing, flag.ptr, sizeof sing, cudaMemcpyDeviceToHost, st));
+      CA_CUDA(cudaStreamSynchronize(st));
+      if (sing) fail(CA_ERR_INVALID, "cnab2: B - dt/2 A is singular");
+      h->cn_dense = m > kCnDenseMax || getenv("CA_CNAB2_DENSE") != nullptr;  // (test hook: the DGEMM form at any size)
+      if (!h->cn_dense) {
+        std::vector<double> M1(mm), M2(mm);
+        CA_CUDA(cudaMemcpy(M1.data(), h->cn_M1.ptr, mm * sizeof(double), cudaMemcpyDeviceToHost));
+        CA_CUDA(cudaMemcpy(M2.data(), h->cn_M2.ptr, mm * sizeof(double), cudaMemcpyDeviceToHost));
+        std::vector<Term> lin;
+        lin.reserve((size_t)2 * mm);
+        for (int j = 0; j < m; ++j)
+          for (int i = 0; i < m; ++i) {
+            if (M1[i + (size_t)m * j] != 0.0) lin.push_back(Term{i, j, 2 * m, M1[i + (size_t)m * j]});
+            if (M2[i + (size_t)m * j] != 0.0) lin.push_back(Term{i, m + j, 2 * m, M2[i + (size_t)m * j]});
+          }
+        h->cn_lin_stream.build_rect(lin, m, 2 * m);
+        h->cn_lin.upload(pack_terms(std::move(lin), m, true, nt_max_for(window_modes_for(2 * m)), window_modes_for(2 * m), 2 * m));
+      }
       h->cn_R = R;
       h->cn_dt = dt;
       h->cn_built = true;
@@ -956,7 +974,12 @@ extern "C" int32_t ca_model_cnab2_batched_dev(ca_model* h, const double* dX0, in
                                                                         cur + per);
       CA_CUDA(cudaGetLastError());
       count_launch();
-      eval_pack(h->cn_lin, h->cn_lin_stream, cur, nstates, nstates, nxt, nstates, st);
+      if (h->cn_dense) {  // x_{n+1} = M1 x_n + M2 g for every state: [nstates x m] = [nstates x m] [m x m]'
+        launch_dgemm((int)nstates, m, m, 1.0, colmajor(cur, nstates), transposed(colmajor(h->cn_M1.ptr, m)), 0.0, nxt, 1, nstates, st);
+        launch_dgemm((int)nstates, m, m, 1.0, colmajor(cur + per, nstates), transposed(colmajor(h->cn_M2.ptr, m)), 1.0, nxt, 1, nstates, st);
+      } else {
+        eval_pack(h->cn_lin, h->cn_lin_stream, cur, nstates, nstates, nxt, nstates, st);
+      }
       std::swap(cur, nxt);
       if (n % nsave == 0 && dXsave && k < nsaves) {
         CA_CUDA(cudaMemcpyAsync(dXsave + (size_t)k * per, cur, per * 8, cudaMemcpyDeviceToDevice, st));

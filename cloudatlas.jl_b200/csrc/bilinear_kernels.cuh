@@ -542,6 +542,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16z(double* smem_dst, const double* gsrc, int src_bytes) {  // zero-fills beyond src_bytes
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
@@ -612,24 +616,50 @@ __device__ __forceinline__ void stage_ahead(int g, int gtotal, const WindowDesc*
     const char* psrc = reinterpret_cast<const char*>(pairs + (size_t)W.ks_begin * 4);
     char* pdst = reinterpret_cast<char*>(S.pairs + (size_t)((g + 1) & 1) * kWindowMaxKs * 4);
     for (int c = tid; c < nks; c += NTHR) cp_async16(pdst + c * 16, psrc + c * 16);  // one k-step = 4 packed pairs = 16 B
-    // one state row (32 states = 256 B) per warp instruction; the lane is the state
-    const bool ok = s0 + lane < nstates;
-    const double* xg = X + (ok ? s0 + lane : 0);
-    const double* yg = MODE == MODE_QUAD ? nullptr : Y + (ok ? s0 + lane : 0);
     const int32_t* md = S.modes + ((g + 1) & 1) * S.wpad;
     double* xb = S.bufs + (size_t)((g + 1) & 1) * S.bufstride;
     double* yb = xb + (size_t)S.wmax * ROW;
+    // 16-byte copies when the ensemble allows it (even leading dimension, 16-byte aligned base): a warp instruction
+    // then moves TWO state rows (32 states = 256 B each; lane = row half, pair of states) -- half the staging
+    // instructions of the 8-byte form, which remains for odd leading dimensions
+    const bool wide = ((ldx & 1) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
+                      (MODE == MODE_QUAD || (reinterpret_cast<uintptr_t>(Y) & 15) == 0);
+    if (wide) {
+      const int h2 = 2 * (lane & 15), sub = lane >> 4;
+      const int64_t s = s0 + h2;
+      const int nbytes = s + 1 < nstates ? 16 : (s < nstates ? 8 : 0);
+      const double* xg = X + (nbytes ? s : 0);
+      const double* yg = MODE == MODE_QUAD ? nullptr : Y + (nbytes ? s : 0);
 #pragma unroll 4
-    for (int l = warp; l < nmodes; l += NW) {
-      const int gm = md[l];
-      const int slot = l * ROW + (lane ^ swz<kWinMT>(l));
-      if (gm == one_mode) {
-        xb[slot] = 1.0;
-        if (MODE != MODE_QUAD) yb[slot] = MODE == MODE_JVP ? 0.0 : 1.0;
-      } else {
-        const int64_t off = ldx * (int64_t)gm;
-        cp_async8(xb + slot, xg + off, ok ? 8 : 0);
-        if (MODE != MODE_QUAD) cp_async8(yb + slot, yg + off, ok ? 8 : 0);
+      for (int l = 2 * warp + sub; l < nmodes; l += 2 * NW) {
+        const int gm = md[l];
+        const int slot = l * ROW + (h2 ^ swz<kWinMT>(l));  // the swizzle flips bits 2-3 of the state: pairs stay adjacent
+        if (gm == one_mode) {
+          xb[slot] = xb[slot + 1] = 1.0;
+          if (MODE != MODE_QUAD) yb[slot] = yb[slot + 1] = MODE == MODE_JVP ? 0.0 : 1.0;
+        } else {
+          const int64_t off = ldx * (int64_t)gm;
+          cp_async16z(xb + slot, xg + off, nbytes);
+          if (MODE != MODE_QUAD) cp_async16z(yb + slot, yg + off, nbytes);
+        }
+      }
+    } else {
+      // one state row per warp instruction; the lane is the state
+      const bool ok = s0 + lane < nstates;
+      const double* xg = X + (ok ? s0 + lane : 0);
+      const double* yg = MODE == MODE_QUAD ? nullptr : Y + (ok ? s0 + lane : 0);
+#pragma unroll 4
+      for (int l = warp; l < nmodes; l += NW) {
+        const int gm = md[l];
+        const int slot = l * ROW + (lane ^ swz<kWinMT>(l));
+        if (gm == one_mode) {
+          xb[slot] = 1.0;
+          if (MODE != MODE_QUAD) yb[slot] = MODE == MODE_JVP ? 0.0 : 1.0;
+        } else {
+          const int64_t off = ldx * (int64_t)gm;
+          cp_async8(xb + slot, xg + off, ok ? 8 : 0);
+          if (MODE != MODE_QUAD) cp_async8(yb + slot, yg + off, ok ? 8 : 0);
+        }
       }
     }
   }
@@ -656,14 +686,24 @@ struct ValRing {
   const char* src;  // the share's first value
   int n;            // k-steps in the share
 
+  static constexpr int kBatchBytes = KB * NT * 256;                 // 2048 (NT = 1, 2) or 1536 (NT = 3)
+  static constexpr int kCopies = (kBatchBytes + 511) / 512;         // 16-byte copies per lane and full batch
+  uint32_t dst_lane;     // shared-memory address of this lane's first 16 bytes in slot 0
+  const char* src_lane;  // this lane's first 16 bytes of the share
+
   __device__ __forceinline__ void issue(int b, int lane) const {
-    const int bytes = min(KB, n - b * KB) * (NT * 256);  // <= 0 past the end: an empty group keeps the count uniform
-    const char* s = src + (size_t)b * KB * (NT * 256);  // (a batch fills the whole slot only for NT = 1, 2)
-    char* d = ring + (b & 1) * kValSlotBytes;
+    const int left = n - b * KB;  // k-steps from batch b on; <= 0 past the end: an empty group keeps the count uniform
+    const char* s = src_lane + (size_t)b * kBatchBytes;
+    const uint32_t d = dst_lane + (b & 1) * kValSlotBytes;
+    if (left >= KB) {  // (warp-uniform) a full batch: constant offsets, no per-copy predicate
 #pragma unroll
-    for (int c = 0; c < kValSlotBytes / 512; ++c) {
-      const int o = c * 512 + lane * 16;
-      if (o < bytes) cp_async16(d + o, s + o);
+      for (int c = 0; c < kCopies; ++c)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + c * 512), "l"(s + c * 512) : "memory");
+    } else if (left > 0) {
+      const int bytes = left * (NT * 256) - lane * 16;
+#pragma unroll
+      for (int c = 0; c < kCopies; ++c)
+        if (c * 512 < bytes) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + c * 512), "l"(s + c * 512) : "memory");
     }
     cp_async_commit();
   }
@@ -673,6 +713,8 @@ struct ValRing {
     warp_share<NW>(nks, warp, k0, k1);
     n = k1 - k0;
     src = reinterpret_cast<const char*>(vals0 + (size_t)k0 * NT * 32);
+    src_lane = src + lane * 16;
+    dst_lane = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;
     __syncwarp();  // every lane is done reading the previous share's slots
     issue(0, lane);
     issue(1, lane);

@@ -83,7 +83,8 @@ struct ca_model {
   ca::DevicePack cn_lin;              // dense [M1 M2] acting on [x; g] (2m inputs), per (R, dt)
   ca::StreamPack cn_lin_stream;
   double cn_R = 0.0, cn_dt = 0.0;
-  bool cn_built = false;
+  bool cn_built = false, cn_dense = false;
+  ca::DeviceBuffer<double> cn_M1, cn_M2;   // M1 = LHS^-1 RHS, M2 = LHS^-1 (column-major), formed on the device per (R, dt)
   ca::DeviceBuffer<double> cn_buf[2], cn_n[2];
   ca::DevicePack obs;                 // two output rows: shear and dissipation (ODEModels.jl:65-137)
   ca::StreamPack obs_stream;

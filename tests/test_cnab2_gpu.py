@@ -65,3 +65,21 @@ def test_ensemble_with_windowed_operators(ca, nagata_H, known, monkeypatch):
     for s in (0, 33, 69):
         _, Xr = ref_cnab2(X0[s], ref, 250.0, 0.02, 12, 4)
         assert np.max(np.abs(X[:, s, :] - Xr)) / np.max(np.abs(Xr)) < 1e-11
+
+
+def test_dense_gemm_form_of_the_implicit_step(ca, nagata_H, monkeypatch):
+    """Beyond 1024 modes the implicit operators M1 = LHS^-1 RHS, M2 = LHS^-1 (factored on the device per (R, dt)) are
+    applied as two DGEMMs instead of a packed operator; forced here onto the 44-mode model, ensembles and few states."""
+    from oracle.model import ODEModel, cnab2 as ref_cnab2
+    monkeypatch.setenv("CA_CNAB2_DENSE", "1")
+    ref = ODEModel(1.0, 2.0, 2, 2, 3, nagata_H)
+    dev = ca.ModelOperators(ref.B, ref.A1, ref.A2, ref.N.ijk, ref.N.val)
+    rng = np.random.default_rng(11)
+    X0 = 0.05 * rng.standard_normal((70, 44))
+    t, X = ca.cnab2(X0, dev, 250.0, 0.02, 12, 4)
+    assert X.shape == (3, 70, 44)
+    for s in (0, 33, 69):
+        _, Xr = ref_cnab2(X0[s], ref, 250.0, 0.02, 12, 4)
+        assert np.max(np.abs(X[:, s, :] - Xr)) / np.max(np.abs(Xr)) < 1e-11
+    _, Xf = ca.cnab2(X0[:2], dev, 250.0, 0.02, 12, 4)
+    assert np.max(np.abs(Xf - X[:, :2, :])) < 1e-13
