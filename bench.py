@@ -468,8 +468,8 @@ def large_basis_case(ca, H, jkl, world, rank, max_over_ranks, barrier, dmma_peak
            "m": int(m), "nnz_N": int(nnz), "n_gpus": world, "first_pass": passes[0], "steady_pass": passes[1],
            "all_gather_busbw_GBs": busbw, "nvlink_busbw_measured_GBs": NVLINK_BUSBW_MEASURED,
            "all_gather_frac_of_measured": (busbw / NVLINK_BUSBW_MEASURED) if busbw else None,
-           "collective": "ca_assemble_sharded: slab sizes (8-byte all-gather), then an all-gather-v of the slabs as one ncclGroup of "
-                         "point-to-point transfers straight into place (csrc/comm.cu)" if world > 1 else "none (one GPU)",
+           "collective": "ca_assemble_sharded: slab sizes (8-byte all-gather), then every piece of every slab broadcast in place "
+                         "inside one ncclGroup (csrc/comm.cu)" if world > 1 else "none (one GPU)",
            "rhs_evals_per_sec": world * nstates / (rhs_ms * 1e-3), "jvp_per_sec": world * nstates / (jvp_ms * 1e-3),
            "rhs_ms": rhs_ms, "jvp_ms": jvp_ms, "kernel_path": model.kernel_path(nstates)[0],
            "executed_fma_per_state": fma, "rhs_executed_tflops_per_gpu": exec_tf, "rhs_executed_frac_of_dmma_peak": exec_tf / dmma_peak,
