@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcloudatlas_b200.so")
+# CLOUDATLAS_B200_LIB: another build of the same library (tools/build_variant.sh: tuning experiments)
+LIB_PATH = os.environ.get("CLOUDATLAS_B200_LIB") or os.path.join(_HERE, "lib", "libcloudatlas_b200.so")
 
 
 class CloudAtlasError(RuntimeError):

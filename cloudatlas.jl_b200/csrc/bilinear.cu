@@ -213,10 +213,11 @@ void launch_windowed_nt(const DevicePack& op, const double* dX, const double* dY
   const size_t smem = windowed_smem_bytes<MODE, NT3>(wmax);
   CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  constexpr int threads = WinCfg<MODE, NT3>::NW * 32;
+  constexpr int threads = WinCfg<MODE, NT3>::THREADS;
   CA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) fail(CA_ERR_UNSUPPORTED, "windowed kernel does not fit (smem %zu B)", smem);
-  const int64_t nblocks = (nstates + 8 * kWinMT - 1) / (8 * kWinMT);
+  constexpr int teams = WinCfg<MODE, NT3>::TEAMS;  // blocks of 32 states per CTA and pass
+  const int64_t nblocks = ((nstates + 8 * kWinMT - 1) / (8 * kWinMT) + teams - 1) / teams;
   const int grid = (int)std::min<int64_t>(nblocks, (int64_t)device_cfg().sms * per_sm);
   kern<<<grid, threads, smem, stream>>>(op.windows.ptr, op.nwin, op.nwin_nt3, op.nwin_nt2, op.modes.ptr, op.pairs_windowed(),
                                         op.vals.ptr, op.rows.ptr, wmax, op.nin - 1, dX, dY, nstates, ldx, dOUT, ldo);

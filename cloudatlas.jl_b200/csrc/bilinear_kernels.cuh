@@ -36,6 +36,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// barrier `id` (1 ..) among NTHREADS threads of the CTA (the consumer warps of one team of the windowed kernel)
+template <int NTHREADS>
+__device__ __forceinline__ void named_barrier(int id) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "n"(NTHREADS) : "memory");
+}
+
 // State slot swizzle inside a mode's row of the shared tile.  An LDS.64 of a warp is served in two
 // half-warp phases; in a phase the four pair columns read four modes x 32 B.  XOR-ing bits 2-3 of the
 // state slot with the low bits of the mode index sends modes with distinct (mode & 3) -- e.g. the
@@ -207,15 +213,19 @@ __device__ __forceinline__ void range_accumulate(const uint2* __restrict__ pairs
 }
 
 // n-tiles [NT0, NT0 + NTC) of an accumulator with NTA n-tiles (NTC <= kNtMax: the reduction buffer holds two)
-template <int MT, int NTA, int NT0, int NTC, int NW>
+template <int MT, int NTA, int NT0, int NTC, int NW, bool WS = false>
 __device__ __forceinline__ void tile_reduce_store_part(int rows_off, const int32_t* __restrict__ rows,
                                                        double* red, const double (&acc)[MT][NTA][2],
                                                        int warp, int lane, int64_t s0, int64_t nstates,
-                                                       double* __restrict__ OUT, int64_t ldo) {
+                                                       double* __restrict__ OUT, int64_t ldo, int bar_id = 1) {
   static_assert(NTC <= kNtMax && NT0 + NTC <= NTA, "slice of the accumulator");
   constexpr int ROW = 8 * MT;
   const int r = lane >> 2, c = lane & 3;
-  __syncthreads();  // previous tile's readers are done with `red`
+  auto barrier = [bar_id] {  // WS: `warp` counts within the NW warps that share the reduction
+    if constexpr (WS) named_barrier<NW * 32>(bar_id);
+    else __syncthreads();
+  };
+  barrier();  // previous tile's readers are done with `red`
   double* mine = red + warp * (kNtMax * 8 * ROW);
 #pragma unroll
   for (int nt = 0; nt < NTC; ++nt)
@@ -224,8 +234,8 @@ __device__ __forceinline__ void tile_reduce_store_part(int rows_off, const int32
       mine[(nt * 8 + c * 2 + 0) * ROW + mt * 8 + r] = acc[mt][NT0 + nt][0];
       mine[(nt * 8 + c * 2 + 1) * ROW + mt * 8 + r] = acc[mt][NT0 + nt][1];
     }
-  __syncthreads();
-  for (int o = threadIdx.x; o < NTC * 8 * ROW; o += NW * 32) {
+  barrier();
+  for (int o = warp * 32 + lane; o < NTC * 8 * ROW; o += NW * 32) {
     const int n = o / ROW, s = o % ROW;
     const int row = __ldg(rows + rows_off + NT0 * 8 + n);
     double sum = 0.0;
@@ -235,16 +245,16 @@ __device__ __forceinline__ void tile_reduce_store_part(int rows_off, const int32
   }
 }
 
-template <int MT, int NT, int NW = kWarps>
+template <int MT, int NT, int NW = kWarps, bool WS = false>
 __device__ __forceinline__ void tile_reduce_store(int rows_off, const int32_t* __restrict__ rows,
                                                   double* red, const double (&acc)[MT][NT][2],
                                                   int warp, int lane, int64_t s0, int64_t nstates,
-                                                  double* __restrict__ OUT, int64_t ldo) {
+                                                  double* __restrict__ OUT, int64_t ldo, int bar_id = 1) {
   if constexpr (NT <= kNtMax) {
-    tile_reduce_store_part<MT, NT, 0, NT, NW>(rows_off, rows, red, acc, warp, lane, s0, nstates, OUT, ldo);
+    tile_reduce_store_part<MT, NT, 0, NT, NW, WS>(rows_off, rows, red, acc, warp, lane, s0, nstates, OUT, ldo, bar_id);
   } else {  // three n-tiles: two passes through the two-tile reduction buffer
-    tile_reduce_store_part<MT, NT, 0, kNtMax, NW>(rows_off, rows, red, acc, warp, lane, s0, nstates, OUT, ldo);
-    tile_reduce_store_part<MT, NT, kNtMax, NT - kNtMax, NW>(rows_off, rows, red, acc, warp, lane, s0, nstates, OUT, ldo);
+    tile_reduce_store_part<MT, NT, 0, kNtMax, NW, WS>(rows_off, rows, red, acc, warp, lane, s0, nstates, OUT, ldo, bar_id);
+    tile_reduce_store_part<MT, NT, kNtMax, NT - kNtMax, NW, WS>(rows_off, rows, red, acc, warp, lane, s0, nstates, OUT, ldo, bar_id);
   }
 }
 
@@ -516,19 +526,21 @@ bilinear_batched_kernel(const TileDesc* __restrict__ tiles, int ntiles, int nt2_
 // ------------------------------------------------------------------------------------------------
 // Windowed variant for large m: instead of the whole state tile, shared memory holds the rows of the
 // modes one WINDOW of k-steps touches (<= wmax, see pack.h), gathered with cp.async into a double
-// buffer while the previous window is being multiplied.  One barrier per window; accumulators live
-// across the windows of a tile.  Footprint: 2 x wmax x 256 B per vector, independent of m.
+// buffer while the previous window is being multiplied.  Accumulators live across the windows of a
+// tile.  Footprint: 2 x wmax x 256 B per vector, independent of m.
 //
-// Everything a window needs arrives through the same cp.async pipeline, so no warp ever waits on a
-// dependent L2 load: at the top of window g (right after its barrier) the CTA issues
-//   the state rows and the pair words of window g+1   (their descriptor and mode list are already in smem),
-//   the mode list of window g+2                       (its descriptor is already in smem),
-//   the descriptor of window g+3,
-// and the next barrier's cp.async.wait_all makes all of it visible.  Operator values stay in registers,
-// prefetched kPrefetch k-steps ahead with loads that are pinned in program order (volatile asm: the
-// compiler otherwise sinks them to the end of the unrolled body and exposes the L2 latency).
+// The CTA is split by role:
+//   producer warps  gather the state rows and the pair words of window g+1 into the free slot -- every byte through
+//                   cp.async, completion signalled by cp.async.mbarrier.arrive on the slot's `full` barrier;
+//   consumer warps  wait on `full`, multiply their share of the window's k-steps (operator values through a per-warp
+//                   cp.async ring straight from L2), and release the slot on its `empty` barrier.
+// (WinCfg: warps per role, CTAs per SM and slots per evaluation mode.)
+// No CTA-wide barrier per window: consumer warps drift apart by up to a window, so one warp's window turn-over
+// (barrier wait, value-ring restart, ragged last batch) hides behind the other warps' DMMAs instead of idling the
+// FP64 pipe for the whole CTA -- in the one-role version of round 1 the k-step bodies ran at pipe speed but made up
+// only 58 % of the time.  Consumers meet (named barrier) only at the end of a tile, to sum their partial accumulators
+// in a fixed order.
 constexpr int kWinMT = 4;
-constexpr int kDescRing = 4;
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -549,187 +561,302 @@ __device__ __forceinline__ void cp_async16z(double* smem_dst, const double* gsrc
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// ---- mbarriers (shared memory, CTA scope)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+// the arrival happens when all cp.async operations this thread has issued so far have landed
+__device__ __forceinline__ void mbar_arrive_on_copies(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
 constexpr int kValSlotBytes = 2048;               // one batch of operator values: 4 k-steps (nt = 2) or 8 (nt = 1)
 constexpr int kValRingBytes = 2 * kValSlotBytes;  // per warp
 
+// the constant rows of the pseudo mode (index nin - 1: 1 for x, 1 or 0 for the second vector), staged like any other
+// row so that every byte of a window arrives through cp.async and one arrive-on-copies covers the slot
+__device__ __align__(16) const double kRowOfOnes[32] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                                          1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+__device__ __align__(16) const double kRowOfZeros[32] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                           0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
 struct WinSmem {
-  double* bufs;      // [2][bufstride] state rows of the current / next window; a finished tile's reduction reuses the current one
-  uint32_t* pairs;   // [2][kWindowMaxKs * 4] packed pair words (first | second << 16) of the current / next window
-  WindowDesc* desc;  // ring of kDescRing descriptors: windows g .. g+3
-  int32_t* modes;    // [2][wpad] mode lists of windows g+1 / g+2
-  char* vring;       // [NW][kValRingBytes] operator values, two batches per warp
-  int wmax, wpad;
+  double* bufs;      // [SLOTS][bufstride] state rows of the window slots
+  uint32_t* pairs;   // [SLOTS][kWindowMaxKs * 4] packed pair words (first | second << 16)
+  double* red;       // reduction buffer of a finished tile (SEPRED), else nullptr: the tile's last slot is reused
+  char* vring;       // [NWC][kValRingBytes] operator values, two batches per consumer warp
+  uint64_t* full;    // [SLOTS] slot filled   (producer threads arrive when their copies have landed)
+  uint64_t* empty;   // [SLOTS] slot released (one arrival per consumer warp)
+  int wmax;
   size_t bufstride;  // doubles
 };
 
-// warps per CTA: two CTAs of 8 warps per SM for one-vector evaluation; the two-vector modes need twice the window
-// buffers, so one CTA of 16 warps shares them
-// NT3 (tiles of three n-tiles, CA_NT3): 24 accumulator doubles per thread need more than 128 registers, so that
-// variant runs one CTA of 8 warps per SM in every mode.
+// One CTA per SM holds TEAMS independent teams of NWC consumer + NWP producer warps; a team works on its own block of
+// 32 states with its own window slots and barriers.  What fits into 227 KB of shared memory and 64 K registers:
+//   one vector  (f):                       two teams of 6 + 2 warps, two window slots of <= 32 KB each -- the teams drift
+//                                          apart, so one's tile reductions and window turn-overs overlap the other's DMMAs
+//   two vectors (Jacobian action, N(x,y)): one team of 12 + 4 warps, two slots of <= 64 KB
+//   packs with three-n-tile tiles (CA_NT3 / the packer's choice at m ~ 3000) carry 24 accumulator doubles per thread:
+//                                          8 + 4 warps at <= 168 registers, as two teams of 4 + 2 for one vector
+// Warp order: all consumers (team by team), then all producers, so that every scheduler (warp % 4) gets the same
+// number of consumer warps -- two CTAs of 6 + 2 warps per SM instead leave two schedulers with half the DMMA work of
+// the other two (measured: 14.1 against 11.4 ms at 999 modes).
+// SLOTS: window slots in flight.  SEPRED: the tile reduction has a buffer of its own and the slot is released before
+// the reduction; otherwise the reduction reuses the tile's last slot.
 template <int MODE, bool NT3 = false>
 struct WinCfg {
-  static constexpr int NW = (MODE == MODE_QUAD || NT3) ? 8 : 16;
-  static constexpr int CTAS = (MODE == MODE_QUAD && !NT3) ? 2 : 1;
+#ifdef CA_WIN_ONE_TEAM  // tuning hook (tools/build_variant.sh)
+  static constexpr int TEAMS = 1;
+#else
+  static constexpr int TEAMS = MODE == MODE_QUAD ? 2 : 1;
+#endif
+  static constexpr int NWC = (NT3 ? 8 : 12) / TEAMS;
+  static constexpr int NWP = 4 / TEAMS;
+  static constexpr int THREADS = TEAMS * (NWC + NWP) * 32;
+  static constexpr int SLOTS = (MODE == MODE_QUAD && TEAMS == 1) ? 3 : 2;
+  static constexpr bool SEPRED = TEAMS == 1 && (MODE == MODE_QUAD || NT3);
+};
+
+struct RingPos {  // position in the ring of window slots: slot index and the parity of its current use
+  int slot = 0;
+  uint32_t phase = 0;
+  template <int SLOTS>
+  __device__ __forceinline__ void next() {
+    if (++slot == SLOTS) {
+      slot = 0;
+      phase ^= 1u;
+    }
+  }
 };
 
 template <int MODE, bool NT3 = false>
 __host__ __device__ inline size_t window_buf_doubles(int wmax) {
   const size_t row = 8 * kWinMT;
   const size_t states = (size_t)(MODE == MODE_QUAD ? 1 : 2) * wmax * row;
-  const size_t red = (size_t)WinCfg<MODE, NT3>::NW * kNtMax * 8 * row;
-  return states > red ? states : red;
+  const size_t red = (size_t)WinCfg<MODE, NT3>::NWC * kNtMax * 8 * row;
+  return WinCfg<MODE, NT3>::SEPRED || states > red ? states : red;
+}
+
+template <int MODE, bool NT3 = false>
+__host__ __device__ inline size_t windowed_team_bytes(int wmax) {  // a multiple of 16
+  using Cfg = WinCfg<MODE, NT3>;
+  return Cfg::SLOTS * (window_buf_doubles<MODE, NT3>(wmax) * sizeof(double) + (size_t)kWindowMaxKs * 4 * sizeof(uint32_t)) +
+         (Cfg::SEPRED ? (size_t)Cfg::NWC * kNtMax * 8 * 8 * kWinMT * sizeof(double) : 0) + (size_t)Cfg::NWC * kValRingBytes +
+         2 * Cfg::SLOTS * sizeof(uint64_t);
 }
 
 template <int MODE, bool NT3 = false>
 __host__ __device__ inline size_t windowed_smem_bytes(int wmax) {
-  const size_t wpad = ((size_t)wmax + 3) & ~(size_t)3;
-  return 2 * window_buf_doubles<MODE, NT3>(wmax) * sizeof(double) + (size_t)2 * kWindowMaxKs * 4 * sizeof(uint32_t) +
-         kDescRing * sizeof(WindowDesc) + 2 * wpad * sizeof(int32_t) + (size_t)WinCfg<MODE, NT3>::NW * kValRingBytes;
+  return WinCfg<MODE, NT3>::TEAMS * windowed_team_bytes<MODE, NT3>(wmax);
 }
 
 template <int MODE, bool NT3 = false>
 __device__ __forceinline__ WinSmem carve_window_smem(double* smem, int wmax) {
   WinSmem S;
   S.wmax = wmax;
-  S.wpad = (wmax + 3) & ~3;
   S.bufstride = window_buf_doubles<MODE, NT3>(wmax);
   S.bufs = smem;
-  S.pairs = reinterpret_cast<uint32_t*>(smem + 2 * S.bufstride);
-  S.desc = reinterpret_cast<WindowDesc*>(S.pairs + (size_t)2 * kWindowMaxKs * 4);
-  S.modes = reinterpret_cast<int32_t*>(S.desc + kDescRing);
-  S.vring = reinterpret_cast<char*>(S.modes + 2 * S.wpad);
+  using Cfg = WinCfg<MODE, NT3>;
+  double* after = smem + Cfg::SLOTS * S.bufstride;
+  S.red = Cfg::SEPRED ? after : nullptr;
+  if (Cfg::SEPRED) after += (size_t)Cfg::NWC * kNtMax * 8 * 8 * kWinMT;
+  S.pairs = reinterpret_cast<uint32_t*>(after);
+  S.vring = reinterpret_cast<char*>(S.pairs + (size_t)Cfg::SLOTS * kWindowMaxKs * 4);
+  S.full = reinterpret_cast<uint64_t*>(S.vring + (size_t)Cfg::NWC * kValRingBytes);
+  S.empty = S.full + Cfg::SLOTS;
   return S;
 }
 
-// Issued by the whole CTA right after the barrier of window g (g == -1: block prologue).
-template <int MODE, bool NT3 = false>
-__device__ __forceinline__ void stage_ahead(int g, int gtotal, const WindowDesc* __restrict__ windows,
-                                            const int32_t* __restrict__ modes, const uint32_t* __restrict__ pairs,
-                                            const WinSmem& S, int one_mode, const double* __restrict__ X,
-                                            const double* __restrict__ Y, int64_t s0, int64_t nstates, int64_t ldx) {
+// ---- producer warps: stage every window of every state block this CTA owns, in consumption order
+template <int MODE, bool NT3>
+__device__ __forceinline__ void window_producer(const WindowDesc* __restrict__ windows, int nwin,
+                                                const int32_t* __restrict__ modes, const uint32_t* __restrict__ pairs,
+                                                const WinSmem& S, int one_mode, const double* __restrict__ X,
+                                                const double* __restrict__ Y, int64_t nstates, int64_t ldx, int team,
+                                                int ptid) {  // ptid: index among the team's producer threads
   constexpr int ROW = 8 * kWinMT;
-  constexpr int NW = WinCfg<MODE, NT3>::NW, NTHR = NW * 32;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (g + 1 < gtotal) {
-    const WindowDesc& W = S.desc[(g + 1) & (kDescRing - 1)];
-    const int nks = W.nks, nmodes = W.nmodes;
-    const char* psrc = reinterpret_cast<const char*>(pairs + (size_t)W.ks_begin * 4);
-    char* pdst = reinterpret_cast<char*>(S.pairs + (size_t)((g + 1) & 1) * kWindowMaxKs * 4);
-    for (int c = tid; c < nks; c += NTHR) cp_async16(pdst + c * 16, psrc + c * 16);  // one k-step = 4 packed pairs = 16 B
-    const int32_t* md = S.modes + ((g + 1) & 1) * S.wpad;
-    double* xb = S.bufs + (size_t)((g + 1) & 1) * S.bufstride;
-    double* yb = xb + (size_t)S.wmax * ROW;
-    // 16-byte copies when the ensemble allows it (even leading dimension, 16-byte aligned base): a warp instruction
-    // then moves TWO state rows (32 states = 256 B each; lane = row half, pair of states) -- half the staging
-    // instructions of the 8-byte form, which remains for odd leading dimensions
-    const bool wide = ((ldx & 1) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
-                      (MODE == MODE_QUAD || (reinterpret_cast<uintptr_t>(Y) & 15) == 0);
-    if (wide) {
-      const int h2 = 2 * (lane & 15), sub = lane >> 4;
-      const int64_t s = s0 + h2;
-      const int nbytes = s + 1 < nstates ? 16 : (s < nstates ? 8 : 0);
-      const double* xg = X + (nbytes ? s : 0);
-      const double* yg = MODE == MODE_QUAD ? nullptr : Y + (nbytes ? s : 0);
-#pragma unroll 4
-      for (int l = 2 * warp + sub; l < nmodes; l += 2 * NW) {
-        const int gm = md[l];
-        const int slot = l * ROW + (h2 ^ swz<kWinMT>(l));  // the swizzle flips bits 2-3 of the state: pairs stay adjacent
-        if (gm == one_mode) {
-          xb[slot] = xb[slot + 1] = 1.0;
-          if (MODE != MODE_QUAD) yb[slot] = yb[slot + 1] = MODE == MODE_JVP ? 0.0 : 1.0;
+  constexpr int NWP = WinCfg<MODE, NT3>::NWP, NPT = NWP * 32, TEAMS = WinCfg<MODE, NT3>::TEAMS;
+  const int pwarp = ptid >> 5, lane = ptid & 31;
+  const int64_t nblocks = (nstates + ROW - 1) / ROW;
+  // 16-byte copies when the ensemble allows it (even leading dimension, 16-byte aligned base): a warp instruction
+  // then moves TWO state rows (32 states = 256 B each; lane = row half, pair of states) -- half the staging
+  // instructions of the 8-byte form, which remains for odd leading dimensions
+  const bool wide = ((ldx & 1) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
+                    (MODE == MODE_QUAD || (reinterpret_cast<uintptr_t>(Y) & 15) == 0);
+  const int h2 = 2 * (lane & 15), sub = lane >> 4;
+  const double* const one_y = MODE == MODE_JVP ? kRowOfZeros : kRowOfOnes;
+  RingPos pos;
+  for (int64_t blk = (int64_t)blockIdx.x * TEAMS + team; blk < nblocks; blk += (int64_t)gridDim.x * TEAMS) {
+    const int64_t s0 = blk * ROW;
+    // this lane's piece of a state row: byte count inside the ensemble (0: beyond the last state -> zero fill)
+    const int64_t sw = s0 + h2;
+    const int nbytes_w = sw + 1 < nstates ? 16 : (sw < nstates ? 8 : 0);
+    const int nbytes_n = s0 + lane < nstates ? 8 : 0;
+    const int64_t soff = wide ? (nbytes_w ? sw : 0) : (nbytes_n ? s0 + lane : 0);
+    const int coff = wide ? h2 : lane;  // the same piece of a constant row
+    for (int g = 0; g < nwin; ++g, pos.next<WinCfg<MODE, NT3>::SLOTS>()) {
+      const WindowDesc* W = windows + g;
+      const int nks = __ldg(&W->nks), nmodes = __ldg(&W->nmodes);
+      const int32_t* mp = modes + __ldg(&W->modes_off);
+      const char* psrc = reinterpret_cast<const char*>(pairs + (size_t)__ldg(&W->ks_begin) * 4);
+      int mch[8];  // the window's mode list, 32 per register (wmax <= 256: pair words hold 8-bit local rows)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mch[j] = j * 32 + lane < nmodes ? __ldg(mp + j * 32 + lane) : 0;
+      const int slot = pos.slot;
+      mbar_wait(&S.empty[slot], pos.phase ^ 1u);  // the consumers are done with the slot's previous window
+      char* pdst = reinterpret_cast<char*>(S.pairs + (size_t)slot * kWindowMaxKs * 4);
+      for (int c = ptid; c < nks; c += NPT) cp_async16(pdst + c * 16, psrc + c * 16);  // one k-step = 4 packed pairs = 16 B
+      double* xb = S.bufs + (size_t)slot * S.bufstride;
+      double* yb = xb + (size_t)S.wmax * ROW;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j * 32 >= nmodes) break;
+        if (wide) {
+#pragma unroll
+          for (int r = 2 * pwarp + sub; r < 32; r += 2 * NWP) {
+            const int gm = __shfl_sync(0xffffffffu, mch[j], r);
+            const int l = j * 32 + r;
+            if (l < nmodes) {
+              const int slotw = l * ROW + (h2 ^ swz<kWinMT>(l));  // the swizzle flips bits 2-3 of the state: pairs stay adjacent
+              const bool one = gm == one_mode;
+              const int64_t off = ldx * (int64_t)gm + soff;
+              cp_async16z(xb + slotw, one ? kRowOfOnes + coff : X + off, one ? 16 : nbytes_w);
+              if (MODE != MODE_QUAD) cp_async16z(yb + slotw, one ? one_y + coff : Y + off, one ? 16 : nbytes_w);
+            }
+          }
         } else {
-          const int64_t off = ldx * (int64_t)gm;
-          cp_async16z(xb + slot, xg + off, nbytes);
-          if (MODE != MODE_QUAD) cp_async16z(yb + slot, yg + off, nbytes);
+#pragma unroll
+          for (int r = pwarp; r < 32; r += NWP) {
+            const int gm = __shfl_sync(0xffffffffu, mch[j], r);
+            const int l = j * 32 + r;
+            if (l < nmodes) {
+              const int slotn = l * ROW + (lane ^ swz<kWinMT>(l));
+              const bool one = gm == one_mode;
+              const int64_t off = ldx * (int64_t)gm + soff;
+              cp_async8(xb + slotn, one ? kRowOfOnes + coff : X + off, one ? 8 : nbytes_n);
+              if (MODE != MODE_QUAD) cp_async8(yb + slotn, one ? one_y + coff : Y + off, one ? 8 : nbytes_n);
+            }
+          }
         }
       }
-    } else {
-      // one state row per warp instruction; the lane is the state
-      const bool ok = s0 + lane < nstates;
-      const double* xg = X + (ok ? s0 + lane : 0);
-      const double* yg = MODE == MODE_QUAD ? nullptr : Y + (ok ? s0 + lane : 0);
-#pragma unroll 4
-      for (int l = warp; l < nmodes; l += NW) {
-        const int gm = md[l];
-        const int slot = l * ROW + (lane ^ swz<kWinMT>(l));
-        if (gm == one_mode) {
-          xb[slot] = 1.0;
-          if (MODE != MODE_QUAD) yb[slot] = MODE == MODE_JVP ? 0.0 : 1.0;
-        } else {
-          const int64_t off = ldx * (int64_t)gm;
-          cp_async8(xb + slot, xg + off, ok ? 8 : 0);
-          if (MODE != MODE_QUAD) cp_async8(yb + slot, yg + off, ok ? 8 : 0);
-        }
-      }
+      mbar_arrive_on_copies(&S.full[slot]);
     }
   }
-  if (g + 2 < gtotal) {
-    const WindowDesc& W2 = S.desc[(g + 2) & (kDescRing - 1)];
-    const int nmodes = W2.nmodes;
-    const int32_t* src = modes + W2.modes_off;
-    int32_t* md = S.modes + ((g + 2) & 1) * S.wpad;
-    for (int l = tid; l < nmodes; l += NTHR) cp_async4(md + l, src + l);
-  }
-  if (g + 3 < gtotal && tid < (int)(sizeof(WindowDesc) / 16))
-    cp_async16(reinterpret_cast<char*>(S.desc + ((g + 3) & (kDescRing - 1))) + tid * 16,
-               reinterpret_cast<const char*>(windows + g + 3) + tid * 16);
-  cp_async_commit();
+  cp_async_wait_all();
 }
 
-// Operator values of a warp's share of a window go through a two-slot ring in shared memory, one cp.async group per
-// batch: ptxas keeps LDGSTS / commit / wait in program order, whereas plain register prefetch loads (having no
+// Operator values of a warp's shares go through a two-slot ring in shared memory, one cp.async group per batch of KB
+// k-steps: ptxas keeps LDGSTS / commit / wait in program order, whereas plain register prefetch loads (having no
 // consumer inside the unrolled body) get sunk to the end of the body, right in front of their use.
-template <int NT, int NW>
+// The ring runs ACROSS windows: while the last two batches of a share are multiplied, the first two of the warp's share
+// of the next window are already on their way, so a window turn-over does not expose the L2 / HBM latency.
+// Group accounting: exactly one group is committed per multiplied batch (real or empty), and `advance` tops the new
+// share up to two; hence at the top of batch b the two newest groups are (batch b, batch b + 1) and
+// cp.async.wait_group 1 means "batch b has landed".
+template <int NT>
 struct ValRing {
-  static constexpr int KB = kValSlotBytes / (NT * 256);  // k-steps per batch
-  char* ring;       // this warp's kValRingBytes
-  const char* src;  // the share's first value
-  int n;            // k-steps in the share
+  static constexpr int KB = kValSlotBytes / (NT * 256);      // k-steps per batch
+  static constexpr int kBatchBytes = KB * NT * 256;          // 2048 (NT = 1, 2) or 1536 (NT = 3)
+  static constexpr int kCopies = (kBatchBytes + 511) / 512;  // 16-byte copies per lane and full batch
+  const char* ring;     // this warp's kValRingBytes
+  uint32_t dst_lane;    // shared-memory address of this lane's first 16 bytes in slot 0
+  uint32_t par;         // slot of batch 0 of the current share
+  const char* cur_src;  // this lane's first 16 bytes of the current share
+  int cur_n;            // its k-steps
+  const char* nxt_src;  // the warp's share of the next window (nxt_n < 0: not known)
+  int nxt_n, nxt_issued;
 
-  static constexpr int kBatchBytes = KB * NT * 256;                 // 2048 (NT = 1, 2) or 1536 (NT = 3)
-  static constexpr int kCopies = (kBatchBytes + 511) / 512;         // 16-byte copies per lane and full batch
-  uint32_t dst_lane;     // shared-memory address of this lane's first 16 bytes in slot 0
-  const char* src_lane;  // this lane's first 16 bytes of the share
-
-  __device__ __forceinline__ void issue(int b, int lane) const {
-    const int left = n - b * KB;  // k-steps from batch b on; <= 0 past the end: an empty group keeps the count uniform
+  __device__ __forceinline__ void init(char* ring_, int lane) {
+    ring = ring_;
+    dst_lane = (uint32_t)__cvta_generic_to_shared(ring_) + lane * 16;
+    par = 0;
+    cur_src = nxt_src = nullptr;
+    cur_n = 0;
+    nxt_n = -1;
+    nxt_issued = 0;
+  }
+  __device__ __forceinline__ void copy_batch(const char* src_lane, int n, int b, uint32_t slot, int lane) const {
+    const int left = n - b * KB;  // k-steps from batch b on (> 0)
     const char* s = src_lane + (size_t)b * kBatchBytes;
-    const uint32_t d = dst_lane + (b & 1) * kValSlotBytes;
+    const uint32_t d = dst_lane + (slot & 1) * kValSlotBytes;
     if (left >= KB) {  // (warp-uniform) a full batch: constant offsets, no per-copy predicate
 #pragma unroll
       for (int c = 0; c < kCopies; ++c)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + c * 512), "l"(s + c * 512) : "memory");
-    } else if (left > 0) {
+    } else {
       const int bytes = left * (NT * 256) - lane * 16;
 #pragma unroll
       for (int c = 0; c < kCopies; ++c)
         if (c * 512 < bytes) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + c * 512), "l"(s + c * 512) : "memory");
     }
-    cp_async_commit();
   }
-  // batches 0 and 1 of this warp's share of a window; issued before the previous window's barrier
-  __device__ __forceinline__ void begin(const double* __restrict__ vals0, int nks, int warp, int lane) {
-    int k0, k1;
-    warp_share<NW>(nks, warp, k0, k1);
-    n = k1 - k0;
-    src = reinterpret_cast<const char*>(vals0 + (size_t)k0 * NT * 32);
-    src_lane = src + lane * 16;
-    dst_lane = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;
-    __syncwarp();  // every lane is done reading the previous share's slots
-    issue(0, lane);
-    issue(1, lane);
+  // share [k0, k1) of the window whose values start at vals0 comes after the current one
+  __device__ __forceinline__ void set_next(const double* __restrict__ vals0, int k0, int k1, int lane) {
+    nxt_src = reinterpret_cast<const char*>(vals0 + (size_t)k0 * NT * 32) + lane * 16;
+    nxt_n = k1 - k0;
+    nxt_issued = 0;
+  }
+  // the next share becomes the current one; afterwards its batches 0 and 1 are the two newest groups
+  __device__ __forceinline__ void advance(int lane) {
+    par = (par + (uint32_t)((cur_n + KB - 1) / KB)) & 1u;
+    cur_src = nxt_src;
+    cur_n = nxt_n > 0 ? nxt_n : 0;
+    const int have = nxt_issued;
+    nxt_n = -1;
+    nxt_issued = 0;
+    __syncwarp();  // every lane is done reading the finished share's slots
+    for (int j = have; j < 2; ++j) {
+      if (j * KB < cur_n) copy_batch(cur_src, cur_n, j, par + j, lane);
+      cp_async_commit();
+    }
+  }
+  // after batch b of the current share has been multiplied: batch b + 2, or else the next share's next batch
+  __device__ __forceinline__ void issue_after(int b, int lane) {
+    const int q = b + 2;
+    if (q * KB < cur_n) {
+      copy_batch(cur_src, cur_n, q, par + q, lane);
+#ifdef CA_WIN_RING_CONTINUOUS  // tuning hook (measured 2 % slower than restarting the ring at every window)
+    } else if (nxt_issued < 2 && nxt_issued * KB < nxt_n) {
+      copy_batch(nxt_src, nxt_n, nxt_issued, par + (uint32_t)((cur_n + KB - 1) / KB) + nxt_issued, lane);
+      ++nxt_issued;
+#endif
+    }
+    cp_async_commit();
   }
 };
 
-// ps: the window's pair words in shared memory
-template <int MT, int NT, int MODE, bool NT3 = false>
-__device__ __forceinline__ void window_accumulate(const uint32_t* ps, int nks, const double* xs, const double* ys,
-                                                  int warp, int lane, const ValRing<NT, WinCfg<MODE, NT3>::NW>& vr,
-                                                  double (&acc)[MT][NT][2]) {
-  constexpr int KB = ValRing<NT, WinCfg<MODE, NT3>::NW>::KB;
+// The share of consumer warp `warp` (of NW) of window g (nks k-steps): whole batches of KB k-steps, so that only the
+// last share can end on a ragged batch (the slow, not unrolled path); which warp takes which part rotates with g.
+// (Tried and dropped: uneven shares in the first / last window of a tile, to spread the warps' window turn-overs in
+// time -- no gain once the one-vector mode runs two teams, and a loss combined with the rotation.)
+template <int KB, int NW>
+__device__ __forceinline__ void batch_share(int nks, int warp, int g, int& k0, int& k1) {
+  const int nb = (nks + KB - 1) / KB;
+  const int share = (warp + g) % NW;
+  k0 = min(nks, (nb * share / NW) * KB);
+  k1 = min(nks, (nb * (share + 1) / NW) * KB);
+}
+
+// ps: the window's pair words in shared memory; [k0, k1): this warp's k-steps (the current share of vr)
+template <int MT, int NT, int MODE>
+__device__ __forceinline__ void window_accumulate(const uint32_t* ps, int k0, int k1, const double* xs, const double* ys,
+                                                  int lane, ValRing<NT>& vr, double (&acc)[MT][NT][2]) {
+  constexpr int KB = ValRing<NT>::KB;
   const uint32_t r8 = 8u * (lane >> 2);
-  int k0, k1;
-  warp_share<WinCfg<MODE, NT3>::NW>(nks, warp, k0, k1);
   const int n = k1 - k0;
   if (n <= 0) return;
   const uint32_t* pp = ps + (size_t)k0 * 4 + (lane & 3);
@@ -750,11 +877,9 @@ __device__ __forceinline__ void window_accumulate(const uint32_t* ps, int nks, c
   };
   const int nb = (n + KB - 1) / KB;
   for (int b = 0; b < nb; ++b) {
-    if (b >= 2) {  // batches 0 and 1 landed before the window's barrier
-      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-      __syncwarp();
-    }
-    const char* slot = vb + (b & 1) * kValSlotBytes;
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // batch b has landed (see ValRing)
+    __syncwarp();
+    const char* slot = vb + ((vr.par + b) & 1) * kValSlotBytes;
     const int cnt = min(KB, n - b * KB);
     if (cnt == KB) {
 #pragma unroll
@@ -763,88 +888,125 @@ __device__ __forceinline__ void window_accumulate(const uint32_t* ps, int nks, c
       for (int kk = 0; kk < cnt; ++kk) step(b * KB + kk, slot, kk);
     }
     __syncwarp();  // the slot is refilled now
-    vr.issue(b + 2, lane);
+    vr.issue_after(b, lane);
   }
 }
 
-// windows [gb, ge) all belong to tiles with NT n-tiles; gtotal = number of windows of the operator
-template <int NT, int MODE, bool NT3 = false>
-__device__ __forceinline__ void run_windows(const WindowDesc* __restrict__ windows, int gb, int ge, int gtotal,
-                                            const int32_t* __restrict__ modes, const uint32_t* __restrict__ pairs,
+// Consumer side of windows [gb, ge), all of tiles with NT n-tiles.  // (`pos`: the ring position, advanced in step with the producers').  Window descriptors are read from global
+// memory two windows ahead, one 4-byte word per lane, and broadcast by shuffles when their turn comes.
+template <int NT, int MODE, bool NT3>
+__device__ __forceinline__ void run_windows(const WindowDesc* __restrict__ windows, int gb, int ge,
                                             const double* __restrict__ vals, const int32_t* __restrict__ rows,
-                                            const WinSmem& S, int one_mode, int warp, int lane,
-                                            const double* __restrict__ X, const double* __restrict__ Y, int64_t s0,
-                                            int64_t nstates, int64_t ldx, double* __restrict__ OUT, int64_t ldo) {
-  constexpr int MT = kWinMT, ROW = 8 * MT;
+                                            const WinSmem& S, RingPos& pos, int warp, int lane, int64_t s0,
+                                            int64_t nstates, double* __restrict__ OUT, int64_t ldo, int bar_id) {
+  constexpr int MT = kWinMT, ROW = 8 * MT, NWC = WinCfg<MODE, NT3>::NWC, KB = ValRing<NT>::KB;
+  constexpr int kWords = sizeof(WindowDesc) / 4;
   if (gb >= ge) return;
-  ValRing<NT, WinCfg<MODE, NT3>::NW> vr;
-  vr.ring = S.vring + warp * kValRingBytes;
+  auto desc_word = [&](int g) -> int {
+    return (g < ge && lane < kWords) ? __ldg(reinterpret_cast<const int*>(windows + g) + lane) : 0;
+  };
+  auto field = [&](int dw, int word) -> int { return __shfl_sync(0xffffffffu, dw, word); };
+  ValRing<NT> vr;
+  vr.init(S.vring + warp * kValRingBytes, lane);
   double acc[MT][NT][2];
-  {
-    const WindowDesc& W0 = S.desc[gb & (kDescRing - 1)];
-    vr.begin(vals + W0.vals_off, W0.nks, warp, lane);
-  }
+  int dw_n = desc_word(gb);  // descriptor of the window after the current one (here: of the first)
+  int k0 = 0, k1 = 0, last = 0, rows_off = 0;
+  // window g, described by dw_n: this warp's share of it becomes vr's next share
+  auto take_next = [&](int g) {
+    const int nks = field(dw_n, 1);
+    const int64_t vals_off = (int64_t)(uint32_t)field(dw_n, 8) | ((int64_t)field(dw_n, 9) << 32);
+    last = field(dw_n, 5);
+    rows_off = field(dw_n, 6);
+    batch_share<KB, NWC>(nks, warp, g, k0, k1);
+    vr.set_next(vals + vals_off, k0, k1, lane);
+  };
+  take_next(gb);
+  vr.advance(lane);
+  dw_n = desc_word(gb + 1);
   bool fresh = true;
-  for (int g = gb; g < ge; ++g) {
-    cp_async_wait_all();
-    __syncthreads();  // window g (+ mode list g+1, descriptor g+2) has landed; window g-1's buffers are free
-    stage_ahead<MODE, NT3>(g, gtotal, windows, modes, pairs, S, one_mode, X, Y, s0, nstates, ldx);
+  for (int g = gb; g < ge; ++g, pos.next<WinCfg<MODE, NT3>::SLOTS>()) {
+    const int dw_nn = desc_word(g + 2);  // in flight during this window
+    const int k0c = k0, k1c = k1, rows_off_c = rows_off;
+    const bool last_c = last != 0;
+    const int slot = pos.slot;
+    mbar_wait(&S.full[slot], pos.phase);
     if (fresh) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
     }
-    const WindowDesc& W = S.desc[g & (kDescRing - 1)];
-    const int nks = W.nks, rows_off = W.rows_off;
-    const bool last = W.last != 0;
-    double* cur = S.bufs + (size_t)(g & 1) * S.bufstride;
+    double* cur = S.bufs + (size_t)slot * S.bufstride;
     const double* xs = cur;
     const double* ys = MODE == MODE_QUAD ? xs : xs + (size_t)S.wmax * ROW;
-    window_accumulate<MT, NT, MODE, NT3>(S.pairs + (size_t)(g & 1) * kWindowMaxKs * 4, nks, xs, ys, warp, lane, vr, acc);
+    window_accumulate<MT, NT, MODE>(S.pairs + (size_t)slot * kWindowMaxKs * 4, k0c, k1c, xs, ys, lane, vr, acc);
+    // only now: the next window's share in registers across the k-steps costs the Jacobian action (at its 128
+    // registers) 4 % at 999 modes and 9 % at 2962
     if (g + 1 < ge) {
-      const WindowDesc& Wn = S.desc[(g + 1) & (kDescRing - 1)];
-      vr.begin(vals + Wn.vals_off, Wn.nks, warp, lane);
+      take_next(g + 1);  // k0, k1, last, rows_off now describe window g + 1
+      vr.advance(lane);
     }
-    // the reduction buffer is the finished window's state buffer: its first barrier frees it, and the next
-    // window's barrier comes before anything is staged into it again
-    if (last) tile_reduce_store<MT, NT, WinCfg<MODE, NT3>::NW>(rows_off, rows, cur, acc, warp, lane, s0, nstates, OUT, ldo);
-    fresh = last;
+    if constexpr (WinCfg<MODE, NT3>::SEPRED) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.empty[slot]);
+      if (last_c) tile_reduce_store<MT, NT, NWC, true>(rows_off_c, rows, S.red, acc, warp, lane, s0, nstates, OUT, ldo, bar_id);
+    } else {
+      // the reduction buffer is the finished window's slot: the consumers' barrier inside frees it of readers, and it
+      // is released to the producers only after the sums
+      if (last_c) tile_reduce_store<MT, NT, NWC, true>(rows_off_c, rows, cur, acc, warp, lane, s0, nstates, OUT, ldo, bar_id);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.empty[slot]);
+    }
+    fresh = last_c;
+    dw_n = dw_nn;
   }
 }
 
 // NT3: the pack has tiles of three n-tiles (CA_NT3); a separate instantiation, so that the register allocation of the
 // two-n-tile kernel does not change with it
 template <int MODE, bool NT3>
-__global__ void __launch_bounds__(WinCfg<MODE, NT3>::NW * 32, WinCfg<MODE, NT3>::CTAS)
+__global__ void __launch_bounds__(WinCfg<MODE, NT3>::THREADS, 1)
 bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, int nwin, int nwin_nt3, int nwin_nt2,
                          const int32_t* __restrict__ modes, const uint32_t* __restrict__ pairs,
                          const double* __restrict__ vals, const int32_t* __restrict__ rows, int wmax, int one_mode,
                          const double* __restrict__ X, const double* __restrict__ Y, int64_t nstates, int64_t ldx,
                          double* __restrict__ OUT, int64_t ldo) {
   constexpr int ROW = 8 * kWinMT;
+  using Cfg = WinCfg<MODE, NT3>;
+  constexpr int NWC = Cfg::NWC, NWP = Cfg::NWP, TEAMS = Cfg::TEAMS;
   extern __shared__ __align__(16) double smem[];
-  const WinSmem S = carve_window_smem<MODE, NT3>(smem, wmax);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t nblocks = (nstates + ROW - 1) / ROW;
   if (nwin <= 0) return;
-  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+  const size_t team_doubles = windowed_team_bytes<MODE, NT3>(wmax) / sizeof(double);
+  if (tid == 0) {
+    for (int t = 0; t < TEAMS; ++t) {
+      const WinSmem St = carve_window_smem<MODE, NT3>(smem + t * team_doubles, wmax);
+      for (int q = 0; q < Cfg::SLOTS; ++q) {
+        mbar_init(&St.full[q], NWP * 32);
+        mbar_init(&St.empty[q], NWC);
+      }
+    }
+  }
+  __syncthreads();  // the only CTA-wide barrier
+  const bool producer = warp >= TEAMS * NWC;
+  const int team = producer ? (warp - TEAMS * NWC) / NWP : warp / NWC;
+  const WinSmem S = carve_window_smem<MODE, NT3>(smem + team * team_doubles, wmax);
+  if (producer) {
+    window_producer<MODE, NT3>(windows, nwin, modes, pairs, S, one_mode, X, Y, nstates, ldx, team,
+                               tid - (TEAMS * NWC + team * NWP) * 32);
+    return;
+  }
+  const int cwarp = warp - team * NWC;  // consumer warp within the team
+  const int64_t nblocks = (nstates + ROW - 1) / ROW;
+  RingPos pos;
+  for (int64_t blk = (int64_t)blockIdx.x * TEAMS + team; blk < nblocks; blk += (int64_t)gridDim.x * TEAMS) {
     const int64_t s0 = blk * ROW;
-    __syncthreads();  // the previous block's last window and reduction are finished
-    constexpr int kDescWords = sizeof(WindowDesc) / 4;
-    if (tid < 2 * kDescWords && tid / kDescWords < nwin)  // descriptors 0 and 1 directly
-      reinterpret_cast<uint32_t*>(S.desc)[tid] = __ldg(reinterpret_cast<const uint32_t*>(windows) + tid);
-    __syncthreads();
-    for (int l = tid; l < S.desc[0].nmodes; l += WinCfg<MODE, NT3>::NW * 32) S.modes[l] = __ldg(modes + S.desc[0].modes_off + l);
-    __syncthreads();
-    stage_ahead<MODE, NT3>(-1, nwin, windows, modes, pairs, S, one_mode, X, Y, s0, nstates, ldx);
     if constexpr (NT3)
-      run_windows<3, MODE, NT3>(windows, 0, nwin_nt3, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane, X, Y, s0,
-                           nstates, ldx, OUT, ldo);
-    run_windows<2, MODE, NT3>(windows, nwin_nt3, nwin_nt3 + nwin_nt2, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane,
-                         X, Y, s0, nstates, ldx, OUT, ldo);
-    run_windows<1, MODE, NT3>(windows, nwin_nt3 + nwin_nt2, nwin, nwin, modes, pairs, vals, rows, S, one_mode, warp, lane, X, Y,
-                         s0, nstates, ldx, OUT, ldo);
+      run_windows<3, MODE, NT3>(windows, 0, nwin_nt3, vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo, 1 + team);
+    run_windows<2, MODE, NT3>(windows, nwin_nt3, nwin_nt3 + nwin_nt2, vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo,
+                              1 + team);
+    run_windows<1, MODE, NT3>(windows, nwin_nt3 + nwin_nt2, nwin, vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo,
+                              1 + team);
   }
 }
 

@@ -725,15 +725,20 @@ PackedHost finalize_pack(PackedHost P, std::vector<PackedHost>& parts, const std
   }
   P.tiles = std::move(sorted);
   if (window_modes > 0 && getenv("CA_TIMING")) {
-    int64_t ks = 0, md = 0, small = 0;
+    int64_t ks = 0, md = 0;
+    int64_t hist[5] = {0, 0, 0, 0, 0}, hks[5] = {0, 0, 0, 0, 0};  // windows / k-steps by window length: < 64, < 128, < 256, < 384, more
     for (const WindowDesc& W : P.windows) {
       ks += W.nks;
       md += W.nmodes;
-      small += W.nks < 64;
+      const int b = W.nks < 64 ? 0 : W.nks < 128 ? 1 : W.nks < 256 ? 2 : W.nks < 384 ? 3 : 4;
+      hist[b]++;
+      hks[b] += W.nks;
     }
     const double n = std::max<double>(1.0, (double)P.windows.size());
-    fprintf(stderr, "[ca timing] pack_terms: %zu tiles, %zu windows, %.1f k-steps and %.1f modes per window, %lld windows < 64 k-steps\n",
-            P.tiles.size(), P.windows.size(), ks / n, md / n, (long long)small);
+    fprintf(stderr, "[ca timing] pack_terms: %zu tiles, %zu windows, %.1f k-steps and %.1f modes per window; windows (k-steps) by length "
+            "< 64: %lld (%lld), < 128: %lld (%lld), < 256: %lld (%lld), < 384: %lld (%lld), more: %lld (%lld)\n",
+            P.tiles.size(), P.windows.size(), ks / n, md / n, (long long)hist[0], (long long)hks[0], (long long)hist[1], (long long)hks[1],
+            (long long)hist[2], (long long)hks[2], (long long)hist[3], (long long)hks[3], (long long)hist[4], (long long)hks[4]);
   }
   {  // LPT schedule of whole tiles onto 8 warps (weight = DMMAs per state tile)
     std::vector<int32_t> idx(P.tiles.size());
