@@ -386,6 +386,13 @@ struct DenseCfgT {
 };
 using DenseWide = DenseCfgT<8, 12>;
 using DenseTwin = DenseCfgT<4, 8>;
+// DenseRing: 128 x 128 tile, 16 warps, one CTA per SM, chunks of 8 points in a THREE-stage ring with one mbarrier per
+// stage instead of a CTA barrier per chunk (dense_contract_ring_kernel)
+struct DenseRing : DenseCfgT<8, 8> {
+  static constexpr int Stages = 3;
+  static constexpr size_t StageDoubles = (size_t)Kc * kDI + (size_t)Kc * Bld + J * Q * 3 + kDK * Q * 9;
+  static constexpr size_t SmemDoubles = Stages * StageDoubles + Stages;  // + the mbarriers
+};
 
 struct DenseTables {
   int m, mpad, nq, nchunks;
@@ -561,6 +568,161 @@ dense_contract_kernel(DenseTables T, int it0, int njt, double* __restrict__ Nd /
     asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();  // A(chunk+1), tables(chunk+2), B(chunk+1) published; everyone is done with A(chunk), B(chunk)
   }
+  // epilogue: N = -C into the dense slab
+  const int m = T.m;
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    const int i = it * kDI + wi * 32 + mt * 8 + r;
+    if (i >= m || i < row0 || i >= row1) continue;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ocol = wc * 32 + nt * 8 + 2 * c + e;
+        const int j = j0 + ocol / kDK, k = k0 + ocol % kDK;
+        if (j < m && k < m) Nd[((size_t)(i - row0) * m + j) * m + k] = -acc[mt][nt][e];
+      }
+  }
+}
+
+// The same contraction without a CTA barrier in the loop.  In the two-buffer kernel above every chunk ends in a
+// __syncthreads (B(c+1) is written by all threads and read by all warps): ncu put 9 % of the warp time into that
+// barrier, with the DMMA pipe 84.6 % busy.  Here the operands live in a ring of three stages with one mbarrier each:
+//   during chunk c a thread  issues the cp.async of A(c+1) and of the tables of chunk c+2 (arrival on barrier (c+1)
+//                            when those copies have landed: cp.async.mbarrier.arrive.noinc),
+//                            generates its values of B(c+1) in the FIRST HALF of the chunk's k-steps and then arrives
+//                            on barrier (c+1) (release), and multiplies A(c), B(c) in all k-steps;
+//   before chunk c+1         it waits on barrier (c+1) -- which needs every thread past the MIDDLE of chunk c only, so
+//                            warps may drift by half a chunk without anyone waiting.
+// Stage (c+1) mod 3 held chunk c-2: a thread that has passed barrier (c) knows that everyone is past the middle of
+// chunk c-1, hence done reading chunk c-2.
+__device__ __forceinline__ void dense_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void dense_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void dense_mbar_arrive_on_copies(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void dense_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(a), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+
+__global__ void __launch_bounds__(DenseRing::Threads, 1)
+dense_contract_ring_kernel(DenseTables T, int it0, int njt, double* __restrict__ Nd /* [rows][m][m] */, int row0, int row1) {
+  using Cfg = DenseRing;
+  constexpr int kDJ = Cfg::J, kDQ = Cfg::Q, kDKc = Cfg::Kc, kDCols = Cfg::Cols, kDThreads = Cfg::Threads, kDBld = Cfg::Bld;
+  constexpr int KS = Cfg::KS, NS = Cfg::Stages, kHalf = KS / 2;  // k-steps per chunk; generation happens in the first kHalf
+  static_assert(KS % 2 == 0 && (KS / kHalf) * kHalf == KS, "values per generating k-step");
+  constexpr int kPer = KS / kHalf;  // B values a thread generates per k-step of the first half
+  extern __shared__ __align__(16) double sm[];
+  double* Abuf = sm;                                 // [NS][KS][128 rows][4]
+  double* Bbuf = Abuf + NS * (kDKc * kDI);           // [NS][Kc][Bld]
+  double* Utb = Bbuf + NS * (kDKc * kDBld);          // [NS][Q][3 a][J modes]
+  double* Gtb = Utb + NS * (kDJ * kDQ * 3);          // [NS][Q][9 (a*3+c)][16 modes]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Gtb + NS * (kDK * kDQ * 9));  // [NS]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = lane >> 2, c = lane & 3;
+  const int it = it0 + blockIdx.y;
+  const int jt = blockIdx.x % njt, kt = blockIdx.x / njt;
+  const int j0 = jt * kDJ, k0 = kt * kDK;
+  const int wi = warp / Cfg::WC, wc = warp % Cfg::WC;
+  const int nchunks = T.nchunks;
+
+  auto stage_A = [&](int chunk) {
+    const double* src = T.A + ((size_t)it * nchunks + chunk) * (kDKc * kDI);
+    double* dst = Abuf + (chunk % NS) * (kDKc * kDI);
+    for (int e = tid; e < kDKc * kDI / 2; e += kDThreads) cp_async16(dst + 2 * e, src + 2 * e);
+  };
+  auto stage_tables = [&](int chunk) {
+    const double* usrc = T.U + ((size_t)jt * nchunks + chunk) * (kDJ * kDQ * 3);
+    for (int e = tid; e < kDJ * kDQ * 3 / 2; e += kDThreads) cp_async16(Utb + (chunk % NS) * (kDJ * kDQ * 3) + 2 * e, usrc + 2 * e);
+    const double* gsrc = T.G9 + ((size_t)kt * nchunks + chunk) * (kDK * kDQ * 9);
+    for (int e = tid; e < kDK * kDQ * 9 / 2; e += kDThreads) cp_async16(Gtb + (chunk % NS) * (kDK * kDQ * 9) + 2 * e, gsrc + 2 * e);
+  };
+  const int col = tid % kDCols, kg = tid / kDCols;
+  const int jj = col / kDK, kk = col % kDK;
+  auto generate = [&](int stage, int step, double& u0, double& u1, double& u2) {
+    const int q = kg * (KS / 3) + step / 3, cc = step % 3;
+    const double* u = Utb + stage * (kDJ * kDQ * 3) + jj;
+    const double* g = Gtb + stage * (kDK * kDQ * 9) + kk;
+    if (cc == 0) {
+      u0 = u[(q * 3) * kDJ];
+      u1 = u[(q * 3 + 1) * kDJ];
+      u2 = u[(q * 3 + 2) * kDJ];
+    }
+    const double v = u0 * g[(q * 9 + cc) * kDK] + u1 * g[(q * 9 + 3 + cc) * kDK] + u2 * g[(q * 9 + 6 + cc) * kDK];
+    Bbuf[stage * (kDKc * kDBld) + (kg * KS + step) * kDBld + col] = v;
+  };
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  // prologue: barriers; tables(0) and A(0); then tables(1) in flight while B(0) is generated in full; all of it
+  // arrives on barrier 0
+  if (tid == 0)
+    for (int s = 0; s < NS; ++s) dense_mbar_init(&bar[s], 2 * kDThreads);  // per thread: its copies and its B values
+  stage_tables(0);
+  stage_A(0);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  __syncthreads();
+  if (nchunks > 1) stage_tables(1);
+  dense_mbar_arrive_on_copies(&bar[0]);
+  {
+    double u0 = 0, u1 = 0, u2 = 0;
+#pragma unroll
+    for (int step = 0; step < KS; ++step) generate(0, step, u0, u1, u2);
+  }
+  dense_mbar_arrive(&bar[0]);
+
+  int stage = 0;        // chunk % NS
+  uint32_t parity = 0;  // (chunk / NS) & 1
+  for (int chunk = 0; chunk < nchunks; ++chunk) {
+    dense_mbar_wait(&bar[stage], parity);  // A(chunk), B(chunk), tables(chunk+1) are in shared memory and visible
+    const int nstage = stage + 1 == NS ? 0 : stage + 1;
+    if (chunk + 1 < nchunks) stage_A(chunk + 1);       // into the stage chunk-2 has left
+    if (chunk + 2 < nchunks) stage_tables(chunk + 2);  // into the stage whose tables (of chunk-1) were last read in chunk-2
+    dense_mbar_arrive_on_copies(&bar[nstage]);
+    const bool gen = chunk + 1 < nchunks;
+    const double* Ab = Abuf + stage * (kDKc * kDI);
+    const double* Bb = Bbuf + stage * (kDKc * kDBld);
+    double u0 = 0, u1 = 0, u2 = 0;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) af[mt] = Ab[(ks * kDI + wi * 32 + mt * 8 + r) * 4 + c];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) bf[nt] = Bb[(ks * 4 + c) * kDBld + wc * 32 + nt * 8 + r];
+      if (ks < kHalf && gen) {
+#pragma unroll
+        for (int e = 0; e < kPer; ++e) generate(nstage, ks * kPer + e, u0, u1, u2);
+      }
+      if (ks == kHalf) dense_mbar_arrive(&bar[nstage]);  // this thread's part of B(chunk+1) is written
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                       : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
+                       : "d"(af[mt]), "d"(bf[nt]));
+        }
+    }
+    stage = nstage;
+    if (stage == 0) parity ^= 1u;
+  }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
   // epilogue: N = -C into the dense slab
   const int m = T.m;
 #pragma unroll
@@ -911,8 +1073,15 @@ int32_t ca::assemble_slab(double alpha, double gamma, const int64_t* ijkl, int64
         const int nxg = dopt.nx > 0 ? dopt.nx : 3 * T.J + 1, nzg = dopt.nz > 0 ? dopt.nz : 3 * T.K + 1, nyg = T.ny;
         if (nxg <= 3 * T.J || nzg <= 3 * T.K)
           fail(CA_ERR_INVALID, "grid %d x %d x %d is not exact for J, K = %d, %d (need Nx > 3J, Nz > 3K)", nxg, nyg, nzg, T.J, T.K);
-        const bool twin = !(getenv("CA_DENSE_CFG") && getenv("CA_DENSE_CFG")[0] == 'W');  // W: the wide one-CTA-per-SM shape
-        const int kDQ = twin ? DenseTwin::Q : DenseWide::Q, kDJ = twin ? DenseTwin::J : DenseWide::J;
+        // tile shape of the contraction: R (default) the three-stage ring, T the twin two-CTA shape, W the wide one
+        const char shape = getenv("CA_DENSE_CFG") ? getenv("CA_DENSE_CFG")[0] : 'R';
+        auto with_cfg = [&](auto&& f) {
+          if (shape == 'T') f(DenseTwin{});
+          else if (shape == 'W') f(DenseWide{});
+          else f(DenseRing{});
+        };
+        int kDQ = 0, kDJ = 0;
+        with_cfg([&](auto cfg) { kDQ = decltype(cfg)::Q; kDJ = decltype(cfg)::J; });
         const int nreal = nxg * nyg * nzg, nq = (nreal + kDQ - 1) / kDQ * kDQ, nchunks = nq / kDQ;
         const int mpad = (m + kDI - 1) / kDI * kDI;
         if ((double)rows * m * m * 8.0 > 100e9)
@@ -950,54 +1119,51 @@ int32_t ca::assemble_slab(double alpha, double gamma, const int64_t* ijkl, int64
         Nd.alloc((size_t)rows * m * m);
         CA_CUDA(cudaMemsetAsync(dmax.ptr, 0, sizeof(double)));
         const int64_t ntab = (int64_t)mpad * nq;
+        auto tables = [&](double* raw, const double* mixed) {
+          with_cfg([&](auto cfg) {
+            dense_tables_kernel<decltype(cfg)><<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr,
+                                                                                      dezd.ptr, dF.ptr, T.ny, dwq.ptr, dU.ptr, dG9.ptr, dA.ptr,
+                                                                                      nchunks, raw, mixed);
+          });
+          CA_CUDA(cudaGetLastError());
+          count_launch();
+        };
         if (dopt.mix) {
           // Phi = Psi C on the grid: 12 planes (u_c, d_a u_c) of the plain basis, one GEMM [12 nq x m] . [m x m], then the
           // tiled operand layouts from the mixed planes.  ~0.5 % of the contraction's arithmetic.
           DeviceBuffer<double> raw, mixed;
           raw.alloc((size_t)12 * nq * m);
           mixed.alloc((size_t)12 * nq * m);
-          if (twin)
-            dense_tables_kernel<DenseTwin><<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr, dezd.ptr, dF.ptr,
-                                                                                   T.ny, dwq.ptr, dU.ptr, dG9.ptr, dA.ptr, nchunks, raw.ptr, nullptr);
-          else
-            dense_tables_kernel<DenseWide><<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr, dezd.ptr, dF.ptr,
-                                                                                   T.ny, dwq.ptr, dU.ptr, dG9.ptr, dA.ptr, nchunks, raw.ptr, nullptr);
-          CA_CUDA(cudaGetLastError());
-          count_launch();
+          tables(raw.ptr, nullptr);
           launch_dgemm(12 * nq, m, m, 1.0, rowmajor(raw.ptr, m), colmajor(dmix.ptr, m), 0.0, mixed.ptr, m, 1, nullptr);
-          if (twin)
-            dense_tables_kernel<DenseTwin><<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr, dezd.ptr, dF.ptr,
-                                                                                   T.ny, dwq.ptr, dU.ptr, dG9.ptr, dA.ptr, nchunks, nullptr, mixed.ptr);
-          else
-            dense_tables_kernel<DenseWide><<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr, dezd.ptr, dF.ptr,
-                                                                                   T.ny, dwq.ptr, dU.ptr, dG9.ptr, dA.ptr, nchunks, nullptr, mixed.ptr);
-          CA_CUDA(cudaGetLastError());
-          count_launch();
+          tables(nullptr, mixed.ptr);
           CA_CUDA(cudaStreamSynchronize(nullptr));  // raw / mixed are released here
         } else {
-          if (twin)
-            dense_tables_kernel<DenseTwin><<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr, dezd.ptr, dF.ptr,
-                                                                                   T.ny, dwq.ptr, dU.ptr, dG9.ptr, dA.ptr, nchunks, nullptr, nullptr);
-          else
-            dense_tables_kernel<DenseWide><<<(unsigned)((ntab + 255) / 256), 256>>>(b, mpad, nxg, nyg, nzg, nq, dex.ptr, dexd.ptr, dez.ptr, dezd.ptr, dF.ptr,
-                                                                                   T.ny, dwq.ptr, dU.ptr, dG9.ptr, dA.ptr, nchunks, nullptr, nullptr);
-          CA_CUDA(cudaGetLastError());
-          count_launch();
+          tables(nullptr, nullptr);
         }
         DenseTables DT{m, mpad, nq, nchunks, dU.ptr, dG9.ptr, dA.ptr};
         const int it0 = r0 / kDI, nit = (r1 + kDI - 1) / kDI - it0;
         const int njt = (m + kDJ - 1) / kDJ, nkt = (m + kDK - 1) / kDK;
-        const size_t smem = (twin ? DenseTwin::SmemDoubles : DenseWide::SmemDoubles) * sizeof(double);
-        CA_CUDA(cudaFuncSetAttribute(dense_contract_kernel<DenseTwin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DenseTwin::SmemDoubles * sizeof(double))));
-        CA_CUDA(cudaFuncSetAttribute(dense_contract_kernel<DenseWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DenseWide::SmemDoubles * sizeof(double))));
         cudaEvent_t c0, c1;
         CA_CUDA(cudaEventCreate(&c0));
         CA_CUDA(cudaEventCreate(&c1));
-        CA_CUDA(cudaEventRecord(c0));
-        if (twin)
-          dense_contract_kernel<DenseTwin><<<dim3((unsigned)(njt * nkt), (unsigned)nit), DenseTwin::Threads, smem>>>(DT, it0, njt, Nd.ptr, r0, r1);
-        else
-          dense_contract_kernel<DenseWide><<<dim3((unsigned)(njt * nkt), (unsigned)nit), DenseWide::Threads, smem>>>(DT, it0, njt, Nd.ptr, r0, r1);
+        const dim3 cgrid((unsigned)(njt * nkt), (unsigned)nit);
+        if (shape == 'T' || shape == 'W') {
+          with_cfg([&](auto cfg) {
+            using Cfg = decltype(cfg);
+            if constexpr (!std::is_same<Cfg, DenseRing>::value) {
+              const size_t smem = Cfg::SmemDoubles * sizeof(double);
+              CA_CUDA(cudaFuncSetAttribute(dense_contract_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+              CA_CUDA(cudaEventRecord(c0));
+              dense_contract_kernel<Cfg><<<cgrid, Cfg::Threads, smem>>>(DT, it0, njt, Nd.ptr, r0, r1);
+            }
+          });
+        } else {
+          const size_t smem = DenseRing::SmemDoubles * sizeof(double);
+          CA_CUDA(cudaFuncSetAttribute(dense_contract_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CA_CUDA(cudaEventRecord(c0));
+          dense_contract_ring_kernel<<<cgrid, DenseRing::Threads, smem>>>(DT, it0, njt, Nd.ptr, r0, r1);
+        }
         CA_CUDA(cudaGetLastError());
         count_launch();
         CA_CUDA(cudaEventRecord(c1));
