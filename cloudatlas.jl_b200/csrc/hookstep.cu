@@ -178,14 +178,28 @@ __device__ void warp_lu_solve(const double* W, const int* perm, double* b, int m
 }
 
 // In-place LU with partial pivoting (first maximal |entry| wins, like LAPACK's idamax).  Returns false
-// on an exactly zero pivot.
+// on an exactly zero pivot.  m <= kWarpLuMax: one warp (above).  Larger systems use the whole CTA, three barriers per
+// column:
+//   warp 0 finds the pivot and publishes its index, its signed value and the old diagonal entry            | barrier
+//   all threads swap rows k and p in the columns j != k; column k is written from the published scalars
+//   (diagonal <- pivot, multipliers l_r = W[r,k] / pivot with the swapped entry taken from the scalar)       | barrier
+//   rank-one update of the trailing block: warp w takes the columns k+1+w, k+1+w+8, ..., a lane its rows     | barrier
+// Same operations on the same values as warp_lu (l = w / pivot, w <- fma(-l, u, w)): the factors are bit-identical.
+// (Round 1 ran the 44 x 44 factorisations of the reference's configs[1] on ONE warp: 70 % of that search.)
+#ifndef CA_WARP_LU_MAX
+#define CA_WARP_LU_MAX 24
+#endif
+constexpr int kWarpLuOnly = CA_WARP_LU_MAX;  // up to here the one-warp factorisation is the faster one
 __device__ bool block_lu(double* W, int* piv, int* perm, int m, int* flag) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  if (m <= kWarpLuMax) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (m <= kWarpLuOnly) {
     if (tid < 32) warp_lu(W, piv, perm, m, flag);
     __syncthreads();
     return *flag == 0;
   }
+  __shared__ double pivot_and_diag[2];
+  for (int i = tid; i < m; i += kHookThreads) perm[i] = i;
+  __syncthreads();
   for (int k = 0; k < m; ++k) {
     if (tid < 32) {
       double best = -1.0;
@@ -194,34 +208,37 @@ __device__ bool block_lu(double* W, int* piv, int* perm, int m, int* flag) {
         const double v = fabs(W[r + m * k]);
         if (v > best) { best = v; at = r; }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oa = __shfl_xor_sync(0xffffffffu, at, o);
-        if (ob > best || (ob == best && oa < at)) { best = ob; at = oa; }
-      }
+      warp_argmax(best, at, best, at);
       if (lane == 0) {
         piv[k] = at;
-        if (best == 0.0) *flag = 1;
+        if (best == 0.0) {
+          *flag = 1;
+        } else {
+          const int t = perm[k];
+          perm[k] = perm[at];
+          perm[at] = t;
+          pivot_and_diag[0] = W[at + m * k];
+          pivot_and_diag[1] = W[k + m * k];
+        }
       }
     }
     __syncthreads();
     if (*flag) return false;
     const int p = piv[k];
+    const double pivot = pivot_and_diag[0], diag = pivot_and_diag[1];
     if (p != k)
-      for (int j = tid; j < m; j += kHookThreads) {
-        const double t = W[k + m * j];
-        W[k + m * j] = W[p + m * j];
-        W[p + m * j] = t;
-      }
+      for (int j = tid; j < m; j += kHookThreads)
+        if (j != k) {
+          const double t = W[k + m * j];
+          W[k + m * j] = W[p + m * j];
+          W[p + m * j] = t;
+        }
+    for (int r = k + tid; r < m; r += kHookThreads)
+      W[r + m * k] = r == k ? pivot : (r == p ? diag : W[r + m * k]) / pivot;
     __syncthreads();
-    const double pivot = W[k + m * k];
-    for (int r = k + 1 + tid; r < m; r += kHookThreads) W[r + m * k] /= pivot;
-    __syncthreads();
-    const int n = m - k - 1;
-    for (int idx = tid; idx < n * n; idx += kHookThreads) {
-      const int r = k + 1 + idx % n, c = k + 1 + idx / n;
-      W[r + m * c] = fma(-W[r + m * k], W[k + m * c], W[r + m * c]);
+    for (int c = k + 1 + warp; c < m; c += kHookThreads / 32) {
+      const double u = W[k + m * c];  // broadcast
+      for (int r = k + 1 + lane; r < m; r += 32) W[r + m * c] = fma(-W[r + m * k], u, W[r + m * c]);
     }
     __syncthreads();
   }
@@ -231,7 +248,7 @@ __device__ bool block_lu(double* W, int* piv, int* perm, int m, int* flag) {
 // b <- (LU)^-1 b
 __device__ void block_lu_solve(const double* W, const int* piv, const int* perm, double* b, int m) {
   const int tid = threadIdx.x;
-  if (m <= kWarpLuMax) {
+  if (m <= kWarpLuMax) {  // two rows per lane in registers, shuffles instead of barriers: faster than the CTA loops below
     if (tid < 32) warp_lu_solve(W, perm, b, m);
     __syncthreads();
     return;
@@ -249,6 +266,83 @@ __device__ void block_lu_solve(const double* W, const int* piv, const int* perm,
   }
   for (int c = m - 1; c >= 0; --c) {
     if (tid == 0) b[c] /= W[c + m * c];
+    __syncthreads();
+    const double f = b[c];
+    for (int r = tid; r < c; r += kHookThreads) b[r] = fma(-W[r + m * c], f, b[r]);
+    __syncthreads();
+  }
+}
+
+// Cholesky factorisation of the symmetric positive definite H + mu I of the hookstep's mu search (the reference's
+// `\` takes the same route for a Hermitian matrix): half the arithmetic of the LU, no pivot search, two barriers per
+// column.  The strict lower triangle of W receives L (and the upper triangle its transpose), the diagonal of L goes to
+// cd[] (W's diagonal is left alone, so that reading the pivot and scaling the column need no barrier between them).  Returns false on a non-positive pivot
+// (the caller then refills W and uses the pivoted LU).
+#ifndef CA_HOOK_CHOL_MIN
+#define CA_HOOK_CHOL_MIN 0  // tuning hook: systems smaller than this keep the LU
+#endif
+__device__ bool block_chol(double* W, double* cd, int m) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int k = 0; k < m; ++k) {
+    const double akk = W[k + m * k];
+    if (!(akk > 0.0)) return false;  // the same value in every thread
+    const double d = sqrt(akk);
+    if (tid == 0) cd[k] = d;
+    for (int r = k + 1 + tid; r < m; r += kHookThreads) {
+      const double l = W[r + m * k] / d;
+      W[r + m * k] = l;
+      W[k + m * r] = l;  // L' mirrored into the (otherwise unused) upper triangle: the back substitution reads columns
+    }
+    __syncthreads();
+    for (int c = k + 1 + warp; c < m; c += kHookThreads / 32) {
+      const double lc = W[c + m * k];  // broadcast
+      for (int r = c + lane; r < m; r += 32) W[r + m * c] = fma(-W[r + m * k], lc, W[r + m * c]);
+    }
+    __syncthreads();
+  }
+  return true;
+}
+
+// b <- (L L')^-1 b
+__device__ void block_chol_solve(const double* W, const double* cd, double* b, int m) {
+  const int tid = threadIdx.x;
+  if (m <= kWarpLuMax) {  // one warp, rows lane and lane + 32 in registers
+    if (tid < 32) {
+      const int lane = tid, r0 = lane, r1 = lane + 32;
+      double b0 = r0 < m ? b[r0] : 0.0, b1 = r1 < m ? b[r1] : 0.0;
+      for (int c = 0; c < m; ++c) {  // L y = b
+        double mine = c < 32 ? b0 : b1;
+        if (lane == (c & 31)) mine /= cd[c];
+        const double f = __shfl_sync(0xffffffffu, mine, c & 31);
+        if (r0 == c) b0 = f;
+        if (r1 == c) b1 = f;
+        if (r0 > c && r0 < m) b0 = fma(-W[r0 + m * c], f, b0);
+        if (r1 > c && r1 < m) b1 = fma(-W[r1 + m * c], f, b1);
+      }
+      for (int c = m - 1; c >= 0; --c) {  // L' x = y: column c of L' is row c of L
+        double mine = c < 32 ? b0 : b1;
+        if (lane == (c & 31)) mine /= cd[c];
+        const double f = __shfl_sync(0xffffffffu, mine, c & 31);
+        if (r0 == c) b0 = f;
+        if (r1 == c) b1 = f;
+        if (r0 < c) b0 = fma(-W[r0 + m * c], f, b0);
+        if (r1 < c) b1 = fma(-W[r1 + m * c], f, b1);
+      }
+      if (r0 < m) b[r0] = b0;
+      if (r1 < m) b[r1] = b1;
+    }
+    __syncthreads();
+    return;
+  }
+  for (int c = 0; c < m; ++c) {
+    if (tid == 0) b[c] /= cd[c];
+    __syncthreads();
+    const double f = b[c];
+    for (int r = c + 1 + tid; r < m; r += kHookThreads) b[r] = fma(-W[r + m * c], f, b[r]);
+    __syncthreads();
+  }
+  for (int c = m - 1; c >= 0; --c) {
+    if (tid == 0) b[c] /= cd[c];
     __syncthreads();
     const double f = b[c];
     for (int r = tid; r < c; r += kHookThreads) b[r] = fma(-W[r + m * c], f, b[r]);
@@ -320,6 +414,24 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
   int* perm = piv + m;               // m ints
   int* flag = perm + m;
 
+  __shared__ double chol_diag[96];  // m <= 95
+  bool chol = false;  // W holds a Cholesky factor (else the pivoted LU)
+  // factor W = H + mu I (already filled in): Cholesky, or -- on a non-positive pivot -- refill and pivoted LU
+  auto factor_spd = [&](double mu) -> bool {
+    if (m >= CA_HOOK_CHOL_MIN && block_chol(W, chol_diag, m)) {
+      chol = true;
+      return true;
+    }
+    __syncthreads();
+    for (int e = tid; e < m * m; e += kHookThreads) W[e] = H[e] + ((e % m) == (e / m) ? mu : 0.0);
+    __syncthreads();
+    chol = false;
+    return block_lu(W, piv, perm, m, flag);
+  };
+  auto solve_spd = [&](double* b) {
+    if (chol) block_chol_solve(W, chol_diag, b, m);
+    else block_lu_solve(W, piv, perm, b, m);
+  };
   const double invR = 1.0 / a.R[s];
   const double ftol = a.p.ftol, xtol = a.p.xtol;
   double delta = a.p.delta;
@@ -396,16 +508,16 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
             for (int e = tid; e < m * m; e += kHookThreads) W[e] = H[e] + ((e % m) == (e / m) ? mu : 0.0);
           for (int i = tid; i < m; i += kHookThreads) t1[i] = dx[i];
           __syncthreads();
-          { TIC; const bool okk = it != 0 || block_lu(W, piv, perm, m, flag); TOC(2); if (!okk) { singular = true; break; } }
-          { TIC; block_lu_solve(W, piv, perm, t1, m); TOC(3); }
+          { TIC; const bool okk = it != 0 || factor_spd(mu); TOC(2); if (!okk) { singular = true; break; } }
+          { TIC; solve_spd(t1); TOC(3); }
           const double phiprime = -(1.0 / norm_dx) * block_dot(dx, t1, m, scratch);
           mu = mu - (norm_dx / delta) * (phi / phiprime);
           // dx = -(H + mu I) \ (Df' fx)
           for (int e = tid; e < m * m; e += kHookThreads) W[e] = H[e] + ((e % m) == (e / m) ? mu : 0.0);
           for (int i = tid; i < m; i += kHookThreads) dx[i] = -g[i];
           __syncthreads();
-          { TIC; const bool okk = block_lu(W, piv, perm, m, flag); TOC(2); if (!okk) { singular = true; break; } }
-          { TIC; block_lu_solve(W, piv, perm, dx, m); TOC(3); }
+          { TIC; const bool okk = factor_spd(mu); TOC(2); if (!okk) { singular = true; break; } }
+          { TIC; solve_spd(dx); TOC(3); }
           norm_dx = sqrt(block_dot(dx, dx, m, scratch));
           if (fabs(norm_dx - delta) / delta <= 1e-4) break;
         }
