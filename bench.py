@@ -375,7 +375,7 @@ def dense_assembly_case(ca, H, world, rank, max_over_ranks, barrier, dmma_peak):
             "bound": "tensor", "pipe": "fp64 DMMA", "achieved": flops_total / sec / 1e12 / world, "peak": dmma_peak,
             "unit": "TFLOP/s per GPU", "frac": flops_total / sec / 1e12 / world / dmma_peak,
             "contract_seconds": sec, "wall_seconds": wall, "algorithmic_flops": flops_total, "n_gpus": world,
-            "nnz_rank0": int(nnz), "kernel": "dense_contract_kernel"}
+            "nnz_rank0": int(nnz), "kernel": "dense_contract_ring_kernel"}
 
 
 NVLINK_BUSBW_MEASURED = 725.0   # GB/s, all-gather bus bandwidth measured on this pool's 8 x B200 boxes
@@ -501,7 +501,7 @@ def mixed_basis_case(ca, H, dmma_peak):
     out = {"workload": "dense quadrature assembly of N on a mixed random-coefficient basis Phi = (Psi diag(s)) C, m=999, rows 384:512, grid 16x33x16",
            "bound": "tensor", "pipe": "fp64 DMMA", "achieved": tf, "peak": dmma_peak, "unit": "TFLOP/s", "frac": tf / dmma_peak,
            "contract_seconds": info["contract_seconds"], "wall_seconds": wall, "nnz_slab": int(slab.nnz),
-           "dense_fraction_of_slab": slab.nnz / (128.0 * m * m), "kernel": "dense_contract_kernel"}
+           "dense_fraction_of_slab": slab.nnz / (128.0 * m * m), "kernel": "dense_contract_ring_kernel"}
     del slab
     return out
 

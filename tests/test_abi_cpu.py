@@ -154,7 +154,10 @@ def test_sass_of_the_hot_kernels():
     assert "sm_100a" in arch and "sm_90" not in arch and "sm_80" not in arch
     sass = subprocess.run(["cuobjdump", "-sass", libpath], capture_output=True, text=True).stdout
     for pattern, need in (("bilinear_warptile_kernel", ("DMMA.8x8x4", "LDGSTS")),
-                          ("bilinear_windowed_kernel", ("DMMA.8x8x4", "LDGSTS", "LDGDEPBAR")),
+                          # role-split kernels: cp.async completion arrives on mbarriers (ARRIVES.LDGSTSBAR), waits are
+                          # SYNCS try-waits
+                          ("bilinear_windowed_kernel", ("DMMA.8x8x4", "LDGSTS", "LDGDEPBAR", "ARRIVES.LDGSTSBAR", "SYNCS")),
+                          ("dense_contract_ring_kernel", ("DMMA.8x8x4", "LDGSTS", "ARRIVES.LDGSTSBAR", "SYNCS")),
                           ("dense_contract_kernel", ("DMMA.8x8x4", "LDGSTS"))):
         blocks = [b for b in sass.split("Function : ")[1:] if pattern in b.split("\n", 1)[0]]
         assert blocks, pattern

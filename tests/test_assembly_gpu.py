@@ -218,6 +218,21 @@ def test_dense_quadrature_row_slabs(ca):
     assert np.array_equal(np.concatenate([p[1] for p in parts]), full[1])
 
 
+@pytest.mark.parametrize("shape", ["R", "T", "W"])
+def test_dense_contraction_shapes_agree_and_repeat(ca, shape, monkeypatch):
+    """The three tile shapes of the dense contraction (R: three-stage mbarrier ring, the default; T, W: the two-buffer
+    kernels) give the same operator on the 307-mode basis, rows 100:180 (two row tiles, ragged columns), and the same
+    bits on a second run -- the ring kernel has no CTA barrier in its loop, a missing dependency would show here."""
+    ijkl = ca.basisIndices(3, 3, 12, lib_H(ca))
+    sep = ca.AssemblySlab(1.0, 2.0, ijkl, False, 100, 180).coo_host()
+    monkeypatch.setenv("CA_DENSE_CFG", shape)
+    a = ca.AssemblySlab(1.0, 2.0, ijkl, False, 100, 180, dense=True).coo_host()
+    b = ca.AssemblySlab(1.0, 2.0, ijkl, False, 100, 180, dense=True).coo_host()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[0], sep[0])
+    assert np.max(np.abs(a[1] - sep[1])) < 1e-13 * np.max(np.abs(sep[1]))
+
+
 def test_random_coefficient_basis_mode_scale(ca):
     """north_star: "random-coefficient bases" = the reference's data model c * Psi (BasisFunctions.jl:417) with
     s_n ~ U(0.5, 2), seed 20251029: N'_ijk = s_i s_j s_k N_ijk, B'_ij = s_i s_j B_ij, same pattern; both

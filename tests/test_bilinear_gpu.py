@@ -201,6 +201,35 @@ def test_windowed_kernel_full_size_windows_m307(ca, nagata_H, monkeypatch):
     assert relerr(N(dX, dV).cpu().numpy()[sub], np.stack([ref(X[s], V[s]) for s in sub])) < TOL
 
 
+def test_windowed_kernel_many_blocks_repeatable(ca, nagata_H, monkeypatch):
+    """The role-split windowed kernel over several blocks of 32 states per team (the window ring and the mbarrier
+    phases run on across blocks; 20,011 states > 2 teams x 148 CTAs x 32): identical bits on repeated launches (a race
+    between producer and consumer warps would show as run-to-run differences), agreement with the whole-tile kernel,
+    both leading-dimension parities (16-byte and 8-byte gathers) and all three evaluation modes."""
+    import torch
+    ijk, val, m = model_coo((3, 3, 12), nagata_H)
+    whole = ca.SparseBilinear(ijk, val, m)
+    n = 20011
+    rng = np.random.default_rng(77)
+    for ld in (n + 1, n + 2):  # even and odd
+        bx = torch.zeros((m, ld), dtype=torch.float64, device="cuda")
+        bv = torch.zeros((m, ld), dtype=torch.float64, device="cuda")
+        bx[:, :n] = torch.from_numpy(0.1 * rng.standard_normal((m, n)))
+        bv[:, :n] = torch.from_numpy(rng.standard_normal((m, n)))
+        dX, dV = bx.t()[:n], bv.t()[:n]
+        monkeypatch.delenv("CA_FORCE_WINDOW_MODES", raising=False)
+        want = [whole(dX), whole.jvp(dX, dV), whole(dX, dV)]
+        monkeypatch.setenv("CA_FORCE_WINDOW_MODES", "128")
+        N = ca.SparseBilinear(ijk, val, m)
+        first = [N(dX), N.jvp(dX, dV), N(dX, dV)]
+        for a, b in zip(first, want):
+            assert relerr(a.cpu().numpy(), b.cpu().numpy()) < TOL
+        for _ in range(3):
+            again = [N(dX), N.jvp(dX, dV), N(dX, dV)]
+            for a, b in zip(first, again):
+                assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("wm", [8, 24, 96])
 def test_windowed_kernel_forced_at_small_m(ca, nagata_H, wm, monkeypatch):
     """The large-m (windowed, cp.async double-buffered) kernel, forced onto small operators."""
