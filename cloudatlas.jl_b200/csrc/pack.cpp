@@ -744,6 +744,8 @@ PackedHost finalize_pack(PackedHost P, std::vector<PackedHost>& parts, const std
     std::vector<int32_t> idx(P.tiles.size());
     std::iota(idx.begin(), idx.end(), 0);
     // cycles of the FP64 pipe per k-step: 4 nt DMMAs x 16 plus the four pair products (tools/dmma_dmul_mix.cu)
+    // (measured at 307 modes, round 2: a one-n-tile k-step really costs ~110 -- it is shared-memory bound -- but weights of
+    // 100 / 111 / 125 change the time by -0.5 / +1.2 / +2.6 %: the schedule's granularity, not its weights, is what is left)
     auto weight = [&](int32_t t) { return (int64_t)P.tiles[t].nks * (P.tiles[t].nt == 2 ? 144 : 82) + 40; };
     std::stable_sort(idx.begin(), idx.end(), [&](int32_t x, int32_t y) { return weight(x) > weight(y); });
     int64_t load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
