@@ -273,80 +273,180 @@ __device__ void block_lu_solve(const double* W, const int* piv, const int* perm,
   }
 }
 
-// Cholesky factorisation of the symmetric positive definite H + mu I of the hookstep's mu search (the reference's
-// `\` takes the same route for a Hermitian matrix): half the arithmetic of the LU, no pivot search, two barriers per
-// column.  The strict lower triangle of W receives L (and the upper triangle its transpose), the diagonal of L goes to
-// cd[] (W's diagonal is left alone, so that reading the pivot and scaling the column need no barrier between them).  Returns false on a non-positive pivot
-// (the caller then refills W and uses the pivoted LU).
-#ifndef CA_HOOK_CHOL_MIN
-#define CA_HOOK_CHOL_MIN 0  // tuning hook: systems smaller than this keep the LU
-#endif
-__device__ bool block_chol(double* W, double* cd, int m) {
+// ---- the hookstep's mu search in a basis where H = Df'Df is tridiagonal -------------------------------------------
+// Hookstep.jl:21-74 solves (H + mu I) dx = -Df'f  and  (H + mu I) t = dx  for ~20 values of mu per hookstep (Newton
+// iteration on mu for |dx(mu)| = delta), each a dense factorisation in the reference: ~400 factorisations of a 44 x 44
+// matrix in the 44-mode search, 70 % of its time in round 1 and still 53 % with a CTA-wide Cholesky.  Here H is
+// reduced ONCE per Newton step to H = Q T Q' (Householder, T tridiagonal); in the coordinates z = Q'dx every solve is
+// a pivoted LU of the tridiagonal T + mu I (O(m)), |dx| = |z| and dx.t = z.(Q't), so a mu iteration is O(m) scalar
+// work without a barrier.  Q is never formed: the reflectors stay in H's columns and one warp applies them to the
+// three vectors a hookstep needs (Q'g, Q'dx_newton, Q z).
+struct Tridiag {            // arrays of m entries, carved from the (then idle) factorisation workspace W
+  double *a, *b;            // diagonal and sub-diagonal of T
+  double *v0, *beta;        // first component and 2 / |v|^2 of reflector k (the rest of v_k is H[k+2.., k]); beta = 0: none
+  double *qg, *z, *t;       // Q'g; coordinates of the current dx; a solve's result
+  double *dl, *rd, *du, *du2;  // factors of T + mu I: multipliers, 1 / diagonal of U, its two super-diagonals
+  double *v, *p;            // p: Householder work vector (v: spare)
+  int* piv;                 // 1: rows i and i+1 were interchanged
+  static constexpr int kDoubles = 14;  // 13 arrays of doubles + one of ints, in units of m doubles
+  __device__ void carve(double* W, int m) {
+    a = W; b = a + m; v0 = b + m; beta = v0 + m; qg = beta + m; z = qg + m; t = z + m;
+    dl = t + m; rd = dl + m; du = rd + m; du2 = du + m; v = du2 + m; p = v + m;
+    piv = reinterpret_cast<int*>(p + m);
+  }
+};
+
+// H (m x m, symmetric, column-major) -> T.a, T.b and the reflectors (v0, beta; tails in H's columns).
+// Two barriers per column: the norms and dot products are computed by every warp for itself (same data, same order of
+// operations, hence the same value in every thread) instead of through block-wide reductions.
+__device__ void block_tridiagonalise(double* H, Tridiag& T, int m) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int k = 0; k < m; ++k) {
-    const double akk = W[k + m * k];
-    if (!(akk > 0.0)) return false;  // the same value in every thread
-    const double d = sqrt(akk);
-    if (tid == 0) cd[k] = d;
-    for (int r = k + 1 + tid; r < m; r += kHookThreads) {
-      const double l = W[r + m * k] / d;
-      W[r + m * k] = l;
-      W[k + m * r] = l;  // L' mirrored into the (otherwise unused) upper triangle: the back substitution reads columns
+  auto warp_sum = [](double s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+  };
+  for (int k = 0; k + 2 < m; ++k) {
+    const int n = m - k - 1;                    // trailing block H22 = H[k+1.., k+1..]
+    const double* x = H + (k + 1) + m * k;      // the column below the diagonal: v = (v0, x[1..])
+    double part = 0.0;
+    for (int i = 1 + lane; i < n; i += 32) part = fma(x[i], x[i], part);
+    const double sigma = warp_sum(part);
+    const double x0 = x[0];
+    if (sigma == 0.0) {                          // already tridiagonal in this column (same value in every thread)
+      if (tid == 0) { T.a[k] = H[k + m * k]; T.b[k] = x0; T.v0[k] = 0.0; T.beta[k] = 0.0; }
+      continue;
+    }
+    const double alpha = -copysign(sqrt(x0 * x0 + sigma), x0);
+    const double v0 = x0 - alpha;
+    const double beta = 2.0 / (v0 * v0 + sigma);  // reflector I - beta v v'
+    if (tid == 0) { T.a[k] = H[k + m * k]; T.b[k] = alpha; T.v0[k] = v0; T.beta[k] = beta; }
+    // p = beta H22 v: four lanes per row (columns j = g, g + 4, ...), combined by shuffles; H22 is symmetric, so the
+    // lanes of a row group walk down columns and consecutive rows are consecutive addresses
+    for (int i0 = 0; i0 < n; i0 += kHookThreads / 4) {
+      const int i = i0 + (tid >> 2), g = tid & 3;
+      double sum = 0.0, sum2 = 0.0;
+      if (i < n) {
+        const double* hrow = H + (k + 1 + i) + m * (k + 1);
+        int j = g;
+        for (; j + 4 < n; j += 8) {  // two independent chains
+          sum = fma(hrow[m * j], j == 0 ? v0 : x[j], sum);
+          sum2 = fma(hrow[m * (j + 4)], x[j + 4], sum2);
+        }
+        if (j < n) sum = fma(hrow[m * j], j == 0 ? v0 : x[j], sum);
+        sum += sum2;
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      if (i < n && g == 0) T.p[i] = beta * sum;
     }
     __syncthreads();
-    for (int c = k + 1 + warp; c < m; c += kHookThreads / 32) {
-      const double lc = W[c + m * k];  // broadcast
-      for (int r = c + lane; r < m; r += 32) W[r + m * c] = fma(-W[r + m * k], lc, W[r + m * c]);
+    part = 0.0;
+    for (int i = lane; i < n; i += 32) part = fma(i == 0 ? v0 : x[i], T.p[i], part);
+    const double K = 0.5 * beta * warp_sum(part);
+    // H22 -= v w' + w v' with w = p - K v: a warp per column, lanes over the rows
+    double vi[3], wi[3];  // this lane's rows (m <= 95: at most three)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int i = lane + 32 * r;
+      vi[r] = i < n ? (i == 0 ? v0 : x[i]) : 0.0;
+      wi[r] = i < n ? T.p[i] - K * vi[r] : 0.0;
+    }
+    for (int j = warp; j < n; j += kHookThreads / 32) {
+      const double vj = j == 0 ? v0 : x[j], wj = T.p[j] - K * vj;
+      double* hcol = H + (k + 1) + m * (k + 1 + j);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int i = lane + 32 * r;
+        if (i < n) hcol[i] -= vi[r] * wj + wi[r] * vj;
+      }
     }
     __syncthreads();
   }
-  return true;
+  if (tid == 0) {
+    if (m >= 2) { T.a[m - 2] = H[(m - 2) + m * (m - 2)]; T.b[m - 2] = H[(m - 1) + m * (m - 2)]; }
+    T.a[m - 1] = H[(m - 1) + m * (m - 1)];
+  }
+  __syncthreads();
 }
 
-// b <- (L L')^-1 b
-__device__ void block_chol_solve(const double* W, const double* cd, double* b, int m) {
-  const int tid = threadIdx.x;
-  if (m <= kWarpLuMax) {  // one warp, rows lane and lane + 32 in registers
-    if (tid < 32) {
-      const int lane = tid, r0 = lane, r1 = lane + 32;
-      double b0 = r0 < m ? b[r0] : 0.0, b1 = r1 < m ? b[r1] : 0.0;
-      for (int c = 0; c < m; ++c) {  // L y = b
-        double mine = c < 32 ? b0 : b1;
-        if (lane == (c & 31)) mine /= cd[c];
-        const double f = __shfl_sync(0xffffffffu, mine, c & 31);
-        if (r0 == c) b0 = f;
-        if (r1 == c) b1 = f;
-        if (r0 > c && r0 < m) b0 = fma(-W[r0 + m * c], f, b0);
-        if (r1 > c && r1 < m) b1 = fma(-W[r1 + m * c], f, b1);
-      }
-      for (int c = m - 1; c >= 0; --c) {  // L' x = y: column c of L' is row c of L
-        double mine = c < 32 ? b0 : b1;
-        if (lane == (c & 31)) mine /= cd[c];
-        const double f = __shfl_sync(0xffffffffu, mine, c & 31);
-        if (r0 == c) b0 = f;
-        if (r1 == c) b1 = f;
-        if (r0 < c) b0 = fma(-W[r0 + m * c], f, b0);
-        if (r1 < c) b1 = fma(-W[r1 + m * c], f, b1);
-      }
-      if (r0 < m) b[r0] = b0;
-      if (r1 < m) b[r1] = b1;
+// One warp: y <- Q' y (transpose) or y <- Q y, Q = P_0 P_1 ... P_{m-3}, P_k = I - beta_k v_k v_k' on components k+1..
+__device__ void warp_apply_reflectors(const double* H, const Tridiag& T, double* y, int m, bool transpose) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  for (int q = 0; q + 2 < m; ++q) {
+    const int k = transpose ? q : m - 3 - q;
+    const double beta = T.beta[k];
+    if (beta == 0.0) continue;
+    const int n = m - k - 1;
+    const double* tail = H + (k + 1) + m * k;  // tail[i] = v_i for i >= 1
+    double dot = 0.0;
+    for (int i = lane; i < n; i += 32) dot = fma(i == 0 ? T.v0[k] : tail[i], y[k + 1 + i], dot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const double c = beta * dot;
+    for (int i = lane; i < n; i += 32) y[k + 1 + i] -= c * (i == 0 ? T.v0[k] : tail[i]);
+    __syncwarp();
+  }
+}
+
+// One thread: LU with partial pivoting of the tridiagonal T + mu I (the mu iteration may step to negative mu, where
+// the matrix is indefinite; the reference's `\` pivots too).  Gaussian elimination with row interchanges between
+// neighbours, fill-in on a second super-diagonal (LAPACK dgttrf's scheme): dl = multipliers, rd = 1 / diagonal of U,
+// du, du2 = super-diagonals of U divided by their row's pivot.  False on an exactly zero pivot.
+__device__ bool tridiag_factor(const Tridiag& T, double mu, int m) {
+  double d = T.a[0] + mu;           // current diagonal entry
+  double u = m > 1 ? T.b[0] : 0.0;  // current super-diagonal entry (T is symmetric: the same b)
+#pragma unroll 4  // (the loads of T.a, T.b do not depend on the chain d -> 1/d -> d: let them run ahead)
+  for (int i = 0; i + 1 < m; ++i) {
+    const double sub = T.b[i], dnext = T.a[i + 1] + mu, unext = i + 2 < m ? T.b[i + 1] : 0.0;
+    if (fabs(d) >= fabs(sub)) {
+      if (d == 0.0) return false;
+      const double r = 1.0 / d, f = sub * r;
+      T.dl[i] = f;
+      T.rd[i] = r;
+      T.du[i] = u * r;  // the super-diagonals are stored divided by the pivot: one fma per row on the solve's chain
+      T.du2[i] = 0.0;
+      T.piv[i] = 0;
+      d = dnext - f * u;
+      u = unext;
+    } else {  // interchange rows i and i+1
+      const double r = 1.0 / sub, f = d * r;
+      T.dl[i] = f;
+      T.rd[i] = r;
+      T.du[i] = dnext * r;
+      T.du2[i] = unext * r;
+      T.piv[i] = 1;
+      d = u - f * dnext;
+      u = -f * unext;
     }
-    __syncthreads();
-    return;
   }
-  for (int c = 0; c < m; ++c) {
-    if (tid == 0) b[c] /= cd[c];
-    __syncthreads();
-    const double f = b[c];
-    for (int r = c + 1 + tid; r < m; r += kHookThreads) b[r] = fma(-W[r + m * c], f, b[r]);
-    __syncthreads();
+  if (d == 0.0) return false;
+  T.rd[m - 1] = 1.0 / d;
+  return true;
+}
+// out = (T + mu I)^-1 rhs from the factors (out != rhs)
+__device__ void tridiag_solve(const Tridiag& T, const double* rhs, double* out, int m) {
+  double cur = rhs[0];
+#pragma unroll 4
+  for (int i = 0; i + 1 < m; ++i) {
+    const double nxt = rhs[i + 1];
+    if (T.piv[i]) {
+      out[i] = nxt;
+      cur = cur - T.dl[i] * nxt;
+    } else {
+      out[i] = cur;
+      cur = nxt - T.dl[i] * cur;
+    }
   }
-  for (int c = m - 1; c >= 0; --c) {
-    if (tid == 0) b[c] /= cd[c];
-    __syncthreads();
-    const double f = b[c];
-    for (int r = tid; r < c; r += kHookThreads) b[r] = fma(-W[r + m * c], f, b[r]);
-    __syncthreads();
+  double x1 = cur * T.rd[m - 1], x2 = 0.0;
+  out[m - 1] = x1;
+#pragma unroll 4
+  for (int i = m - 2; i >= 0; --i) {
+    const double x0 = fma(-T.du[i], x1, fma(-T.du2[i], x2, out[i] * T.rd[i]));
+    out[i] = x0;
+    x2 = x1;
+    x1 = x0;
   }
 }
 
@@ -400,7 +500,7 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
   double* Df = sm;
   double* H = Df + m * m;
   double* W = H + m * m;
-  double* x = W + m * m;
+  double* x = W + (m * m > Tridiag::kDoubles * m ? m * m : Tridiag::kDoubles * m);
   double* fx = x + m;
   double* dx = fx + m;
   double* dxn = dx + m;   // Newton step
@@ -414,24 +514,9 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
   int* perm = piv + m;               // m ints
   int* flag = perm + m;
 
-  __shared__ double chol_diag[96];  // m <= 95
-  bool chol = false;  // W holds a Cholesky factor (else the pivoted LU)
-  // factor W = H + mu I (already filled in): Cholesky, or -- on a non-positive pivot -- refill and pivoted LU
-  auto factor_spd = [&](double mu) -> bool {
-    if (m >= CA_HOOK_CHOL_MIN && block_chol(W, chol_diag, m)) {
-      chol = true;
-      return true;
-    }
-    __syncthreads();
-    for (int e = tid; e < m * m; e += kHookThreads) W[e] = H[e] + ((e % m) == (e / m) ? mu : 0.0);
-    __syncthreads();
-    chol = false;
-    return block_lu(W, piv, perm, m, flag);
-  };
-  auto solve_spd = [&](double* b) {
-    if (chol) block_chol_solve(W, chol_diag, b, m);
-    else block_lu_solve(W, piv, perm, b, m);
-  };
+  Tridiag T;       // the mu search's workspace lives in W (idle between two Newton factorisations)
+  T.carve(W, m);
+  __shared__ int mu_status;  // 0 ok, 1: a tridiagonal factorisation met a zero pivot
   const double invR = 1.0 / a.R[s];
   const double ftol = a.p.ftol, xtol = a.p.xtol;
   double delta = a.p.delta;
@@ -475,7 +560,7 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
     for (int i = tid; i < m; i += kHookThreads) { dxn[i] = dx[i]; xh[i] = x[i] + dx[i]; }
     __syncthreads();
 
-    bool have_H = false;
+    bool have_H = false, have_qg = false;
     bool xtol_exit = false;
     int nh = 0;
     for (int h = 0; h < a.p.Nhook; ++h) {
@@ -492,35 +577,55 @@ __global__ void __launch_bounds__(kHookThreads, 1) hookstep_kernel(SolverArgs a)
           }
           __syncthreads();
           block_gemv(Df, fx, g, m, true);  // Df' fx
-          have_H = true;
           TOC(4);
+          { TIC; block_tridiagonalise(H, T, m); TOC(2); }  // H = Q T Q'; H now holds the reflectors
+          have_H = true;
         }
-        double mu = 1e-6;
-        double norm_dx = norm_dx_newt;
-        for (int i = tid; i < m; i += kHookThreads) dx[i] = dxn[i];
-        __syncthreads();
-        bool singular = false;
-        for (int it = 0; it < a.p.Nmusearch; ++it) {
-          const double phi = norm_dx - delta;
-          // phi' = -(1/norm_dx) * dot(dx, (H + mu I) \ dx).  After the first pass W already holds the LU of
-          // H + mu I: it was factored for this mu at the end of the previous pass (the reference factors twice).
-          if (it == 0)
-            for (int e = tid; e < m * m; e += kHookThreads) W[e] = H[e] + ((e % m) == (e / m) ? mu : 0.0);
-          for (int i = tid; i < m; i += kHookThreads) t1[i] = dx[i];
+        // ---- Newton iteration on mu, in the coordinates z = Q' dx: warp 0 alone, O(m) scalar work per iteration
+        {
+          TIC;
+          if (tid < 32) {
+            if (!have_qg) {
+              for (int i = tid; i < m; i += 32) T.qg[i] = g[i];
+              warp_apply_reflectors(H, T, T.qg, m, true);  // Q' g
+            }
+            for (int i = tid; i < m; i += 32) T.z[i] = dxn[i];
+            warp_apply_reflectors(H, T, T.z, m, true);      // Q' dx_newton
+            if (tid == 0) {
+              double* t = T.t;
+              double mu = 1e-6;
+              double norm_dx = norm_dx_newt;
+              int status = 0;
+              // factors of H + mu I for the current mu; the reference factors twice per iteration (same matrix)
+              if (!tridiag_factor(T, mu, m)) status = 1;
+              for (int it = 0; it < a.p.Nmusearch && status == 0; ++it) {
+                const double phi = norm_dx - delta;
+                tridiag_solve(T, T.z, t, m);  // (H + mu I) \ dx
+                double zt = 0.0;
+#pragma unroll 4
+                for (int i = 0; i < m; ++i) zt = fma(T.z[i], t[i], zt);
+                const double phiprime = -(1.0 / norm_dx) * zt;
+                mu = mu - (norm_dx / delta) * (phi / phiprime);
+                if (!tridiag_factor(T, mu, m)) { status = 1; break; }
+                for (int i = 0; i < m; ++i) t[i] = -T.qg[i];
+                tridiag_solve(T, t, T.z, m);  // dx = -(H + mu I) \ (Df' fx)
+                double zz = 0.0;
+#pragma unroll 4
+                for (int i = 0; i < m; ++i) zz = fma(T.z[i], T.z[i], zz);
+                norm_dx = sqrt(zz);
+                if (fabs(norm_dx - delta) / delta <= 1e-4) break;
+              }
+              mu_status = status;
+            }
+            __syncwarp();
+            warp_apply_reflectors(H, T, T.z, m, false);      // dx = Q z
+            for (int i = tid; i < m; i += 32) dx[i] = T.z[i];
+          }
+          have_qg = true;
           __syncthreads();
-          { TIC; const bool okk = it != 0 || factor_spd(mu); TOC(2); if (!okk) { singular = true; break; } }
-          { TIC; solve_spd(t1); TOC(3); }
-          const double phiprime = -(1.0 / norm_dx) * block_dot(dx, t1, m, scratch);
-          mu = mu - (norm_dx / delta) * (phi / phiprime);
-          // dx = -(H + mu I) \ (Df' fx)
-          for (int e = tid; e < m * m; e += kHookThreads) W[e] = H[e] + ((e % m) == (e / m) ? mu : 0.0);
-          for (int i = tid; i < m; i += kHookThreads) dx[i] = -g[i];
-          __syncthreads();
-          { TIC; const bool okk = factor_spd(mu); TOC(2); if (!okk) { singular = true; break; } }
-          { TIC; solve_spd(dx); TOC(3); }
-          norm_dx = sqrt(block_dot(dx, dx, m, scratch));
-          if (fabs(norm_dx - delta) / delta <= 1e-4) break;
+          TOC(3);
         }
+        const bool singular = mu_status != 0;
         if (singular) { exit_reason = CA_EXIT_SINGULAR; xtol_exit = true; break; }
       }
       block_gemv(Df, dx, t1, m, false);  // Df dx
@@ -614,10 +719,14 @@ extern "C" int32_t ca_hookstep_solve_model(ca_model* h, const double* R, const d
       if (!(R[s] != 0.0)) fail(CA_ERR_INVALID, "R must be non-zero");
     h->bind();
     const int m = (int)h->m;
-    const size_t smem = ((size_t)3 * m * m + 9 * (size_t)m + 8) * sizeof(double) + (2 * (size_t)m + 4) * sizeof(int);
+    // Df, H, W (the factorisation workspace; it also holds the mu search's vectors: Tridiag::kDoubles = 14 per mode)
+    const size_t wdoubles = std::max((size_t)m * m, (size_t)14 * m);
+    const size_t smem = ((size_t)2 * m * m + wdoubles + 9 * (size_t)m + 8) * sizeof(double) + (2 * (size_t)m + 4) * sizeof(int);
     int optin = 0;
     CA_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    if (smem > (size_t)optin || getenv("CA_HOOK_LARGE")) {  // beyond the one-CTA solver: global-memory solver, still device-resident
+    cudaFuncAttributes fattr;
+    CA_CUDA(cudaFuncGetAttributes(&fattr, hookstep_kernel));  // the kernel's static shared memory counts against the same limit
+    if (smem + fattr.sharedSizeBytes > (size_t)optin || getenv("CA_HOOK_LARGE")) {  // beyond the one-CTA solver: global-memory solver, still device-resident
       hookstep_solve_large(h, R, Xguess, nsolve, p, X_out, success, logs);
       return;
     }
