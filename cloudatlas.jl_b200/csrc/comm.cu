@@ -273,6 +273,21 @@ int32_t ca_assemble_sharded(ca_comm* comm, double alpha, double gamma, const int
     for (int r = 0; r < world; ++r) noff[(size_t)r + 1] = noff[(size_t)r] + nnz_of[(size_t)r];
     const int64_t nnz = noff[(size_t)world];
 
+    // ---- how the COO arrays travel (the matrices always go as broadcasts):
+    //   broadcasts  every piece of every slab broadcast in place (no padding, no extra pass)              -- the default
+    //   padded      slabs padded to the largest one, ONE in-place ncclAllGather per array, then a device-to-device
+    //               compaction into the contiguous arrays                                      -- CA_GATHER=allgather
+    // Measured at m = 2962 (9.48 GB), both in one run: 2 GPUs 8.2 ms (broadcasts) / 12.4 ms (padded); 8 GPUs 28.8 ms
+    // (288 GB/s bus bandwidth) / 31.1 ms -- NCCL's own all-gather is no faster than the 64 grouped broadcasts on this
+    // node, and the compaction comes on top.
+    bool padded = false;
+    if (const char* e = getenv("CA_GATHER")) padded = e[0] == 'a';
+    size_t nmax = 0;
+    for (int r = 0; r < world; ++r) nmax = std::max(nmax, (size_t)nnz_of[(size_t)r]);
+    if (nmax == 0) padded = false;
+    std::vector<DeviceBuffer<int64_t>> pad_i(nloc), pad_j(nloc), pad_k(nloc);
+    std::vector<DeviceBuffer<double>> pad_v(nloc);
+
     // ---- full arrays on every device, own slab copied into place
     std::vector<cudaEvent_t> ev0(nloc), ev1(nloc);
     for (size_t d = 0; d < nloc; ++d) {
@@ -305,23 +320,28 @@ int32_t ca_assemble_sharded(ca_comm* comm, double alpha, double gamma, const int
       F.oj.alloc((size_t)nnz);
       F.ok.alloc((size_t)nnz);
       F.oval.alloc((size_t)nnz);
-      const size_t n = (size_t)S.nnz, at = (size_t)noff[(size_t)r];
+      const size_t n = (size_t)S.nnz;
+      if (padded) {  // own slab into its slot of the staging arrays
+        pad_i[d].alloc((size_t)world * nmax);
+        pad_j[d].alloc((size_t)world * nmax);
+        pad_k[d].alloc((size_t)world * nmax);
+        pad_v[d].alloc((size_t)world * nmax);
+      }
+      const size_t at = padded ? (size_t)r * nmax : (size_t)noff[(size_t)r];
       if (n) {
-        CA_CUDA(cudaMemcpyAsync(F.oi.ptr + at, S.oi.ptr, n * 8, cudaMemcpyDeviceToDevice, c->streams[d]));
-        CA_CUDA(cudaMemcpyAsync(F.oj.ptr + at, S.oj.ptr, n * 8, cudaMemcpyDeviceToDevice, c->streams[d]));
-        CA_CUDA(cudaMemcpyAsync(F.ok.ptr + at, S.ok.ptr, n * 8, cudaMemcpyDeviceToDevice, c->streams[d]));
-        CA_CUDA(cudaMemcpyAsync(F.oval.ptr + at, S.oval.ptr, n * 8, cudaMemcpyDeviceToDevice, c->streams[d]));
+        CA_CUDA(cudaMemcpyAsync((padded ? pad_i[d].ptr : F.oi.ptr) + at, S.oi.ptr, n * 8, cudaMemcpyDeviceToDevice, c->streams[d]));
+        CA_CUDA(cudaMemcpyAsync((padded ? pad_j[d].ptr : F.oj.ptr) + at, S.oj.ptr, n * 8, cudaMemcpyDeviceToDevice, c->streams[d]));
+        CA_CUDA(cudaMemcpyAsync((padded ? pad_k[d].ptr : F.ok.ptr) + at, S.ok.ptr, n * 8, cudaMemcpyDeviceToDevice, c->streams[d]));
+        CA_CUDA(cudaMemcpyAsync((padded ? pad_v[d].ptr : F.oval.ptr) + at, S.oval.ptr, n * 8, cudaMemcpyDeviceToDevice, c->streams[d]));
       }
       CA_CUDA(cudaEventCreate(&ev0[d]));
       CA_CUDA(cudaEventCreate(&ev1[d]));
       CA_CUDA(cudaEventRecord(ev0[d], c->streams[d]));
     }
 
-    // ---- the all-gather(-v): every piece of every rank's slab broadcast in place, one group.  Measured (m = 2962,
-    // 9.48 GB): 8.2 ms between 2 GPUs (580 GB/s bus bandwidth), 28.9 ms on 8 GPUs (287 GB/s).  The alternative -- the
-    // same pieces as grouped point-to-point ncclSend / ncclRecv, all pairs at once -- was built and measured: equal at
-    // 2 GPUs, SLOWER at 8 (40.2 ms) and 6.9 s of connection set-up for the 56 pairs on first use; a padded
-    // ncclAllGather would need a compaction pass over the 9.5 GB afterwards.
+    // ---- the all-gather(-v), one group.  (Also built and measured: the same pieces as grouped point-to-point
+    // ncclSend / ncclRecv, all pairs at once -- equal at 2 GPUs, 40.2 ms at 8 and 6.9 s of connection set-up for the 56
+    // pairs on first use.)
     CA_NCCL(nccl().GroupStart());
     for (size_t d = 0; d < nloc; ++d) {
       ca_assembly& F = *full[d];
@@ -334,17 +354,35 @@ int32_t ca_assemble_sharded(ca_comm* comm, double alpha, double gamma, const int
             double* p = fm[q] + (size_t)bounds[(size_t)r] * m;
             CA_NCCL(nccl().Broadcast(p, p, rows * (size_t)m, ncclFloat64, r, c->comms[d], c->streams[d]));
           }
-        if (n) {
+        if (n && !padded) {
           CA_NCCL(nccl().Broadcast(F.oi.ptr + at, F.oi.ptr + at, n, ncclInt64, r, c->comms[d], c->streams[d]));
           CA_NCCL(nccl().Broadcast(F.oj.ptr + at, F.oj.ptr + at, n, ncclInt64, r, c->comms[d], c->streams[d]));
           CA_NCCL(nccl().Broadcast(F.ok.ptr + at, F.ok.ptr + at, n, ncclInt64, r, c->comms[d], c->streams[d]));
           CA_NCCL(nccl().Broadcast(F.oval.ptr + at, F.oval.ptr + at, n, ncclFloat64, r, c->comms[d], c->streams[d]));
         }
       }
+      if (padded) {  // in place: the send buffer is this rank's slot of the receive buffer
+        const size_t mine = (size_t)c->ranks[d] * nmax;
+        CA_NCCL(nccl().AllGather(pad_i[d].ptr + mine, pad_i[d].ptr, nmax, ncclInt64, c->comms[d], c->streams[d]));
+        CA_NCCL(nccl().AllGather(pad_j[d].ptr + mine, pad_j[d].ptr, nmax, ncclInt64, c->comms[d], c->streams[d]));
+        CA_NCCL(nccl().AllGather(pad_k[d].ptr + mine, pad_k[d].ptr, nmax, ncclInt64, c->comms[d], c->streams[d]));
+        CA_NCCL(nccl().AllGather(pad_v[d].ptr + mine, pad_v[d].ptr, nmax, ncclFloat64, c->comms[d], c->streams[d]));
+      }
     }
     CA_NCCL(nccl().GroupEnd());
     for (size_t d = 0; d < nloc; ++d) {
       CA_CUDA(cudaSetDevice(c->devices[d]));
+      if (padded) {  // compaction: slot r -> its place in the contiguous arrays
+        ca_assembly& F = *full[d];
+        for (int r = 0; r < world; ++r) {
+          const size_t n = (size_t)nnz_of[(size_t)r], from = (size_t)r * nmax, to = (size_t)noff[(size_t)r];
+          if (!n) continue;
+          CA_CUDA(cudaMemcpyAsync(F.oi.ptr + to, pad_i[d].ptr + from, n * 8, cudaMemcpyDeviceToDevice, c->streams[d]));
+          CA_CUDA(cudaMemcpyAsync(F.oj.ptr + to, pad_j[d].ptr + from, n * 8, cudaMemcpyDeviceToDevice, c->streams[d]));
+          CA_CUDA(cudaMemcpyAsync(F.ok.ptr + to, pad_k[d].ptr + from, n * 8, cudaMemcpyDeviceToDevice, c->streams[d]));
+          CA_CUDA(cudaMemcpyAsync(F.oval.ptr + to, pad_v[d].ptr + from, n * 8, cudaMemcpyDeviceToDevice, c->streams[d]));
+        }
+      }
       CA_CUDA(cudaEventRecord(ev1[d], c->streams[d]));
     }
     for (size_t d = 0; d < nloc; ++d) {
