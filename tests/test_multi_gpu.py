@@ -57,10 +57,13 @@ def model_obs(ca, model, x):
 
 
 @pytest.mark.skipif("ngpus() < 2")
+@pytest.mark.parametrize("gather", ["bcast", "allgather"])
 @pytest.mark.parametrize("JKL,dense", [((2, 2, 3), False), ((3, 3, 12), False), ((2, 2, 3), True)], ids=["44d", "307", "44d-dense"])
-def test_one_process_many_devices(ca, JKL, dense):
-    """ca_comm_init_all: every device ends up with the full operator, bit-identical to the single-GPU assembly."""
+def test_one_process_many_devices(ca, JKL, dense, gather, monkeypatch):
+    """ca_comm_init_all: every device ends up with the full operator, bit-identical to the single-GPU assembly -- by the
+    default gather (grouped in-place broadcasts) and by the padded ncclAllGather + compaction (CA_GATHER=allgather)."""
     import torch
+    monkeypatch.setenv("CA_GATHER", gather)
     n = min(ngpus(), 4)
     ijkl = ca.basisIndices(*JKL, nagata(ca))
     ref = ca.AssemblySlab(1.0, 2.0, ijkl, dense=dense)
