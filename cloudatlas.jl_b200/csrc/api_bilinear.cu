@@ -377,7 +377,8 @@ extern "C" int32_t ca_selftest_pack(const int64_t* ijk, const double* val, int64
           seen[(size_t)t]++;
           const bool first_part = q < P.sched_off[w] + P.sched_nt2[w];
           bad += first_part != (P.tiles[(size_t)t].nt >= 2);  // (three n-tiles only occur in windowed packs, which do not use the schedule)
-          (P.tiles[(size_t)t].nt == 2 ? ks2 : ks1) += P.tiles[(size_t)t].nks;
+          (P.tiles[(size_t)t].nt == 2 ? ks2 : ks1) += (P.tiles[(size_t)t].nks + kStreamAlign - 1) / kStreamAlign * kStreamAlign;
+          if (P.stream_layout) bad += P.tiles[(size_t)t].ks_begin % kStreamAlign != 0;
         }
         if (P.stream_layout) bad += ks2 != P.sched_ks2[w] || ks1 != P.sched_ks1[w];
       }

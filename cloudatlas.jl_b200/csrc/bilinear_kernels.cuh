@@ -301,6 +301,7 @@ struct WarpSchedule {
 // four k-steps ahead into registers left ~14 % of the issue slots waiting on L2.  Operator values are consumed last
 // in a k-step (by the DMMAs) and stay register-prefetched.
 constexpr int kPairBatch = 8;                    // k-steps per cp.async group (256 B)
+static_assert(kPairBatch == kStreamAlign, "tiles start on batch boundaries of the pair stream (pack.cpp)");
 constexpr int kPairBatches = 4;                  // ring = 4 batches = 32 k-steps = 1 KB per warp
 constexpr int kPairRingBytes = kPairBatch * kPairBatches * 32;
 
@@ -324,17 +325,17 @@ struct PairRing {
 #pragma unroll
     for (int b = 0; b < kPairBatches - 1; ++b) issue_batch(b, lane);
   }
-  // pair word of k-step g for this lane's column; refills one batch ahead at batch boundaries
-  __device__ __forceinline__ uint2 next(int lane) {
-    if ((g & (kPairBatch - 1)) == 0) {  // warp-uniform
-      __syncwarp();                     // the batch slot refilled now was consumed by every lane
-      issue_batch(g / kPairBatch + kPairBatches - 1, lane);
-      asm volatile("cp.async.wait_group %0;\n" ::"n"(kPairBatches - 1) : "memory");
-      __syncwarp();                     // batch g / kPairBatch has landed for all lanes
-    }
-    const uint2 w = reinterpret_cast<const uint2*>(ring)[(g & (kPairBatch * kPairBatches - 1)) * 4 + (lane & 3)];
-    ++g;
-    return w;
+  // g is on a batch boundary (tiles start on one, pack.cpp): refills one batch ahead and makes the batch of k-steps
+  // g .. g + kPairBatch - 1 readable
+  __device__ __forceinline__ void batch(int lane) const {
+    __syncwarp();                       // the batch slot refilled now was consumed by every lane
+    issue_batch(g / kPairBatch + kPairBatches - 1, lane);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(kPairBatches - 1) : "memory");
+    __syncwarp();                       // batch g / kPairBatch has landed for all lanes
+  }
+  // pair word of k-step g + u (u < kPairBatch) for this lane's column
+  __device__ __forceinline__ uint2 word(int u, int lane) const {
+    return reinterpret_cast<const uint2*>(ring)[((g & (kPairBatch * kPairBatches - 1)) + u) * 4 + (lane & 3)];
   }
   __device__ __forceinline__ void end() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 };
@@ -365,23 +366,34 @@ __device__ __forceinline__ void tile_accumulate_ring(const double* __restrict__ 
     if constexpr (FACT) kstep_factored<MT, NT>(pw, bv, xsb, r8, xa, y, acc);
     else kstep<MT, NT, MODE>(pw, bv, xsb, ysb, r8, xa, va, acc);
   };
+  // whole batches of the pair ring: one refill, then kPairBatch k-steps without a branch -- ptxas moves the shared-memory
+  // loads of the following k-steps up between the DMMAs of the current one (with a refill check in front of every
+  // k-step each of them was a basic block of its own and exposed its LDS -> DMUL -> DMMA chain)
+  static_assert(kPairBatch % kPrefetch == 0, "the value registers rotate with period kPrefetch");
   int i = 0;
-  for (; i + kPrefetch <= nks; i += kPrefetch) {
+  for (; i + kPairBatch <= nks; i += kPairBatch) {
+    pr.batch(lane);
 #pragma unroll
-    for (int u = 0; u < kPrefetch; ++u) {
-      uint2 pw = pr.next(lane);
+    for (int u = 0; u < kPairBatch; ++u) {
+      uint2 pw = pr.word(u, lane);
       if (i + u == 0) pw.x &= ~kSameA;  // first k-step of a tile loads its first factors
-      one(pw, pf.bv[u]);
-      prefetch_vals<NT>(pf.bv[u], vp, min(i + u + kPrefetch, nks - 1));
+      one(pw, pf.bv[u % kPrefetch]);
+      prefetch_vals<NT>(pf.bv[u % kPrefetch], vp, min(i + u + kPrefetch, nks - 1));
     }
+    pr.g += kPairBatch;
   }
+  if (i < nks) {  // the tile's last, partial batch; the stream continues on the next batch boundary
+    pr.batch(lane);
 #pragma unroll
-  for (int u = 0; u < kPrefetch - 1; ++u) {
-    if (i + u < nks) {
-      uint2 pw = pr.next(lane);
-      if (i + u == 0) pw.x &= ~kSameA;
-      one(pw, pf.bv[u]);
+    for (int u = 0; u < kPairBatch - 1; ++u) {
+      if (i + u < nks) {
+        uint2 pw = pr.word(u, lane);
+        if (i + u == 0) pw.x &= ~kSameA;
+        one(pw, pf.bv[u % kPrefetch]);
+        if (u + kPrefetch < kPairBatch - 1) prefetch_vals<NT>(pf.bv[u % kPrefetch], vp, min(i + u + kPrefetch, nks - 1));
+      }
     }
+    pr.g += kPairBatch;
   }
   if constexpr (FACT) flush_run<MT, NT>(xa, y, acc);  // the tile's last run
 }
@@ -474,6 +486,13 @@ bilinear_warptile_kernel(const TileDesc* __restrict__ tiles, const int32_t* __re
     }
     __syncthreads();
     const int b = ws.off[warp], mid = b + ws.nt2[warp], e = ws.off[warp + 1];
+    // Two-n-tile k-steps saturate the FP64 pipe (8 DMMA + 4 DMUL), one-n-tile k-steps (4 + 4) keep it ~70 % busy: half
+    // the warps of every scheduler (warps 4-7) start with their one-n-tile tiles, so the two kinds overlap (-1.1 %)
+    if (warp & 4) {
+      run_my_tiles<MT, 1, MODE, FACT>(tiles, sched, mid, e, ws.ks1[warp], pairs, vals, rows, xs, ys, ring, lane, s0, nstates, OUT, ldo);
+      run_my_tiles<MT, 2, MODE, FACT>(tiles, sched, b, mid, ws.ks2[warp], pairs, vals, rows, xs, ys, ring, lane, s0, nstates, OUT, ldo);
+      continue;
+    }
     run_my_tiles<MT, 2, MODE, FACT>(tiles, sched, b, mid, ws.ks2[warp], pairs, vals, rows, xs, ys, ring, lane, s0, nstates, OUT, ldo);
     run_my_tiles<MT, 1, MODE, FACT>(tiles, sched, mid, e, ws.ks1[warp], pairs, vals, rows, xs, ys, ring, lane, s0, nstates, OUT, ldo);
   }

@@ -782,14 +782,18 @@ PackedHost finalize_pack(PackedHost P, std::vector<PackedHost>& parts, const std
         for (int q = P.sched_off[w]; q < P.sched_off[w + 1]; ++q) {
           TileDesc& T = P.tiles[P.sched[q]];
           const size_t p0 = (size_t)T.ks_begin * 4, v0 = (size_t)T.vals_off;
+          // every tile starts on a batch boundary of the kernel's pair ring (kStreamAlign k-steps): the k-step loop then
+          // runs in whole batches with one ring refill per batch and no branch inside
+          np.resize((np.size() + 4 * kStreamAlign - 1) / (4 * kStreamAlign) * (4 * kStreamAlign), 0u);
           T.ks_begin = (int32_t)(np.size() / 4);
           T.vals_off = vals_at;
           vals_at += (int64_t)T.nks * T.nt * 32;
           np.insert(np.end(), P.pairs.begin() + p0, P.pairs.begin() + p0 + (size_t)T.nks * 4);
           if (have_vals) nv.insert(nv.end(), P.vals.begin() + v0, P.vals.begin() + v0 + (size_t)T.nks * T.nt * 32);
-          (T.nt == 2 ? P.sched_ks2[w] : P.sched_ks1[w]) += T.nks;
+          (T.nt == 2 ? P.sched_ks2[w] : P.sched_ks1[w]) += (T.nks + kStreamAlign - 1) / kStreamAlign * kStreamAlign;
         }
       }
+      np.resize((np.size() + 4 * kStreamAlign - 1) / (4 * kStreamAlign) * (4 * kStreamAlign), 0u);
       P.pairs.swap(np);
       if (have_vals) P.vals.swap(nv);
       P.stream_layout = true;

@@ -48,6 +48,7 @@ struct alignas(16) WindowDesc {
   int64_t pad_;
 };
 static_assert(sizeof(WindowDesc) == 48, "the windowed kernel copies descriptors as three 16-byte words");
+constexpr int kStreamAlign = 8;    // = kPairBatch of the whole-tile kernel (bilinear_kernels.cuh)
 constexpr int kWindowMaxKs = 448;  // k-steps per window (the kernel stages a window's pair words, 4 B per pair, in shared memory)
 
 struct PackedHost {
@@ -71,7 +72,8 @@ struct PackedHost {
   int32_t sched_nt2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double sched_imbalance = 0.0;
   // When the pack is not windowed the tiles of a warp are laid out contiguously in schedule order, so that a warp's
-  // pairs and values form one stream per nt class (sched_ks2 / sched_ks1 k-steps) that can be prefetched across tiles.
+  // pairs and values form one stream per nt class that can be prefetched across tiles; in the pair stream every tile
+  // starts on a multiple of kStreamAlign k-steps (sched_ks2 / sched_ks1: stream lengths in k-steps, padding included).
   int32_t sched_ks2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sched_ks1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool stream_layout = false;
   int64_t nterms = 0;           // merged non-zero terms
