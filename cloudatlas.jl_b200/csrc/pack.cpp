@@ -744,9 +744,10 @@ PackedHost finalize_pack(PackedHost P, std::vector<PackedHost>& parts, const std
     std::vector<int32_t> idx(P.tiles.size());
     std::iota(idx.begin(), idx.end(), 0);
     // cycles of the FP64 pipe per k-step: 4 nt DMMAs x 16 plus the four pair products (tools/dmma_dmul_mix.cu)
-    // (measured at 307 modes, round 2: a one-n-tile k-step really costs ~110 -- it is shared-memory bound -- but weights of
-    // 100 / 111 / 125 change the time by -0.5 / +1.2 / +2.6 %: the schedule's granularity, not its weights, is what is left)
-    auto weight = [&](int32_t t) { return (int64_t)P.tiles[t].nks * (P.tiles[t].nt == 2 ? 144 : 82) + 40; };
+    // (a one-n-tile k-step, 4 DMMA + 4 DMUL, takes 0.78 of the time of a two-n-tile one in the kernel -- its phases keep
+    // the pipe only ~70 % busy; measured with weights 82 / 100 / 112 / 125: 13.38 / 13.30 / 13.50 / 13.73 ms per 2*10^5
+    // states at 307 modes -- the schedule's granularity matters more than the exact weight)
+    auto weight = [&](int32_t t) { return (int64_t)P.tiles[t].nks * (P.tiles[t].nt == 2 ? 144 : 100) + 40; };
     std::stable_sort(idx.begin(), idx.end(), [&](int32_t x, int32_t y) { return weight(x) > weight(y); });
     int64_t load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<int32_t> bins[8];
