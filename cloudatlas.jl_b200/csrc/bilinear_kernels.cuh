@@ -862,7 +862,9 @@ struct ValRing {
 // last share can end on a ragged batch (the slow, not unrolled path); which warp takes which part rotates with g.
 // (Tried and dropped: uneven shares in the first / last window of a tile, to spread the warps' window turn-overs in
 // time -- no gain once the one-vector mode runs two teams, and a loss combined with the rotation; one team of 14 + 2
-// warps for the two-vector modes with shares weighted 3 : 4 to balance the schedulers -- 6 % slower than 12 + 4.)
+// warps for the two-vector modes with shares weighted 3 : 4 to balance the schedulers -- 6 % slower than 12 + 4; the
+// second team walking the one-n-tile windows first, as the whole-tile kernel's warps 4-7 do -- 4-7 % slower: the two
+// teams then stream different parts of the operator and no longer share it in L2.)
 template <int KB, int NW>
 __device__ __forceinline__ void batch_share(int nks, int warp, int g, int& k0, int& k1) {
   const int nb = (nks + KB - 1) / KB;
