@@ -34,6 +34,18 @@ void DevicePack::upload_meta(const PackedHost& P) {
     nwin_nt2 += P.tiles[W.tile].nt == 2;
   }
   windows.upload(P.windows.data(), P.windows.size());
+  tile_first_window.clear();
+  dmma_before_tile.clear();
+  int64_t dm = 0;
+  for (size_t g = 0; g < P.windows.size(); ++g) {
+    if (g == 0 || P.windows[g - 1].last) {
+      tile_first_window.push_back((int32_t)g);
+      dmma_before_tile.push_back(dm);
+    }
+    dm += (int64_t)P.windows[g].nks * P.windows[g].nt;
+  }
+  tile_first_window.push_back((int32_t)P.windows.size());
+  dmma_before_tile.push_back(dm);
   modes.upload(P.modes.data(), P.modes.size());
   sched.upload(P.sched.data(), P.sched.size());
   for (int w = 0; w < 9; ++w) sched_off[w] = P.sched_off[w];
@@ -218,8 +230,29 @@ void launch_windowed_nt(const DevicePack& op, const double* dX, const double* dY
   if (per_sm < 1) fail(CA_ERR_UNSUPPORTED, "windowed kernel does not fit (smem %zu B)", smem);
   constexpr int teams = WinCfg<MODE, NT3>::TEAMS;  // blocks of 32 states per CTA and pass
   const int64_t nblocks = ((nstates + 8 * kWinMT - 1) / (8 * kWinMT) + teams - 1) / teams;
-  const int grid = (int)std::min<int64_t>(nblocks, (int64_t)device_cfg().sms * per_sm);
-  kern<<<grid, threads, smem, stream>>>(op.windows.ptr, op.nwin, op.nwin_nt3, op.nwin_nt2, op.modes.ptr, op.pairs_windowed(),
+  const int64_t slots = (int64_t)device_cfg().sms * per_sm;
+  // ensembles too small to give every SM a block of states: the tiles (independent output rows) are split into `parts`
+  // ranges of about equal DMMA count and every block of states is walked by `parts` CTAs, one range each
+  WindowParts wp;
+  wp.n = 1;
+  if (nblocks < slots && !getenv("CA_WIN_NO_SPLIT")) {
+    const int ntl = (int)op.tile_first_window.size() - 1;
+    wp.n = (int)std::max<int64_t>(1, std::min<int64_t>({slots / nblocks, (int64_t)WindowParts::kMax, (int64_t)ntl}));
+  }
+  wp.first[0] = 0;
+  wp.first[wp.n] = op.nwin;
+  if (wp.n > 1) {
+    const int ntl = (int)op.tile_first_window.size() - 1;
+    const int64_t total = op.dmma_before_tile[(size_t)ntl];
+    int t = 0;
+    for (int p = 1; p < wp.n; ++p) {  // first tile boundary at or after p / n of the work
+      const int64_t want = total * p / wp.n;
+      while (t < ntl && op.dmma_before_tile[(size_t)t] < want) ++t;
+      wp.first[p] = op.tile_first_window[(size_t)t];
+    }
+  }
+  const int grid = (int)std::min<int64_t>(nblocks, slots / wp.n) * wp.n;
+  kern<<<grid, threads, smem, stream>>>(op.windows.ptr, wp, op.nwin_nt3, op.nwin_nt2, op.modes.ptr, op.pairs_windowed(),
                                         op.vals.ptr, op.rows.ptr, wmax, op.nin - 1, dX, dY, nstates, ldx, dOUT, ldo);
   CA_CUDA(cudaGetLastError());
   count_launch();

@@ -33,6 +33,9 @@ struct DevicePack {
   int32_t window_modes = 0, nwin = 0, nwin_nt3 = 0, nwin_nt2 = 0, max_window_modes = 0;
   DeviceBuffer<WindowDesc> windows;
   DeviceBuffer<int32_t> modes;
+  // tile boundaries in the window list, with the DMMAs before them: small ensembles split the windows among CTAs there
+  std::vector<int32_t> tile_first_window;  // ntiles_with_windows + 1 entries, the last one = nwin
+  std::vector<int64_t> dmma_before_tile;   // same length: cumulative nks * nt
   void upload(const PackedHost& P);
   // everything but the values (device build: the values are placed on the device, DevicePack::vals is filled there)
   void upload_meta(const PackedHost& P);

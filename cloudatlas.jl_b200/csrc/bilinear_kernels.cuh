@@ -650,6 +650,14 @@ struct WinCfg {
   static constexpr bool SEPRED = TEAMS == 1 && (MODE == MODE_QUAD || NT3);
 };
 
+// Window ranges [first[p], first[p+1]) for the CTAs that share a block of states (tile boundaries; n == 1: one CTA
+// walks all windows)
+struct WindowParts {
+  static constexpr int kMax = 32;
+  int n;
+  int first[kMax + 1];
+};
+
 struct RingPos {  // position in the ring of window slots: slot index and the parity of its current use
   int slot = 0;
   uint32_t phase = 0;
@@ -702,7 +710,7 @@ __device__ __forceinline__ WinSmem carve_window_smem(double* smem, int wmax) {
 
 // ---- producer warps: stage every window of every state block this CTA owns, in consumption order
 template <int MODE, bool NT3>
-__device__ __forceinline__ void window_producer(const WindowDesc* __restrict__ windows, int nwin,
+__device__ __forceinline__ void window_producer(const WindowDesc* __restrict__ windows, int w0, int w1, int nparts,
                                                 const int32_t* __restrict__ modes, const uint32_t* __restrict__ pairs,
                                                 const WinSmem& S, int one_mode, const double* __restrict__ X,
                                                 const double* __restrict__ Y, int64_t nstates, int64_t ldx, int team,
@@ -719,7 +727,7 @@ __device__ __forceinline__ void window_producer(const WindowDesc* __restrict__ w
   const int h2 = 2 * (lane & 15), sub = lane >> 4;
   const double* const one_y = MODE == MODE_JVP ? kRowOfZeros : kRowOfOnes;
   RingPos pos;
-  for (int64_t blk = (int64_t)blockIdx.x * TEAMS + team; blk < nblocks; blk += (int64_t)gridDim.x * TEAMS) {
+  for (int64_t blk = (int64_t)(blockIdx.x / nparts) * TEAMS + team; blk < nblocks; blk += (int64_t)(gridDim.x / nparts) * TEAMS) {
     const int64_t s0 = blk * ROW;
     // this lane's piece of a state row: byte count inside the ensemble (0: beyond the last state -> zero fill)
     const int64_t sw = s0 + h2;
@@ -727,7 +735,7 @@ __device__ __forceinline__ void window_producer(const WindowDesc* __restrict__ w
     const int nbytes_n = s0 + lane < nstates ? 8 : 0;
     const int64_t soff = wide ? (nbytes_w ? sw : 0) : (nbytes_n ? s0 + lane : 0);
     const int coff = wide ? h2 : lane;  // the same piece of a constant row
-    for (int g = 0; g < nwin; ++g, pos.next<WinCfg<MODE, NT3>::SLOTS>()) {
+    for (int g = w0; g < w1; ++g, pos.next<WinCfg<MODE, NT3>::SLOTS>()) {
       const WindowDesc* W = windows + g;
       const int nks = __ldg(&W->nks), nmodes = __ldg(&W->nmodes);
       const int32_t* mp = modes + __ldg(&W->modes_off);
@@ -988,7 +996,7 @@ __device__ __forceinline__ void run_windows(const WindowDesc* __restrict__ windo
 // two-n-tile kernel does not change with it
 template <int MODE, bool NT3>
 __global__ void __launch_bounds__(WinCfg<MODE, NT3>::THREADS, 1)
-bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, int nwin, int nwin_nt3, int nwin_nt2,
+bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, const WindowParts parts, int nwin_nt3, int nwin_nt2,
                          const int32_t* __restrict__ modes, const uint32_t* __restrict__ pairs,
                          const double* __restrict__ vals, const int32_t* __restrict__ rows, int wmax, int one_mode,
                          const double* __restrict__ X, const double* __restrict__ Y, int64_t nstates, int64_t ldx,
@@ -998,7 +1006,10 @@ bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, int nwin, int n
   constexpr int NWC = Cfg::NWC, NWP = Cfg::NWP, TEAMS = Cfg::TEAMS;
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (nwin <= 0) return;
+  // this CTA's range of windows (whole tiles): CTAs blockIdx.x % parts.n of the same block of states share the tiles
+  const int part = blockIdx.x % parts.n;
+  const int w0 = parts.first[part], w1 = parts.first[part + 1];
+  if (w1 <= w0) return;
   const size_t team_doubles = windowed_team_bytes<MODE, NT3>(wmax) / sizeof(double);
   if (tid == 0) {
     for (int t = 0; t < TEAMS; ++t) {
@@ -1014,21 +1025,21 @@ bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, int nwin, int n
   const int team = producer ? (warp - TEAMS * NWC) / NWP : warp / NWC;
   const WinSmem S = carve_window_smem<MODE, NT3>(smem + team * team_doubles, wmax);
   if (producer) {
-    window_producer<MODE, NT3>(windows, nwin, modes, pairs, S, one_mode, X, Y, nstates, ldx, team,
+    window_producer<MODE, NT3>(windows, w0, w1, parts.n, modes, pairs, S, one_mode, X, Y, nstates, ldx, team,
                                tid - (TEAMS * NWC + team * NWP) * 32);
     return;
   }
   const int cwarp = warp - team * NWC;  // consumer warp within the team
   const int64_t nblocks = (nstates + ROW - 1) / ROW;
   RingPos pos;
-  for (int64_t blk = (int64_t)blockIdx.x * TEAMS + team; blk < nblocks; blk += (int64_t)gridDim.x * TEAMS) {
+  const int c3 = nwin_nt3, c2 = nwin_nt3 + nwin_nt2;  // class boundaries in the window list: [0, c3) three n-tiles, [c3, c2) two, rest one
+  for (int64_t blk = (int64_t)(blockIdx.x / parts.n) * TEAMS + team; blk < nblocks; blk += (int64_t)(gridDim.x / parts.n) * TEAMS) {
     const int64_t s0 = blk * ROW;
     if constexpr (NT3)
-      run_windows<3, MODE, NT3>(windows, 0, nwin_nt3, vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo, 1 + team);
-    run_windows<2, MODE, NT3>(windows, nwin_nt3, nwin_nt3 + nwin_nt2, vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo,
+      run_windows<3, MODE, NT3>(windows, w0, min(w1, c3), vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo, 1 + team);
+    run_windows<2, MODE, NT3>(windows, max(w0, c3), min(w1, c2), vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo,
                               1 + team);
-    run_windows<1, MODE, NT3>(windows, nwin_nt3 + nwin_nt2, nwin, vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo,
-                              1 + team);
+    run_windows<1, MODE, NT3>(windows, max(w0, c2), w1, vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo, 1 + team);
   }
 }
 
