@@ -837,7 +837,7 @@ extern "C" int32_t ca_model_kernel_path(ca_model* h, int64_t nstates, int32_t* p
   return guarded([&] {
     if (!h || !path) fail(CA_ERR_INVALID, "null argument");
     if (h->m <= kJitMaxM && nstates >= kJitMinStates && h->small.ready) *path = 2;
-    else if (nstates > kStreamMaxStates && batched_fits(h->op, MODE_QUAD)) *path = batched_variant(h->op);
+    else if (nstates > kStreamMaxStates && batched_fits(h->op, MODE_QUAD)) *path = batched_variant(h->op, nstates);
     else *path = 1;
     if (source) *source = h->small.source.c_str();
     if (log) *log = h->small.log.c_str();

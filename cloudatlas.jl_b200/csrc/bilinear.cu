@@ -46,6 +46,9 @@ void DevicePack::upload_meta(const PackedHost& P) {
   }
   tile_first_window.push_back((int32_t)P.windows.size());
   dmma_before_tile.push_back(dm);
+  dmma_before_tile_index.assign(P.tiles.size() + 1, 0);
+  for (size_t t = 0; t < P.tiles.size(); ++t)
+    dmma_before_tile_index[t + 1] = dmma_before_tile_index[t] + (int64_t)P.tiles[t].nks * P.tiles[t].nt;
   modes.upload(P.modes.data(), P.modes.size());
   sched.upload(P.sched.data(), P.sched.size());
   for (int w = 0; w < 9; ++w) sched_off[w] = P.sched_off[w];
@@ -149,7 +152,32 @@ void launch_warptile(const DevicePack& op, const double* dX, const double* dY, i
 template <int MT, int MODE>
 void launch_one(const DevicePack& op, const double* dX, const double* dY, int64_t nstates, int64_t ldx,
                 double* dOUT, int64_t ldo, cudaStream_t stream) {
-  if (op.stream_layout && op.sched_imbalance <= kMaxSchedImbalance && !getenv("CA_FORCE_KSPLIT")) {
+  auto kern = bilinear_batched_kernel<MT, MODE>;
+  const size_t smem = batched_smem_bytes<MT, MODE>(op.nin);
+  CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  const int64_t nblocks = (nstates + 8 * MT - 1) / (8 * MT);
+  const int64_t slots = (int64_t)device_cfg().sms * std::max(per_sm, 1);
+  // Ensembles with fewer blocks of states than CTA slots: the k-split kernel with the TILES (independent output rows)
+  // divided among `parts` CTAs per block of states, instead of one CTA (whole tiles per warp) per block and an idle
+  // machine -- 1,000 states of the 307-mode model otherwise take as long as 9,472
+  WindowParts tp;
+  tp.n = 1;
+  if (per_sm >= 1 && nblocks * 2 <= slots && op.ntiles >= 2 && !getenv("CA_WIN_NO_SPLIT"))
+    tp.n = (int)std::min<int64_t>({slots / nblocks, (int64_t)WindowParts::kMax, (int64_t)op.ntiles});
+  tp.first[0] = 0;
+  tp.first[tp.n] = op.ntiles;
+  if (tp.n > 1) {
+    const int64_t total = op.dmma_before_tile_index[(size_t)op.ntiles];
+    int t = 0;
+    for (int p = 1; p < tp.n; ++p) {
+      const int64_t want = total * p / tp.n;
+      while (t < op.ntiles && op.dmma_before_tile_index[(size_t)t] < want) ++t;
+      tp.first[p] = t;
+    }
+  }
+  if (tp.n == 1 && op.stream_layout && op.sched_imbalance <= kMaxSchedImbalance && !getenv("CA_FORCE_KSPLIT")) {
     // packs in factored pair order: the quadratic evaluation needs no pair products (bilinear_kernels.cuh)
     if (MODE == MODE_QUAD && op.symmetric && op.pair_order == kOrderFactored && !getenv("CA_NO_FACTORED"))
       launch_warptile<MT, MODE_QUAD, true>(op, dX, dY, nstates, ldx, dOUT, ldo, stream);
@@ -157,15 +185,9 @@ void launch_one(const DevicePack& op, const double* dX, const double* dY, int64_
       launch_warptile<MT, MODE>(op, dX, dY, nstates, ldx, dOUT, ldo, stream);
     return;
   }
-  auto kern = bilinear_batched_kernel<MT, MODE>;
-  const size_t smem = batched_smem_bytes<MT, MODE>(op.nin);
-  CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  CA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
   if (per_sm < 1) fail(CA_ERR_UNSUPPORTED, "batched kernel does not fit (smem %zu B)", smem);
-  const int64_t nblocks = (nstates + 8 * MT - 1) / (8 * MT);
-  const int grid = (int)std::min<int64_t>(nblocks, (int64_t)device_cfg().sms * per_sm);
-  kern<<<grid, kThreads, smem, stream>>>(op.tiles.ptr, op.ntiles, op.nt2_tiles, op.pairs_for(MT), op.vals.ptr,
+  const int grid = (int)std::min<int64_t>(nblocks, slots / tp.n) * tp.n;
+  kern<<<grid, kThreads, smem, stream>>>(op.tiles.ptr, tp, op.nt2_tiles, op.pairs_for(MT), op.vals.ptr,
                                          op.rows.ptr, op.nin, dX, dY, nstates, ldx, dOUT, ldo);
   CA_CUDA(cudaGetLastError());
   count_launch();
@@ -199,8 +221,11 @@ int window_modes_for(int32_t m) {
   return batched_smem_bytes<4, MODE_JVP>(m + 1) <= (size_t)227 * 1024 ? 0 : kWindowModes;
 }
 
-int batched_variant(const DevicePack& op) {
+int batched_variant(const DevicePack& op, int64_t nstates) {
   if (op.window_modes > 0) return 4;
+  // small ensembles (fewer blocks of 32 states than half the CTA slots): k-split kernel with the tiles divided among CTAs
+  const int64_t nblocks = (nstates + 31) / 32, slots = 2 * (int64_t)device_cfg().sms;
+  if (nstates > 0 && nblocks * 2 <= slots && op.ntiles >= 2 && !getenv("CA_WIN_NO_SPLIT")) return 3;
   return op.stream_layout && op.sched_imbalance <= kMaxSchedImbalance && !getenv("CA_FORCE_KSPLIT") ? 0 : 3;
 }
 

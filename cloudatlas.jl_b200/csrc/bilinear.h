@@ -36,6 +36,7 @@ struct DevicePack {
   // tile boundaries in the window list, with the DMMAs before them: small ensembles split the windows among CTAs there
   std::vector<int32_t> tile_first_window;  // ntiles_with_windows + 1 entries, the last one = nwin
   std::vector<int64_t> dmma_before_tile;   // same length: cumulative nks * nt
+  std::vector<int64_t> dmma_before_tile_index;  // whole-tile packs: ntiles + 1 entries in the order of `tiles`
   void upload(const PackedHost& P);
   // everything but the values (device build: the values are placed on the device, DevicePack::vals is filled there)
   void upload_meta(const PackedHost& P);
@@ -67,7 +68,7 @@ int nt_max_for(int window_modes);
 // true if the DMMA ensemble kernel can hold a state tile of this operator in shared memory
 bool batched_fits(const DevicePack& op, int mode);
 // which DMMA ensemble kernel launch_batched picks: 0 whole tiles per warp, 3 k-steps split across warps, 4 windowed
-int batched_variant(const DevicePack& op);
+int batched_variant(const DevicePack& op, int64_t nstates = 0);
 constexpr int64_t kStreamMaxStates = 16;  // at or below this many states the streaming kernel is used
 
 // Row-chunked CSR for the few-state ("streaming") evaluation: the operator is read once from HBM per pass

@@ -60,6 +60,14 @@ __host__ __device__ __forceinline__ uint32_t factor_word(int mode) {
   return (uint32_t)mode * (64u * MT) | ((uint32_t)swz<MT>(mode) << 3);
 }
 constexpr uint32_t kSameA = 1u;
+
+// Ranges [first[p], first[p+1]) of windows (windowed kernel) or tiles (k-split kernel) for the CTAs that share a block
+// of states when the ensemble has fewer blocks than the machine has CTA slots; n == 1: one CTA walks everything
+struct WindowParts {
+  static constexpr int kMax = 32;
+  int n;
+  int first[kMax + 1];
+};
 // windowed packs: rows are window-local (< 256), so both address words of a pair fit 16 bits and a pair is one word
 __host__ __device__ __forceinline__ uint32_t pack_window_pair(int a_local, int b_local, bool same_a) {
   return (factor_word<4>(a_local) | (same_a ? kSameA : 0u)) | (factor_word<4>(b_local) << 16);
@@ -507,7 +515,7 @@ inline size_t warptile_smem_bytes(int nin) {
 // X, Y: nstates x (nin-1) column-major with leading dimension ldx; OUT: nstates x m, ldo.
 template <int MT, int MODE>
 __global__ void __launch_bounds__(kThreads, 2)
-bilinear_batched_kernel(const TileDesc* __restrict__ tiles, int ntiles, int nt2_tiles,
+bilinear_batched_kernel(const TileDesc* __restrict__ tiles, const WindowParts parts, int nt2_tiles,
                         const uint2* __restrict__ pairs, const double* __restrict__ vals,
                         const int32_t* __restrict__ rows, int nin, const double* __restrict__ X,
                         const double* __restrict__ Y, int64_t nstates, int64_t ldx,
@@ -519,8 +527,11 @@ bilinear_batched_kernel(const TileDesc* __restrict__ tiles, int ntiles, int nt2_
   double* red = (MODE == MODE_QUAD ? smem + (size_t)nin * ROW : smem + 2 * (size_t)nin * ROW);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t nblocks = (nstates + ROW - 1) / ROW;
+  const int part = blockIdx.x % parts.n;  // this CTA's range of tiles
+  const int t0 = parts.first[part], t1 = parts.first[part + 1];
+  if (t1 <= t0) return;
 
-  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+  for (int64_t blk = blockIdx.x / parts.n; blk < nblocks; blk += gridDim.x / parts.n) {
     const int64_t s0 = blk * ROW;
     __syncthreads();  // everyone is done with the previous block's xs
     for (int o = threadIdx.x; o < nin * ROW; o += kThreads) {
@@ -537,8 +548,8 @@ bilinear_batched_kernel(const TileDesc* __restrict__ tiles, int ntiles, int nt2_
       if (MODE != MODE_QUAD) ys[j * ROW + (s ^ swz<MT>(j))] = vy;
     }
     __syncthreads();
-    run_tiles<MT, 2, MODE>(tiles, 0, nt2_tiles, pairs, vals, rows, xs, ys, red, warp, lane, s0, nstates, OUT, ldo);
-    run_tiles<MT, 1, MODE>(tiles, nt2_tiles, ntiles, pairs, vals, rows, xs, ys, red, warp, lane, s0, nstates, OUT, ldo);
+    run_tiles<MT, 2, MODE>(tiles, t0, min(t1, nt2_tiles), pairs, vals, rows, xs, ys, red, warp, lane, s0, nstates, OUT, ldo);
+    run_tiles<MT, 1, MODE>(tiles, max(t0, nt2_tiles), t1, pairs, vals, rows, xs, ys, red, warp, lane, s0, nstates, OUT, ldo);
   }
 }
 
@@ -648,14 +659,6 @@ struct WinCfg {
   static constexpr int THREADS = TEAMS * (NWC + NWP) * 32;
   static constexpr int SLOTS = (MODE == MODE_QUAD && TEAMS == 1) ? 3 : 2;
   static constexpr bool SEPRED = TEAMS == 1 && (MODE == MODE_QUAD || NT3);
-};
-
-// Window ranges [first[p], first[p+1]) for the CTAs that share a block of states (tile boundaries; n == 1: one CTA
-// walks all windows)
-struct WindowParts {
-  static constexpr int kMax = 32;
-  int n;
-  int first[kMax + 1];
 };
 
 struct RingPos {  // position in the ring of window slots: slot index and the parity of its current use
