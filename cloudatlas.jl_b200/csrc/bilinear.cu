@@ -125,6 +125,23 @@ const LaunchCfg& device_cfg() {
 // whole tiles per warp when the packer's LPT schedule is balanced (no reduction, no per-tile barriers)
 constexpr double kMaxSchedImbalance = 1.08;
 
+// How many CTAs should share a block of states (each taking a range of tiles)?  With p parts, floor(slots / p) blocks
+// are in flight at a time and every pass takes 1 / p of a whole block's time: minimise ceil(nblocks / floor(slots / p)) / p.
+// p > 1 only if it saves at least 10 % (one CTA per block keeps all CTAs on the same part of the operator in L2).
+int choose_parts(int64_t nblocks, int64_t slots, int max_parts) {
+  if (nblocks <= 0 || slots <= 0 || nblocks >= 2 * slots || getenv("CA_WIN_NO_SPLIT")) return 1;
+  auto cost = [&](int p) {
+    const int64_t in_flight = slots / p;
+    return in_flight < 1 ? 1e30 : (double)((nblocks + in_flight - 1) / in_flight) / p;
+  };
+  double lowest = cost(1);
+  for (int p = 2; p <= max_parts; ++p) lowest = std::min(lowest, cost(p));
+  if (lowest > 0.9 * cost(1)) return 1;
+  for (int p = 2; p <= max_parts; ++p)  // the fewest parts within 6 % of the best: every part has its fixed costs
+    if (cost(p) <= 1.06 * lowest) return p;
+  return 1;
+}
+
 template <int MT, int MODE, bool FACT = false>
 void launch_warptile(const DevicePack& op, const double* dX, const double* dY, int64_t nstates, int64_t ldx,
                      double* dOUT, int64_t ldo, cudaStream_t stream) {
@@ -164,8 +181,8 @@ void launch_one(const DevicePack& op, const double* dX, const double* dY, int64_
   // machine -- 1,000 states of the 307-mode model otherwise take as long as 9,472
   WindowParts tp;
   tp.n = 1;
-  if (per_sm >= 1 && nblocks * 2 <= slots && op.ntiles >= 2 && !getenv("CA_WIN_NO_SPLIT"))
-    tp.n = (int)std::min<int64_t>({slots / nblocks, (int64_t)WindowParts::kMax, (int64_t)op.ntiles});
+  if (per_sm >= 1 && nblocks * 2 <= slots && op.ntiles >= 2)
+    tp.n = choose_parts(nblocks, slots, std::min<int>(WindowParts::kMax, op.ntiles));
   tp.first[0] = 0;
   tp.first[tp.n] = op.ntiles;
   if (tp.n > 1) {
@@ -258,12 +275,9 @@ void launch_windowed_nt(const DevicePack& op, const double* dX, const double* dY
   const int64_t slots = (int64_t)device_cfg().sms * per_sm;
   // ensembles too small to give every SM a block of states: the tiles (independent output rows) are split into `parts`
   // ranges of about equal DMMA count and every block of states is walked by `parts` CTAs, one range each
+  // ensembles that do not fill whole passes of the machine: see choose_parts
   WindowParts wp;
-  wp.n = 1;
-  if (nblocks < slots && !getenv("CA_WIN_NO_SPLIT")) {
-    const int ntl = (int)op.tile_first_window.size() - 1;
-    wp.n = (int)std::max<int64_t>(1, std::min<int64_t>({slots / nblocks, (int64_t)WindowParts::kMax, (int64_t)ntl}));
-  }
+  wp.n = choose_parts(nblocks, slots, std::min<int>(WindowParts::kMax, (int)op.tile_first_window.size() - 1));
   wp.first[0] = 0;
   wp.first[wp.n] = op.nwin;
   if (wp.n > 1) {
@@ -276,7 +290,7 @@ void launch_windowed_nt(const DevicePack& op, const double* dX, const double* dY
       wp.first[p] = op.tile_first_window[(size_t)t];
     }
   }
-  const int grid = (int)std::min<int64_t>(nblocks, slots / wp.n) * wp.n;
+  const int grid = (int)std::min<int64_t>(nblocks, std::max<int64_t>(slots / wp.n, 1)) * wp.n;
   kern<<<grid, threads, smem, stream>>>(op.windows.ptr, wp, op.nwin_nt3, op.nwin_nt2, op.modes.ptr, op.pairs_windowed(),
                                         op.vals.ptr, op.rows.ptr, wmax, op.nin - 1, dX, dY, nstates, ldx, dOUT, ldo);
   CA_CUDA(cudaGetLastError());
