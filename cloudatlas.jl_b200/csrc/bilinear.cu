@@ -262,7 +262,7 @@ namespace {
 template <int MODE, bool NT3>
 void launch_windowed_nt(const DevicePack& op, const double* dX, const double* dY, int64_t nstates, int64_t ldx,
                         double* dOUT, int64_t ldo, cudaStream_t stream) {
-  auto kern = bilinear_windowed_kernel<MODE, NT3>;
+  auto kern = bilinear_windowed_kernel<MODE, NT3, false>;  // (same resources as the SPLIT instantiation)
   const int wmax = std::max(op.max_window_modes, 1);
   const size_t smem = windowed_smem_bytes<MODE, NT3>(wmax);
   CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -291,8 +291,15 @@ void launch_windowed_nt(const DevicePack& op, const double* dX, const double* dY
     }
   }
   const int grid = (int)std::min<int64_t>(nblocks, std::max<int64_t>(slots / wp.n, 1)) * wp.n;
-  kern<<<grid, threads, smem, stream>>>(op.windows.ptr, wp, op.nwin_nt3, op.nwin_nt2, op.modes.ptr, op.pairs_windowed(),
-                                        op.vals.ptr, op.rows.ptr, wmax, op.nin - 1, dX, dY, nstates, ldx, dOUT, ldo);
+  if (wp.n > 1) {
+    auto kern_split = bilinear_windowed_kernel<MODE, NT3, true>;
+    CA_CUDA(cudaFuncSetAttribute(kern_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern_split<<<grid, threads, smem, stream>>>(op.windows.ptr, wp, op.nwin_nt3, op.nwin_nt2, op.modes.ptr, op.pairs_windowed(),
+                                                op.vals.ptr, op.rows.ptr, wmax, op.nin - 1, dX, dY, nstates, ldx, dOUT, ldo);
+  } else {
+    kern<<<grid, threads, smem, stream>>>(op.windows.ptr, wp, op.nwin_nt3, op.nwin_nt2, op.modes.ptr, op.pairs_windowed(),
+                                          op.vals.ptr, op.rows.ptr, wmax, op.nin - 1, dX, dY, nstates, ldx, dOUT, ldo);
+  }
   CA_CUDA(cudaGetLastError());
   count_launch();
 }

@@ -997,7 +997,10 @@ __device__ __forceinline__ void run_windows(const WindowDesc* __restrict__ windo
 
 // NT3: the pack has tiles of three n-tiles (CA_NT3); a separate instantiation, so that the register allocation of the
 // two-n-tile kernel does not change with it
-template <int MODE, bool NT3>
+// SPLIT: several CTAs share a block of states (parts.n > 1).  A separate instantiation, so that the one-CTA-per-block
+// code of the large ensembles stays exactly what it was (with run-time ranges ptxas arranged the one-n-tile k-steps
+// of the three-n-tile variant in blocks of one again: +4 % at m = 2962).
+template <int MODE, bool NT3, bool SPLIT>
 __global__ void __launch_bounds__(WinCfg<MODE, NT3>::THREADS, 1)
 bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, const WindowParts parts, int nwin_nt3, int nwin_nt2,
                          const int32_t* __restrict__ modes, const uint32_t* __restrict__ pairs,
@@ -1010,8 +1013,9 @@ bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, const WindowPar
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // this CTA's range of windows (whole tiles): CTAs blockIdx.x % parts.n of the same block of states share the tiles
-  const int part = blockIdx.x % parts.n;
-  const int w0 = parts.first[part], w1 = parts.first[part + 1];
+  const int nparts = SPLIT ? parts.n : 1;
+  const int part = SPLIT ? blockIdx.x % nparts : 0;
+  const int w0 = SPLIT ? parts.first[part] : 0, w1 = SPLIT ? parts.first[part + 1] : parts.first[1];
   if (w1 <= w0) return;
   const size_t team_doubles = windowed_team_bytes<MODE, NT3>(wmax) / sizeof(double);
   if (tid == 0) {
@@ -1028,7 +1032,7 @@ bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, const WindowPar
   const int team = producer ? (warp - TEAMS * NWC) / NWP : warp / NWC;
   const WinSmem S = carve_window_smem<MODE, NT3>(smem + team * team_doubles, wmax);
   if (producer) {
-    window_producer<MODE, NT3>(windows, w0, w1, parts.n, modes, pairs, S, one_mode, X, Y, nstates, ldx, team,
+    window_producer<MODE, NT3>(windows, w0, w1, nparts, modes, pairs, S, one_mode, X, Y, nstates, ldx, team,
                                tid - (TEAMS * NWC + team * NWP) * 32);
     return;
   }
@@ -1036,13 +1040,20 @@ bilinear_windowed_kernel(const WindowDesc* __restrict__ windows, const WindowPar
   const int64_t nblocks = (nstates + ROW - 1) / ROW;
   RingPos pos;
   const int c3 = nwin_nt3, c2 = nwin_nt3 + nwin_nt2;  // class boundaries in the window list: [0, c3) three n-tiles, [c3, c2) two, rest one
-  for (int64_t blk = (int64_t)(blockIdx.x / parts.n) * TEAMS + team; blk < nblocks; blk += (int64_t)(gridDim.x / parts.n) * TEAMS) {
+  for (int64_t blk = (int64_t)(blockIdx.x / nparts) * TEAMS + team; blk < nblocks; blk += (int64_t)(gridDim.x / nparts) * TEAMS) {
     const int64_t s0 = blk * ROW;
-    if constexpr (NT3)
-      run_windows<3, MODE, NT3>(windows, w0, min(w1, c3), vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo, 1 + team);
-    run_windows<2, MODE, NT3>(windows, max(w0, c3), min(w1, c2), vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo,
-                              1 + team);
-    run_windows<1, MODE, NT3>(windows, max(w0, c2), w1, vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo, 1 + team);
+    if constexpr (SPLIT) {
+      if constexpr (NT3)
+        run_windows<3, MODE, NT3>(windows, w0, min(w1, c3), vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo, 1 + team);
+      run_windows<2, MODE, NT3>(windows, max(w0, c3), min(w1, c2), vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo,
+                                1 + team);
+      run_windows<1, MODE, NT3>(windows, max(w0, c2), w1, vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo, 1 + team);
+    } else {
+      if constexpr (NT3)
+        run_windows<3, MODE, NT3>(windows, 0, c3, vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo, 1 + team);
+      run_windows<2, MODE, NT3>(windows, c3, c2, vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo, 1 + team);
+      run_windows<1, MODE, NT3>(windows, c2, w1, vals, rows, S, pos, cwarp, lane, s0, nstates, OUT, ldo, 1 + team);
+    }
   }
 }
 
