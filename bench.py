@@ -406,6 +406,7 @@ def large_basis_case(ca, H, jkl, world, rank, max_over_ranks, barrier, dmma_peak
         passes.append({"assembly_wall_seconds": max_over_ranks(t1 - t0), "slab_device_seconds": max_over_ranks(st["device_seconds"]),
                        "all_gather_seconds": max_over_ranks(st["gather_seconds"]), "all_gather_bytes": st["gather_bytes"],
                        "model_create_seconds": max_over_ranks(bi["seconds"]["total"]),
+                       "model_create_phases_rank0": {k: round(v, 4) for k, v in bi["seconds"].items()},
                        "time_to_first_eval_seconds": max_over_ranks(t2 - t0)})
         nnz = slab.nnz
         if rep == 0:
