@@ -295,7 +295,7 @@ def run_b200(args):
         "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
         "peak_source": "measured in this run (ca_measure_fp64_peak: DMMA loop); MEASURED_PEAKS.json has no FP64 entry",
         "dfma_peak": dfma_peak, "traffic": traffic,
-        "traffic_source": "stored ncu --set full capture (profiles/ncu_traffic.json, profiles/r01_rhs307_ncu_raw.csv): "
+        "traffic_source": "stored ncu --set full capture (profiles/ncu_traffic.json, profiles/r02_rhs307_final_ncu_raw.csv): "
                           "dram__bytes_read.sum + dram__bytes_write.sum of one launch scaled to this launch's states; not re-measured in this run",
         "kernel": KERNEL_NAMES.get(model.kernel_path(n)[0], model.kernel_path(n)[0]), "kernel_ms": kernel_ms,
         "algorithmic_flops_per_state": flops_state, "executed_fma_per_state": info["padded_fma_per_state"],
