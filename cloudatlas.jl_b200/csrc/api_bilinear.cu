@@ -264,6 +264,13 @@ int32_t ca_bilinear_jacobian(ca_bilinear* h, const double* x, double* DN) {
 
 }  // extern "C"
 
+extern "C" int32_t ca_selftest_choose_parts(int64_t nblocks, int64_t slots, int32_t max_parts, int32_t* parts) {
+  return guarded([&] {
+    if (!parts) fail(CA_ERR_INVALID, "ca_selftest_choose_parts: parts is null");
+    *parts = choose_parts(nblocks, slots, max_parts);
+  });
+}
+
 extern "C" int32_t ca_selftest_pack_digest(const int64_t* ijk, const double* val, int64_t nnz, int64_t m,
                                            int32_t symmetric, int32_t window_modes, uint64_t* digest8) {
   return guarded([&] {

@@ -99,6 +99,23 @@ const uint32_t* DevicePack::pairs_windowed() const {
   return pairs_win.ptr;
 }
 
+// How many CTAs should share a block of states (each taking a range of tiles)?  With p parts, floor(slots / p) blocks
+// are in flight at a time and every pass takes 1 / p of a whole block's time: minimise ceil(nblocks / floor(slots / p)) / p.
+// p > 1 only if it saves at least 10 % (one CTA per block keeps all CTAs on the same part of the operator in L2).
+int choose_parts(int64_t nblocks, int64_t slots, int max_parts) {
+  if (nblocks <= 0 || slots <= 0 || nblocks >= 2 * slots || getenv("CA_WIN_NO_SPLIT")) return 1;
+  auto cost = [&](int p) {
+    const int64_t in_flight = slots / p;
+    return in_flight < 1 ? 1e30 : (double)((nblocks + in_flight - 1) / in_flight) / p;
+  };
+  double lowest = cost(1);
+  for (int p = 2; p <= max_parts; ++p) lowest = std::min(lowest, cost(p));
+  if (lowest > 0.9 * cost(1)) return 1;
+  for (int p = 2; p <= max_parts; ++p)  // the fewest parts within 6 % of the best: every part has its fixed costs
+    if (cost(p) <= 1.06 * lowest) return p;
+  return 1;
+}
+
 namespace {
 
 struct LaunchCfg {
@@ -124,23 +141,6 @@ const LaunchCfg& device_cfg() {
 
 // whole tiles per warp when the packer's LPT schedule is balanced (no reduction, no per-tile barriers)
 constexpr double kMaxSchedImbalance = 1.08;
-
-// How many CTAs should share a block of states (each taking a range of tiles)?  With p parts, floor(slots / p) blocks
-// are in flight at a time and every pass takes 1 / p of a whole block's time: minimise ceil(nblocks / floor(slots / p)) / p.
-// p > 1 only if it saves at least 10 % (one CTA per block keeps all CTAs on the same part of the operator in L2).
-int choose_parts(int64_t nblocks, int64_t slots, int max_parts) {
-  if (nblocks <= 0 || slots <= 0 || nblocks >= 2 * slots || getenv("CA_WIN_NO_SPLIT")) return 1;
-  auto cost = [&](int p) {
-    const int64_t in_flight = slots / p;
-    return in_flight < 1 ? 1e30 : (double)((nblocks + in_flight - 1) / in_flight) / p;
-  };
-  double lowest = cost(1);
-  for (int p = 2; p <= max_parts; ++p) lowest = std::min(lowest, cost(p));
-  if (lowest > 0.9 * cost(1)) return 1;
-  for (int p = 2; p <= max_parts; ++p)  // the fewest parts within 6 % of the best: every part has its fixed costs
-    if (cost(p) <= 1.06 * lowest) return p;
-  return 1;
-}
 
 template <int MT, int MODE, bool FACT = false>
 void launch_warptile(const DevicePack& op, const double* dX, const double* dY, int64_t nstates, int64_t ldx,

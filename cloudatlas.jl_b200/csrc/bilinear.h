@@ -69,6 +69,7 @@ int nt_max_for(int window_modes);
 bool batched_fits(const DevicePack& op, int mode);
 // which DMMA ensemble kernel launch_batched picks: 0 whole tiles per warp, 3 k-steps split across warps, 4 windowed
 int batched_variant(const DevicePack& op, int64_t nstates = 0);
+int choose_parts(int64_t nblocks, int64_t slots, int max_parts);
 constexpr int64_t kStreamMaxStates = 16;  // at or below this many states the streaming kernel is used
 
 // Row-chunked CSR for the few-state ("streaming") evaluation: the operator is read once from HBM per pass

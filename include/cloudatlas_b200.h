@@ -382,6 +382,11 @@ int32_t ca_selftest_lu_solve(double* A, int64_t m, double* b, int32_t* singular)
 int32_t ca_selftest_small_kernel(const int64_t* ijk, const double* val, int64_t nnz, int64_t m,
                                  int64_t* cubin_bytes, int32_t* threads, int32_t* stages, int64_t* source_bytes);
 
+/* How many CTAs share a block of 32 states in the ensemble kernels (each taking a range of tiles) when the ensemble
+ * has `nblocks` blocks and the machine `slots` CTA slots: 1 for ensembles that fill whole passes, more for small ones
+ * (csrc/bilinear.cu: choose_parts).  Pure host logic, no device needed. */
+int32_t ca_selftest_choose_parts(int64_t nblocks, int64_t slots, int32_t max_parts, int32_t* parts);
+
 #ifdef __cplusplus
 }
 #endif

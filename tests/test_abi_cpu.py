@@ -186,3 +186,29 @@ def test_pack_fill_at_307(nagata_H):
     s128 = pack_stats(ijk, val, 307, 1, 128)
     assert s128["mismatches"] == 0 and s128["max_window_modes"] <= 128
     assert s128["nwindows"] > sw["ntiles"] and s128["padded_fma"] < 1.05 * st["padded_fma"]
+
+
+def test_parts_per_block_of_states():
+    """csrc/bilinear.cu choose_parts: ensembles that fill whole passes of the machine keep one CTA per block of 32
+    states; smaller ones divide the tiles among several CTAs per block (never more than allowed, never more than the
+    slots), and the launch never exceeds the slots."""
+    import ctypes as C
+    from cloudatlas_b200._lib import lib, check
+    lib.ca_selftest_choose_parts.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int32)]
+    lib.ca_selftest_choose_parts.restype = C.c_int32
+
+    def parts(nblocks, slots, mx=32):
+        p = C.c_int32(0)
+        check(lib.ca_selftest_choose_parts(nblocks, slots, mx, C.byref(p)))
+        return p.value
+
+    for nblocks, slots in ((148, 148), (296, 148), (296, 296), (592, 148), (31250, 296), (0, 148)):
+        assert parts(nblocks, slots) == 1                      # whole passes (the bench sizes), or nothing to do
+    assert parts(1, 148) >= 30 and parts(1, 148, 5) == 5         # one block: (nearly) as many parts as allowed
+    assert parts(16, 148) == 9 and parts(47, 148) == 3 and parts(93, 148) == 3
+    for slots in (148, 296):
+        for nblocks in range(1, 2 * slots):
+            p = parts(nblocks, slots)
+            assert 1 <= p <= 32 and (p == 1 or p * min(nblocks, slots // p) <= slots)
+            if nblocks <= slots // 2:
+                assert p >= 2                                    # small ensembles are always split
