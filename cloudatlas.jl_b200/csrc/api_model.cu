@@ -403,6 +403,8 @@ static void build_model_on_host(ca_model* hmodel, const double* B, const double*
     h->hL1 = hL1;
     h->hL2 = hL2;
     h->hB.assign(B, B + (size_t)m * m);
+    h->B_on_device = false;
+    h->dB.release();
     h->hA1.assign(A1, A1 + (size_t)m * m);
     h->hA2.assign(A2, A2 + (size_t)m * m);
     h->ncoo.resize((size_t)nnz);
@@ -903,10 +905,11 @@ extern "C" int32_t ca_model_cnab2_batched_dev(ca_model* h, const double* dX0, in
       CA_CUDA(cudaDeviceSynchronize());
       const size_t mm = (size_t)m * m;
       std::vector<double> lhs(mm), rhs(mm);
+      const std::vector<double>& hB = h->host_B();
       for (size_t e = 0; e < mm; ++e) {
         const double a = h->hA1[e] + (1.0 / R) * h->hA2[e];
-        lhs[e] = h->hB[e] - (dt / 2) * a;
-        rhs[e] = h->hB[e] + (dt / 2) * a;
+        lhs[e] = hB[e] - (dt / 2) * a;
+        rhs[e] = hB[e] + (dt / 2) * a;
       }
       DeviceBuffer<double> dlhs, drhs;
       DeviceBuffer<int32_t> piv, flag;

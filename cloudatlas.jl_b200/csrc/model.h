@@ -57,7 +57,18 @@ struct ca_model {
     }
     return ncoo;
   }
-  // fills hB, hA1, hA2, hL1, hL2 (column-major)
+  // B (unfolded, column-major) on the host: the device build keeps it on the device until cnab2 asks for it
+  ca::DeviceBuffer<double> dB;
+  bool B_on_device = false;
+  const std::vector<double>& host_B() {
+    if (B_on_device) {
+      hB.resize((size_t)m * m);
+      CA_CUDA(cudaMemcpy(hB.data(), dB.ptr, hB.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      B_on_device = false;
+    }
+    return hB;
+  }
+  // fills hA1, hA2, hL1, hL2 (column-major)
   void host_linear() {
     if (!linear_on_device) return;
     const size_t mm = (size_t)m * m;

@@ -611,6 +611,34 @@ void FoldedDevice::to_host_terms(std::vector<Term>& out, int32_t m) const {
   });
 }
 
+// off-diagonal non-zeros of B (column-major m x m) as a list of (row, column); count may exceed cap (the caller checks)
+__global__ void __launch_bounds__(256)
+b_offdiag_kernel(const double* __restrict__ B, int m, int2* __restrict__ list, int32_t* __restrict__ count, int32_t cap) {
+  const int64_t n = (int64_t)m * m;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {  // (grid_for caps the grid)
+    const int i = (int)(e % m), j = (int)(e / m);
+    if (i != j && B[e] != 0.0) {
+      const int32_t pos = atomicAdd(count, 1);
+      if (pos < cap) list[pos] = make_int2(i, j);
+    }
+  }
+}
+
+// the diagonal blocks of B, row-major one after the other: out[off[b] + a g + c] = B[rows[a], rows[c]]
+__global__ void __launch_bounds__(256)
+b_gather_blocks_kernel(const double* __restrict__ B, int m, const int32_t* __restrict__ rows,
+                       const int32_t* __restrict__ row_off, const int64_t* __restrict__ off, int nb,
+                       double* __restrict__ out) {
+  const int b = blockIdx.x;
+  if (b >= nb) return;
+  const int r0 = row_off[b], g = row_off[b + 1] - r0;
+  double* o = out + off[b];
+  for (int e = threadIdx.x; e < g * g; e += blockDim.x) {
+    const int a = e / g, c = e % g;
+    o[e] = B[rows[r0 + a] + (int64_t)m * rows[r0 + c]];
+  }
+}
+
 }  // namespace ca
 
 // Builds *h from device-resident operators.  Returns false (nothing built) when the device build does not apply and
@@ -644,32 +672,46 @@ bool build_model_on_device(ca_model* h, const double* dB, const double* dA1, con
   }
   int32_t flags[4];
   CA_CUDA(cudaMemcpyAsync(flags, dflags.ptr, sizeof flags, cudaMemcpyDeviceToHost, st));
-  // ---- B to the host: blocks = connected components of its pattern, inverted there
-  h->hB.resize((size_t)m * m);
-  CA_CUDA(cudaMemcpyAsync(h->hB.data(), dB, (size_t)m * m * sizeof(double), cudaMemcpyDeviceToHost, st));
+  // ---- blocks of B = connected components of its pattern.  B stays on the device (a copy for cnab2, which needs it
+  // unfolded); only the list of its off-diagonal non-zeros and, afterwards, its diagonal blocks travel to the host,
+  // where the components are found (union-find) and the blocks inverted (round 2, first version: the whole of B was
+  // downloaded and scanned, 41 ms of the 0.18 s build at m = 2962)
+  h->dB.alloc((size_t)m * m);
+  CA_CUDA(cudaMemcpyAsync(h->dB.ptr, dB, (size_t)m * m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  h->hB.clear();
+  h->B_on_device = true;
+  const int32_t cap = (int32_t)std::min<int64_t>((int64_t)m * (kMaxBlockRows - 1), (int64_t)1 << 30);
+  DeviceBuffer<int2> d_list;
+  DeviceBuffer<int32_t> d_count;
+  d_list.alloc((size_t)std::max(cap, 1));
+  d_count.alloc(1);
+  CA_CUDA(cudaMemsetAsync(d_count.ptr, 0, sizeof(int32_t), st));
+  b_offdiag_kernel<<<grid_for((int64_t)m * m), 256, 0, st>>>(dB, m, d_list.ptr, d_count.ptr, cap);
+  CA_CUDA(cudaGetLastError());
+  count_launch();
+  int32_t noff = 0;
+  CA_CUDA(cudaMemcpyAsync(&noff, d_count.ptr, sizeof noff, cudaMemcpyDeviceToHost, st));
   CA_CUDA(cudaStreamSynchronize(st));
   if (flags[0]) fail(CA_ERR_INVALID, "ca_model_create: an N entry has an index outside 1:%lld", (long long)m64);
   if (flags[1] || flags[2]) return false;
-  const double* B = h->hB.data();
+  if (noff > cap) return false;  // some block has more than kMaxBlockRows rows: host build
+  std::vector<int2> edges((size_t)noff);
+  if (noff) CA_CUDA(cudaMemcpyAsync(edges.data(), d_list.ptr, (size_t)noff * sizeof(int2), cudaMemcpyDeviceToHost, st));
+  CA_CUDA(cudaStreamSynchronize(st));
   std::vector<int> comp(m);
   std::iota(comp.begin(), comp.end(), 0);
   auto find = [&](int a) {
     while (comp[a] != a) a = comp[a] = comp[comp[a]];
     return a;
   };
-  for (int j = 0; j < m; ++j) {
-    const double* col = B + (size_t)m * j;
-    for (int i = 0; i < m; ++i)
-      if (i != j && col[i] != 0.0) {  // (i,j) and (j,i) are both visited: either direction links the two modes
-        const int a = find(i), b = find(j);
-        if (a != b) comp[std::max(a, b)] = std::min(a, b);
-      }
+  for (const int2& e : edges) {  // either direction links the two modes; the root of a component is its smallest mode
+    const int a = find(e.x), b = find(e.y);
+    if (a != b) comp[std::max(a, b)] = std::min(a, b);
   }
   std::map<int, std::vector<int>> blocks;
   for (int i = 0; i < m; ++i) blocks[find(i)].push_back(i);
   const int nb = (int)blocks.size();
   std::vector<int32_t> h_rows, h_row_off{0}, h_blk_of(m), h_pos_in(m);
-  std::vector<double> h_binv;
   std::vector<int64_t> h_binv_off{0};
   int gmax = 0;
   {
@@ -679,32 +721,43 @@ bool build_model_on_device(ca_model* h, const double* dB, const double* dA1, con
       const int g = (int)G.size();
       gmax = std::max(gmax, g);
       if (g > kMaxBlockRows) return false;
-      std::vector<double> Bg((size_t)g * g), Binv;
-      for (int a = 0; a < g; ++a)
-        for (int c = 0; c < g; ++c) Bg[(size_t)a * g + c] = B[G[a] + (size_t)m * G[c]];
-      if (!invert_block_rm(Bg, g, Binv)) fail(CA_ERR_INVALID, "ca_model_create: B is singular");
       for (int a = 0; a < g; ++a) {
         h_rows.push_back(G[a]);
         h_blk_of[G[a]] = b;
         h_pos_in[G[a]] = a;
       }
       h_row_off.push_back((int32_t)h_rows.size());
-      h_binv.insert(h_binv.end(), Binv.begin(), Binv.end());
-      h_binv_off.push_back((int64_t)h_binv.size());
+      h_binv_off.push_back(h_binv_off.back() + (int64_t)g * g);
       ++b;
     }
   }
-  const int64_t uwords = ((int64_t)m * m + 31) / 32, swords = ((int64_t)nin * nin + 31) / 32;
-  if ((int64_t)nb * swords * 4 > kMaxBitmapBytes) return false;
   DeviceBuffer<int32_t> d_rows, d_row_off, d_blk_of, d_pos_in;
   DeviceBuffer<double> d_binv;
   DeviceBuffer<int64_t> d_binv_off;
   d_rows.upload(h_rows.data(), h_rows.size(), st);
   d_row_off.upload(h_row_off.data(), h_row_off.size(), st);
+  d_binv_off.upload(h_binv_off.data(), h_binv_off.size(), st);
+  d_binv.alloc((size_t)std::max<int64_t>(h_binv_off.back(), 1));
+  b_gather_blocks_kernel<<<(unsigned)nb, 256, 0, st>>>(dB, m, d_rows.ptr, d_row_off.ptr, d_binv_off.ptr, nb, d_binv.ptr);
+  CA_CUDA(cudaGetLastError());
+  count_launch();
+  std::vector<double> h_binv((size_t)h_binv_off.back());
+  if (!h_binv.empty())
+    CA_CUDA(cudaMemcpyAsync(h_binv.data(), d_binv.ptr, h_binv.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CA_CUDA(cudaStreamSynchronize(st));
+  for (int b = 0; b < nb; ++b) {  // invert in place, block by block (row-major g x g)
+    const int g = h_row_off[(size_t)b + 1] - h_row_off[(size_t)b];
+    std::vector<double> Bg(h_binv.begin() + h_binv_off[(size_t)b], h_binv.begin() + h_binv_off[(size_t)b + 1]), Binv;
+    if (!invert_block_rm(Bg, g, Binv)) fail(CA_ERR_INVALID, "ca_model_create: B is singular");
+    std::copy(Binv.begin(), Binv.end(), h_binv.begin() + h_binv_off[(size_t)b]);
+  }
+  const int64_t uwords = ((int64_t)m * m + 31) / 32, swords = ((int64_t)nin * nin + 31) / 32;
+  if ((int64_t)nb * swords * 4 > kMaxBitmapBytes) return false;
   d_blk_of.upload(h_blk_of.data(), h_blk_of.size(), st);
   d_pos_in.upload(h_pos_in.data(), h_pos_in.size(), st);
-  d_binv.upload(h_binv.data(), h_binv.size(), st);
-  d_binv_off.upload(h_binv_off.data(), h_binv_off.size(), st);
+  if (!h_binv.empty())
+    CA_CUDA(cudaMemcpyAsync(d_binv.ptr, h_binv.data(), h_binv.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CA_CUDA(cudaStreamSynchronize(st));  // h_binv is a pageable local
   const BlockMap bm{d_blk_of.ptr, d_pos_in.ptr, d_row_off.ptr, d_rows.ptr, d_binv.ptr, d_binv_off.ptr};
   h->nblocks = nb;
   lap(S.blocks, t0);
