@@ -57,7 +57,8 @@ void eval_batched_host(const LaunchFn& launch, cudaStream_t streams[kStage], Dev
                        int64_t m_in, int64_t m_out, int64_t ld_host = -1 /* leading dimension of X and OUT; default nstates */);
 
 // Packing policy: operators whose two-vector state tile (x and y/v, 32 states) fits in shared memory use
-// whole-tile packing; larger ones are packed in windows of kWindowModes modes (128: two CTAs per SM still fit for one-vector evaluation).
+// whole-tile packing; larger ones are packed in windows of kWindowModes modes (128: two window slots per team fit for two teams
+// (one vector) or one team (two vectors) per SM, bilinear_kernels.cuh WinCfg).
 constexpr int kWindowModes = 128;
 int window_modes_for(int32_t m);
 // n-tiles (of 8 output rows) a tile may have: 2; windowed packs may take 3 (row clusters of 17-24 rows -- most of a
